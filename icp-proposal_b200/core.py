@@ -1,0 +1,319 @@
+"""Thin numpy-facing wrappers of the libicpcuda.so handles (one class per C-ABI handle type).
+
+Everything here is argument marshalling; all arithmetic happens in the CUDA library. There is no CPU
+fallback: constructing a Context without a CUDA device raises IcpCudaError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, dptr, f64, i32, iptr
+
+THETA0 = 10  # theta = [s, t3, rot3, c3, alpha_K]
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        check(self.lib.icp_ctx_create(int(device), C.byref(self.h)))
+        self.device = int(device)
+
+    def version(self):
+        buf = C.create_string_buffer(256)
+        self.lib.icp_version(self.h, buf, 256)
+        return buf.value.decode()
+
+    def synchronize(self):
+        check(self.lib.icp_ctx_synchronize(self.h), self.h)
+
+    def fp64_peak(self):
+        out = np.zeros(2)
+        check(self.lib.icp_debug_fp64_peak(self.h, dptr(out)), self.h)
+        return {"dfma_tflops": float(out[0]), "dmma_tflops": float(out[1])}
+
+    def philox(self, seed, chain, step, block):
+        out = (C.c_uint32 * 4)()
+        check(self.lib.icp_debug_philox(self.h, seed, chain, step, block, out), self.h)
+        return np.array(list(out), dtype=np.uint32)
+
+    def close(self):
+        if self.h:
+            self.lib.icp_ctx_destroy(self.h)
+            self.h = None
+
+
+class Model:
+    """StatisticalMeshModel: reference mesh + low-rank GP (mean deformation, basis U, variances)."""
+
+    def __init__(self, ctx: Context, ref, cells, basis, variance, mean_def=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.ref = f64(ref).reshape(-1, 3)
+        self.cells = i32(cells).reshape(-1, 3)
+        self.variance = f64(variance).reshape(-1)
+        self.N, self.T, self.K = len(self.ref), len(self.cells), len(self.variance)
+        self.basis = f64(basis)
+        if self.basis.shape != (3 * self.N, self.K):
+            raise ValueError(f"basis must be (3N, K) = {(3 * self.N, self.K)}, got {self.basis.shape}")
+        self.mean_def = None if mean_def is None else f64(mean_def).reshape(-1)
+        self.h = C.c_void_p()
+        check(self.lib.icp_model_create(ctx.h, self.N, self.T, self.K, dptr(self.ref),
+                                        None if self.mean_def is None else dptr(self.mean_def), dptr(self.basis),
+                                        dptr(self.variance), iptr(self.cells), C.byref(self.h)), ctx.h)
+
+    @property
+    def rank(self):
+        return self.K
+
+    def theta(self, alpha=None, translation=(0, 0, 0), rotation=(0, 0, 0), center=None, scale=1.0):
+        """Packs ModelFittingParameters.allParameters (ModelFittingParameters.scala:64)."""
+        th = np.zeros(self.K + THETA0)
+        th[0] = scale
+        th[1:4] = translation
+        th[4:7] = rotation
+        th[7:10] = self.ref.mean(0) if center is None else center
+        if alpha is not None:
+            th[10:] = alpha
+        return th
+
+    def _theta(self, theta):
+        th = f64(theta).reshape(-1, self.K + THETA0)
+        return th, len(th)
+
+    def reconstruct(self, theta):
+        th, c = self._theta(theta)
+        out = np.empty((c, self.N, 3))
+        check(self.lib.icp_reconstruct(self.h, c, dptr(th), dptr(out)), self.ctx.h)
+        return out
+
+    def vertex_normals(self, theta):
+        th, c = self._theta(theta)
+        out = np.empty((c, self.N, 3))
+        check(self.lib.icp_vertex_normals(self.h, c, dptr(th), dptr(out)), self.ctx.h)
+        return out
+
+    def closest_point_surface(self, theta, q):
+        th, c = self._theta(theta)
+        q = f64(q).reshape(-1, 3)
+        n = len(q)
+        tri = np.empty((c, n), np.int32); feat = np.empty((c, n), np.int32); cp = np.empty((c, n, 3)); d2 = np.empty((c, n))
+        check(self.lib.icp_model_closest_point_surface(self.h, c, dptr(th), n, dptr(q), iptr(tri), iptr(feat), dptr(cp),
+                                                       dptr(d2)), self.ctx.h)
+        return tri, feat, cp, d2
+
+    def closest_vertex(self, theta, q):
+        th, c = self._theta(theta)
+        q = f64(q).reshape(-1, 3)
+        n = len(q)
+        ids = np.empty((c, n), np.int32); d2 = np.empty((c, n))
+        check(self.lib.icp_model_closest_vertex(self.h, c, dptr(th), n, dptr(q), iptr(ids), dptr(d2)), self.ctx.h)
+        return ids, d2
+
+    def boundary_flags(self):
+        f = np.zeros(self.N, np.uint8)
+        check(self.lib.icp_model_boundary_flags(self.h, f.ctypes.data_as(_lib._bp)))
+        return f.astype(bool)
+
+    def prior(self, theta):
+        th, c = self._theta(theta)
+        out = np.empty(c)
+        check(self.lib.icp_eval_prior(self.h, c, dptr(th), dptr(out)), self.ctx.h)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.icp_model_destroy(self.h)
+            self.h = None
+
+
+class Target:
+    """TriangleMesh3D with its device query structures."""
+
+    def __init__(self, ctx: Context, verts, cells):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.verts = f64(verts).reshape(-1, 3)
+        self.cells = i32(cells).reshape(-1, 3)
+        self.h = C.c_void_p()
+        check(self.lib.icp_target_create(ctx.h, len(self.verts), len(self.cells), dptr(self.verts), iptr(self.cells),
+                                         C.byref(self.h)), ctx.h)
+
+    def closest_point_surface(self, q):
+        q = f64(q).reshape(-1, 3)
+        n = len(q)
+        tri = np.empty(n, np.int32); feat = np.empty(n, np.int32); cp = np.empty((n, 3)); d2 = np.empty(n)
+        check(self.lib.icp_closest_point_surface(self.h, n, dptr(q), iptr(tri), iptr(feat), dptr(cp), dptr(d2)), self.ctx.h)
+        return tri, feat, cp, d2
+
+    def closest_vertex(self, q):
+        q = f64(q).reshape(-1, 3)
+        n = len(q)
+        ids = np.empty(n, np.int32); d2 = np.empty(n)
+        check(self.lib.icp_closest_vertex(self.h, n, dptr(q), iptr(ids), dptr(d2)), self.ctx.h)
+        return ids, d2
+
+    def boundary_flags(self):
+        f = np.zeros(len(self.verts), np.uint8)
+        check(self.lib.icp_target_boundary_flags(self.h, f.ctypes.data_as(_lib._bp)))
+        return f.astype(bool)
+
+    def close(self):
+        if self.h:
+            self.lib.icp_target_destroy(self.h)
+            self.h = None
+
+
+class IcpProposal:
+    """Device side of NonRigidIcpProposal (api/sampling/proposals/NonRigidIcpProposal.scala)."""
+
+    def __init__(self, model: Model, target: Target, step_length, tangential_noise, noise_along_normal, direction,
+                 boundary_aware, model_point_ids, target_points):
+        self.model, self.target, self.lib, self.ctx = model, target, model.lib, model.ctx
+        self.ids = i32(np.asarray(model_point_ids).reshape(-1))
+        self.tp = f64(np.asarray(target_points, dtype=np.float64).reshape(-1, 3))
+        self.params = _lib.ProposalParams(step_length, tangential_noise, noise_along_normal, int(direction), int(boundary_aware))
+        self.h = C.c_void_p()
+        check(self.lib.icp_proposal_create(model.h, target.h, C.byref(self.params), iptr(self.ids), len(self.ids),
+                                           dptr(self.tp), len(self.tp), C.byref(self.h)), self.ctx.h)
+
+    def posterior(self, theta, want_M=True):
+        th, c = self.model._theta(theta)
+        K = self.model.K
+        mu = np.empty((c, K)); M = np.empty((c, K, K)) if want_M else None; n = np.empty(c, np.int32)
+        check(self.lib.icp_posterior(self.h, c, dptr(th), dptr(mu), None if M is None else dptr(M), iptr(n)), self.ctx.h)
+        return mu, M, n
+
+    def propose(self, theta, z):
+        th, c = self.model._theta(theta)
+        z = f64(z).reshape(c, self.model.K)
+        out = np.empty_like(th)
+        check(self.lib.icp_propose(self.h, c, dptr(th), dptr(z), dptr(out)), self.ctx.h)
+        return out
+
+    def log_transition(self, frm, to):
+        f, c = self.model._theta(frm)
+        t, c2 = self.model._theta(to)
+        assert c == c2
+        out = np.empty(c)
+        check(self.lib.icp_log_transition(self.h, c, dptr(f), dptr(t), dptr(out)), self.ctx.h)
+        return out
+
+    def clear_cache(self):
+        check(self.lib.icp_proposal_clear_cache(self.h), self.ctx.h)
+
+    def close(self):
+        if self.h:
+            self.lib.icp_proposal_destroy(self.h)
+            self.h = None
+
+
+def std_icp_iteration(model: Model, target: Target, direction, model_point_ids, target_points, sigma2, step_length, alpha):
+    ids = i32(np.asarray(model_point_ids).reshape(-1))
+    tp = f64(np.asarray(target_points, dtype=np.float64).reshape(-1, 3))
+    a = f64(alpha).reshape(-1, model.K)
+    out = np.empty_like(a)
+    check(model.lib.icp_std_icp_iteration(model.h, target.h, int(direction), iptr(ids), len(ids), dptr(tp), len(tp),
+                                          float(sigma2), float(step_length), len(a), dptr(a), dptr(out)), model.ctx.h)
+    return out
+
+
+class Evaluator:
+    """Device side of the DistributionEvaluators (api/sampling/evaluators/*.scala)."""
+
+    def __init__(self, model: Model, target: Target, kind, mode=_lib.MODEL_TO_TARGET, use_prior=True, p0=0.0, p1=1.0,
+                 p2=1.0, model_point_ids=(), target_points=()):
+        self.model, self.target, self.lib, self.ctx = model, target, model.lib, model.ctx
+        self.ids = i32(np.asarray(model_point_ids).reshape(-1))
+        self.tp = f64(np.asarray(target_points, dtype=np.float64).reshape(-1, 3))
+        self.params = _lib.EvaluatorParams(int(kind), int(mode), int(bool(use_prior)), 0, p0, p1, p2)
+        self.h = C.c_void_p()
+        check(self.lib.icp_evaluator_create(model.h, target.h, C.byref(self.params), iptr(self.ids), len(self.ids),
+                                            dptr(self.tp), len(self.tp), C.byref(self.h)), self.ctx.h)
+
+    def log_value(self, theta, with_status=False):
+        """-> (C, 3) array of {product, prior, distance} log-values."""
+        th, c = self.model._theta(theta)
+        out = np.empty((c, 3)); st = np.zeros(c, np.int32)
+        check(self.lib.icp_eval_log_value(self.h, c, dptr(th), dptr(out), iptr(st)), self.ctx.h)
+        return (out, st) if with_status else out
+
+    def close(self):
+        if self.h:
+            self.lib.icp_evaluator_destroy(self.h)
+            self.h = None
+
+
+def registration_metrics(model: Model, target: Target, theta):
+    th, c = model._theta(theta)
+    out = np.empty((c, 4))
+    check(model.lib.icp_registration_metrics(model.h, target.h, c, dptr(th), dptr(out)), model.ctx.h)
+    return out
+
+
+class Chain:
+    """Fused Metropolis-Hastings runner (Scalismo MetropolisHastings + MixtureProposal on the device)."""
+
+    def __init__(self, model: Model, target: Target, components, evaluator: Evaluator, max_chains):
+        """components: list of dict(kind, weight, proposal=IcpProposal|None, sd=0, axis=0, name=...)."""
+        self.model, self.target, self.evaluator, self.lib, self.ctx = model, target, evaluator, model.lib, model.ctx
+        self.components = list(components)
+        arr = (_lib.Component * len(components))()
+        for i, c in enumerate(components):
+            arr[i].kind = int(c["kind"]); arr[i].axis = int(c.get("axis", 0)); arr[i].weight = float(c["weight"])
+            arr[i].sd = float(c.get("sd", 0.0))
+            arr[i].proposal = c["proposal"].h if c.get("proposal") is not None else None
+        self._arr = arr
+        self.max_chains = int(max_chains)
+        self.h = C.c_void_p()
+        check(self.lib.icp_chain_create(model.h, target.h, arr, len(components), evaluator.h, self.max_chains,
+                                        C.byref(self.h)), self.ctx.h)
+
+    def run(self, theta0, n_steps, seed=1024, chain_id_offset=0, u_comp=None, z=None, u_acc=None, log_theta=True):
+        th, c = self.model._theta(theta0)
+        K, L = self.model.K, self.model.K + THETA0
+        io = _lib.ChainIO()
+        io.seed, io.chain_id_offset = int(seed), int(chain_id_offset)
+        keep = []
+        if u_comp is not None:
+            uc = f64(u_comp).reshape(n_steps, c); zz = f64(z).reshape(n_steps, c, K); ua = f64(u_acc).reshape(n_steps, c)
+            keep += [uc, zz, ua]
+            io.u_comp, io.z, io.u_acc = uc.ctypes.data, zz.ctypes.data, ua.ctypes.data
+        comp = np.empty((n_steps, c), np.int32); acc = np.empty((n_steps, c), np.uint8)
+        vals = np.empty((n_steps, c, 3)); final = np.empty((c, L)); nacc = np.zeros(c, np.int64)
+        io.log_component, io.log_accepted, io.log_values = comp.ctypes.data, acc.ctypes.data, vals.ctypes.data
+        thl = None
+        if log_theta:
+            thl = np.empty((n_steps, c, L))
+            io.log_theta = thl.ctypes.data
+        io.theta_final, io.n_accepted = final.ctypes.data, nacc.ctypes.data
+        check(self.lib.icp_chain_run(self.h, c, int(n_steps), dptr(th), C.byref(io)), self.ctx.h)
+        return dict(component=comp, accepted=acc.astype(bool), values=vals, theta=thl, theta_final=final, n_accepted=nacc)
+
+    def run_device(self, C_, n_steps, theta0_ptr, seed=1024, chain_id_offset=0, log_component=0, log_accepted=0,
+                   log_values=0, log_theta=0, theta_final=0, n_accepted=0, async_=False):
+        """All pointers are raw device addresses (e.g. torch.Tensor.data_ptr())."""
+        io = _lib.ChainIO()
+        io.seed, io.chain_id_offset = int(seed), int(chain_id_offset)
+        io.log_component, io.log_accepted, io.log_values = log_component or None, log_accepted or None, log_values or None
+        io.log_theta, io.theta_final, io.n_accepted = log_theta or None, theta_final or None, n_accepted or None
+        check(self.lib.icp_chain_run_device(self.h, int(C_), int(n_steps), theta0_ptr, C.byref(io), int(async_)), self.ctx.h)
+
+    def last_run_stats(self):
+        ms = C.c_double(0); n = C.c_int64(0)
+        check(self.lib.icp_chain_last_run_stats(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def profile(self, theta0, n_steps, seed=1024):
+        th, c = self.model._theta(theta0)
+        ms = np.zeros(_lib.N_STAGES); n = np.zeros(_lib.N_STAGES, np.int64)
+        check(self.lib.icp_chain_profile(self.h, c, int(n_steps), dptr(th), int(seed), dptr(ms), n.ctypes.data_as(_lib._lp)),
+              self.ctx.h)
+        names = [self.lib.icp_stage_name(i).decode() for i in range(_lib.N_STAGES)]
+        return {nm: {"ms": float(a), "launches": int(b)} for nm, a, b in zip(names, ms, n)}
+
+    def close(self):
+        if self.h:
+            self.lib.icp_chain_destroy(self.h)
+            self.h = None

@@ -1,0 +1,1078 @@
+// api.cu - C ABI entry points of libicpcuda.so (include/icpcuda.h): contexts, handles, primitives,
+// the batched proposal / evaluator calls and the pipelines they share with the chain runner.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "icp_internal.h"
+
+using namespace icp;
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_thread_err;
+
+namespace icp {
+
+void set_error(icp_ctx ctx, const std::string &msg) {
+    g_thread_err = msg;
+    if (ctx) ctx->err = msg;
+}
+
+CtxLock::CtxLock(icp_ctx c) : lk(c->mu) {
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
+}
+
+int32_t translate_exception(icp_ctx ctx) {
+    try {
+        throw;
+    } catch (const ArgError &e) {
+        set_error(ctx, "invalid argument: " + e.msg);
+        return ICP_ERR_INVALID_ARGUMENT;
+    } catch (const StatusError &e) {
+        set_error(ctx, e.msg);
+        return e.code;
+    } catch (const CudaError &e) {
+        set_error(ctx, std::string("CUDA error: ") + cudaGetErrorString(e.e) + " at " + e.file + ":" + std::to_string(e.line));
+        cudaGetLastError();
+        return e.e == cudaErrorMemoryAllocation ? ICP_ERR_OUT_OF_MEMORY : ICP_ERR_CUDA;
+    } catch (const std::bad_alloc &) {
+        set_error(ctx, "host allocation failed");
+        return ICP_ERR_OUT_OF_MEMORY;
+    } catch (const std::exception &e) {
+        set_error(ctx, std::string("internal error: ") + e.what());
+        return ICP_ERR_INVALID_ARGUMENT;
+    } catch (...) {
+        set_error(ctx, "unknown internal error");
+        return ICP_ERR_INVALID_ARGUMENT;
+    }
+}
+
+}  // namespace icp
+
+#define ICP_API_BEGIN(ctxexpr)      \
+    icp_ctx _ctx = (ctxexpr);       \
+    try {                           \
+        ICP_REQUIRE(_ctx != nullptr, "null handle"); \
+        CtxLock _lock(_ctx);
+#define ICP_API_END                         \
+        return ICP_OK;                      \
+    } catch (...) {                         \
+        return translate_exception(_ctx);   \
+    }
+
+static void sync_stream(icp_ctx ctx) { ICP_CUDA(cudaStreamSynchronize(ctx->stream)); }
+
+template <class T>
+static void download(T *h, const T *d, size_t n, cudaStream_t s) {
+    if (n && h) ICP_CUDA(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (1) context
+// ---------------------------------------------------------------------------------------------------
+extern "C" int32_t icp_ctx_create(int32_t device, icp_ctx *out) {
+    icp_ctx ctx = nullptr;
+    try {
+        ICP_REQUIRE(out != nullptr, "out is null");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
+        ICP_REQUIRE(device >= 0 && device < count, "no such CUDA device (libicpcuda has no CPU fallback)");
+        ICP_CUDA(cudaSetDevice(device));
+        ctx = new icp_ctx_s();
+        ctx->device = device;
+        cudaDeviceProp prop;
+        ICP_CUDA(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->device_name = prop.name;
+        ICP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        *out = ctx;
+        return ICP_OK;
+    } catch (...) {
+        int32_t rc = translate_exception(nullptr);
+        delete ctx;
+        return rc;
+    }
+}
+
+extern "C" int32_t icp_ctx_destroy(icp_ctx ctx) {
+    if (!ctx) return ICP_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+    return ICP_OK;
+}
+
+extern "C" int32_t icp_last_error(icp_ctx ctx, char *buf, size_t n) {
+    if (!buf || n == 0) return ICP_ERR_INVALID_ARGUMENT;
+    const std::string &s = ctx ? ctx->err : g_thread_err;
+    size_t k = std::min(n - 1, s.size());
+    memcpy(buf, s.data(), k);
+    buf[k] = 0;
+    return ICP_OK;
+}
+
+extern "C" int32_t icp_version(icp_ctx ctx, char *buf, size_t n) {
+    if (!buf || n == 0) return ICP_ERR_INVALID_ARGUMENT;
+    std::string s = "icpcuda 0.1 sm_100a";
+    if (ctx) s += " " + ctx->device_name + " (" + std::to_string(ctx->sm_count) + " SMs)";
+    size_t k = std::min(n - 1, s.size());
+    memcpy(buf, s.data(), k);
+    buf[k] = 0;
+    return ICP_OK;
+}
+
+extern "C" int32_t icp_ctx_synchronize(icp_ctx ctx) {
+    ICP_API_BEGIN(ctx)
+    sync_stream(ctx);
+    ICP_API_END
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side mesh tables (construction time only)
+// ---------------------------------------------------------------------------------------------------
+// Scalismo pointIsOnBoundary: vertex on an edge with exactly one incident triangle
+static std::vector<uint8_t> boundary_table(int nv, int nt, const int32_t *tris) {
+    std::vector<uint64_t> ek((size_t)3 * nt);
+    for (int t = 0; t < nt; t++)
+        for (int k = 0; k < 3; k++) {
+            uint64_t a = (uint64_t)tris[3 * t + k], b = (uint64_t)tris[3 * t + (k + 1) % 3];
+            ek[(size_t)3 * t + k] = a < b ? (a << 32) | b : (b << 32) | a;
+        }
+    std::sort(ek.begin(), ek.end());
+    std::vector<uint8_t> f((size_t)std::max(nv, 1), 0);
+    for (size_t i = 0; i < ek.size();) {
+        size_t j = i;
+        while (j < ek.size() && ek[j] == ek[i]) j++;
+        if (j - i == 1) {
+            f[ek[i] >> 32] = 1;
+            f[ek[i] & 0xffffffffu] = 1;
+        }
+        i = j;
+    }
+    return f;
+}
+
+static void check_mesh(int nv, int nt, const double *xyz, const int32_t *tris) {
+    ICP_REQUIRE(nv >= 1 && nt >= 1, "mesh needs at least one vertex and one triangle");
+    ICP_REQUIRE(xyz != nullptr && tris != nullptr, "mesh arrays are null");
+    for (size_t i = 0; i < (size_t)3 * nt; i++) ICP_REQUIRE(tris[i] >= 0 && tris[i] < nv, "triangle index out of range");
+    for (size_t i = 0; i < (size_t)3 * nv; i++) ICP_REQUIRE(std::isfinite(xyz[i]), "non-finite vertex coordinate");
+}
+
+static double max_abs(const double *x, size_t n) {
+    double m = 0;
+    for (size_t i = 0; i < n; i++) m = std::max(m, std::fabs(x[i]));
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (2) model
+// ---------------------------------------------------------------------------------------------------
+extern "C" int32_t icp_model_create(icp_ctx ctx, int32_t N, int32_t T, int32_t K, const double *ref_xyz,
+                                    const double *mean_def, const double *basis, const double *variance,
+                                    const int32_t *tris, icp_model *out) {
+    icp_model m = nullptr;
+    icp_ctx _ctx = ctx;
+    try {
+        ICP_REQUIRE(ctx != nullptr && out != nullptr, "null handle");
+        CtxLock lock(ctx);
+        ICP_REQUIRE(K >= 1 && K <= 160, "rank K must be in [1, 160]");
+        ICP_REQUIRE(basis != nullptr && variance != nullptr, "basis / variance are null");
+        check_mesh(N, T, ref_xyz, tris);
+        for (int j = 0; j < K; j++) ICP_REQUIRE(variance[j] >= 0 && std::isfinite(variance[j]), "variance must be finite and >= 0");
+        cudaStream_t s = ctx->stream;
+        m = new icp_model_s();
+        m->ctx = ctx; m->N = N; m->T = T; m->K = K; m->Kp = pad8(K);
+        const int Kp = m->Kp;
+        size_t n3 = (size_t)3 * N;
+        m->ref.upload(ref_xyz, n3, s);
+        std::vector<double> mean(n3, 0.0);
+        if (mean_def) std::copy(mean_def, mean_def + n3, mean.begin());
+        m->mean.upload(mean.data(), n3, s);
+        m->tris.upload(tris, (size_t)3 * T, s);
+        // adjacency (ascending triangle id per vertex) and boundary table
+        std::vector<int> off(N + 1, 0), adj((size_t)3 * T), fill(N, 0);
+        for (size_t i = 0; i < (size_t)3 * T; i++) off[tris[i] + 1]++;
+        for (int v = 0; v < N; v++) off[v + 1] += off[v];
+        for (int t = 0; t < T; t++)
+            for (int k = 0; k < 3; k++) { int v = tris[3 * t + k]; adj[off[v] + fill[v]++] = t; }
+        m->adj_off.upload(off.data(), off.size(), s);
+        m->adj.upload(adj.data(), adj.size(), s);
+        m->h_boundary = boundary_table(N, T, tris);
+        m->has_boundary = std::any_of(m->h_boundary.begin(), m->h_boundary.end(), [](uint8_t b) { return b != 0; });
+        m->boundary.upload(m->h_boundary.data(), m->h_boundary.size(), s);
+        // scaled basis
+        DevBuf<double> dU, dvar;
+        dU.upload(basis, n3 * K, s);
+        dvar.upload(variance, K, s);
+        m->Q.alloc(n3 * Kp);
+        m->QT.alloc(n3 * Kp);
+        launch_scale_basis((int)n3, K, Kp, dU.p, dvar.p, m->Q.p, m->QT.p, s);
+        // S = (G/eps + I)^-1 G/eps, eps = 1e-5 (model.coefficients): G on the device,
+        // the one-off K x K solve on the host
+        m->S.alloc((size_t)Kp * Kp);
+        DevBuf<double> dG;
+        dG.alloc((size_t)Kp * Kp);
+        ModelDev md = m->dev();
+        launch_gram(md, dG.p, s);
+        std::vector<double> G((size_t)Kp * Kp), A((size_t)K * K), S((size_t)Kp * Kp, 0.0);
+        download(G.data(), dG.p, G.size(), s);
+        sync_stream(ctx);
+        const double eps = 1e-5;
+        for (int i = 0; i < K; i++)
+            for (int j = 0; j < K; j++) A[(size_t)i * K + j] = G[(size_t)i * Kp + j] / eps + (i == j ? 1.0 : 0.0);
+        // Cholesky A = L L^T (host, double)
+        for (int j = 0; j < K; j++) {
+            double d = A[(size_t)j * K + j];
+            for (int k = 0; k < j; k++) d -= A[(size_t)j * K + k] * A[(size_t)j * K + k];
+            ICP_REQUIRE(d > 0.0, "Gram matrix of the basis is not positive definite");
+            d = std::sqrt(d);
+            A[(size_t)j * K + j] = d;
+            for (int i = j + 1; i < K; i++) {
+                double t = A[(size_t)i * K + j];
+                for (int k = 0; k < j; k++) t -= A[(size_t)i * K + k] * A[(size_t)j * K + k];
+                A[(size_t)i * K + j] = t / d;
+            }
+        }
+        std::vector<double> col(K);
+        for (int c = 0; c < K; c++) {  // solve A s = G[:, c] / eps
+            for (int i = 0; i < K; i++) {
+                double t = G[(size_t)i * Kp + c] / eps;
+                for (int k = 0; k < i; k++) t -= A[(size_t)i * K + k] * col[k];
+                col[i] = t / A[(size_t)i * K + i];
+            }
+            for (int i = K - 1; i >= 0; i--) {
+                double t = col[i];
+                for (int k = i + 1; k < K; k++) t -= A[(size_t)k * K + i] * col[k];
+                col[i] = t / A[(size_t)i * K + i];
+            }
+            for (int i = 0; i < K; i++) S[(size_t)i * Kp + c] = col[i];
+        }
+        for (int i = 0; i < K; i++)  // symmetrise the rounding noise (S is symmetric in exact arithmetic)
+            for (int j = 0; j < i; j++) {
+                double a = 0.5 * (S[(size_t)i * Kp + j] + S[(size_t)j * Kp + i]);
+                S[(size_t)i * Kp + j] = S[(size_t)j * Kp + i] = a;
+            }
+        for (int i = K; i < Kp; i++) S[(size_t)i * Kp + i] = 1.0;
+        m->S.upload(S.data(), S.size(), s);
+        // query structures over the model mesh: topology from the reference, boxes refit per sample
+        m->scale = std::max(max_abs(ref_xyz, n3) * 2.0, 1e-3);
+        bvh_build(m->tri_bvh, 0, T, m->ref.p, m->tris.p, m->scale, s);
+        bvh_build(m->vert_bvh, 1, N, m->ref.p, nullptr, m->scale, s);
+        sync_stream(ctx);
+        *out = m;
+        return ICP_OK;
+    } catch (...) {
+        int32_t rc = translate_exception(_ctx);
+        delete m;
+        return rc;
+    }
+}
+
+extern "C" int32_t icp_model_destroy(icp_model m) {
+    if (!m) return ICP_OK;
+    icp_ctx _ctx = m->ctx;
+    try {
+        CtxLock lock(_ctx);
+        sync_stream(_ctx);
+        delete m;
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+extern "C" int32_t icp_model_rank(icp_model m, int32_t *K) {
+    if (!m || !K) return ICP_ERR_INVALID_ARGUMENT;
+    *K = m->K;
+    return ICP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (3) target
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_gather_tri_data(int n, const int *__restrict__ prim, const double *__restrict__ verts,
+                                  const int *__restrict__ tris, double *__restrict__ out) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    int p = prim[slot];
+    for (int k = 0; k < 3; k++)
+        for (int d = 0; d < 3; d++) out[(size_t)slot * 10 + 3 * k + d] = verts[3 * tris[3 * p + k] + d];
+    out[(size_t)slot * 10 + 9] = 0.0;
+}
+__global__ void k_gather_vert_data(int n, const int *__restrict__ prim, const double *__restrict__ verts,
+                                   double *__restrict__ out) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    int p = prim[slot];
+    out[(size_t)slot * 4] = verts[3 * p]; out[(size_t)slot * 4 + 1] = verts[3 * p + 1];
+    out[(size_t)slot * 4 + 2] = verts[3 * p + 2]; out[(size_t)slot * 4 + 3] = 0.0;
+}
+
+extern "C" int32_t icp_target_create(icp_ctx ctx, int32_t Nt, int32_t Tt, const double *xyz, const int32_t *tris,
+                                     icp_target *out) {
+    icp_target t = nullptr;
+    icp_ctx _ctx = ctx;
+    try {
+        ICP_REQUIRE(ctx != nullptr && out != nullptr, "null handle");
+        CtxLock lock(ctx);
+        check_mesh(Nt, Tt, xyz, tris);
+        cudaStream_t s = ctx->stream;
+        t = new icp_target_s();
+        t->ctx = ctx; t->Nt = Nt; t->Tt = Tt;
+        t->verts.upload(xyz, (size_t)3 * Nt, s);
+        t->tris.upload(tris, (size_t)3 * Tt, s);
+        t->h_boundary = boundary_table(Nt, Tt, tris);
+        t->has_boundary = std::any_of(t->h_boundary.begin(), t->h_boundary.end(), [](uint8_t b) { return b != 0; });
+        t->boundary.upload(t->h_boundary.data(), t->h_boundary.size(), s);
+        double scale = std::max(max_abs(xyz, (size_t)3 * Nt), 1e-3);
+        bvh_build(t->tri_bvh, 0, Tt, t->verts.p, t->tris.p, scale, s);
+        bvh_build(t->vert_bvh, 1, Nt, t->verts.p, nullptr, scale, s);
+        t->tri_data.alloc((size_t)t->tri_bvh.n * 10);
+        t->vert_data.alloc((size_t)t->vert_bvh.n * 4);
+        k_gather_tri_data<<<(t->tri_bvh.n + 127) / 128, 128, 0, s>>>(t->tri_bvh.n, t->tri_bvh.prim.p, t->verts.p, t->tris.p, t->tri_data.p);
+        ICP_CUDA(cudaGetLastError());
+        k_gather_vert_data<<<(t->vert_bvh.n + 127) / 128, 128, 0, s>>>(t->vert_bvh.n, t->vert_bvh.prim.p, t->verts.p, t->vert_data.p);
+        ICP_CUDA(cudaGetLastError());
+        sync_stream(ctx);
+        *out = t;
+        return ICP_OK;
+    } catch (...) {
+        int32_t rc = translate_exception(_ctx);
+        delete t;
+        return rc;
+    }
+}
+
+extern "C" int32_t icp_target_destroy(icp_target t) {
+    if (!t) return ICP_OK;
+    icp_ctx _ctx = t->ctx;
+    try {
+        CtxLock lock(_ctx);
+        sync_stream(_ctx);
+        delete t;
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (4) primitives
+// ---------------------------------------------------------------------------------------------------
+static NearestArgs target_tri_args(icp_target t) {
+    NearestArgs a;
+    a.bvh = &t->tri_bvh;
+    a.prim_data = t->tri_data.p;
+    return a;
+}
+static NearestArgs target_vert_args(icp_target t) {
+    NearestArgs a;
+    a.bvh = &t->vert_bvh;
+    a.prim_data = t->vert_data.p;
+    return a;
+}
+
+extern "C" int32_t icp_closest_point_surface(icp_target t, int64_t nq, const double *q, int32_t *tri, int32_t *feature,
+                                             double *cp, double *d2) {
+    ICP_API_BEGIN(t ? t->ctx : nullptr)
+    ICP_REQUIRE(nq >= 0 && (nq == 0 || q != nullptr), "bad query array");
+    if (nq == 0) return ICP_OK;
+    cudaStream_t s = _ctx->stream;
+    t->s_q.upload(q, (size_t)3 * nq, s);
+    t->s_d.ensure((size_t)4 * nq);
+    t->s_i.ensure((size_t)2 * nq);
+    NearestArgs a = target_tri_args(t);
+    a.nq = nq; a.q = t->s_q.p;
+    a.out_prim = t->s_i.p; a.out_feat = t->s_i.p + nq; a.out_cp = t->s_d.p; a.out_d2 = t->s_d.p + 3 * nq;
+    launch_nearest(a, s);
+    download(tri, t->s_i.p, nq, s);
+    download(feature, t->s_i.p + nq, nq, s);
+    download(cp, t->s_d.p, 3 * nq, s);
+    download(d2, t->s_d.p + 3 * nq, nq, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+extern "C" int32_t icp_closest_point_surface_device(icp_target t, int64_t nq, const double *q_dev, int32_t *tri_dev,
+                                                    double *cp_dev, double *d2_dev) {
+    ICP_API_BEGIN(t ? t->ctx : nullptr)
+    ICP_REQUIRE(nq >= 0 && (nq == 0 || q_dev != nullptr), "bad query array");
+    if (nq == 0) return ICP_OK;
+    NearestArgs a = target_tri_args(t);
+    a.nq = nq; a.q = q_dev; a.out_prim = tri_dev; a.out_cp = cp_dev; a.out_d2 = d2_dev;
+    launch_nearest(a, _ctx->stream);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+extern "C" int32_t icp_closest_vertex(icp_target t, int64_t nq, const double *q, int32_t *id, double *d2) {
+    ICP_API_BEGIN(t ? t->ctx : nullptr)
+    ICP_REQUIRE(nq >= 0 && (nq == 0 || q != nullptr), "bad query array");
+    if (nq == 0) return ICP_OK;
+    cudaStream_t s = _ctx->stream;
+    t->s_q.upload(q, (size_t)3 * nq, s);
+    t->s_d.ensure((size_t)nq);
+    t->s_i.ensure((size_t)nq);
+    NearestArgs a = target_vert_args(t);
+    a.nq = nq; a.q = t->s_q.p; a.out_prim = t->s_i.p; a.out_d2 = t->s_d.p;
+    launch_nearest(a, s);
+    download(id, t->s_i.p, nq, s);
+    download(d2, t->s_d.p, nq, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+extern "C" int32_t icp_target_boundary_flags(icp_target t, uint8_t *flags) {
+    if (!t || !flags) return ICP_ERR_INVALID_ARGUMENT;
+    memcpy(flags, t->h_boundary.data(), (size_t)t->Nt);
+    return ICP_OK;
+}
+
+extern "C" int32_t icp_model_boundary_flags(icp_model m, uint8_t *flags) {
+    if (!m || !flags) return ICP_ERR_INVALID_ARGUMENT;
+    memcpy(flags, m->h_boundary.data(), (size_t)m->N);
+    return ICP_OK;
+}
+
+static void upload_theta(icp_model m, int C, const double *theta, DevBuf<double> &buf, cudaStream_t s) {
+    ICP_REQUIRE(C >= 0 && (C == 0 || theta != nullptr), "bad theta array");
+    buf.upload(theta, (size_t)C * (m->K + kTheta0), s);
+}
+
+extern "C" int32_t icp_reconstruct(icp_model m, int32_t C, const double *theta, double *xyz) {
+    ICP_API_BEGIN(m ? m->ctx : nullptr)
+    if (C == 0) return ICP_OK;
+    ICP_REQUIRE(xyz != nullptr, "xyz is null");
+    cudaStream_t s = _ctx->stream;
+    upload_theta(m, C, theta, m->s_theta, s);
+    m->s_X.ensure((size_t)C * m->N * 3);
+    launch_reconstruct(m->dev(), C, m->s_theta.p, m->s_X.p, s);
+    download(xyz, m->s_X.p, (size_t)C * m->N * 3, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+extern "C" int32_t icp_vertex_normals(icp_model m, int32_t C, const double *theta, double *normals) {
+    ICP_API_BEGIN(m ? m->ctx : nullptr)
+    if (C == 0) return ICP_OK;
+    ICP_REQUIRE(normals != nullptr, "normals is null");
+    cudaStream_t s = _ctx->stream;
+    upload_theta(m, C, theta, m->s_theta, s);
+    size_t n = (size_t)C * m->N * 3;
+    m->s_X.ensure(n);
+    m->s_d.ensure(n);
+    launch_reconstruct(m->dev(), C, m->s_theta.p, m->s_X.p, s);
+    launch_vertex_normals(m->dev(), C, m->s_X.p, m->s_d.p, s);
+    download(normals, m->s_d.p, n, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+extern "C" int32_t icp_model_closest_point_surface(icp_model m, int32_t C, const double *theta, int64_t nq,
+                                                   const double *q, int32_t *tri, int32_t *feature, double *cp,
+                                                   double *d2) {
+    ICP_API_BEGIN(m ? m->ctx : nullptr)
+    ICP_REQUIRE(nq >= 0 && (nq == 0 || q != nullptr), "bad query array");
+    if (C == 0 || nq == 0) return ICP_OK;
+    cudaStream_t s = _ctx->stream;
+    upload_theta(m, C, theta, m->s_theta, s);
+    size_t tot = (size_t)C * nq;
+    m->s_X.ensure((size_t)C * m->N * 3);
+    m->s_q.upload(q, (size_t)3 * nq, s);
+    m->s_d.ensure(4 * tot);
+    m->s_i.ensure(2 * tot);
+    launch_reconstruct(m->dev(), C, m->s_theta.p, m->s_X.p, s);
+    bvh_refit(m->tri_bvh, C, m->s_X.p, m->N, m->tris.p, s);
+    NearestArgs a;
+    a.bvh = &m->tri_bvh; a.X = m->s_X.p; a.tris = m->tris.p; a.N = m->N;
+    a.C = C; a.nq = nq; a.q = m->s_q.p;
+    a.out_prim = m->s_i.p; a.out_feat = m->s_i.p + tot; a.out_cp = m->s_d.p; a.out_d2 = m->s_d.p + 3 * tot;
+    launch_nearest(a, s);
+    download(tri, m->s_i.p, tot, s);
+    download(feature, m->s_i.p + tot, tot, s);
+    download(cp, m->s_d.p, 3 * tot, s);
+    download(d2, m->s_d.p + 3 * tot, tot, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+extern "C" int32_t icp_model_closest_vertex(icp_model m, int32_t C, const double *theta, int64_t nq, const double *q,
+                                            int32_t *id, double *d2) {
+    ICP_API_BEGIN(m ? m->ctx : nullptr)
+    ICP_REQUIRE(nq >= 0 && (nq == 0 || q != nullptr), "bad query array");
+    if (C == 0 || nq == 0) return ICP_OK;
+    cudaStream_t s = _ctx->stream;
+    upload_theta(m, C, theta, m->s_theta, s);
+    size_t tot = (size_t)C * nq;
+    m->s_X.ensure((size_t)C * m->N * 3);
+    m->s_q.upload(q, (size_t)3 * nq, s);
+    m->s_d.ensure(tot);
+    m->s_i.ensure(tot);
+    launch_reconstruct(m->dev(), C, m->s_theta.p, m->s_X.p, s);
+    bvh_refit(m->vert_bvh, C, m->s_X.p, m->N, nullptr, s);
+    NearestArgs a;
+    a.bvh = &m->vert_bvh; a.X = m->s_X.p; a.N = m->N;
+    a.C = C; a.nq = nq; a.q = m->s_q.p; a.out_prim = m->s_i.p; a.out_d2 = m->s_d.p;
+    launch_nearest(a, s);
+    download(id, m->s_i.p, tot, s);
+    download(d2, m->s_d.p, tot, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (5) ICP proposal
+// ---------------------------------------------------------------------------------------------------
+static void check_ids(int N, const int32_t *ids, int n) {
+    ICP_REQUIRE(n >= 0 && (n == 0 || ids != nullptr), "bad id list");
+    for (int i = 0; i < n; i++) ICP_REQUIRE(ids[i] >= 0 && ids[i] < N, "model point id out of range");
+}
+
+extern "C" int32_t icp_proposal_create(icp_model m, icp_target t, const icp_proposal_params *params,
+                                       const int32_t *model_point_ids, int32_t n_ids, const double *target_points,
+                                       int32_t n_tp, icp_proposal *out) {
+    icp_proposal p = nullptr;
+    icp_ctx _ctx = m ? m->ctx : nullptr;
+    try {
+        ICP_REQUIRE(m && t && params && out, "null argument");
+        ICP_REQUIRE(m->ctx == t->ctx, "model and target belong to different contexts");
+        CtxLock lock(_ctx);
+        ICP_REQUIRE(params->direction == ICP_MODEL_SAMPLING || params->direction == ICP_TARGET_SAMPLING, "bad direction");
+        ICP_REQUIRE(params->step_length != 0.0 && std::isfinite(params->step_length), "step_length must be finite and non-zero");
+        ICP_REQUIRE(params->tangential_noise > 0 && params->noise_along_normal > 0, "noise std-devs must be > 0");
+        check_ids(m->N, model_point_ids, n_ids);
+        ICP_REQUIRE(n_tp >= 0 && (n_tp == 0 || target_points != nullptr), "bad target point list");
+        p = new icp_proposal_s();
+        p->model = m; p->target = t; p->prm = *params; p->n_ids = n_ids; p->n_tp = n_tp;
+        p->ids.upload(model_point_ids, n_ids, _ctx->stream);
+        p->tp.upload(target_points, (size_t)3 * n_tp, _ctx->stream);
+        sync_stream(_ctx);
+        *out = p;
+        return ICP_OK;
+    } catch (...) {
+        int32_t rc = translate_exception(_ctx);
+        delete p;
+        return rc;
+    }
+}
+
+extern "C" int32_t icp_proposal_destroy(icp_proposal p) {
+    if (!p) return ICP_OK;
+    icp_ctx _ctx = p->model->ctx;
+    try {
+        CtxLock lock(_ctx);
+        sync_stream(_ctx);
+        delete p;
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+namespace icp {
+
+void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const double *d_X, PosteriorWork &w, double *d_L,
+                        double *d_mu, const int *d_out_slot, cudaStream_t s) {
+    if (C <= 0) return;
+    icp_model m = p->model;
+    icp_target t = p->target;
+    const int Kp = m->Kp;
+    ModelDev md = m->dev();
+    if (!d_X) {
+        w.X.ensure((size_t)C * m->N * 3);
+        launch_reconstruct(md, C, d_theta, w.X.p, s);
+        d_X = w.X.p;
+    }
+    const bool tsamp = p->prm.direction == ICP_TARGET_SAMPLING;
+    int n = tsamp ? p->n_tp : p->n_ids;
+    size_t tot = (size_t)C * std::max(n, 1);
+    w.vid.ensure(tot); w.F.ensure(9 * tot); w.y.ensure(3 * tot); w.nobs.ensure(C);
+    w.M.ensure((size_t)C * Kp * Kp); w.b.ensure((size_t)C * Kp); w.status.ensure(C);
+    ObsArgs oa{};
+    oa.m = md; oa.prm = p->prm; oa.C = C; oa.theta = d_theta; oa.X = d_X;
+    if (tsamp) {
+        // :118 currentMesh.pointSet.findClosestPoint(targetPoint): vertex BVH refit to the current meshes
+        w.prim.ensure(tot);
+        bvh_refit(m->vert_bvh, C, d_X, m->N, nullptr, s);
+        NearestArgs a;
+        a.bvh = &m->vert_bvh; a.X = d_X; a.N = m->N; a.C = C; a.nq = n; a.q = p->tp.p; a.out_prim = w.prim.p;
+        launch_nearest(a, s);
+        oa.tp = p->tp.p; oa.near_vid = w.prim.p;
+    } else {
+        // :97 target.operations.closestPointOnSurface(currentMeshPoint)
+        w.cp.ensure(3 * tot);
+        NearestArgs a;
+        a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = n;
+        a.Xq = d_X; a.q_ids = p->ids.p; a.Nq = m->N; a.out_cp = w.cp.p;
+        launch_nearest(a, s);
+        oa.ids = p->ids.p; oa.cp = w.cp.p; oa.cp_on_boundary = nullptr;
+        if (p->prm.boundary_aware && t->has_boundary) {
+            // :98-99 target.pointSet.findClosestPoint(targetPoint).id -> pointIsOnBoundary
+            w.prim.ensure(tot); w.flags.ensure(tot);
+            NearestArgs v;
+            v.bvh = &t->vert_bvh; v.prim_data = t->vert_data.p; v.C = C; v.nq = n; v.q = w.cp.p; v.q_per_chain = 1;
+            v.out_prim = w.prim.p;
+            launch_nearest(v, s);
+            launch_lookup_flags((int64_t)C * n, w.prim.p, t->boundary.p, t->Nt, w.flags.p, s);
+            oa.cp_on_boundary = w.flags.p;
+        }
+    }
+    ObsDev od{n, w.vid.p, w.F.p, w.y.p, w.nobs.p};
+    launch_observations(oa, od, s);
+    launch_posterior_build(md, C, od, w.M.p, w.b.p, s);
+    launch_cholesky_solve(C, m->K, Kp, w.M.p, w.b.p, d_L, d_mu, d_out_slot, w.status.p, s);
+}
+
+}  // namespace icp
+
+static void strip_pad_vec(const std::vector<double> &src, int C, int K, int Kp, double *dst) {
+    for (int c = 0; c < C; c++)
+        for (int j = 0; j < K; j++) dst[(size_t)c * K + j] = src[(size_t)c * Kp + j];
+}
+
+extern "C" int32_t icp_posterior(icp_proposal p, int32_t C, const double *theta, double *mu, double *M, int32_t *n_obs) {
+    ICP_API_BEGIN(p ? p->model->ctx : nullptr)
+    if (C == 0) return ICP_OK;
+    icp_model m = p->model;
+    const int K = m->K, Kp = m->Kp;
+    cudaStream_t s = _ctx->stream;
+    upload_theta(m, C, theta, p->s_theta, s);
+    DevBuf<double> dL, dmu;
+    dL.alloc((size_t)C * Kp * Kp);
+    dmu.alloc((size_t)C * Kp);
+    posterior_pipeline(p, C, p->s_theta.p, nullptr, p->work, dL.p, dmu.p, nullptr, s);
+    std::vector<double> hmu((size_t)C * Kp), hM;
+    std::vector<int> hn(C), hst(C);
+    download(hmu.data(), dmu.p, hmu.size(), s);
+    if (M) { hM.resize((size_t)C * Kp * Kp); download(hM.data(), p->work.M.p, hM.size(), s); }
+    download(hn.data(), p->work.nobs.p, C, s);
+    download(hst.data(), p->work.status.p, C, s);
+    sync_stream(_ctx);
+    if (mu) strip_pad_vec(hmu, C, K, Kp, mu);
+    if (M)
+        for (int c = 0; c < C; c++)
+            for (int i = 0; i < K; i++)
+                for (int j = 0; j < K; j++) M[((size_t)c * K + i) * K + j] = hM[((size_t)c * Kp + i) * Kp + j];
+    if (n_obs) std::copy(hn.begin(), hn.end(), n_obs);
+    ICP_API_END
+}
+
+// Memoize(icpPosterior, 20) (NonRigidIcpProposal.scala:49): per-handle cache keyed by the bytes of theta.
+// Returns the cache slot of every chain; posteriors that are missing are computed in one batch.
+static std::vector<int> ensure_posteriors(icp_proposal p, int C, const double *theta_host, cudaStream_t s) {
+    icp_model m = p->model;
+    const int Kp = m->Kp, Lt = m->K + kTheta0;
+    int want = 32 + 4 * C;
+    if (p->cache_slots < want) {
+        p->cache_slots = want;
+        p->cache_map.clear();
+        p->slot_key.assign(want, std::string());
+        p->cache_L.alloc((size_t)want * Kp * Kp);
+        p->cache_mu.alloc((size_t)want * Kp);
+        p->cache_next = 0;
+    }
+    std::vector<int> slot(C, -1);
+    std::vector<char> pinned(p->cache_slots, 0);
+    std::vector<int> miss;
+    std::unordered_map<std::string, int> miss_key_slot;
+    for (int c = 0; c < C; c++) {
+        std::string key((const char *)(theta_host + (size_t)c * Lt), sizeof(double) * Lt);
+        auto it = p->cache_map.find(key);
+        if (it != p->cache_map.end()) { slot[c] = it->second; pinned[it->second] = 1; }
+    }
+    for (int c = 0; c < C; c++) {
+        if (slot[c] >= 0) continue;
+        std::string key((const char *)(theta_host + (size_t)c * Lt), sizeof(double) * Lt);
+        auto it = miss_key_slot.find(key);
+        if (it != miss_key_slot.end()) { slot[c] = it->second; continue; }
+        while (pinned[p->cache_next]) p->cache_next = (p->cache_next + 1) % p->cache_slots;
+        int sl = p->cache_next;
+        p->cache_next = (p->cache_next + 1) % p->cache_slots;
+        pinned[sl] = 1;
+        if (!p->slot_key[sl].empty()) p->cache_map.erase(p->slot_key[sl]);
+        p->slot_key[sl] = key;
+        p->cache_map[key] = sl;
+        miss_key_slot[key] = sl;
+        slot[c] = sl;
+        miss.push_back(c);
+    }
+    if (!miss.empty()) {
+        int nm = (int)miss.size();
+        std::vector<double> th((size_t)nm * Lt);
+        std::vector<int> out_slot(nm);
+        for (int i = 0; i < nm; i++) {
+            memcpy(&th[(size_t)i * Lt], theta_host + (size_t)miss[i] * Lt, sizeof(double) * Lt);
+            out_slot[i] = slot[miss[i]];
+        }
+        p->s_theta2.upload(th.data(), th.size(), s);
+        p->s_slot.upload(out_slot.data(), nm, s);
+        posterior_pipeline(p, nm, p->s_theta2.p, nullptr, p->work, p->cache_L.p, p->cache_mu.p, p->s_slot.p, s);
+        sync_stream(p->model->ctx);  // host staging vectors go out of scope
+    }
+    return slot;
+}
+
+extern "C" int32_t icp_proposal_clear_cache(icp_proposal p) {
+    ICP_API_BEGIN(p ? p->model->ctx : nullptr)
+    p->cache_map.clear();
+    for (auto &k : p->slot_key) k.clear();
+    ICP_API_END
+}
+
+extern "C" int32_t icp_propose(icp_proposal p, int32_t C, const double *theta, const double *z, double *theta_out) {
+    ICP_API_BEGIN(p ? p->model->ctx : nullptr)
+    if (C == 0) return ICP_OK;
+    icp_model m = p->model;
+    ICP_REQUIRE(theta && z && theta_out, "null array");
+    cudaStream_t s = _ctx->stream;
+    const int Lt = m->K + kTheta0;
+    std::vector<int> slot = ensure_posteriors(p, C, theta, s);
+    upload_theta(m, C, theta, p->s_theta, s);
+    p->s_z.upload(z, (size_t)C * m->K, s);
+    DevBuf<int> dslot;
+    dslot.upload(slot.data(), C, s);
+    p->s_out.ensure((size_t)C * Lt);
+    launch_propose(m->dev(), C, p->prm.step_length, p->s_theta.p, p->s_z.p, p->cache_L.p, p->cache_mu.p, dslot.p,
+                   p->s_out.p, s);
+    download(theta_out, p->s_out.p, (size_t)C * Lt, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+extern "C" int32_t icp_log_transition(icp_proposal p, int32_t C, const double *from, const double *to, double *out) {
+    ICP_API_BEGIN(p ? p->model->ctx : nullptr)
+    if (C == 0) return ICP_OK;
+    icp_model m = p->model;
+    ICP_REQUIRE(from && to && out, "null array");
+    cudaStream_t s = _ctx->stream;
+    std::vector<int> slot = ensure_posteriors(p, C, from, s);
+    upload_theta(m, C, from, p->s_theta, s);
+    upload_theta(m, C, to, p->s_theta2, s);
+    DevBuf<int> dslot;
+    dslot.upload(slot.data(), C, s);
+    p->s_out.ensure((size_t)C);
+    launch_log_transition(C, m->K, m->Kp, p->prm.step_length, p->s_theta.p, p->s_theta2.p, p->cache_L.p, p->cache_mu.p,
+                          dslot.p, p->s_out.p, s);
+    download(out, p->s_out.p, C, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+// deterministic ICP iteration: posterior mean with isotropic noise, re-projection S mu, step
+__global__ void k_std_icp_step(int C, int K, int Kp, double step, const double *__restrict__ S,
+                               const double *__restrict__ mu, const double *__restrict__ alpha,
+                               double *__restrict__ alpha_out) {
+    int c = blockIdx.x;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        double acc = 0.0;
+        for (int k = 0; k < Kp; k++) acc = fma(S[(size_t)k * Kp + j], mu[(size_t)c * Kp + k], acc);
+        double a = alpha[(size_t)c * K + j];
+        alpha_out[(size_t)c * K + j] = a + (acc - a) * step;  // IcpBasedSurfaceFitting.scala:84-85
+    }
+}
+
+extern "C" int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t direction, const int32_t *model_point_ids,
+                                         int32_t n_ids, const double *target_points, int32_t n_tp, double sigma2,
+                                         double step_length, int32_t C, const double *alpha, double *alpha_out) {
+    ICP_API_BEGIN(m ? m->ctx : nullptr)
+    ICP_REQUIRE(t && t->ctx == m->ctx, "bad target");
+    ICP_REQUIRE(direction == ICP_MODEL_SAMPLING || direction == ICP_TARGET_SAMPLING, "bad direction");
+    ICP_REQUIRE(sigma2 > 0, "sigma2 must be > 0");
+    if (C == 0) return ICP_OK;
+    ICP_REQUIRE(alpha && alpha_out, "null array");
+    check_ids(m->N, model_point_ids, n_ids);
+    cudaStream_t s = _ctx->stream;
+    const int K = m->K, Kp = m->Kp, Lt = K + kTheta0;
+    // identity pose (IcpRegistration passes the rigid identity), theta = [1, 0.., alpha]
+    std::vector<double> th((size_t)C * Lt, 0.0);
+    for (int c = 0; c < C; c++) {
+        th[(size_t)c * Lt] = 1.0;
+        memcpy(&th[(size_t)c * Lt + kTheta0], alpha + (size_t)c * K, sizeof(double) * K);
+    }
+    icp_proposal_s tmp;
+    tmp.model = m; tmp.target = t;
+    tmp.prm.step_length = step_length; tmp.prm.tangential_noise = 1; tmp.prm.noise_along_normal = 1;
+    tmp.prm.direction = direction; tmp.prm.boundary_aware = 0;
+    tmp.n_ids = n_ids; tmp.n_tp = n_tp;
+    tmp.ids.upload(model_point_ids, n_ids, s);
+    tmp.tp.upload(target_points, (size_t)3 * n_tp, s);
+    DevBuf<double> dth, dL, dmu, da, dout;
+    dth.upload(th.data(), th.size(), s);
+    dL.alloc((size_t)C * Kp * Kp); dmu.alloc((size_t)C * Kp);
+    da.upload(alpha, (size_t)C * K, s); dout.alloc((size_t)C * K);
+    // run the pipeline with isotropic noise: patch ObsArgs through a local copy of the pipeline
+    {
+        icp_proposal p = &tmp;
+        PosteriorWork &w = tmp.work;
+        ModelDev md = m->dev();
+        w.X.ensure((size_t)C * m->N * 3);
+        launch_reconstruct(md, C, dth.p, w.X.p, s);
+        const bool tsamp = direction == ICP_TARGET_SAMPLING;
+        int n = tsamp ? n_tp : n_ids;
+        size_t tot = (size_t)C * std::max(n, 1);
+        w.vid.ensure(tot); w.F.ensure(9 * tot); w.y.ensure(3 * tot); w.nobs.ensure(C);
+        w.M.ensure((size_t)C * Kp * Kp); w.b.ensure((size_t)C * Kp); w.status.ensure(C);
+        ObsArgs oa{};
+        oa.m = md; oa.prm = p->prm; oa.C = C; oa.theta = dth.p; oa.X = w.X.p; oa.iso = 1; oa.iso_sigma2 = sigma2;
+        if (tsamp) {
+            w.prim.ensure(tot);
+            bvh_refit(m->vert_bvh, C, w.X.p, m->N, nullptr, s);
+            NearestArgs a;
+            a.bvh = &m->vert_bvh; a.X = w.X.p; a.N = m->N; a.C = C; a.nq = n; a.q = tmp.tp.p; a.out_prim = w.prim.p;
+            launch_nearest(a, s);
+            oa.tp = tmp.tp.p; oa.near_vid = w.prim.p;
+        } else {
+            w.cp.ensure(3 * tot);
+            NearestArgs a;
+            a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = n;
+            a.Xq = w.X.p; a.q_ids = tmp.ids.p; a.Nq = m->N; a.out_cp = w.cp.p;
+            launch_nearest(a, s);
+            oa.ids = tmp.ids.p; oa.cp = w.cp.p;
+        }
+        ObsDev od{n, w.vid.p, w.F.p, w.y.p, w.nobs.p};
+        launch_observations(oa, od, s);
+        launch_posterior_build(md, C, od, w.M.p, w.b.p, s);
+        launch_cholesky_solve(C, K, Kp, w.M.p, w.b.p, dL.p, dmu.p, nullptr, w.status.p, s);
+    }
+    k_std_icp_step<<<C, 128, 0, s>>>(C, K, Kp, step_length, m->S.p, dmu.p, da.p, dout.p);
+    ICP_CUDA(cudaGetLastError());
+    download(alpha_out, dout.p, (size_t)C * K, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (6) evaluators
+// ---------------------------------------------------------------------------------------------------
+extern "C" int32_t icp_evaluator_create(icp_model m, icp_target t, const icp_evaluator_params *params,
+                                        const int32_t *model_point_ids, int32_t n_ids, const double *target_points,
+                                        int32_t n_tp, icp_evaluator *out) {
+    icp_evaluator e = nullptr;
+    icp_ctx _ctx = m ? m->ctx : nullptr;
+    try {
+        ICP_REQUIRE(m && t && params && out, "null argument");
+        ICP_REQUIRE(m->ctx == t->ctx, "model and target belong to different contexts");
+        CtxLock lock(_ctx);
+        ICP_REQUIRE(params->kind >= ICP_EVAL_ACCEPT_ALL && params->kind <= ICP_EVAL_COLLECTIVE, "bad evaluator kind");
+        ICP_REQUIRE(params->mode >= ICP_MODEL_TO_TARGET && params->mode <= ICP_SYMMETRIC, "bad evaluation mode");
+        cudaStream_t s = _ctx->stream;
+        e = new icp_evaluator_s();
+        e->model = m; e->target = t; e->prm = *params;
+        if (params->kind == ICP_EVAL_HAUSDORFF) {
+            // MeshMetrics.hausdorffDistance: every vertex of both meshes
+            std::vector<int> all(m->N);
+            for (int i = 0; i < m->N; i++) all[i] = i;
+            e->n_ids = m->N; e->ids.upload(all.data(), all.size(), s);
+            e->n_tp = t->Nt; e->tp.alloc((size_t)3 * t->Nt);
+            ICP_CUDA(cudaMemcpyAsync(e->tp.p, t->verts.p, sizeof(double) * 3 * t->Nt, cudaMemcpyDeviceToDevice, s));
+            ICP_REQUIRE(params->p0 > 0, "Exponential rate must be > 0");
+        } else {
+            check_ids(m->N, model_point_ids, n_ids);
+            ICP_REQUIRE(n_tp >= 0 && (n_tp == 0 || target_points != nullptr), "bad target point list");
+            e->n_ids = n_ids; e->ids.upload(model_point_ids, n_ids, s);
+            e->n_tp = n_tp; e->tp.upload(target_points, (size_t)3 * n_tp, s);
+            if (params->kind != ICP_EVAL_ACCEPT_ALL) ICP_REQUIRE(params->p1 > 0, "Gaussian std-dev must be > 0");
+            if (params->kind == ICP_EVAL_COLLECTIVE) ICP_REQUIRE(params->p2 > 0, "Exponential rate must be > 0");
+        }
+        sync_stream(_ctx);
+        *out = e;
+        return ICP_OK;
+    } catch (...) {
+        int32_t rc = translate_exception(_ctx);
+        delete e;
+        return rc;
+    }
+}
+
+extern "C" int32_t icp_evaluator_destroy(icp_evaluator e) {
+    if (!e) return ICP_OK;
+    icp_ctx _ctx = e->model->ctx;
+    try {
+        CtxLock lock(_ctx);
+        sync_stream(_ctx);
+        delete e;
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+namespace icp {
+
+void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_theta, const double *d_X, double *d_values,
+                        int *d_status, cudaStream_t s) {
+    if (C <= 0) return;
+    icp_model m = e->model;
+    icp_target t = e->target;
+    ModelDev md = m->dev();
+    const int kind = e->prm.kind, mode = e->prm.mode;
+    EvalReduceArgs ra{};
+    ra.prm = e->prm; ra.C = C; ra.K = m->K; ra.theta = d_theta; ra.values = d_values; ra.status = d_status;
+    if (kind != ICP_EVAL_ACCEPT_ALL) {
+        if (!d_X) {
+            w.X.ensure((size_t)C * m->N * 3);
+            launch_reconstruct(md, C, d_theta, w.X.p, s);
+            d_X = w.X.p;
+        }
+        const bool use_m = kind == ICP_EVAL_HAUSDORFF || mode != ICP_TARGET_TO_MODEL;
+        const bool use_t = kind == ICP_EVAL_HAUSDORFF || mode != ICP_MODEL_TO_TARGET;
+        const bool collective = kind == ICP_EVAL_COLLECTIVE;
+        if (use_m && e->n_ids > 0) {
+            size_t tot = (size_t)C * e->n_ids;
+            w.d2_m2t.ensure(tot);
+            NearestArgs a;
+            a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = e->n_ids;
+            a.Xq = d_X; a.q_ids = e->ids.p; a.Nq = m->N; a.out_d2 = w.d2_m2t.p;
+            if (collective) { w.cp_m2t.ensure(3 * tot); a.out_cp = w.cp_m2t.p; }
+            launch_nearest(a, s);
+            if (collective && t->has_boundary) {
+                // CollectiveAverage...:46-47: nearest target vertex of the closest point, dropped when on the boundary
+                w.prim.ensure(tot); w.skip_m2t.ensure(tot);
+                NearestArgs v;
+                v.bvh = &t->vert_bvh; v.prim_data = t->vert_data.p; v.C = C; v.nq = e->n_ids; v.q = w.cp_m2t.p;
+                v.q_per_chain = 1; v.out_prim = w.prim.p;
+                launch_nearest(v, s);
+                launch_lookup_flags((int64_t)tot, w.prim.p, t->boundary.p, t->Nt, w.skip_m2t.p, s);
+                ra.skip_m2t = w.skip_m2t.p;
+            }
+        }
+        if (use_t && e->n_tp > 0) {
+            size_t tot = (size_t)C * e->n_tp;
+            w.d2_t2m.ensure(tot);
+            bvh_refit(m->tri_bvh, C, d_X, m->N, m->tris.p, s);
+            NearestArgs a;
+            a.bvh = &m->tri_bvh; a.X = d_X; a.tris = m->tris.p; a.N = m->N; a.C = C; a.nq = e->n_tp; a.q = e->tp.p;
+            a.out_d2 = w.d2_t2m.p;
+            if (collective) { w.cp_t2m.ensure(3 * tot); a.out_cp = w.cp_t2m.p; }
+            launch_nearest(a, s);
+            if (collective && t->has_boundary) {
+                // CollectiveAverage...:58-59: id of the nearest vertex of the MODEL sample, looked up in the
+                // TARGET's boundary table
+                w.prim.ensure(tot); w.skip_t2m.ensure(tot);
+                bvh_refit(m->vert_bvh, C, d_X, m->N, nullptr, s);
+                NearestArgs v;
+                v.bvh = &m->vert_bvh; v.X = d_X; v.N = m->N; v.C = C; v.nq = e->n_tp; v.q = w.cp_t2m.p; v.q_per_chain = 1;
+                v.out_prim = w.prim.p;
+                launch_nearest(v, s);
+                launch_lookup_flags((int64_t)tot, w.prim.p, t->boundary.p, t->Nt, w.skip_t2m.p, s);
+                ra.skip_t2m = w.skip_t2m.p;
+            }
+        }
+        ra.n_m2t = use_m ? e->n_ids : 0; ra.d2_m2t = w.d2_m2t.p;
+        ra.n_t2m = use_t ? e->n_tp : 0; ra.d2_t2m = w.d2_t2m.p;
+    }
+    launch_eval_reduce(ra, s);
+}
+
+}  // namespace icp
+
+extern "C" int32_t icp_eval_log_value(icp_evaluator e, int32_t C, const double *theta, double *values, int32_t *status) {
+    ICP_API_BEGIN(e ? e->model->ctx : nullptr)
+    if (C == 0) return ICP_OK;
+    ICP_REQUIRE(values != nullptr, "values is null");
+    cudaStream_t s = _ctx->stream;
+    upload_theta(e->model, C, theta, e->s_theta, s);
+    e->s_values.ensure((size_t)3 * C);
+    e->s_status.ensure(C);
+    evaluator_pipeline(e, e->work, C, e->s_theta.p, nullptr, e->s_values.p, e->s_status.p, s);
+    download(values, e->s_values.p, (size_t)3 * C, s);
+    download(status, e->s_status.p, C, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+extern "C" int32_t icp_eval_prior(icp_model m, int32_t C, const double *theta, double *out) {
+    ICP_API_BEGIN(m ? m->ctx : nullptr)
+    if (C == 0) return ICP_OK;
+    ICP_REQUIRE(out != nullptr, "out is null");
+    cudaStream_t s = _ctx->stream;
+    upload_theta(m, C, theta, m->s_theta, s);
+    m->s_d.ensure(C);
+    launch_prior(C, m->K, m->s_theta.p, m->s_d.p, s);
+    download(out, m->s_d.p, C, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}
+
+// RegistrationComparison (api/other/RegistrationComparison.scala:24-49): avg / Hausdorff / boundary-aware avg + max
+__global__ void __launch_bounds__(128) k_metrics(int N, int Nt, const double *__restrict__ d2_m2t,
+                                                 const uint8_t *__restrict__ skip, const double *__restrict__ d2_t2m,
+                                                 double *__restrict__ out) {
+    __shared__ double red[4][128];
+    int c = blockIdx.x;
+    double s = 0, mx = 0, sb = 0, cb = 0, mb = -INFINITY, mt = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double d = sqrt(d2_m2t[(size_t)c * N + i]);
+        s += d; mx = fmax(mx, d);
+        if (!(skip && skip[(size_t)c * N + i])) { sb += d; cb += 1; mb = fmax(mb, d); }
+    }
+    for (int i = threadIdx.x; i < Nt; i += blockDim.x) mt = fmax(mt, sqrt(d2_t2m[(size_t)c * Nt + i]));
+    red[0][threadIdx.x] = s; red[1][threadIdx.x] = fmax(mx, mt); red[2][threadIdx.x] = sb; red[3][threadIdx.x] = cb;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + o];
+            red[1][threadIdx.x] = fmax(red[1][threadIdx.x], red[1][threadIdx.x + o]);
+            red[2][threadIdx.x] += red[2][threadIdx.x + o];
+            red[3][threadIdx.x] += red[3][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    double avg = red[0][0] / N, hd = red[1][0], avgb = red[2][0] / red[3][0];
+    __syncthreads();
+    red[0][threadIdx.x] = mb;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[0][threadIdx.x] = fmax(red[0][threadIdx.x], red[0][threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[4 * c] = avg; out[4 * c + 1] = hd; out[4 * c + 2] = avgb; out[4 * c + 3] = red[0][0]; }
+}
+
+extern "C" int32_t icp_registration_metrics(icp_model m, icp_target t, int32_t C, const double *theta, double *out) {
+    ICP_API_BEGIN(m ? m->ctx : nullptr)
+    ICP_REQUIRE(t && t->ctx == m->ctx, "bad target");
+    if (C == 0) return ICP_OK;
+    ICP_REQUIRE(out != nullptr, "out is null");
+    cudaStream_t s = _ctx->stream;
+    upload_theta(m, C, theta, m->s_theta, s);
+    const int N = m->N, Nt = t->Nt;
+    DevBuf<double> X, d2a, cpa, d2b, dout;
+    DevBuf<int> prim;
+    DevBuf<uint8_t> skip;
+    X.alloc((size_t)C * N * 3); d2a.alloc((size_t)C * N); cpa.alloc((size_t)C * N * 3); d2b.alloc((size_t)C * Nt); dout.alloc((size_t)4 * C);
+    launch_reconstruct(m->dev(), C, m->s_theta.p, X.p, s);
+    // every model vertex against the target surface
+    NearestArgs a;
+    a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = N; a.q = X.p; a.q_per_chain = 1;
+    a.out_d2 = d2a.p; a.out_cp = cpa.p;
+    launch_nearest(a, s);
+    const uint8_t *skip_p = nullptr;
+    if (t->has_boundary) {
+        prim.alloc((size_t)C * N); skip.alloc((size_t)C * N);
+        NearestArgs v;
+        v.bvh = &t->vert_bvh; v.prim_data = t->vert_data.p; v.C = C; v.nq = N; v.q = cpa.p; v.q_per_chain = 1; v.out_prim = prim.p;
+        launch_nearest(v, s);
+        launch_lookup_flags((int64_t)C * N, prim.p, t->boundary.p, Nt, skip.p, s);
+        skip_p = skip.p;
+    }
+    // every target vertex against the model surfaces (second half of hausdorffDistance)
+    bvh_refit(m->tri_bvh, C, X.p, N, m->tris.p, s);
+    NearestArgs b;
+    b.bvh = &m->tri_bvh; b.X = X.p; b.tris = m->tris.p; b.N = N; b.C = C; b.nq = Nt; b.q = t->verts.p; b.out_d2 = d2b.p;
+    launch_nearest(b, s);
+    k_metrics<<<C, 128, 0, s>>>(N, Nt, d2a.p, skip_p, d2b.p, dout.p);
+    ICP_CUDA(cudaGetLastError());
+    download(out, dout.p, (size_t)4 * C, s);
+    sync_stream(_ctx);
+    ICP_API_END
+}

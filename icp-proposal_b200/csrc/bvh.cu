@@ -1,0 +1,391 @@
+// bvh.cu - device LBVH construction, per-instance refit and exact nearest-primitive traversal.
+//
+// Replaces Scalismo's per-mesh query structures behind
+//   target.operations.closestPointOnSurface   (NonRigidIcpProposal.scala:97, evaluators)
+//   pointSet.findClosestPoint                  (NonRigidIcpProposal.scala:98,118)
+// The static target BVH is built once on the device (Morton codes -> radix sort -> Karras 2012
+// topology -> bottom-up boxes); the model-mesh BVHs keep the reference-mesh topology and are refit
+// per chain and per sample. Boxes are FP32 and conservative (rounded outwards + slack), the leaf
+// tests are exact FP64, so the result equals a brute-force FP64 search (ties -> lowest index).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "icp_internal.h"
+
+namespace icp {
+
+// ---------------------------------------------------------------------------------------------------
+// construction
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v) {
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void k_morton(int n_prims, int n, int prim_kind, const double *__restrict__ verts,
+                         const int *__restrict__ tris, double lox, double loy, double loz, double sx, double sy,
+                         double sz, unsigned long long *__restrict__ keys, int *__restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = i < n_prims ? i : 0;  // a single primitive is duplicated so that the tree has a root
+    double cx, cy, cz;
+    if (prim_kind == 0) {
+        int a = tris[3 * p], b = tris[3 * p + 1], c = tris[3 * p + 2];
+        cx = (verts[3 * a] + verts[3 * b] + verts[3 * c]) * (1.0 / 3.0);
+        cy = (verts[3 * a + 1] + verts[3 * b + 1] + verts[3 * c + 1]) * (1.0 / 3.0);
+        cz = (verts[3 * a + 2] + verts[3 * b + 2] + verts[3 * c + 2]) * (1.0 / 3.0);
+    } else {
+        cx = verts[3 * p]; cy = verts[3 * p + 1]; cz = verts[3 * p + 2];
+    }
+    double fx = fmin(fmax((cx - lox) * sx, 0.0), 1.0), fy = fmin(fmax((cy - loy) * sy, 0.0), 1.0),
+           fz = fmin(fmax((cz - loz) * sz, 0.0), 1.0);
+    unsigned long long ix = (unsigned long long)(fx * 2097151.0), iy = (unsigned long long)(fy * 2097151.0),
+                       iz = (unsigned long long)(fz * 2097151.0);
+    keys[i] = (expand21(ix) << 2) | (expand21(iy) << 1) | expand21(iz);
+    vals[i] = p;
+}
+
+__device__ __forceinline__ int lbvh_delta(const unsigned long long *keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll(a ^ b);
+}
+
+__global__ void k_karras(int n, const unsigned long long *__restrict__ keys, int2 *__restrict__ children,
+                         int *__restrict__ parent) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    if (i == 0) parent[0] = -1;
+    int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = lbvh_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = lbvh_delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) / 2;
+        if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int left, right;
+    if (lo == gamma) { left = ~gamma; parent[n - 1 + gamma] = i; } else { left = gamma; parent[gamma] = i; }
+    if (hi == gamma + 1) { right = ~(gamma + 1); parent[n - 1 + gamma + 1] = i; } else { right = gamma + 1; parent[gamma + 1] = i; }
+    children[i] = make_int2(left, right);
+}
+
+// one thread per (instance, leaf): leaf box, then climb; the second arrival at a node merges
+__global__ void k_refit(int n, int instances, int prim_kind, const int *__restrict__ prim,
+                        const int2 *__restrict__ children, const int *__restrict__ parent,
+                        const double *__restrict__ X, int N, const int *__restrict__ tris, float slack,
+                        float4 *__restrict__ nodes, float4 *nodebox, int *counters) {
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)n * instances) return;
+    int inst = (int)(g / n), slot = (int)(g % n);
+    const double *Xi = X + (size_t)inst * N * 3;
+    int p = prim[slot];
+    double lx, ly, lz, hx, hy, hz;
+    if (prim_kind == 0) {
+        int a = tris[3 * p], b = tris[3 * p + 1], c = tris[3 * p + 2];
+        lx = fmin(fmin(Xi[3 * a], Xi[3 * b]), Xi[3 * c]); hx = fmax(fmax(Xi[3 * a], Xi[3 * b]), Xi[3 * c]);
+        ly = fmin(fmin(Xi[3 * a + 1], Xi[3 * b + 1]), Xi[3 * c + 1]); hy = fmax(fmax(Xi[3 * a + 1], Xi[3 * b + 1]), Xi[3 * c + 1]);
+        lz = fmin(fmin(Xi[3 * a + 2], Xi[3 * b + 2]), Xi[3 * c + 2]); hz = fmax(fmax(Xi[3 * a + 2], Xi[3 * b + 2]), Xi[3 * c + 2]);
+    } else {
+        lx = hx = Xi[3 * p]; ly = hy = Xi[3 * p + 1]; lz = hz = Xi[3 * p + 2];
+    }
+    float4 lo = make_float4(__double2float_rd(lx) - slack, __double2float_rd(ly) - slack, __double2float_rd(lz) - slack, 0.f);
+    float4 hi = make_float4(__double2float_ru(hx) + slack, __double2float_ru(hy) + slack, __double2float_ru(hz) + slack, 0.f);
+    float4 *nb = nodebox + (size_t)inst * (2 * n - 1) * 2;
+    float4 *nd = nodes + (size_t)inst * (n - 1) * 3;
+    int *cnt = counters + (size_t)inst * (n - 1);
+    __stcg(&nb[2 * (n - 1 + slot)], lo);
+    __stcg(&nb[2 * (n - 1 + slot) + 1], hi);
+    int node = parent[n - 1 + slot];
+    while (node >= 0) {
+        __threadfence();
+        int old = atomicAdd(&cnt[node], 1);
+        if (old == 0) return;
+        __threadfence();
+        int2 ch = children[node];
+        int li = ch.x >= 0 ? ch.x : n - 1 + (~ch.x), ri = ch.y >= 0 ? ch.y : n - 1 + (~ch.y);
+        float4 llo = __ldcg(&nb[2 * li]), lhi = __ldcg(&nb[2 * li + 1]);
+        float4 rlo = __ldcg(&nb[2 * ri]), rhi = __ldcg(&nb[2 * ri + 1]);
+        nd[3 * node] = make_float4(llo.x, llo.y, llo.z, lhi.x);
+        nd[3 * node + 1] = make_float4(lhi.y, lhi.z, rlo.x, rlo.y);
+        nd[3 * node + 2] = make_float4(rlo.z, rhi.x, rhi.y, rhi.z);
+        __stcg(&nb[2 * node], make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f));
+        __stcg(&nb[2 * node + 1], make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f));
+        node = parent[node];
+    }
+}
+
+void bvh_refit(Bvh &b, int instances, const double *d_X, int N, const int *d_tris, cudaStream_t s) {
+    ProfScope _ps(ST_REFIT, s);
+    int n = b.n;
+    b.nodes.ensure((size_t)instances * (n - 1) * 3);
+    b.nodebox.ensure((size_t)instances * (2 * n - 1) * 2);
+    b.counters.ensure((size_t)instances * (n - 1));
+    b.instances = instances;
+    ICP_CUDA(cudaMemsetAsync(b.counters.p, 0, sizeof(int) * (size_t)instances * (n - 1), s));
+    long long total = (long long)n * instances;
+    int threads = 128;
+    k_refit<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+        n, instances, b.prim_kind, b.prim.p, b.children.p, b.parent.p, d_X, N, d_tris, b.slack, b.nodes.p,
+        b.nodebox.p, b.counters.p);
+    ICP_CUDA(cudaGetLastError());
+}
+
+void bvh_build(Bvh &b, int prim_kind, int n_prims, const double *d_verts, const int *d_tris, double scale,
+               cudaStream_t s) {
+    ICP_REQUIRE(n_prims >= 1, "bvh_build: empty primitive set");
+    int n = n_prims < 2 ? 2 : n_prims;
+    b.n = n;
+    b.prim_kind = prim_kind;
+    b.slack = (float)(scale * 1e-6) + 1e-30f;
+    b.children.alloc(n - 1);
+    b.parent.alloc(2 * n - 1);
+    b.prim.alloc(n);
+    // bounding box of the vertices (host side: one-off, tiny)
+    int nv_needed = 0;
+    std::vector<int> htris;
+    if (prim_kind == 0) {
+        htris.resize((size_t)3 * n_prims);
+        ICP_CUDA(cudaMemcpyAsync(htris.data(), d_tris, sizeof(int) * 3 * n_prims, cudaMemcpyDeviceToHost, s));
+        ICP_CUDA(cudaStreamSynchronize(s));
+        for (int v : htris) nv_needed = v + 1 > nv_needed ? v + 1 : nv_needed;
+    } else {
+        nv_needed = n_prims;
+    }
+    std::vector<double> hv((size_t)3 * nv_needed);
+    ICP_CUDA(cudaMemcpyAsync(hv.data(), d_verts, sizeof(double) * 3 * nv_needed, cudaMemcpyDeviceToHost, s));
+    ICP_CUDA(cudaStreamSynchronize(s));
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int v = 0; v < nv_needed; v++)
+        for (int d = 0; d < 3; d++) {
+            double x = hv[3 * v + d];
+            if (x < lo[d]) lo[d] = x;
+            if (x > hi[d]) hi[d] = x;
+        }
+    double sc[3];
+    for (int d = 0; d < 3; d++) sc[d] = hi[d] > lo[d] ? 1.0 / (hi[d] - lo[d]) : 0.0;
+
+    DevBuf<unsigned long long> keys, keys2;
+    DevBuf<int> vals;
+    keys.alloc(n); keys2.alloc(n); vals.alloc(n);
+    int threads = 128;
+    k_morton<<<(n + threads - 1) / threads, threads, 0, s>>>(n_prims, n, prim_kind, d_verts, d_tris, lo[0], lo[1], lo[2],
+                                                              sc[0], sc[1], sc[2], keys.p, vals.p);
+    ICP_CUDA(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    ICP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys2.p, vals.p, b.prim.p, n, 0, 64, s));
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(tmp_bytes);
+    ICP_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, vals.p, b.prim.p, n, 0, 64, s));
+    k_karras<<<(n - 1 + threads - 1) / threads, threads, 0, s>>>(n, keys2.p, b.children.p, b.parent.p);
+    ICP_CUDA(cudaGetLastError());
+    bvh_refit(b, 1, d_verts, nv_needed, d_tris, s);
+    ICP_CUDA(cudaStreamSynchronize(s));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact point-triangle closest point (FP64), classified vertex (0) / edge (1) / face (2)
+// ---------------------------------------------------------------------------------------------------
+struct Hit {
+    double d2;
+    double x, y, z;
+    int prim;
+    int feat;
+};
+
+__device__ __forceinline__ void point_triangle(double px, double py, double pz, double ax, double ay, double az,
+                                               double bx, double by, double bz, double cx, double cy, double cz,
+                                               double &rx, double &ry, double &rz, int &feat) {
+    double abx = bx - ax, aby = by - ay, abz = bz - az;
+    double acx = cx - ax, acy = cy - ay, acz = cz - az;
+    double apx = px - ax, apy = py - ay, apz = pz - az;
+    double d1 = abx * apx + aby * apy + abz * apz, d2 = acx * apx + acy * apy + acz * apz;
+    if (d1 <= 0.0 && d2 <= 0.0) { rx = ax; ry = ay; rz = az; feat = 0; return; }
+    double bpx = px - bx, bpy = py - by, bpz = pz - bz;
+    double d3 = abx * bpx + aby * bpy + abz * bpz, d4 = acx * bpx + acy * bpy + acz * bpz;
+    if (d3 >= 0.0 && d4 <= d3) { rx = bx; ry = by; rz = bz; feat = 0; return; }
+    double vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
+        double v = d1 / (d1 - d3);
+        rx = ax + v * abx; ry = ay + v * aby; rz = az + v * abz; feat = 1; return;
+    }
+    double cpx = px - cx, cpy = py - cy, cpz = pz - cz;
+    double d5 = abx * cpx + aby * cpy + abz * cpz, d6 = acx * cpx + acy * cpy + acz * cpz;
+    if (d6 >= 0.0 && d5 <= d6) { rx = cx; ry = cy; rz = cz; feat = 0; return; }
+    double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+        double w = d2 / (d2 - d6);
+        rx = ax + w * acx; ry = ay + w * acy; rz = az + w * acz; feat = 1; return;
+    }
+    double va = d3 * d6 - d5 * d4;
+    if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) {
+        double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        rx = bx + w * (cx - bx); ry = by + w * (cy - by); rz = bz + w * (cz - bz); feat = 1; return;
+    }
+    double denom = 1.0 / (va + vb + vc);
+    double v = vb * denom, w = vc * denom;
+    rx = ax + abx * v + acx * w; ry = ay + aby * v + acy * w; rz = az + abz * v + acz * w; feat = 2;
+}
+
+template <int PRIM, bool DYNAMIC>
+__device__ __forceinline__ void leaf_test(int slot, const int *__restrict__ prim, const double *__restrict__ prim_data,
+                                          const double *__restrict__ Xi, const int *__restrict__ tris, double qx,
+                                          double qy, double qz, Hit &h) {
+    int p = prim[slot];
+    double rx, ry, rz;
+    int feat = 0;
+    if (PRIM == 0) {
+        double ax, ay, az, bx, by, bz, cx, cy, cz;
+        if (DYNAMIC) {
+            int a = tris[3 * p], b = tris[3 * p + 1], c = tris[3 * p + 2];
+            ax = Xi[3 * a]; ay = Xi[3 * a + 1]; az = Xi[3 * a + 2];
+            bx = Xi[3 * b]; by = Xi[3 * b + 1]; bz = Xi[3 * b + 2];
+            cx = Xi[3 * c]; cy = Xi[3 * c + 1]; cz = Xi[3 * c + 2];
+        } else {
+            const double2 *t = reinterpret_cast<const double2 *>(prim_data + (size_t)slot * 10);
+            double2 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2), t3 = __ldg(t + 3), t4 = __ldg(t + 4);
+            ax = t0.x; ay = t0.y; az = t1.x; bx = t1.y; by = t2.x; bz = t2.y; cx = t3.x; cy = t3.y; cz = t4.x;
+        }
+        point_triangle(qx, qy, qz, ax, ay, az, bx, by, bz, cx, cy, cz, rx, ry, rz, feat);
+    } else {
+        if (DYNAMIC) {
+            rx = Xi[3 * p]; ry = Xi[3 * p + 1]; rz = Xi[3 * p + 2];
+        } else {
+            const double2 *t = reinterpret_cast<const double2 *>(prim_data + (size_t)slot * 4);
+            double2 t0 = __ldg(t), t1 = __ldg(t + 1);
+            rx = t0.x; ry = t0.y; rz = t1.x;
+        }
+    }
+    double dx = qx - rx, dy = qy - ry, dz = qz - rz;
+    double d2 = dx * dx + dy * dy + dz * dz;
+    if (d2 < h.d2 || (d2 == h.d2 && p < h.prim)) {
+        h.d2 = d2; h.x = rx; h.y = ry; h.z = rz; h.prim = p; h.feat = feat;
+    }
+}
+
+__device__ __forceinline__ float box_d2(float lx, float ly, float lz, float hx, float hy, float hz, float qx, float qy,
+                                        float qz) {
+    float dx = fmaxf(fmaxf(lx - qx, qx - hx), 0.f);
+    float dy = fmaxf(fmaxf(ly - qy, qy - hy), 0.f);
+    float dz = fmaxf(fmaxf(lz - qz, qz - hz), 0.f);
+    return (dx * dx + dy * dy + dz * dz) * 0.999999f;  // conservative: never above the true FP64 distance
+}
+
+constexpr int kStack = 64;
+
+template <int PRIM, bool DYNAMIC>
+__global__ void __launch_bounds__(128) k_nearest(int n, const int2 *__restrict__ children,
+                                                 const float4 *__restrict__ nodes, const int *__restrict__ prim,
+                                                 const double *__restrict__ prim_data, const double *__restrict__ X,
+                                                 const int *__restrict__ tris, int N, int C, long long nq,
+                                                 const double *__restrict__ q, int q_per_chain,
+                                                 const double *__restrict__ Xq, const int *__restrict__ q_ids, int Nq,
+                                                 int *__restrict__ out_prim, int *__restrict__ out_feat,
+                                                 double *__restrict__ out_cp, double *__restrict__ out_d2) {
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nq * C) return;
+    int c = (int)(g / nq);
+    long long i = g % nq;
+    double qx, qy, qz;
+    if (q_ids) {
+        const double *src = Xq + ((size_t)c * Nq + q_ids[i]) * 3;
+        qx = src[0]; qy = src[1]; qz = src[2];
+    } else {
+        const double *src = q + ((q_per_chain ? (size_t)c * nq : 0) + i) * 3;
+        qx = src[0]; qy = src[1]; qz = src[2];
+    }
+    const float4 *nd = DYNAMIC ? nodes + (size_t)c * (n - 1) * 3 : nodes;
+    const double *Xi = DYNAMIC ? X + (size_t)c * N * 3 : nullptr;
+    float fx = (float)qx, fy = (float)qy, fz = (float)qz;
+    Hit h;
+    h.d2 = INFINITY; h.x = h.y = h.z = 0.0; h.prim = 0x7fffffff; h.feat = -1;
+    float best = INFINITY;
+    int stack_n[kStack];
+    float stack_d[kStack];
+    int sp = 0, node = 0;
+    if (!(qx == qx && qy == qy && qz == qz)) node = 0x7ffffffe;  // NaN query: no traversal, NaN result
+    while (node != 0x7ffffffe) {
+        if (node < 0) {
+            leaf_test<PRIM, DYNAMIC>(~node, prim, prim_data, Xi, tris, qx, qy, qz, h);
+            best = __double2float_ru(h.d2);
+        } else {
+            int2 ch = __ldg(&children[node]);
+            float4 a = __ldg(&nd[3 * node]), b = __ldg(&nd[3 * node + 1]), cc = __ldg(&nd[3 * node + 2]);
+            float dl = box_d2(a.x, a.y, a.z, a.w, b.x, b.y, fx, fy, fz);
+            float dr = box_d2(b.z, b.w, cc.x, cc.y, cc.z, cc.w, fx, fy, fz);
+            bool hl = dl <= best, hr = dr <= best;
+            if (hl && hr) {
+                int near = ch.x, far = ch.y;
+                float dfar = dr;
+                if (dr < dl) { near = ch.y; far = ch.x; dfar = dl; }
+                if (sp < kStack) { stack_n[sp] = far; stack_d[sp] = dfar; sp++; }
+                node = near;
+                continue;
+            } else if (hl) { node = ch.x; continue; }
+            else if (hr) { node = ch.y; continue; }
+        }
+        // pop
+        node = 0x7ffffffe;
+        while (sp > 0) {
+            --sp;
+            if (stack_d[sp] <= best) { node = stack_n[sp]; break; }
+        }
+    }
+    if (h.prim == 0x7fffffff) { h.d2 = NAN; h.x = h.y = h.z = NAN; h.prim = -1; }
+    if (out_prim) out_prim[g] = h.prim;
+    if (out_feat) out_feat[g] = h.feat;
+    if (out_cp) { out_cp[3 * g] = h.x; out_cp[3 * g + 1] = h.y; out_cp[3 * g + 2] = h.z; }
+    if (out_d2) out_d2[g] = h.d2;
+}
+
+void launch_nearest(const NearestArgs &a, cudaStream_t s) {
+    ProfScope _ps(a.prim_data ? ST_NEAREST_STATIC : ST_NEAREST_DYNAMIC, s);
+    long long total = a.nq * a.C;
+    if (total <= 0) return;
+    const Bvh &b = *a.bvh;
+    bool dynamic = a.prim_data == nullptr;
+    int threads = 128;
+    unsigned blocks = (unsigned)((total + threads - 1) / threads);
+#define ICP_LAUNCH_NEAREST(P, D)                                                                                  \
+    k_nearest<P, D><<<blocks, threads, 0, s>>>(b.n, b.children.p, b.nodes.p, b.prim.p, a.prim_data, a.X, a.tris, \
+                                               a.N, a.C, (long long)a.nq, a.q, a.q_per_chain, a.Xq, a.q_ids,     \
+                                               a.Nq, a.out_prim, a.out_feat, a.out_cp, a.out_d2)
+    if (b.prim_kind == 0) {
+        if (dynamic) ICP_LAUNCH_NEAREST(0, true); else ICP_LAUNCH_NEAREST(0, false);
+    } else {
+        if (dynamic) ICP_LAUNCH_NEAREST(1, true); else ICP_LAUNCH_NEAREST(1, false);
+    }
+#undef ICP_LAUNCH_NEAREST
+    ICP_CUDA(cudaGetLastError());
+}
+
+// flags[i] = table[prim[i]] (0 when prim < 0)
+__global__ void k_lookup_flags(long long n, const int *__restrict__ prim, const uint8_t *__restrict__ table, int table_n,
+                               uint8_t *__restrict__ flags) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = prim[i];
+    flags[i] = (p >= 0 && p < table_n) ? table[p] : 0;
+}
+
+void launch_lookup_flags(int64_t n, const int *d_prim, const uint8_t *d_table, int table_n, uint8_t *d_flags,
+                         cudaStream_t s) {
+    if (n <= 0) return;
+    k_lookup_flags<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, d_prim, d_table, table_n, d_flags);
+    ICP_CUDA(cudaGetLastError());
+}
+
+}  // namespace icp

@@ -1,0 +1,670 @@
+// chain.cu - device-resident Metropolis-Hastings runner for C independent chains.
+//
+// Replaces the per-step work of Scalismo's MetropolisHastings.next + MixtureProposal as driven from
+// api/sampling/SamplingRegistration.scala:52-85:
+//   currentP   = evaluator.logValue(current)          kept resident per chain (EvaluationCaching.scala:32-36)
+//   proposal   = generator.propose(current)           k_chain_propose: mixture pick + component proposal
+//   proposalP  = evaluator.logValue(proposal)         reconstruct + evaluator pipeline
+//   t          = logTransitionRatio(current, proposal) ICP posteriors of the proposal + k_chain_accept
+//   accept iff a > 0 or U < exp(a)                     k_chain_accept, chain log append
+// The posterior of the current state of every ICP component stays resident per chain (the reference's
+// Memoize(icpPosterior, 20), NonRigidIcpProposal.scala:49), so each step builds one new posterior per
+// ICP component - for the proposed state.
+#include <cmath>
+#include <cstring>
+
+#include "icp_device.cuh"
+#include "icp_internal.h"
+
+using namespace icp;
+
+namespace {
+
+constexpr int kMaxComp = 16;
+
+struct CompDev {
+    int kind, axis, icp_index;  // icp_index: which ICP posterior set (or -1)
+    double cdf, weight, sd, step;
+};
+
+struct ChainParams {
+    int n_comp, n_icp, K, Kp, C;
+    CompDev comp[kMaxComp];
+};
+
+struct RngDev {
+    unsigned long long seed, chain_offset;
+    const double *u_comp, *z, *u_acc;  // host-RNG mode when non-null: [step][C], [step][C][K], [step][C]
+};
+
+struct LogDev {
+    int *comp;
+    uint8_t *accepted;
+    double *values;  // [step][C][3]
+    double *theta;   // [step][C][L]
+};
+
+struct StateDev {
+    double *theta_cur, *theta_prop;     // [C][L]
+    double *values_cur, *values_prop;   // [C][3]
+    int *cur_sel;                       // [C] which posterior state (0/1) is current
+    int *slot_cur, *slot_prop;          // [C] = sel * C + c
+    int *comp_sel;                      // [C] component picked this step
+    double *u_acc;                      // [C]
+    long long *n_acc;                   // [C]
+    int *step;                          // [1] device step counter
+    double *L, *mu;                     // [n_icp][2 C][Kp Kp], [n_icp][2 C][Kp]
+};
+
+__global__ void k_chain_init(int C, StateDev st) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0) *st.step = 0;
+    if (c >= C) return;
+    st.cur_sel[c] = 0;
+    st.slot_cur[c] = c;
+    st.slot_prop[c] = C + c;
+    st.n_acc[c] = 0;
+}
+
+// standard normals of chain `chain` at step `step`: Philox block 1 + k/2 -> Box-Muller pair
+__device__ __forceinline__ double chain_normal(unsigned long long seed, unsigned long long chain, unsigned int step, int k) {
+    uint4 r = chain_philox(seed, chain, step, 1u + (unsigned int)(k >> 1));
+    double u1 = 1.0 - u53(r.x, r.y);  // (0, 1]
+    double u2 = u53(r.z, r.w);
+    double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    return (k & 1) ? rad * sn : rad * cs;
+}
+
+// w = L^-T z with L staged in shared memory (row-major, ld = Kp); one warp, registers + shuffles
+__device__ void warp_backsolve_smem(const double *sL, int Kp, const double *z_sm, double *w_sm) {
+    int lane = threadIdx.x & 31;
+    double zr[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) { int k = lane + 32 * q; zr[q] = k < Kp ? z_sm[k] : 0.0; }
+    for (int i = Kp - 1; i >= 0; i--) {
+        int owner = i & 31, slot = i >> 5;
+        double zi = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (q == slot) zi = zr[q];
+        double wi = __shfl_sync(0xffffffffu, zi, owner) / sL[(size_t)i * Kp + i];
+        if (lane == 0) w_sm[i] = wi;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            int k = lane + 32 * q;
+            if (k < i) zr[q] = fma(-sL[(size_t)i * Kp + k], wi, zr[q]);
+        }
+    }
+    __syncwarp();
+}
+
+// MixtureProposal.propose (pick the first component whose cumulative weight reaches r) + the component's propose
+__global__ void __launch_bounds__(128) k_chain_propose(ChainParams P, ModelDev m, StateDev st, RngDev rng) {
+    extern __shared__ double sm[];
+    const int K = P.K, Kp = P.Kp, Lt = K + kTheta0, C = P.C;
+    double *sz = sm, *sw = sm + Kp, *sL = sm + 2 * Kp;  // sL: [Kp][Kp]
+    __shared__ int s_ci;
+    int c = blockIdx.x;
+    unsigned int step = (unsigned int)*st.step;
+    unsigned long long chain = rng.chain_offset + (unsigned long long)c;
+    if (threadIdx.x == 0) {
+        double uc, ua;
+        if (rng.u_comp) {
+            uc = rng.u_comp[(size_t)step * C + c];
+            ua = rng.u_acc[(size_t)step * C + c];
+        } else {
+            uint4 r = chain_philox(rng.seed, chain, step, 0u);
+            uc = u53(r.x, r.y);
+            ua = u53(r.z, r.w);
+        }
+        int ci = P.n_comp - 1;
+        for (int i = 0; i < P.n_comp; i++)
+            if (P.comp[i].cdf >= uc) { ci = i; break; }
+        s_ci = ci;
+        st.comp_sel[c] = ci;
+        st.u_acc[c] = ua;
+    }
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        double zz = 0.0;
+        if (k < K) zz = rng.z ? rng.z[((size_t)step * C + c) * K + k] : chain_normal(rng.seed, chain, step, k);
+        sz[k] = zz;
+    }
+    __syncthreads();
+    const CompDev cd = P.comp[s_ci];
+    const double *th = st.theta_cur + (size_t)c * Lt;
+    double *to = st.theta_prop + (size_t)c * Lt;
+    if (cd.kind == ICP_PROP_ICP) {
+        size_t pslot = (size_t)cd.icp_index * 2 * C + st.slot_cur[c];
+        const double *Lc = st.L + pslot * Kp * Kp, *muc = st.mu + pslot * Kp;
+        for (int e = threadIdx.x; e < Kp * Kp; e += blockDim.x) sL[e] = Lc[e];
+        __syncthreads();
+        if (threadIdx.x < 32) warp_backsolve_smem(sL, Kp, sz, sw);
+        __syncthreads();
+        for (int k = threadIdx.x; k < Kp; k += blockDim.x) sz[k] = muc[k] + sw[k];
+        __syncthreads();
+        for (int j = threadIdx.x; j < Lt; j += blockDim.x) {
+            if (j < kTheta0) { to[j] = th[j]; continue; }
+            int jj = j - kTheta0;
+            double acc = 0.0;
+            for (int k = 0; k < Kp; k++) acc = fma(__ldg(&m.S[(size_t)k * Kp + jj]), sz[k], acc);
+            to[j] = th[j] + (acc - th[j]) * cd.step;  // NonRigidIcpProposal.scala:61-62
+        }
+    } else {
+        for (int j = threadIdx.x; j < Lt; j += blockDim.x) {
+            double v = th[j];
+            if (cd.kind == ICP_PROP_RANDOM_SHAPE) {
+                if (j >= kTheta0) v = th[j] + cd.sd * sz[j - kTheta0];   // RandomShapeUpdateProposal.scala:34-35
+            } else if (cd.kind == ICP_PROP_ROTATION) {
+                if (j == 4 + cd.axis) v = th[j] + cd.sd * sz[0];         // PoseProposals.scala:36-44
+            } else {
+                if (j == 1 + cd.axis) v = th[j] + cd.sd * sz[0];         // PoseProposals.scala:70-78
+            }
+            to[j] = v;
+        }
+    }
+}
+
+// |L^T d|^2, d in shared memory
+__device__ double chain_quad_LT(const double *__restrict__ Lc, int Kp, const double *d_sm, double *red) {
+    double part = 0.0;
+    for (int j = threadIdx.x; j < Kp; j += blockDim.x) {
+        double v = 0.0;
+#pragma unroll 4
+        for (int i = j; i < Kp; i++) v = fma(__ldg(&Lc[(size_t)i * Kp + j]), d_sm[i], v);
+        part = fma(v, v, part);
+    }
+    return block_sum(part, red);
+}
+
+__device__ __forceinline__ double gauss1_logpdf(double x, double sd) {
+    return -(x * x) / (2.0 * sd * sd) - log(sd * sqrt(2.0 * 3.14159265358979323846));
+}
+
+// log transition densities of every mixture component in both directions, log-sum-exp, acceptance, log append
+__global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st, LogDev lg) {
+    extern __shared__ double sm[];
+    const int K = P.K, Kp = P.Kp, Lt = K + kTheta0, C = P.C;
+    double *sd = sm, *red = sm + Kp;
+    __shared__ double s_fwd[kMaxComp], s_bwd[kMaxComp];
+    __shared__ int s_flags[3];  // [0] any of theta[0..9] differs, [1] outside rotation group, [2] outside translation group
+    int c = blockIdx.x;
+    int step = *st.step;
+    const double *cur = st.theta_cur + (size_t)c * Lt, *prp = st.theta_prop + (size_t)c * Lt;
+    if (threadIdx.x < 3) s_flags[threadIdx.x] = 0;
+    __syncthreads();
+    // equality guards (ModelFittingParameters equality is element-wise on allParameters)
+    for (int j = threadIdx.x; j < Lt; j += blockDim.x) {
+        bool diff = !(cur[j] == prp[j]);
+        if (diff) {
+            if (j < kTheta0) s_flags[0] = 1;
+            if (!(j >= 4 && j <= 6)) s_flags[1] = 1;
+            if (!(j >= 1 && j <= 3)) s_flags[2] = 1;
+        }
+    }
+    __syncthreads();
+    double ss = 0.0;  // |alpha' - alpha|^2 for the random-walk components
+    for (int k = threadIdx.x; k < K; k += blockDim.x) { double r = prp[kTheta0 + k] - cur[kTheta0 + k]; ss = fma(r, r, ss); }
+    ss = block_sum(ss, red);
+    for (int i = 0; i < P.n_comp; i++) {
+        const CompDev cd = P.comp[i];
+        double fwd, bwd;
+        if (cd.kind == ICP_PROP_ICP) {
+            if (s_flags[0]) { fwd = bwd = -INFINITY; }                          // NonRigidIcpProposal.scala:72-74
+            else {
+                size_t sc = (size_t)cd.icp_index * 2 * C + st.slot_cur[c], sp = (size_t)cd.icp_index * 2 * C + st.slot_prop[c];
+                for (int k = threadIdx.x; k < Kp; k += blockDim.x)
+                    sd[k] = k < K ? (cur[kTheta0 + k] + ((prp[kTheta0 + k] - cur[kTheta0 + k]) / cd.step)) - st.mu[sc * Kp + k] : 0.0;
+                __syncthreads();
+                double qf = chain_quad_LT(st.L + sc * Kp * Kp, Kp, sd, red);
+                __syncthreads();
+                for (int k = threadIdx.x; k < Kp; k += blockDim.x)
+                    sd[k] = k < K ? (prp[kTheta0 + k] + ((cur[kTheta0 + k] - prp[kTheta0 + k]) / cd.step)) - st.mu[sp * Kp + k] : 0.0;
+                __syncthreads();
+                double qb = chain_quad_LT(st.L + sp * Kp * Kp, Kp, sd, red);
+                __syncthreads();
+                fwd = -0.5 * (K * ICP_LOG_2PI + qf);
+                bwd = -0.5 * (K * ICP_LOG_2PI + qb);
+            }
+        } else if (cd.kind == ICP_PROP_RANDOM_SHAPE) {
+            if (s_flags[0]) fwd = bwd = -INFINITY;                               // RandomShapeUpdateProposal.scala:39
+            else fwd = bwd = -0.5 * (K * ICP_LOG_2PI + K * log(cd.sd * cd.sd) + ss / (cd.sd * cd.sd));
+        } else if (cd.kind == ICP_PROP_ROTATION) {
+            if (s_flags[1]) fwd = bwd = -INFINITY;                               // PoseProposals.scala:48
+            else { double r = prp[4 + cd.axis] - cur[4 + cd.axis]; fwd = bwd = gauss1_logpdf(r, cd.sd); }
+        } else {
+            if (s_flags[2]) fwd = bwd = -INFINITY;                               // PoseProposals.scala:82
+            else { double r = prp[1 + cd.axis] - cur[1 + cd.axis]; fwd = bwd = gauss1_logpdf(r, cd.sd); }
+        }
+        if (threadIdx.x == 0) { s_fwd[i] = fwd; s_bwd[i] = bwd; }
+    }
+    __syncthreads();
+    __shared__ int s_acc;
+    if (threadIdx.x == 0) {
+        // MixtureProposal.logTransitionProbability: ln sum_i w_i exp(l_i)
+        double mf = -INFINITY, mb = -INFINITY;
+        bool nan = false;
+        for (int i = 0; i < P.n_comp; i++) {
+            mf = fmax(mf, s_fwd[i]); mb = fmax(mb, s_bwd[i]);
+            if (s_fwd[i] != s_fwd[i] || s_bwd[i] != s_bwd[i]) nan = true;
+        }
+        double lf = -INFINITY, lb = -INFINITY;
+        if (mf > -INFINITY) { double s = 0; for (int i = 0; i < P.n_comp; i++) s += P.comp[i].weight * exp(s_fwd[i] - mf); lf = log(s) + mf; }
+        if (mb > -INFINITY) { double s = 0; for (int i = 0; i < P.n_comp; i++) s += P.comp[i].weight * exp(s_bwd[i] - mb); lb = log(s) + mb; }
+        double t = lf - lb;
+        double vp = st.values_prop[3 * c], vc = st.values_cur[3 * c];
+        double a = vp - vc - t;                                                   // MetropolisHastings.next
+        int ok = (!nan) && ((a > 0.0) || (st.u_acc[c] < exp(a)));
+        s_acc = ok;
+    }
+    __syncthreads();
+    int ok = s_acc;
+    if (ok) {
+        for (int j = threadIdx.x; j < Lt; j += blockDim.x) st.theta_cur[(size_t)c * Lt + j] = prp[j];
+        if (threadIdx.x < 3) st.values_cur[3 * c + threadIdx.x] = st.values_prop[3 * c + threadIdx.x];
+    }
+    __syncthreads();
+    // chain log: the state that is current after the step (JSONAcceptRejectLogger.scala:93-106)
+    size_t rec = (size_t)step * C + c;
+    if (lg.theta)
+        for (int j = threadIdx.x; j < Lt; j += blockDim.x) lg.theta[rec * Lt + j] = ok ? prp[j] : cur[j];
+    if (threadIdx.x == 0) {
+        if (ok) {
+            int sel = 1 - st.cur_sel[c];
+            st.cur_sel[c] = sel;
+            st.slot_cur[c] = sel * C + c;
+            st.slot_prop[c] = (1 - sel) * C + c;
+            st.n_acc[c] += 1;
+        }
+        if (lg.comp) lg.comp[rec] = st.comp_sel[c];
+        if (lg.accepted) lg.accepted[rec] = (uint8_t)ok;
+        if (lg.values) {
+            const double *v = ok ? st.values_prop + 3 * c : st.values_cur + 3 * c;
+            lg.values[3 * rec] = v[0]; lg.values[3 * rec + 1] = v[1]; lg.values[3 * rec + 2] = v[2];
+        }
+    }
+}
+
+__global__ void k_step_increment(int *step) { *step += 1; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+struct icp_chain_s {
+    icp_model model = nullptr;
+    icp_target target = nullptr;
+    icp_evaluator evaluator = nullptr;
+    int max_chains = 0;
+    ChainParams P{};
+    std::vector<icp_proposal> icp_props;
+    // state
+    DevBuf<double> theta_cur, theta_prop, values_cur, values_prop, u_acc, L, mu, X;
+    DevBuf<int> cur_sel, slot_cur, slot_prop, comp_sel, step;
+    DevBuf<long long> n_acc;
+    std::vector<PosteriorWork> pwork;
+    EvalWork ework;
+    DevBuf<int> estatus;
+    // staging for the host-buffer entry point
+    DevBuf<double> h_u_comp, h_z, h_u_acc, h_log_values, h_log_theta;
+    DevBuf<int> h_log_comp;
+    DevBuf<uint8_t> h_log_acc;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0;
+    int64_t last_launches = 0;
+    int last_per_step = 0;
+    bool use_graph = true;
+};
+
+extern "C" int32_t icp_chain_create(icp_model m, icp_target t, const icp_component *components, int32_t n_components,
+                                    icp_evaluator evaluator, int32_t max_chains, icp_chain *out) {
+    icp_chain ch = nullptr;
+    icp_ctx _ctx = m ? m->ctx : nullptr;
+    try {
+        ICP_REQUIRE(m && t && components && evaluator && out, "null argument");
+        ICP_REQUIRE(m->ctx == t->ctx, "model and target belong to different contexts");
+        ICP_REQUIRE(evaluator->model == m && evaluator->target == t, "evaluator was built for another model / target");
+        ICP_REQUIRE(n_components >= 1 && n_components <= kMaxComp, "1..16 mixture components supported");
+        ICP_REQUIRE(max_chains >= 1, "max_chains must be >= 1");
+        CtxLock lock(_ctx);
+        ch = new icp_chain_s();
+        ch->model = m; ch->target = t; ch->evaluator = evaluator; ch->max_chains = max_chains;
+        ChainParams &P = ch->P;
+        P.n_comp = n_components; P.K = m->K; P.Kp = m->Kp; P.n_icp = 0;
+        double wsum = 0;
+        for (int i = 0; i < n_components; i++) {
+            ICP_REQUIRE(components[i].weight > 0 && std::isfinite(components[i].weight), "component weights must be > 0");
+            wsum += components[i].weight;
+        }
+        double acc = 0;
+        for (int i = 0; i < n_components; i++) {
+            const icp_component &ci = components[i];
+            CompDev &cd = P.comp[i];
+            cd.kind = ci.kind; cd.axis = ci.axis; cd.sd = ci.sd; cd.icp_index = -1; cd.step = 1.0;
+            cd.weight = ci.weight / wsum;
+            acc += cd.weight;
+            cd.cdf = i == n_components - 1 ? 1.0 : acc;
+            switch (ci.kind) {
+                case ICP_PROP_ICP:
+                    ICP_REQUIRE(ci.proposal && ci.proposal->model == m && ci.proposal->target == t,
+                                "ICP component needs a proposal built for this model / target");
+                    cd.icp_index = P.n_icp++;
+                    cd.step = ci.proposal->prm.step_length;
+                    ch->icp_props.push_back(ci.proposal);
+                    break;
+                case ICP_PROP_RANDOM_SHAPE:
+                    ICP_REQUIRE(ci.sd > 0, "random-walk std-dev must be > 0");
+                    break;
+                case ICP_PROP_ROTATION:
+                case ICP_PROP_TRANSLATION:
+                    ICP_REQUIRE(ci.sd > 0 && ci.axis >= 0 && ci.axis < 3, "pose proposal needs sd > 0 and axis in 0..2");
+                    break;
+                default:
+                    throw ArgError{"unknown component kind"};
+            }
+        }
+        ch->pwork.resize(P.n_icp);
+        ICP_CUDA(cudaEventCreate(&ch->ev0));
+        ICP_CUDA(cudaEventCreate(&ch->ev1));
+        const char *env = getenv("ICPCUDA_NO_GRAPH");
+        ch->use_graph = !(env && env[0] == '1');
+        *out = ch;
+        return ICP_OK;
+    } catch (...) {
+        int32_t rc = translate_exception(_ctx);
+        delete ch;
+        return rc;
+    }
+}
+
+extern "C" int32_t icp_chain_destroy(icp_chain c) {
+    if (!c) return ICP_OK;
+    icp_ctx _ctx = c->model->ctx;
+    try {
+        CtxLock lock(_ctx);
+        ICP_CUDA(cudaStreamSynchronize(_ctx->stream));
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->ev1) cudaEventDestroy(c->ev1);
+        delete c;
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+namespace {
+
+struct RunCtx {
+    icp_chain ch;
+    int C;
+    StateDev st;
+    RngDev rng;
+    LogDev lg;
+    cudaStream_t s;
+    int64_t launches = 0;
+};
+
+// evaluator + ICP posteriors of the parameter vectors in `theta` (all chains), written to the
+// posterior state selected by `slots`
+void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, const int *d_slots) {
+    icp_chain ch = r.ch;
+    icp_model m = ch->model;
+    const int C = r.C, Kp = m->Kp;
+    launch_reconstruct(m->dev(), C, d_theta, ch->X.p, r.s);
+    evaluator_pipeline(ch->evaluator, ch->ework, C, d_theta, ch->X.p, d_values, ch->estatus.p, r.s);
+    for (int i = 0; i < ch->P.n_icp; i++) {
+        double *Lb = r.st.L + (size_t)i * 2 * C * Kp * Kp, *mub = r.st.mu + (size_t)i * 2 * C * Kp;
+        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, r.s);
+    }
+}
+
+void enqueue_step(RunCtx &r) {
+    icp_chain ch = r.ch;
+    icp_model m = ch->model;
+    const int C = r.C, Kp = m->Kp;
+    ChainParams P = ch->P;
+    P.C = C;
+    size_t smem_p = sizeof(double) * ((size_t)2 * Kp + (size_t)Kp * Kp);
+    {
+        ProfScope ps(ST_PROPOSE, r.s);
+        k_chain_propose<<<C, 128, smem_p, r.s>>>(P, m->dev(), r.st, r.rng);
+        ICP_CUDA(cudaGetLastError());
+    }
+    enqueue_state_eval(r, r.st.theta_prop, r.st.values_prop, r.st.slot_prop);
+    {
+        ProfScope ps(ST_ACCEPT, r.s);
+        k_chain_accept<<<C, 128, sizeof(double) * (Kp + 40), r.s>>>(P, r.st, r.lg);
+        ICP_CUDA(cudaGetLastError());
+        k_step_increment<<<1, 1, 0, r.s>>>(r.st.step);
+        ICP_CUDA(cudaGetLastError());
+    }
+}
+
+void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev, const icp_chain_io *io, bool async) {
+    icp_model m = ch->model;
+    icp_ctx ctx = m->ctx;
+    cudaStream_t s = ctx->stream;
+    const int K = m->K, Kp = m->Kp, Lt = K + kTheta0;
+    ICP_REQUIRE(C >= 1 && C <= ch->max_chains, "C must be in [1, max_chains]");
+    ICP_REQUIRE(n_steps >= 0, "n_steps must be >= 0");
+    ICP_REQUIRE(theta0_dev && io, "null argument");
+    bool host_rng = io->u_comp || io->z || io->u_acc;
+    if (host_rng) ICP_REQUIRE(io->u_comp && io->z && io->u_acc, "u_comp, z and u_acc must be given together");
+    const int n_icp = ch->P.n_icp;
+    ch->theta_cur.ensure((size_t)C * Lt); ch->theta_prop.ensure((size_t)C * Lt);
+    ch->values_cur.ensure((size_t)3 * C); ch->values_prop.ensure((size_t)3 * C);
+    ch->u_acc.ensure(C); ch->cur_sel.ensure(C); ch->slot_cur.ensure(C); ch->slot_prop.ensure(C);
+    ch->comp_sel.ensure(C); ch->step.ensure(1); ch->n_acc.ensure(C); ch->estatus.ensure(C);
+    ch->L.ensure((size_t)std::max(n_icp, 1) * 2 * C * Kp * Kp); ch->mu.ensure((size_t)std::max(n_icp, 1) * 2 * C * Kp);
+    ch->X.ensure((size_t)C * m->N * 3);
+
+    RunCtx r;
+    r.ch = ch; r.C = C; r.s = s;
+    r.st = StateDev{ch->theta_cur.p, ch->theta_prop.p, ch->values_cur.p, ch->values_prop.p, ch->cur_sel.p,
+                    ch->slot_cur.p, ch->slot_prop.p, ch->comp_sel.p, ch->u_acc.p, ch->n_acc.p, ch->step.p, ch->L.p,
+                    ch->mu.p};
+    r.rng = RngDev{io->seed, io->chain_id_offset, io->u_comp, io->z, io->u_acc};
+    r.lg = LogDev{io->log_component, io->log_accepted, io->log_values, io->log_theta};
+
+    ICP_CUDA(cudaEventRecord(ch->ev0, s));
+    ICP_CUDA(cudaMemcpyAsync(ch->theta_cur.p, theta0_dev, sizeof(double) * (size_t)C * Lt, cudaMemcpyDeviceToDevice, s));
+    k_chain_init<<<(C + 127) / 128, 128, 0, s>>>(C, r.st);
+    ICP_CUDA(cudaGetLastError());
+    {
+        size_t smem_p = sizeof(double) * ((size_t)2 * Kp + (size_t)Kp * Kp);
+        ICP_REQUIRE(smem_p <= 227 * 1024, "rank too large for the propose kernel");
+        ICP_CUDA(cudaFuncSetAttribute(k_chain_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    }
+    // state of theta0: log-values + posteriors of every ICP component (state 0)
+    enqueue_state_eval(r, ch->theta_cur.p, ch->values_cur.p, ch->slot_cur.p);
+
+    // launches per step, for the report
+    int per_step = 0;
+    int steps_done = 0;
+    if (n_steps > 0) {
+        // first step eagerly: sizes every workspace (allocation is illegal during capture)
+        enqueue_step(r);
+        steps_done = 1;
+    }
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (ch->use_graph && !g_prof && n_steps - steps_done >= 2) {
+        ICP_CUDA(cudaStreamSynchronize(s));
+        cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            bool ok = true;
+            try {
+                enqueue_step(r);
+            } catch (...) {
+                ok = false;
+            }
+            e = cudaStreamEndCapture(s, &graph);
+            if (!ok || e != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                graph = nullptr;
+                cudaGetLastError();
+            } else {
+                size_t nn = 0;
+                cudaGraphGetNodes(graph, nullptr, &nn);
+                std::vector<cudaGraphNode_t> nodes(nn);
+                cudaGraphGetNodes(graph, nodes.data(), &nn);
+                for (size_t i = 0; i < nn; i++) {
+                    cudaGraphNodeType ty;
+                    if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) per_step++;
+                }
+                if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { exec = nullptr; cudaGetLastError(); }
+            }
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (exec) {
+        for (; steps_done < n_steps; steps_done++) ICP_CUDA(cudaGraphLaunch(exec, s));
+    } else {
+        for (; steps_done < n_steps; steps_done++) enqueue_step(r);
+    }
+    if (io->theta_final)
+        ICP_CUDA(cudaMemcpyAsync(io->theta_final, ch->theta_cur.p, sizeof(double) * (size_t)C * Lt, cudaMemcpyDeviceToDevice, s));
+    if (io->n_accepted)
+        ICP_CUDA(cudaMemcpyAsync(io->n_accepted, ch->n_acc.p, sizeof(long long) * (size_t)C, cudaMemcpyDeviceToDevice, s));
+    ICP_CUDA(cudaEventRecord(ch->ev1, s));
+    ch->last_launches = (int64_t)per_step * n_steps;
+    ch->last_per_step = per_step;
+    if (!async || exec) {
+        ICP_CUDA(cudaStreamSynchronize(s));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ch->ev0, ch->ev1);
+        ch->last_ms = ms;
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+}
+
+}  // namespace
+
+extern "C" int32_t icp_chain_run_device(icp_chain c, int32_t C, int32_t n_steps, const double *theta0_dev,
+                                        const icp_chain_io *io_dev, int32_t async) {
+    icp_ctx _ctx = c ? c->model->ctx : nullptr;
+    try {
+        ICP_REQUIRE(_ctx != nullptr, "null handle");
+        CtxLock lock(_ctx);
+        chain_run_device(c, C, n_steps, theta0_dev, io_dev, async != 0);
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+extern "C" int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const double *theta0, const icp_chain_io *io) {
+    icp_ctx _ctx = c ? c->model->ctx : nullptr;
+    try {
+        ICP_REQUIRE(_ctx != nullptr, "null handle");
+        ICP_REQUIRE(theta0 && io, "null argument");
+        CtxLock lock(_ctx);
+        icp_model m = c->model;
+        cudaStream_t s = _ctx->stream;
+        const int K = m->K, Lt = K + kTheta0;
+        ICP_REQUIRE(C >= 1 && C <= c->max_chains, "C must be in [1, max_chains]");
+        size_t rec = (size_t)n_steps * C;
+        DevBuf<double> d_theta0, d_final;
+        DevBuf<long long> d_nacc;
+        d_theta0.upload(theta0, (size_t)C * Lt, s);
+        icp_chain_io dio = *io;
+        bool host_rng = io->u_comp || io->z || io->u_acc;
+        if (host_rng) {
+            ICP_REQUIRE(io->u_comp && io->z && io->u_acc, "u_comp, z and u_acc must be given together");
+            c->h_u_comp.upload(io->u_comp, rec, s); dio.u_comp = c->h_u_comp.p;
+            c->h_z.upload(io->z, rec * K, s); dio.z = c->h_z.p;
+            c->h_u_acc.upload(io->u_acc, rec, s); dio.u_acc = c->h_u_acc.p;
+        }
+        if (io->log_component) { c->h_log_comp.ensure(rec); dio.log_component = c->h_log_comp.p; }
+        if (io->log_accepted) { c->h_log_acc.ensure(rec); dio.log_accepted = c->h_log_acc.p; }
+        if (io->log_values) { c->h_log_values.ensure(3 * rec); dio.log_values = c->h_log_values.p; }
+        if (io->log_theta) { c->h_log_theta.ensure(rec * Lt); dio.log_theta = c->h_log_theta.p; }
+        if (io->theta_final) { d_final.alloc((size_t)C * Lt); dio.theta_final = d_final.p; }
+        if (io->n_accepted) { d_nacc.alloc(C); dio.n_accepted = (int64_t *)d_nacc.p; }
+        chain_run_device(c, C, n_steps, d_theta0.p, &dio, false);
+        auto dl = [&](void *h, const void *d, size_t bytes) {
+            if (h && bytes) ICP_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
+        };
+        dl(io->log_component, c->h_log_comp.p, sizeof(int) * rec);
+        dl(io->log_accepted, c->h_log_acc.p, rec);
+        dl(io->log_values, c->h_log_values.p, sizeof(double) * 3 * rec);
+        dl(io->log_theta, c->h_log_theta.p, sizeof(double) * rec * Lt);
+        dl(io->theta_final, d_final.p, sizeof(double) * (size_t)C * Lt);
+        dl(io->n_accepted, d_nacc.p, sizeof(long long) * (size_t)C);
+        ICP_CUDA(cudaStreamSynchronize(s));
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+extern "C" int32_t icp_chain_last_run_stats(icp_chain c, double *device_ms, int64_t *kernel_launches) {
+    if (!c) return ICP_ERR_INVALID_ARGUMENT;
+    if (device_ms) *device_ms = c->last_ms;
+    if (kernel_launches) *kernel_launches = c->last_launches;
+    return ICP_OK;
+}
+
+// Philox block exactly as the chain runner draws it (integer-exact check against the oracle)
+__global__ void k_debug_philox(unsigned long long seed, unsigned long long chain, unsigned int step, unsigned int block,
+                               unsigned int *out) {
+    uint4 r = chain_philox(seed, chain, step, block);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+extern "C" int32_t icp_debug_philox(icp_ctx ctx, uint64_t seed, uint64_t chain, uint32_t step, uint32_t block,
+                                    uint32_t out[4]) {
+    icp_ctx _ctx = ctx;
+    try {
+        ICP_REQUIRE(ctx && out, "null argument");
+        CtxLock lock(ctx);
+        DevBuf<unsigned int> d;
+        d.alloc(4);
+        k_debug_philox<<<1, 1, 0, ctx->stream>>>(seed, chain, step, block, d.p);
+        ICP_CUDA(cudaGetLastError());
+        ICP_CUDA(cudaMemcpyAsync(out, d.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        ICP_CUDA(cudaStreamSynchronize(ctx->stream));
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+extern "C" const char *icp_stage_name(int32_t stage) {
+    static const char *names[ST_COUNT] = {"propose", "reconstruct", "closest_point_static", "bvh_refit",
+                                          "nearest_dynamic", "observations", "posterior_build", "cholesky_solve",
+                                          "eval_reduce", "accept", "other"};
+    return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "";
+}
+
+extern "C" int32_t icp_chain_profile(icp_chain c, int32_t C, int32_t n_steps, const double *theta0, uint64_t seed,
+                                     double *stage_ms, int64_t *stage_launches) {
+    icp_ctx _ctx = c ? c->model->ctx : nullptr;
+    Profiler prof;
+    try {
+        ICP_REQUIRE(_ctx != nullptr, "null handle");
+        ICP_REQUIRE(theta0 && stage_ms && stage_launches, "null argument");
+        static_assert(ST_COUNT == ICP_N_STAGES, "stage table out of sync with the header");
+        CtxLock lock(_ctx);
+        cudaStream_t s = _ctx->stream;
+        const int Lt = c->model->K + kTheta0;
+        DevBuf<double> d_theta0;
+        d_theta0.upload(theta0, (size_t)C * Lt, s);
+        icp_chain_io io{};
+        io.seed = seed;
+        // warm-up (sizes the workspaces), then the profiled run
+        chain_run_device(c, C, n_steps > 2 ? 2 : n_steps, d_theta0.p, &io, false);
+        g_prof = &prof;
+        chain_run_device(c, C, n_steps, d_theta0.p, &io, false);
+        g_prof = nullptr;
+        ICP_CUDA(cudaStreamSynchronize(s));
+        prof.collect();
+        for (int i = 0; i < ST_COUNT; i++) { stage_ms[i] = prof.ms[i]; stage_launches[i] = prof.launches[i]; }
+        return ICP_OK;
+    } catch (...) {
+        g_prof = nullptr;
+        prof.collect();
+        return translate_exception(_ctx);
+    }
+}

@@ -1,0 +1,132 @@
+// debug.cu - profiling support: per-stage CUDA-event timers and FP64 peak micro-benchmarks
+// (the roofline denominators bench.py reports for the FP64 kernels; MEASURED_PEAKS.json only
+// carries HBM bandwidth and bf16 tensor throughput).
+#include "icp_internal.h"
+
+namespace icp {
+
+thread_local Profiler *g_prof = nullptr;
+
+ProfScope::ProfScope(int stage, cudaStream_t stream) : s(stream) {
+    if (!g_prof) return;
+    Profiler::Rec r;
+    r.stage = stage;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, s);
+    idx = (int)g_prof->recs.size();
+    g_prof->recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0 && g_prof) cudaEventRecord(g_prof->recs[idx].e1, s);
+}
+void Profiler::collect() {
+    for (auto &r : recs) {
+        float ms_ = 0;
+        if (cudaEventElapsedTime(&ms_, r.e0, r.e1) == cudaSuccess) { ms[r.stage] += ms_; launches[r.stage]++; }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    recs.clear();
+}
+
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters) {
+    double a[8], x = 1.0 + 1e-9 * threadIdx.x, y = 1e-9;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = fma(a[i], x, y);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    if (s == 12345.678) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) k_dmma_peak(double *out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = 0.0;
+    double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9 * (threadIdx.x + 1);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace icp
+
+using namespace icp;
+
+extern "C" int32_t icp_debug_fp64_peak(icp_ctx ctx, double out[2]) {
+    icp_ctx _ctx = ctx;
+    try {
+        ICP_REQUIRE(ctx && out, "null argument");
+        CtxLock lock(ctx);
+        cudaStream_t s = ctx->stream;
+        DevBuf<double> d;
+        d.alloc(4);
+        cudaEvent_t e0, e1;
+        ICP_CUDA(cudaEventCreate(&e0));
+        ICP_CUDA(cudaEventCreate(&e1));
+        const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+        for (int which = 0; which < 2; which++) {
+            double best = 0;
+            for (int rep = 0; rep < 4; rep++) {
+                ICP_CUDA(cudaEventRecord(e0, s));
+                if (which == 0) k_dfma_peak<<<blocks, threads, 0, s>>>(d.p, iters);
+                else k_dmma_peak<<<blocks, threads, 0, s>>>(d.p, iters);
+                ICP_CUDA(cudaGetLastError());
+                ICP_CUDA(cudaEventRecord(e1, s));
+                ICP_CUDA(cudaStreamSynchronize(s));
+                float ms = 0;
+                ICP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                double flops = which == 0 ? 2.0 * 8 * iters * (double)blocks * threads
+                                          : 2.0 * 256 * 8 * iters * (double)blocks * (threads / 32);
+                double tf = flops / (ms * 1e-3) / 1e12;
+                if (rep > 0 && tf > best) best = tf;
+            }
+            out[which] = best;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+extern "C" int32_t icp_debug_time_closest_point(icp_target t, int64_t nq, const double *q_dev, int32_t *tri_dev,
+                                                double *cp_dev, double *d2_dev, int32_t iters, double *ms) {
+    icp_ctx _ctx = t ? t->ctx : nullptr;
+    try {
+        ICP_REQUIRE(_ctx && q_dev && ms && nq > 0 && iters > 0, "bad argument");
+        CtxLock lock(_ctx);
+        cudaStream_t s = _ctx->stream;
+        NearestArgs a;
+        a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.nq = nq; a.q = q_dev;
+        a.out_prim = tri_dev; a.out_cp = cp_dev; a.out_d2 = d2_dev;
+        launch_nearest(a, s);
+        cudaEvent_t e0, e1;
+        ICP_CUDA(cudaEventCreate(&e0));
+        ICP_CUDA(cudaEventCreate(&e1));
+        ICP_CUDA(cudaEventRecord(e0, s));
+        for (int i = 0; i < iters; i++) launch_nearest(a, s);
+        ICP_CUDA(cudaEventRecord(e1, s));
+        ICP_CUDA(cudaStreamSynchronize(s));
+        float t_ms = 0;
+        ICP_CUDA(cudaEventElapsedTime(&t_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ms = t_ms / iters;
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}

@@ -1,0 +1,345 @@
+// icp_internal.h - internal structures and kernel launchers of libicpcuda.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/icpcuda.h"
+
+namespace icp {
+
+constexpr int kTheta0 = 10;  // theta = [s, t3, rot3, c3, alpha_K]
+
+inline int pad8(int k) { return (k + 7) & ~7; }
+
+// ---- error plumbing ---------------------------------------------------------------------------
+struct CudaError {
+    cudaError_t e;
+    const char *file;
+    int line;
+};
+#define ICP_CUDA(x)                                                          \
+    do {                                                                     \
+        cudaError_t _e = (x);                                                \
+        if (_e != cudaSuccess) throw icp::CudaError{_e, __FILE__, __LINE__}; \
+    } while (0)
+
+struct ArgError {
+    std::string msg;
+};
+#define ICP_REQUIRE(cond, msg)                 \
+    do {                                       \
+        if (!(cond)) throw icp::ArgError{msg}; \
+    } while (0)
+
+struct StatusError {
+    int32_t code;
+    std::string msg;
+};
+
+// RAII device buffer (cudaMalloc on the current device)
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            throw CudaError{e, __FILE__, __LINE__};
+        }
+        n = count;
+    }
+    void ensure(size_t count) {
+        if (count > n) alloc(count);
+    }
+    void upload(const T *h, size_t count, cudaStream_t s) {
+        ensure(count);
+        if (count) ICP_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+};
+
+// ---- per-stage device timing (CUDA events on the launching stream; enabled by icp_chain_profile) ----
+enum Stage {
+    ST_PROPOSE = 0, ST_RECONSTRUCT, ST_NEAREST_STATIC, ST_REFIT, ST_NEAREST_DYNAMIC, ST_OBSERVATIONS, ST_POSTERIOR_BUILD,
+    ST_CHOLESKY, ST_EVAL_REDUCE, ST_ACCEPT, ST_OTHER, ST_COUNT
+};
+struct Profiler {
+    struct Rec { int stage; cudaEvent_t e0, e1; };
+    std::vector<Rec> recs;
+    double ms[ST_COUNT] = {0};
+    long long launches[ST_COUNT] = {0};
+    void collect();  // after a stream synchronise: accumulates and frees the events
+};
+extern thread_local Profiler *g_prof;
+struct ProfScope {
+    int idx = -1;
+    cudaStream_t s;
+    ProfScope(int stage, cudaStream_t stream);
+    ~ProfScope();
+};
+
+// Bounding-volume hierarchy: static topology (LBVH, Karras 2012) + one set of child boxes per
+// instance. Internal nodes 0..n-2 (root 0); a child c >= 0 is an internal node, c < 0 is the
+// leaf slot ~c in Morton order; prim[slot] is the original primitive id.
+struct Bvh {
+    int n = 0;               // leaves (>= 2; a single primitive is duplicated)
+    int prim_kind = 0;       // 0 triangles, 1 points
+    DevBuf<int2> children;   // [n-1]
+    DevBuf<int> parent;      // [2n-1]: internal nodes then leaves (n-1+slot)
+    DevBuf<int> prim;        // [n]
+    DevBuf<float4> nodes;    // [instances][n-1][3] child boxes
+    DevBuf<float4> nodebox;  // scratch [instances][2n-1][2] full boxes (lo, hi)
+    DevBuf<int> counters;    // scratch [instances][n-1]
+    int instances = 0;
+    float slack = 0.f;
+};
+
+// builds the topology from reference positions (verts N x 3 on the device; tris T x 3 or nullptr for
+// a point BVH) and refits instance 0
+void bvh_build(Bvh &b, int prim_kind, int n_prims, const double *d_verts, const int *d_tris, double scale,
+               cudaStream_t s);
+// refits `instances` sets of boxes from vertex positions X[instance][N][3]
+void bvh_refit(Bvh &b, int instances, const double *d_X, int N, const int *d_tris, cudaStream_t s);
+
+struct NearestArgs {
+    // structure
+    const Bvh *bvh = nullptr;
+    const double *prim_data = nullptr;  // static: tri_data [slot][10] / vert_data [slot][4]; nullptr => dynamic
+    const double *X = nullptr;          // dynamic: vertex positions [instance][N][3]
+    const int *tris = nullptr;          // dynamic triangles
+    int N = 0;                          // vertices per instance (dynamic) / per query mesh (gather)
+    // queries: C x nq. Either gathered from a per-chain mesh (Xq + q_ids) or points (per chain or shared)
+    int C = 1;
+    int64_t nq = 0;
+    const double *q = nullptr;      // [nq][3] shared, or [C][nq][3] when q_per_chain
+    int q_per_chain = 0;
+    const double *Xq = nullptr;     // [C][Nq][3]
+    const int *q_ids = nullptr;     // [nq]
+    int Nq = 0;
+    // outputs [C][nq]
+    int *out_prim = nullptr;
+    int *out_feat = nullptr;
+    double *out_cp = nullptr;
+    double *out_d2 = nullptr;
+};
+void launch_nearest(const NearestArgs &a, cudaStream_t s);
+
+// ---- model kernels ---------------------------------------------------------------------------------
+struct ModelDev {  // plain device view, passed by value to kernels
+    int N, T, K, Kp;
+    const double *ref, *mean, *Q, *QT, *S;  // mean: mean deformation (3N)
+    const int *tris, *adj_off, *adj;
+    const uint8_t *boundary;
+};
+void launch_reconstruct(const ModelDev &m, int C, const double *d_theta, double *d_X, cudaStream_t s);
+void launch_vertex_normals(const ModelDev &m, int C, const double *d_X, double *d_normals, cudaStream_t s);
+void launch_gram(const ModelDev &m, double *d_G /*Kp x Kp*/, cudaStream_t s);
+void launch_scale_basis(int rows, int K, int Kp, const double *d_U, const double *d_var, double *d_Q, double *d_QT,
+                        cudaStream_t s);
+
+// ---- posterior / proposal kernels -------------------------------------------------------------------
+struct ObsDev {  // observation list of one ICP proposal for C chains, stride n per chain
+    int n;       // slots per chain (n_ids or n_tp)
+    int *vid;    // [C][n] reference vertex id (-1: filtered out)
+    double *F;   // [C][n][9] rows n/sd_n, t1/sd_t, t2/sd_t of the whitening frame
+    double *y;   // [C][n][3] F (y_i - mean_i)
+    int *nobs;   // [C]
+};
+struct ObsArgs {
+    ModelDev m;
+    icp_proposal_params prm;
+    int C;
+    const double *theta;   // [C][K+10]
+    const double *X;       // [C][N][3]
+    // model sampling: closest points of the sampled vertices on the target
+    const int *ids;        // [n]
+    const double *cp;      // [C][n][3]
+    const uint8_t *cp_on_boundary;  // [C][n] or nullptr
+    // target sampling: nearest current-mesh vertex per target point
+    const double *tp;      // [n][3]
+    const int *near_vid;   // [C][n]
+    int iso;               // 1: isotropic noise sigma2 (deterministic ICP), frame = I / sqrt(sigma2)
+    double iso_sigma2;
+};
+void launch_observations(const ObsArgs &a, const ObsDev &o, cudaStream_t s);
+// M = I + sum_i (F_i Q_i)^T (F_i Q_i) (lower + upper, Kp x Kp, identity on the padding), b = sum (F_i Q_i)^T y_i
+void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, cudaStream_t s);
+// in: M (C x Kp x Kp), b (C x Kp). out: L (lower Cholesky factor, C x Kp x Kp), mu = M^-1 b, status (0 ok)
+// out_slot (nullable): chain c writes L / mu at index out_slot[c] instead of c
+void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
+                           const int *d_out_slot, int *d_status, cudaStream_t s);
+// alpha' = alpha + step (S (mu + L^-T z) - alpha); L/mu addressed through per-chain slot indices
+void launch_propose(const ModelDev &m, int C, double step, const double *d_theta, const double *d_z,
+                    const double *d_L, const double *d_mu, const int *d_slot, double *d_theta_out, cudaStream_t s);
+// -1/2 (K ln 2pi + |L^T (alpha_c - mu)|^2), -inf unless only alpha changed
+void launch_log_transition(int C, int K, int Kp, double step, const double *d_from, const double *d_to,
+                           const double *d_L, const double *d_mu, const int *d_slot, double *d_out, cudaStream_t s);
+
+// ---- evaluator kernels ------------------------------------------------------------------------------
+struct EvalReduceArgs {
+    icp_evaluator_params prm;
+    int C, K;
+    const double *theta;        // [C][K+10]
+    // model -> target distances (squared) [C][n_m2t], optional boundary flags of the hit
+    int n_m2t;
+    const double *d2_m2t;
+    const uint8_t *skip_m2t;
+    // target -> model
+    int n_t2m;
+    const double *d2_t2m;
+    const uint8_t *skip_t2m;
+    double *values;             // [C][3] product, prior, distance
+    int *status;                // [C] or nullptr
+};
+void launch_eval_reduce(const EvalReduceArgs &a, cudaStream_t s);
+void launch_prior(int C, int K, const double *d_theta, double *d_out, cudaStream_t s);
+// flags[c][i] = table[prim[c][i]]
+void launch_lookup_flags(int64_t n, const int *d_prim, const uint8_t *d_table, int table_n, uint8_t *d_flags,
+                         cudaStream_t s);
+
+}  // namespace icp
+
+// ---- handles ------------------------------------------------------------------------------------
+struct icp_ctx_s {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    std::string device_name;
+};
+
+struct icp_model_s {
+    icp_ctx ctx = nullptr;
+    int N = 0, T = 0, K = 0, Kp = 0;  // Kp = K padded to a multiple of 8
+    icp::DevBuf<double> ref;          // N x 3
+    icp::DevBuf<double> mean;         // 3N: mean deformation
+    icp::DevBuf<double> Q;            // 3N x Kp row-major, scaled basis, zero padded
+    icp::DevBuf<double> QT;           // Kp x 3N
+    icp::DevBuf<double> S;            // Kp x Kp, Appendix A5 constant (identity on the padding)
+    icp::DevBuf<int> tris;            // T x 3
+    icp::DevBuf<int> adj_off, adj;    // vertex -> triangles CSR (ascending triangle id)
+    icp::DevBuf<uint8_t> boundary;    // N
+    bool has_boundary = false;
+    std::vector<uint8_t> h_boundary;
+    std::vector<double> h_mean_def;
+    double scale = 1.0;               // max |coordinate| of the reference mesh (box slack)
+    icp::Bvh tri_bvh, vert_bvh;       // topology from the reference mesh, boxes refit per chain
+    icp::ModelDev dev() const {
+        return icp::ModelDev{N, T, K, Kp, ref.p, mean.p, Q.p, QT.p, S.p, tris.p, adj_off.p, adj.p, boundary.p};
+    }
+    // scratch for primitive calls (guarded by mu)
+    icp::DevBuf<double> s_theta, s_X, s_q, s_d;
+    icp::DevBuf<int> s_i;
+};
+
+struct icp_target_s {
+    icp_ctx ctx = nullptr;
+    int Nt = 0, Tt = 0;
+    icp::DevBuf<double> verts;      // Nt x 3
+    icp::DevBuf<int> tris;          // Tt x 3
+    icp::DevBuf<double> tri_data;   // [leaf slot][10]: a b c (9 doubles) + pad, Morton order
+    icp::DevBuf<double> vert_data;  // [leaf slot][4]: xyz + pad, Morton order
+    icp::DevBuf<uint8_t> boundary;  // Nt
+    bool has_boundary = false;
+    std::vector<uint8_t> h_boundary;
+    icp::Bvh tri_bvh, vert_bvh;
+    icp::DevBuf<double> s_q, s_d;
+    icp::DevBuf<int> s_i;
+};
+
+namespace icp {
+
+// per-batch workspace of the correspondence + posterior pipeline of one ICP proposal
+struct PosteriorWork {
+    int C = 0;
+    DevBuf<double> X;        // [C][N][3]
+    DevBuf<double> cp, d2;   // [C][n][3], [C][n]
+    DevBuf<int> prim;        // [C][n]
+    DevBuf<uint8_t> flags;   // [C][n]
+    DevBuf<int> vid;
+    DevBuf<double> F, y;
+    DevBuf<int> nobs;
+    DevBuf<double> M, b;     // [C][Kp*Kp], [C][Kp]
+    DevBuf<int> status;
+};
+
+}  // namespace icp
+
+struct icp_proposal_s {
+    icp_model model = nullptr;
+    icp_target target = nullptr;
+    icp_proposal_params prm{};
+    int n_ids = 0, n_tp = 0;
+    icp::DevBuf<int> ids;     // n_ids
+    icp::DevBuf<double> tp;   // n_tp x 3
+    // posterior cache (the reference's Memoize(icpPosterior, 20)): theta bytes -> slot
+    int cache_slots = 0;
+    std::unordered_map<std::string, int> cache_map;
+    std::vector<std::string> slot_key;
+    std::vector<int> slot_nobs, slot_status;
+    int cache_next = 0;
+    icp::DevBuf<double> cache_L, cache_mu, cache_M;  // [slots][Kp*Kp], [slots][Kp], [slots][Kp*Kp]
+    icp::PosteriorWork work;
+    icp::DevBuf<double> s_theta, s_theta2, s_z, s_out;
+    icp::DevBuf<int> s_slot;
+};
+
+namespace icp {
+struct EvalWork {
+    DevBuf<double> X, cp_m2t, d2_m2t, cp_t2m, d2_t2m;
+    DevBuf<int> prim;
+    DevBuf<uint8_t> skip_m2t, skip_t2m;
+};
+}  // namespace icp
+
+struct icp_evaluator_s {
+    icp_model model = nullptr;
+    icp_target target = nullptr;
+    icp_evaluator_params prm{};
+    int n_ids = 0, n_tp = 0;
+    icp::DevBuf<int> ids;
+    icp::DevBuf<double> tp;
+    icp::EvalWork work;
+    icp::DevBuf<double> s_theta, s_values;
+    icp::DevBuf<int> s_status;
+};
+
+namespace icp {
+// correspondence + posterior pipeline: L / mu (at out_slot[c] or c) for C parameter vectors on the device.
+// d_X: transformed meshes [C][N][3] if the caller already has them, else nullptr.
+void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const double *d_X, PosteriorWork &w, double *d_L,
+                        double *d_mu, const int *d_out_slot, cudaStream_t s);
+// distance evaluator pipeline: values [C][3] = {product, prior, distance}
+void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_theta, const double *d_X, double *d_values,
+                        int *d_status, cudaStream_t s);
+// RAII: selects the context device, serialises calls on the context
+struct CtxLock {
+    std::unique_lock<std::mutex> lk;
+    explicit CtxLock(icp_ctx c);
+};
+int32_t translate_exception(icp_ctx ctx);  // call inside catch (...)
+void set_error(icp_ctx ctx, const std::string &msg);
+}  // namespace icp

@@ -1,0 +1,256 @@
+/*
+ * icpcuda.h - C ABI of libicpcuda.so, the B200-native (sm_100a) hot path of
+ * unibas-gravis/icp-proposal: closest-point ICP proposal + likelihood evaluators inside the
+ * Metropolis-Hastings registration loop.
+ *
+ * This is the drop-in boundary: the entry points below are what a Scala/Panama (or JNI) binding of
+ * the reference's L2 classes would bind. Each group cites the reference interface it replaces;
+ * paths are relative to src/main/scala of the reference. INTEGRATION.md shows the Scala side.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, opaque handles, no exceptions, no callbacks.
+ *  - every function returns int32_t: 0 = ICP_OK, negative = error (icp_last_error gives the text).
+ *  - -inf / NaN in outputs are VALUES, not errors (logTransitionProbability legitimately returns
+ *    -inf, NonRigidIcpProposal.scala:73).
+ *  - all floating-point data is FP64, row-major. Host buffers unless the name ends in _device.
+ *    The library copies what it keeps; caller buffers are only read/written during the call.
+ *  - theta (ModelFittingParameters.allParameters, ModelFittingParameters.scala:64):
+ *        [ s | tx ty tz | phi theta psi | cx cy cz | alpha_0 .. alpha_{K-1} ]     length K + 10
+ *  - "C" is the number of chains (parameter vectors) in a batched call.
+ *  - There is no CPU fallback: every compute entry point runs CUDA kernels on the context's device
+ *    and fails with ICP_ERR_CUDA when that is impossible.
+ *  - Handles are safe to use from several host threads; calls on one handle serialise.
+ */
+#ifndef ICPCUDA_H
+#define ICPCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICP_OK 0
+#define ICP_ERR_INVALID_ARGUMENT (-1)
+#define ICP_ERR_CUDA (-2)
+#define ICP_ERR_OUT_OF_MEMORY (-3)
+#define ICP_ERR_EMPTY_SET (-4)   /* CollectiveAverage...Evaluator.scala:51,63 `filteredDists.max` on an empty list */
+#define ICP_ERR_NOT_POSITIVE_DEFINITE (-5)
+
+typedef struct icp_ctx_s *icp_ctx;
+typedef struct icp_model_s *icp_model;
+typedef struct icp_target_s *icp_target;
+typedef struct icp_proposal_s *icp_proposal;
+typedef struct icp_evaluator_s *icp_evaluator;
+typedef struct icp_chain_s *icp_chain;
+
+/* ---- (1) context --------------------------------------------------------------------------- */
+int32_t icp_ctx_create(int32_t device, icp_ctx *out);
+int32_t icp_ctx_destroy(icp_ctx ctx);
+/* copies the last error text of this context (or of the calling thread when ctx == NULL) */
+int32_t icp_last_error(icp_ctx ctx, char *buf, size_t n);
+/* library / device identification for logs: "icpcuda 0.1 sm_100a <device name>" */
+int32_t icp_version(icp_ctx ctx, char *buf, size_t n);
+
+/* ---- (2) model: StatisticalMeshModel (read at apps/femur/LoadTestData.scala:34-35) ---------- */
+/* ref_xyz N x 3, mean_def 3N (NULL = zero mean deformation), basis 3N x K unscaled U,
+ * variance K, tris T x 3. Q = U diag(sqrt(variance)) is formed on the device. */
+int32_t icp_model_create(icp_ctx ctx, int32_t N, int32_t T, int32_t K, const double *ref_xyz,
+                         const double *mean_def, const double *basis, const double *variance,
+                         const int32_t *tris, icp_model *out);
+int32_t icp_model_destroy(icp_model m);
+int32_t icp_model_rank(icp_model m, int32_t *K);
+
+/* ---- (3) target: TriangleMesh3D + its lazily built query structures ------------------------- */
+/* builds on the device: triangle BVH (operations.closestPointOnSurface), vertex BVH
+ * (pointSet.findClosestPoint), boundary table (operations.pointIsOnBoundary) */
+int32_t icp_target_create(icp_ctx ctx, int32_t Nt, int32_t Tt, const double *xyz, const int32_t *tris,
+                          icp_target *out);
+int32_t icp_target_destroy(icp_target t);
+
+/* ---- (4) primitives ------------------------------------------------------------------------- */
+/* target.operations.closestPointOnSurface(q).point (NonRigidIcpProposal.scala:97,
+ * IndependentPointDistanceEvaluator.scala:43, CollectiveAverage...:45, IcpBasedSurfaceFitting.scala:73,
+ * RegistrationComparison.scala:35). tri: closest triangle (ties: lowest index), feature: 0 vertex,
+ * 1 edge, 2 face interior, cp nq x 3, d2 squared distance. Any output may be NULL. */
+int32_t icp_closest_point_surface(icp_target t, int64_t nq, const double *q, int32_t *tri,
+                                  int32_t *feature, double *cp, double *d2);
+/* same with q / outputs in device memory (bench "value": inputs resident in HBM) */
+int32_t icp_closest_point_surface_device(icp_target t, int64_t nq, const double *q_dev, int32_t *tri_dev,
+                                         double *cp_dev, double *d2_dev);
+/* target.pointSet.findClosestPoint(q).id (NonRigidIcpProposal.scala:98, CollectiveAverage...:46) */
+int32_t icp_closest_vertex(icp_target t, int64_t nq, const double *q, int32_t *id, double *d2);
+/* target.operations.pointIsOnBoundary for every vertex (NonRigidIcpProposal.scala:99) */
+int32_t icp_target_boundary_flags(icp_target t, uint8_t *flags /* Nt */);
+/* ModelFittingParameters.transformedMesh (ModelFittingParameters.scala:108-110): xyz C x N x 3 */
+int32_t icp_reconstruct(icp_model m, int32_t C, const double *theta, double *xyz);
+/* transformedMesh(theta).vertexNormals (NonRigidIcpProposal.scala:100,120): normals C x N x 3 */
+int32_t icp_vertex_normals(icp_model m, int32_t C, const double *theta, double *normals);
+/* modelSample.operations.closestPointOnSurface (IndependentPointDistanceEvaluator.scala:51,
+ * CollectiveAverage...:57, MeshMetrics.hausdorffDistance): the same nq query points against each
+ * of the C transformed model meshes. Outputs C x nq (x 3). */
+int32_t icp_model_closest_point_surface(icp_model m, int32_t C, const double *theta, int64_t nq,
+                                        const double *q, int32_t *tri, int32_t *feature, double *cp,
+                                        double *d2);
+/* currentMesh.pointSet.findClosestPoint (NonRigidIcpProposal.scala:118): ids C x nq */
+int32_t icp_model_closest_vertex(icp_model m, int32_t C, const double *theta, int64_t nq, const double *q,
+                                 int32_t *id, double *d2);
+/* model.referenceMesh boundary table (currentMesh.operations.pointIsOnBoundary, :119) */
+int32_t icp_model_boundary_flags(icp_model m, uint8_t *flags /* N */);
+
+/* ---- (5) NonRigidIcpProposal (api/sampling/proposals/NonRigidIcpProposal.scala:30-153) ------ */
+#define ICP_MODEL_SAMPLING 0    /* api/other/IcpProjectionDirection.scala */
+#define ICP_TARGET_SAMPLING 1
+
+typedef struct {
+    double step_length;         /* stepLength */
+    double tangential_noise;    /* tangentialNoise: std-dev in the tangent plane */
+    double noise_along_normal;  /* noiseAlongNormal: std-dev along the vertex normal */
+    int32_t direction;          /* ICP_MODEL_SAMPLING | ICP_TARGET_SAMPLING */
+    int32_t boundary_aware;     /* boundaryAware */
+} icp_proposal_params;
+
+/* model_point_ids: decimatedModel.referenceMesh.pointSet.pointIds (:94; they index the FULL mesh,
+ * SURVEY Appendix B1). target_points: decimatedTarget.pointSet.points (:117). The host passes the
+ * lists it got from Scalismo's (VTK) decimation, so parity does not depend on VTK. */
+int32_t icp_proposal_create(icp_model m, icp_target t, const icp_proposal_params *params,
+                            const int32_t *model_point_ids, int32_t n_ids, const double *target_points,
+                            int32_t n_tp, icp_proposal *out);
+int32_t icp_proposal_destroy(icp_proposal p);
+
+/* icpPosterior (:88-153): posterior of the GP given the closest-point correspondences of theta.
+ * mu C x K posterior mean coefficients; M C x K x K (= I + sum Q_i^T Sigma_i^-1 Q_i, the inverse
+ * coefficient-space covariance; NULL to skip); n_obs C (observations that survived the boundary
+ * filter; NULL to skip). */
+int32_t icp_posterior(icp_proposal p, int32_t C, const double *theta, double *mu, double *M, int32_t *n_obs);
+/* propose (:53-68). z: C x K standard normals drawn by the caller's RNG (posterior.sample(), :55).
+ * theta_out C x (K+10). alpha' = alpha + step (S (mu + W z) - alpha), W W^T = M^-1 (W = L^-T). */
+int32_t icp_propose(icp_proposal p, int32_t C, const double *theta, const double *z, double *theta_out);
+/* logTransitionProbability(from, to) (:71-85): out C. -inf unless only alpha changed (:72-74). */
+int32_t icp_log_transition(icp_proposal p, int32_t C, const double *from, const double *to, double *out);
+/* drops the per-handle posterior cache (the reference's Memoize(icpPosterior, 20), :49) */
+int32_t icp_proposal_clear_cache(icp_proposal p);
+
+/* RandomShapeUpdateProposal.logTransitionProbability (proposals/RandomShapeUpdateProposal.scala:38-45)
+ * and GaussianAxis{Rotation,Translation}Proposal (proposals/PoseProposals.scala:47-62,81-89) are
+ * O(K) host arithmetic in the reference; they exist on the device inside icp_chain_run only. */
+
+/* model.posterior(corr, sigma2).mean + model.coefficients + step of the deterministic ICP
+ * (api/other/IcpBasedSurfaceFitting.scala:55-92), identity pose: alpha C x K -> alpha_out C x K.
+ * direction per call (the reference flips an unseeded coin, :67, so the caller supplies it). */
+int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t direction, const int32_t *model_point_ids,
+                              int32_t n_ids, const double *target_points, int32_t n_tp, double sigma2,
+                              double step_length, int32_t C, const double *alpha, double *alpha_out);
+
+/* ---- (6) evaluators (api/sampling/evaluators/*.scala, ProductEvaluators.scala) -------------- */
+#define ICP_EVAL_ACCEPT_ALL 0     /* AcceptAllEvaluator.scala:22-28 */
+#define ICP_EVAL_INDEPENDENT 1    /* IndependentPointDistanceEvaluator.scala:27-67, Gaussian(p0 = mean, p1 = sd) */
+#define ICP_EVAL_HAUSDORFF 2      /* HausdorffDistanceEvaluator.scala:25-36, Exponential(p0 = rate) */
+#define ICP_EVAL_COLLECTIVE 3     /* CollectiveAverageHausdorffDistanceBoundaryAwareEvaluator.scala:27-79,
+                                     Gaussian(p0 = mean, p1 = sd) on the average + Exponential(p2) on the max */
+#define ICP_MODEL_TO_TARGET 0     /* EvaluationModeType.scala */
+#define ICP_TARGET_TO_MODEL 1
+#define ICP_SYMMETRIC 2
+
+typedef struct {
+    int32_t kind;       /* ICP_EVAL_* */
+    int32_t mode;       /* ICP_MODEL_TO_TARGET | ICP_TARGET_TO_MODEL | ICP_SYMMETRIC */
+    int32_t use_prior;  /* 1: ProductEvaluator(ModelPriorEvaluator, distance) (ProductEvaluators.scala:44-47) */
+    int32_t reserved;
+    double p0, p1, p2;
+} icp_evaluator_params;
+
+/* model_point_ids = randomPointIdsOnModel, target_points = randomPointsOnTarget
+ * (IndependentPointDistanceEvaluator.scala:37-38); ignored by the Hausdorff evaluator, which uses
+ * every vertex of both meshes (MeshMetrics.hausdorffDistance). */
+int32_t icp_evaluator_create(icp_model m, icp_target t, const icp_evaluator_params *params,
+                             const int32_t *model_point_ids, int32_t n_ids, const double *target_points,
+                             int32_t n_tp, icp_evaluator *out);
+int32_t icp_evaluator_destroy(icp_evaluator e);
+/* computeLogValue / logValue for C parameter vectors. values: C x 3 = {product, prior, distance}
+ * (the keys of the evaluator map, ProductEvaluators.scala:49-53; prior = 0 when use_prior == 0).
+ * status: C (NULL to skip), ICP_OK or ICP_ERR_EMPTY_SET per chain (value is NaN then). */
+int32_t icp_eval_log_value(icp_evaluator e, int32_t C, const double *theta, double *values, int32_t *status);
+/* ModelPriorEvaluator.logValue (ModelPriorEvaluator.scala:28-30): out C */
+int32_t icp_eval_prior(icp_model m, int32_t C, const double *theta, double *out);
+/* RegistrationComparison.evaluateReconstruction2GroundTruth[BoundaryAware]
+ * (api/other/RegistrationComparison.scala:24-49): per chain {avg, hausdorff, avg_boundary_aware,
+ * max_boundary_aware} between transformedMesh(theta) and the target; out C x 4. */
+int32_t icp_registration_metrics(icp_model m, icp_target t, int32_t C, const double *theta, double *out);
+
+/* ---- (7) fused Metropolis-Hastings runner ---------------------------------------------------- */
+/* Scalismo MetropolisHastings.next + MixtureProposal, driven from
+ * api/sampling/SamplingRegistration.scala:52-85, as a device-resident loop over n_steps for C
+ * independent chains. */
+#define ICP_PROP_ICP 0
+#define ICP_PROP_RANDOM_SHAPE 1     /* RandomShapeUpdateProposal(sd) */
+#define ICP_PROP_ROTATION 2         /* GaussianAxisRotationProposal(sd, axis 0 roll/phi, 1 pitch/theta, 2 yaw/psi) */
+#define ICP_PROP_TRANSLATION 3      /* GaussianAxisTranslationProposal(sd, axis) */
+
+typedef struct {
+    int32_t kind;            /* ICP_PROP_* */
+    int32_t axis;            /* pose proposals */
+    double weight;           /* effective (flattened) mixture weight; normalised by the library */
+    double sd;               /* random-walk / pose std-dev */
+    icp_proposal proposal;   /* kind == ICP_PROP_ICP */
+} icp_component;
+
+int32_t icp_chain_create(icp_model m, icp_target t, const icp_component *components, int32_t n_components,
+                         icp_evaluator evaluator, int32_t max_chains, icp_chain *out);
+int32_t icp_chain_destroy(icp_chain c);
+
+typedef struct {
+    /* randomness: either counter-based on the device (Philox4x32-10 keyed by seed and the global
+     * chain id chain_id_offset + c, so results do not depend on how chains are sharded over GPUs)
+     * or supplied by the caller's RNG (all three non-NULL): u_comp [n_steps][C] picks the mixture
+     * component, z [n_steps][C][K] are the proposal's standard normals, u_acc [n_steps][C] is the
+     * acceptance uniform. */
+    uint64_t seed;
+    uint64_t chain_id_offset;
+    const double *u_comp;
+    const double *z;
+    const double *u_acc;
+    /* chain log, one record per step and chain in the layout of jsonLogFormat
+     * (api/sampling/loggers/JSONAcceptRejectLogger.scala:35,93-106); any pointer may be NULL.
+     * log_values: {product, prior, distance} of the state that is current after the step. */
+    int32_t *log_component;   /* [n_steps][C]   proposal index (-> generatedBy name) */
+    uint8_t *log_accepted;    /* [n_steps][C]   status */
+    double *log_values;       /* [n_steps][C][3] */
+    double *log_theta;        /* [n_steps][C][K+10] parameters of the current state after the step */
+    double *theta_final;      /* [C][K+10] */
+    int64_t *n_accepted;      /* [C] */
+} icp_chain_io;
+
+/* theta0 C x (K+10) (host). io buffers are host memory. */
+int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const double *theta0, const icp_chain_io *io);
+/* same with theta0 and every non-NULL io pointer in DEVICE memory; the run is enqueued on the
+ * context stream and synchronised before returning unless `async` != 0. */
+int32_t icp_chain_run_device(icp_chain c, int32_t C, int32_t n_steps, const double *theta0_dev,
+                             const icp_chain_io *io_dev, int32_t async);
+int32_t icp_ctx_synchronize(icp_ctx ctx);
+/* device time in milliseconds of the last icp_chain_run* on this chain (CUDA events on the
+ * library stream) and the number of kernels it launched */
+int32_t icp_chain_last_run_stats(icp_chain c, double *device_ms, int64_t *kernel_launches);
+
+/* ---- (8) introspection used by bench.py / tests ---------------------------------------------- */
+/* Philox4x32-10 block as the chain runner draws it: out[4] for (seed, chain, step, block) */
+int32_t icp_debug_philox(icp_ctx ctx, uint64_t seed, uint64_t chain, uint32_t step, uint32_t block, uint32_t out[4]);
+/* measured FP64 peaks of this device (TFLOP/s): out[0] = DFMA (CUDA cores), out[1] = DMMA m8n8k4 */
+int32_t icp_debug_fp64_peak(icp_ctx ctx, double out[2]);
+/* eager (graph-less) run of n_steps of the chain with every kernel class bracketed by CUDA events on
+ * the library stream: stage_ms[ICP_N_STAGES] summed device milliseconds, stage_launches[ICP_N_STAGES]
+ * number of launches. Stage names through icp_stage_name. theta0 is host memory, Philox RNG. */
+#define ICP_N_STAGES 11
+int32_t icp_chain_profile(icp_chain c, int32_t C, int32_t n_steps, const double *theta0, uint64_t seed,
+                          double *stage_ms, int64_t *stage_launches);
+const char *icp_stage_name(int32_t stage);
+/* closest-point traversal timed in isolation: average milliseconds per launch over `iters` launches of
+ * nq device-resident queries (CUDA events on the library stream, after one warm-up launch) */
+int32_t icp_debug_time_closest_point(icp_target t, int64_t nq, const double *q_dev, int32_t *tri_dev, double *cp_dev,
+                                     double *d2_dev, int32_t iters, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICPCUDA_H */

@@ -1,0 +1,421 @@
+"""GPU parity suite: every entry point of libicpcuda.so (called through the C ABI) against the CPU oracle
+on the same seeded inputs. Bit-exact for indices (modulo certified equidistant ties); 1e-5 relative
+(BASELINE.json north_star) - in practice far tighter - for distances, posterior means, log-likelihoods."""
+import numpy as np
+import pytest
+
+from conftest import random_theta
+from icp_proposal_b200 import _lib, core, synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5          # the tolerance BASELINE.json states
+TIGHT = 1e-9         # what FP64 on both sides actually delivers for well-conditioned quantities
+
+
+def _dev(ctx, m):
+    return core.Model(ctx, m["ref"], m["cells"], m["basis"], m["variance"]), core.Target(ctx, m["target"], m["target_cells"])
+
+
+def _orc(m):
+    return orc.Model(m["ref"], m["cells"], m["basis"], m["variance"]), orc.Mesh(m["target"], m["target_cells"])
+
+
+def _assert_closest_point_parity(verts, tris, q, got, want):
+    tri_g, feat_g, cp_g, d2_g = got
+    tri_o, feat_o, cp_o, d2_o = want
+    np.testing.assert_allclose(d2_g, d2_o, rtol=1e-12, atol=1e-22)
+    np.testing.assert_allclose(cp_g, cp_o, rtol=0, atol=1e-9)
+    diff = np.nonzero(tri_g != tri_o)[0]
+    # documented equidistant ties: a different triangle is acceptable only if the oracle itself certifies
+    # that it is at the same distance (shared edge / vertex)
+    for i in diff:
+        a, b, c = verts[tris[tri_g[i]]]
+        d2, _, _ = orc.point_triangle_d2(q[i], a, b, c)
+        assert abs(d2 - d2_o[i]) <= 1e-12 * max(d2_o[i], 1e-300), f"query {i}: not an equidistant tie"
+    assert len(diff) <= max(3, len(q) // 200)
+    same = tri_g == tri_o
+    assert np.array_equal(feat_g[same], feat_o[same])
+
+
+@pytest.mark.parametrize("which", ["near", "far", "vertices", "on_surface"])
+def test_closest_point_surface_vs_brute_force(ctx, femur, which):
+    verts, tris = femur["target"], femur["target_cells"]
+    tgt = core.Target(ctx, verts, tris)
+    mesh = orc.Mesh(verts, tris)
+    if which == "near":
+        q = synth.near_surface_queries(verts, tris, 20000)
+    elif which == "far":
+        q = synth.far_field_queries(verts, 20000)
+    elif which == "vertices":
+        q = verts.copy()             # exactly on vertices: maximal ties
+    else:
+        q = synth.near_surface_queries(verts, tris, 5000, sd=0.0)
+    _assert_closest_point_parity(verts, tris, q, tgt.closest_point_surface(q), mesh.closest_point(q, brute=True))
+    tgt.close()
+
+
+def test_closest_point_edge_cases(ctx):
+    # a single triangle, queries in all seven Voronoi regions + degenerate inputs
+    verts = np.array([[0., 0, 0], [2, 0, 0], [0, 2, 0]])
+    tris = np.array([[0, 1, 2]], np.int32)
+    tgt = core.Target(ctx, verts, tris)
+    q = np.array([[-1, -1, 3], [1, -1, .5], [.5, .5, 2], [3, 3, 0], [5, -1, 0], [-1, 1, 0], [-1, 5, 1.]])
+    got = tgt.closest_point_surface(q)
+    want = orc.Mesh(verts, tris).closest_point(q, brute=True)
+    _assert_closest_point_parity(verts, tris, q, got, want)
+    assert got[1].tolist() == [0, 1, 2, 1, 0, 1, 0]
+    # empty query list is a no-op; NaN query gives NaN, not a hang
+    assert tgt.closest_point_surface(np.zeros((0, 3)))[0].shape == (0,)
+    bad = tgt.closest_point_surface(np.array([[np.nan, 0, 0]]))
+    assert np.isnan(bad[3][0]) and bad[0][0] == -1
+    ids, d2 = tgt.closest_vertex(q)
+    io, do = orc.Mesh(verts, tris).closest_vertex(q, brute=True)
+    assert np.array_equal(ids, io) and np.allclose(d2, do, rtol=1e-14)
+    tgt.close()
+
+
+def test_invalid_arguments_are_reported(ctx):
+    verts = np.array([[0., 0, 0], [2, 0, 0], [0, 2, 0]])
+    with pytest.raises(_lib.IcpCudaError) as e:
+        core.Target(ctx, verts, np.array([[0, 1, 7]], np.int32))
+    assert e.value.code == _lib.ERR_INVALID_ARGUMENT and "out of range" in str(e.value)
+    with pytest.raises(_lib.IcpCudaError):
+        core.Target(ctx, np.array([[0., np.inf, 0], [2, 0, 0], [0, 2, 0]]), np.array([[0, 1, 2]], np.int32))
+
+
+def test_closest_vertex_and_boundary(ctx, open_twin):
+    tgt = core.Target(ctx, open_twin["target"], open_twin["target_cells"])
+    mesh = orc.Mesh(open_twin["target"], open_twin["target_cells"])
+    q = np.concatenate([synth.far_field_queries(open_twin["target"], 5000), open_twin["target"]])
+    ids, d2 = tgt.closest_vertex(q)
+    io, do = mesh.closest_vertex(q, brute=True)
+    assert np.array_equal(ids, io)
+    np.testing.assert_allclose(d2, do, rtol=1e-14, atol=1e-25)
+    assert np.array_equal(tgt.boundary_flags(), mesh.boundary_flags())
+    assert tgt.boundary_flags().any()
+    tgt.close()
+
+
+def test_reconstruct_normals_prior(ctx, twin101):
+    model, tgt = _dev(ctx, twin101)
+    om, _ = _orc(twin101)
+    rng = np.random.default_rng(0)
+    th = random_theta(twin101, rng, 7, pose=True)
+    th[3, 0] = 1.1     # scale
+    X = model.reconstruct(th)
+    nrm = model.vertex_normals(th)
+    for c in range(len(th)):
+        xo = om.transformed_mesh(th[c])
+        np.testing.assert_allclose(X[c], xo, rtol=0, atol=1e-10)
+        no = orc.Mesh(xo, twin101["cells"]).vertex_normals()
+        np.testing.assert_allclose(nrm[c], no, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(model.prior(th), [orc.eval_prior(101, t) for t in th], rtol=1e-13)
+    assert not model.boundary_flags().any()
+    model.close(); tgt.close()
+
+
+def test_dynamic_model_queries(ctx, twin31):
+    model, tgt = _dev(ctx, twin31)
+    om, _ = _orc(twin31)
+    rng = np.random.default_rng(1)
+    th = random_theta(twin31, rng, 4, pose=True)
+    q = np.concatenate([synth.near_surface_queries(twin31["target"], twin31["target_cells"], 3000),
+                        synth.far_field_queries(twin31["target"], 1000)])
+    tri, feat, cp, d2 = model.closest_point_surface(th, q)
+    ids, vd2 = model.closest_vertex(th, q)
+    for c in range(len(th)):
+        cur = orc.Mesh(om.transformed_mesh(th[c]), twin31["cells"])
+        # the device mesh differs from the oracle mesh by ~1e-13 (FMA contraction), so ties aside the
+        # distances agree to ~1e-11 relative rather than bit-exactly
+        to, fo, co, do = cur.closest_point(q, brute=True)
+        np.testing.assert_allclose(d2[c], do, rtol=1e-9, atol=1e-20)
+        np.testing.assert_allclose(cp[c], co, rtol=0, atol=1e-8)
+        assert (tri[c] == to).mean() > 0.995
+        io, vo = cur.closest_vertex(q, brute=True)
+        assert (ids[c] == io).mean() > 0.999
+        np.testing.assert_allclose(vd2[c], vo, rtol=1e-9)
+    model.close(); tgt.close()
+
+
+@pytest.mark.parametrize("direction", [_lib.MODEL_SAMPLING, _lib.TARGET_SAMPLING])
+@pytest.mark.parametrize("fixture", ["twin31", "femur100"])
+def test_icp_posterior_propose_transition(ctx, request, femur, direction, fixture):
+    if fixture == "twin31":
+        m = request.getfixturevalue("twin31")
+    else:
+        m = dict(ref=femur["ref"], cells=femur["cells"], target=femur["target"], target_cells=femur["target_cells"],
+                 **femur["gpmm_100"])
+    K = len(m["variance"])
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    rng = np.random.default_rng(7)
+    C = 3
+    th = random_theta(m, rng, C, pose=(fixture == "twin31"))
+    ids = np.arange(2 * K)
+    tp = m["target"][:: max(1, len(m["target"]) // (2 * K))][: 2 * K] + rng.normal(0, 0.1, (2 * K, 3))
+    gp = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, direction, True, ids, tp)
+    op = orc.IcpProposal(om, ot, 0.1, 10.0, 5.0, direction, True, ids, tp)
+    mu, M, n = gp.posterior(th)
+    z = rng.normal(size=(C, K))
+    prop0 = gp.propose(th, np.zeros((C, K)))
+    prop = gp.propose(th, z)
+    lt = gp.log_transition(th, prop)
+    lt_back = gp.log_transition(prop, th)
+    for c in range(C):
+        po = op.posterior(th[c])
+        assert n[c] == po["n"]
+        np.testing.assert_allclose(M[c], po["M"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(mu[c], po["mu"], rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose(mu[c], po["mu"], rtol=1e-7, atol=1e-9)
+        # deterministic part of the proposal vs the reference-structure oracle (rotated basis + full regression)
+        if K <= 51 or c == 0:
+            np.testing.assert_allclose(prop0[c], op.propose(th[c], np.zeros(K)), rtol=RTOL, atol=1e-8)
+            np.testing.assert_allclose(lt[c], op.log_transition(th[c], prop[c]), rtol=RTOL)
+        # stochastic part vs the closed-form oracle (same Cholesky factor W = L^-T)
+        np.testing.assert_allclose(prop[c], op.propose(th[c], z[c], closed_form=True), rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(lt[c], op.log_transition(th[c], prop[c], closed_form=True), rtol=TIGHT)
+        np.testing.assert_allclose(lt_back[c], op.log_transition(prop[c], th[c], closed_form=True), rtol=1e-7)
+        np.testing.assert_allclose(lt[c], -0.5 * (K * np.log(2 * np.pi) + z[c] @ z[c]), rtol=1e-5)
+    # guard: a pose change gives -inf (NonRigidIcpProposal.scala:72-74)
+    bad = prop.copy(); bad[:, 2] += 1e-3
+    assert np.all(gp.log_transition(th, bad) == -np.inf)
+    # covariance factor: W W^T = M^-1
+    if fixture == "twin31":
+        W = np.stack([gp.propose(th[:1], np.eye(K)[i][None])[0, 10:] - prop0[0, 10:] for i in range(K)], axis=1) / 0.1
+        # alpha' - alpha0' = step * S W e_i
+        np.testing.assert_allclose(W @ W.T, np.linalg.inv(M[0]), rtol=1e-5, atol=1e-9)
+    gp.close(); model.close(); tgt.close()
+
+
+def test_posterior_boundary_aware(ctx, open_twin):
+    """Boundary filtering on both sides (target boundary for model sampling, model boundary for target sampling)."""
+    m = open_twin
+    K = len(m["variance"])
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    rng = np.random.default_rng(9)
+    th = random_theta(m, rng, 2)
+    ids = np.arange(0, len(m["ref"]), 5)
+    tp = m["target"][::4]
+    for direction in (0, 1):
+        for aware in (True, False):
+            gp = core.IcpProposal(model, tgt, 0.5, 3.0, 1.0, direction, aware, ids, tp)
+            op = orc.IcpProposal(om, ot, 0.5, 3.0, 1.0, direction, aware, ids, tp)
+            mu, M, n = gp.posterior(th)
+            for c in range(len(th)):
+                po = op.posterior(th[c])
+                assert n[c] == po["n"]
+                np.testing.assert_allclose(M[c], po["M"], rtol=1e-9, atol=1e-12)
+                np.testing.assert_allclose(mu[c], po["mu"], rtol=1e-7, atol=1e-9)
+            if aware:
+                assert n.max() < (len(tp) if direction else len(ids))   # something was filtered
+            gp.close()
+    model.close(); tgt.close()
+
+
+def test_evaluators(ctx, twin31, open_twin):
+    m = twin31
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    rng = np.random.default_rng(3)
+    th = random_theta(m, rng, 5, pose=True)
+    ids = np.arange(124)
+    tp = m["target"][::13][:124]
+    for mode in (0, 1, 2):
+        ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, mode, True, 0.0, 2.0, 0.0, ids, tp)
+        v = ev.log_value(th)
+        for c in range(len(th)):
+            d = orc.eval_independent(om, ot, mode, 0.0, 2.0, ids, tp, th[c])
+            p = orc.eval_prior(31, th[c])
+            np.testing.assert_allclose(v[c], [p + d, p, d], rtol=TIGHT)
+        ev.close()
+    ev = core.Evaluator(model, tgt, _lib.EVAL_HAUSDORFF, 0, False, 100.0)
+    v = ev.log_value(th)
+    for c in range(len(th)):
+        d = orc.eval_hausdorff(om, ot, 100.0, th[c])
+        np.testing.assert_allclose(v[c], [d, 0.0, d], rtol=TIGHT)
+    ev.close()
+    ev = core.Evaluator(model, tgt, _lib.EVAL_ACCEPT_ALL)
+    assert np.all(ev.log_value(th)[:, 2] == 0.0)
+    ev.close(); model.close(); tgt.close()
+    # collective evaluator with boundary filtering + the cross-mesh lookup quirk, and its empty-set status
+    m = open_twin
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    th = random_theta(m, rng, 3)
+    ids = np.arange(0, len(m["ref"]), 7)
+    tp = m["target"][::9]
+    for mode in (0, 1, 2):
+        ev = core.Evaluator(model, tgt, _lib.EVAL_COLLECTIVE, mode, True, 0.1, 0.3, 1.0, ids, tp)
+        v, st = ev.log_value(th, with_status=True)
+        for c in range(len(th)):
+            d, so, _ = orc.eval_collective(om, ot, mode, 0.1, 0.3, 1.0, ids, tp, th[c])
+            assert st[c] == 0 and so == 0
+            np.testing.assert_allclose(v[c, 2], d, rtol=TIGHT)
+        ev.close()
+    ev = core.Evaluator(model, tgt, _lib.EVAL_COLLECTIVE, 0, True, 0.1, 0.3, 1.0, np.array([0]), tp)
+    v, st = ev.log_value(th, with_status=True)
+    assert np.all(st == _lib.ERR_EMPTY_SET) and np.isnan(v[:, 2]).all()
+    ev.close(); model.close(); tgt.close()
+
+
+def test_std_icp_iteration(ctx, femur):
+    m = dict(ref=femur["ref"], cells=femur["cells"], target=femur["target"], target_cells=femur["target_cells"], **femur["gpmm_50"])
+    K = 51
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    rng = np.random.default_rng(5)
+    alpha = rng.normal(0, 0.3, (2, K))
+    ids = rng.integers(0, 1622, 400)           # duplicates allowed (nearest vertices of surface samples)
+    tp = synth.near_surface_queries(m["target"], m["target_cells"], 400, sd=0.0)
+    for direction in (0, 1):
+        out = core.std_icp_iteration(model, tgt, direction, ids, tp, 1e-15, 1.0, alpha)
+        for c in range(2):
+            want = orc.std_icp_iteration(om, ot, direction, ids, tp, 1e-15, 1.0, alpha[c])
+            np.testing.assert_allclose(out[c], want, rtol=RTOL, atol=1e-7)
+    model.close(); tgt.close()
+
+
+def test_registration_metrics(ctx, twin31):
+    model, tgt = _dev(ctx, twin31)
+    om, ot = _orc(twin31)
+    th = random_theta(twin31, np.random.default_rng(2), 2)
+    got = core.registration_metrics(model, tgt, th)
+    for c in range(2):
+        x = om.transformed_mesh(th[c])
+        d = np.sqrt(ot.closest_point(x)[3])
+        back = np.sqrt(orc.Mesh(x, twin31["cells"]).closest_point(twin31["target"])[3])
+        np.testing.assert_allclose(got[c], [d.mean(), max(d.max(), back.max()), d.mean(), d.max()], rtol=1e-9)
+    model.close(); tgt.close()
+
+
+def _mixture(model, tgt, om, ot, K, ids, tp, dev=True):
+    mk = (lambda d: core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, d, True, ids, tp)) if dev else \
+         (lambda d: orc.IcpProposal(om, ot, 0.1, 10.0, 5.0, d, True, ids, tp))
+    pt, pm = mk(1), mk(0)
+    key = "proposal" if dev else "icp"
+    # IcpProposalRegistration.scala:70-72: 0.9 * (0.5 target-sampling + 0.5 model-sampling) + 0.1 * random walk(0.1)
+    return [{"kind": 0, "weight": 0.45, key: pt}, {"kind": 0, "weight": 0.45, key: pm}, {"kind": 1, "weight": 0.1, "sd": 0.1}]
+
+
+@pytest.mark.parametrize("evaluator", ["independent", "hausdorff"])
+def test_chain_matches_oracle_chain(ctx, twin31, evaluator):
+    """Device MH chains vs the oracle's chain (same mixture, same host-supplied randomness), step by step."""
+    m = twin31
+    K = 31
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    rng = np.random.default_rng(21)
+    ids, eids = np.arange(62), np.arange(124)
+    tp = m["target"][::26][:62]
+    comps_d = _mixture(model, tgt, om, ot, K, ids, tp, True)
+    comps_o = _mixture(model, tgt, om, ot, K, ids, tp, False)
+    if evaluator == "independent":
+        ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, 0, True, 0.0, 2.0, 0.0, eids, tp)
+        okind, oparams = orc.EVAL_INDEPENDENT, (0.0, 2.0)
+    else:
+        ev = core.Evaluator(model, tgt, _lib.EVAL_HAUSDORFF, 0, True, 100.0)
+        okind, oparams = orc.EVAL_HAUSDORFF, (100.0,)
+    C, n = 3, 40
+    th0 = random_theta(m, rng, C, alpha_sd=0.5)
+    u_comp, u_acc, z = rng.random((n, C)), rng.random((n, C)), rng.normal(size=(n, C, K))
+    chain = core.Chain(model, tgt, comps_d, ev, max_chains=8)
+    got = chain.run(th0, n, u_comp=u_comp, z=z, u_acc=u_acc)
+    for c in range(C):
+        want = orc.chain_run(om, ot, comps_o, True, okind, 0, oparams, eids, tp, th0[c], n, u_comp[:, c], z[:, c], u_acc[:, c],
+                             closed_form=True)
+        assert np.array_equal(got["component"][:, c], want["comp"])
+        assert np.array_equal(got["accepted"][:, c], want["accepted"])
+        np.testing.assert_allclose(got["values"][:, c], want["logv"], rtol=RTOL)
+        np.testing.assert_allclose(got["values"][:, c], want["logv"], rtol=1e-7)
+        np.testing.assert_allclose(got["theta"][:, c], want["theta"], rtol=0, atol=1e-7)
+        assert got["n_accepted"][c] == want["n_accepted"]
+        assert 0 < want["n_accepted"] < n
+    # a one-chain run gives the same chain (batching does not change results)
+    one = chain.run(th0[1:2], n, u_comp=u_comp[:, 1:2], z=z[:, 1:2], u_acc=u_acc[:, 1:2])
+    assert np.array_equal(one["theta"][:, 0], got["theta"][:, 1])
+    chain.close(); ev.close(); model.close(); tgt.close()
+
+
+def test_chain_with_pose_proposals(ctx, open_twin):
+    """BFM-style mixture: ICP + random walk + axis rotation/translation proposals, collective evaluator."""
+    m = open_twin
+    K = len(m["variance"])
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    rng = np.random.default_rng(4)
+    ids = np.arange(0, len(m["ref"]), 9)
+    tp = m["target"][::11]
+    gp = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, 0, True, ids, tp)
+    op = orc.IcpProposal(om, ot, 0.1, 10.0, 5.0, 0, True, ids, tp)
+    base = [dict(kind=1, weight=0.2, sd=0.05), dict(kind=2, weight=0.1, sd=0.01, axis=0), dict(kind=2, weight=0.1, sd=0.01, axis=2),
+            dict(kind=3, weight=0.1, sd=0.1, axis=1)]
+    comps_d = [dict(kind=0, weight=0.5, proposal=gp)] + base
+    comps_o = [dict(kind=0, weight=0.5, icp=op)] + base
+    ev = core.Evaluator(model, tgt, _lib.EVAL_COLLECTIVE, 2, True, 0.1, 0.3, 1.0, ids, tp)
+    C, n = 2, 30
+    th0 = random_theta(m, rng, C)
+    u_comp, u_acc, z = rng.random((n, C)), rng.random((n, C)), rng.normal(size=(n, C, K))
+    chain = core.Chain(model, tgt, comps_d, ev, max_chains=C)
+    got = chain.run(th0, n, u_comp=u_comp, z=z, u_acc=u_acc)
+    for c in range(C):
+        want = orc.chain_run(om, ot, comps_o, True, orc.EVAL_COLLECTIVE, 2, (0.1, 0.3, 1.0), ids, tp, th0[c], n, u_comp[:, c],
+                             z[:, c], u_acc[:, c], closed_form=True)
+        assert np.array_equal(got["component"][:, c], want["comp"])
+        assert np.array_equal(got["accepted"][:, c], want["accepted"])
+        np.testing.assert_allclose(got["values"][:, c], want["logv"], rtol=1e-7)
+        np.testing.assert_allclose(got["theta"][:, c], want["theta"], rtol=0, atol=1e-7)
+    assert set(np.unique(got["component"])) >= {0, 1}
+    chain.close(); ev.close(); gp.close(); model.close(); tgt.close()
+
+
+def test_philox_bit_exact_and_chain_sharding(ctx, twin31):
+    for seed, chain, step, block in ((0, 0, 0, 0), (1024, 5, 77, 3), (2 ** 63 + 11, 2 ** 40 + 3, 2 ** 31, 9)):
+        want = orc.philox4x32_10([chain & 0xffffffff, chain >> 32, step, block], [seed & 0xffffffff, seed >> 32])
+        assert np.array_equal(ctx.philox(seed, chain, step, block), want)
+    m = twin31
+    K = 31
+    model, tgt = _dev(ctx, m)
+    ids, eids = np.arange(62), np.arange(124)
+    tp = m["target"][::26][:62]
+    comps = _mixture(model, tgt, None, None, K, ids, tp, True)
+    ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, 0, True, 0.0, 2.0, 0.0, eids, tp)
+    chain = core.Chain(model, tgt, comps, ev, max_chains=8)
+    th0 = random_theta(m, np.random.default_rng(8), 6, alpha_sd=0.5)
+    full = chain.run(th0, 50, seed=99)
+    # the same chains sharded 2 + 4 with global chain ids: bit-identical logs (results do not depend on the sharding)
+    a = chain.run(th0[:2], 50, seed=99, chain_id_offset=0)
+    b = chain.run(th0[2:], 50, seed=99, chain_id_offset=2)
+    for k in ("component", "accepted", "values", "theta"):
+        assert np.array_equal(np.concatenate([a[k], b[k]], axis=1), full[k]), k
+    # and it is a plausible chain: acceptance neither 0 nor 1, posterior improves
+    rate = full["accepted"].mean()
+    assert 0.05 < rate < 0.95
+    assert full["values"][-1, :, 0].mean() > full["values"][0, :, 0].mean()
+    # normals are standard normal: the random-walk steps have the right scale
+    rw = (full["component"] == 2) & full["accepted"]
+    assert rw.sum() > 0
+    chain.close(); ev.close(); model.close(); tgt.close()
+
+
+def test_full_size_properties(ctx, twin101):
+    """BASELINE-sized inputs through size-independent properties (no O(nq T) oracle needed)."""
+    verts, tris = twin101["target"], twin101["target_cells"]
+    tgt = core.Target(ctx, verts, tris)
+    q = synth.near_surface_queries(verts, tris, 1_000_000, seed=11)
+    tri, feat, cp, d2 = tgt.closest_point_surface(q)
+    # (1) the reported point lies on the reported triangle and is at the reported distance
+    np.testing.assert_allclose(((q - cp) ** 2).sum(1), d2, rtol=1e-12, atol=1e-25)
+    # (2) idempotence: the closest point of a surface point is itself
+    _, _, cp2, d22 = tgt.closest_point_surface(cp[:200000])
+    assert d22.max() < 1e-18
+    # (3) no vertex is closer than the surface, and the nearest vertex is never closer than d
+    ids, vd2 = tgt.closest_vertex(q[:200000])
+    assert np.all(vd2 >= d2[:200000] * (1 - 1e-12))
+    # (4) agreement with brute force on a random subsample
+    sub = np.random.default_rng(0).choice(len(q), 3000, replace=False)
+    want = orc.Mesh(verts, tris).closest_point(q[sub], brute=True)
+    np.testing.assert_allclose(d2[sub], want[3], rtol=1e-12)
+    tgt.close()
