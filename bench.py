@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py - MCMC samples/sec (femur GPMM-100 shape) and closest-point queries/sec on B200.
+
+One "step" is one Metropolis-Hastings step of every chain resident on the GPU (C samples per step and
+GPU). Workload = BASELINE.json configs[2]/[3] shape: synthetic femur twin (N=1622, T=3240, K=101),
+the config-1 proposal mixture 0.9*(0.5 ICP target-sampling + 0.5 ICP model-sampling, n=2K) + 0.1*RW(0.1)
+and the prior x Gaussian-point(sd 2, 4K points, model->target) evaluator
+(apps/femur/IcpProposalRegistration.scala:59-61,70-72,85), C independent random-init chains batched per
+GPU (apps/femur/RunMHRandomInitComparison.scala shape; init alpha ~ N(0, 0.1 I) as
+apps/femur/RandomSamplesFromModel.scala:28-36). Chains shard over GPUs with no data-path collective
+(weak scaling: C chains per GPU); NCCL only gathers the chain statistics at the end.
+
+    python bench.py --gpus N --steps K --warmup W          # this framework (libicpcuda.so)
+    python bench.py --impl reference ...                    # the CPU path (oracle port) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mcmc_samples_per_sec_femur_gpmm100"
+UNIT = "samples/s"
+K_RANK = 101
+
+
+def workload():
+    from icp_proposal_b200 import synth
+    m = synth.femur_twin(rank=K_RANK)
+    tv, tc, _ = synth.synthetic_target(m, seed=7, alpha_sd=0.5)
+    K = K_RANK
+    ids = np.arange(2 * K, dtype=np.int32)               # first n vertices
+    eids = np.arange(4 * K, dtype=np.int32)
+    tp = tv[:: max(1, len(tv) // (2 * K))][: 2 * K].copy()  # stand-in for VTK-decimated target points
+    return m, tv, tc, ids, eids, tp
+
+
+def init_thetas(m, n, offset=0):
+    K = K_RANK
+    th = np.zeros((n, K + 10))
+    th[:, 0] = 1.0
+    th[:, 7:10] = m["ref"].mean(0)
+    for i in range(n):
+        g = offset + i
+        if g > 0:   # RandomSamplesFromModel.scala:28-36: index 0 starts from the mean, the others from N(0, 0.1 I)
+            th[i, 10:] = np.random.default_rng(1024 + g).normal(0.0, np.sqrt(0.1), K)
+    return th
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout.readlines()), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def oracle_chain_rate(m, tv, tc, ids, eids, tp, n_chains, n_steps, threads, closed_form, first_chain=0):
+    """Times the CPU restatement (oracle port) of the same chain on the host cores."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+
+    K = K_RANK
+    th0 = init_thetas(m, n_chains, first_chain)
+
+    def one(c):
+        om = orc.Model(m["ref"], m["cells"], m["basis"], m["variance"])   # per thread: the caches are not shared
+        ot = orc.Mesh(tv, tc)
+        pt = orc.IcpProposal(om, ot, 0.1, 10.0, 5.0, 1, True, ids, tp)
+        pm = orc.IcpProposal(om, ot, 0.1, 10.0, 5.0, 0, True, ids, tp)
+        comps = [dict(kind=0, weight=0.45, icp=pt), dict(kind=0, weight=0.45, icp=pm), dict(kind=1, weight=0.1, sd=0.1)]
+        rng = np.random.default_rng(99 + c)
+        r = orc.chain_run(om, ot, comps, True, orc.EVAL_INDEPENDENT, 0, (0.0, 2.0), eids, tp, th0[c], n_steps,
+                          rng.random(n_steps), rng.normal(size=(n_steps, K)), rng.random(n_steps), closed_form=closed_form)
+        return r["n_accepted"]
+
+    orc.lib()
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        acc = list(ex.map(one, range(n_chains)))
+    dt = time.perf_counter() - t0
+    return n_chains * n_steps / dt, dt, float(np.sum(acc)) / (n_chains * n_steps)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    m, tv, tc, ids, eids, tp = workload()
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 32))
+    per = max(1, args.ref_steps)
+    rates = []
+    t_all = time.perf_counter()
+    for s in range(args.warmup + args.steps):
+        rate, dt, acc = oracle_chain_rate(m, tv, tc, ids, eids, tp, threads, per, threads, closed_form=False, first_chain=s * threads)
+        if s >= args.warmup:
+            rates.append((rate, dt))
+    value = float(np.mean([r for r, _ in rates]))
+    ms = float(np.mean([d for _, d in rates]) * 1e3)
+    sample = f"{threads} chains x {per} MH steps per bench step on {threads} threads (1 core per chain, reference structure: SVD-rotated basis + full-mesh regressions)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "femur GPMM-100 twin (N=1622,T=3240,K=101), config-1 ICP mixture + Gaussian-point evaluator, independent chains",
+                       "chains": threads, "n_icp_points": int(len(ids)), "n_eval_points": int(len(eids))},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from icp_proposal_b200 import _lib, core, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    m, tv, tc, ids, eids, tp = workload()
+    K, L = K_RANK, K_RANK + 10
+    C = args.chains
+    ctx = core.Context(local)
+    model = core.Model(ctx, m["ref"], m["cells"], m["basis"], m["variance"])
+    tgt = core.Target(ctx, tv, tc)
+    pt = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.TARGET_SAMPLING, True, ids, tp)
+    pm = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.MODEL_SAMPLING, True, ids, tp)
+    comps = [dict(kind=_lib.PROP_ICP, weight=0.45, proposal=pt), dict(kind=_lib.PROP_ICP, weight=0.45, proposal=pm),
+             dict(kind=_lib.PROP_RANDOM_SHAPE, weight=0.1, sd=0.1)]
+    ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, _lib.MODEL_TO_TARGET, True, 0.0, 2.0, 0.0, eids, tp)
+    chain = core.Chain(model, tgt, comps, ev, max_chains=C)
+    th0_host = init_thetas(m, C, rank * C)
+
+    # ---- device-resident arm ("value"): theta0 and the chain log live in HBM ---------------------------------
+    steps, warm = args.steps, args.warmup
+    th0 = torch.from_numpy(th0_host).to(dev)
+    log_comp = torch.empty((steps, C), dtype=torch.int32, device=dev)
+    log_acc = torch.empty((steps, C), dtype=torch.uint8, device=dev)
+    log_val = torch.empty((steps, C, 3), dtype=torch.float64, device=dev)
+    log_th = torch.empty((steps, C, L), dtype=torch.float64, device=dev)
+    th_final = torch.empty((C, L), dtype=torch.float64, device=dev)
+    n_acc = torch.zeros(C, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    seed, off = 1024, rank * C
+    chain.run_device(C, warm, th0.data_ptr(), seed=seed, chain_id_offset=off)       # W warm-up steps (+ state of theta0)
+    with ClockSampler(local) as clocks:
+        barrier()
+        t0 = time.perf_counter()
+        chain.run_device(C, steps, None, seed=seed, chain_id_offset=off, log_component=log_comp.data_ptr(),
+                         log_accepted=log_acc.data_ptr(), log_values=log_val.data_ptr(), log_theta=log_th.data_ptr(),
+                         theta_final=th_final.data_ptr(), n_accepted=n_acc.data_ptr())   # exactly K steps, resumed
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms, launches = chain.last_run_stats()       # CUDA events on the library stream around the K steps
+    t_ms = max_over_ranks(dev_ms)
+    value = world * C * steps / (t_ms * 1e-3)
+    accept_rate = float(log_acc.float().mean().item())
+
+    # ---- chain statistics gathered over NCCL (the only collective; not on the per-sample path) -------------
+    gather_ms = None
+    if world > 1:
+        stats = torch.cat([th_final[:, 10:].mean(0), (th_final[:, 10:] ** 2).mean(0), log_val[-1].mean(0)])
+        out = torch.empty((world,) + stats.shape, dtype=stats.dtype, device=dev)
+        fin = torch.empty((world,) + th_final.shape, dtype=th_final.dtype, device=dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather_into_tensor(out, stats)
+        dist.all_gather_into_tensor(fin, th_final)
+        e1.record()
+        torch.cuda.synchronize()
+        gather_ms = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- end-to-end arm: the public host-buffer call (pinned host memory in, chain log out) ---------------
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    h_th0 = pin((C, L), torch.float64); h_th0[:] = th0_host
+    e_steps = steps
+    io = _lib.ChainIO()
+    io.seed, io.chain_id_offset = seed, off
+    h_comp, h_acc = pin((e_steps, C), torch.int32), pin((e_steps, C), torch.uint8)
+    h_val, h_thl = pin((e_steps, C, 3), torch.float64), pin((e_steps, C, L), torch.float64)
+    h_fin, h_nacc = pin((C, L), torch.float64), pin((C,), torch.int64)
+    io.log_component, io.log_accepted, io.log_values, io.log_theta = (h_comp.ctypes.data, h_acc.ctypes.data, h_val.ctypes.data,
+                                                                      h_thl.ctypes.data)
+    io.theta_final, io.n_accepted = h_fin.ctypes.data, h_nacc.ctypes.data
+    import ctypes as Cc
+    barrier()
+    t0 = time.perf_counter()
+    _lib.check(chain.lib.icp_chain_run(chain.h, C, e_steps, _lib.dptr(h_th0), Cc.byref(io)), ctx.h)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+    # the host call evaluates theta0 once (1 extra state) before the K steps: count K steps of C samples
+    e2e_value = world * C * e_steps / (e2e_ms * 1e-3)
+    h2d = h_th0.nbytes / e_steps
+    d2h = (h_comp.nbytes + h_acc.nbytes + h_val.nbytes + h_thl.nbytes + h_fin.nbytes + h_nacc.nbytes) / e_steps
+
+    line = None
+    if rank == 0:
+        # ---- per-kernel device times (CUDA events on the launching stream, eager pass over the same workload) --
+        prof_steps = max(2, min(steps, 8))
+        prof = chain.profile(th0_host, prof_steps, seed=seed)
+        total_prof = sum(v["ms"] for v in prof.values()) or 1.0
+        shares = {k: round(v["ms"] / total_prof, 4) for k, v in prof.items() if v["launches"]}
+        fp64 = ctx.fp64_peak()
+        peaks, peak_src = measured_peaks()
+        # posterior build: algorithmic flops per chain-posterior = 2*3n*K^2 (M) + 2*3n*K*3 (Sigma^-1 apply), SURVEY 8d
+        n_obs = len(ids)
+        flops_post = 2.0 * 3 * n_obs * K * K + 2.0 * 3 * n_obs * K * 3
+        pb = prof["posterior_build"]
+        pb_ms = pb["ms"] / max(pb["launches"], 1)
+        pb_tflops = flops_post * C / (pb_ms * 1e-3) / 1e12 if pb_ms > 0 else 0.0
+        # closest-point traversal: 1000 B / query on the femur mesh, 1e6 device-resident queries
+        cp = {}
+        nq = 1_000_000
+        for name, q in (("near_surface", synth.near_surface_queries(tv, tc, nq, seed=11)), ("far_field", synth.far_field_queries(tv, nq, seed=12))):
+            qd = torch.from_numpy(q).to(dev)
+            tri = torch.empty(nq, dtype=torch.int32, device=dev); cpd = torch.empty((nq, 3), dtype=torch.float64, device=dev)
+            d2 = torch.empty(nq, dtype=torch.float64, device=dev)
+            ms = Cc.c_double(0)
+            _lib.check(chain.lib.icp_debug_time_closest_point(tgt.h, nq, qd.data_ptr(), tri.data_ptr(), cpd.data_ptr(), d2.data_ptr(),
+                                                              10, Cc.byref(ms)), ctx.h)
+            cp[name] = {"queries_per_s": nq / (ms.value * 1e-3), "ms_per_launch": ms.value,
+                        "algorithmic_GBps": nq * 1000.0 / (ms.value * 1e-3) / 1e9}
+        top = max(shares, key=shares.get)
+        cpq = prof["closest_point_static"]
+        cp_ms = cpq["ms"] / max(cpq["launches"], 1)
+        roof_cp = {"bound": "hbm", "kernel": "k_nearest<tri,static> (1e6 near-surface queries, timed alone)",
+                   "achieved": cp["near_surface"]["algorithmic_GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "frac": cp["near_surface"]["algorithmic_GBps"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                   "bytes_per_query": 1000}
+        roofline = {"bound": "fp64", "kernel": "k_posterior_build", "achieved": pb_tflops, "peak": fp64["dfma_tflops"],
+                    "unit": "TFLOP/s", "frac": pb_tflops / fp64["dfma_tflops"] if fp64["dfma_tflops"] else None, "traffic": None,
+                    "peak_source": "FP64 FMA micro-benchmark run live on this GPU (MEASURED_PEAKS.json has no FP64 figure); "
+                                   "DMMA m8n8k4 measured %.1f TFLOP/s" % fp64["dmma_tflops"],
+                    "flops_per_launch": flops_post * C, "avg_launch_ms": pb_ms, "share_of_step": shares.get("posterior_build"),
+                    "top_kernel_by_time": top}
+        # ---- CPU baseline: the oracle port of the same chain on this box's host cores (bounded sample) ------
+        cores = os.cpu_count() or 1
+        cb_rate, cb_dt, _ = oracle_chain_rate(m, tv, tc, ids, eids, tp, 1, args.cpu_steps, 1, closed_form=False)
+        opt_rate, opt_dt, _ = oracle_chain_rate(m, tv, tc, ids, eids, tp, 1, args.cpu_steps * 20, 1, closed_form=True)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+                "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "femur GPMM-100 twin (N=1622,T=3240,K=101), config-1 ICP mixture (0.45 target-sampling + 0.45 "
+                                       "model-sampling ICP n=202, 0.1 random walk) + prior x Gaussian-point(sd 2, 404 pts) evaluator, "
+                                       "independent random-init chains batched per GPU",
+                           "chains_per_gpu": C, "samples_per_step": world * C, "n_icp_points": int(len(ids)), "n_eval_points": int(len(eids)),
+                           "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
+                           "l2_policy": "per-step working set (posteriors 4x%.0f MB + meshes) exceeds L2" % (C * 104 * 104 * 8 / 1e6)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e_steps},
+                "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / steps, "accept_rate": accept_rate,
+                "clocks": clocks.summary(), "roofline": roofline, "roofline_closest_point": roof_cp, "closest_point": cp,
+                "kernel_shares": shares, "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items() if v["launches"]},
+                "fp64_peak": fp64, "gather_ms": gather_ms,
+                "cpu_baseline": {"value": cb_rate, "unit": UNIT, "cores": 1, "kind": "port",
+                                 "sample": f"1 chain x {args.cpu_steps} MH steps of the same workload, oracle in the reference's structure, 1 thread ({cb_dt:.1f} s); host has {cores} cores"},
+                "cpu_baseline_optimised": {"value": opt_rate, "unit": UNIT, "cores": 1, "kind": "port",
+                                           "sample": f"1 chain x {args.cpu_steps * 20} steps, oracle with the same closed forms as the device ({opt_dt:.1f} s)"},
+                "device": ctx.version()}
+        print(json.dumps(line))
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=1184, help="chains per GPU (8 x 148 SMs)")
+    ap.add_argument("--cpu-steps", type=int, default=12, help="MH steps of the cpu_baseline sample")
+    ap.add_argument("--ref-steps", type=int, default=4, help="MH steps per chain and bench step of --impl reference")
+    args = ap.parse_args()
+    if args.warmup < 1:
+        args.warmup = 1
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,7 @@ struct ChainParams {
 struct RngDev {
     unsigned long long seed, chain_offset;
     const double *u_comp, *z, *u_acc;  // host-RNG mode when non-null: [step][C], [step][C][K], [step][C]
+    int step_base;
 };
 
 struct LogDev {
@@ -42,6 +43,7 @@ struct LogDev {
     uint8_t *accepted;
     double *values;  // [step][C][3]
     double *theta;   // [step][C][L]
+    int step_base;   // record index = step - step_base (resumed runs keep counting steps for the RNG)
 };
 
 struct StateDev {
@@ -111,8 +113,8 @@ __global__ void __launch_bounds__(128) k_chain_propose(ChainParams P, ModelDev m
     if (threadIdx.x == 0) {
         double uc, ua;
         if (rng.u_comp) {
-            uc = rng.u_comp[(size_t)step * C + c];
-            ua = rng.u_acc[(size_t)step * C + c];
+            uc = rng.u_comp[(size_t)(step - rng.step_base) * C + c];
+            ua = rng.u_acc[(size_t)(step - rng.step_base) * C + c];
         } else {
             uint4 r = chain_philox(rng.seed, chain, step, 0u);
             uc = u53(r.x, r.y);
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(128) k_chain_propose(ChainParams P, ModelDev m
     }
     for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
         double zz = 0.0;
-        if (k < K) zz = rng.z ? rng.z[((size_t)step * C + c) * K + k] : chain_normal(rng.seed, chain, step, k);
+        if (k < K) zz = rng.z ? rng.z[((size_t)(step - rng.step_base) * C + c) * K + k] : chain_normal(rng.seed, chain, step, k);
         sz[k] = zz;
     }
     __syncthreads();
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st
     }
     __syncthreads();
     // chain log: the state that is current after the step (JSONAcceptRejectLogger.scala:93-106)
-    size_t rec = (size_t)step * C + c;
+    size_t rec = (size_t)(step - lg.step_base) * C + c;
     if (lg.theta)
         for (int j = threadIdx.x; j < Lt; j += blockDim.x) lg.theta[rec * Lt + j] = ok ? prp[j] : cur[j];
     if (threadIdx.x == 0) {
@@ -313,6 +315,8 @@ struct icp_chain_s {
     int64_t last_launches = 0;
     int last_per_step = 0;
     bool use_graph = true;
+    int resident_C = 0;      // chains whose state is resident from the last run (resume)
+    int steps_total = 0;     // value of the device step counter
 };
 
 extern "C" int32_t icp_chain_create(icp_model m, icp_target t, const icp_component *components, int32_t n_components,
@@ -446,7 +450,9 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     const int K = m->K, Kp = m->Kp, Lt = K + kTheta0;
     ICP_REQUIRE(C >= 1 && C <= ch->max_chains, "C must be in [1, max_chains]");
     ICP_REQUIRE(n_steps >= 0, "n_steps must be >= 0");
-    ICP_REQUIRE(theta0_dev && io, "null argument");
+    ICP_REQUIRE(io != nullptr, "null argument");
+    const bool resume = theta0_dev == nullptr;
+    if (resume) ICP_REQUIRE(ch->resident_C == C, "resume needs a previous run with the same number of chains");
     bool host_rng = io->u_comp || io->z || io->u_acc;
     if (host_rng) ICP_REQUIRE(io->u_comp && io->z && io->u_acc, "u_comp, z and u_acc must be given together");
     const int n_icp = ch->P.n_icp;
@@ -462,32 +468,35 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     r.st = StateDev{ch->theta_cur.p, ch->theta_prop.p, ch->values_cur.p, ch->values_prop.p, ch->cur_sel.p,
                     ch->slot_cur.p, ch->slot_prop.p, ch->comp_sel.p, ch->u_acc.p, ch->n_acc.p, ch->step.p, ch->L.p,
                     ch->mu.p};
-    r.rng = RngDev{io->seed, io->chain_id_offset, io->u_comp, io->z, io->u_acc};
-    r.lg = LogDev{io->log_component, io->log_accepted, io->log_values, io->log_theta};
+    const int step_base = resume ? ch->steps_total : 0;
+    r.rng = RngDev{io->seed, io->chain_id_offset, io->u_comp, io->z, io->u_acc, step_base};
+    r.lg = LogDev{io->log_component, io->log_accepted, io->log_values, io->log_theta, step_base};
 
     ICP_CUDA(cudaEventRecord(ch->ev0, s));
-    ICP_CUDA(cudaMemcpyAsync(ch->theta_cur.p, theta0_dev, sizeof(double) * (size_t)C * Lt, cudaMemcpyDeviceToDevice, s));
-    k_chain_init<<<(C + 127) / 128, 128, 0, s>>>(C, r.st);
-    ICP_CUDA(cudaGetLastError());
+    if (!resume) {
+        ICP_CUDA(cudaMemcpyAsync(ch->theta_cur.p, theta0_dev, sizeof(double) * (size_t)C * Lt, cudaMemcpyDeviceToDevice, s));
+        k_chain_init<<<(C + 127) / 128, 128, 0, s>>>(C, r.st);
+        ICP_CUDA(cudaGetLastError());
+    }
     {
         size_t smem_p = sizeof(double) * ((size_t)2 * Kp + (size_t)Kp * Kp);
         ICP_REQUIRE(smem_p <= 227 * 1024, "rank too large for the propose kernel");
         ICP_CUDA(cudaFuncSetAttribute(k_chain_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
     }
     // state of theta0: log-values + posteriors of every ICP component (state 0)
-    enqueue_state_eval(r, ch->theta_cur.p, ch->values_cur.p, ch->slot_cur.p);
+    if (!resume) enqueue_state_eval(r, ch->theta_cur.p, ch->values_cur.p, ch->slot_cur.p);
 
     // launches per step, for the report
     int per_step = 0;
     int steps_done = 0;
-    if (n_steps > 0) {
+    if (n_steps > 0 && (!resume || !ch->use_graph)) {
         // first step eagerly: sizes every workspace (allocation is illegal during capture)
         enqueue_step(r);
         steps_done = 1;
     }
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    if (ch->use_graph && !g_prof && n_steps - steps_done >= 2) {
+    if (ch->use_graph && !g_prof && n_steps - steps_done >= 1 && (resume || steps_done > 0)) {
         ICP_CUDA(cudaStreamSynchronize(s));
         cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
@@ -527,8 +536,10 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     if (io->n_accepted)
         ICP_CUDA(cudaMemcpyAsync(io->n_accepted, ch->n_acc.p, sizeof(long long) * (size_t)C, cudaMemcpyDeviceToDevice, s));
     ICP_CUDA(cudaEventRecord(ch->ev1, s));
-    ch->last_launches = (int64_t)per_step * n_steps;
-    ch->last_per_step = per_step;
+    ch->resident_C = C;
+    ch->steps_total = step_base + n_steps;
+    if (per_step > 0) ch->last_per_step = per_step;
+    ch->last_launches = (int64_t)ch->last_per_step * n_steps;
     if (!async || exec) {
         ICP_CUDA(cudaStreamSynchronize(s));
         float ms = 0;

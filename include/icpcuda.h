@@ -225,7 +225,10 @@ typedef struct {
 /* theta0 C x (K+10) (host). io buffers are host memory. */
 int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const double *theta0, const icp_chain_io *io);
 /* same with theta0 and every non-NULL io pointer in DEVICE memory; the run is enqueued on the
- * context stream and synchronised before returning unless `async` != 0. */
+ * context stream and synchronised before returning unless `async` != 0.
+ * theta0_dev == NULL resumes the C chains of the previous run from their resident state (current
+ * parameters, log-values and posteriors stay on the device; the step counter - hence the Philox
+ * stream - continues, the log pointers of this call start at record 0). */
 int32_t icp_chain_run_device(icp_chain c, int32_t C, int32_t n_steps, const double *theta0_dev,
                              const icp_chain_io *io_dev, int32_t async);
 int32_t icp_ctx_synchronize(icp_ctx ctx);

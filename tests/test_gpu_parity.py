@@ -25,7 +25,9 @@ def _orc(m):
 def _assert_closest_point_parity(verts, tris, q, got, want):
     tri_g, feat_g, cp_g, d2_g = got
     tri_o, feat_o, cp_o, d2_o = want
-    np.testing.assert_allclose(d2_g, d2_o, rtol=1e-12, atol=1e-22)
+    # distances: the device contracts a*b+c into FMAs, the oracle does not -> ~1e-13 mm on 200 mm coordinates;
+    # the stated tolerance is 1e-5 relative
+    np.testing.assert_allclose(np.sqrt(d2_g), np.sqrt(d2_o), rtol=1e-10, atol=1e-11)
     np.testing.assert_allclose(cp_g, cp_o, rtol=0, atol=1e-9)
     diff = np.nonzero(tri_g != tri_o)[0]
     # documented equidistant ties: a different triangle is acceptable only if the oracle itself certifies
@@ -33,8 +35,9 @@ def _assert_closest_point_parity(verts, tris, q, got, want):
     for i in diff:
         a, b, c = verts[tris[tri_g[i]]]
         d2, _, _ = orc.point_triangle_d2(q[i], a, b, c)
-        assert abs(d2 - d2_o[i]) <= 1e-12 * max(d2_o[i], 1e-300), f"query {i}: not an equidistant tie"
-    assert len(diff) <= max(3, len(q) // 200)
+        assert abs(np.sqrt(d2) - np.sqrt(d2_o[i])) <= 1e-11 + 1e-10 * np.sqrt(d2_o[i]), f"query {i}: not an equidistant tie"
+    # (far-field queries mostly hit vertices / edges, where 2-8 triangles tie; FMA contraction decides the last bit)
+    assert len(diff) <= len(q) // 10
     same = tri_g == tri_o
     assert np.array_equal(feat_g[same], feat_o[same])
 
@@ -132,7 +135,11 @@ def test_dynamic_model_queries(ctx, twin31):
         to, fo, co, do = cur.closest_point(q, brute=True)
         np.testing.assert_allclose(d2[c], do, rtol=1e-9, atol=1e-20)
         np.testing.assert_allclose(cp[c], co, rtol=0, atol=1e-8)
-        assert (tri[c] == to).mean() > 0.995
+        assert (tri[c] == to).mean() > 0.97
+        for i in np.nonzero(tri[c] != to)[0]:   # certified equidistant ties only
+            a, b, cc = cur.verts[twin31["cells"][tri[c][i]]]
+            dd, _, _ = orc.point_triangle_d2(q[i], a, b, cc)
+            assert abs(np.sqrt(dd) - np.sqrt(do[i])) <= 1e-9 + 1e-9 * np.sqrt(do[i])
         io, vo = cur.closest_vertex(q, brute=True)
         assert (ids[c] == io).mean() > 0.999
         np.testing.assert_allclose(vd2[c], vo, rtol=1e-9)
@@ -407,7 +414,7 @@ def test_full_size_properties(ctx, twin101):
     q = synth.near_surface_queries(verts, tris, 1_000_000, seed=11)
     tri, feat, cp, d2 = tgt.closest_point_surface(q)
     # (1) the reported point lies on the reported triangle and is at the reported distance
-    np.testing.assert_allclose(((q - cp) ** 2).sum(1), d2, rtol=1e-12, atol=1e-25)
+    np.testing.assert_allclose(((q - cp) ** 2).sum(1), d2, rtol=1e-12, atol=1e-25)  # same arithmetic, both from cp
     # (2) idempotence: the closest point of a surface point is itself
     _, _, cp2, d22 = tgt.closest_point_surface(cp[:200000])
     assert d22.max() < 1e-18
@@ -417,5 +424,5 @@ def test_full_size_properties(ctx, twin101):
     # (4) agreement with brute force on a random subsample
     sub = np.random.default_rng(0).choice(len(q), 3000, replace=False)
     want = orc.Mesh(verts, tris).closest_point(q[sub], brute=True)
-    np.testing.assert_allclose(d2[sub], want[3], rtol=1e-12)
+    np.testing.assert_allclose(np.sqrt(d2[sub]), np.sqrt(want[3]), rtol=1e-10, atol=1e-11)
     tgt.close()
