@@ -13,6 +13,8 @@
 //
 // Sigma_i^-1 = F_i^T F_i with F_i rows n/sd_n, t1/sd_t, t2/sd_t (orthonormal frame of the vertex
 // normal), so M = I + A^T A with A = stack(F_i Q_i): a batched symmetric rank-3n update in FP64.
+#include <cstdlib>
+
 #include "icp_device.cuh"
 #include "icp_internal.h"
 
@@ -203,9 +205,185 @@ __global__ void __launch_bounds__(kPbThreads) k_posterior_build(ModelDev m, ObsD
     if (threadIdx.x < Kp) bvec[(size_t)c * Kp + threadIdx.x] = bacc;
 }
 
+
+// ---- tensor-pipe version: mma.sync.m8n8k4.f64 (DMMA) ----------------------------------------------------
+// M (Kp x Kp) is cut into 8 x 8 blocks; only the NB (NB + 1) / 2 blocks of the lower triangle are computed.
+// They are numbered row-major and dealt out in contiguous runs to the warps of the CTA; each warp keeps its
+// blocks as DMMA accumulator fragments in registers for the whole pass over the observations. One staged
+// chunk = 8 observations = 24 rows of A = 6 k4-steps. For a block (bi, bj) and a k4-step the A- and
+// B-operand fragments are the SAME access pattern into the staged rows (element [k][8 b + i] for lane
+// (i = lane / 4, k = lane % 4)), so a fragment loaded for column block b serves as A operand of block row b
+// and as B operand of block column b. Row stride Kp + 4 makes the fragment loads bank-conflict free.
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int kMmaRows = 3 * kPbObs;  // 24 staged rows = 6 k4-steps
+constexpr int kProdWarps = 2;         // producer warps (stage A = F Q into shared memory, accumulate b)
+constexpr int kMaxNB = 20;         // largest supported Kp / 8
+
+template <int ID>
+__device__ __forceinline__ void named_bar_sync(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void named_bar_arrive(int n) { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+
+// Warp-specialised: warps [0, nwc) are MMA consumers, the last kProdWarps warps are producers. Two staged
+// buffers; named barriers FULL(1 + buf) / EMPTY(3 + buf) hand them back and forth, so the gather of the
+// basis rows (L2 latency) and the 3 x 3 whitening overlap with the DMMA stream of the previous chunk.
+template <int NBLK, int NBMAX, int NWC>
+__global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_build_mma(ModelDev m, ObsDev o,
+                                                                                 double *__restrict__ M,
+                                                                                 double *__restrict__ bvec,
+                                                                                 int nblk_total) {
+    extern __shared__ double sm[];
+    const int Kp = m.Kp, ld = Kp + 4, NB = Kp >> 3;
+    const int bufsz = kMmaRows * ld;
+    double *sA = sm;                    // [2][24][ld]
+    const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int nthreads = (NWC + kProdWarps) * 32, nwc = NWC;
+    const int nchunks = (o.n + kPbObs - 1) / kPbObs;
+    if (warp < nwc) {
+        // ------------------------------- consumers: DMMA ------------------------------------------------
+        const int per = (nblk_total + nwc - 1) / nwc;
+        const int b0 = warp * per;
+        const int nmine = max(0, min(nblk_total, b0 + per) - b0);
+        int bi0, bj0;
+        tri_index(b0 < nblk_total ? b0 : 0, bi0, bj0);
+        double acc[NBLK][2];
+#pragma unroll
+        for (int s = 0; s < NBLK; s++) acc[s][0] = acc[s][1] = 0.0;
+        const int frag = (lane & 3) * ld + (lane >> 2);
+        named_bar_arrive<3>(nthreads);  // both buffers start empty
+        named_bar_arrive<4>(nthreads);
+        for (int ch = 0; ch < nchunks; ch++) {
+            const int buf = ch & 1;
+            if (buf == 0) named_bar_sync<1>(nthreads); else named_bar_sync<2>(nthreads);
+            const double *base = sA + buf * bufsz + frag;
+            int bi = bi0, bj = bj0;
+            double fa[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) fa[k] = base[k * 4 * ld + 8 * bi];
+#pragma unroll
+            for (int s = 0; s < NBLK; s++) {
+                if (s < nmine) {
+                    double fb[6];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) fb[k] = base[k * 4 * ld + 8 * bj];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) dmma_8x8x4(acc[s][0], acc[s][1], fa[k], fb[k]);
+                    if (++bj > bi) {
+                        bj = 0;
+                        if (++bi < NB) {
+#pragma unroll
+                            for (int k = 0; k < 6; k++) fa[k] = base[k * 4 * ld + 8 * bi];
+                        }
+                    }
+                }
+            }
+            if (buf == 0) named_bar_arrive<3>(nthreads); else named_bar_arrive<4>(nthreads);
+        }
+        double *Mc = M + (size_t)c * Kp * Kp;
+        int bi = bi0, bj = bj0;
+#pragma unroll
+        for (int s = 0; s < NBLK; s++) {
+            if (s < nmine) {
+                int i = 8 * bi + (lane >> 2), j = 8 * bj + 2 * (lane & 3);
+                double v0 = acc[s][0] + (i == j ? 1.0 : 0.0), v1 = acc[s][1] + (i == j + 1 ? 1.0 : 0.0);
+                *reinterpret_cast<double2 *>(Mc + (size_t)i * Kp + j) = make_double2(v0, v1);
+                if (bi != bj) {
+                    Mc[(size_t)j * Kp + i] = v0;
+                    Mc[(size_t)(j + 1) * Kp + i] = v1;
+                }
+                if (++bj > bi) { bj = 0; ++bi; }
+            }
+        }
+    } else {
+        // ------------------------------- producers: gather + whiten ----------------------------------------
+        const int pt = tid - nwc * 32;          // 0 .. 63
+        const int ob = pt >> 3, cg = pt & 7;     // observation slot within the chunk, column group
+        const int *vid = o.vid + (size_t)c * o.n;
+        const double *F = o.F + (size_t)c * o.n * 9;
+        const double *y = o.y + (size_t)c * o.n * 3;
+        double bacc[NBMAX];
+#pragma unroll
+        for (int i = 0; i < NBMAX; i++) bacc[i] = 0.0;
+        for (int ch = 0; ch < nchunks; ch++) {
+            const int buf = ch & 1;
+            const int gi = ch * kPbObs + ob;
+            int v = -1;
+            double f[9], yy[3];
+            if (gi < o.n) v = __ldg(&vid[gi]);
+            if (v >= 0) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) f[k] = __ldg(F + (size_t)gi * 9 + k);
+#pragma unroll
+                for (int k = 0; k < 3; k++) yy[k] = __ldg(y + (size_t)gi * 3 + k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; k++) f[k] = 0.0;
+                yy[0] = yy[1] = yy[2] = 0.0;
+            }
+            const double *q = m.Q + (size_t)3 * (v >= 0 ? v : 0) * Kp + cg;
+            double q0[NBMAX], q1[NBMAX], q2[NBMAX];
+#pragma unroll
+            for (int i = 0; i < NBMAX; i++) {
+                if (i < NB) { q0[i] = __ldg(q + 8 * i); q1[i] = __ldg(q + Kp + 8 * i); q2[i] = __ldg(q + 2 * Kp + 8 * i); }
+            }
+            if (buf == 0) named_bar_sync<3>(nthreads); else named_bar_sync<4>(nthreads);   // consumers are done with this buffer
+            double *dst = sA + buf * bufsz + (3 * ob) * ld + cg;
+#pragma unroll
+            for (int i = 0; i < NBMAX; i++) {
+                if (i < NB) {
+                    double a0 = f[0] * q0[i] + f[1] * q1[i] + f[2] * q2[i];
+                    double a1 = f[3] * q0[i] + f[4] * q1[i] + f[5] * q2[i];
+                    double a2 = f[6] * q0[i] + f[7] * q1[i] + f[8] * q2[i];
+                    dst[8 * i] = a0; dst[ld + 8 * i] = a1; dst[2 * ld + 8 * i] = a2;
+                    bacc[i] = fma(a0, yy[0], fma(a1, yy[1], fma(a2, yy[2], bacc[i])));
+                }
+            }
+            if (buf == 0) named_bar_arrive<1>(nthreads); else named_bar_arrive<2>(nthreads);
+        }
+        // reduce b over the 8 observation slots (fixed order: deterministic)
+        named_bar_sync<5>(kProdWarps * 32);      // producers only
+        // the last two buffers may still be read by consumers: use the tail of the shared allocation
+        double *sb = sm + 2 * bufsz;             // [8][Kp]
+#pragma unroll
+        for (int i = 0; i < NBMAX; i++)
+            if (i < NB) sb[ob * Kp + cg + 8 * i] = bacc[i];
+        named_bar_sync<5>(kProdWarps * 32);
+        for (int j = pt; j < Kp; j += kProdWarps * 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; r++) t += sb[r * Kp + j];
+            bvec[(size_t)c * Kp + j] = t;
+        }
+    }
+}
+
+template <int NBLK, int NBMAX, int NWC>
+static void launch_pb_mma(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, int total, cudaStream_t s) {
+    size_t smem = sizeof(double) * ((size_t)2 * kMmaRows * (m.Kp + 4) + 8 * m.Kp);
+    ICP_CUDA(cudaFuncSetAttribute(k_posterior_build_mma<NBLK, NBMAX, NWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_posterior_build_mma<NBLK, NBMAX, NWC><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, d_b, total);
+}
+
 void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, cudaStream_t s) {
     ProfScope _ps(ST_POSTERIOR_BUILD, s);
     if (C <= 0) return;
+    static const bool no_mma = getenv("ICPCUDA_NO_DMMA") && getenv("ICPCUDA_NO_DMMA")[0] == '1';
+    {
+        int NB = m.Kp / 8, total = NB * (NB + 1) / 2;
+        if (!no_mma && NB <= kMaxNB) {
+            if (NB <= 4) launch_pb_mma<4, 4, 4>(m, C, o, d_M, d_b, total, s);
+            else if (NB <= 7) launch_pb_mma<8, 7, 4>(m, C, o, d_M, d_b, total, s);
+            else if (NB <= 13) launch_pb_mma<24, 13, 4>(m, C, o, d_M, d_b, total, s);
+            else launch_pb_mma<28, 20, 8>(m, C, o, d_M, d_b, total, s);
+            ICP_CUDA(cudaGetLastError());
+            return;
+        }
+    }
     int nt = m.Kp / 4, ntiles = nt * (nt + 1) / 2;
     size_t smem = sizeof(double) * ((size_t)3 * kPbObs * m.Kp + 3 * kPbObs);
     ICP_REQUIRE(m.Kp <= kPbThreads, "rank too large for the posterior build kernel (K <= 256)");
@@ -282,10 +460,156 @@ __global__ void __launch_bounds__(kChThreads) k_cholesky_solve(int K, int Kp, co
     (void)K;
 }
 
+
+// ---- blocked left-looking Cholesky with DMMA updates --------------------------------------------------------
+// 8 x 8 blocks; the right-hand side b rides along as block row NB (row Kp real, 7 zero rows), so that after
+// the factorisation it holds y = L^-1 b. Per block column bj:
+//   (1) every block (bi >= bj, bj) -= sum_{p < bj} L(bi, p) L(bj, p)^T      DMMA m8n8k4, blocks dealt to the warps
+//   (2) every thread factors the 8 x 8 diagonal block redundantly in registers (no warp / block hand-offs on
+//       the sqrt -> reciprocal chain) and solves its own row(s) of the panel against it.
+// Back substitution L^T x = y runs 8 unknowns at a time the same way.
+constexpr int kCh2Threads = 128;
+
+__global__ void __launch_bounds__(kCh2Threads) k_cholesky_solve_mma(int K, int Kp, const double *__restrict__ M,
+                                                                     const double *__restrict__ bvec,
+                                                                     double *__restrict__ L, double *__restrict__ mu,
+                                                                     const int *__restrict__ out_slot,
+                                                                     int *__restrict__ status) {
+    extern __shared__ double sm[];
+    const int ld = Kp + 4, NB = Kp >> 3, R = Kp + 8;
+    double *A = sm;                         // [R][ld]
+    double *dinv = A + (size_t)R * ld;      // [Kp] reciprocals of the diagonal of L
+    double *xs = dinv + Kp;                 // [Kp] running right-hand side of the back substitution
+    double *xo = xs + Kp;                   // [Kp] solution
+    __shared__ int bad;
+    const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double *Mc = M + (size_t)c * Kp * Kp;
+    if (tid == 0) bad = 0;
+    for (int e = tid; e < Kp * Kp; e += kCh2Threads) {
+        int i = e / Kp, j = e - i * Kp;
+        A[i * ld + j] = Mc[e];
+    }
+    for (int e = tid; e < 8 * ld; e += kCh2Threads) {
+        int r = e / ld, j = e - r * ld;
+        A[(Kp + r) * ld + j] = (r == 0 && j < Kp) ? bvec[(size_t)c * Kp + j] : 0.0;
+    }
+    __syncthreads();
+    const int fr = lane >> 2, fc = lane & 3;
+    for (int bj = 0; bj < NB; bj++) {
+        if (bj > 0) {
+            for (int bi = bj + warp; bi <= NB; bi += kCh2Threads / 32) {
+                double *pc = A + (8 * bi + fr) * ld + 8 * bj + 2 * fc;
+                double2 cc = *reinterpret_cast<double2 *>(pc);
+                const double *pa = A + (8 * bi + fr) * ld + fc;
+                const double *pb = A + (8 * bj + fr) * ld + fc;
+#pragma unroll 4
+                for (int k = 0; k < 8 * bj; k += 4) dmma_8x8x4(cc.x, cc.y, -pa[k], pb[k]);
+                *reinterpret_cast<double2 *>(pc) = cc;
+            }
+            __syncthreads();
+        }
+        // diagonal block, factored redundantly by every thread
+        double l[8][8], inv[8];
+        const double *D = A + (8 * bj) * ld + 8 * bj;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int k = 0; k <= i; k++) l[i][k] = D[i * ld + k];
+        __syncthreads();
+        bool mybad = false;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            double s = l[j][j];
+            if (!(s > 0.0)) mybad = true;
+            double d = sqrt(s);
+            inv[j] = 1.0 / d;
+            l[j][j] = d;
+#pragma unroll
+            for (int i = j + 1; i < 8; i++) l[i][j] *= inv[j];
+#pragma unroll
+            for (int i = j + 1; i < 8; i++)
+#pragma unroll
+                for (int k = j + 1; k <= i; k++) l[i][k] = fma(-l[i][j], l[k][j], l[i][k]);
+        }
+        if (mybad && tid == 0) bad = 1;
+        if (tid < 8) {
+            dinv[8 * bj + tid] = inv[tid];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i == tid) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) A[(8 * bj + i) * ld + 8 * bj + k] = k <= i ? l[i][k] : 0.0;
+                }
+        }
+        for (int r = 8 * bj + 8 + tid; r < R; r += kCh2Threads) {
+            double *row = A + r * ld + 8 * bj;
+            double x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[j] = row[j];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double t = x[j];
+#pragma unroll
+                for (int k = 0; k < j; k++) t = fma(-x[k], l[j][k], t);
+                x[j] = t * inv[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) row[j] = x[j];
+        }
+        __syncthreads();
+    }
+    // back substitution L^T x = y (y = row Kp of A)
+    for (int k = tid; k < Kp; k += kCh2Threads) xs[k] = A[Kp * ld + k];
+    __syncthreads();
+    for (int bj = NB - 1; bj >= 0; bj--) {
+        const double *D = A + (8 * bj) * ld + 8 * bj;
+        double x[8];
+#pragma unroll
+        for (int i = 7; i >= 0; i--) {
+            double t = xs[8 * bj + i];
+#pragma unroll
+            for (int k = i + 1; k < 8; k++) t = fma(-D[k * ld + i], x[k], t);
+            x[i] = t * dinv[8 * bj + i];
+        }
+        if (tid < 8) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i == tid) xo[8 * bj + i] = x[i];
+        }
+        for (int k = tid; k < 8 * bj; k += kCh2Threads) {
+            double t = xs[k];
+#pragma unroll
+            for (int p = 0; p < 8; p++) t = fma(-A[(8 * bj + p) * ld + k], x[p], t);
+            xs[k] = t;
+        }
+        __syncthreads();
+    }
+    int oc = out_slot ? out_slot[c] : c;
+    double *Lc = L + (size_t)oc * Kp * Kp;
+    bool isbad = bad != 0;
+    for (int e = tid; e < Kp * Kp; e += kCh2Threads) {
+        int i = e / Kp, j = e - i * Kp;
+        double v = j <= i ? A[i * ld + j] : 0.0;
+        Lc[e] = isbad ? NAN : v;
+    }
+    for (int j = tid; j < Kp; j += kCh2Threads) mu[(size_t)oc * Kp + j] = isbad ? NAN : xo[j];
+    if (tid == 0 && status) status[c] = isbad ? 1 : 0;
+    (void)K;
+}
+
 void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
                            const int *d_out_slot, int *d_status, cudaStream_t s) {
     ProfScope _ps(ST_CHOLESKY, s);
     if (C <= 0) return;
+    static const bool no_mma = getenv("ICPCUDA_NO_DMMA") && getenv("ICPCUDA_NO_DMMA")[0] == '1';
+    if (!no_mma) {
+        size_t smem2 = sizeof(double) * ((size_t)(Kp + 8) * (Kp + 4) + 3 * Kp);
+        ICP_REQUIRE(smem2 <= 227 * 1024, "rank too large for the shared-memory Cholesky (K <= 160)");
+        ICP_CUDA(cudaFuncSetAttribute(k_cholesky_solve_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        k_cholesky_solve_mma<<<C, kCh2Threads, smem2, s>>>(K, Kp, d_M, d_b, d_L, d_mu, d_out_slot, d_status);
+        ICP_CUDA(cudaGetLastError());
+        return;
+    }
     size_t smem = sizeof(double) * ((size_t)(Kp + 1) * (Kp + 1) + Kp);
     ICP_REQUIRE(smem <= 227 * 1024, "rank too large for the shared-memory Cholesky (K <= 160)");
     ICP_CUDA(cudaFuncSetAttribute(k_cholesky_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
