@@ -1,0 +1,108 @@
+"""GPU tests of the host-side mirror of the reference API (icp-proposal_b200/api.py): the classes a Scalismo
+chain would call (propose / logTransitionProbability / logValue), the fused SamplingRegistration and the logger."""
+import json
+import math
+
+import numpy as np
+import pytest
+
+from icp_proposal_b200 import api
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup(ctx, twin31):
+    m = twin31
+    model = api.StatisticalMeshModel(ctx, m["ref"], m["cells"], m["basis"], m["variance"])
+    target = api.TriangleMesh3D(ctx, m["target"], m["target_cells"])
+    om = orc.Model(m["ref"], m["cells"], m["basis"], m["variance"])
+    ot = orc.Mesh(m["target"], m["target_cells"])
+    yield m, model, target, om, ot
+    model.close(); target.close()
+
+
+def test_per_call_api_matches_oracle(setup):
+    m, model, target, om, ot = setup
+    K = model.rank
+    rng = np.random.default_rng(0)
+    ids = np.arange(2 * K); tp = m["target"][::26][:2 * K]
+    prop = api.NonRigidIcpProposal(model, target, 0.1, 10.0, 5.0, 2 * K, api.ModelSampling, rand=np.random.default_rng(5),
+                                   model_point_ids=ids, target_points=tp)
+    oprop = orc.IcpProposal(om, ot, 0.1, 10.0, 5.0, 0, True, ids, tp)
+    theta = model.initial_parameters().copy(shapeParameters=api.ShapeParameters(rng.normal(0, 0.3, K)))
+    new = prop.propose(theta)
+    assert new.generatedBy == "ShapeIcpProposal" and np.array_equal(new.allParameters[:10], theta.allParameters[:10])
+    z = np.random.default_rng(5).standard_normal(K)       # the stream the proposal consumed
+    np.testing.assert_allclose(new.allParameters, oprop.propose(theta.allParameters, z, closed_form=True), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(prop.logTransitionProbability(theta, new), oprop.log_transition(theta.allParameters, new.allParameters), rtol=1e-5)
+    np.testing.assert_allclose(prop.logTransitionProbability(new, theta), oprop.log_transition(new.allParameters, theta.allParameters), rtol=1e-5)
+    evs = api.ProductEvaluators.proximityAndIndependent(model, target, api.ModelToTargetEvaluation, 2.0, 4 * K, target_points=tp)
+    assert list(evs) == ["product", "prior", "distance"]
+    d = orc.eval_independent(om, ot, 0, 0.0, 2.0, np.arange(4 * K), tp, new.allParameters)
+    p = orc.eval_prior(K, new.allParameters)
+    np.testing.assert_allclose([evs[k].logValue(new) for k in evs], [p + d, p, d], rtol=1e-9)
+    hd = api.ProductEvaluators.proximityAndHausdorff(model, target, 100.0)
+    np.testing.assert_allclose(hd["distance_haussdorff"].logValue(new), orc.eval_hausdorff(om, ot, 100.0, new.allParameters), rtol=1e-9)
+
+
+def test_host_metropolis_hastings_loop(setup):
+    """The reference's own driver structure: Scalismo-style MH over the per-call (drop-in) classes."""
+    m, model, target, om, ot = setup
+    K = model.rank
+    rng = np.random.default_rng(1)
+    icp = api.MixedProposalDistributions.mixedProposalICP(model, target, 2 * K, rand=rng)
+    rnd = api.MixedProposalDistributions.mixedRandomShapeProposal(model, rand=rng)
+    gen = api.MixtureProposal.fromProposalsWithTransition((0.9, icp), (0.1, rnd), rand=rng)
+    evs = api.ProductEvaluators.proximityAndIndependent(model, target, api.ModelToTargetEvaluation, 2.0, 4 * K)
+    chain = api.MetropolisHastings(gen, evs["product"], rand=rng)
+    logger = api.JSONAcceptRejectLogger(None, evs)
+    theta = model.initial_parameters()
+    v0 = evs["product"].logValue(theta)
+    it = chain.iterator(theta, logger)
+    for _ in range(25):
+        theta = next(it)
+    assert logger.totalSamples == 25 and 0 < logger.numOfAccepted <= 25
+    assert evs["product"].logValue(theta) > v0
+    names = {l.name for l in logger.logStatus}
+    assert names <= {"IcpProposal-TargetSampling-0.1Step", "IcpProposal-ModelSampling-0.1Step", "RandomShape-0.1"}
+    acc = [l for l in logger.logStatus if l.status]
+    assert all(len(l.coeff) == K and len(l.rigid) == 9 for l in acc)
+
+
+def test_sampling_registration_fused(setup, tmp_path):
+    m, model, target, om, ot = setup
+    K = model.rank
+    icp = api.MixedProposalDistributions.mixedProposalICP(model, target, 2 * K)
+    rnd = api.MixedProposalDistributions.mixedRandomShapeProposal(model)
+    gen = api.MixtureProposal.fromProposalsWithTransition((0.9, icp), (0.1, rnd))
+    evs = api.ProductEvaluators.proximityAndIndependent(model, target, api.ModelToTargetEvaluation, 2.0, 4 * K)
+    reg = api.SamplingRegistration(model, target)
+    path = str(tmp_path / "icpProposalRegistration.json")
+    best = reg.runfitting(evs, gen, 300, jsonName=path)
+    log = json.load(open(path))
+    assert len(log) == 300 and set(log[0]) == {"index", "name", "logvalue", "status", "rigid", "coeff", "datetime"}
+    assert set(log[0]["logvalue"]) == {"product", "prior", "distance"}
+    # the registration moves the model onto the target: sub-millimetre average distance, and the best sample's
+    # product value equals the best accepted log entry
+    avg0, _ = api.RegistrationComparison.evaluateReconstruction2GroundTruth("init", model, model.initial_parameters(), target)
+    avg1, hd1 = api.RegistrationComparison.evaluateReconstruction2GroundTruth("best", model, best, target)
+    assert avg1 < 0.5 * avg0 and avg1 < 1.0
+    best_logged = max(l["logvalue"]["product"] for l in log if l["status"])
+    np.testing.assert_allclose(evs["product"].logValue(best), best_logged, rtol=1e-9)
+    # batched random-init chains (RunMHRandomInitComparison shape)
+    th0 = np.tile(model.initial_parameters().allParameters, (5, 1))
+    th0[1:, 10:] = np.random.default_rng(0).normal(0, math.sqrt(0.1), (4, K))
+    bests = reg.runfitting(evs, gen, 200, n_chains=5, initial_batch=th0)
+    assert len(bests) == 5
+    assert all(api.RegistrationComparison.evaluateReconstruction2GroundTruth(i, model, b, target)[0] < 1.5 for i, b in enumerate(bests))
+
+
+def test_deterministic_icp(setup):
+    m, model, target, om, ot = setup
+    fit = api.IcpBasedSurfaceFitting(model, target, 400, 1.0, api.ModelSampling)
+    mesh = fit.runfitting(15, iterationSeq=(1e-15,))
+    d = np.sqrt(target.closest_point_surface(mesh)[3])
+    d0 = np.sqrt(target.closest_point_surface(m["ref"])[3])
+    assert d.mean() < 0.25 * d0.mean()
