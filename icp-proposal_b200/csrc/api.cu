@@ -581,7 +581,7 @@ extern "C" int32_t icp_proposal_destroy(icp_proposal p) {
 namespace icp {
 
 void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const double *d_X, PosteriorWork &w, double *d_L,
-                        double *d_mu, const int *d_out_slot, cudaStream_t s) {
+                        double *d_mu, const int *d_out_slot, cudaStream_t s, const SharedCp *shared) {
     if (C <= 0) return;
     icp_model m = p->model;
     icp_target t = p->target;
@@ -602,20 +602,28 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
     if (tsamp) {
         // :118 currentMesh.pointSet.findClosestPoint(targetPoint): vertex BVH refit to the current meshes
         w.prim.ensure(tot);
-        bvh_refit(m->vert_bvh, C, d_X, m->N, nullptr, s);
-        NearestArgs a;
-        a.bvh = &m->vert_bvh; a.X = d_X; a.N = m->N; a.C = C; a.nq = n; a.q = p->tp.p; a.out_prim = w.prim.p;
-        launch_nearest(a, s);
+        if (!launch_nearest_vertex_brute(m->N, C, d_X, n, p->tp.p, 0, m->scale, w.prim.p, nullptr, s)) {
+            bvh_refit(m->vert_bvh, C, d_X, m->N, nullptr, s);
+            NearestArgs a;
+            a.bvh = &m->vert_bvh; a.X = d_X; a.N = m->N; a.C = C; a.nq = n; a.q = p->tp.p; a.out_prim = w.prim.p;
+            launch_nearest(a, s);
+        }
         oa.tp = p->tp.p; oa.near_vid = w.prim.p;
     } else {
         // :97 target.operations.closestPointOnSurface(currentMeshPoint)
-        w.cp.ensure(3 * tot);
-        NearestArgs a;
-        a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = n;
-        a.Xq = d_X; a.q_ids = p->ids.p; a.Nq = m->N; a.out_cp = w.cp.p;
-        launch_nearest(a, s);
-        oa.ids = p->ids.p; oa.cp = w.cp.p; oa.cp_on_boundary = nullptr;
-        if (p->prm.boundary_aware && t->has_boundary) {
+        const bool need_flags = p->prm.boundary_aware && t->has_boundary;
+        if (shared && !need_flags) {
+            oa.cp = shared->cp; oa.cp_stride = shared->stride; oa.cp_map = shared->map;
+        } else {
+            w.cp.ensure(3 * tot);
+            NearestArgs a;
+            a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = n;
+            a.Xq = d_X; a.q_ids = p->ids.p; a.Nq = m->N; a.out_cp = w.cp.p;
+            launch_nearest(a, s);
+            oa.cp = w.cp.p; oa.cp_stride = n; oa.cp_map = nullptr;
+        }
+        oa.ids = p->ids.p; oa.cp_on_boundary = nullptr;
+        if (need_flags) {
             // :98-99 target.pointSet.findClosestPoint(targetPoint).id -> pointIsOnBoundary
             w.prim.ensure(tot); w.flags.ensure(tot);
             NearestArgs v;
@@ -825,10 +833,12 @@ extern "C" int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t dire
         oa.m = md; oa.prm = p->prm; oa.C = C; oa.theta = dth.p; oa.X = w.X.p; oa.iso = 1; oa.iso_sigma2 = sigma2;
         if (tsamp) {
             w.prim.ensure(tot);
-            bvh_refit(m->vert_bvh, C, w.X.p, m->N, nullptr, s);
-            NearestArgs a;
-            a.bvh = &m->vert_bvh; a.X = w.X.p; a.N = m->N; a.C = C; a.nq = n; a.q = tmp.tp.p; a.out_prim = w.prim.p;
-            launch_nearest(a, s);
+            if (!launch_nearest_vertex_brute(m->N, C, w.X.p, n, tmp.tp.p, 0, m->scale, w.prim.p, nullptr, s)) {
+                bvh_refit(m->vert_bvh, C, w.X.p, m->N, nullptr, s);
+                NearestArgs a;
+                a.bvh = &m->vert_bvh; a.X = w.X.p; a.N = m->N; a.C = C; a.nq = n; a.q = tmp.tp.p; a.out_prim = w.prim.p;
+                launch_nearest(a, s);
+            }
             oa.tp = tmp.tp.p; oa.near_vid = w.prim.p;
         } else {
             w.cp.ensure(3 * tot);
@@ -836,7 +846,7 @@ extern "C" int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t dire
             a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = n;
             a.Xq = w.X.p; a.q_ids = tmp.ids.p; a.Nq = m->N; a.out_cp = w.cp.p;
             launch_nearest(a, s);
-            oa.ids = tmp.ids.p; oa.cp = w.cp.p;
+            oa.ids = tmp.ids.p; oa.cp = w.cp.p; oa.cp_stride = n; oa.cp_map = nullptr;
         }
         ObsDev od{n, w.vid.p, w.F.p, w.y.p, w.nobs.p};
         launch_observations(oa, od, s);
@@ -932,7 +942,7 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
             NearestArgs a;
             a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = e->n_ids;
             a.Xq = d_X; a.q_ids = e->ids.p; a.Nq = m->N; a.out_d2 = w.d2_m2t.p;
-            if (collective) { w.cp_m2t.ensure(3 * tot); a.out_cp = w.cp_m2t.p; }
+            if (collective || w.force_cp_m2t) { w.cp_m2t.ensure(3 * tot); a.out_cp = w.cp_m2t.p; }
             launch_nearest(a, s);
             if (collective && t->has_boundary) {
                 // CollectiveAverage...:46-47: nearest target vertex of the closest point, dropped when on the boundary
@@ -958,11 +968,13 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
                 // CollectiveAverage...:58-59: id of the nearest vertex of the MODEL sample, looked up in the
                 // TARGET's boundary table
                 w.prim.ensure(tot); w.skip_t2m.ensure(tot);
-                bvh_refit(m->vert_bvh, C, d_X, m->N, nullptr, s);
-                NearestArgs v;
-                v.bvh = &m->vert_bvh; v.X = d_X; v.N = m->N; v.C = C; v.nq = e->n_tp; v.q = w.cp_t2m.p; v.q_per_chain = 1;
-                v.out_prim = w.prim.p;
-                launch_nearest(v, s);
+                if (!launch_nearest_vertex_brute(m->N, C, d_X, e->n_tp, w.cp_t2m.p, 1, m->scale, w.prim.p, nullptr, s)) {
+                    bvh_refit(m->vert_bvh, C, d_X, m->N, nullptr, s);
+                    NearestArgs v;
+                    v.bvh = &m->vert_bvh; v.X = d_X; v.N = m->N; v.C = C; v.nq = e->n_tp; v.q = w.cp_t2m.p; v.q_per_chain = 1;
+                    v.out_prim = w.prim.p;
+                    launch_nearest(v, s);
+                }
                 launch_lookup_flags((int64_t)tot, w.prim.p, t->boundary.p, t->Nt, w.skip_t2m.p, s);
                 ra.skip_t2m = w.skip_t2m.p;
             }

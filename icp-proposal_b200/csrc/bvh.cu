@@ -372,6 +372,100 @@ void launch_nearest(const NearestArgs &a, cudaStream_t s) {
     ICP_CUDA(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------
+// nearest vertex of a small per-chain mesh, brute force: FP32 screening of all N vertices from shared memory,
+// exact FP64 re-evaluation of every vertex the FP32 bound cannot exclude (result identical to an FP64 scan,
+// ties -> lowest index). Replaces the vertex-BVH refit + traversal when N is a few thousand
+// (currentMesh.pointSet.findClosestPoint, NonRigidIcpProposal.scala:118).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBruteQ = 2;  // queries per thread: one shared-memory broadcast of a vertex serves kBruteQ pairs per lane
+
+__global__ void __launch_bounds__(128) k_nearest_vertex_brute(int N, int C, const double *__restrict__ X, long long nq,
+                                                              const double *__restrict__ q, int q_per_chain, float scale,
+                                                              int *__restrict__ out_prim, double *__restrict__ out_d2) {
+    extern __shared__ double smd[];
+    double *sx = smd;                                            // [3 N] exact coordinates
+    float4 *sv = reinterpret_cast<float4 *>(smd + 3 * (size_t)((N + 1) & ~1));  // [N] FP32 copy (x, y, z, -)
+    const int c = blockIdx.y;
+    const double *Xc = X + (size_t)c * N * 3;
+    for (int e = threadIdx.x; e < 3 * N; e += blockDim.x) sx[e] = Xc[e];
+    __syncthreads();
+    for (int v = threadIdx.x; v < N; v += blockDim.x)
+        sv[v] = make_float4((float)sx[3 * v], (float)sx[3 * v + 1], (float)sx[3 * v + 2], 0.f);
+    __syncthreads();
+    const long long i0 = (long long)blockIdx.x * blockDim.x * kBruteQ + threadIdx.x;
+    double qx[kBruteQ], qy[kBruteQ], qz[kBruteQ];
+    float fx[kBruteQ], fy[kBruteQ], fz[kBruteQ], best[kBruteQ], second[kBruteQ];
+    int bid[kBruteQ];
+#pragma unroll
+    for (int t = 0; t < kBruteQ; t++) {
+        long long i = i0 + (long long)t * blockDim.x;
+        const double *src = q + ((q_per_chain ? (size_t)c * nq : 0) + (i < nq ? i : 0)) * 3;
+        qx[t] = src[0]; qy[t] = src[1]; qz[t] = src[2];
+        fx[t] = (float)qx[t]; fy[t] = (float)qy[t]; fz[t] = (float)qz[t];
+        best[t] = INFINITY; second[t] = INFINITY; bid[t] = -1;
+    }
+    // single FP32 pass: minimum, runner-up and argmin
+#pragma unroll 4
+    for (int v = 0; v < N; v++) {
+        float4 p = sv[v];
+#pragma unroll
+        for (int t = 0; t < kBruteQ; t++) {
+            float dx = fx[t] - p.x, dy = fy[t] - p.y, dz = fz[t] - p.z;
+            float d2f = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            bool better = d2f < best[t];
+            second[t] = fminf(second[t], better ? best[t] : d2f);
+            bid[t] = better ? v : bid[t];
+            best[t] = better ? d2f : best[t];
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kBruteQ; t++) {
+        long long i = i0 + (long long)t * blockDim.x;
+        if (i >= nq) continue;
+        // |d2f - d2| <= 2 sqrt(3) d delta + 3 delta^2 + 4 eps d2, delta = error of one FP32 coordinate difference.
+        // If the runner-up lies beyond twice that bound the FP32 argmin is the exact FP64 argmin.
+        const float S = fmaxf(fmaxf(fabsf(fx[t]), fabsf(fy[t])), fmaxf(fabsf(fz[t]), scale));
+        const float delta = S * 2.4e-7f;  // 2^-22 S
+        const float thresh = best[t] + 8.f * sqrtf(best[t]) * delta + 8.f * delta * delta + 1e-6f * best[t];
+        int id = bid[t];
+        double d2best = INFINITY;
+        if (!(second[t] > thresh) || id < 0) {
+            // rare: near-tie (or NaN query) -> exact FP64 scan of every vertex the FP32 bound cannot exclude
+            id = -1;
+            for (int v = 0; v < N; v++) {
+                float4 p = sv[v];
+                float dx = fx[t] - p.x, dy = fy[t] - p.y, dz = fz[t] - p.z;
+                float d2f = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                if (d2f <= thresh) {
+                    double ex = qx[t] - sx[3 * v], ey = qy[t] - sx[3 * v + 1], ez = qz[t] - sx[3 * v + 2];
+                    double d2 = ex * ex + ey * ey + ez * ez;
+                    if (d2 < d2best || (d2 == d2best && v < id)) { d2best = d2; id = v; }
+                }
+            }
+        } else {
+            double ex = qx[t] - sx[3 * id], ey = qy[t] - sx[3 * id + 1], ez = qz[t] - sx[3 * id + 2];
+            d2best = ex * ex + ey * ey + ez * ez;
+        }
+        size_t g = (size_t)c * nq + i;
+        if (id < 0) d2best = NAN;
+        if (out_prim) out_prim[g] = id;
+        if (out_d2) out_d2[g] = d2best;
+    }
+}
+
+bool launch_nearest_vertex_brute(int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, double scale,
+                                 int *d_prim, double *d_d2, cudaStream_t s) {
+    size_t smem = sizeof(double) * 3 * (size_t)((N + 1) & ~1) + sizeof(float4) * (size_t)N;
+    if (smem > 100 * 1024 || C <= 0 || nq <= 0) return false;
+    ProfScope _ps(ST_NEAREST_DYNAMIC, s);
+    if (smem > 48 * 1024) ICP_CUDA(cudaFuncSetAttribute(k_nearest_vertex_brute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((nq + 128 * kBruteQ - 1) / (128 * kBruteQ)), C);
+    k_nearest_vertex_brute<<<grid, 128, smem, s>>>(N, C, d_X, (long long)nq, d_q, q_per_chain, (float)scale, d_prim, d_d2);
+    ICP_CUDA(cudaGetLastError());
+    return true;
+}
+
 // flags[i] = table[prim[i]] (0 when prim < 0)
 __global__ void k_lookup_flags(long long n, const int *__restrict__ prim, const uint8_t *__restrict__ table, int table_n,
                                uint8_t *__restrict__ flags) {

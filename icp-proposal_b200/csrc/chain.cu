@@ -12,6 +12,7 @@
 // ICP component - for the proposed state.
 #include <cmath>
 #include <cstring>
+#include <unordered_map>
 
 #include "icp_device.cuh"
 #include "icp_internal.h"
@@ -101,11 +102,34 @@ __device__ void warp_backsolve_smem(const double *sL, int Kp, const double *z_sm
     __syncwarp();
 }
 
+// same with the lower triangle packed row-major (row i at offset i (i + 1) / 2)
+__device__ void warp_backsolve_packed(const double *sL, int Kp, const double *z_sm, double *w_sm) {
+    int lane = threadIdx.x & 31;
+    double zr[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) { int k = lane + 32 * q; zr[q] = k < Kp ? z_sm[k] : 0.0; }
+    for (int i = Kp - 1; i >= 0; i--) {
+        const double *row = sL + (i * (i + 1)) / 2;
+        int owner = i & 31, slot = i >> 5;
+        double zi = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (q == slot) zi = zr[q];
+        double wi = __shfl_sync(0xffffffffu, zi, owner) / row[i];
+        if (lane == 0) w_sm[i] = wi;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            int k = lane + 32 * q;
+            if (k < i) zr[q] = fma(-row[k], wi, zr[q]);
+        }
+    }
+    __syncwarp();
+}
+
 // MixtureProposal.propose (pick the first component whose cumulative weight reaches r) + the component's propose
-__global__ void __launch_bounds__(128) k_chain_propose(ChainParams P, ModelDev m, StateDev st, RngDev rng) {
+__global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m, StateDev st, RngDev rng) {
     extern __shared__ double sm[];
     const int K = P.K, Kp = P.Kp, Lt = K + kTheta0, C = P.C;
-    double *sz = sm, *sw = sm + Kp, *sL = sm + 2 * Kp;  // sL: [Kp][Kp]
+    double *sz = sm, *sw = sm + Kp, *sL = sm + 2 * Kp;  // sL: packed lower triangle, Kp (Kp + 1) / 2
     __shared__ int s_ci;
     int c = blockIdx.x;
     unsigned int step = (unsigned int)*st.step;
@@ -139,17 +163,45 @@ __global__ void __launch_bounds__(128) k_chain_propose(ChainParams P, ModelDev m
     if (cd.kind == ICP_PROP_ICP) {
         size_t pslot = (size_t)cd.icp_index * 2 * C + st.slot_cur[c];
         const double *Lc = st.L + pslot * Kp * Kp, *muc = st.mu + pslot * Kp;
-        for (int e = threadIdx.x; e < Kp * Kp; e += blockDim.x) sL[e] = Lc[e];
+        // lower triangle of L, packed row-major (row i at i (i + 1) / 2): warps take rows, lanes take columns
+        {
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+            for (int i0 = warp; i0 < Kp; i0 += 4 * nw) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    int i = i0 + r * nw;
+                    if (i < Kp) {
+                        const double *src = Lc + (size_t)i * Kp;
+                        double *dst = sL + (i * (i + 1)) / 2;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            int j = lane + 32 * q;
+                            if (j <= i) dst[j] = __ldg(src + j);
+                        }
+                    }
+                }
+            }
+        }
         __syncthreads();
-        if (threadIdx.x < 32) warp_backsolve_smem(sL, Kp, sz, sw);
+        if (threadIdx.x < 32) warp_backsolve_packed(sL, Kp, sz, sw);
         __syncthreads();
         for (int k = threadIdx.x; k < Kp; k += blockDim.x) sz[k] = muc[k] + sw[k];
+        __syncthreads();
+        // S v with S symmetric (read column-wise, coalesced); two halves of the k range per output
+        double *part = sL;  // the factor is no longer needed
+        for (int idx = threadIdx.x; idx < 2 * Kp; idx += blockDim.x) {
+            int jj = idx % Kp, half = idx / Kp;
+            int k0 = half * (Kp / 2), k1 = half ? Kp : Kp / 2;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int k = k0; k < k1; k++) acc = fma(__ldg(&m.S[(size_t)k * Kp + jj]), sz[k], acc);
+            part[idx] = acc;
+        }
         __syncthreads();
         for (int j = threadIdx.x; j < Lt; j += blockDim.x) {
             if (j < kTheta0) { to[j] = th[j]; continue; }
             int jj = j - kTheta0;
-            double acc = 0.0;
-            for (int k = 0; k < Kp; k++) acc = fma(__ldg(&m.S[(size_t)k * Kp + jj]), sz[k], acc);
+            double acc = part[jj] + part[Kp + jj];
             to[j] = th[j] + (acc - th[j]) * cd.step;  // NonRigidIcpProposal.scala:61-62
         }
     } else {
@@ -304,6 +356,8 @@ struct icp_chain_s {
     DevBuf<int> cur_sel, slot_cur, slot_prop, comp_sel, step;
     DevBuf<long long> n_acc;
     std::vector<PosteriorWork> pwork;
+    std::vector<DevBuf<int>> cp_map;     // per ICP component: index of its model points in the evaluator's list
+    std::vector<char> cp_shared;
     EvalWork ework;
     DevBuf<int> estatus;
     // staging for the host-buffer entry point
@@ -367,6 +421,37 @@ extern "C" int32_t icp_chain_create(icp_model m, icp_target t, const icp_compone
             }
         }
         ch->pwork.resize(P.n_icp);
+        // closest points shared with the evaluator: a model-sampling proposal whose point ids all occur in the
+        // evaluator's model->target list reuses those traversals instead of repeating them
+        ch->cp_map.resize(P.n_icp);
+        ch->cp_shared.assign(P.n_icp, 0);
+        {
+            const icp_evaluator_params &ep = evaluator->prm;
+            bool ev_m2t = ep.kind == ICP_EVAL_HAUSDORFF || ((ep.kind == ICP_EVAL_INDEPENDENT || ep.kind == ICP_EVAL_COLLECTIVE) && ep.mode != ICP_TARGET_TO_MODEL);
+            if (ev_m2t && evaluator->n_ids > 0) {
+                std::vector<int> eids(evaluator->n_ids);
+                ICP_CUDA(cudaMemcpy(eids.data(), evaluator->ids.p, sizeof(int) * eids.size(), cudaMemcpyDeviceToHost));
+                std::unordered_map<int, int> pos;
+                for (int i = (int)eids.size() - 1; i >= 0; i--) pos[eids[i]] = i;
+                for (int k = 0; k < P.n_icp; k++) {
+                    icp_proposal pr = ch->icp_props[k];
+                    if (pr->prm.direction != ICP_MODEL_SAMPLING || pr->n_ids == 0) continue;
+                    if (pr->prm.boundary_aware && t->has_boundary) continue;
+                    std::vector<int> pids(pr->n_ids), map(pr->n_ids);
+                    ICP_CUDA(cudaMemcpy(pids.data(), pr->ids.p, sizeof(int) * pids.size(), cudaMemcpyDeviceToHost));
+                    bool ok = true;
+                    for (int i = 0; i < pr->n_ids && ok; i++) {
+                        auto it = pos.find(pids[i]);
+                        if (it == pos.end()) ok = false; else map[i] = it->second;
+                    }
+                    if (!ok) continue;
+                    ch->cp_map[k].upload(map.data(), map.size(), _ctx->stream);
+                    ch->cp_shared[k] = 1;
+                    ch->ework.force_cp_m2t = true;
+                }
+                ICP_CUDA(cudaStreamSynchronize(_ctx->stream));
+            }
+        }
         ICP_CUDA(cudaEventCreate(&ch->ev0));
         ICP_CUDA(cudaEventCreate(&ch->ev1));
         const char *env = getenv("ICPCUDA_NO_GRAPH");
@@ -417,7 +502,8 @@ void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, cons
     evaluator_pipeline(ch->evaluator, ch->ework, C, d_theta, ch->X.p, d_values, ch->estatus.p, r.s);
     for (int i = 0; i < ch->P.n_icp; i++) {
         double *Lb = r.st.L + (size_t)i * 2 * C * Kp * Kp, *mub = r.st.mu + (size_t)i * 2 * C * Kp;
-        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, r.s);
+        SharedCp sh{ch->ework.cp_m2t.p, ch->evaluator->n_ids, ch->cp_map[i].p};
+        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, r.s, ch->cp_shared[i] ? &sh : nullptr);
     }
 }
 
@@ -427,10 +513,10 @@ void enqueue_step(RunCtx &r) {
     const int C = r.C, Kp = m->Kp;
     ChainParams P = ch->P;
     P.C = C;
-    size_t smem_p = sizeof(double) * ((size_t)2 * Kp + (size_t)Kp * Kp);
+    size_t smem_p = sizeof(double) * ((size_t)2 * Kp + (size_t)Kp * (Kp + 1) / 2);
     {
         ProfScope ps(ST_PROPOSE, r.s);
-        k_chain_propose<<<C, 128, smem_p, r.s>>>(P, m->dev(), r.st, r.rng);
+        k_chain_propose<<<C, 256, smem_p, r.s>>>(P, m->dev(), r.st, r.rng);
         ICP_CUDA(cudaGetLastError());
     }
     enqueue_state_eval(r, r.st.theta_prop, r.st.values_prop, r.st.slot_prop);
@@ -479,7 +565,7 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
         ICP_CUDA(cudaGetLastError());
     }
     {
-        size_t smem_p = sizeof(double) * ((size_t)2 * Kp + (size_t)Kp * Kp);
+        size_t smem_p = sizeof(double) * ((size_t)2 * Kp + (size_t)Kp * (Kp + 1) / 2);
         ICP_REQUIRE(smem_p <= 227 * 1024, "rank too large for the propose kernel");
         ICP_CUDA(cudaFuncSetAttribute(k_chain_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
     }

@@ -145,6 +145,10 @@ struct NearestArgs {
     double *out_d2 = nullptr;
 };
 void launch_nearest(const NearestArgs &a, cudaStream_t s);
+// brute-force nearest vertex of C small meshes X[C][N][3] (FP32 screening + exact FP64); returns false (nothing
+// launched) when N is too large for the shared-memory tile, in which case the caller uses the vertex BVH
+bool launch_nearest_vertex_brute(int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, double scale,
+                                 int *d_prim, double *d_d2, cudaStream_t s);
 
 // ---- model kernels ---------------------------------------------------------------------------------
 struct ModelDev {  // plain device view, passed by value to kernels
@@ -175,7 +179,9 @@ struct ObsArgs {
     const double *X;       // [C][N][3]
     // model sampling: closest points of the sampled vertices on the target
     const int *ids;        // [n]
-    const double *cp;      // [C][n][3]
+    const double *cp;      // [C][cp_stride][3]; observation i reads entry cp_map[i] (or i when cp_map is null)
+    int cp_stride;
+    const int *cp_map;
     const uint8_t *cp_on_boundary;  // [C][n] or nullptr
     // target sampling: nearest current-mesh vertex per target point
     const double *tp;      // [n][3]
@@ -312,6 +318,7 @@ struct EvalWork {
     DevBuf<double> X, cp_m2t, d2_m2t, cp_t2m, d2_t2m;
     DevBuf<int> prim;
     DevBuf<uint8_t> skip_m2t, skip_t2m;
+    bool force_cp_m2t = false;  // also keep the model->target closest points (shared with ICP proposals)
 };
 }  // namespace icp
 
@@ -330,8 +337,15 @@ struct icp_evaluator_s {
 namespace icp {
 // correspondence + posterior pipeline: L / mu (at out_slot[c] or c) for C parameter vectors on the device.
 // d_X: transformed meshes [C][N][3] if the caller already has them, else nullptr.
+// shared: closest points another consumer already computed for a superset of this proposal's model points
+// (the evaluator's model->target queries in the chain runner); nullptr = run the traversal here.
+struct SharedCp {
+    const double *cp;   // [C][stride][3]
+    int stride;
+    const int *map;     // [n_ids] index into the shared list
+};
 void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const double *d_X, PosteriorWork &w, double *d_L,
-                        double *d_mu, const int *d_out_slot, cudaStream_t s);
+                        double *d_mu, const int *d_out_slot, cudaStream_t s, const SharedCp *shared = nullptr);
 // distance evaluator pipeline: values [C][3] = {product, prior, distance}
 void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_theta, const double *d_X, double *d_values,
                         int *d_status, cudaStream_t s);

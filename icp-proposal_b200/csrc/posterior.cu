@@ -40,7 +40,8 @@ __global__ void k_observations(ObsArgs a, ObsDev o) {
         else if (a.prm.boundary_aware && m.boundary[id]) drop = true;  // :119,124
     } else {
         id = a.ids[i];
-        tx = a.cp[3 * g]; ty = a.cp[3 * g + 1]; tz = a.cp[3 * g + 2];  // :97 closest point on the target
+        const double *cpp = a.cp + ((size_t)c * a.cp_stride + (a.cp_map ? a.cp_map[i] : i)) * 3;
+        tx = cpp[0]; ty = cpp[1]; tz = cpp[2];                          // :97 closest point on the target
         if (a.prm.boundary_aware && a.cp_on_boundary && a.cp_on_boundary[g]) drop = true;  // :99,104
     }
     double *F = o.F + 9 * g, *y = o.y + 3 * g;
@@ -485,9 +486,31 @@ __global__ void __launch_bounds__(kCh2Threads) k_cholesky_solve_mma(int K, int K
     const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double *Mc = M + (size_t)c * Kp * Kp;
     if (tid == 0) bad = 0;
-    for (int e = tid; e < Kp * Kp; e += kCh2Threads) {
-        int i = e / Kp, j = e - i * Kp;
-        A[i * ld + j] = Mc[e];
+    // lower triangle only; warps take rows, lanes take column pairs, 16 independent 16-byte loads in flight per
+    // thread (a dependent load -> store loop costs one L2 round trip per element)
+    {
+        constexpr int nw = kCh2Threads / 32;
+        for (int i0 = warp; i0 < Kp; i0 += 4 * nw) {
+            double2 v[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                int i = i0 + r * nw;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    int j = 2 * (lane + 32 * q);
+                    v[r][q] = (i < Kp && j <= i) ? __ldg(reinterpret_cast<const double2 *>(Mc + (size_t)i * Kp + j)) : make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                int i = i0 + r * nw;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    int j = 2 * (lane + 32 * q);
+                    if (i < Kp && j <= i) *reinterpret_cast<double2 *>(A + i * ld + j) = v[r][q];
+                }
+            }
+        }
     }
     for (int e = tid; e < 8 * ld; e += kCh2Threads) {
         int r = e / ld, j = e - r * ld;
@@ -502,8 +525,14 @@ __global__ void __launch_bounds__(kCh2Threads) k_cholesky_solve_mma(int K, int K
                 double2 cc = *reinterpret_cast<double2 *>(pc);
                 const double *pa = A + (8 * bi + fr) * ld + fc;
                 const double *pb = A + (8 * bj + fr) * ld + fc;
+                // two accumulators halve the dependent DMMA chain
+                double e0 = 0.0, e1 = 0.0;
 #pragma unroll 4
-                for (int k = 0; k < 8 * bj; k += 4) dmma_8x8x4(cc.x, cc.y, -pa[k], pb[k]);
+                for (int k = 0; k < 8 * bj; k += 8) {
+                    dmma_8x8x4(cc.x, cc.y, -pa[k], pb[k]);
+                    dmma_8x8x4(e0, e1, -pa[k + 4], pb[k + 4]);
+                }
+                cc.x += e0; cc.y += e1;
                 *reinterpret_cast<double2 *>(pc) = cc;
             }
             __syncthreads();
@@ -521,8 +550,13 @@ __global__ void __launch_bounds__(kCh2Threads) k_cholesky_solve_mma(int K, int K
         for (int j = 0; j < 8; j++) {
             double s = l[j][j];
             if (!(s > 0.0)) mybad = true;
-            double d = sqrt(s);
-            inv[j] = 1.0 / d;
+            // 1/sqrt(s) by rsqrt + one Newton step (full double accuracy), sqrt(s) = s * inv: one short dependent
+            // chain instead of a software sqrt followed by a software divide
+            double r = rsqrt(s);
+            r = fma(r * 0.5, fma(-s * r, r, 1.0), r);
+            inv[j] = r;
+            double d = s * r;
+            d = fma(fma(-d, d, s), 0.5 * r, d);
             l[j][j] = d;
 #pragma unroll
             for (int i = j + 1; i < 8; i++) l[i][j] *= inv[j];
