@@ -252,6 +252,7 @@ def run_gpu(args):
                                                                       h_thl.ctypes.data)
     io.theta_final, io.n_accepted = h_fin.ctypes.data, h_nacc.ctypes.data
     import ctypes as Cc
+    _lib.check(chain.lib.icp_chain_run(chain.h, C, warm, _lib.dptr(h_th0), Cc.byref(io)), ctx.h)   # W untimed warm-up steps
     barrier()
     t0 = time.perf_counter()
     _lib.check(chain.lib.icp_chain_run(chain.h, C, e_steps, _lib.dptr(h_th0), Cc.byref(io)), ctx.h)

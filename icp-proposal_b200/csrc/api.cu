@@ -2,6 +2,7 @@
 // the batched proposal / evaluator calls and the pipelines they share with the chain runner.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -90,6 +91,11 @@ extern "C" int32_t icp_ctx_create(int32_t device, icp_ctx *out) {
         ctx->sm_count = prop.multiProcessorCount;
         ctx->device_name = prop.name;
         ICP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        for (int i = 0; i < icp_ctx_s::kAux; i++) {
+            ICP_CUDA(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+            ICP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+        }
+        ICP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         *out = ctx;
         return ICP_OK;
     } catch (...) {
@@ -105,6 +111,11 @@ extern "C" int32_t icp_ctx_destroy(icp_ctx ctx) {
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
+        for (int i = 0; i < icp_ctx_s::kAux; i++) {
+            if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); }
+            if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+        }
+        if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     }
     delete ctx;
     return ICP_OK;
@@ -555,6 +566,16 @@ extern "C" int32_t icp_proposal_create(icp_model m, icp_target t, const icp_prop
         p->model = m; p->target = t; p->prm = *params; p->n_ids = n_ids; p->n_tp = n_tp;
         p->ids.upload(model_point_ids, n_ids, _ctx->stream);
         p->tp.upload(target_points, (size_t)3 * n_tp, _ctx->stream);
+        // constant-Gram fast path: model sampling, anisotropic noise with sd_n <= sd_t (kappa >= 0)
+        {
+            const char *env = getenv("ICPCUDA_NO_GRAM_FAST");
+            if (params->direction == ICP_MODEL_SAMPLING && n_ids > 0 && params->noise_along_normal <= params->tangential_noise &&
+                !(env && env[0] == '1')) {
+                p->Gs.alloc((size_t)m->Kp * m->Kp);
+                launch_gram_rows(m->dev(), n_ids, p->ids.p, p->Gs.p, _ctx->stream);
+                p->gram_fast = true;
+            }
+        }
         sync_stream(_ctx);
         *out = p;
         return ICP_OK;
@@ -636,7 +657,12 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
     }
     ObsDev od{n, w.vid.p, w.F.p, w.y.p, w.nobs.p};
     launch_observations(oa, od, s);
-    launch_posterior_build(md, C, od, w.M.p, w.b.p, s);
+    // every observation is kept (no boundary filtering possible) -> the Gram part of M is the proposal's constant
+    const bool all_kept = !tsamp && !(p->prm.boundary_aware && t->has_boundary);
+    GramFast gf{p->Gs.p, 1.0 / (p->prm.tangential_noise * p->prm.tangential_noise),
+                std::sqrt(std::max(0.0, 1.0 - (p->prm.noise_along_normal * p->prm.noise_along_normal) /
+                                                  (p->prm.tangential_noise * p->prm.tangential_noise)))};
+    launch_posterior_build(md, C, od, w.M.p, w.b.p, s, (p->gram_fast && all_kept) ? &gf : nullptr);
     launch_cholesky_solve(C, m->K, Kp, w.M.p, w.b.p, d_L, d_mu, d_out_slot, w.status.p, s);
 }
 

@@ -388,7 +388,14 @@ __global__ void __launch_bounds__(128) k_nearest_vertex_brute(int N, int C, cons
     float4 *sv = reinterpret_cast<float4 *>(smd + 3 * (size_t)((N + 1) & ~1));  // [N] FP32 copy (x, y, z, -)
     const int c = blockIdx.y;
     const double *Xc = X + (size_t)c * N * 3;
-    for (int e = threadIdx.x; e < 3 * N; e += blockDim.x) sx[e] = Xc[e];
+    // tile load with 8 independent loads in flight per thread (a load -> store loop pays one L2 round trip per element)
+    for (int e0 = threadIdx.x; e0 < 3 * N; e0 += 8 * blockDim.x) {
+        double tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; tmp[u] = e < 3 * N ? __ldg(Xc + e) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; if (e < 3 * N) sx[e] = tmp[u]; }
+    }
     __syncthreads();
     for (int v = threadIdx.x; v < N; v += blockDim.x)
         sv[v] = make_float4((float)sx[3 * v], (float)sx[3 * v + 1], (float)sx[3 * v + 2], 0.f);

@@ -357,7 +357,8 @@ struct icp_chain_s {
     DevBuf<long long> n_acc;
     std::vector<PosteriorWork> pwork;
     std::vector<DevBuf<int>> cp_map;     // per ICP component: index of its model points in the evaluator's list
-    std::vector<char> cp_shared;
+    std::vector<char> cp_shared, on_side;
+    bool use_streams = true;
     EvalWork ework;
     DevBuf<int> estatus;
     // staging for the host-buffer entry point
@@ -425,6 +426,8 @@ extern "C" int32_t icp_chain_create(icp_model m, icp_target t, const icp_compone
         // evaluator's model->target list reuses those traversals instead of repeating them
         ch->cp_map.resize(P.n_icp);
         ch->cp_shared.assign(P.n_icp, 0);
+        ch->on_side.assign(P.n_icp, 0);
+        { const char *e2 = getenv("ICPCUDA_NO_STREAMS"); ch->use_streams = !(e2 && e2[0] == '1'); }
         {
             const icp_evaluator_params &ep = evaluator->prm;
             bool ev_m2t = ep.kind == ICP_EVAL_HAUSDORFF || ((ep.kind == ICP_EVAL_INDEPENDENT || ep.kind == ICP_EVAL_COLLECTIVE) && ep.mode != ICP_TARGET_TO_MODEL);
@@ -498,13 +501,34 @@ void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, cons
     icp_chain ch = r.ch;
     icp_model m = ch->model;
     const int C = r.C, Kp = m->Kp;
+    icp_ctx ctx = m->ctx;
     launch_reconstruct(m->dev(), C, d_theta, ch->X.p, r.s);
+    // fork: ICP pipelines that do not consume the evaluator's closest points run on side streams, concurrently with
+    // the evaluator and with each other (their Cholesky phases are latency bound and overlap the DMMA of the rest).
+    // Profiling runs stay on one stream so that the per-kernel event times do not overlap.
+    // (the model's vertex-BVH boxes are shared scratch: only fork when the nearest-vertex queries use the brute-force tile)
+    const bool brute_ok = sizeof(double) * 3 * (size_t)((m->N + 1) & ~1) + sizeof(float4) * (size_t)m->N <= 100 * 1024;
+    const bool fork = !g_prof && ch->use_streams && brute_ok;
+    int n_side = 0;
+    if (fork) ICP_CUDA(cudaEventRecord(ctx->ev_fork, r.s));
+    for (int i = 0; i < ch->P.n_icp; i++) {
+        if (ch->cp_shared[i] || !fork || n_side >= icp_ctx_s::kAux) continue;
+        cudaStream_t ss = ctx->aux[n_side];
+        ICP_CUDA(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+        double *Lb = r.st.L + (size_t)i * 2 * C * Kp * Kp, *mub = r.st.mu + (size_t)i * 2 * C * Kp;
+        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, ss, nullptr);
+        ICP_CUDA(cudaEventRecord(ctx->ev_join[n_side], ss));
+        ch->on_side[i] = 1;
+        n_side++;
+    }
     evaluator_pipeline(ch->evaluator, ch->ework, C, d_theta, ch->X.p, d_values, ch->estatus.p, r.s);
     for (int i = 0; i < ch->P.n_icp; i++) {
+        if (ch->on_side[i]) { ch->on_side[i] = 0; continue; }
         double *Lb = r.st.L + (size_t)i * 2 * C * Kp * Kp, *mub = r.st.mu + (size_t)i * 2 * C * Kp;
         SharedCp sh{ch->ework.cp_m2t.p, ch->evaluator->n_ids, ch->cp_map[i].p};
         posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, r.s, ch->cp_shared[i] ? &sh : nullptr);
     }
+    for (int k = 0; k < n_side; k++) ICP_CUDA(cudaStreamWaitEvent(r.s, ctx->ev_join[k], 0));   // join
 }
 
 void enqueue_step(RunCtx &r) {

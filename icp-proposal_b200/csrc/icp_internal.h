@@ -191,7 +191,15 @@ struct ObsArgs {
 };
 void launch_observations(const ObsArgs &a, const ObsDev &o, cudaStream_t s);
 // M = I + sum_i (F_i Q_i)^T (F_i Q_i) (lower + upper, Kp x Kp, identity on the padding), b = sum (F_i Q_i)^T y_i
-void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, cudaStream_t s);
+// constant-Gram fast path of the posterior build (see k_posterior_build_mma): Gs = sum_i Q_i^T Q_i over the
+// proposal's model points, gs_scale = 1 / sd_t^2, row_scale = sqrt(1 - sd_n^2 / sd_t^2)
+struct GramFast {
+    const double *Gs;
+    double gs_scale, row_scale;
+};
+void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, cudaStream_t s,
+                            const GramFast *gf = nullptr);
+void launch_gram_rows(const ModelDev &m, int n_ids, const int *d_ids, double *d_G, cudaStream_t s);
 // in: M (C x Kp x Kp), b (C x Kp). out: L (lower Cholesky factor, C x Kp x Kp), mu = M^-1 b, status (0 ok)
 // out_slot (nullable): chain c writes L / mu at index out_slot[c] instead of c
 void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
@@ -232,6 +240,9 @@ struct icp_ctx_s {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    static constexpr int kAux = 3;          // side streams: independent pipelines of one MH step run concurrently
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr};
     std::mutex mu;
     std::string err;
     std::string device_name;
@@ -301,6 +312,8 @@ struct icp_proposal_s {
     int n_ids = 0, n_tp = 0;
     icp::DevBuf<int> ids;     // n_ids
     icp::DevBuf<double> tp;   // n_tp x 3
+    icp::DevBuf<double> Gs;   // Kp x Kp: sum of Q_i^T Q_i over the model points (constant-Gram fast path), empty if unused
+    bool gram_fast = false;
     // posterior cache (the reference's Memoize(icpPosterior, 20)): theta bytes -> slot
     int cache_slots = 0;
     std::unordered_map<std::string, int> cache_map;

@@ -13,6 +13,7 @@
 //
 // Sigma_i^-1 = F_i^T F_i with F_i rows n/sd_n, t1/sd_t, t2/sd_t (orthonormal frame of the vertex
 // normal), so M = I + A^T A with A = stack(F_i Q_i): a batched symmetric rank-3n update in FP64.
+#include <algorithm>
 #include <cstdlib>
 
 #include "icp_device.cuh"
@@ -224,6 +225,7 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 constexpr int kMmaRows = 3 * kPbObs;  // 24 staged rows = 6 k4-steps
 constexpr int kProdWarps = 2;         // producer warps (stage A = F Q into shared memory, accumulate b)
 constexpr int kMaxNB = 20;         // largest supported Kp / 8
+constexpr int kMaxStagedIds = 4096;  // observation ids staged in shared memory by the producers
 
 template <int ID>
 __device__ __forceinline__ void named_bar_sync(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
@@ -233,18 +235,25 @@ __device__ __forceinline__ void named_bar_arrive(int n) { asm volatile("bar.arri
 // Warp-specialised: warps [0, nwc) are MMA consumers, the last kProdWarps warps are producers. Two staged
 // buffers; named barriers FULL(1 + buf) / EMPTY(3 + buf) hand them back and forth, so the gather of the
 // basis rows (L2 latency) and the 3 x 3 whitening overlap with the DMMA stream of the previous chunk.
-template <int NBLK, int NBMAX, int NWC>
+// RPO = rows of A per observation. RPO = 3: the general whitened rows F_i Q_i. RPO = 1 (constant-Gram fast path,
+// model sampling with every observation kept and sd_n <= sd_t): Sigma_i^-1 = I / sd_t^2 + kappa n n^T with
+// kappa = 1/sd_n^2 - 1/sd_t^2, so M = I + Gs / sd_t^2 + sum_i (sqrt(kappa) Q_i^T n_i)(...)^T where
+// Gs = sum_i Q_i^T Q_i is a constant of the proposal: one row per observation, a third of the DMMA work.
+template <int NBLK, int NBMAX, int NWC, int RPO>
 __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_build_mma(ModelDev m, ObsDev o,
                                                                                  double *__restrict__ M,
                                                                                  double *__restrict__ bvec,
-                                                                                 int nblk_total) {
+                                                                                 int nblk_total,
+                                                                                 const double *__restrict__ Gs,
+                                                                                 double gs_scale, double row_scale) {
     extern __shared__ double sm[];
     const int Kp = m.Kp, ld = Kp + 4, NB = Kp >> 3;
     const int bufsz = kMmaRows * ld;
     double *sA = sm;                    // [2][24][ld]
     const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int nthreads = (NWC + kProdWarps) * 32, nwc = NWC;
-    const int nchunks = (o.n + kPbObs - 1) / kPbObs;
+    constexpr int kObsChunk = kMmaRows / RPO;   // observations per staged chunk (8 or 24)
+    const int nchunks = (o.n + kObsChunk - 1) / kObsChunk;
     if (warp < nwc) {
         // ------------------------------- consumers: DMMA ------------------------------------------------
         const int per = (nblk_total + nwc - 1) / nwc;
@@ -292,6 +301,11 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_build_mma
             if (s < nmine) {
                 int i = 8 * bi + (lane >> 2), j = 8 * bj + 2 * (lane & 3);
                 double v0 = acc[s][0] + (i == j ? 1.0 : 0.0), v1 = acc[s][1] + (i == j + 1 ? 1.0 : 0.0);
+                if (RPO == 1) {
+                    double2 g = __ldg(reinterpret_cast<const double2 *>(Gs + (size_t)i * Kp + j));
+                    v0 = fma(g.x, gs_scale, v0);
+                    v1 = fma(g.y, gs_scale, v1);
+                }
                 *reinterpret_cast<double2 *>(Mc + (size_t)i * Kp + j) = make_double2(v0, v1);
                 if (bi != bj) {
                     Mc[(size_t)j * Kp + i] = v0;
@@ -310,38 +324,53 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_build_mma
         double bacc[NBMAX];
 #pragma unroll
         for (int i = 0; i < NBMAX; i++) bacc[i] = 0.0;
+        // the vertex ids gate the addresses of every basis-row load: stage them in shared memory once so that a
+        // pass pays one L2 round trip (ids -> rows would be two dependent ones)
+        int *svid = reinterpret_cast<int *>(sm + 2 * bufsz + 8 * Kp);
+        const bool vid_staged = o.n <= kMaxStagedIds;
+        if (vid_staged) {
+            for (int e = pt; e < o.n; e += kProdWarps * 32) svid[e] = __ldg(&vid[e]);
+            named_bar_sync<5>(kProdWarps * 32);
+        }
         for (int ch = 0; ch < nchunks; ch++) {
             const int buf = ch & 1;
-            const int gi = ch * kPbObs + ob;
-            int v = -1;
-            double f[9], yy[3];
-            if (gi < o.n) v = __ldg(&vid[gi]);
-            if (v >= 0) {
+#pragma unroll 1
+            for (int pass = 0; pass < kObsChunk / 8; pass++) {
+                const int lo = pass * 8 + ob;            // observation slot within the chunk
+                const int gi = ch * kObsChunk + lo;
+                int v = -1;
+                double f[9], yy[3];
+                if (gi < o.n) v = vid_staged ? svid[gi] : __ldg(&vid[gi]);
+                if (v >= 0) {
 #pragma unroll
-                for (int k = 0; k < 9; k++) f[k] = __ldg(F + (size_t)gi * 9 + k);
+                    for (int k = 0; k < 9; k++) f[k] = __ldg(F + (size_t)gi * 9 + k);
 #pragma unroll
-                for (int k = 0; k < 3; k++) yy[k] = __ldg(y + (size_t)gi * 3 + k);
-            } else {
+                    for (int k = 0; k < 3; k++) yy[k] = __ldg(y + (size_t)gi * 3 + k);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 9; k++) f[k] = 0.0;
-                yy[0] = yy[1] = yy[2] = 0.0;
-            }
-            const double *q = m.Q + (size_t)3 * (v >= 0 ? v : 0) * Kp + cg;
-            double q0[NBMAX], q1[NBMAX], q2[NBMAX];
+                    for (int k = 0; k < 9; k++) f[k] = 0.0;
+                    yy[0] = yy[1] = yy[2] = 0.0;
+                }
+                const double *q = m.Q + (size_t)3 * (v >= 0 ? v : 0) * Kp + cg;
+                double q0[NBMAX], q1[NBMAX], q2[NBMAX];
 #pragma unroll
-            for (int i = 0; i < NBMAX; i++) {
-                if (i < NB) { q0[i] = __ldg(q + 8 * i); q1[i] = __ldg(q + Kp + 8 * i); q2[i] = __ldg(q + 2 * Kp + 8 * i); }
-            }
-            if (buf == 0) named_bar_sync<3>(nthreads); else named_bar_sync<4>(nthreads);   // consumers are done with this buffer
-            double *dst = sA + buf * bufsz + (3 * ob) * ld + cg;
+                for (int i = 0; i < NBMAX; i++) {
+                    if (i < NB) { q0[i] = __ldg(q + 8 * i); q1[i] = __ldg(q + Kp + 8 * i); q2[i] = __ldg(q + 2 * Kp + 8 * i); }
+                }
+                if (pass == 0) {  // consumers are done with this buffer
+                    if (buf == 0) named_bar_sync<3>(nthreads); else named_bar_sync<4>(nthreads);
+                }
+                double *dst = sA + buf * bufsz + (RPO * lo) * ld + cg;
 #pragma unroll
-            for (int i = 0; i < NBMAX; i++) {
-                if (i < NB) {
-                    double a0 = f[0] * q0[i] + f[1] * q1[i] + f[2] * q2[i];
-                    double a1 = f[3] * q0[i] + f[4] * q1[i] + f[5] * q2[i];
-                    double a2 = f[6] * q0[i] + f[7] * q1[i] + f[8] * q2[i];
-                    dst[8 * i] = a0; dst[ld + 8 * i] = a1; dst[2 * ld + 8 * i] = a2;
-                    bacc[i] = fma(a0, yy[0], fma(a1, yy[1], fma(a2, yy[2], bacc[i])));
+                for (int i = 0; i < NBMAX; i++) {
+                    if (i < NB) {
+                        double a0 = f[0] * q0[i] + f[1] * q1[i] + f[2] * q2[i];
+                        double a1 = f[3] * q0[i] + f[4] * q1[i] + f[5] * q2[i];
+                        double a2 = f[6] * q0[i] + f[7] * q1[i] + f[8] * q2[i];
+                        if (RPO == 3) { dst[8 * i] = a0; dst[ld + 8 * i] = a1; dst[2 * ld + 8 * i] = a2; }
+                        else dst[8 * i] = a0 * row_scale;
+                        bacc[i] = fma(a0, yy[0], fma(a1, yy[1], fma(a2, yy[2], bacc[i])));
+                    }
                 }
             }
             if (buf == 0) named_bar_arrive<1>(nthreads); else named_bar_arrive<2>(nthreads);
@@ -364,23 +393,29 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_build_mma
 }
 
 template <int NBLK, int NBMAX, int NWC>
-static void launch_pb_mma(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, int total, cudaStream_t s) {
-    size_t smem = sizeof(double) * ((size_t)2 * kMmaRows * (m.Kp + 4) + 8 * m.Kp);
-    ICP_CUDA(cudaFuncSetAttribute(k_posterior_build_mma<NBLK, NBMAX, NWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_posterior_build_mma<NBLK, NBMAX, NWC><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, d_b, total);
+static void launch_pb_mma(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, int total, const GramFast *gf,
+                          cudaStream_t s) {
+    size_t smem = sizeof(double) * ((size_t)2 * kMmaRows * (m.Kp + 4) + 8 * m.Kp) + sizeof(int) * (size_t)std::min(o.n, kMaxStagedIds);
+    if (gf) {
+        ICP_CUDA(cudaFuncSetAttribute(k_posterior_build_mma<NBLK, NBMAX, NWC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_posterior_build_mma<NBLK, NBMAX, NWC, 1><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, d_b, total, gf->Gs, gf->gs_scale, gf->row_scale);
+    } else {
+        ICP_CUDA(cudaFuncSetAttribute(k_posterior_build_mma<NBLK, NBMAX, NWC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_posterior_build_mma<NBLK, NBMAX, NWC, 3><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, d_b, total, nullptr, 0.0, 1.0);
+    }
 }
 
-void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, cudaStream_t s) {
+void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, cudaStream_t s, const GramFast *gf) {
     ProfScope _ps(ST_POSTERIOR_BUILD, s);
     if (C <= 0) return;
     static const bool no_mma = getenv("ICPCUDA_NO_DMMA") && getenv("ICPCUDA_NO_DMMA")[0] == '1';
     {
         int NB = m.Kp / 8, total = NB * (NB + 1) / 2;
         if (!no_mma && NB <= kMaxNB) {
-            if (NB <= 4) launch_pb_mma<4, 4, 4>(m, C, o, d_M, d_b, total, s);
-            else if (NB <= 7) launch_pb_mma<8, 7, 4>(m, C, o, d_M, d_b, total, s);
-            else if (NB <= 13) launch_pb_mma<24, 13, 4>(m, C, o, d_M, d_b, total, s);
-            else launch_pb_mma<28, 20, 8>(m, C, o, d_M, d_b, total, s);
+            if (NB <= 4) launch_pb_mma<4, 4, 4>(m, C, o, d_M, d_b, total, gf, s);
+            else if (NB <= 7) launch_pb_mma<8, 7, 4>(m, C, o, d_M, d_b, total, gf, s);
+            else if (NB <= 13) launch_pb_mma<24, 13, 4>(m, C, o, d_M, d_b, total, gf, s);
+            else launch_pb_mma<28, 20, 8>(m, C, o, d_M, d_b, total, gf, s);
             ICP_CUDA(cudaGetLastError());
             return;
         }
@@ -394,6 +429,23 @@ void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d
     else if (tiles <= 4) k_posterior_build<4><<<C, kPbThreads, smem, s>>>(m, o, d_M, d_b);
     else if (tiles <= 8) k_posterior_build<8><<<C, kPbThreads, smem, s>>>(m, o, d_M, d_b);
     else throw ArgError{"rank too large for the posterior build kernel"};
+    ICP_CUDA(cudaGetLastError());
+}
+
+// Gs[i][j] = sum over the proposal's model points p and d < 3 of Q[3 p + d][i] Q[3 p + d][j] (one-off per proposal)
+__global__ void k_gram_rows(int n_ids, const int *__restrict__ ids, int Kp, const double *__restrict__ Q, double *__restrict__ G) {
+    int i = blockIdx.x, j = threadIdx.x;
+    if (j >= Kp) return;
+    double acc = 0;
+    for (int t = 0; t < n_ids; t++) {
+        const double *q = Q + (size_t)3 * ids[t] * Kp;
+        for (int d = 0; d < 3; d++) acc = fma(q[d * Kp + i], q[d * Kp + j], acc);
+    }
+    G[(size_t)i * Kp + j] = acc;
+}
+
+void launch_gram_rows(const ModelDev &m, int n_ids, const int *d_ids, double *d_G, cudaStream_t s) {
+    k_gram_rows<<<m.Kp, ((m.Kp + 31) / 32) * 32, 0, s>>>(n_ids, d_ids, m.Kp, m.Q, d_G);
     ICP_CUDA(cudaGetLastError());
 }
 
