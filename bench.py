@@ -252,7 +252,8 @@ def run_gpu(args):
                                                                       h_thl.ctypes.data)
     io.theta_final, io.n_accepted = h_fin.ctypes.data, h_nacc.ctypes.data
     import ctypes as Cc
-    _lib.check(chain.lib.icp_chain_run(chain.h, C, warm, _lib.dptr(h_th0), Cc.byref(io)), ctx.h)   # W untimed warm-up steps
+    # untimed warm-up call of the same size (sizes the library's staging buffers; W >= 3 steps run inside it too)
+    _lib.check(chain.lib.icp_chain_run(chain.h, C, max(warm, e_steps), _lib.dptr(h_th0), Cc.byref(io)), ctx.h)
     barrier()
     t0 = time.perf_counter()
     _lib.check(chain.lib.icp_chain_run(chain.h, C, e_steps, _lib.dptr(h_th0), Cc.byref(io)), ctx.h)

@@ -345,6 +345,9 @@ extern "C" int32_t icp_target_create(icp_ctx ctx, int32_t Nt, int32_t Tt, const 
         t->has_boundary = std::any_of(t->h_boundary.begin(), t->h_boundary.end(), [](uint8_t b) { return b != 0; });
         t->boundary.upload(t->h_boundary.data(), t->h_boundary.size(), s);
         double scale = std::max(max_abs(xyz, (size_t)3 * Nt), 1e-3);
+        for (int d = 0; d < 3; d++) { t->lo[d] = 1e300; t->hi[d] = -1e300; }
+        for (int v = 0; v < Nt; v++)
+            for (int d = 0; d < 3; d++) { t->lo[d] = std::min(t->lo[d], xyz[3 * v + d]); t->hi[d] = std::max(t->hi[d], xyz[3 * v + d]); }
         bvh_build(t->tri_bvh, 0, Tt, t->verts.p, t->tris.p, scale, s);
         bvh_build(t->vert_bvh, 1, Nt, t->verts.p, nullptr, scale, s);
         t->tri_data.alloc((size_t)t->tri_bvh.n * 10);
@@ -404,7 +407,7 @@ extern "C" int32_t icp_closest_point_surface(icp_target t, int64_t nq, const dou
     NearestArgs a = target_tri_args(t);
     a.nq = nq; a.q = t->s_q.p;
     a.out_prim = t->s_i.p; a.out_feat = t->s_i.p + nq; a.out_cp = t->s_d.p; a.out_d2 = t->s_d.p + 3 * nq;
-    launch_nearest(a, s);
+    launch_nearest_sorted(a, t->qsort, t->lo, t->hi, s);
     download(tri, t->s_i.p, nq, s);
     download(feature, t->s_i.p + nq, nq, s);
     download(cp, t->s_d.p, 3 * nq, s);
@@ -420,7 +423,7 @@ extern "C" int32_t icp_closest_point_surface_device(icp_target t, int64_t nq, co
     if (nq == 0) return ICP_OK;
     NearestArgs a = target_tri_args(t);
     a.nq = nq; a.q = q_dev; a.out_prim = tri_dev; a.out_cp = cp_dev; a.out_d2 = d2_dev;
-    launch_nearest(a, _ctx->stream);
+    launch_nearest_sorted(a, t->qsort, t->lo, t->hi, _ctx->stream);
     sync_stream(_ctx);
     ICP_API_END
 }
@@ -623,7 +626,8 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
     if (tsamp) {
         // :118 currentMesh.pointSet.findClosestPoint(targetPoint): vertex BVH refit to the current meshes
         w.prim.ensure(tot);
-        if (!launch_nearest_vertex_brute(m->N, C, d_X, n, p->tp.p, 0, m->scale, w.prim.p, nullptr, s)) {
+        static const bool prefer_bvh = getenv("ICPCUDA_NEAREST_VERTEX") && std::string(getenv("ICPCUDA_NEAREST_VERTEX")) == "bvh";
+        if (prefer_bvh || !launch_nearest_vertex_brute(m->N, C, d_X, n, p->tp.p, 0, m->scale, w.prim.p, nullptr, s)) {
             bvh_refit(m->vert_bvh, C, d_X, m->N, nullptr, s);
             NearestArgs a;
             a.bvh = &m->vert_bvh; a.X = d_X; a.N = m->N; a.C = C; a.nq = n; a.q = p->tp.p; a.out_prim = w.prim.p;

@@ -13,6 +13,8 @@
 
 namespace icp {
 
+void bvh_refit_atomic(Bvh &b, int instances, const double *d_X, int N, const int *d_tris, cudaStream_t s);
+
 // ---------------------------------------------------------------------------------------------------
 // construction
 // ---------------------------------------------------------------------------------------------------
@@ -128,7 +130,65 @@ __global__ void k_refit(int n, int instances, int prim_kind, const int *__restri
     }
 }
 
+// level-synchronous refit: one CTA per instance walks the internal nodes in order of increasing height (schedule
+// computed once at build time); no atomics, no counters, boxes of finished levels are read back through L2.
+__global__ void __launch_bounds__(256) k_refit_levels(int n, int prim_kind, const int *__restrict__ prim,
+                                                      const int2 *__restrict__ children, const int *__restrict__ order,
+                                                      const int *__restrict__ level_off, int n_levels,
+                                                      const double *__restrict__ X, int N, const int *__restrict__ tris,
+                                                      float slack, float4 *__restrict__ nodes, float4 *nodebox) {
+    const int inst = blockIdx.x;
+    const double *Xi = X + (size_t)inst * N * 3;
+    float4 *nb = nodebox + (size_t)inst * (2 * n - 1) * 2;
+    float4 *nd = nodes + (size_t)inst * (n - 1) * 3;
+    for (int slot = threadIdx.x; slot < n; slot += blockDim.x) {
+        int p = prim[slot];
+        double lx, ly, lz, hx, hy, hz;
+        if (prim_kind == 0) {
+            int a = tris[3 * p], b = tris[3 * p + 1], c = tris[3 * p + 2];
+            lx = fmin(fmin(Xi[3 * a], Xi[3 * b]), Xi[3 * c]); hx = fmax(fmax(Xi[3 * a], Xi[3 * b]), Xi[3 * c]);
+            ly = fmin(fmin(Xi[3 * a + 1], Xi[3 * b + 1]), Xi[3 * c + 1]); hy = fmax(fmax(Xi[3 * a + 1], Xi[3 * b + 1]), Xi[3 * c + 1]);
+            lz = fmin(fmin(Xi[3 * a + 2], Xi[3 * b + 2]), Xi[3 * c + 2]); hz = fmax(fmax(Xi[3 * a + 2], Xi[3 * b + 2]), Xi[3 * c + 2]);
+        } else {
+            lx = hx = Xi[3 * p]; ly = hy = Xi[3 * p + 1]; lz = hz = Xi[3 * p + 2];
+        }
+        __stcg(&nb[2 * (n - 1 + slot)], make_float4(__double2float_rd(lx) - slack, __double2float_rd(ly) - slack, __double2float_rd(lz) - slack, 0.f));
+        __stcg(&nb[2 * (n - 1 + slot) + 1], make_float4(__double2float_ru(hx) + slack, __double2float_ru(hy) + slack, __double2float_ru(hz) + slack, 0.f));
+    }
+    __syncthreads();
+    for (int lev = 0; lev < n_levels; lev++) {
+        for (int k = level_off[lev] + threadIdx.x; k < level_off[lev + 1]; k += blockDim.x) {
+            int node = order[k];
+            int2 ch = children[node];
+            int li = ch.x >= 0 ? ch.x : n - 1 + (~ch.x), ri = ch.y >= 0 ? ch.y : n - 1 + (~ch.y);
+            float4 llo = __ldcg(&nb[2 * li]), lhi = __ldcg(&nb[2 * li + 1]);
+            float4 rlo = __ldcg(&nb[2 * ri]), rhi = __ldcg(&nb[2 * ri + 1]);
+            nd[3 * node] = make_float4(llo.x, llo.y, llo.z, lhi.x);
+            nd[3 * node + 1] = make_float4(lhi.y, lhi.z, rlo.x, rlo.y);
+            nd[3 * node + 2] = make_float4(rlo.z, rhi.x, rhi.y, rhi.z);
+            __stcg(&nb[2 * node], make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f));
+            __stcg(&nb[2 * node + 1], make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f));
+        }
+        __syncthreads();
+    }
+}
+
 void bvh_refit(Bvh &b, int instances, const double *d_X, int N, const int *d_tris, cudaStream_t s) {
+    if (b.n_levels > 0 && instances >= 8) {
+        ProfScope _ps(ST_REFIT, s);
+        int n = b.n;
+        b.nodes.ensure((size_t)instances * (n - 1) * 3);
+        b.nodebox.ensure((size_t)instances * (2 * n - 1) * 2);
+        b.instances = instances;
+        k_refit_levels<<<instances, 256, 0, s>>>(n, b.prim_kind, b.prim.p, b.children.p, b.order.p, b.level_off.p, b.n_levels,
+                                                 d_X, N, d_tris, b.slack, b.nodes.p, b.nodebox.p);
+        ICP_CUDA(cudaGetLastError());
+        return;
+    }
+    bvh_refit_atomic(b, instances, d_X, N, d_tris, s);
+}
+
+void bvh_refit_atomic(Bvh &b, int instances, const double *d_X, int N, const int *d_tris, cudaStream_t s) {
     ProfScope _ps(ST_REFIT, s);
     int n = b.n;
     b.nodes.ensure((size_t)instances * (n - 1) * 3);
@@ -192,7 +252,36 @@ void bvh_build(Bvh &b, int prim_kind, int n_prims, const double *d_verts, const 
     ICP_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, vals.p, b.prim.p, n, 0, 64, s));
     k_karras<<<(n - 1 + threads - 1) / threads, threads, 0, s>>>(n, keys2.p, b.children.p, b.parent.p);
     ICP_CUDA(cudaGetLastError());
-    bvh_refit(b, 1, d_verts, nv_needed, d_tris, s);
+    // bottom-up schedule for the level-synchronous refit: internal nodes sorted by height
+    {
+        std::vector<int2> hch(n - 1);
+        ICP_CUDA(cudaMemcpyAsync(hch.data(), b.children.p, sizeof(int2) * (n - 1), cudaMemcpyDeviceToHost, s));
+        ICP_CUDA(cudaStreamSynchronize(s));
+        std::vector<int> height(n - 1, -1), stack;
+        stack.push_back(0);
+        while (!stack.empty()) {   // iterative post-order
+            int v = stack.back();
+            int l = hch[v].x, r = hch[v].y;
+            int hl = l < 0 ? 0 : height[l], hr = r < 0 ? 0 : height[r];
+            if (hl >= 0 && hr >= 0) { height[v] = 1 + (hl > hr ? hl : hr); stack.pop_back(); }
+            else { if (l >= 0 && height[l] < 0) stack.push_back(l); if (r >= 0 && height[r] < 0) stack.push_back(r); }
+        }
+        int maxh = 0;
+        for (int v = 0; v < n - 1; v++) maxh = height[v] > maxh ? height[v] : maxh;
+        std::vector<int> off(maxh + 1, 0), order(n - 1);
+        for (int v = 0; v < n - 1; v++) off[height[v]]++;           // heights are 1 .. maxh
+        for (int h = 1, acc = 0; h <= maxh; h++) { int c = off[h]; off[h] = acc; acc += c; }
+        std::vector<int> fill(off.begin(), off.end());
+        for (int v = 0; v < n - 1; v++) order[fill[height[v]]++] = v;
+        std::vector<int> level_off(maxh + 1);
+        for (int h = 1; h <= maxh; h++) level_off[h - 1] = off[h];
+        level_off[maxh] = n - 1;
+        b.order.upload(order.data(), order.size(), s);
+        b.level_off.upload(level_off.data(), level_off.size(), s);
+        b.n_levels = maxh;
+        ICP_CUDA(cudaStreamSynchronize(s));
+    }
+    bvh_refit_atomic(b, 1, d_verts, nv_needed, d_tris, s);
     ICP_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -293,12 +382,14 @@ __global__ void __launch_bounds__(128) k_nearest(int n, const int2 *__restrict__
                                                  const int *__restrict__ tris, int N, int C, long long nq,
                                                  const double *__restrict__ q, int q_per_chain,
                                                  const double *__restrict__ Xq, const int *__restrict__ q_ids, int Nq,
-                                                 int *__restrict__ out_prim, int *__restrict__ out_feat,
-                                                 double *__restrict__ out_cp, double *__restrict__ out_d2) {
+                                                 const int *__restrict__ perm, int *__restrict__ out_prim,
+                                                 int *__restrict__ out_feat, double *__restrict__ out_cp,
+                                                 double *__restrict__ out_d2) {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nq * C) return;
     int c = (int)(g / nq);
     long long i = g % nq;
+    if (perm) { i = perm[i]; g = (long long)c * nq + i; }  // spatially sorted processing order, results in caller order
     double qx, qy, qz;
     if (q_ids) {
         const double *src = Xq + ((size_t)c * Nq + q_ids[i]) * 3;
@@ -362,7 +453,7 @@ void launch_nearest(const NearestArgs &a, cudaStream_t s) {
 #define ICP_LAUNCH_NEAREST(P, D)                                                                                  \
     k_nearest<P, D><<<blocks, threads, 0, s>>>(b.n, b.children.p, b.nodes.p, b.prim.p, a.prim_data, a.X, a.tris, \
                                                a.N, a.C, (long long)a.nq, a.q, a.q_per_chain, a.Xq, a.q_ids,     \
-                                               a.Nq, a.out_prim, a.out_feat, a.out_cp, a.out_d2)
+                                               a.Nq, a.perm, a.out_prim, a.out_feat, a.out_cp, a.out_d2)
     if (b.prim_kind == 0) {
         if (dynamic) ICP_LAUNCH_NEAREST(0, true); else ICP_LAUNCH_NEAREST(0, false);
     } else {
@@ -471,6 +562,46 @@ bool launch_nearest_vertex_brute(int N, int C, const double *d_X, int64_t nq, co
     k_nearest_vertex_brute<<<grid, 128, smem, s>>>(N, C, d_X, (long long)nq, d_q, q_per_chain, (float)scale, d_prim, d_d2);
     ICP_CUDA(cudaGetLastError());
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// large batches of free query points: process them in Morton order so that the 32 queries of a warp walk
+// the same part of the tree (2x on random near-surface queries), write results in the caller's order
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_query_morton(long long nq, const double *__restrict__ q, double lox, double loy, double loz, double sx,
+                               double sy, double sz, unsigned int *__restrict__ keys, int *__restrict__ vals) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    double fx = fmin(fmax((q[3 * i] - lox) * sx, 0.0), 1.0), fy = fmin(fmax((q[3 * i + 1] - loy) * sy, 0.0), 1.0),
+           fz = fmin(fmax((q[3 * i + 2] - loz) * sz, 0.0), 1.0);
+    if (!(fx == fx)) fx = 0.0;
+    if (!(fy == fy)) fy = 0.0;
+    if (!(fz == fz)) fz = 0.0;
+    unsigned long long ix = (unsigned long long)(fx * 1023.0), iy = (unsigned long long)(fy * 1023.0), iz = (unsigned long long)(fz * 1023.0);
+    // 5 bits per axis (32^3 cells) are enough for warp coherence and sort in two 8-bit radix passes
+    keys[i] = (unsigned int)(((expand21(ix) << 2) | (expand21(iy) << 1) | expand21(iz)) >> 15);
+    vals[i] = (int)i;
+}
+
+void launch_nearest_sorted(NearestArgs a, QuerySort &qs, const double lo[3], const double hi[3], cudaStream_t s) {
+    const long long nq = a.nq;
+    if (a.C != 1 || a.q == nullptr || nq < 16384 || nq > 0x7fffffffLL) { launch_nearest(a, s); return; }
+    ProfScope _ps(ST_NEAREST_STATIC, s);
+    qs.keys.ensure(nq); qs.keys2.ensure(nq); qs.vals.ensure(nq); qs.perm.ensure(nq);
+    double sc[3], l2[3];
+    for (int d = 0; d < 3; d++) {  // twice the structure's box: far-field queries still get distinct codes
+        double c = 0.5 * (lo[d] + hi[d]), h = hi[d] - lo[d];
+        l2[d] = c - h;
+        sc[d] = h > 0 ? 1.0 / (2.0 * h) : 0.0;
+    }
+    k_query_morton<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(nq, a.q, l2[0], l2[1], l2[2], sc[0], sc[1], sc[2], qs.keys.p, qs.vals.p);
+    ICP_CUDA(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    ICP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, qs.keys.p, qs.keys2.p, qs.vals.p, qs.perm.p, (int)nq, 0, 15, s));
+    qs.tmp.ensure(tmp_bytes);
+    ICP_CUDA(cub::DeviceRadixSort::SortPairs(qs.tmp.p, tmp_bytes, qs.keys.p, qs.keys2.p, qs.vals.p, qs.perm.p, (int)nq, 0, 15, s));
+    a.perm = qs.perm.p;
+    launch_nearest(a, s);
 }
 
 // flags[i] = table[prim[i]] (0 when prim < 0)

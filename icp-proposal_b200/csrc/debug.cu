@@ -112,12 +112,12 @@ extern "C" int32_t icp_debug_time_closest_point(icp_target t, int64_t nq, const 
         NearestArgs a;
         a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.nq = nq; a.q = q_dev;
         a.out_prim = tri_dev; a.out_cp = cp_dev; a.out_d2 = d2_dev;
-        launch_nearest(a, s);
+        launch_nearest_sorted(a, t->qsort, t->lo, t->hi, s);
         cudaEvent_t e0, e1;
         ICP_CUDA(cudaEventCreate(&e0));
         ICP_CUDA(cudaEventCreate(&e1));
         ICP_CUDA(cudaEventRecord(e0, s));
-        for (int i = 0; i < iters; i++) launch_nearest(a, s);
+        for (int i = 0; i < iters; i++) launch_nearest_sorted(a, t->qsort, t->lo, t->hi, s);
         ICP_CUDA(cudaEventRecord(e1, s));
         ICP_CUDA(cudaStreamSynchronize(s));
         float t_ms = 0;

@@ -111,7 +111,9 @@ struct Bvh {
     DevBuf<int> prim;        // [n]
     DevBuf<float4> nodes;    // [instances][n-1][3] child boxes
     DevBuf<float4> nodebox;  // scratch [instances][2n-1][2] full boxes (lo, hi)
-    DevBuf<int> counters;    // scratch [instances][n-1]
+    DevBuf<int> counters;    // scratch [instances][n-1] (atomic refit)
+    DevBuf<int> order, level_off;  // internal nodes by increasing height + level boundaries (level-synchronous refit)
+    int n_levels = 0;
     int instances = 0;
     float slack = 0.f;
 };
@@ -138,6 +140,7 @@ struct NearestArgs {
     const double *Xq = nullptr;     // [C][Nq][3]
     const int *q_ids = nullptr;     // [nq]
     int Nq = 0;
+    const int *perm = nullptr;      // optional processing order (C == 1): thread g handles query perm[g]
     // outputs [C][nq]
     int *out_prim = nullptr;
     int *out_feat = nullptr;
@@ -145,6 +148,15 @@ struct NearestArgs {
     double *out_d2 = nullptr;
 };
 void launch_nearest(const NearestArgs &a, cudaStream_t s);
+// scratch of the query-ordering pass of large point batches
+struct QuerySort {
+    DevBuf<unsigned int> keys, keys2;
+    DevBuf<int> vals, perm;
+    DevBuf<unsigned char> tmp;
+};
+// like launch_nearest for free query points; batches >= 16384 are processed in Morton order (lo / hi: bounding box of
+// the structure). Results are written in the caller's order either way.
+void launch_nearest_sorted(NearestArgs a, QuerySort &qs, const double lo[3], const double hi[3], cudaStream_t s);
 // brute-force nearest vertex of C small meshes X[C][N][3] (FP32 screening + exact FP64); returns false (nothing
 // launched) when N is too large for the shared-memory tile, in which case the caller uses the vertex BVH
 bool launch_nearest_vertex_brute(int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, double scale,
@@ -283,6 +295,8 @@ struct icp_target_s {
     bool has_boundary = false;
     std::vector<uint8_t> h_boundary;
     icp::Bvh tri_bvh, vert_bvh;
+    icp::QuerySort qsort;
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // bounding box of the vertices
     icp::DevBuf<double> s_q, s_d;
     icp::DevBuf<int> s_i;
 };

@@ -24,72 +24,100 @@ namespace icp {
 // ---------------------------------------------------------------------------------------------------
 // observations
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_observations(ObsArgs a, ObsDev o) {
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)a.C * o.n) return;
-    int c = (int)(g / o.n), i = (int)(g % o.n);
+// One CTA per chain: the chain's mesh is staged in shared memory (coalesced, 8 loads in flight per thread), then one
+// thread per observation gathers the one-ring of its vertex from shared memory - the gather is 4 dependent
+// index -> index -> index -> coordinate loads per adjacent triangle, which costs ~30 cycles each from shared
+// memory instead of an L2 round trip.
+template <bool STAGED>
+__global__ void __launch_bounds__(256) k_observations(ObsArgs a, ObsDev o) {
+    extern __shared__ double sX[];
     const ModelDev &m = a.m;
+    int c;
+    long long g;
+    int i;
+    const double *Xc;
+    if (STAGED) {
+        c = blockIdx.x;
+        const double *Xg = a.X + (size_t)c * m.N * 3;
+        for (int e0 = threadIdx.x; e0 < 3 * m.N; e0 += 8 * blockDim.x) {
+            double tmp[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; tmp[u] = e < 3 * m.N ? __ldg(Xg + e) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; if (e < 3 * m.N) sX[e] = tmp[u]; }
+        }
+        __syncthreads();
+        Xc = sX;
+    } else {
+        long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (gt >= (long long)a.C * o.n) return;
+        c = (int)(gt / o.n);
+        Xc = a.X + (size_t)c * m.N * 3;
+    }
     const double *th = a.theta + (size_t)c * (m.K + kTheta0);
-    const double *Xc = a.X + (size_t)c * m.N * 3;
-    int id;
-    double tx, ty, tz;
-    bool drop = false;
-    if (a.prm.direction == ICP_TARGET_SAMPLING) {
-        id = a.near_vid[g];                                         // :118 findClosestPoint on the current mesh
-        tx = a.tp[3 * i]; ty = a.tp[3 * i + 1]; tz = a.tp[3 * i + 2];
-        if (id < 0) drop = true;
-        else if (a.prm.boundary_aware && m.boundary[id]) drop = true;  // :119,124
-    } else {
-        id = a.ids[i];
-        const double *cpp = a.cp + ((size_t)c * a.cp_stride + (a.cp_map ? a.cp_map[i] : i)) * 3;
-        tx = cpp[0]; ty = cpp[1]; tz = cpp[2];                          // :97 closest point on the target
-        if (a.prm.boundary_aware && a.cp_on_boundary && a.cp_on_boundary[g]) drop = true;  // :99,104
+    for (int i0 = STAGED ? threadIdx.x : 0; i0 < (STAGED ? o.n : 1); i0 += blockDim.x) {
+        if (STAGED) { i = i0; g = (long long)c * o.n + i; }
+        else { g = (long long)blockIdx.x * blockDim.x + threadIdx.x; i = (int)(g % o.n); }
+        int id;
+        double tx, ty, tz;
+        bool drop = false;
+        if (a.prm.direction == ICP_TARGET_SAMPLING) {
+            id = a.near_vid[g];                                         // :118 findClosestPoint on the current mesh
+            tx = a.tp[3 * i]; ty = a.tp[3 * i + 1]; tz = a.tp[3 * i + 2];
+            if (id < 0) drop = true;
+            else if (a.prm.boundary_aware && m.boundary[id]) drop = true;  // :119,124
+        } else {
+            id = a.ids[i];
+            const double *cpp = a.cp + ((size_t)c * a.cp_stride + (a.cp_map ? a.cp_map[i] : i)) * 3;
+            tx = cpp[0]; ty = cpp[1]; tz = cpp[2];                          // :97 closest point on the target
+            if (a.prm.boundary_aware && a.cp_on_boundary && a.cp_on_boundary[g]) drop = true;  // :99,104
+        }
+        double *F = o.F + 9 * g, *y = o.y + 3 * g;
+        if (drop) {
+            o.vid[g] = -1;
+            for (int k = 0; k < 9; k++) F[k] = 0.0;
+            y[0] = y[1] = y[2] = 0.0;
+            continue;
+        }
+        atomicAdd(&o.nobs[c], 1);
+        o.vid[g] = id;
+        double f[9];
+        if (a.iso) {
+            double w = 1.0 / sqrt(a.iso_sigma2);
+            for (int k = 0; k < 9; k++) f[k] = 0.0;
+            f[0] = f[4] = f[8] = w;
+        } else {
+            double nx, ny, nz;
+            vertex_normal_dev(m, Xc, id, nx, ny, nz);                   // :100,120 currentMesh.vertexNormals.atPoint(id)
+            // SurfaceNoiseHelpers.scala:39: normalize again
+            double nn = sqrt(nx * nx + ny * ny + nz * nz);
+            nx /= nn; ny /= nn; nz /= nn;
+            // :44-48 candidate = n x e_x; (inverted) fallback test; n x e_y otherwise
+            double c0 = 0.0, c1 = nz, c2 = -ny;
+            double t1x, t1y, t1z;
+            if (c0 * c0 + c1 * c1 + c2 * c2 < 0.0001) { t1x = c0; t1y = c1; t1z = c2; }
+            else { t1x = -nz; t1y = 0.0; t1z = nx; }
+            double tn = sqrt(t1x * t1x + t1y * t1y + t1z * t1z);
+            t1x /= tn; t1y /= tn; t1z /= tn;                             // 0/0 = NaN exactly where the reference yields NaN
+            double t2x = ny * t1z - nz * t1y, t2y = nz * t1x - nx * t1z, t2z = nx * t1y - ny * t1x;
+            double t2n = sqrt(t2x * t2x + t2y * t2y + t2z * t2z);
+            t2x /= t2n; t2y /= t2n; t2z /= t2n;
+            double wn = 1.0 / a.prm.noise_along_normal, wt = 1.0 / a.prm.tangential_noise;
+            f[0] = nx * wn; f[1] = ny * wn; f[2] = nz * wn;
+            f[3] = t1x * wt; f[4] = t1y * wt; f[5] = t1z * wt;
+            f[6] = t2x * wt; f[7] = t2y * wt; f[8] = t2z * wt;
+        }
+        double R[9];
+        pose_matrix(th, R);
+        double ix, iy, iz;
+        inverse_pose(th, R, tx, ty, tz, ix, iy, iz);                    // :108,129 inversePoseTransform(targetPoint)
+        double y0 = (ix - m.ref[3 * id]) - m.mean[3 * id], y1 = (iy - m.ref[3 * id + 1]) - m.mean[3 * id + 1],
+               y2 = (iz - m.ref[3 * id + 2]) - m.mean[3 * id + 2];
+        for (int k = 0; k < 9; k++) F[k] = f[k];
+        y[0] = f[0] * y0 + f[1] * y1 + f[2] * y2;
+        y[1] = f[3] * y0 + f[4] * y1 + f[5] * y2;
+        y[2] = f[6] * y0 + f[7] * y1 + f[8] * y2;
     }
-    double *F = o.F + 9 * g, *y = o.y + 3 * g;
-    if (drop) {
-        o.vid[g] = -1;
-        for (int k = 0; k < 9; k++) F[k] = 0.0;
-        y[0] = y[1] = y[2] = 0.0;
-        return;
-    }
-    atomicAdd(&o.nobs[c], 1);
-    o.vid[g] = id;
-    double f[9];
-    if (a.iso) {
-        double w = 1.0 / sqrt(a.iso_sigma2);
-        for (int k = 0; k < 9; k++) f[k] = 0.0;
-        f[0] = f[4] = f[8] = w;
-    } else {
-        double nx, ny, nz;
-        vertex_normal_dev(m, Xc, id, nx, ny, nz);                   // :100,120 currentMesh.vertexNormals.atPoint(id)
-        // SurfaceNoiseHelpers.scala:39: normalize again
-        double nn = sqrt(nx * nx + ny * ny + nz * nz);
-        nx /= nn; ny /= nn; nz /= nn;
-        // :44-48 candidate = n x e_x; (inverted) fallback test; n x e_y otherwise
-        double c0 = 0.0, c1 = nz, c2 = -ny;
-        double t1x, t1y, t1z;
-        if (c0 * c0 + c1 * c1 + c2 * c2 < 0.0001) { t1x = c0; t1y = c1; t1z = c2; }
-        else { t1x = -nz; t1y = 0.0; t1z = nx; }
-        double tn = sqrt(t1x * t1x + t1y * t1y + t1z * t1z);
-        t1x /= tn; t1y /= tn; t1z /= tn;                             // 0/0 = NaN exactly where the reference yields NaN
-        double t2x = ny * t1z - nz * t1y, t2y = nz * t1x - nx * t1z, t2z = nx * t1y - ny * t1x;
-        double t2n = sqrt(t2x * t2x + t2y * t2y + t2z * t2z);
-        t2x /= t2n; t2y /= t2n; t2z /= t2n;
-        double wn = 1.0 / a.prm.noise_along_normal, wt = 1.0 / a.prm.tangential_noise;
-        f[0] = nx * wn; f[1] = ny * wn; f[2] = nz * wn;
-        f[3] = t1x * wt; f[4] = t1y * wt; f[5] = t1z * wt;
-        f[6] = t2x * wt; f[7] = t2y * wt; f[8] = t2z * wt;
-    }
-    double R[9];
-    pose_matrix(th, R);
-    double ix, iy, iz;
-    inverse_pose(th, R, tx, ty, tz, ix, iy, iz);                    // :108,129 inversePoseTransform(targetPoint)
-    double y0 = (ix - m.ref[3 * id]) - m.mean[3 * id], y1 = (iy - m.ref[3 * id + 1]) - m.mean[3 * id + 1],
-           y2 = (iz - m.ref[3 * id + 2]) - m.mean[3 * id + 2];
-    for (int k = 0; k < 9; k++) F[k] = f[k];
-    y[0] = f[0] * y0 + f[1] * y1 + f[2] * y2;
-    y[1] = f[3] * y0 + f[4] * y1 + f[5] * y2;
-    y[2] = f[6] * y0 + f[7] * y1 + f[8] * y2;
 }
 
 void launch_observations(const ObsArgs &a, const ObsDev &o, cudaStream_t s) {
@@ -97,7 +125,13 @@ void launch_observations(const ObsArgs &a, const ObsDev &o, cudaStream_t s) {
     long long total = (long long)a.C * o.n;
     ICP_CUDA(cudaMemsetAsync(o.nobs, 0, sizeof(int) * a.C, s));
     if (total <= 0) return;
-    k_observations<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a, o);
+    size_t smem = sizeof(double) * 3 * (size_t)a.m.N;
+    if (smem <= 160 * 1024 && o.n >= 32) {
+        ICP_CUDA(cudaFuncSetAttribute(k_observations<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_observations<true><<<a.C, 256, smem, s>>>(a, o);
+    } else {
+        k_observations<false><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, o);
+    }
     ICP_CUDA(cudaGetLastError());
 }
 
