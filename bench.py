@@ -254,11 +254,14 @@ def run_gpu(args):
     import ctypes as Cc
     # untimed warm-up call of the same size (sizes the library's staging buffers; W >= 3 steps run inside it too)
     _lib.check(chain.lib.icp_chain_run(chain.h, C, max(warm, e_steps), _lib.dptr(h_th0), Cc.byref(io)), ctx.h)
-    barrier()
-    t0 = time.perf_counter()
-    _lib.check(chain.lib.icp_chain_run(chain.h, C, e_steps, _lib.dptr(h_th0), Cc.byref(io)), ctx.h)
-    torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_runs = []
+    for _ in range(3):          # three timed end-to-end calls of exactly K steps; the median is reported, all are listed
+        barrier()
+        t0 = time.perf_counter()
+        _lib.check(chain.lib.icp_chain_run(chain.h, C, e_steps, _lib.dptr(h_th0), Cc.byref(io)), ctx.h)
+        torch.cuda.synchronize()
+        e2e_runs.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+    e2e_ms = float(np.median(e2e_runs))
     barrier()
     # the host call evaluates theta0 once (1 extra state) before the K steps: count K steps of C samples
     e2e_value = world * C * e_steps / (e2e_ms * 1e-3)
@@ -318,7 +321,8 @@ def run_gpu(args):
                            "chains_per_gpu": C, "samples_per_step": world * C, "n_icp_points": int(len(ids)), "n_eval_points": int(len(eids)),
                            "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
                            "l2_policy": "per-step working set (posteriors 4x%.0f MB + meshes) exceeds L2" % (C * 104 * 104 * 8 / 1e6)},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e_steps},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e_steps,
+                        "runs_ms": e2e_runs, "note": "median of 3 host-buffer icp_chain_run calls of K steps: pinned theta0 in, full chain log out"},
                 "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / steps, "accept_rate": accept_rate,
                 "clocks": clocks.summary(), "roofline": roofline, "roofline_closest_point": roof_cp, "closest_point": cp,
                 "kernel_shares": shares, "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items() if v["launches"]},
@@ -340,7 +344,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chains", type=int, default=1184, help="chains per GPU (8 x 148 SMs)")
+    ap.add_argument("--chains", type=int, default=2368, help="chains per GPU (16 x 148 SMs)")
     ap.add_argument("--cpu-steps", type=int, default=12, help="MH steps of the cpu_baseline sample")
     ap.add_argument("--ref-steps", type=int, default=4, help="MH steps per chain and bench step of --impl reference")
     args = ap.parse_args()

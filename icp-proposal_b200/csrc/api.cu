@@ -205,6 +205,7 @@ extern "C" int32_t icp_model_create(icp_ctx ctx, int32_t N, int32_t T, int32_t K
         const int Kp = m->Kp;
         size_t n3 = (size_t)3 * N;
         m->ref.upload(ref_xyz, n3, s);
+        m->h_ref.assign(ref_xyz, ref_xyz + n3);
         std::vector<double> mean(n3, 0.0);
         if (mean_def) std::copy(mean_def, mean_def + n3, mean.begin());
         m->mean.upload(mean.data(), n3, s);
@@ -546,6 +547,30 @@ extern "C" int32_t icp_model_closest_vertex(icp_model m, int32_t C, const double
 // ---------------------------------------------------------------------------------------------------
 // (5) ICP proposal
 // ---------------------------------------------------------------------------------------------------
+// Order in which the closest-point kernel walks a list of model points: Morton order of their reference positions,
+// so that the 32 queries of a warp stay close together in the target tree (results keep the caller's order).
+static std::vector<int> morton_perm(const std::vector<double> &ref, const int32_t *ids, int n) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n; i++)
+        for (int d = 0; d < 3; d++) { double x = ref[(size_t)3 * ids[i] + d]; lo[d] = std::min(lo[d], x); hi[d] = std::max(hi[d], x); }
+    std::vector<std::pair<uint32_t, int>> key(n);
+    for (int i = 0; i < n; i++) {
+        uint32_t code = 0;
+        uint32_t q[3];
+        for (int d = 0; d < 3; d++) {
+            double f = hi[d] > lo[d] ? (ref[(size_t)3 * ids[i] + d] - lo[d]) / (hi[d] - lo[d]) : 0.0;
+            q[d] = (uint32_t)(std::min(std::max(f, 0.0), 1.0) * 1023.0);
+        }
+        for (int b = 9; b >= 0; b--)
+            for (int d = 0; d < 3; d++) code = (code << 1) | ((q[d] >> b) & 1u);
+        key[i] = {code, i};
+    }
+    std::sort(key.begin(), key.end());
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; i++) perm[i] = key[i].second;
+    return perm;
+}
+
 static void check_ids(int N, const int32_t *ids, int n) {
     ICP_REQUIRE(n >= 0 && (n == 0 || ids != nullptr), "bad id list");
     for (int i = 0; i < n; i++) ICP_REQUIRE(ids[i] >= 0 && ids[i] < N, "model point id out of range");
@@ -568,6 +593,7 @@ extern "C" int32_t icp_proposal_create(icp_model m, icp_target t, const icp_prop
         p = new icp_proposal_s();
         p->model = m; p->target = t; p->prm = *params; p->n_ids = n_ids; p->n_tp = n_tp;
         p->ids.upload(model_point_ids, n_ids, _ctx->stream);
+        if (n_ids > 0) { std::vector<int> pm = morton_perm(m->h_ref, model_point_ids, n_ids); p->qperm.upload(pm.data(), pm.size(), _ctx->stream); sync_stream(_ctx); }
         p->tp.upload(target_points, (size_t)3 * n_tp, _ctx->stream);
         // constant-Gram fast path: model sampling, anisotropic noise with sd_n <= sd_t (kappa >= 0)
         {
@@ -643,7 +669,7 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
             w.cp.ensure(3 * tot);
             NearestArgs a;
             a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = n;
-            a.Xq = d_X; a.q_ids = p->ids.p; a.Nq = m->N; a.out_cp = w.cp.p;
+            a.Xq = d_X; a.q_ids = p->ids.p; a.Nq = m->N; a.out_cp = w.cp.p; a.perm = p->qperm.p;
             launch_nearest(a, s);
             oa.cp = w.cp.p; oa.cp_stride = n; oa.cp_map = nullptr;
         }
@@ -666,8 +692,11 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
     GramFast gf{p->Gs.p, 1.0 / (p->prm.tangential_noise * p->prm.tangential_noise),
                 std::sqrt(std::max(0.0, 1.0 - (p->prm.noise_along_normal * p->prm.noise_along_normal) /
                                                   (p->prm.tangential_noise * p->prm.tangential_noise)))};
-    launch_posterior_build(md, C, od, w.M.p, w.b.p, s, (p->gram_fast && all_kept) ? &gf : nullptr);
-    launch_cholesky_solve(C, m->K, Kp, w.M.p, w.b.p, d_L, d_mu, d_out_slot, w.status.p, s);
+    const GramFast *gfp = (p->gram_fast && all_kept) ? &gf : nullptr;
+    if (!launch_posterior_fused(md, C, od, gfp, w.want_M ? w.M.p : nullptr, d_L, d_mu, d_out_slot, w.status.p, s)) {
+        launch_posterior_build(md, C, od, w.M.p, w.b.p, s, gfp);
+        launch_cholesky_solve(C, m->K, Kp, w.M.p, w.b.p, d_L, d_mu, d_out_slot, w.status.p, s);
+    }
 }
 
 }  // namespace icp
@@ -687,7 +716,9 @@ extern "C" int32_t icp_posterior(icp_proposal p, int32_t C, const double *theta,
     DevBuf<double> dL, dmu;
     dL.alloc((size_t)C * Kp * Kp);
     dmu.alloc((size_t)C * Kp);
+    p->work.want_M = M != nullptr;
     posterior_pipeline(p, C, p->s_theta.p, nullptr, p->work, dL.p, dmu.p, nullptr, s);
+    p->work.want_M = false;
     std::vector<double> hmu((size_t)C * Kp), hM;
     std::vector<int> hn(C), hst(C);
     download(hmu.data(), dmu.p, hmu.size(), s);
@@ -912,6 +943,7 @@ extern "C" int32_t icp_evaluator_create(icp_model m, icp_target t, const icp_eva
             std::vector<int> all(m->N);
             for (int i = 0; i < m->N; i++) all[i] = i;
             e->n_ids = m->N; e->ids.upload(all.data(), all.size(), s);
+            { std::vector<int> pm = morton_perm(m->h_ref, all.data(), m->N); e->qperm.upload(pm.data(), pm.size(), s); sync_stream(_ctx); }
             e->n_tp = t->Nt; e->tp.alloc((size_t)3 * t->Nt);
             ICP_CUDA(cudaMemcpyAsync(e->tp.p, t->verts.p, sizeof(double) * 3 * t->Nt, cudaMemcpyDeviceToDevice, s));
             ICP_REQUIRE(params->p0 > 0, "Exponential rate must be > 0");
@@ -919,6 +951,7 @@ extern "C" int32_t icp_evaluator_create(icp_model m, icp_target t, const icp_eva
             check_ids(m->N, model_point_ids, n_ids);
             ICP_REQUIRE(n_tp >= 0 && (n_tp == 0 || target_points != nullptr), "bad target point list");
             e->n_ids = n_ids; e->ids.upload(model_point_ids, n_ids, s);
+            if (n_ids > 0) { std::vector<int> pm = morton_perm(m->h_ref, model_point_ids, n_ids); e->qperm.upload(pm.data(), pm.size(), s); sync_stream(_ctx); }
             e->n_tp = n_tp; e->tp.upload(target_points, (size_t)3 * n_tp, s);
             if (params->kind != ICP_EVAL_ACCEPT_ALL) ICP_REQUIRE(params->p1 > 0, "Gaussian std-dev must be > 0");
             if (params->kind == ICP_EVAL_COLLECTIVE) ICP_REQUIRE(params->p2 > 0, "Exponential rate must be > 0");
@@ -971,7 +1004,7 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
             w.d2_m2t.ensure(tot);
             NearestArgs a;
             a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = e->n_ids;
-            a.Xq = d_X; a.q_ids = e->ids.p; a.Nq = m->N; a.out_d2 = w.d2_m2t.p;
+            a.Xq = d_X; a.q_ids = e->ids.p; a.Nq = m->N; a.out_d2 = w.d2_m2t.p; a.perm = e->qperm.p;
             if (collective || w.force_cp_m2t) { w.cp_m2t.ensure(3 * tot); a.out_cp = w.cp_m2t.p; }
             launch_nearest(a, s);
             if (collective && t->has_boundary) {

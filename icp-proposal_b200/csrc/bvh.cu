@@ -578,8 +578,8 @@ __global__ void k_query_morton(long long nq, const double *__restrict__ q, doubl
     if (!(fy == fy)) fy = 0.0;
     if (!(fz == fz)) fz = 0.0;
     unsigned long long ix = (unsigned long long)(fx * 1023.0), iy = (unsigned long long)(fy * 1023.0), iz = (unsigned long long)(fz * 1023.0);
-    // 5 bits per axis (32^3 cells) are enough for warp coherence and sort in two 8-bit radix passes
-    keys[i] = (unsigned int)(((expand21(ix) << 2) | (expand21(iy) << 1) | expand21(iz)) >> 15);
+    // 8 bits per axis: three 8-bit radix passes
+    keys[i] = (unsigned int)(((expand21(ix) << 2) | (expand21(iy) << 1) | expand21(iz)) >> 6);
     vals[i] = (int)i;
 }
 
@@ -597,9 +597,9 @@ void launch_nearest_sorted(NearestArgs a, QuerySort &qs, const double lo[3], con
     k_query_morton<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(nq, a.q, l2[0], l2[1], l2[2], sc[0], sc[1], sc[2], qs.keys.p, qs.vals.p);
     ICP_CUDA(cudaGetLastError());
     size_t tmp_bytes = 0;
-    ICP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, qs.keys.p, qs.keys2.p, qs.vals.p, qs.perm.p, (int)nq, 0, 15, s));
+    ICP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, qs.keys.p, qs.keys2.p, qs.vals.p, qs.perm.p, (int)nq, 0, 24, s));
     qs.tmp.ensure(tmp_bytes);
-    ICP_CUDA(cub::DeviceRadixSort::SortPairs(qs.tmp.p, tmp_bytes, qs.keys.p, qs.keys2.p, qs.vals.p, qs.perm.p, (int)nq, 0, 15, s));
+    ICP_CUDA(cub::DeviceRadixSort::SortPairs(qs.tmp.p, tmp_bytes, qs.keys.p, qs.keys2.p, qs.vals.p, qs.perm.p, (int)nq, 0, 24, s));
     a.perm = qs.perm.p;
     launch_nearest(a, s);
 }

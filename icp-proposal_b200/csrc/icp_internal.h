@@ -212,6 +212,8 @@ struct GramFast {
 void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, cudaStream_t s,
                             const GramFast *gf = nullptr);
 void launch_gram_rows(const ModelDev &m, int n_ids, const int *d_ids, double *d_G, cudaStream_t s);
+bool launch_posterior_fused(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, double *d_M_or_null, double *d_L,
+                            double *d_mu, const int *d_out_slot, int *d_status, cudaStream_t s);
 // in: M (C x Kp x Kp), b (C x Kp). out: L (lower Cholesky factor, C x Kp x Kp), mu = M^-1 b, status (0 ok)
 // out_slot (nullable): chain c writes L / mu at index out_slot[c] instead of c
 void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
@@ -274,6 +276,7 @@ struct icp_model_s {
     bool has_boundary = false;
     std::vector<uint8_t> h_boundary;
     std::vector<double> h_mean_def;
+    std::vector<double> h_ref;        // reference vertices (host copy: spatial ordering of query lists)
     double scale = 1.0;               // max |coordinate| of the reference mesh (box slack)
     icp::Bvh tri_bvh, vert_bvh;       // topology from the reference mesh, boxes refit per chain
     icp::ModelDev dev() const {
@@ -314,6 +317,7 @@ struct PosteriorWork {
     DevBuf<double> F, y;
     DevBuf<int> nobs;
     DevBuf<double> M, b;     // [C][Kp*Kp], [C][Kp]
+    bool want_M = false;     // the primitive API returns M; the chain runner never needs it in global memory
     DevBuf<int> status;
 };
 
@@ -326,6 +330,7 @@ struct icp_proposal_s {
     int n_ids = 0, n_tp = 0;
     icp::DevBuf<int> ids;     // n_ids
     icp::DevBuf<double> tp;   // n_tp x 3
+    icp::DevBuf<int> qperm;   // processing order of the model points (Morton order of their reference positions)
     icp::DevBuf<double> Gs;   // Kp x Kp: sum of Q_i^T Q_i over the model points (constant-Gram fast path), empty if unused
     bool gram_fast = false;
     // posterior cache (the reference's Memoize(icpPosterior, 20)): theta bytes -> slot
@@ -355,6 +360,7 @@ struct icp_evaluator_s {
     icp_evaluator_params prm{};
     int n_ids = 0, n_tp = 0;
     icp::DevBuf<int> ids;
+    icp::DevBuf<int> qperm;   // processing order of the model points (Morton order of their reference positions)
     icp::DevBuf<double> tp;
     icp::EvalWork work;
     icp::DevBuf<double> s_theta, s_values;

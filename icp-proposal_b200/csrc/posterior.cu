@@ -557,6 +557,128 @@ __global__ void __launch_bounds__(kChThreads) k_cholesky_solve(int K, int Kp, co
 // Back substitution L^T x = y runs 8 unknowns at a time the same way.
 constexpr int kCh2Threads = 128;
 
+// Factorises the matrix staged in shared memory (A: [Kp + 8][Kp + 4], lower triangle of M in rows 0..Kp-1, b in row Kp,
+// rows Kp+1..Kp+7 zero), solves M mu = b and stores L (lower, zero upper) and mu. Every one of the NT threads of the CTA
+// must call it (it synchronises the CTA); *bad (shared) must have been cleared before the preceding barrier.
+template <int NT>
+__device__ void chol_factor_solve_store(double *A, int Kp, int *bad, double *__restrict__ Lc, double *__restrict__ muc,
+                                        int *__restrict__ status) {
+    const int ld = Kp + 4, NB = Kp >> 3, R = Kp + 8;
+    double *dinv = A + (size_t)R * ld;      // [Kp] reciprocals of the diagonal of L
+    double *xs = dinv + Kp;                 // [Kp] running right-hand side of the back substitution
+    double *xo = xs + Kp;                   // [Kp] solution
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fc = lane & 3;
+    for (int bj = 0; bj < NB; bj++) {
+        if (bj > 0) {
+            for (int bi = bj + warp; bi <= NB; bi += NT / 32) {
+                double *pc = A + (8 * bi + fr) * ld + 8 * bj + 2 * fc;
+                double2 cc = *reinterpret_cast<double2 *>(pc);
+                const double *pa = A + (8 * bi + fr) * ld + fc;
+                const double *pb = A + (8 * bj + fr) * ld + fc;
+                // two accumulators halve the dependent DMMA chain
+                double e0 = 0.0, e1 = 0.0;
+#pragma unroll 4
+                for (int k = 0; k < 8 * bj; k += 8) {
+                    dmma_8x8x4(cc.x, cc.y, -pa[k], pb[k]);
+                    dmma_8x8x4(e0, e1, -pa[k + 4], pb[k + 4]);
+                }
+                cc.x += e0; cc.y += e1;
+                *reinterpret_cast<double2 *>(pc) = cc;
+            }
+            __syncthreads();
+        }
+        // diagonal block, factored redundantly by every thread
+        double l[8][8], inv[8];
+        const double *D = A + (8 * bj) * ld + 8 * bj;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int k = 0; k <= i; k++) l[i][k] = D[i * ld + k];
+        __syncthreads();
+        bool mybad = false;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            double s = l[j][j];
+            if (!(s > 0.0)) mybad = true;
+            // 1/sqrt(s) by rsqrt + one Newton step (full double accuracy), sqrt(s) = s * inv: one short dependent
+            // chain instead of a software sqrt followed by a software divide
+            double r = rsqrt(s);
+            r = fma(r * 0.5, fma(-s * r, r, 1.0), r);
+            inv[j] = r;
+            double d = s * r;
+            d = fma(fma(-d, d, s), 0.5 * r, d);
+            l[j][j] = d;
+#pragma unroll
+            for (int i = j + 1; i < 8; i++) l[i][j] *= inv[j];
+#pragma unroll
+            for (int i = j + 1; i < 8; i++)
+#pragma unroll
+                for (int k = j + 1; k <= i; k++) l[i][k] = fma(-l[i][j], l[k][j], l[i][k]);
+        }
+        if (mybad && tid == 0) *bad = 1;
+        if (tid < 8) {
+            dinv[8 * bj + tid] = inv[tid];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i == tid) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) A[(8 * bj + i) * ld + 8 * bj + k] = k <= i ? l[i][k] : 0.0;
+                }
+        }
+        for (int r = 8 * bj + 8 + tid; r < R; r += NT) {
+            double *row = A + r * ld + 8 * bj;
+            double x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[j] = row[j];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double t = x[j];
+#pragma unroll
+                for (int k = 0; k < j; k++) t = fma(-x[k], l[j][k], t);
+                x[j] = t * inv[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) row[j] = x[j];
+        }
+        __syncthreads();
+    }
+    // back substitution L^T x = y (y = row Kp of A)
+    for (int k = tid; k < Kp; k += NT) xs[k] = A[Kp * ld + k];
+    __syncthreads();
+    for (int bj = NB - 1; bj >= 0; bj--) {
+        const double *D = A + (8 * bj) * ld + 8 * bj;
+        double x[8];
+#pragma unroll
+        for (int i = 7; i >= 0; i--) {
+            double t = xs[8 * bj + i];
+#pragma unroll
+            for (int k = i + 1; k < 8; k++) t = fma(-D[k * ld + i], x[k], t);
+            x[i] = t * dinv[8 * bj + i];
+        }
+        if (tid < 8) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i == tid) xo[8 * bj + i] = x[i];
+        }
+        for (int k = tid; k < 8 * bj; k += NT) {
+            double t = xs[k];
+#pragma unroll
+            for (int p = 0; p < 8; p++) t = fma(-A[(8 * bj + p) * ld + k], x[p], t);
+            xs[k] = t;
+        }
+        __syncthreads();
+    }
+    bool isbad = *bad != 0;
+    for (int e = tid; e < Kp * Kp; e += NT) {
+        int i = e / Kp, j = e - i * Kp;
+        double v = j <= i ? A[i * ld + j] : 0.0;
+        Lc[e] = isbad ? NAN : v;
+    }
+    for (int j = tid; j < Kp; j += NT) muc[j] = isbad ? NAN : xo[j];
+    if (tid == 0 && status) *status = isbad ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(kCh2Threads) k_cholesky_solve_mma(int K, int Kp, const double *__restrict__ M,
                                                                      const double *__restrict__ bvec,
                                                                      double *__restrict__ L, double *__restrict__ mu,
@@ -603,118 +725,224 @@ __global__ void __launch_bounds__(kCh2Threads) k_cholesky_solve_mma(int K, int K
         A[(Kp + r) * ld + j] = (r == 0 && j < Kp) ? bvec[(size_t)c * Kp + j] : 0.0;
     }
     __syncthreads();
-    const int fr = lane >> 2, fc = lane & 3;
-    for (int bj = 0; bj < NB; bj++) {
-        if (bj > 0) {
-            for (int bi = bj + warp; bi <= NB; bi += kCh2Threads / 32) {
-                double *pc = A + (8 * bi + fr) * ld + 8 * bj + 2 * fc;
-                double2 cc = *reinterpret_cast<double2 *>(pc);
-                const double *pa = A + (8 * bi + fr) * ld + fc;
-                const double *pb = A + (8 * bj + fr) * ld + fc;
-                // two accumulators halve the dependent DMMA chain
-                double e0 = 0.0, e1 = 0.0;
-#pragma unroll 4
-                for (int k = 0; k < 8 * bj; k += 8) {
-                    dmma_8x8x4(cc.x, cc.y, -pa[k], pb[k]);
-                    dmma_8x8x4(e0, e1, -pa[k + 4], pb[k + 4]);
-                }
-                cc.x += e0; cc.y += e1;
-                *reinterpret_cast<double2 *>(pc) = cc;
-            }
-            __syncthreads();
-        }
-        // diagonal block, factored redundantly by every thread
-        double l[8][8], inv[8];
-        const double *D = A + (8 * bj) * ld + 8 * bj;
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-#pragma unroll
-            for (int k = 0; k <= i; k++) l[i][k] = D[i * ld + k];
-        __syncthreads();
-        bool mybad = false;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            double s = l[j][j];
-            if (!(s > 0.0)) mybad = true;
-            // 1/sqrt(s) by rsqrt + one Newton step (full double accuracy), sqrt(s) = s * inv: one short dependent
-            // chain instead of a software sqrt followed by a software divide
-            double r = rsqrt(s);
-            r = fma(r * 0.5, fma(-s * r, r, 1.0), r);
-            inv[j] = r;
-            double d = s * r;
-            d = fma(fma(-d, d, s), 0.5 * r, d);
-            l[j][j] = d;
-#pragma unroll
-            for (int i = j + 1; i < 8; i++) l[i][j] *= inv[j];
-#pragma unroll
-            for (int i = j + 1; i < 8; i++)
-#pragma unroll
-                for (int k = j + 1; k <= i; k++) l[i][k] = fma(-l[i][j], l[k][j], l[i][k]);
-        }
-        if (mybad && tid == 0) bad = 1;
-        if (tid < 8) {
-            dinv[8 * bj + tid] = inv[tid];
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (i == tid) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) A[(8 * bj + i) * ld + 8 * bj + k] = k <= i ? l[i][k] : 0.0;
-                }
-        }
-        for (int r = 8 * bj + 8 + tid; r < R; r += kCh2Threads) {
-            double *row = A + r * ld + 8 * bj;
-            double x[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) x[j] = row[j];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                double t = x[j];
-#pragma unroll
-                for (int k = 0; k < j; k++) t = fma(-x[k], l[j][k], t);
-                x[j] = t * inv[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j++) row[j] = x[j];
-        }
-        __syncthreads();
-    }
-    // back substitution L^T x = y (y = row Kp of A)
-    for (int k = tid; k < Kp; k += kCh2Threads) xs[k] = A[Kp * ld + k];
-    __syncthreads();
-    for (int bj = NB - 1; bj >= 0; bj--) {
-        const double *D = A + (8 * bj) * ld + 8 * bj;
-        double x[8];
-#pragma unroll
-        for (int i = 7; i >= 0; i--) {
-            double t = xs[8 * bj + i];
-#pragma unroll
-            for (int k = i + 1; k < 8; k++) t = fma(-D[k * ld + i], x[k], t);
-            x[i] = t * dinv[8 * bj + i];
-        }
-        if (tid < 8) {
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (i == tid) xo[8 * bj + i] = x[i];
-        }
-        for (int k = tid; k < 8 * bj; k += kCh2Threads) {
-            double t = xs[k];
-#pragma unroll
-            for (int p = 0; p < 8; p++) t = fma(-A[(8 * bj + p) * ld + k], x[p], t);
-            xs[k] = t;
-        }
-        __syncthreads();
-    }
     int oc = out_slot ? out_slot[c] : c;
-    double *Lc = L + (size_t)oc * Kp * Kp;
-    bool isbad = bad != 0;
-    for (int e = tid; e < Kp * Kp; e += kCh2Threads) {
-        int i = e / Kp, j = e - i * Kp;
-        double v = j <= i ? A[i * ld + j] : 0.0;
-        Lc[e] = isbad ? NAN : v;
-    }
-    for (int j = tid; j < Kp; j += kCh2Threads) mu[(size_t)oc * Kp + j] = isbad ? NAN : xo[j];
-    if (tid == 0 && status) status[c] = isbad ? 1 : 0;
+    chol_factor_solve_store<kCh2Threads>(A, Kp, &bad, L + (size_t)oc * Kp * Kp, mu + (size_t)oc * Kp, status ? status + c : nullptr);
     (void)K;
+}
+
+// Fused variant: posterior build (as k_posterior_build_mma) + Cholesky + solve in one kernel. The accumulator
+// fragments go straight into the shared-memory matrix of the factorisation (M never visits global memory unless the
+// caller asks for it), and with two CTAs per SM the latency-bound factorisation of one chain overlaps the DMMA
+// stream of the other.
+// RPO = rows of A per observation. RPO = 3: the general whitened rows F_i Q_i. RPO = 1 (constant-Gram fast path,
+// model sampling with every observation kept and sd_n <= sd_t): Sigma_i^-1 = I / sd_t^2 + kappa n n^T with
+// kappa = 1/sd_n^2 - 1/sd_t^2, so M = I + Gs / sd_t^2 + sum_i (sqrt(kappa) Q_i^T n_i)(...)^T where
+// Gs = sum_i Q_i^T Q_i is a constant of the proposal: one row per observation, a third of the DMMA work.
+template <int NBLK, int NBMAX, int NWC, int RPO>
+__global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(ModelDev m, ObsDev o, double *__restrict__ M_out,
+                                                                             int nblk_total, const double *__restrict__ Gs,
+                                                                             double gs_scale, double row_scale,
+                                                                             double *__restrict__ L, double *__restrict__ mu,
+                                                                             const int *__restrict__ out_slot,
+                                                                             int *__restrict__ status) {
+    extern __shared__ double sm[];
+    const int Kp = m.Kp, ld = Kp + 4, NB = Kp >> 3;
+    const int bufsz = kMmaRows * ld;
+    double *sA = sm;                    // [2][24][ld]; later reused as the matrix of the factorisation
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int nthreads = (NWC + kProdWarps) * 32, nwc = NWC;
+    constexpr int kObsChunk = kMmaRows / RPO;   // observations per staged chunk (8 or 24)
+    const int nchunks = (o.n + kObsChunk - 1) / kObsChunk;
+    if (warp < nwc) {
+        // ------------------------------- consumers: DMMA ------------------------------------------------
+        const int per = (nblk_total + nwc - 1) / nwc;
+        const int b0 = warp * per;
+        const int nmine = max(0, min(nblk_total, b0 + per) - b0);
+        int bi0, bj0;
+        tri_index(b0 < nblk_total ? b0 : 0, bi0, bj0);
+        double acc[NBLK][2];
+#pragma unroll
+        for (int s = 0; s < NBLK; s++) acc[s][0] = acc[s][1] = 0.0;
+        const int frag = (lane & 3) * ld + (lane >> 2);
+        named_bar_arrive<3>(nthreads);  // both buffers start empty
+        named_bar_arrive<4>(nthreads);
+        for (int ch = 0; ch < nchunks; ch++) {
+            const int buf = ch & 1;
+            if (buf == 0) named_bar_sync<1>(nthreads); else named_bar_sync<2>(nthreads);
+            const double *base = sA + buf * bufsz + frag;
+            int bi = bi0, bj = bj0;
+            double fa[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) fa[k] = base[k * 4 * ld + 8 * bi];
+#pragma unroll
+            for (int s = 0; s < NBLK; s++) {
+                if (s < nmine) {
+                    double fb[6];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) fb[k] = base[k * 4 * ld + 8 * bj];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) dmma_8x8x4(acc[s][0], acc[s][1], fa[k], fb[k]);
+                    if (++bj > bi) {
+                        bj = 0;
+                        if (++bi < NB) {
+#pragma unroll
+                            for (int k = 0; k < 6; k++) fa[k] = base[k * 4 * ld + 8 * bi];
+                        }
+                    }
+                }
+            }
+            if (buf == 0) named_bar_arrive<3>(nthreads); else named_bar_arrive<4>(nthreads);
+        }
+        named_bar_sync<6>(nthreads);   // staging buffers and the b scratch are free: the matrix takes their place
+        int bi = bi0, bj = bj0;
+#pragma unroll
+        for (int s = 0; s < NBLK; s++) {
+            if (s < nmine) {
+                int i = 8 * bi + (lane >> 2), j = 8 * bj + 2 * (lane & 3);
+                double v0 = acc[s][0] + (i == j ? 1.0 : 0.0), v1 = acc[s][1] + (i == j + 1 ? 1.0 : 0.0);
+                if (RPO == 1) {
+                    double2 g = __ldg(reinterpret_cast<const double2 *>(Gs + (size_t)i * Kp + j));
+                    v0 = fma(g.x, gs_scale, v0);
+                    v1 = fma(g.y, gs_scale, v1);
+                }
+                *reinterpret_cast<double2 *>(sA + (size_t)i * ld + j) = make_double2(v0, v1);
+                if (++bj > bi) { bj = 0; ++bi; }
+            }
+        }
+    } else {
+        // ------------------------------- producers: gather + whiten ----------------------------------------
+        const int pt = tid - nwc * 32;          // 0 .. 63
+        const int ob = pt >> 3, cg = pt & 7;     // observation slot within the chunk, column group
+        const int *vid = o.vid + (size_t)c * o.n;
+        const double *F = o.F + (size_t)c * o.n * 9;
+        const double *y = o.y + (size_t)c * o.n * 3;
+        double bacc[NBMAX];
+#pragma unroll
+        for (int i = 0; i < NBMAX; i++) bacc[i] = 0.0;
+        // the vertex ids gate the addresses of every basis-row load: stage them in shared memory once so that a
+        // pass pays one L2 round trip (ids -> rows would be two dependent ones)
+        int *svid = reinterpret_cast<int *>(sm + 2 * bufsz + 8 * Kp);
+        const bool vid_staged = o.n <= kMaxStagedIds;
+        if (vid_staged) {
+            for (int e = pt; e < o.n; e += kProdWarps * 32) svid[e] = __ldg(&vid[e]);
+            named_bar_sync<5>(kProdWarps * 32);
+        }
+        for (int ch = 0; ch < nchunks; ch++) {
+            const int buf = ch & 1;
+#pragma unroll 1
+            for (int pass = 0; pass < kObsChunk / 8; pass++) {
+                const int lo = pass * 8 + ob;            // observation slot within the chunk
+                const int gi = ch * kObsChunk + lo;
+                int v = -1;
+                double f[9], yy[3];
+                if (gi < o.n) v = vid_staged ? svid[gi] : __ldg(&vid[gi]);
+                if (v >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 9; k++) f[k] = __ldg(F + (size_t)gi * 9 + k);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) yy[k] = __ldg(y + (size_t)gi * 3 + k);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 9; k++) f[k] = 0.0;
+                    yy[0] = yy[1] = yy[2] = 0.0;
+                }
+                const double *q = m.Q + (size_t)3 * (v >= 0 ? v : 0) * Kp + cg;
+                double q0[NBMAX], q1[NBMAX], q2[NBMAX];
+#pragma unroll
+                for (int i = 0; i < NBMAX; i++) {
+                    if (i < NB) { q0[i] = __ldg(q + 8 * i); q1[i] = __ldg(q + Kp + 8 * i); q2[i] = __ldg(q + 2 * Kp + 8 * i); }
+                }
+                if (pass == 0) {  // consumers are done with this buffer
+                    if (buf == 0) named_bar_sync<3>(nthreads); else named_bar_sync<4>(nthreads);
+                }
+                double *dst = sA + buf * bufsz + (RPO * lo) * ld + cg;
+#pragma unroll
+                for (int i = 0; i < NBMAX; i++) {
+                    if (i < NB) {
+                        double a0 = f[0] * q0[i] + f[1] * q1[i] + f[2] * q2[i];
+                        double a1 = f[3] * q0[i] + f[4] * q1[i] + f[5] * q2[i];
+                        double a2 = f[6] * q0[i] + f[7] * q1[i] + f[8] * q2[i];
+                        if (RPO == 3) { dst[8 * i] = a0; dst[ld + 8 * i] = a1; dst[2 * ld + 8 * i] = a2; }
+                        else dst[8 * i] = a0 * row_scale;
+                        bacc[i] = fma(a0, yy[0], fma(a1, yy[1], fma(a2, yy[2], bacc[i])));
+                    }
+                }
+            }
+            if (buf == 0) named_bar_arrive<1>(nthreads); else named_bar_arrive<2>(nthreads);
+        }
+        // reduce b over the 8 observation slots (fixed order: deterministic)
+        named_bar_sync<5>(kProdWarps * 32);      // producers only
+        // the last two buffers may still be read by consumers: use the tail of the shared allocation
+        double *sb = sm + 2 * bufsz;             // [8][Kp]
+#pragma unroll
+        for (int i = 0; i < NBMAX; i++)
+            if (i < NB) sb[ob * Kp + cg + 8 * i] = bacc[i];
+        named_bar_sync<5>(kProdWarps * 32);
+        double bval[(8 * NBMAX + kProdWarps * 32 - 1) / (kProdWarps * 32)];
+#pragma unroll
+        for (int u = 0; u < (8 * NBMAX + kProdWarps * 32 - 1) / (kProdWarps * 32); u++) {
+            int j = pt + u * kProdWarps * 32;
+            double t = 0.0;
+            if (j < Kp) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) t += sb[r * Kp + j];
+            }
+            bval[u] = t;
+        }
+        named_bar_sync<6>(nthreads);
+        // right-hand side = block row NB of the factorisation (row Kp real, 7 zero rows)
+        for (int e = pt; e < 8 * ld; e += kProdWarps * 32) sA[(size_t)Kp * ld + e] = 0.0;
+        named_bar_sync<5>(kProdWarps * 32);
+#pragma unroll
+        for (int u = 0; u < (8 * NBMAX + kProdWarps * 32 - 1) / (kProdWarps * 32); u++) {
+            int j = pt + u * kProdWarps * 32;
+            if (j < Kp) sA[(size_t)Kp * ld + j] = bval[u];
+        }
+    }
+    __syncthreads();
+    if (M_out) {   // only the primitive API (icp_posterior) asks for M
+        double *Mc = M_out + (size_t)c * Kp * Kp;
+        for (int e = tid; e < Kp * Kp; e += nthreads) {
+            int i = e / Kp, j = e - i * Kp;
+            Mc[e] = j <= i ? sA[(size_t)i * ld + j] : sA[(size_t)j * ld + i];
+        }
+    }
+    const int oc = out_slot ? out_slot[c] : c;
+    chol_factor_solve_store<nthreads>(sA, Kp, &bad, L + (size_t)oc * Kp * Kp, mu + (size_t)oc * Kp, status ? status + c : nullptr);
+}
+
+template <int NBLK, int NBMAX, int NWC>
+static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M, int total, const GramFast *gf, double *d_L,
+                         double *d_mu, const int *d_out_slot, int *d_status, cudaStream_t s) {
+    const int Kp = m.Kp, ld = Kp + 4;
+    size_t stage = (size_t)2 * kMmaRows * ld + 8 * Kp + (std::min(o.n, kMaxStagedIds) + 1) / 2;
+    size_t fact = (size_t)(Kp + 8) * ld + 3 * Kp;
+    size_t smem = sizeof(double) * std::max(stage, fact);
+    if (gf) {
+        ICP_CUDA(cudaFuncSetAttribute(k_posterior_fused<NBLK, NBMAX, NWC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_posterior_fused<NBLK, NBMAX, NWC, 1><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, total, gf->Gs, gf->gs_scale, gf->row_scale, d_L, d_mu, d_out_slot, d_status);
+    } else {
+        ICP_CUDA(cudaFuncSetAttribute(k_posterior_fused<NBLK, NBMAX, NWC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_posterior_fused<NBLK, NBMAX, NWC, 3><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, total, nullptr, 0.0, 1.0, d_L, d_mu, d_out_slot, d_status);
+    }
+}
+
+// posterior build + Cholesky + solve in one launch; returns false when the shape is outside the DMMA kernels' range
+// (the caller then runs launch_posterior_build + launch_cholesky_solve)
+bool launch_posterior_fused(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, double *d_M_or_null, double *d_L,
+                            double *d_mu, const int *d_out_slot, int *d_status, cudaStream_t s) {
+    static const bool off = (getenv("ICPCUDA_NO_DMMA") && getenv("ICPCUDA_NO_DMMA")[0] == '1') ||
+                            (getenv("ICPCUDA_NO_FUSE") && getenv("ICPCUDA_NO_FUSE")[0] == '1');
+    const int NB = m.Kp / 8, total = NB * (NB + 1) / 2;
+    if (off || NB > 13 || C <= 0) return false;   // NB <= 13: the 192-thread variants; the fused matrix must fit 2 CTAs / SM
+    ProfScope _ps(ST_POSTERIOR_BUILD, s);
+    if (NB <= 4) launch_fused<4, 4, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, s);
+    else if (NB <= 7) launch_fused<8, 7, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, s);
+    else launch_fused<24, 13, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, s);
+    ICP_CUDA(cudaGetLastError());
+    return true;
 }
 
 void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
