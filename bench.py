@@ -255,7 +255,7 @@ def run_gpu(args):
     # untimed warm-up call of the same size (sizes the library's staging buffers; W >= 3 steps run inside it too)
     _lib.check(chain.lib.icp_chain_run(chain.h, C, max(warm, e_steps), _lib.dptr(h_th0), Cc.byref(io)), ctx.h)
     e2e_runs = []
-    for _ in range(3):          # three timed end-to-end calls of exactly K steps; the median is reported, all are listed
+    for _ in range(5):          # five timed end-to-end calls of exactly K steps; the median is reported, all are listed
         barrier()
         t0 = time.perf_counter()
         _lib.check(chain.lib.icp_chain_run(chain.h, C, e_steps, _lib.dptr(h_th0), Cc.byref(io)), ctx.h)
@@ -322,7 +322,7 @@ def run_gpu(args):
                            "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
                            "l2_policy": "per-step working set (posteriors 4x%.0f MB + meshes) exceeds L2" % (C * 104 * 104 * 8 / 1e6)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e_steps,
-                        "runs_ms": e2e_runs, "note": "median of 3 host-buffer icp_chain_run calls of K steps: pinned theta0 in, full chain log out"},
+                        "runs_ms": e2e_runs, "note": "median of 5 host-buffer icp_chain_run calls of K steps: pinned theta0 in, full chain log out"},
                 "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / steps, "accept_rate": accept_rate,
                 "clocks": clocks.summary(), "roofline": roofline, "roofline_closest_point": roof_cp, "closest_point": cp,
                 "kernel_shares": shares, "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items() if v["launches"]},

@@ -371,6 +371,11 @@ struct icp_chain_s {
     int last_per_step = 0;
     bool use_graph = true;
     int resident_C = 0;      // chains whose state is resident from the last run (resume)
+    int sized_C = 0;         // every workspace is allocated for this many chains (graph capture cannot allocate)
+    cudaGraphExec_t exec = nullptr;   // cached step graph + the bytes of the kernel arguments it was captured with
+    std::string exec_key;
+    DevBuf<double> d_theta0, d_final;   // persistent staging of the host-buffer entry point
+    DevBuf<long long> d_nacc;
     int steps_total = 0;     // value of the device step counter
 };
 
@@ -474,6 +479,7 @@ extern "C" int32_t icp_chain_destroy(icp_chain c) {
     try {
         CtxLock lock(_ctx);
         ICP_CUDA(cudaStreamSynchronize(_ctx->stream));
+        if (c->exec) cudaGraphExecDestroy(c->exec);
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
         delete c;
@@ -596,44 +602,60 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     // state of theta0: log-values + posteriors of every ICP component (state 0)
     if (!resume) enqueue_state_eval(r, ch->theta_cur.p, ch->values_cur.p, ch->slot_cur.p);
 
-    // launches per step, for the report
-    int per_step = 0;
+    // The step graph is cached on the chain: its kernel arguments are the state / RNG / log descriptors by value, so it
+    // can be replayed by any later call whose descriptors are byte-identical (same C, buffers, seed, offsets).
     int steps_done = 0;
-    if (n_steps > 0 && (!resume || !ch->use_graph)) {
+    const bool sized = ch->sized_C == C;
+    if (n_steps > 0 && (!sized || !ch->use_graph || g_prof)) {
         // first step eagerly: sizes every workspace (allocation is illegal during capture)
         enqueue_step(r);
         steps_done = 1;
+        ch->sized_C = C;
     }
-    cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    if (ch->use_graph && !g_prof && n_steps - steps_done >= 1 && (resume || steps_done > 0)) {
-        ICP_CUDA(cudaStreamSynchronize(s));
-        cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
-        if (e == cudaSuccess) {
-            bool ok = true;
-            try {
-                enqueue_step(r);
-            } catch (...) {
-                ok = false;
-            }
-            e = cudaStreamEndCapture(s, &graph);
-            if (!ok || e != cudaSuccess || !graph) {
-                if (graph) cudaGraphDestroy(graph);
-                graph = nullptr;
-                cudaGetLastError();
-            } else {
-                size_t nn = 0;
-                cudaGraphGetNodes(graph, nullptr, &nn);
-                std::vector<cudaGraphNode_t> nodes(nn);
-                cudaGraphGetNodes(graph, nodes.data(), &nn);
-                for (size_t i = 0; i < nn; i++) {
-                    cudaGraphNodeType ty;
-                    if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) per_step++;
-                }
-                if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { exec = nullptr; cudaGetLastError(); }
-            }
+    if (ch->use_graph && !g_prof && n_steps - steps_done >= 1) {
+        ChainParams Pk = ch->P;
+        Pk.C = C;
+        std::string key;
+        key.append((const char *)&Pk, sizeof Pk);
+        key.append((const char *)&r.st, sizeof r.st);
+        key.append((const char *)&r.rng, sizeof r.rng);
+        key.append((const char *)&r.lg, sizeof r.lg);
+        if (ch->exec && ch->exec_key == key) {
+            exec = ch->exec;
         } else {
-            cudaGetLastError();
+            if (ch->exec) { cudaGraphExecDestroy(ch->exec); ch->exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                bool ok = true;
+                try {
+                    enqueue_step(r);
+                } catch (...) {
+                    ok = false;
+                }
+                e = cudaStreamEndCapture(s, &graph);
+                if (!ok || e != cudaSuccess || !graph) {
+                    if (graph) cudaGraphDestroy(graph);
+                    graph = nullptr;
+                    cudaGetLastError();
+                } else {
+                    size_t nn = 0;
+                    int per_step = 0;
+                    cudaGraphGetNodes(graph, nullptr, &nn);
+                    std::vector<cudaGraphNode_t> nodes(nn);
+                    cudaGraphGetNodes(graph, nodes.data(), &nn);
+                    for (size_t i = 0; i < nn; i++) {
+                        cudaGraphNodeType ty;
+                        if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) per_step++;
+                    }
+                    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { exec = nullptr; cudaGetLastError(); }
+                    cudaGraphDestroy(graph);
+                    if (exec) { ch->exec = exec; ch->exec_key = key; ch->last_per_step = per_step; }
+                }
+            } else {
+                cudaGetLastError();
+            }
         }
     }
     if (exec) {
@@ -648,16 +670,13 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     ICP_CUDA(cudaEventRecord(ch->ev1, s));
     ch->resident_C = C;
     ch->steps_total = step_base + n_steps;
-    if (per_step > 0) ch->last_per_step = per_step;
     ch->last_launches = (int64_t)ch->last_per_step * n_steps;
-    if (!async || exec) {
+    if (!async) {
         ICP_CUDA(cudaStreamSynchronize(s));
         float ms = 0;
         cudaEventElapsedTime(&ms, ch->ev0, ch->ev1);
         ch->last_ms = ms;
     }
-    if (exec) cudaGraphExecDestroy(exec);
-    if (graph) cudaGraphDestroy(graph);
 }
 
 }  // namespace
@@ -686,8 +705,8 @@ extern "C" int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const 
         const int K = m->K, Lt = K + kTheta0;
         ICP_REQUIRE(C >= 1 && C <= c->max_chains, "C must be in [1, max_chains]");
         size_t rec = (size_t)n_steps * C;
-        DevBuf<double> d_theta0, d_final;
-        DevBuf<long long> d_nacc;
+        DevBuf<double> &d_theta0 = c->d_theta0, &d_final = c->d_final;
+        DevBuf<long long> &d_nacc = c->d_nacc;
         d_theta0.upload(theta0, (size_t)C * Lt, s);
         icp_chain_io dio = *io;
         bool host_rng = io->u_comp || io->z || io->u_acc;
@@ -701,8 +720,8 @@ extern "C" int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const 
         if (io->log_accepted) { c->h_log_acc.ensure(rec); dio.log_accepted = c->h_log_acc.p; }
         if (io->log_values) { c->h_log_values.ensure(3 * rec); dio.log_values = c->h_log_values.p; }
         if (io->log_theta) { c->h_log_theta.ensure(rec * Lt); dio.log_theta = c->h_log_theta.p; }
-        if (io->theta_final) { d_final.alloc((size_t)C * Lt); dio.theta_final = d_final.p; }
-        if (io->n_accepted) { d_nacc.alloc(C); dio.n_accepted = (int64_t *)d_nacc.p; }
+        if (io->theta_final) { d_final.ensure((size_t)C * Lt); dio.theta_final = d_final.p; }
+        if (io->n_accepted) { d_nacc.ensure(C); dio.n_accepted = (int64_t *)d_nacc.p; }
         chain_run_device(c, C, n_steps, d_theta0.p, &dio, false);
         auto dl = [&](void *h, const void *d, size_t bytes) {
             if (h && bytes) ICP_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));

@@ -309,19 +309,49 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_build_mma
             double fa[6];
 #pragma unroll
             for (int k = 0; k < 6; k++) fa[k] = base[k * 4 * ld + 8 * bi];
+            // blocks are taken two at a time when both lie in the same block row (same A fragment): their DMMAs are
+            // interleaved so that consecutive DMMAs never accumulate into the same registers
 #pragma unroll
-            for (int s = 0; s < NBLK; s++) {
-                if (s < nmine) {
-                    double fb[6];
+            for (int s = 0; s < NBLK; s += 2) {
+                if (s + 1 < NBLK && s + 1 < nmine && bj + 1 <= bi) {
 #pragma unroll
-                    for (int k = 0; k < 6; k++) fb[k] = base[k * 4 * ld + 8 * bj];
+                    for (int half = 0; half < 2; half++) {
+                        double f0[3], f1[3];
 #pragma unroll
-                    for (int k = 0; k < 6; k++) dmma_8x8x4(acc[s][0], acc[s][1], fa[k], fb[k]);
-                    if (++bj > bi) {
+                        for (int k = 0; k < 3; k++) {
+                            f0[k] = base[(3 * half + k) * 4 * ld + 8 * bj];
+                            f1[k] = base[(3 * half + k) * 4 * ld + 8 * bj + 8];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            dmma_8x8x4(acc[s][0], acc[s][1], fa[3 * half + k], f0[k]);
+                            dmma_8x8x4(acc[s + 1 < NBLK ? s + 1 : s][0], acc[s + 1 < NBLK ? s + 1 : s][1], fa[3 * half + k], f1[k]);
+                        }
+                    }
+                    bj += 2;
+                    if (bj > bi) {
                         bj = 0;
                         if (++bi < NB) {
 #pragma unroll
                             for (int k = 0; k < 6; k++) fa[k] = base[k * 4 * ld + 8 * bi];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        if (s + u < NBLK && s + u < nmine) {
+                            double fb[6];
+#pragma unroll
+                            for (int k = 0; k < 6; k++) fb[k] = base[k * 4 * ld + 8 * bj];
+#pragma unroll
+                            for (int k = 0; k < 6; k++) dmma_8x8x4(acc[s + u < NBLK ? s + u : s][0], acc[s + u < NBLK ? s + u : s][1], fa[k], fb[k]);
+                            if (++bj > bi) {
+                                bj = 0;
+                                if (++bi < NB) {
+#pragma unroll
+                                    for (int k = 0; k < 6; k++) fa[k] = base[k * 4 * ld + 8 * bi];
+                                }
+                            }
                         }
                     }
                 }
@@ -776,19 +806,49 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
             double fa[6];
 #pragma unroll
             for (int k = 0; k < 6; k++) fa[k] = base[k * 4 * ld + 8 * bi];
+            // blocks are taken two at a time when both lie in the same block row (same A fragment): their DMMAs are
+            // interleaved so that consecutive DMMAs never accumulate into the same registers
 #pragma unroll
-            for (int s = 0; s < NBLK; s++) {
-                if (s < nmine) {
-                    double fb[6];
+            for (int s = 0; s < NBLK; s += 2) {
+                if (s + 1 < NBLK && s + 1 < nmine && bj + 1 <= bi) {
 #pragma unroll
-                    for (int k = 0; k < 6; k++) fb[k] = base[k * 4 * ld + 8 * bj];
+                    for (int half = 0; half < 2; half++) {
+                        double f0[3], f1[3];
 #pragma unroll
-                    for (int k = 0; k < 6; k++) dmma_8x8x4(acc[s][0], acc[s][1], fa[k], fb[k]);
-                    if (++bj > bi) {
+                        for (int k = 0; k < 3; k++) {
+                            f0[k] = base[(3 * half + k) * 4 * ld + 8 * bj];
+                            f1[k] = base[(3 * half + k) * 4 * ld + 8 * bj + 8];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            dmma_8x8x4(acc[s][0], acc[s][1], fa[3 * half + k], f0[k]);
+                            dmma_8x8x4(acc[s + 1 < NBLK ? s + 1 : s][0], acc[s + 1 < NBLK ? s + 1 : s][1], fa[3 * half + k], f1[k]);
+                        }
+                    }
+                    bj += 2;
+                    if (bj > bi) {
                         bj = 0;
                         if (++bi < NB) {
 #pragma unroll
                             for (int k = 0; k < 6; k++) fa[k] = base[k * 4 * ld + 8 * bi];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        if (s + u < NBLK && s + u < nmine) {
+                            double fb[6];
+#pragma unroll
+                            for (int k = 0; k < 6; k++) fb[k] = base[k * 4 * ld + 8 * bj];
+#pragma unroll
+                            for (int k = 0; k < 6; k++) dmma_8x8x4(acc[s + u < NBLK ? s + u : s][0], acc[s + u < NBLK ? s + u : s][1], fa[k], fb[k]);
+                            if (++bj > bi) {
+                                bj = 0;
+                                if (++bi < NB) {
+#pragma unroll
+                                    for (int k = 0; k < 6; k++) fa[k] = base[k * 4 * ld + 8 * bi];
+                                }
+                            }
                         }
                     }
                 }
