@@ -261,6 +261,18 @@ constexpr int kProdWarps = 2;         // producer warps (stage A = F Q into shar
 constexpr int kMaxNB = 20;         // largest supported Kp / 8
 constexpr int kMaxStagedIds = 4096;  // observation ids staged in shared memory by the producers
 
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int ID>
 __device__ __forceinline__ void named_bar_sync(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
 template <int ID>
@@ -889,48 +901,115 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
             for (int e = pt; e < o.n; e += kProdWarps * 32) svid[e] = __ldg(&vid[e]);
             named_bar_sync<5>(kProdWarps * 32);
         }
-        for (int ch = 0; ch < nchunks; ch++) {
-            const int buf = ch & 1;
+        if (vid_staged) {
+            // cp.async pipeline: the basis rows (and F, y) of pass p + 1 stream into shared memory while pass p is
+            // whitened - the producers no longer wait one L2 round trip per pass with nothing in flight
+            constexpr int ppc = kObsChunk / 8;            // passes (of 8 observations) per staged chunk
+            const int npass = nchunks * ppc;
+            double *raw = sm + 2 * bufsz + 8 * Kp + ((kMaxStagedIds < o.n ? kMaxStagedIds : o.n) + 3) / 4 * 2;   // 16-byte aligned
+            double *meta = raw + (size_t)2 * 8 * 3 * Kp;  // [2][8][12]: F (9) and y (3) of each observation of a pass
+            auto issue = [&](int pp) {
+                const int rb = pp & 1, gi = pp * 8 + ob;
+                const int v = gi < o.n ? svid[gi] : -1;
+                const double *src = m.Q + (size_t)3 * (v >= 0 ? v : 0) * Kp;
+                double *dr = raw + (size_t)((rb * 8 + ob) * 3) * Kp;
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+#pragma unroll
+                    for (int i = 0; i < (4 * NBMAX + 7) / 8; i++) {
+                        int j = 2 * (cg + 8 * i);
+                        if (j < Kp) cp_async_16(dr + d * Kp + j, src + d * Kp + j);
+                    }
+                if (gi < o.n) {
+                    double *dm = meta + (rb * 8 + ob) * 12;
+                    int k = cg;
+                    cp_async_8(dm + k, F + (size_t)gi * 9 + k);
+                    k = cg + 8;
+                    if (k < 9) cp_async_8(dm + k, F + (size_t)gi * 9 + k);
+                    else if (k < 12) cp_async_8(dm + k, y + (size_t)gi * 3 + (k - 9));
+                }
+                cp_async_commit();
+            };
+            issue(0);
 #pragma unroll 1
-            for (int pass = 0; pass < kObsChunk / 8; pass++) {
-                const int lo = pass * 8 + ob;            // observation slot within the chunk
-                const int gi = ch * kObsChunk + lo;
-                int v = -1;
+            for (int pp = 0; pp < npass; pp++) {
+                const int ch = pp / ppc, sub = pp - ch * ppc, buf = ch & 1, rb = pp & 1;
+                if (pp + 1 < npass) { issue(pp + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+                named_bar_sync<5>(kProdWarps * 32);       // every producer thread's copies of this pass have landed
+                const int gi = pp * 8 + ob;
+                const int v = gi < o.n ? svid[gi] : -1;
+                const double *mm = meta + (rb * 8 + ob) * 12;
                 double f[9], yy[3];
-                if (gi < o.n) v = vid_staged ? svid[gi] : __ldg(&vid[gi]);
-                if (v >= 0) {
 #pragma unroll
-                    for (int k = 0; k < 9; k++) f[k] = __ldg(F + (size_t)gi * 9 + k);
+                for (int k = 0; k < 9; k++) f[k] = v >= 0 ? mm[k] : 0.0;
 #pragma unroll
-                    for (int k = 0; k < 3; k++) yy[k] = __ldg(y + (size_t)gi * 3 + k);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 9; k++) f[k] = 0.0;
-                    yy[0] = yy[1] = yy[2] = 0.0;
-                }
-                const double *q = m.Q + (size_t)3 * (v >= 0 ? v : 0) * Kp + cg;
-                double q0[NBMAX], q1[NBMAX], q2[NBMAX];
-#pragma unroll
-                for (int i = 0; i < NBMAX; i++) {
-                    if (i < NB) { q0[i] = __ldg(q + 8 * i); q1[i] = __ldg(q + Kp + 8 * i); q2[i] = __ldg(q + 2 * Kp + 8 * i); }
-                }
-                if (pass == 0) {  // consumers are done with this buffer
+                for (int k = 0; k < 3; k++) yy[k] = v >= 0 ? mm[9 + k] : 0.0;
+                if (sub == 0) {  // consumers are done with this buffer
                     if (buf == 0) named_bar_sync<3>(nthreads); else named_bar_sync<4>(nthreads);
                 }
-                double *dst = sA + buf * bufsz + (RPO * lo) * ld + cg;
+                const double *rr = raw + (size_t)((rb * 8 + ob) * 3) * Kp + cg;
+                double *dst = sA + buf * bufsz + (RPO * (sub * 8 + ob)) * ld + cg;
 #pragma unroll
                 for (int i = 0; i < NBMAX; i++) {
                     if (i < NB) {
-                        double a0 = f[0] * q0[i] + f[1] * q1[i] + f[2] * q2[i];
-                        double a1 = f[3] * q0[i] + f[4] * q1[i] + f[5] * q2[i];
-                        double a2 = f[6] * q0[i] + f[7] * q1[i] + f[8] * q2[i];
+                        double q0 = rr[8 * i], q1 = rr[Kp + 8 * i], q2 = rr[2 * Kp + 8 * i];
+                        double a0 = f[0] * q0 + f[1] * q1 + f[2] * q2;
+                        double a1 = f[3] * q0 + f[4] * q1 + f[5] * q2;
+                        double a2 = f[6] * q0 + f[7] * q1 + f[8] * q2;
                         if (RPO == 3) { dst[8 * i] = a0; dst[ld + 8 * i] = a1; dst[2 * ld + 8 * i] = a2; }
                         else dst[8 * i] = a0 * row_scale;
                         bacc[i] = fma(a0, yy[0], fma(a1, yy[1], fma(a2, yy[2], bacc[i])));
                     }
                 }
+                if (sub == ppc - 1) {
+                    if (buf == 0) named_bar_arrive<1>(nthreads); else named_bar_arrive<2>(nthreads);
+                }
+                named_bar_sync<5>(kProdWarps * 32);       // the raw buffer may be refilled by the pass after next
             }
-            if (buf == 0) named_bar_arrive<1>(nthreads); else named_bar_arrive<2>(nthreads);
+        } else {
+        for (int ch = 0; ch < nchunks; ch++) {
+                const int buf = ch & 1;
+    #pragma unroll 1
+                for (int pass = 0; pass < kObsChunk / 8; pass++) {
+                    const int lo = pass * 8 + ob;            // observation slot within the chunk
+                    const int gi = ch * kObsChunk + lo;
+                    int v = -1;
+                    double f[9], yy[3];
+                    if (gi < o.n) v = vid_staged ? svid[gi] : __ldg(&vid[gi]);
+                    if (v >= 0) {
+    #pragma unroll
+                        for (int k = 0; k < 9; k++) f[k] = __ldg(F + (size_t)gi * 9 + k);
+    #pragma unroll
+                        for (int k = 0; k < 3; k++) yy[k] = __ldg(y + (size_t)gi * 3 + k);
+                    } else {
+    #pragma unroll
+                        for (int k = 0; k < 9; k++) f[k] = 0.0;
+                        yy[0] = yy[1] = yy[2] = 0.0;
+                    }
+                    const double *q = m.Q + (size_t)3 * (v >= 0 ? v : 0) * Kp + cg;
+                    double q0[NBMAX], q1[NBMAX], q2[NBMAX];
+    #pragma unroll
+                    for (int i = 0; i < NBMAX; i++) {
+                        if (i < NB) { q0[i] = __ldg(q + 8 * i); q1[i] = __ldg(q + Kp + 8 * i); q2[i] = __ldg(q + 2 * Kp + 8 * i); }
+                    }
+                    if (pass == 0) {  // consumers are done with this buffer
+                        if (buf == 0) named_bar_sync<3>(nthreads); else named_bar_sync<4>(nthreads);
+                    }
+                    double *dst = sA + buf * bufsz + (RPO * lo) * ld + cg;
+    #pragma unroll
+                    for (int i = 0; i < NBMAX; i++) {
+                        if (i < NB) {
+                            double a0 = f[0] * q0[i] + f[1] * q1[i] + f[2] * q2[i];
+                            double a1 = f[3] * q0[i] + f[4] * q1[i] + f[5] * q2[i];
+                            double a2 = f[6] * q0[i] + f[7] * q1[i] + f[8] * q2[i];
+                            if (RPO == 3) { dst[8 * i] = a0; dst[ld + 8 * i] = a1; dst[2 * ld + 8 * i] = a2; }
+                            else dst[8 * i] = a0 * row_scale;
+                            bacc[i] = fma(a0, yy[0], fma(a1, yy[1], fma(a2, yy[2], bacc[i])));
+                        }
+                    }
+                }
+                if (buf == 0) named_bar_arrive<1>(nthreads); else named_bar_arrive<2>(nthreads);
+            }
         }
         // reduce b over the 8 observation slots (fixed order: deterministic)
         named_bar_sync<5>(kProdWarps * 32);      // producers only
@@ -977,7 +1056,7 @@ template <int NBLK, int NBMAX, int NWC>
 static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M, int total, const GramFast *gf, double *d_L,
                          double *d_mu, const int *d_out_slot, int *d_status, cudaStream_t s) {
     const int Kp = m.Kp, ld = Kp + 4;
-    size_t stage = (size_t)2 * kMmaRows * ld + 8 * Kp + (std::min(o.n, kMaxStagedIds) + 1) / 2;
+    size_t stage = (size_t)2 * kMmaRows * ld + 8 * Kp + (std::min(o.n, kMaxStagedIds) + 3) / 4 * 2 + (size_t)2 * 8 * 3 * Kp + 2 * 8 * 12;
     size_t fact = (size_t)(Kp + 8) * ld + 3 * Kp;
     size_t smem = sizeof(double) * std::max(stage, fact);
     if (gf) {
