@@ -143,7 +143,7 @@ int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t direction, cons
                               int32_t n_ids, const double *target_points, int32_t n_tp, double sigma2,
                               double step_length, int32_t C, const double *alpha, double *alpha_out);
 
-/* ---- (6) evaluators (api/sampling/evaluators/*.scala, ProductEvaluators.scala) -------------- */
+/* ---- (6) evaluators (api/sampling/evaluators/<Name>.scala, ProductEvaluators.scala) -------------- */
 #define ICP_EVAL_ACCEPT_ALL 0     /* AcceptAllEvaluator.scala:22-28 */
 #define ICP_EVAL_INDEPENDENT 1    /* IndependentPointDistanceEvaluator.scala:27-67, Gaussian(p0 = mean, p1 = sd) */
 #define ICP_EVAL_HAUSDORFF 2      /* HausdorffDistanceEvaluator.scala:25-36, Exponential(p0 = rate) */
