@@ -91,6 +91,7 @@ _SIGS = {
     "icp_chain_last_run_stats": [_h, _dp, _lp],
     "icp_debug_philox": [_h, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)],
     "icp_debug_fp64_peak": [_h, _dp],
+    "icp_debug_dmma_sweep": [_h, C.c_int32, C.c_int32, C.c_int32, _dp],
     "icp_chain_profile": [_h, C.c_int32, C.c_int32, _dp, C.c_uint64, _dp, _lp],
     "icp_debug_time_closest_point": [_h, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _dp],
 }

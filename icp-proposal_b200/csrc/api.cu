@@ -645,7 +645,7 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
     const bool tsamp = p->prm.direction == ICP_TARGET_SAMPLING;
     int n = tsamp ? p->n_tp : p->n_ids;
     size_t tot = (size_t)C * std::max(n, 1);
-    w.vid.ensure(tot); w.F.ensure(9 * tot); w.y.ensure(3 * tot); w.nobs.ensure(C);
+    w.vid.ensure(tot); w.F.ensure(9 * tot); w.y.ensure(3 * tot); w.nobs.ensure(2 * (size_t)C);
     w.M.ensure((size_t)C * Kp * Kp); w.b.ensure((size_t)C * Kp); w.status.ensure(C);
     ObsArgs oa{};
     oa.m = md; oa.prm = p->prm; oa.C = C; oa.theta = d_theta; oa.X = d_X;
@@ -686,6 +686,7 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
         }
     }
     ObsDev od{n, w.vid.p, w.F.p, w.y.p, w.nobs.p};
+    od.nrows = w.nobs.p + C;
     launch_observations(oa, od, s);
     // every observation is kept (no boundary filtering possible) -> the Gram part of M is the proposal's constant
     const bool all_kept = !tsamp && !(p->prm.boundary_aware && t->has_boundary);

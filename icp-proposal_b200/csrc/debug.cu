@@ -130,3 +130,61 @@ extern "C" int32_t icp_debug_time_closest_point(icp_target t, int64_t nq, const 
         return translate_exception(_ctx);
     }
 }
+
+// DMMA issue-rate experiment (tools/dmma_sweep.py): throughput as a function of the number of resident warps and of
+// independent accumulators per warp. out: TFLOP/s.
+template <int NACC>
+__global__ void k_dmma_sweep(double *out, int iters) {
+    double c[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) c[i][0] = c[i][1] = 0.0;
+    double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9 * (threadIdx.x + 1);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < NACC; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+extern "C" int32_t icp_debug_dmma_sweep(icp_ctx ctx, int32_t warps_per_cta, int32_t ctas_per_sm, int32_t nacc, double *tflops) {
+    icp_ctx _ctx = ctx;
+    try {
+        ICP_REQUIRE(ctx && tflops, "null argument");
+        CtxLock lock(ctx);
+        cudaStream_t s = ctx->stream;
+        DevBuf<double> d;
+        d.alloc(4);
+        cudaEvent_t e0, e1;
+        ICP_CUDA(cudaEventCreate(&e0));
+        ICP_CUDA(cudaEventCreate(&e1));
+        const int iters = 8192, blocks = ctx->sm_count * ctas_per_sm, threads = warps_per_cta * 32;
+        // dynamic shared memory pins the number of resident CTAs per SM
+        size_t smem = (size_t)(200 * 1024) / ctas_per_sm;
+        double best = 0;
+        for (int rep = 0; rep < 3; rep++) {
+            ICP_CUDA(cudaEventRecord(e0, s));
+            if (nacc == 1) { ICP_CUDA(cudaFuncSetAttribute(k_dmma_sweep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_dmma_sweep<1><<<blocks, threads, smem, s>>>(d.p, iters); }
+            else if (nacc == 2) { ICP_CUDA(cudaFuncSetAttribute(k_dmma_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_dmma_sweep<2><<<blocks, threads, smem, s>>>(d.p, iters); }
+            else if (nacc == 4) { ICP_CUDA(cudaFuncSetAttribute(k_dmma_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_dmma_sweep<4><<<blocks, threads, smem, s>>>(d.p, iters); }
+            else { ICP_CUDA(cudaFuncSetAttribute(k_dmma_sweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k_dmma_sweep<8><<<blocks, threads, smem, s>>>(d.p, iters); nacc = 8; }
+            ICP_CUDA(cudaGetLastError());
+            ICP_CUDA(cudaEventRecord(e1, s));
+            ICP_CUDA(cudaStreamSynchronize(s));
+            float ms = 0;
+            ICP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            double tf = 2.0 * 256 * nacc * iters * (double)blocks * warps_per_cta / (ms * 1e-3) / 1e12;
+            if (tf > best) best = tf;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *tflops = best;
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}

@@ -181,7 +181,8 @@ struct ObsDev {  // observation list of one ICP proposal for C chains, stride n 
     int *vid;    // [C][n] reference vertex id (-1: filtered out)
     double *F;   // [C][n][9] rows n/sd_n, t1/sd_t, t2/sd_t of the whitening frame
     double *y;   // [C][n][3] F (y_i - mean_i)
-    int *nobs;   // [C]
+    int *nobs;   // [C] observations kept
+    int *nrows = nullptr;  // [C] leading slots in use (<= n; observations of one vertex may share a slot); null: n
 };
 struct ObsArgs {
     ModelDev m;

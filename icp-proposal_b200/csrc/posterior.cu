@@ -24,10 +24,144 @@ namespace icp {
 // ---------------------------------------------------------------------------------------------------
 // observations
 // ---------------------------------------------------------------------------------------------------
-// One CTA per chain: the chain's mesh is staged in shared memory (coalesced, 8 loads in flight per thread), then one
+// One CTA per chain: the chain's mesh is staged in shared memory, then one
 // thread per observation gathers the one-ring of its vertex from shared memory - the gather is 4 dependent
 // index -> index -> index -> coordinate loads per adjacent triangle, which costs ~30 cycles each from shared
 // memory instead of an L2 round trip.
+// rows of the whitening frame of vertex id: n / sd_n, t1 / sd_t, t2 / sd_t (SurfaceNoiseHelpers.scala:32-60)
+__device__ __forceinline__ void whitening_frame(const ObsArgs &a, const double *Xc, int id, double (&f)[9]) {
+    if (a.iso) {
+        double w = 1.0 / sqrt(a.iso_sigma2);
+        for (int k = 0; k < 9; k++) f[k] = 0.0;
+        f[0] = f[4] = f[8] = w;
+        return;
+    }
+    double nx, ny, nz;
+    vertex_normal_dev(a.m, Xc, id, nx, ny, nz);                 // :100,120 currentMesh.vertexNormals.atPoint(id)
+    // SurfaceNoiseHelpers.scala:39: normalize again
+    double nn = sqrt(nx * nx + ny * ny + nz * nz);
+    nx /= nn; ny /= nn; nz /= nn;
+    // :44-48 candidate = n x e_x; (inverted) fallback test; n x e_y otherwise
+    double c0 = 0.0, c1 = nz, c2 = -ny;
+    double t1x, t1y, t1z;
+    if (c0 * c0 + c1 * c1 + c2 * c2 < 0.0001) { t1x = c0; t1y = c1; t1z = c2; }
+    else { t1x = -nz; t1y = 0.0; t1z = nx; }
+    double tn = sqrt(t1x * t1x + t1y * t1y + t1z * t1z);
+    t1x /= tn; t1y /= tn; t1z /= tn;                             // 0/0 = NaN exactly where the reference yields NaN
+    double t2x = ny * t1z - nz * t1y, t2y = nz * t1x - nx * t1z, t2z = nx * t1y - ny * t1x;
+    double t2n = sqrt(t2x * t2x + t2y * t2y + t2z * t2z);
+    t2x /= t2n; t2y /= t2n; t2z /= t2n;
+    double wn = 1.0 / a.prm.noise_along_normal, wt = 1.0 / a.prm.tangential_noise;
+    f[0] = nx * wn; f[1] = ny * wn; f[2] = nz * wn;
+    f[3] = t1x * wt; f[4] = t1y * wt; f[5] = t1z * wt;
+    f[6] = t2x * wt; f[7] = t2y * wt; f[8] = t2z * wt;
+}
+
+// Target sampling, one CTA per chain: observations that share their closest model vertex v also share the frame F_v
+// (it depends on the vertex normal only), so their m_v contributions  Q_v^T F_v^T F_v Q_v  and  Q_v^T F_v^T F_v y_i
+// collapse into ONE row triple  sqrt(m_v) F_v Q_v  with right-hand side  F_v (sum_i y_i) / sqrt(m_v).  With 2000
+// target points on a 1622-vertex model ~40 % of the rows disappear before the rank update (used when n >= N / 2).  The grouping is a
+// counting sort by vertex id in shared memory; every segment is put in ascending observation order before its y_i
+// are summed, so the result does not depend on the order the atomics landed in.
+__device__ __forceinline__ void observations_grouped(const ObsArgs &a, const ObsDev &o, int c, const double *sX, int *s_int) {
+    const ModelDev &m = a.m;
+    const int N = m.N, n = o.n, tid = threadIdx.x, nt = blockDim.x;
+    int *s_cnt = s_int, *s_off = s_cnt + N, *s_slot = s_off + N, *s_cur = s_slot + N, *s_seg = s_cur + N;
+    __shared__ int s_part[2][256], s_tot[2];
+    const int *near = a.near_vid + (size_t)c * n;
+    for (int v = tid; v < N; v += nt) { s_cnt[v] = 0; s_cur[v] = 0; }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        int id = near[i];                                               // :118 findClosestPoint on the current mesh
+        if (id >= 0 && !(a.prm.boundary_aware && m.boundary[id])) atomicAdd(&s_cnt[id], 1);  // :119,124
+    }
+    __syncthreads();
+    // exclusive scans of the counts (segment offsets) and of the non-empty flags (output slots)
+    const int per = (N + nt - 1) / nt, v0 = tid * per, v1 = min(N, v0 + per);
+    int sc = 0, sf = 0;
+    for (int v = v0; v < v1; v++) { sc += s_cnt[v]; sf += s_cnt[v] > 0; }
+    s_part[0][tid] = sc; s_part[1][tid] = sf;
+    __syncthreads();
+    if (tid < 2) {
+        int run = 0;
+        for (int t = 0; t < nt; t++) { int x = s_part[tid][t]; s_part[tid][t] = run; run += x; }
+        s_tot[tid] = run;
+    }
+    __syncthreads();
+    sc = s_part[0][tid]; sf = s_part[1][tid];
+    for (int v = v0; v < v1; v++) { s_off[v] = sc; s_slot[v] = sf; sc += s_cnt[v]; sf += s_cnt[v] > 0; }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        int id = near[i];
+        if (id >= 0 && !(a.prm.boundary_aware && m.boundary[id])) s_seg[s_off[id] + atomicAdd(&s_cur[id], 1)] = i;
+    }
+    __syncthreads();
+    const int kept = s_tot[0], rows = s_tot[1];
+    if (tid == 0) { o.nobs[c] = kept; if (o.nrows) o.nrows[c] = rows; }
+    const double *th = a.theta + (size_t)c * (m.K + kTheta0);
+    double R[9];
+    pose_matrix(th, R);
+    for (int v = tid; v < N; v += nt) {
+        const int mv = s_cnt[v];
+        if (mv == 0) continue;
+        int *seg = s_seg + s_off[v];
+        for (int p = 1; p < mv; p++) {                                   // ascending observation order
+            int key = seg[p], q = p - 1;
+            while (q >= 0 && seg[q] > key) { seg[q + 1] = seg[q]; q--; }
+            seg[q + 1] = key;
+        }
+        double f[9];
+        whitening_frame(a, sX, v, f);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int p = 0; p < mv; p++) {
+            const int i = seg[p];
+            double ix, iy, iz;
+            inverse_pose(th, R, a.tp[3 * i], a.tp[3 * i + 1], a.tp[3 * i + 2], ix, iy, iz);  // :129
+            s0 += (ix - m.ref[3 * v]) - m.mean[3 * v];
+            s1 += (iy - m.ref[3 * v + 1]) - m.mean[3 * v + 1];
+            s2 += (iz - m.ref[3 * v + 2]) - m.mean[3 * v + 2];
+        }
+        const long long g = (long long)c * n + s_slot[v];
+        double *F = o.F + 9 * g, *y = o.y + 3 * g;
+        o.vid[g] = v;
+        if (mv > 1) {
+            const double w = sqrt((double)mv);
+            for (int k = 0; k < 9; k++) f[k] *= w;
+            s0 /= mv; s1 /= mv; s2 /= mv;                                // F_v sum / sqrt(m) = (sqrt(m) F_v) (sum / m)
+        }
+        for (int k = 0; k < 9; k++) F[k] = f[k];
+        y[0] = f[0] * s0 + f[1] * s1 + f[2] * s2;
+        y[1] = f[3] * s0 + f[4] * s1 + f[5] * s2;
+        y[2] = f[6] * s0 + f[7] * s1 + f[8] * s2;
+    }
+    for (int u = rows + tid; u < n; u += nt) {                           // unused slots contribute nothing
+        const long long g = (long long)c * n + u;
+        o.vid[g] = -1;
+        for (int k = 0; k < 9; k++) o.F[9 * g + k] = 0.0;
+        o.y[3 * g] = o.y[3 * g + 1] = o.y[3 * g + 2] = 0.0;
+    }
+}
+
+// stages chain c's mesh in shared memory (coalesced, 8 loads in flight per thread)
+__device__ __forceinline__ void stage_mesh(const ObsArgs &a, int c, double *sX) {
+    const int n3 = 3 * a.m.N;
+    const double *Xg = a.X + (size_t)c * n3;
+    for (int e0 = threadIdx.x; e0 < n3; e0 += 8 * blockDim.x) {
+        double tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; tmp[u] = e < n3 ? __ldg(Xg + e) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; if (e < n3) sX[e] = tmp[u]; }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_observations_grouped(ObsArgs a, ObsDev o) {
+    extern __shared__ double sX[];
+    stage_mesh(a, blockIdx.x, sX);
+    observations_grouped(a, o, blockIdx.x, sX, reinterpret_cast<int *>(sX + 3 * a.m.N));
+}
+
 template <bool STAGED>
 __global__ void __launch_bounds__(256) k_observations(ObsArgs a, ObsDev o) {
     extern __shared__ double sX[];
@@ -38,20 +172,14 @@ __global__ void __launch_bounds__(256) k_observations(ObsArgs a, ObsDev o) {
     const double *Xc;
     if (STAGED) {
         c = blockIdx.x;
-        const double *Xg = a.X + (size_t)c * m.N * 3;
-        for (int e0 = threadIdx.x; e0 < 3 * m.N; e0 += 8 * blockDim.x) {
-            double tmp[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; tmp[u] = e < 3 * m.N ? __ldg(Xg + e) : 0.0; }
-#pragma unroll
-            for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; if (e < 3 * m.N) sX[e] = tmp[u]; }
-        }
-        __syncthreads();
+        stage_mesh(a, c, sX);
         Xc = sX;
+        if (threadIdx.x == 0 && o.nrows) o.nrows[c] = o.n;
     } else {
         long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
         if (gt >= (long long)a.C * o.n) return;
         c = (int)(gt / o.n);
+        if (gt % o.n == 0 && o.nrows) o.nrows[c] = o.n;
         Xc = a.X + (size_t)c * m.N * 3;
     }
     const double *th = a.theta + (size_t)c * (m.K + kTheta0);
@@ -82,31 +210,7 @@ __global__ void __launch_bounds__(256) k_observations(ObsArgs a, ObsDev o) {
         atomicAdd(&o.nobs[c], 1);
         o.vid[g] = id;
         double f[9];
-        if (a.iso) {
-            double w = 1.0 / sqrt(a.iso_sigma2);
-            for (int k = 0; k < 9; k++) f[k] = 0.0;
-            f[0] = f[4] = f[8] = w;
-        } else {
-            double nx, ny, nz;
-            vertex_normal_dev(m, Xc, id, nx, ny, nz);                   // :100,120 currentMesh.vertexNormals.atPoint(id)
-            // SurfaceNoiseHelpers.scala:39: normalize again
-            double nn = sqrt(nx * nx + ny * ny + nz * nz);
-            nx /= nn; ny /= nn; nz /= nn;
-            // :44-48 candidate = n x e_x; (inverted) fallback test; n x e_y otherwise
-            double c0 = 0.0, c1 = nz, c2 = -ny;
-            double t1x, t1y, t1z;
-            if (c0 * c0 + c1 * c1 + c2 * c2 < 0.0001) { t1x = c0; t1y = c1; t1z = c2; }
-            else { t1x = -nz; t1y = 0.0; t1z = nx; }
-            double tn = sqrt(t1x * t1x + t1y * t1y + t1z * t1z);
-            t1x /= tn; t1y /= tn; t1z /= tn;                             // 0/0 = NaN exactly where the reference yields NaN
-            double t2x = ny * t1z - nz * t1y, t2y = nz * t1x - nx * t1z, t2z = nx * t1y - ny * t1x;
-            double t2n = sqrt(t2x * t2x + t2y * t2y + t2z * t2z);
-            t2x /= t2n; t2y /= t2n; t2z /= t2n;
-            double wn = 1.0 / a.prm.noise_along_normal, wt = 1.0 / a.prm.tangential_noise;
-            f[0] = nx * wn; f[1] = ny * wn; f[2] = nz * wn;
-            f[3] = t1x * wt; f[4] = t1y * wt; f[5] = t1z * wt;
-            f[6] = t2x * wt; f[7] = t2y * wt; f[8] = t2z * wt;
-        }
+        whitening_frame(a, Xc, id, f);
         double R[9];
         pose_matrix(th, R);
         double ix, iy, iz;
@@ -123,10 +227,24 @@ __global__ void __launch_bounds__(256) k_observations(ObsArgs a, ObsDev o) {
 void launch_observations(const ObsArgs &a, const ObsDev &o, cudaStream_t s) {
     ProfScope _ps(ST_OBSERVATIONS, s);
     long long total = (long long)a.C * o.n;
-    ICP_CUDA(cudaMemsetAsync(o.nobs, 0, sizeof(int) * a.C, s));
+    if (o.nrows == o.nobs + a.C) {   // the usual layout: one clear for both counters
+        ICP_CUDA(cudaMemsetAsync(o.nobs, 0, sizeof(int) * 2 * a.C, s));
+    } else {
+        ICP_CUDA(cudaMemsetAsync(o.nobs, 0, sizeof(int) * a.C, s));
+        if (o.nrows) ICP_CUDA(cudaMemsetAsync(o.nrows, 0, sizeof(int) * a.C, s));
+    }
     if (total <= 0) return;
+    static const bool no_group = getenv("ICPCUDA_NO_GROUPING") && getenv("ICPCUDA_NO_GROUPING")[0] == '1';
+    // grouping needs the per-chain row count to be honoured downstream (o.nrows); it pays once vertices are shared
+    // often (n target points on N vertices leave ~N (1 - exp(-n / N)) distinct ones): below n = N / 2 fewer than
+    // a fifth of the rows would go, less than the sort costs
+    const int grouped = a.prm.direction == ICP_TARGET_SAMPLING && o.nrows && !no_group && 2 * (long long)o.n >= a.m.N;
     size_t smem = sizeof(double) * 3 * (size_t)a.m.N;
-    if (smem <= 160 * 1024 && o.n >= 32) {
+    size_t smem_g = smem + sizeof(int) * (4 * (size_t)a.m.N + o.n);
+    if (grouped && smem_g <= 160 * 1024) {
+        ICP_CUDA(cudaFuncSetAttribute(k_observations_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        k_observations_grouped<<<a.C, 256, smem_g, s>>>(a, o);
+    } else if (smem <= 160 * 1024 && o.n >= 32) {
         ICP_CUDA(cudaFuncSetAttribute(k_observations<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_observations<true><<<a.C, 256, smem, s>>>(a, o);
     } else {
@@ -299,7 +417,8 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_build_mma
     const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int nthreads = (NWC + kProdWarps) * 32, nwc = NWC;
     constexpr int kObsChunk = kMmaRows / RPO;   // observations per staged chunk (8 or 24)
-    const int nchunks = (o.n + kObsChunk - 1) / kObsChunk;
+    const int nrows = o.nrows ? o.nrows[c] : o.n;   // slots in use (uniform over the CTA)
+    const int nchunks = (nrows + kObsChunk - 1) / kObsChunk;
     if (warp < nwc) {
         // ------------------------------- consumers: DMMA ------------------------------------------------
         const int per = (nblk_total + nwc - 1) / nwc;
@@ -405,7 +524,7 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_build_mma
         int *svid = reinterpret_cast<int *>(sm + 2 * bufsz + 8 * Kp);
         const bool vid_staged = o.n <= kMaxStagedIds;
         if (vid_staged) {
-            for (int e = pt; e < o.n; e += kProdWarps * 32) svid[e] = __ldg(&vid[e]);
+            for (int e = pt; e < nrows; e += kProdWarps * 32) svid[e] = __ldg(&vid[e]);
             named_bar_sync<5>(kProdWarps * 32);
         }
         for (int ch = 0; ch < nchunks; ch++) {
@@ -416,7 +535,7 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_build_mma
                 const int gi = ch * kObsChunk + lo;
                 int v = -1;
                 double f[9], yy[3];
-                if (gi < o.n) v = vid_staged ? svid[gi] : __ldg(&vid[gi]);
+                if (gi < nrows) v = vid_staged ? svid[gi] : __ldg(&vid[gi]);
                 if (v >= 0) {
 #pragma unroll
                     for (int k = 0; k < 9; k++) f[k] = __ldg(F + (size_t)gi * 9 + k);
@@ -772,6 +891,55 @@ __global__ void __launch_bounds__(kCh2Threads) k_cholesky_solve_mma(int K, int K
     (void)K;
 }
 
+// ---- consumer roles for Kp = 104 (13 block rows): rectangular / triangular block sets per warp -----------------------
+// Block indices are split into groups A = 0..4, B = 5..8, C = 9..12. The lower triangle then is
+//   tri(A) 15 + tri(B) 10 + tri(C) 10 + rect(B x A) 20 + rect(C x A) 20 + rect(C x B) 16 = 91 blocks,
+// dealt as  warp 0: B x A (20) | warp 1: C x A (20) | warp 2: C x B + tri(B) (26) | warp 3: tri(A) + tri(C) (25).
+// Within a rectangle every row fragment is reused by all its columns and vice versa, and in a triangle the row and
+// column fragments coincide: 35 shared-memory fragment loads per k4-step for the 91 DMMAs (the run-length assignment of
+// the generic path needs ~100), which takes the shared-memory pipe off the critical path of the tensor pipe.
+template <int RB, int CB>
+__device__ __forceinline__ void mma_rect_chunk(double (&acc)[RB * CB][2], const double *base, int ld, int r0, int c0) {
+#pragma unroll
+    for (int k = 0; k < kMmaRows / 4; k++) {
+        double fr[RB], fc[CB];
+#pragma unroll
+        for (int i = 0; i < RB; i++) fr[i] = base[k * 4 * ld + 8 * (r0 + i)];
+#pragma unroll
+        for (int j = 0; j < CB; j++) fc[j] = base[k * 4 * ld + 8 * (c0 + j)];
+#pragma unroll
+        for (int i = 0; i < RB; i++)
+#pragma unroll
+            for (int j = 0; j < CB; j++) dmma_8x8x4(acc[i * CB + j][0], acc[i * CB + j][1], fr[i], fc[j]);
+    }
+}
+template <int TB>
+__device__ __forceinline__ void mma_tri_chunk(double (&acc)[TB * (TB + 1) / 2][2], const double *base, int ld, int r0) {
+#pragma unroll
+    for (int k = 0; k < kMmaRows / 4; k++) {
+        double f[TB];
+#pragma unroll
+        for (int i = 0; i < TB; i++) f[i] = base[k * 4 * ld + 8 * (r0 + i)];
+#pragma unroll
+        for (int i = 0; i < TB; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) dmma_8x8x4(acc[i * (i + 1) / 2 + j][0], acc[i * (i + 1) / 2 + j][1], f[i], f[j]);
+    }
+}
+// accumulator block (bi, bj) -> shared-memory matrix of the factorisation (+ I, + Gs / sd_t^2 on the fast path)
+template <int RPO>
+__device__ __forceinline__ void store_block(double *sA, int ld, int Kp, int bi, int bj, int lane, const double (&a)[2],
+                                            const double *__restrict__ Gs, double gs_scale) {
+    int i = 8 * bi + (lane >> 2), j = 8 * bj + 2 * (lane & 3);
+    double v0 = a[0] + (i == j ? 1.0 : 0.0), v1 = a[1] + (i == j + 1 ? 1.0 : 0.0);
+    if (RPO == 1) {
+        double2 g = __ldg(reinterpret_cast<const double2 *>(Gs + (size_t)i * Kp + j));
+        v0 = fma(g.x, gs_scale, v0);
+        v1 = fma(g.y, gs_scale, v1);
+    }
+    *reinterpret_cast<double2 *>(sA + (size_t)i * ld + j) = make_double2(v0, v1);
+}
+
 // Fused variant: posterior build (as k_posterior_build_mma) + Cholesky + solve in one kernel. The accumulator
 // fragments go straight into the shared-memory matrix of the factorisation (M never visits global memory unless the
 // caller asks for it), and with two CTAs per SM the latency-bound factorisation of one chain overlaps the DMMA
@@ -796,9 +964,63 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
     const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int nthreads = (NWC + kProdWarps) * 32, nwc = NWC;
     constexpr int kObsChunk = kMmaRows / RPO;   // observations per staged chunk (8 or 24)
-    const int nchunks = (o.n + kObsChunk - 1) / kObsChunk;
+    const int nrows = o.nrows ? o.nrows[c] : o.n;   // slots in use (uniform over the CTA)
+    const int nchunks = (nrows + kObsChunk - 1) / kObsChunk;
     if (warp < nwc) {
         // ------------------------------- consumers: DMMA ------------------------------------------------
+        const int frag = (lane & 3) * ld + (lane >> 2);
+        if (NBMAX == 13 && NWC == 4 && NB == 13) {
+            // rectangular / triangular roles (see mma_rect_chunk)
+            named_bar_arrive<3>(nthreads);  // both buffers start empty
+            named_bar_arrive<4>(nthreads);
+#define ICP_CONSUME(...)                                                                               \
+            for (int ch = 0; ch < nchunks; ch++) {                                                     \
+                const int buf = ch & 1;                                                                \
+                if (buf == 0) named_bar_sync<1>(nthreads); else named_bar_sync<2>(nthreads);           \
+                const double *base = sA + buf * bufsz + frag;                                          \
+                __VA_ARGS__                                                                            \
+                if (buf == 0) named_bar_arrive<3>(nthreads); else named_bar_arrive<4>(nthreads);       \
+            }                                                                                          \
+            named_bar_sync<6>(nthreads); /* staging buffers are free: the matrix takes their place */
+            if (warp == 0) {          // rows B (5..8) x cols A (0..4)
+                double acc[20][2] = {};
+                ICP_CONSUME(mma_rect_chunk<4, 5>(acc, base, ld, 5, 0);)
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 5; j++) store_block<RPO>(sA, ld, Kp, 5 + i, j, lane, acc[i * 5 + j], Gs, gs_scale);
+            } else if (warp == 1) {   // rows C (9..12) x cols A
+                double acc[20][2] = {};
+                ICP_CONSUME(mma_rect_chunk<4, 5>(acc, base, ld, 9, 0);)
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 5; j++) store_block<RPO>(sA, ld, Kp, 9 + i, j, lane, acc[i * 5 + j], Gs, gs_scale);
+            } else if (warp == 2) {   // rows C x cols B, and the triangle of B
+                double acc[16][2] = {}, tri[10][2] = {};
+                ICP_CONSUME(mma_rect_chunk<4, 4>(acc, base, ld, 9, 5); mma_tri_chunk<4>(tri, base, ld, 5);)
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) store_block<RPO>(sA, ld, Kp, 9 + i, 5 + j, lane, acc[i * 4 + j], Gs, gs_scale);
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j <= i; j++) store_block<RPO>(sA, ld, Kp, 5 + i, 5 + j, lane, tri[i * (i + 1) / 2 + j], Gs, gs_scale);
+            } else {                  // the triangles of A and of C
+                double ta[15][2] = {}, tc[10][2] = {};
+                ICP_CONSUME(mma_tri_chunk<5>(ta, base, ld, 0); mma_tri_chunk<4>(tc, base, ld, 9);)
+#pragma unroll
+                for (int i = 0; i < 5; i++)
+#pragma unroll
+                    for (int j = 0; j <= i; j++) store_block<RPO>(sA, ld, Kp, i, j, lane, ta[i * (i + 1) / 2 + j], Gs, gs_scale);
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j <= i; j++) store_block<RPO>(sA, ld, Kp, 9 + i, 9 + j, lane, tc[i * (i + 1) / 2 + j], Gs, gs_scale);
+            }
+#undef ICP_CONSUME
+        } else {
         const int per = (nblk_total + nwc - 1) / nwc;
         const int b0 = warp * per;
         const int nmine = max(0, min(nblk_total, b0 + per) - b0);
@@ -807,7 +1029,6 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
         double acc[NBLK][2];
 #pragma unroll
         for (int s = 0; s < NBLK; s++) acc[s][0] = acc[s][1] = 0.0;
-        const int frag = (lane & 3) * ld + (lane >> 2);
         named_bar_arrive<3>(nthreads);  // both buffers start empty
         named_bar_arrive<4>(nthreads);
         for (int ch = 0; ch < nchunks; ch++) {
@@ -883,6 +1104,7 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
                 if (++bj > bi) { bj = 0; ++bi; }
             }
         }
+        }
     } else {
         // ------------------------------- producers: gather + whiten ----------------------------------------
         const int pt = tid - nwc * 32;          // 0 .. 63
@@ -898,61 +1120,61 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
         int *svid = reinterpret_cast<int *>(sm + 2 * bufsz + 8 * Kp);
         const bool vid_staged = o.n <= kMaxStagedIds;
         if (vid_staged) {
-            for (int e = pt; e < o.n; e += kProdWarps * 32) svid[e] = __ldg(&vid[e]);
+            for (int e = pt; e < nrows; e += kProdWarps * 32) svid[e] = __ldg(&vid[e]);
             named_bar_sync<5>(kProdWarps * 32);
         }
         if (vid_staged) {
-            // cp.async pipeline: the basis rows (and F, y) of pass p + 1 stream into shared memory while pass p is
-            // whitened - the producers no longer wait one L2 round trip per pass with nothing in flight
+            // cp.async pipeline, private per thread: every producer thread copies exactly the 3 x NB basis entries it
+            // will whiten itself (8-byte cp.async into its own shared-memory slot), one pass ahead, so the only waits
+            // are its own cp.async group and the FULL / EMPTY hand-off with the consumers - no producer-side barriers.
             constexpr int ppc = kObsChunk / 8;            // passes (of 8 observations) per staged chunk
+            constexpr int kSlot = 3 * NBMAX;              // doubles per thread and buffer
             const int npass = nchunks * ppc;
-            double *raw = sm + 2 * bufsz + 8 * Kp + ((kMaxStagedIds < o.n ? kMaxStagedIds : o.n) + 3) / 4 * 2;   // 16-byte aligned
-            double *meta = raw + (size_t)2 * 8 * 3 * Kp;  // [2][8][12]: F (9) and y (3) of each observation of a pass
+            double *raw = sm + 2 * bufsz + 8 * Kp + ((kMaxStagedIds < o.n ? kMaxStagedIds : o.n) + 3) / 4 * 2;
+            double *mine = raw + (size_t)pt * kSlot;      // + rb * 64 * kSlot
+            double fn[9], yn[3];
+            int vn = -1;
             auto issue = [&](int pp) {
                 const int rb = pp & 1, gi = pp * 8 + ob;
-                const int v = gi < o.n ? svid[gi] : -1;
-                const double *src = m.Q + (size_t)3 * (v >= 0 ? v : 0) * Kp;
-                double *dr = raw + (size_t)((rb * 8 + ob) * 3) * Kp;
+                vn = gi < nrows ? svid[gi] : -1;
+                const double *src = m.Q + (size_t)3 * (vn >= 0 ? vn : 0) * Kp + cg;
+                double *dr = mine + (size_t)rb * (kProdWarps * 32) * kSlot;
 #pragma unroll
                 for (int d = 0; d < 3; d++)
 #pragma unroll
-                    for (int i = 0; i < (4 * NBMAX + 7) / 8; i++) {
-                        int j = 2 * (cg + 8 * i);
-                        if (j < Kp) cp_async_16(dr + d * Kp + j, src + d * Kp + j);
-                    }
-                if (gi < o.n) {
-                    double *dm = meta + (rb * 8 + ob) * 12;
-                    int k = cg;
-                    cp_async_8(dm + k, F + (size_t)gi * 9 + k);
-                    k = cg + 8;
-                    if (k < 9) cp_async_8(dm + k, F + (size_t)gi * 9 + k);
-                    else if (k < 12) cp_async_8(dm + k, y + (size_t)gi * 3 + (k - 9));
-                }
+                    for (int i = 0; i < NBMAX; i++)
+                        if (i < NB) cp_async_8(dr + d * NBMAX + i, src + d * Kp + 8 * i);
                 cp_async_commit();
+                if (vn >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 9; k++) fn[k] = __ldg(F + (size_t)gi * 9 + k);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) yn[k] = __ldg(y + (size_t)gi * 3 + k);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 9; k++) fn[k] = 0.0;
+                    yn[0] = yn[1] = yn[2] = 0.0;
+                }
             };
             issue(0);
 #pragma unroll 1
             for (int pp = 0; pp < npass; pp++) {
                 const int ch = pp / ppc, sub = pp - ch * ppc, buf = ch & 1, rb = pp & 1;
-                if (pp + 1 < npass) { issue(pp + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-                named_bar_sync<5>(kProdWarps * 32);       // every producer thread's copies of this pass have landed
-                const int gi = pp * 8 + ob;
-                const int v = gi < o.n ? svid[gi] : -1;
-                const double *mm = meta + (rb * 8 + ob) * 12;
                 double f[9], yy[3];
 #pragma unroll
-                for (int k = 0; k < 9; k++) f[k] = v >= 0 ? mm[k] : 0.0;
+                for (int k = 0; k < 9; k++) f[k] = fn[k];
 #pragma unroll
-                for (int k = 0; k < 3; k++) yy[k] = v >= 0 ? mm[9 + k] : 0.0;
+                for (int k = 0; k < 3; k++) yy[k] = yn[k];
+                if (pp + 1 < npass) { issue(pp + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
                 if (sub == 0) {  // consumers are done with this buffer
                     if (buf == 0) named_bar_sync<3>(nthreads); else named_bar_sync<4>(nthreads);
                 }
-                const double *rr = raw + (size_t)((rb * 8 + ob) * 3) * Kp + cg;
+                const double *rr = mine + (size_t)rb * (kProdWarps * 32) * kSlot;
                 double *dst = sA + buf * bufsz + (RPO * (sub * 8 + ob)) * ld + cg;
 #pragma unroll
                 for (int i = 0; i < NBMAX; i++) {
                     if (i < NB) {
-                        double q0 = rr[8 * i], q1 = rr[Kp + 8 * i], q2 = rr[2 * Kp + 8 * i];
+                        double q0 = rr[i], q1 = rr[NBMAX + i], q2 = rr[2 * NBMAX + i];
                         double a0 = f[0] * q0 + f[1] * q1 + f[2] * q2;
                         double a1 = f[3] * q0 + f[4] * q1 + f[5] * q2;
                         double a2 = f[6] * q0 + f[7] * q1 + f[8] * q2;
@@ -964,7 +1186,6 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
                 if (sub == ppc - 1) {
                     if (buf == 0) named_bar_arrive<1>(nthreads); else named_bar_arrive<2>(nthreads);
                 }
-                named_bar_sync<5>(kProdWarps * 32);       // the raw buffer may be refilled by the pass after next
             }
         } else {
         for (int ch = 0; ch < nchunks; ch++) {
@@ -975,7 +1196,7 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
                     const int gi = ch * kObsChunk + lo;
                     int v = -1;
                     double f[9], yy[3];
-                    if (gi < o.n) v = vid_staged ? svid[gi] : __ldg(&vid[gi]);
+                    if (gi < nrows) v = vid_staged ? svid[gi] : __ldg(&vid[gi]);
                     if (v >= 0) {
     #pragma unroll
                         for (int k = 0; k < 9; k++) f[k] = __ldg(F + (size_t)gi * 9 + k);
@@ -1049,7 +1270,6 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
         }
     }
     const int oc = out_slot ? out_slot[c] : c;
-    if (gs_scale == -12345.0) return;   // timing experiment only (tools/): skip the factorisation
     chol_factor_solve_store<nthreads>(sA, Kp, &bad, L + (size_t)oc * Kp * Kp, mu + (size_t)oc * Kp, status ? status + c : nullptr);
 }
 
@@ -1057,7 +1277,7 @@ template <int NBLK, int NBMAX, int NWC>
 static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M, int total, const GramFast *gf, double *d_L,
                          double *d_mu, const int *d_out_slot, int *d_status, cudaStream_t s) {
     const int Kp = m.Kp, ld = Kp + 4;
-    size_t stage = (size_t)2 * kMmaRows * ld + 8 * Kp + (std::min(o.n, kMaxStagedIds) + 3) / 4 * 2 + (size_t)2 * 8 * 3 * Kp + 2 * 8 * 12;
+    size_t stage = (size_t)2 * kMmaRows * ld + 8 * Kp + (std::min(o.n, kMaxStagedIds) + 3) / 4 * 2 + (size_t)2 * kProdWarps * 32 * 3 * NBMAX;
     size_t fact = (size_t)(Kp + 8) * ld + 3 * Kp;
     size_t smem = sizeof(double) * std::max(stage, fact);
     if (gf) {
@@ -1065,8 +1285,7 @@ static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M,
         k_posterior_fused<NBLK, NBMAX, NWC, 1><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, total, gf->Gs, gf->gs_scale, gf->row_scale, d_L, d_mu, d_out_slot, d_status);
     } else {
         ICP_CUDA(cudaFuncSetAttribute(k_posterior_fused<NBLK, NBMAX, NWC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        static const bool skip = getenv("ICPCUDA_DEBUG_SKIP_CHOL") != nullptr;
-        k_posterior_fused<NBLK, NBMAX, NWC, 3><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, total, nullptr, skip ? -12345.0 : 0.0, 1.0, d_L, d_mu, d_out_slot, d_status);
+        k_posterior_fused<NBLK, NBMAX, NWC, 3><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, total, nullptr, 0.0, 1.0, d_L, d_mu, d_out_slot, d_status);
     }
 }
 

@@ -241,6 +241,9 @@ int32_t icp_chain_last_run_stats(icp_chain c, double *device_ms, int64_t *kernel
 int32_t icp_debug_philox(icp_ctx ctx, uint64_t seed, uint64_t chain, uint32_t step, uint32_t block, uint32_t out[4]);
 /* measured FP64 peaks of this device (TFLOP/s): out[0] = DFMA (CUDA cores), out[1] = DMMA m8n8k4 */
 int32_t icp_debug_fp64_peak(icp_ctx ctx, double out[2]);
+/* DMMA issue-rate experiment: TFLOP/s of mma.sync.m8n8k4.f64 with warps_per_cta x ctas_per_sm resident warps per SM and
+ * nacc (1, 2, 4, 8) independent accumulators per warp */
+int32_t icp_debug_dmma_sweep(icp_ctx ctx, int32_t warps_per_cta, int32_t ctas_per_sm, int32_t nacc, double *tflops);
 /* eager (graph-less) run of n_steps of the chain with every kernel class bracketed by CUDA events on
  * the library stream: stage_ms[ICP_N_STAGES] summed device milliseconds, stage_launches[ICP_N_STAGES]
  * number of launches. Stage names through icp_stage_name. theta0 is host memory, Philox RNG. */

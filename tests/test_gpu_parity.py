@@ -222,6 +222,33 @@ def test_posterior_boundary_aware(ctx, open_twin):
     model.close(); tgt.close()
 
 
+@pytest.mark.parametrize("fixture", ["twin31", "open_twin"])
+def test_posterior_target_sampling_shared_vertices(ctx, request, fixture):
+    """n >= N / 2 target points: observations that share their closest model vertex are merged into one row triple
+    (sqrt(m) F_v Q_v, F_v sum(y) / sqrt(m)) before the rank update; M, mu and the kept count must not change."""
+    m = request.getfixturevalue(fixture)
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    rng = np.random.default_rng(21)
+    N = len(m["ref"])
+    th = random_theta(m, rng, 3, pose=True)
+    tp = np.concatenate([m["target"], m["target"][::2] + rng.normal(0, 0.05, m["target"][::2].shape)])[: max(2 * N, 64)]
+    assert 2 * len(tp) >= N
+    for aware in (True, False):
+        gp = core.IcpProposal(model, tgt, 0.3, 4.0, 2.0, _lib.TARGET_SAMPLING, aware, np.arange(4), tp)
+        op = orc.IcpProposal(om, ot, 0.3, 4.0, 2.0, _lib.TARGET_SAMPLING, aware, np.arange(4), tp)
+        mu, M, n = gp.posterior(th)
+        for c in range(len(th)):
+            po = op.posterior(th[c])
+            assert n[c] == po["n"]
+            np.testing.assert_allclose(M[c], po["M"], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(mu[c], po["mu"], rtol=1e-7, atol=1e-9)
+        # the merge is exercised: more observations than model vertices
+        assert n.max() > N or len(tp) > N
+        gp.close()
+    model.close(); tgt.close()
+
+
 def test_evaluators(ctx, twin31, open_twin):
     m = twin31
     model, tgt = _dev(ctx, m)
