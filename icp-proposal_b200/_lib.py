@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicpcuda.so")
+# ICPCUDA_LIB_TAG selects an experiment build of the same CUDA library (tools/fused_timing.py); default: the product build
+LIB_PATH = os.path.join(_HERE, "libicpcuda" + ("_" + os.environ["ICPCUDA_LIB_TAG"] if os.environ.get("ICPCUDA_LIB_TAG") else "") + ".so")
 
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_EMPTY_SET, ERR_NOT_POSITIVE_DEFINITE = -1, -2, -3, -4, -5

@@ -8,11 +8,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libicpcuda.so")
+# experiment builds (extra -D flags) go to their own library / object directory: ICPCUDA_LIB_TAG=timing -> libicpcuda_timing.so
+_TAG = os.environ.get("ICPCUDA_LIB_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libicpcuda" + ("_" + _TAG if _TAG else "") + ".so")
 SOURCES = ["api.cu", "bvh.cu", "model.cu", "posterior.cu", "evaluate.cu", "chain.cu", "debug.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr"]
+              "--expt-relaxed-constexpr"] + os.environ.get("ICPCUDA_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

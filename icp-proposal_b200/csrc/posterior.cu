@@ -383,6 +383,10 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_16_ca(void *smem_dst, const void *gsrc) {   // allocates in L1
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
@@ -390,6 +394,8 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kRawStages = 2;         // producer ring: passes of raw basis rows in flight per thread
 
 template <int ID>
 __device__ __forceinline__ void named_bar_sync(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
@@ -718,6 +724,16 @@ __global__ void __launch_bounds__(kChThreads) k_cholesky_solve(int K, int Kp, co
 // Back substitution L^T x = y runs 8 unknowns at a time the same way.
 constexpr int kCh2Threads = 128;
 
+#ifdef ICP_FUSED_TIMING
+// experiment build only (ICPCUDA_LIB_TAG=timing ICPCUDA_NVCC_EXTRA=-DICP_FUSED_TIMING, tools/fused_timing.py):
+// per-CTA clock64() phase times
+constexpr int kFtStride = 12;
+__device__ long long g_ft[kFtStride * 8192];
+#define ICP_FT(...) __VA_ARGS__
+#else
+#define ICP_FT(...)
+#endif
+
 // Factorises the matrix staged in shared memory (A: [Kp + 8][Kp + 4], lower triangle of M in rows 0..Kp-1, b in row Kp,
 // rows Kp+1..Kp+7 zero), solves M mu = b and stores L (lower, zero upper) and mu. Every one of the NT threads of the CTA
 // must call it (it synchronises the CTA); *bad (shared) must have been cleared before the preceding barrier.
@@ -730,6 +746,7 @@ __device__ void chol_factor_solve_store(double *A, int Kp, int *bad, double *__r
     double *xo = xs + Kp;                   // [Kp] solution
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fc = lane & 3;
+    ICP_FT(const long long ftc0 = clock64();)
     for (int bj = 0; bj < NB; bj++) {
         if (bj > 0) {
             for (int bi = bj + warp; bi <= NB; bi += NT / 32) {
@@ -805,6 +822,7 @@ __device__ void chol_factor_solve_store(double *A, int Kp, int *bad, double *__r
         __syncthreads();
     }
     // back substitution L^T x = y (y = row Kp of A)
+    ICP_FT(const long long ftc1 = clock64();)
     for (int k = tid; k < Kp; k += NT) xs[k] = A[Kp * ld + k];
     __syncthreads();
     for (int bj = NB - 1; bj >= 0; bj--) {
@@ -830,13 +848,16 @@ __device__ void chol_factor_solve_store(double *A, int Kp, int *bad, double *__r
         }
         __syncthreads();
     }
+    ICP_FT(if (tid == 0 && blockIdx.x < 8192) {
+        g_ft[kFtStride * blockIdx.x + 8] = ftc1 - ftc0; g_ft[kFtStride * blockIdx.x + 9] = clock64() - ftc1;
+    })
     bool isbad = *bad != 0;
     for (int e = tid; e < Kp * Kp; e += NT) {
         int i = e / Kp, j = e - i * Kp;
         double v = j <= i ? A[i * ld + j] : 0.0;
-        Lc[e] = isbad ? NAN : v;
+        __stcs(Lc + e, isbad ? NAN : v);   // streaming: 86 KB per chain must not evict the basis from L2
     }
-    for (int j = tid; j < Kp; j += NT) muc[j] = isbad ? NAN : xo[j];
+    for (int j = tid; j < Kp; j += NT) __stcs(muc + j, isbad ? NAN : xo[j]);
     if (tid == 0 && status) *status = isbad ? 1 : 0;
 }
 
@@ -949,13 +970,13 @@ __device__ __forceinline__ void store_block(double *sA, int ld, int Kp, int bi, 
 // kappa = 1/sd_n^2 - 1/sd_t^2, so M = I + Gs / sd_t^2 + sum_i (sqrt(kappa) Q_i^T n_i)(...)^T where
 // Gs = sum_i Q_i^T Q_i is a constant of the proposal: one row per observation, a third of the DMMA work.
 template <int NBLK, int NBMAX, int NWC, int RPO>
-__global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(ModelDev m, ObsDev o, double *__restrict__ M_out,
+__global__ void __launch_bounds__((NWC + kProdWarps) * 32, 2) k_posterior_fused(ModelDev m, ObsDev o, double *__restrict__ M_out,
                                                                              int nblk_total, const double *__restrict__ Gs,
                                                                              double gs_scale, double row_scale,
                                                                              double *__restrict__ L, double *__restrict__ mu,
                                                                              const int *__restrict__ out_slot,
                                                                              int *__restrict__ status) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int Kp = m.Kp, ld = Kp + 4, NB = Kp >> 3;
     const int bufsz = kMmaRows * ld;
     double *sA = sm;                    // [2][24][ld]; later reused as the matrix of the factorisation
@@ -966,6 +987,7 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
     constexpr int kObsChunk = kMmaRows / RPO;   // observations per staged chunk (8 or 24)
     const int nrows = o.nrows ? o.nrows[c] : o.n;   // slots in use (uniform over the CTA)
     const int nchunks = (nrows + kObsChunk - 1) / kObsChunk;
+    ICP_FT(long long ft0 = clock64(); long long ftw = 0; long long ftw2 = 0;)
     if (warp < nwc) {
         // ------------------------------- consumers: DMMA ------------------------------------------------
         const int frag = (lane & 3) * ld + (lane >> 2);
@@ -976,11 +998,14 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
 #define ICP_CONSUME(...)                                                                               \
             for (int ch = 0; ch < nchunks; ch++) {                                                     \
                 const int buf = ch & 1;                                                                \
+                ICP_FT(long long fta = clock64();)                                                     \
                 if (buf == 0) named_bar_sync<1>(nthreads); else named_bar_sync<2>(nthreads);           \
+                ICP_FT(ftw += clock64() - fta;)                                                        \
                 const double *base = sA + buf * bufsz + frag;                                          \
                 __VA_ARGS__                                                                            \
                 if (buf == 0) named_bar_arrive<3>(nthreads); else named_bar_arrive<4>(nthreads);       \
             }                                                                                          \
+            ICP_FT(if (tid == 0 && c < 8192) { g_ft[kFtStride * c + 1] = ftw; g_ft[kFtStride * c + 2] = clock64() - ft0; }) \
             named_bar_sync<6>(nthreads); /* staging buffers are free: the matrix takes their place */
             if (warp == 0) {          // rows B (5..8) x cols A (0..4)
                 double acc[20][2] = {};
@@ -1112,9 +1137,10 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
         const int *vid = o.vid + (size_t)c * o.n;
         const double *F = o.F + (size_t)c * o.n * 9;
         const double *y = o.y + (size_t)c * o.n * 3;
-        double bacc[NBMAX];
+        constexpr int kNJ = (NBMAX + 1) / 2;     // column pairs per producer thread on the 16-byte path
+        double bacc[2 * kNJ];
 #pragma unroll
-        for (int i = 0; i < NBMAX; i++) bacc[i] = 0.0;
+        for (int i = 0; i < 2 * kNJ; i++) bacc[i] = 0.0;
         // the vertex ids gate the addresses of every basis-row load: stage them in shared memory once so that a
         // pass pays one L2 round trip (ids -> rows would be two dependent ones)
         int *svid = reinterpret_cast<int *>(sm + 2 * bufsz + 8 * Kp);
@@ -1124,63 +1150,96 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
             named_bar_sync<5>(kProdWarps * 32);
         }
         if (vid_staged) {
-            // cp.async pipeline, private per thread: every producer thread copies exactly the 3 x NB basis entries it
-            // will whiten itself (8-byte cp.async into its own shared-memory slot), one pass ahead, so the only waits
-            // are its own cp.async group and the FULL / EMPTY hand-off with the consumers - no producer-side barriers.
+            // cp.async pipeline, private per thread: every producer thread copies exactly the basis entries it will
+            // whiten itself - column pairs (2 cg + 16 j, + 1) of its observation's 3 rows, as 16-byte cp.async.ca into
+            // its own shared-memory slot - one pass ahead, so the only waits are its own cp.async group and the
+            // FULL / EMPTY hand-off with the consumers: no producer-side barriers. 8 lanes cover one 128-byte line; the
+            // copies allocate in L1 because the two CTAs of an SM read the same rows (.cg was 2x slower here).
             constexpr int ppc = kObsChunk / 8;            // passes (of 8 observations) per staged chunk
-            constexpr int kSlot = 3 * NBMAX;              // doubles per thread and buffer
+            constexpr int kSlot = 3 * kNJ * 2;            // doubles per thread and stage
             const int npass = nchunks * ppc;
             double *raw = sm + 2 * bufsz + 8 * Kp + ((kMaxStagedIds < o.n ? kMaxStagedIds : o.n) + 3) / 4 * 2;
-            double *mine = raw + (size_t)pt * kSlot;      // + rb * 64 * kSlot
-            double fn[9], yn[3];
-            int vn = -1;
-            auto issue = [&](int pp) {
-                const int rb = pp & 1, gi = pp * 8 + ob;
-                vn = gi < nrows ? svid[gi] : -1;
-                const double *src = m.Q + (size_t)3 * (vn >= 0 ? vn : 0) * Kp + cg;
-                double *dr = mine + (size_t)rb * (kProdWarps * 32) * kSlot;
+            double *mine = raw + (size_t)pt * kSlot;      // + (pass % kRawStages) * 64 * kSlot
+            // per-observation scalars (F, F y) travel one pass ahead in registers; nothing may consume them before the
+            // next pass (they come from DRAM: a use here would stall the producer for a full DRAM round trip per pass)
+            double fn[12];
+            auto issue = [&](int pp) {                    // basis rows of pass pp -> this thread's slot (one group)
+                if (pp < npass) {
+                    const int gi = pp * 8 + ob;
+                    const int v = gi < nrows ? svid[gi] : -1;
+                    const double *src = m.Q + (size_t)3 * (v >= 0 ? v : 0) * Kp + 2 * cg;
+                    double *dr = mine + (size_t)(pp % kRawStages) * (kProdWarps * 32) * kSlot;
 #pragma unroll
-                for (int d = 0; d < 3; d++)
+                    for (int d = 0; d < 3; d++)
 #pragma unroll
-                    for (int i = 0; i < NBMAX; i++)
-                        if (i < NB) cp_async_8(dr + d * NBMAX + i, src + d * Kp + 8 * i);
+                        for (int j = 0; j < kNJ; j++)
+                            if (2 * cg + 16 * j < Kp) cp_async_16_ca(dr + (d * kNJ + j) * 2, src + d * Kp + 16 * j);
+                }
                 cp_async_commit();
+            };
+            auto frame = [&](int pp) {
+                const int gi = pp * 8 + ob;
+                const int vn = gi < nrows ? svid[gi] : -1;
                 if (vn >= 0) {
 #pragma unroll
                     for (int k = 0; k < 9; k++) fn[k] = __ldg(F + (size_t)gi * 9 + k);
 #pragma unroll
-                    for (int k = 0; k < 3; k++) yn[k] = __ldg(y + (size_t)gi * 3 + k);
+                    for (int k = 0; k < 3; k++) fn[9 + k] = __ldg(y + (size_t)gi * 3 + k);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 9; k++) fn[k] = 0.0;
-                    yn[0] = yn[1] = yn[2] = 0.0;
+                    for (int k = 0; k < 12; k++) fn[k] = 0.0;
                 }
             };
-            issue(0);
+#pragma unroll
+            for (int st = 0; st < kRawStages - 1; st++) issue(st);
+            frame(0);
 #pragma unroll 1
             for (int pp = 0; pp < npass; pp++) {
-                const int ch = pp / ppc, sub = pp - ch * ppc, buf = ch & 1, rb = pp & 1;
-                double f[9], yy[3];
+                const int ch = pp / ppc, sub = pp - ch * ppc, buf = ch & 1, rb = pp % kRawStages;
+                constexpr int kNF = RPO == 1 ? 6 : 12;
+                double f[kNF];
+                if (RPO == 1) {
+                    // only the normal row is staged, and b += Q_i^T (F_i^T F_i y_i) needs no tangential rows either:
+                    // g = row_scale * n / sd_n and w = F^T (F y)
 #pragma unroll
-                for (int k = 0; k < 9; k++) f[k] = fn[k];
+                    for (int k = 0; k < 3; k++) {
+                        f[k] = fn[k] * row_scale;
+                        f[3 + k] = fn[k] * fn[9] + fn[3 + k] * fn[10] + fn[6 + k] * fn[11];
+                    }
+                } else {
 #pragma unroll
-                for (int k = 0; k < 3; k++) yy[k] = yn[k];
-                if (pp + 1 < npass) { issue(pp + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+                    for (int k = 0; k < kNF; k++) f[k] = fn[k];
+                }
+                ICP_FT(long long fta = clock64();)
+                if (pp + 1 < npass) frame(pp + 1);
+                issue(pp + kRawStages - 1);               // refills the slot read in pass pp - 1
+                cp_async_wait<kRawStages - 1>();          // all but the newest kRawStages - 1 groups: pass pp has landed
+                ICP_FT(long long ftb = clock64(); ftw2 += ftb - fta;)
                 if (sub == 0) {  // consumers are done with this buffer
                     if (buf == 0) named_bar_sync<3>(nthreads); else named_bar_sync<4>(nthreads);
                 }
-                const double *rr = mine + (size_t)rb * (kProdWarps * 32) * kSlot;
-                double *dst = sA + buf * bufsz + (RPO * (sub * 8 + ob)) * ld + cg;
+                ICP_FT(ftw += clock64() - ftb;)
+                const double2 *rr = reinterpret_cast<const double2 *>(mine + (size_t)rb * (kProdWarps * 32) * kSlot);
+                double *dst = sA + buf * bufsz + (RPO * (sub * 8 + ob)) * ld + 2 * cg;
 #pragma unroll
-                for (int i = 0; i < NBMAX; i++) {
-                    if (i < NB) {
-                        double q0 = rr[i], q1 = rr[NBMAX + i], q2 = rr[2 * NBMAX + i];
-                        double a0 = f[0] * q0 + f[1] * q1 + f[2] * q2;
-                        double a1 = f[3] * q0 + f[4] * q1 + f[5] * q2;
-                        double a2 = f[6] * q0 + f[7] * q1 + f[8] * q2;
-                        if (RPO == 3) { dst[8 * i] = a0; dst[ld + 8 * i] = a1; dst[2 * ld + 8 * i] = a2; }
-                        else dst[8 * i] = a0 * row_scale;
-                        bacc[i] = fma(a0, yy[0], fma(a1, yy[1], fma(a2, yy[2], bacc[i])));
+                for (int j = 0; j < kNJ; j++) {
+                    if (2 * cg + 16 * j < Kp) {
+                        const double2 q0 = rr[j], q1 = rr[kNJ + j], q2 = rr[2 * kNJ + j];
+                        if (RPO == 1) {
+                            *reinterpret_cast<double2 *>(dst + 16 * j) =
+                                make_double2(f[0] * q0.x + f[1] * q1.x + f[2] * q2.x, f[0] * q0.y + f[1] * q1.y + f[2] * q2.y);
+                            bacc[2 * j] = fma(q0.x, f[3], fma(q1.x, f[4], fma(q2.x, f[5], bacc[2 * j])));
+                            bacc[2 * j + 1] = fma(q0.y, f[3], fma(q1.y, f[4], fma(q2.y, f[5], bacc[2 * j + 1])));
+                        } else {
+                            const double a0x = f[0] * q0.x + f[1] * q1.x + f[2] * q2.x, a0y = f[0] * q0.y + f[1] * q1.y + f[2] * q2.y;
+                            const double a1x = f[3] * q0.x + f[4] * q1.x + f[5] * q2.x, a1y = f[3] * q0.y + f[4] * q1.y + f[5] * q2.y;
+                            const double a2x = f[6] * q0.x + f[7] * q1.x + f[8] * q2.x, a2y = f[6] * q0.y + f[7] * q1.y + f[8] * q2.y;
+                            *reinterpret_cast<double2 *>(dst + 16 * j) = make_double2(a0x, a0y);
+                            *reinterpret_cast<double2 *>(dst + ld + 16 * j) = make_double2(a1x, a1y);
+                            *reinterpret_cast<double2 *>(dst + 2 * ld + 16 * j) = make_double2(a2x, a2y);
+                            bacc[2 * j] = fma(a0x, f[9], fma(a1x, f[10], fma(a2x, f[11], bacc[2 * j])));
+                            bacc[2 * j + 1] = fma(a0y, f[9], fma(a1y, f[10], fma(a2y, f[11], bacc[2 * j + 1])));
+                        }
                     }
                 }
                 if (sub == ppc - 1) {
@@ -1232,13 +1291,20 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
                 if (buf == 0) named_bar_arrive<1>(nthreads); else named_bar_arrive<2>(nthreads);
             }
         }
+        ICP_FT(if (pt == 0 && c < 8192) { g_ft[kFtStride * c + 3] = ftw; g_ft[kFtStride * c + 4] = ftw2; g_ft[kFtStride * c + 5] = clock64() - ft0; })
         // reduce b over the 8 observation slots (fixed order: deterministic)
         named_bar_sync<5>(kProdWarps * 32);      // producers only
         // the last two buffers may still be read by consumers: use the tail of the shared allocation
         double *sb = sm + 2 * bufsz;             // [8][Kp]
+        if (vid_staged) {
 #pragma unroll
-        for (int i = 0; i < NBMAX; i++)
-            if (i < NB) sb[ob * Kp + cg + 8 * i] = bacc[i];
+            for (int j = 0; j < kNJ; j++)
+                if (2 * cg + 16 * j < Kp) { sb[ob * Kp + 2 * cg + 16 * j] = bacc[2 * j]; sb[ob * Kp + 2 * cg + 16 * j + 1] = bacc[2 * j + 1]; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NBMAX; i++)
+                if (i < NB) sb[ob * Kp + cg + 8 * i] = bacc[i];
+        }
         named_bar_sync<5>(kProdWarps * 32);
         double bval[(8 * NBMAX + kProdWarps * 32 - 1) / (kProdWarps * 32)];
 #pragma unroll
@@ -1270,14 +1336,26 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_fused(Mod
         }
     }
     const int oc = out_slot ? out_slot[c] : c;
+    ICP_FT(long long ftc = clock64();)
     chol_factor_solve_store<nthreads>(sA, Kp, &bad, L + (size_t)oc * Kp * Kp, mu + (size_t)oc * Kp, status ? status + c : nullptr);
+    ICP_FT(if (tid == 0 && c < 8192) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_ft[kFtStride * c] = ft0; g_ft[kFtStride * c + 6] = ftc - ft0; g_ft[kFtStride * c + 7] = ((clock64() - ft0) << 8) | smid;
+    })
 }
+
+#ifdef ICP_FUSED_TIMING
+extern "C" int icp_debug_fused_timing(long long *out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_ft, sizeof(long long) * (size_t)n);
+}
+#endif
 
 template <int NBLK, int NBMAX, int NWC>
 static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M, int total, const GramFast *gf, double *d_L,
                          double *d_mu, const int *d_out_slot, int *d_status, cudaStream_t s) {
     const int Kp = m.Kp, ld = Kp + 4;
-    size_t stage = (size_t)2 * kMmaRows * ld + 8 * Kp + (std::min(o.n, kMaxStagedIds) + 3) / 4 * 2 + (size_t)2 * kProdWarps * 32 * 3 * NBMAX;
+    size_t stage = (size_t)2 * kMmaRows * ld + 8 * Kp + (std::min(o.n, kMaxStagedIds) + 3) / 4 * 2 + (size_t)kRawStages * kProdWarps * 32 * 3 * ((NBMAX + 1) / 2) * 2;
     size_t fact = (size_t)(Kp + 8) * ld + 3 * Kp;
     size_t smem = sizeof(double) * std::max(stage, fact);
     if (gf) {
