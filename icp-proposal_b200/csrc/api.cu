@@ -694,7 +694,8 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
                 std::sqrt(std::max(0.0, 1.0 - (p->prm.noise_along_normal * p->prm.noise_along_normal) /
                                                   (p->prm.tangential_noise * p->prm.tangential_noise)))};
     const GramFast *gfp = (p->gram_fast && all_kept) ? &gf : nullptr;
-    if (!launch_posterior_fused(md, C, od, gfp, w.want_M ? w.M.p : nullptr, d_L, d_mu, d_out_slot, w.status.p, s)) {
+    w.Mp.ensure((size_t)C * (Kp / 8) * (Kp / 8 + 1) / 2 * 64);
+    if (!launch_posterior_fused(md, C, od, gfp, w.want_M ? w.M.p : nullptr, d_L, d_mu, d_out_slot, w.status.p, w.Mp.p, w.b.p, s)) {
         launch_posterior_build(md, C, od, w.M.p, w.b.p, s, gfp);
         launch_cholesky_solve(C, m->K, Kp, w.M.p, w.b.p, d_L, d_mu, d_out_slot, w.status.p, s);
     }

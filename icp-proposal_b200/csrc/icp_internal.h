@@ -214,7 +214,7 @@ void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d
                             const GramFast *gf = nullptr);
 void launch_gram_rows(const ModelDev &m, int n_ids, const int *d_ids, double *d_G, cudaStream_t s);
 bool launch_posterior_fused(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, double *d_M_or_null, double *d_L,
-                            double *d_mu, const int *d_out_slot, int *d_status, cudaStream_t s);
+                            double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s);
 // in: M (C x Kp x Kp), b (C x Kp). out: L (lower Cholesky factor, C x Kp x Kp), mu = M^-1 b, status (0 ok)
 // out_slot (nullable): chain c writes L / mu at index out_slot[c] instead of c
 void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
@@ -318,6 +318,7 @@ struct PosteriorWork {
     DevBuf<double> F, y;
     DevBuf<int> nobs;
     DevBuf<double> M, b;     // [C][Kp*Kp], [C][Kp]
+    DevBuf<double> Mp;       // [C][NB (NB + 1) / 2][64] block-packed lower triangle of M (rank update -> factorisation)
     bool want_M = false;     // the primitive API returns M; the chain runner never needs it in global memory
     DevBuf<int> status;
 };

@@ -735,7 +735,7 @@ __device__ long long g_ft[kFtStride * 8192];
 #endif
 
 // Factorises the matrix staged in shared memory (A: [Kp + 8][Kp + 4], lower triangle of M in rows 0..Kp-1, b in row Kp,
-// rows Kp+1..Kp+7 zero), solves M mu = b and stores L (lower, zero upper) and mu. Every one of the NT threads of the CTA
+// rows Kp+1..Kp+7 zero), solves M mu = b and stores L (lower triangle only) and mu. Every one of the NT threads of the CTA
 // must call it (it synchronises the CTA); *bad (shared) must have been cleared before the preceding barrier.
 template <int NT>
 __device__ void chol_factor_solve_store(double *A, int Kp, int *bad, double *__restrict__ Lc, double *__restrict__ muc,
@@ -854,8 +854,7 @@ __device__ void chol_factor_solve_store(double *A, int Kp, int *bad, double *__r
     bool isbad = *bad != 0;
     for (int e = tid; e < Kp * Kp; e += NT) {
         int i = e / Kp, j = e - i * Kp;
-        double v = j <= i ? A[i * ld + j] : 0.0;
-        __stcs(Lc + e, isbad ? NAN : v);   // streaming: 86 KB per chain must not evict the basis from L2
+        if (j <= i) __stcs(Lc + e, isbad ? NAN : A[i * ld + j]);   // only the lower triangle is ever read; streaming stores
     }
     for (int j = tid; j < Kp; j += NT) __stcs(muc + j, isbad ? NAN : xo[j]);
     if (tid == 0 && status) *status = isbad ? 1 : 0;
@@ -947,6 +946,215 @@ __device__ __forceinline__ void mma_tri_chunk(double (&acc)[TB * (TB + 1) / 2][2
             for (int j = 0; j <= i; j++) dmma_8x8x4(acc[i * (i + 1) / 2 + j][0], acc[i * (i + 1) / 2 + j][1], f[i], f[j]);
     }
 }
+// ---- block-packed Cholesky: four chains per SM ---------------------------------------------------------------------
+// The factorisation is a chain of Kp dependent pivots (rsqrt -> scale -> update): latency, not throughput. What hides
+// latency is residency, so the matrix is kept block-packed in shared memory - only the NB (NB + 1) / 2 lower-triangle
+// 8 x 8 blocks, 64 doubles each, 46.6 KB at Kp = 104 instead of 97 KB for the padded square - and four 128-thread CTAs
+// share an SM. Inside a block, column bit 2 is flipped on rows with bit 1 set, which makes the DMMA fragment loads
+// (rows lane / 4, columns lane % 4 (+ 4)) conflict free without padding. Same left-looking algorithm as
+// chol_factor_solve_store; the right-hand side is a vector and takes part in the DMMA update as a block whose rows
+// 1..7 are zero.
+__device__ __forceinline__ int pk_swz(int r) { return (r & 2) << 1; }
+__device__ __forceinline__ int pk_blk(int bi, int bj) { return ((bi * (bi + 1) >> 1) + bj) * 64; }
+__device__ __forceinline__ int pk_at(int i, int j) {   // element (i, j) of a stored block
+    const int r = i & 7;
+    return pk_blk(i >> 3, j >> 3) + r * 8 + ((j & 7) ^ pk_swz(r));
+}
+
+constexpr int kCh3Threads = 128;
+__global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, const double *__restrict__ Mp,
+                                                                    const double *__restrict__ bvec, double *__restrict__ M_out,
+                                                                    double *__restrict__ L, double *__restrict__ mu,
+                                                                    const int *__restrict__ out_slot, int *__restrict__ status) {
+    extern __shared__ __align__(16) double sp[];
+    constexpr int NT = kCh3Threads;
+    const int NB = Kp >> 3, ntri = NB * (NB + 1) / 2;
+    double *A = sp;                  // [ntri][64]
+    double *yv = A + ntri * 64;      // [Kp] b, then y = L^-1 b
+    double *dinv = yv + Kp;          // [Kp] reciprocals of the diagonal of L
+    double *xs = dinv + Kp;          // [Kp] running right-hand side of the back substitution
+    double *xo = xs + Kp;            // [Kp] solution
+    __shared__ int bad;
+    const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fc = lane & 3, sw = pk_swz(fr);
+    {
+        ICP_FT(const long long ftl = clock64();)
+        const double2 *src = reinterpret_cast<const double2 *>(Mp + (size_t)c * ntri * 64);
+        // 16-byte chunk e: block e / 32, row (e / 4) % 8, columns 2 (e % 4), + 1; 8 independent loads in flight per thread
+        for (int e0 = tid; e0 < ntri * 32; e0 += 8 * NT) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int e = e0 + u * NT; if (e < ntri * 32) v[u] = __ldcs(src + e); }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int e = e0 + u * NT, r = (e >> 2) & 7;
+                if (e < ntri * 32) *reinterpret_cast<double2 *>(A + (e >> 5) * 64 + r * 8 + ((2 * (e & 3)) ^ pk_swz(r))) = v[u];
+            }
+        }
+        for (int k = tid; k < Kp; k += NT) yv[k] = __ldcs(bvec + (size_t)c * Kp + k);
+        if (tid == 0) bad = 0;
+        ICP_FT(if (tid == 0 && c < 8192) g_ft[kFtStride * c + 8] = clock64() - ftl;)
+    }
+    __syncthreads();
+    ICP_FT(const long long ftf = clock64();)
+    if (M_out) {   // only the primitive API (icp_posterior) asks for M
+        double *Mc = M_out + (size_t)c * Kp * Kp;
+        for (int e = tid; e < Kp * Kp; e += NT) {
+            const int i = e / Kp, j = e - i * Kp;
+            Mc[e] = j <= i ? A[pk_at(i, j)] : A[pk_at(j, i)];
+        }
+        __syncthreads();
+    }
+    for (int bj = 0; bj < NB; bj++) {
+        if (bj > 0) {
+            const double *pb = A + pk_blk(bj, 0) + fr * 8;
+            const int o0 = fc ^ sw, o1 = o0 ^ 4;
+            for (int bi = bj + warp; bi <= NB; bi += NT / 32) {
+                double e0 = 0.0, e1 = 0.0;   // two accumulators halve the dependent DMMA chain
+                if (bi < NB) {
+                    double *pc = A + pk_blk(bi, bj) + fr * 8 + ((2 * fc) ^ sw);
+                    double2 cc = *reinterpret_cast<double2 *>(pc);
+                    const double *pa = A + pk_blk(bi, 0) + fr * 8;
+#pragma unroll 4
+                    for (int p = 0; p < bj; p++) {
+                        dmma_8x8x4(cc.x, cc.y, -pa[p * 64 + o0], pb[p * 64 + o0]);
+                        dmma_8x8x4(e0, e1, -pa[p * 64 + o1], pb[p * 64 + o1]);
+                    }
+                    cc.x += e0; cc.y += e1;
+                    *reinterpret_cast<double2 *>(pc) = cc;
+                } else {   // right-hand side: row 0 of the operand block is y, rows 1..7 are zero
+                    double2 cc = make_double2(0.0, 0.0);
+                    if (fr == 0) cc = *reinterpret_cast<double2 *>(yv + 8 * bj + 2 * fc);
+#pragma unroll 4
+                    for (int p = 0; p < bj; p++) {
+                        const double a0 = fr == 0 ? -yv[8 * p + fc] : 0.0, a1 = fr == 0 ? -yv[8 * p + fc + 4] : 0.0;
+                        dmma_8x8x4(cc.x, cc.y, a0, pb[p * 64 + o0]);
+                        dmma_8x8x4(e0, e1, a1, pb[p * 64 + o1]);
+                    }
+                    if (fr == 0) *reinterpret_cast<double2 *>(yv + 8 * bj + 2 * fc) = make_double2(cc.x + e0, cc.y + e1);
+                }
+            }
+            __syncthreads();
+        }
+        // diagonal block: warp 0 factors it (every lane redundantly, so the rsqrt -> scale chain has no hand-offs) and
+        // publishes L_jj and the reciprocal pivots through shared memory. With four chains per SM the other warps'
+        // issue slots are worth more to the other chains than a redundant copy of this chain would be.
+        double *D = A + pk_blk(bj, bj);
+        if (warp == 0) {
+            double l[8][8], inv[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int k = 0; k <= i; k++) l[i][k] = D[i * 8 + (k ^ pk_swz(i))];
+            __syncwarp();
+            bool mybad = false;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double s = l[j][j];
+                if (!(s > 0.0)) mybad = true;
+                // 1/sqrt(s) by rsqrt + one Newton step (full double accuracy), sqrt(s) = s * inv
+                double r = rsqrt(s);
+                r = fma(r * 0.5, fma(-s * r, r, 1.0), r);
+                inv[j] = r;
+                double d = s * r;
+                d = fma(fma(-d, d, s), 0.5 * r, d);
+                l[j][j] = d;
+#pragma unroll
+                for (int i = j + 1; i < 8; i++) l[i][j] *= inv[j];
+#pragma unroll
+                for (int i = j + 1; i < 8; i++)
+#pragma unroll
+                    for (int k = j + 1; k <= i; k++) l[i][k] = fma(-l[i][j], l[k][j], l[i][k]);
+            }
+            if (mybad && lane == 0) bad = 1;
+            if (lane < 8) {
+                dinv[8 * bj + lane] = inv[lane];
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (i == lane) {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) D[i * 8 + (k ^ pk_swz(i))] = k <= i ? l[i][k] : 0.0;
+                    }
+            }
+        }
+        __syncthreads();
+        if (8 * bj + 8 + tid <= Kp) {   // panel rows (one per thread); r == Kp is the right-hand side
+            double l[8][8], inv[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                inv[j] = dinv[8 * bj + j];
+#pragma unroll
+                for (int k = 0; k < j; k++) l[j][k] = D[j * 8 + (k ^ pk_swz(j))];
+            }
+            for (int r = 8 * bj + 8 + tid; r <= Kp; r += NT) {
+                double x[8];
+                double *row = r < Kp ? A + pk_blk(r >> 3, bj) + (r & 7) * 8 : yv + 8 * bj;
+                const int rs = r < Kp ? pk_swz(r & 7) : 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) x[j] = row[j ^ rs];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    double t = x[j];
+#pragma unroll
+                    for (int k = 0; k < j; k++) t = fma(-x[k], l[j][k], t);
+                    x[j] = t * inv[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) row[j ^ rs] = x[j];
+            }
+        }
+        __syncthreads();
+    }
+    // back substitution L^T x = y
+    ICP_FT(const long long ftb = clock64(); if (tid == 0 && c < 8192) g_ft[kFtStride * c + 9] = ftb - ftf;)
+    for (int k = tid; k < Kp; k += NT) xs[k] = yv[k];
+    __syncthreads();
+    for (int bj = NB - 1; bj >= 0; bj--) {
+        const double *D = A + pk_blk(bj, bj);
+        double x[8];
+#pragma unroll
+        for (int i = 7; i >= 0; i--) {
+            double t = xs[8 * bj + i];
+#pragma unroll
+            for (int k = i + 1; k < 8; k++) t = fma(-D[k * 8 + (i ^ pk_swz(k))], x[k], t);
+            x[i] = t * dinv[8 * bj + i];
+        }
+        if (tid < 8) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i == tid) xo[8 * bj + i] = x[i];
+        }
+        for (int k = tid; k < 8 * bj; k += NT) {
+            const double *blk = A + pk_blk(bj, k >> 3);   // elements (8 bj + p, k), p = 0..7
+            double t = xs[k];
+#pragma unroll
+            for (int p = 0; p < 8; p++) t = fma(-blk[p * 8 + ((k & 7) ^ pk_swz(p))], x[p], t);
+            xs[k] = t;
+        }
+        __syncthreads();
+    }
+    ICP_FT(const long long fts = clock64(); if (tid == 0 && c < 8192) g_ft[kFtStride * c + 10] = fts - ftb;)
+    const bool isbad = bad != 0;
+    const int oc = out_slot ? out_slot[c] : c;
+    double *Lc = L + (size_t)oc * Kp * Kp;
+    // Only the lower triangle of L is ever read (back substitutions and L^T products), so only it is written: a warp
+    // writes row i as i / 2 + 1 column pairs (the pair that straddles the diagonal carries the stored zero). Streaming
+    // stores: 43 KB per chain must not evict the basis from L2.
+    for (int i = warp; i < Kp; i += NT / 32) {
+        const double *rowp = A + pk_blk(i >> 3, 0) + (i & 7) * 8;
+        const int rs = pk_swz(i & 7);
+        for (int jp = lane; jp <= (i >> 1); jp += 32) {
+            const int j = 2 * jp;
+            double2 v = *reinterpret_cast<const double2 *>(rowp + (j >> 3) * 64 + ((j & 7) ^ rs));
+            if (isbad) v = make_double2(NAN, NAN);
+            __stcs(reinterpret_cast<double2 *>(Lc + (size_t)i * Kp + j), v);
+        }
+    }
+    for (int j = tid; j < Kp; j += NT) __stcs(mu + (size_t)oc * Kp + j, isbad ? NAN : xo[j]);
+    if (tid == 0 && status) status[c] = isbad ? 1 : 0;
+    ICP_FT(if (tid == 0 && c < 8192) g_ft[kFtStride * c + 11] = clock64() - fts;)
+}
+
 // accumulator block (bi, bj) -> shared-memory matrix of the factorisation (+ I, + Gs / sd_t^2 on the fast path)
 template <int RPO>
 __device__ __forceinline__ void store_block(double *sA, int ld, int Kp, int bi, int bj, int lane, const double (&a)[2],
@@ -958,7 +1166,11 @@ __device__ __forceinline__ void store_block(double *sA, int ld, int Kp, int bi, 
         v0 = fma(g.x, gs_scale, v0);
         v1 = fma(g.y, gs_scale, v1);
     }
-    *reinterpret_cast<double2 *>(sA + (size_t)i * ld + j) = make_double2(v0, v1);
+    if (ld > 0) *reinterpret_cast<double2 *>(sA + (size_t)i * ld + j) = make_double2(v0, v1);
+    else        // ld == 0: sA is the chain's block-packed matrix in global memory (see k_cholesky_packed); a warp
+                // writes one contiguous 512-byte block
+        *reinterpret_cast<double2 *>(sA + (size_t)(bi * (bi + 1) / 2 + bj) * 64 + 4 * (lane >> 2) * 2 + 2 * (lane & 3)) =
+            make_double2(v0, v1);
 }
 
 // Fused variant: posterior build (as k_posterior_build_mma) + Cholesky + solve in one kernel. The accumulator
@@ -969,7 +1181,9 @@ __device__ __forceinline__ void store_block(double *sA, int ld, int Kp, int bi, 
 // model sampling with every observation kept and sd_n <= sd_t): Sigma_i^-1 = I / sd_t^2 + kappa n n^T with
 // kappa = 1/sd_n^2 - 1/sd_t^2, so M = I + Gs / sd_t^2 + sum_i (sqrt(kappa) Q_i^T n_i)(...)^T where
 // Gs = sum_i Q_i^T Q_i is a constant of the proposal: one row per observation, a third of the DMMA work.
-template <int NBLK, int NBMAX, int NWC, int RPO>
+// CHOL = false: rank update only - the lower-triangle blocks of M go to global memory block-packed (M_out; 64 doubles
+// per 8 x 8 block, row-major over the block triangle) and b to mu; k_cholesky_packed factorises them at twice the occupancy.
+template <int NBLK, int NBMAX, int NWC, int RPO, bool CHOL>
 __global__ void __launch_bounds__((NWC + kProdWarps) * 32, 2) k_posterior_fused(ModelDev m, ObsDev o, double *__restrict__ M_out,
                                                                              int nblk_total, const double *__restrict__ Gs,
                                                                              double gs_scale, double row_scale,
@@ -987,6 +1201,8 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32, 2) k_posterior_fused(
     constexpr int kObsChunk = kMmaRows / RPO;   // observations per staged chunk (8 or 24)
     const int nrows = o.nrows ? o.nrows[c] : o.n;   // slots in use (uniform over the CTA)
     const int nchunks = (nrows + kObsChunk - 1) / kObsChunk;
+    double *Mdst = CHOL ? sA : M_out + (size_t)c * nblk_total * 64;   // where the accumulator blocks go
+    const int ldst = CHOL ? ld : 0;
     ICP_FT(long long ft0 = clock64(); long long ftw = 0; long long ftw2 = 0;)
     if (warp < nwc) {
         // ------------------------------- consumers: DMMA ------------------------------------------------
@@ -1006,43 +1222,43 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32, 2) k_posterior_fused(
                 if (buf == 0) named_bar_arrive<3>(nthreads); else named_bar_arrive<4>(nthreads);       \
             }                                                                                          \
             ICP_FT(if (tid == 0 && c < 8192) { g_ft[kFtStride * c + 1] = ftw; g_ft[kFtStride * c + 2] = clock64() - ft0; }) \
-            named_bar_sync<6>(nthreads); /* staging buffers are free: the matrix takes their place */
+            if (CHOL) named_bar_sync<6>(nthreads); /* staging buffers are free: the matrix takes their place */
             if (warp == 0) {          // rows B (5..8) x cols A (0..4)
                 double acc[20][2] = {};
                 ICP_CONSUME(mma_rect_chunk<4, 5>(acc, base, ld, 5, 0);)
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int j = 0; j < 5; j++) store_block<RPO>(sA, ld, Kp, 5 + i, j, lane, acc[i * 5 + j], Gs, gs_scale);
+                    for (int j = 0; j < 5; j++) store_block<RPO>(Mdst, ldst, Kp, 5 + i, j, lane, acc[i * 5 + j], Gs, gs_scale);
             } else if (warp == 1) {   // rows C (9..12) x cols A
                 double acc[20][2] = {};
                 ICP_CONSUME(mma_rect_chunk<4, 5>(acc, base, ld, 9, 0);)
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int j = 0; j < 5; j++) store_block<RPO>(sA, ld, Kp, 9 + i, j, lane, acc[i * 5 + j], Gs, gs_scale);
+                    for (int j = 0; j < 5; j++) store_block<RPO>(Mdst, ldst, Kp, 9 + i, j, lane, acc[i * 5 + j], Gs, gs_scale);
             } else if (warp == 2) {   // rows C x cols B, and the triangle of B
                 double acc[16][2] = {}, tri[10][2] = {};
                 ICP_CONSUME(mma_rect_chunk<4, 4>(acc, base, ld, 9, 5); mma_tri_chunk<4>(tri, base, ld, 5);)
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) store_block<RPO>(sA, ld, Kp, 9 + i, 5 + j, lane, acc[i * 4 + j], Gs, gs_scale);
+                    for (int j = 0; j < 4; j++) store_block<RPO>(Mdst, ldst, Kp, 9 + i, 5 + j, lane, acc[i * 4 + j], Gs, gs_scale);
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int j = 0; j <= i; j++) store_block<RPO>(sA, ld, Kp, 5 + i, 5 + j, lane, tri[i * (i + 1) / 2 + j], Gs, gs_scale);
+                    for (int j = 0; j <= i; j++) store_block<RPO>(Mdst, ldst, Kp, 5 + i, 5 + j, lane, tri[i * (i + 1) / 2 + j], Gs, gs_scale);
             } else {                  // the triangles of A and of C
                 double ta[15][2] = {}, tc[10][2] = {};
                 ICP_CONSUME(mma_tri_chunk<5>(ta, base, ld, 0); mma_tri_chunk<4>(tc, base, ld, 9);)
 #pragma unroll
                 for (int i = 0; i < 5; i++)
 #pragma unroll
-                    for (int j = 0; j <= i; j++) store_block<RPO>(sA, ld, Kp, i, j, lane, ta[i * (i + 1) / 2 + j], Gs, gs_scale);
+                    for (int j = 0; j <= i; j++) store_block<RPO>(Mdst, ldst, Kp, i, j, lane, ta[i * (i + 1) / 2 + j], Gs, gs_scale);
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int j = 0; j <= i; j++) store_block<RPO>(sA, ld, Kp, 9 + i, 9 + j, lane, tc[i * (i + 1) / 2 + j], Gs, gs_scale);
+                    for (int j = 0; j <= i; j++) store_block<RPO>(Mdst, ldst, Kp, 9 + i, 9 + j, lane, tc[i * (i + 1) / 2 + j], Gs, gs_scale);
             }
 #undef ICP_CONSUME
         } else {
@@ -1113,19 +1329,12 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32, 2) k_posterior_fused(
             }
             if (buf == 0) named_bar_arrive<3>(nthreads); else named_bar_arrive<4>(nthreads);
         }
-        named_bar_sync<6>(nthreads);   // staging buffers and the b scratch are free: the matrix takes their place
+        if (CHOL) named_bar_sync<6>(nthreads);   // staging buffers and the b scratch are free: the matrix takes their place
         int bi = bi0, bj = bj0;
 #pragma unroll
         for (int s = 0; s < NBLK; s++) {
             if (s < nmine) {
-                int i = 8 * bi + (lane >> 2), j = 8 * bj + 2 * (lane & 3);
-                double v0 = acc[s][0] + (i == j ? 1.0 : 0.0), v1 = acc[s][1] + (i == j + 1 ? 1.0 : 0.0);
-                if (RPO == 1) {
-                    double2 g = __ldg(reinterpret_cast<const double2 *>(Gs + (size_t)i * Kp + j));
-                    v0 = fma(g.x, gs_scale, v0);
-                    v1 = fma(g.y, gs_scale, v1);
-                }
-                *reinterpret_cast<double2 *>(sA + (size_t)i * ld + j) = make_double2(v0, v1);
+                store_block<RPO>(Mdst, ldst, Kp, bi, bj, lane, acc[s], Gs, gs_scale);
                 if (++bj > bi) { bj = 0; ++bi; }
             }
         }
@@ -1317,6 +1526,19 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32, 2) k_posterior_fused(
             }
             bval[u] = t;
         }
+        if (!CHOL) {
+#pragma unroll
+            for (int u = 0; u < (8 * NBMAX + kProdWarps * 32 - 1) / (kProdWarps * 32); u++) {
+                int j = pt + u * kProdWarps * 32;
+                if (j < Kp) mu[(size_t)c * Kp + j] = bval[u];
+            }
+            ICP_FT(if (pt == 0 && c < 8192) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                g_ft[kFtStride * c] = ft0; g_ft[kFtStride * c + 6] = clock64() - ft0; g_ft[kFtStride * c + 7] = ((clock64() - ft0) << 8) | smid;
+            })
+            return;
+        }
         named_bar_sync<6>(nthreads);
         // right-hand side = block row NB of the factorisation (row Kp real, 7 zero rows)
         for (int e = pt; e < 8 * ld; e += kProdWarps * 32) sA[(size_t)Kp * ld + e] = 0.0;
@@ -1327,6 +1549,7 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32, 2) k_posterior_fused(
             if (j < Kp) sA[(size_t)Kp * ld + j] = bval[u];
         }
     }
+    if (!CHOL) return;
     __syncthreads();
     if (M_out) {   // only the primitive API (icp_posterior) asks for M
         double *Mc = M_out + (size_t)c * Kp * Kp;
@@ -1353,32 +1576,57 @@ extern "C" int icp_debug_fused_timing(long long *out, int n) {
 
 template <int NBLK, int NBMAX, int NWC>
 static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M, int total, const GramFast *gf, double *d_L,
-                         double *d_mu, const int *d_out_slot, int *d_status, cudaStream_t s) {
+                         double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s) {
     const int Kp = m.Kp, ld = Kp + 4;
     size_t stage = (size_t)2 * kMmaRows * ld + 8 * Kp + (std::min(o.n, kMaxStagedIds) + 3) / 4 * 2 + (size_t)kRawStages * kProdWarps * 32 * 3 * ((NBMAX + 1) / 2) * 2;
     size_t fact = (size_t)(Kp + 8) * ld + 3 * Kp;
+    const unsigned nthr = (NWC + kProdWarps) * 32;
+    if (d_Mp) {
+        // rank update (block-packed M and b to global memory), then the high-occupancy factorisation
+        size_t smem = sizeof(double) * stage;
+        {
+            ProfScope _ps(ST_POSTERIOR_BUILD, s);
+            if (gf) {
+                ICP_CUDA(cudaFuncSetAttribute(k_posterior_fused<NBLK, NBMAX, NWC, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_posterior_fused<NBLK, NBMAX, NWC, 1, false><<<C, nthr, smem, s>>>(m, o, d_Mp, total, gf->Gs, gf->gs_scale, gf->row_scale, nullptr, d_b, nullptr, nullptr);
+            } else {
+                ICP_CUDA(cudaFuncSetAttribute(k_posterior_fused<NBLK, NBMAX, NWC, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_posterior_fused<NBLK, NBMAX, NWC, 3, false><<<C, nthr, smem, s>>>(m, o, d_Mp, total, nullptr, 0.0, 1.0, nullptr, d_b, nullptr, nullptr);
+            }
+            ICP_CUDA(cudaGetLastError());
+        }
+        ProfScope _ps(ST_CHOLESKY, s);
+        size_t smem_c = sizeof(double) * ((size_t)total * 64 + 4 * Kp);
+        ICP_CUDA(cudaFuncSetAttribute(k_cholesky_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        k_cholesky_packed<<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, d_M, d_L, d_mu, d_out_slot, d_status);
+        return;
+    }
+    ProfScope _ps(ST_POSTERIOR_BUILD, s);
     size_t smem = sizeof(double) * std::max(stage, fact);
     if (gf) {
-        ICP_CUDA(cudaFuncSetAttribute(k_posterior_fused<NBLK, NBMAX, NWC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_posterior_fused<NBLK, NBMAX, NWC, 1><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, total, gf->Gs, gf->gs_scale, gf->row_scale, d_L, d_mu, d_out_slot, d_status);
+        ICP_CUDA(cudaFuncSetAttribute(k_posterior_fused<NBLK, NBMAX, NWC, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_posterior_fused<NBLK, NBMAX, NWC, 1, true><<<C, nthr, smem, s>>>(m, o, d_M, total, gf->Gs, gf->gs_scale, gf->row_scale, d_L, d_mu, d_out_slot, d_status);
     } else {
-        ICP_CUDA(cudaFuncSetAttribute(k_posterior_fused<NBLK, NBMAX, NWC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_posterior_fused<NBLK, NBMAX, NWC, 3><<<C, (NWC + kProdWarps) * 32, smem, s>>>(m, o, d_M, total, nullptr, 0.0, 1.0, d_L, d_mu, d_out_slot, d_status);
+        ICP_CUDA(cudaFuncSetAttribute(k_posterior_fused<NBLK, NBMAX, NWC, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_posterior_fused<NBLK, NBMAX, NWC, 3, true><<<C, nthr, smem, s>>>(m, o, d_M, total, nullptr, 0.0, 1.0, d_L, d_mu, d_out_slot, d_status);
     }
 }
 
-// posterior build + Cholesky + solve in one launch; returns false when the shape is outside the DMMA kernels' range
-// (the caller then runs launch_posterior_build + launch_cholesky_solve)
+// posterior build + Cholesky + solve; returns false when the shape is outside the DMMA kernels' range (the caller then
+// runs launch_posterior_build + launch_cholesky_solve). Default: two launches - the rank update writes M block-packed
+// (d_Mp, C x NB (NB + 1) / 2 x 64 doubles) and b (d_b), k_cholesky_packed factorises at four chains per SM.
+// ICPCUDA_FUSE=1 (or d_Mp == nullptr): the single-launch variant, whose factorisation runs at two chains per SM.
 bool launch_posterior_fused(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, double *d_M_or_null, double *d_L,
-                            double *d_mu, const int *d_out_slot, int *d_status, cudaStream_t s) {
+                            double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s) {
     static const bool off = (getenv("ICPCUDA_NO_DMMA") && getenv("ICPCUDA_NO_DMMA")[0] == '1') ||
                             (getenv("ICPCUDA_NO_FUSE") && getenv("ICPCUDA_NO_FUSE")[0] == '1');
+    static const bool one_launch = getenv("ICPCUDA_FUSE") && getenv("ICPCUDA_FUSE")[0] == '1';
     const int NB = m.Kp / 8, total = NB * (NB + 1) / 2;
     if (off || NB > 13 || C <= 0) return false;   // NB <= 13: the 192-thread variants; the fused matrix must fit 2 CTAs / SM
-    ProfScope _ps(ST_POSTERIOR_BUILD, s);
-    if (NB <= 4) launch_fused<4, 4, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, s);
-    else if (NB <= 7) launch_fused<8, 7, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, s);
-    else launch_fused<24, 13, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, s);
+    if (one_launch) d_Mp = nullptr;
+    if (NB <= 4) launch_fused<4, 4, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, d_Mp, d_b, s);
+    else if (NB <= 7) launch_fused<8, 7, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, d_Mp, d_b, s);
+    else launch_fused<24, 13, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, d_Mp, d_b, s);
     ICP_CUDA(cudaGetLastError());
     return true;
 }

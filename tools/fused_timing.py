@@ -49,8 +49,12 @@ cols = [t[:, 1], t[:, 2], t[:, 3], t[:, 4], t[:, 5], t[:, 6], tot]
 print(f"direction {a.direction}: {n} CTAs, median clocks (p10 .. p90)")
 for nm, v in zip(names, cols):
     print(f"  {nm:32s} {np.median(v):9.0f}  ({np.percentile(v, 10):.0f} .. {np.percentile(v, 90):.0f})")
-print(f"  factorisation + store             {np.median(tot - t[:, 6]):9.0f}  (factor {np.median(t[:, 8]):.0f}, back substitution "
-      f"{np.median(t[:, 9]):.0f}, store L / mu {np.median(tot - t[:, 6] - t[:, 8] - t[:, 9]):.0f})")
+if os.environ.get("ICPCUDA_FUSE") == "1":
+    print(f"  factorisation + store             {np.median(tot - t[:, 6]):9.0f}  (factor {np.median(t[:, 8]):.0f}, back substitution "
+          f"{np.median(t[:, 9]):.0f}, store L / mu {np.median(tot - t[:, 6] - t[:, 8] - t[:, 9]):.0f})")
+else:
+    print(f"  k_cholesky_packed: load {np.median(t[:, 8]):.0f}, factor {np.median(t[:, 9]):.0f}, back substitution {np.median(t[:, 10]):.0f}, "
+          f"store L / mu {np.median(t[:, 11]):.0f}")
 first = start < np.percentile(start, 12)
 print(f"  first-wave CTAs: total {np.median(tot[first]):.0f}; later waves: {np.median(tot[~first]):.0f}")
 print(f"  span of the launch {start.max() + tot[start.argmax()]:.0f} clocks; CTAs per SM {np.bincount(smid).max()}")
