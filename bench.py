@@ -279,17 +279,32 @@ def run_gpu(args):
         shares = {k: round(v["ms"] / total_prof, 4) for k, v in prof.items() if v["launches"]}
         fp64 = ctx.fp64_peak()
         peaks, peak_src = measured_peaks()
-        # fused posterior kernel (build + Cholesky + solve), two launches per step (target- and model-sampling proposal).
-        # Algorithmic flops per chain-posterior: 2*3n*K^2 (M) + 2*3n*K*3 (Sigma^-1 apply) + K^3/3 (Cholesky)
-        # + 2*K^2 (solves) = 13.1 MFLOP at n = 202, K = 101 - what the reference's regression computes per posterior.
+        # posterior = rank-update kernel (k_posterior_fused<.., CHOL = false>: M = I + A^T A, b = A^T y on the FP64 tensor
+        # pipe) + k_cholesky_packed; each twice per step (target- and model-sampling proposal). The rank update dominates.
+        # Its algorithmic flops per chain-posterior: 2*3n*K^2 (M) + 2*3n*K*3 (Sigma^-1 apply) = 12.4 MFLOP at
+        # n = 202, K = 101 - what the reference's regression computes per posterior before it factorises.
         n_obs = len(ids)
-        flops_post = 2.0 * 3 * n_obs * K * K + 2.0 * 3 * n_obs * K * 3 + K ** 3 / 3.0 + 2.0 * K * K
+        flops_post = 2.0 * 3 * n_obs * K * K + 2.0 * 3 * n_obs * K * 3
+        flops_chol = K ** 3 / 3.0 + 2.0 * K * K
         # executed on the tensor pipe: only the 91 lower-triangle 8x8 blocks (Kp = 104), and one row per observation instead
         # of three for the model-sampling proposal (constant-Gram fast path); Cholesky as above
         nb = (K + 7) // 8
         blocks = nb * (nb + 1) // 2
         rows_t, rows_m = 3 * 8 * ((n_obs + 7) // 8), 24 * ((n_obs + 23) // 24)
-        flops_exec = 0.5 * (2.0 * 64 * blocks * rows_t + 2.0 * 64 * blocks * rows_m) + K ** 3 / 3.0 + 2.0 * K * K
+        flops_exec = 0.5 * (2.0 * 64 * blocks * rows_t + 2.0 * 64 * blocks * rows_m)
+        Kp = 8 * nb
+        ch = prof.get("cholesky_solve", {"ms": 0.0, "launches": 0})
+        ch_ms = ch["ms"] / max(ch["launches"], 1)
+        # k_cholesky_packed per launch: reads the packed blocks + b, writes the lower triangle of L + mu
+        ch_bytes = C * 8.0 * (64 * blocks + Kp + Kp * (Kp + 1) / 2 + Kp)
+        roof_chol = None
+        if ch["launches"]:
+            roof_chol = {"bound": "hbm", "kernel": "k_cholesky_packed", "achieved": ch_bytes / (ch_ms * 1e-3) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ch_bytes / (ch_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "traffic": 2.76e8 * C / 2368.0, "avg_launch_ms": ch_ms, "flops_per_launch": flops_chol * C,
+                         "share_of_step": shares.get("cholesky_solve"),
+                         "note": "a chain of Kp dependent pivots per matrix: latency-bound by construction (4 chains per SM hide "
+                                 "it); traffic = dram read + write per launch from profiles/r1h (ncu --set full, C = 2368), scaled by C"}
         pb = prof["posterior_build"]
         pb_ms = pb["ms"] / max(pb["launches"], 1)
         pb_tflops = flops_post * C / (pb_ms * 1e-3) / 1e12 if pb_ms > 0 else 0.0
@@ -313,13 +328,15 @@ def run_gpu(args):
                    "achieved": cp["near_surface"]["algorithmic_GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": cp["near_surface"]["algorithmic_GBps"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                    "bytes_per_query": 1000}
-        roofline = {"bound": "tensor", "pipe": "FP64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA)", "kernel": "k_posterior_fused",
+        roofline = {"bound": "tensor", "pipe": "FP64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA)",
+                    "kernel": "k_posterior_fused<.., CHOL = false> (rank update M = I + A^T A, b = A^T y)",
                     "achieved": pb_tflops, "peak": fp64["dmma_tflops"], "unit": "TFLOP/s",
                     "frac": pb_tflops / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
                     "hw_achieved": pb_hw, "hw_frac": pb_hw / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
-                    "traffic": 2.03e8 * C / 2368.0,
-                    "traffic_note": "dram read+write per launch from profiles/r1f (ncu --set full, C = 2368: 51 + 152 MB), scaled by C; "
-                                    "algorithmic bytes per launch = C * (8 Kp^2 + 8 Kp) written (L, mu) ~ 206 MB",
+                    "traffic": 1.62e8 * C / 2368.0,
+                    "traffic_note": "dram read+write per launch from profiles/r1h (ncu --set full, C = 2368), scaled by C; "
+                                    "algorithmic bytes per launch = C * (8 * 64 * 91 + 8 Kp) written (packed M, b) ~ 112 MB plus the "
+                                    "observation frames read (~ 48 MB); the basis rows come from L2",
                     "peak_source": "DMMA m8n8k4 micro-benchmark run live on this GPU (MEASURED_PEAKS.json has no FP64 figure); "
                                    "DFMA measured %.1f TFLOP/s" % fp64["dfma_tflops"],
                     "flops_per_launch": flops_post * C, "executed_flops_per_launch": flops_exec * C, "avg_launch_ms": pb_ms,
@@ -342,7 +359,7 @@ def run_gpu(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e_steps,
                         "runs_ms": e2e_runs, "note": "median of 5 host-buffer icp_chain_run calls of K steps: pinned theta0 in, full chain log out"},
                 "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / steps, "accept_rate": accept_rate,
-                "clocks": clocks.summary(), "roofline": roofline, "roofline_closest_point": roof_cp, "closest_point": cp,
+                "clocks": clocks.summary(), "roofline": roofline, "roofline_cholesky": roof_chol, "roofline_closest_point": roof_cp, "closest_point": cp,
                 "kernel_shares": shares, "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items() if v["launches"]},
                 "fp64_peak": fp64, "gather_ms": gather_ms,
                 "cpu_baseline": {"value": cb_rate, "unit": UNIT, "cores": 1, "kind": "port",

@@ -80,29 +80,9 @@ __device__ __forceinline__ double chain_normal(unsigned long long seed, unsigned
     return (k & 1) ? rad * sn : rad * cs;
 }
 
-// w = L^-T z with L staged in shared memory (row-major, ld = Kp); one warp, registers + shuffles
-__device__ void warp_backsolve_smem(const double *sL, int Kp, const double *z_sm, double *w_sm) {
-    int lane = threadIdx.x & 31;
-    double zr[8];
-#pragma unroll
-    for (int q = 0; q < 8; q++) { int k = lane + 32 * q; zr[q] = k < Kp ? z_sm[k] : 0.0; }
-    for (int i = Kp - 1; i >= 0; i--) {
-        int owner = i & 31, slot = i >> 5;
-        double zi = 0.0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) if (q == slot) zi = zr[q];
-        double wi = __shfl_sync(0xffffffffu, zi, owner) / sL[(size_t)i * Kp + i];
-        if (lane == 0) w_sm[i] = wi;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            int k = lane + 32 * q;
-            if (k < i) zr[q] = fma(-sL[(size_t)i * Kp + k], wi, zr[q]);
-        }
-    }
-    __syncwarp();
-}
-
-// same with the lower triangle packed row-major (row i at offset i (i + 1) / 2)
+// w = L^-T z, one warp, registers + shuffles; L staged in shared memory with
+// the lower triangle packed row-major (row i at offset i (i + 1) / 2); the diagonal entries have been replaced
+// by their reciprocals (one parallel division per row instead of a division on every step of the serial chain)
 __device__ void warp_backsolve_packed(const double *sL, int Kp, const double *z_sm, double *w_sm) {
     int lane = threadIdx.x & 31;
     double zr[8];
@@ -114,7 +94,7 @@ __device__ void warp_backsolve_packed(const double *sL, int Kp, const double *z_
         double zi = 0.0;
 #pragma unroll
         for (int q = 0; q < 8; q++) if (q == slot) zi = zr[q];
-        double wi = __shfl_sync(0xffffffffu, zi, owner) / row[i];
+        double wi = __shfl_sync(0xffffffffu, zi, owner) * row[i];
         if (lane == 0) w_sm[i] = wi;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
@@ -183,6 +163,8 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
             }
         }
         __syncthreads();
+        for (int i = threadIdx.x; i < Kp; i += blockDim.x) { double *d = sL + (i * (i + 1)) / 2 + i; *d = 1.0 / *d; }
+        __syncthreads();
         if (threadIdx.x < 32) warp_backsolve_packed(sL, Kp, sz, sw);
         __syncthreads();
         for (int k = threadIdx.x; k < Kp; k += blockDim.x) sz[k] = muc[k] + sw[k];
@@ -219,16 +201,24 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
     }
 }
 
-// |L^T d|^2, d in shared memory
-__device__ double chain_quad_LT(const double *__restrict__ Lc, int Kp, const double *d_sm, double *red) {
-    double part = 0.0;
+// |L^T d|^2 (d in shared memory), two of them at once (forward and backward density of one ICP component): the two factors stream from DRAM
+// concurrently, which doubles the loads in flight of this latency-bound kernel
+__device__ void chain_quad_LT2(const double *__restrict__ La, const double *__restrict__ Lb, int Kp, const double *da_sm,
+                               const double *db_sm, double *red, double &qa, double &qb) {
+    double pa = 0.0, pb = 0.0;
     for (int j = threadIdx.x; j < Kp; j += blockDim.x) {
-        double v = 0.0;
+        double va = 0.0, vb = 0.0;
 #pragma unroll 4
-        for (int i = j; i < Kp; i++) v = fma(__ldg(&Lc[(size_t)i * Kp + j]), d_sm[i], v);
-        part = fma(v, v, part);
+        for (int i = j; i < Kp; i++) {
+            va = fma(__ldg(&La[(size_t)i * Kp + j]), da_sm[i], va);
+            vb = fma(__ldg(&Lb[(size_t)i * Kp + j]), db_sm[i], vb);
+        }
+        pa = fma(va, va, pa);
+        pb = fma(vb, vb, pb);
     }
-    return block_sum(part, red);
+    qa = block_sum(pa, red);
+    __syncthreads();
+    qb = block_sum(pb, red);
 }
 
 __device__ __forceinline__ double gauss1_logpdf(double x, double sd) {
@@ -239,7 +229,7 @@ __device__ __forceinline__ double gauss1_logpdf(double x, double sd) {
 __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st, LogDev lg) {
     extern __shared__ double sm[];
     const int K = P.K, Kp = P.Kp, Lt = K + kTheta0, C = P.C;
-    double *sd = sm, *red = sm + Kp;
+    double *sd = sm, *sd2 = sm + Kp, *red = sm + 2 * Kp;
     __shared__ double s_fwd[kMaxComp], s_bwd[kMaxComp];
     __shared__ int s_flags[3];  // [0] any of theta[0..9] differs, [1] outside rotation group, [2] outside translation group
     int c = blockIdx.x;
@@ -267,15 +257,13 @@ __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st
             if (s_flags[0]) { fwd = bwd = -INFINITY; }                          // NonRigidIcpProposal.scala:72-74
             else {
                 size_t sc = (size_t)cd.icp_index * 2 * C + st.slot_cur[c], sp = (size_t)cd.icp_index * 2 * C + st.slot_prop[c];
-                for (int k = threadIdx.x; k < Kp; k += blockDim.x)
+                for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
                     sd[k] = k < K ? (cur[kTheta0 + k] + ((prp[kTheta0 + k] - cur[kTheta0 + k]) / cd.step)) - st.mu[sc * Kp + k] : 0.0;
+                    sd2[k] = k < K ? (prp[kTheta0 + k] + ((cur[kTheta0 + k] - prp[kTheta0 + k]) / cd.step)) - st.mu[sp * Kp + k] : 0.0;
+                }
                 __syncthreads();
-                double qf = chain_quad_LT(st.L + sc * Kp * Kp, Kp, sd, red);
-                __syncthreads();
-                for (int k = threadIdx.x; k < Kp; k += blockDim.x)
-                    sd[k] = k < K ? (prp[kTheta0 + k] + ((cur[kTheta0 + k] - prp[kTheta0 + k]) / cd.step)) - st.mu[sp * Kp + k] : 0.0;
-                __syncthreads();
-                double qb = chain_quad_LT(st.L + sp * Kp * Kp, Kp, sd, red);
+                double qf, qb;
+                chain_quad_LT2(st.L + sc * Kp * Kp, st.L + sp * Kp * Kp, Kp, sd, sd2, red, qf, qb);
                 __syncthreads();
                 fwd = -0.5 * (K * ICP_LOG_2PI + qf);
                 bwd = -0.5 * (K * ICP_LOG_2PI + qb);
@@ -552,7 +540,7 @@ void enqueue_step(RunCtx &r) {
     enqueue_state_eval(r, r.st.theta_prop, r.st.values_prop, r.st.slot_prop);
     {
         ProfScope ps(ST_ACCEPT, r.s);
-        k_chain_accept<<<C, 128, sizeof(double) * (Kp + 40), r.s>>>(P, r.st, r.lg);
+        k_chain_accept<<<C, 128, sizeof(double) * (2 * Kp + 40), r.s>>>(P, r.st, r.lg);
         ICP_CUDA(cudaGetLastError());
         k_step_increment<<<1, 1, 0, r.s>>>(r.st.step);
         ICP_CUDA(cudaGetLastError());

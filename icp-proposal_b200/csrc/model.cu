@@ -26,7 +26,7 @@ void launch_scale_basis(int rows, int K, int Kp, const double *d_U, const double
     ICP_CUDA(cudaGetLastError());
 }
 
-constexpr int kRecCH = 4;  // chains per CTA
+constexpr int kRecCH = 8;   // chains per CTA: every basis entry fetched from L2 serves 8 chains (at 4 the kernel sat on the L2 bandwidth cap)
 
 // thread = vertex, CTA = 128 vertices x kRecCH chains; alpha tiles broadcast from shared memory,
 // Q^T rows streamed coalesced from L2 (the basis is shared by every chain)
