@@ -22,6 +22,7 @@ using namespace icp;
 namespace {
 
 constexpr int kMaxComp = 16;
+constexpr int kMaxNBc = 20;   // Kp <= 160 (icp_model_create enforces it)
 
 struct CompDev {
     int kind, axis, icp_index;  // icp_index: which ICP posterior set (or -1)
@@ -201,20 +202,42 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
     }
 }
 
-// |L^T d|^2 (d in shared memory), two of them at once (forward and backward density of one ICP component): the two factors stream from DRAM
-// concurrently, which doubles the loads in flight of this latency-bound kernel
+// |L_a^T d_a|^2 and |L_b^T d_b|^2 (forward and backward density of one ICP component; d in shared memory). Row-cooperative:
+// the warps deal the rows, a lane owns the columns lane + 32 q, so every load is one contiguous row segment, all lanes of
+// all warps stay busy (a column-per-thread loop leaves the triangle's short columns idle) and 2 x 4 rows are in flight
+// per warp. part: 2 * nwarps * Kp doubles of shared memory.
 __device__ void chain_quad_LT2(const double *__restrict__ La, const double *__restrict__ Lb, int Kp, const double *da_sm,
-                               const double *db_sm, double *red, double &qa, double &qb) {
+                               const double *db_sm, double *part, double *red, double &qa, double &qb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    constexpr int kQ = (8 * kMaxNBc + 31) / 32;   // column slots per lane
+    double va[kQ], vb[kQ];
+#pragma unroll
+    for (int q = 0; q < kQ; q++) va[q] = vb[q] = 0.0;
+#pragma unroll 2
+    for (int i = warp; i < Kp; i += nw) {
+        const double dai = da_sm[i], dbi = db_sm[i];
+        const double *ra = La + (size_t)i * Kp, *rb = Lb + (size_t)i * Kp;
+#pragma unroll
+        for (int q = 0; q < kQ; q++) {
+            const int j = lane + 32 * q;
+            if (j <= i) {
+                va[q] = fma(__ldg(ra + j), dai, va[q]);
+                vb[q] = fma(__ldg(rb + j), dbi, vb[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kQ; q++) {
+        const int j = lane + 32 * q;
+        if (j < Kp) { part[(size_t)warp * Kp + j] = va[q]; part[(size_t)(nw + warp) * Kp + j] = vb[q]; }
+    }
+    __syncthreads();
     double pa = 0.0, pb = 0.0;
     for (int j = threadIdx.x; j < Kp; j += blockDim.x) {
-        double va = 0.0, vb = 0.0;
-#pragma unroll 4
-        for (int i = j; i < Kp; i++) {
-            va = fma(__ldg(&La[(size_t)i * Kp + j]), da_sm[i], va);
-            vb = fma(__ldg(&Lb[(size_t)i * Kp + j]), db_sm[i], vb);
-        }
-        pa = fma(va, va, pa);
-        pb = fma(vb, vb, pb);
+        double sa = 0.0, sb = 0.0;
+        for (int w = 0; w < nw; w++) { sa += part[(size_t)w * Kp + j]; sb += part[(size_t)(nw + w) * Kp + j]; }
+        pa = fma(sa, sa, pa);
+        pb = fma(sb, sb, pb);
     }
     qa = block_sum(pa, red);
     __syncthreads();
@@ -229,7 +252,7 @@ __device__ __forceinline__ double gauss1_logpdf(double x, double sd) {
 __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st, LogDev lg) {
     extern __shared__ double sm[];
     const int K = P.K, Kp = P.Kp, Lt = K + kTheta0, C = P.C;
-    double *sd = sm, *sd2 = sm + Kp, *red = sm + 2 * Kp;
+    double *sd = sm, *sd2 = sm + Kp, *red = sm + 2 * Kp, *part = sm + 2 * Kp + 40;   // part: [2][nwarps][Kp]
     __shared__ double s_fwd[kMaxComp], s_bwd[kMaxComp];
     __shared__ int s_flags[3];  // [0] any of theta[0..9] differs, [1] outside rotation group, [2] outside translation group
     int c = blockIdx.x;
@@ -263,7 +286,7 @@ __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st
                 }
                 __syncthreads();
                 double qf, qb;
-                chain_quad_LT2(st.L + sc * Kp * Kp, st.L + sp * Kp * Kp, Kp, sd, sd2, red, qf, qb);
+                chain_quad_LT2(st.L + sc * Kp * Kp, st.L + sp * Kp * Kp, Kp, sd, sd2, part, red, qf, qb);
                 __syncthreads();
                 fwd = -0.5 * (K * ICP_LOG_2PI + qf);
                 bwd = -0.5 * (K * ICP_LOG_2PI + qb);
@@ -540,7 +563,7 @@ void enqueue_step(RunCtx &r) {
     enqueue_state_eval(r, r.st.theta_prop, r.st.values_prop, r.st.slot_prop);
     {
         ProfScope ps(ST_ACCEPT, r.s);
-        k_chain_accept<<<C, 128, sizeof(double) * (2 * Kp + 40), r.s>>>(P, r.st, r.lg);
+        k_chain_accept<<<C, 128, sizeof(double) * (2 * Kp + 40 + 2 * 4 * Kp), r.s>>>(P, r.st, r.lg);
         ICP_CUDA(cudaGetLastError());
         k_step_increment<<<1, 1, 0, r.s>>>(r.st.step);
         ICP_CUDA(cudaGetLastError());
