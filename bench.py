@@ -301,7 +301,7 @@ def run_gpu(args):
         if ch["launches"]:
             roof_chol = {"bound": "hbm", "kernel": "k_cholesky_packed", "achieved": ch_bytes / (ch_ms * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ch_bytes / (ch_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                         "traffic": 2.76e8 * C / 2368.0, "avg_launch_ms": ch_ms, "flops_per_launch": flops_chol * C,
+                         "traffic": 1.76e8 * C / 2368.0, "avg_launch_ms": ch_ms, "flops_per_launch": flops_chol * C,
                          "share_of_step": shares.get("cholesky_solve"),
                          "note": "a chain of Kp dependent pivots per matrix: latency-bound by construction (4 chains per SM hide "
                                  "it); traffic = dram read + write per launch from profiles/r1h (ncu --set full, C = 2368), scaled by C"}
@@ -333,7 +333,7 @@ def run_gpu(args):
                     "achieved": pb_tflops, "peak": fp64["dmma_tflops"], "unit": "TFLOP/s",
                     "frac": pb_tflops / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
                     "hw_achieved": pb_hw, "hw_frac": pb_hw / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
-                    "traffic": 1.62e8 * C / 2368.0,
+                    "traffic": 1.08e8 * C / 2368.0,
                     "traffic_note": "dram read+write per launch from profiles/r1h (ncu --set full, C = 2368), scaled by C; "
                                     "algorithmic bytes per launch = C * (8 * 64 * 91 + 8 Kp) written (packed M, b) ~ 112 MB plus the "
                                     "observation frames read (~ 48 MB); the basis rows come from L2",
