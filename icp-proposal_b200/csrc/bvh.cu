@@ -476,7 +476,10 @@ __global__ void __launch_bounds__(128) k_nearest_vertex_brute(int N, int C, cons
                                                               int *__restrict__ out_prim, double *__restrict__ out_d2) {
     extern __shared__ double smd[];
     double *sx = smd;                                            // [3 N] exact coordinates
-    float4 *sv = reinterpret_cast<float4 *>(smd + 3 * (size_t)((N + 1) & ~1));  // [N] FP32 copy (x, y, z, -)
+    // FP32 copy as three arrays [Np] (Np = N rounded up to even, padded with a vertex at infinity): a 64-bit load
+    // yields the same coordinate of two consecutive vertices, the operand shape of the packed f32x2 arithmetic
+    const int Np = (N + 1) & ~1;
+    float *svx = reinterpret_cast<float *>(smd + 3 * (size_t)Np), *svy = svx + Np, *svz = svy + Np;
     const int c = blockIdx.y;
     const double *Xc = X + (size_t)c * N * 3;
     // tile load with 8 independent loads in flight per thread (a load -> store loop pays one L2 round trip per element)
@@ -488,8 +491,10 @@ __global__ void __launch_bounds__(128) k_nearest_vertex_brute(int N, int C, cons
         for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; if (e < 3 * N) sx[e] = tmp[u]; }
     }
     __syncthreads();
-    for (int v = threadIdx.x; v < N; v += blockDim.x)
-        sv[v] = make_float4((float)sx[3 * v], (float)sx[3 * v + 1], (float)sx[3 * v + 2], 0.f);
+    for (int v = threadIdx.x; v < Np; v += blockDim.x) {
+        const bool real = v < N;
+        svx[v] = real ? (float)sx[3 * v] : 1e30f; svy[v] = real ? (float)sx[3 * v + 1] : 1e30f; svz[v] = real ? (float)sx[3 * v + 2] : 1e30f;
+    }
     __syncthreads();
     const long long i0 = (long long)blockIdx.x * blockDim.x * kBruteQ + threadIdx.x;
     double qx[kBruteQ], qy[kBruteQ], qz[kBruteQ];
@@ -503,18 +508,32 @@ __global__ void __launch_bounds__(128) k_nearest_vertex_brute(int N, int C, cons
         fx[t] = (float)qx[t]; fy[t] = (float)qy[t]; fz[t] = (float)qz[t];
         best[t] = INFINITY; second[t] = INFINITY; bid[t] = -1;
     }
-    // single FP32 pass: minimum, runner-up and argmin
+    // single FP32 pass: minimum, runner-up and argmin; two vertices per step with packed f32x2 arithmetic (sm_100:
+    // FADD2 / FMUL2 / FFMA2 - half the instructions of the distance evaluation). The rounding of each lane is that of
+    // the scalar sequence d2f = fma(dx, dx, fma(dy, dy, dz * dz)), which the exact-rescan branch below repeats.
+    float2 nqx[kBruteQ], nqy[kBruteQ], nqz[kBruteQ];
+#pragma unroll
+    for (int t = 0; t < kBruteQ; t++) { nqx[t] = make_float2(-fx[t], -fx[t]); nqy[t] = make_float2(-fy[t], -fy[t]); nqz[t] = make_float2(-fz[t], -fz[t]); }
 #pragma unroll 4
-    for (int v = 0; v < N; v++) {
-        float4 p = sv[v];
+    for (int v = 0; v < Np; v += 2) {
+        const float2 px = *reinterpret_cast<const float2 *>(svx + v), py = *reinterpret_cast<const float2 *>(svy + v),
+                     pz = *reinterpret_cast<const float2 *>(svz + v);
 #pragma unroll
         for (int t = 0; t < kBruteQ; t++) {
-            float dx = fx[t] - p.x, dy = fy[t] - p.y, dz = fz[t] - p.z;
-            float d2f = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-            bool better = d2f < best[t];
-            second[t] = fminf(second[t], better ? best[t] : d2f);
-            bid[t] = better ? v : bid[t];
-            best[t] = better ? d2f : best[t];
+            const float2 dx = __fadd2_rn(px, nqx[t]), dy = __fadd2_rn(py, nqy[t]), dz = __fadd2_rn(pz, nqz[t]);
+            const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+            {
+                const bool better = d2.x < best[t];
+                second[t] = fminf(second[t], better ? best[t] : d2.x);
+                bid[t] = better ? v : bid[t];
+                best[t] = better ? d2.x : best[t];
+            }
+            {
+                const bool better = d2.y < best[t];
+                second[t] = fminf(second[t], better ? best[t] : d2.y);
+                bid[t] = better ? v + 1 : bid[t];
+                best[t] = better ? d2.y : best[t];
+            }
         }
     }
 #pragma unroll
@@ -532,8 +551,7 @@ __global__ void __launch_bounds__(128) k_nearest_vertex_brute(int N, int C, cons
             // rare: near-tie (or NaN query) -> exact FP64 scan of every vertex the FP32 bound cannot exclude
             id = -1;
             for (int v = 0; v < N; v++) {
-                float4 p = sv[v];
-                float dx = fx[t] - p.x, dy = fy[t] - p.y, dz = fz[t] - p.z;
+                float dx = svx[v] - fx[t], dy = svy[v] - fy[t], dz = svz[v] - fz[t];
                 float d2f = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                 if (d2f <= thresh) {
                     double ex = qx[t] - sx[3 * v], ey = qy[t] - sx[3 * v + 1], ez = qz[t] - sx[3 * v + 2];
@@ -554,7 +572,7 @@ __global__ void __launch_bounds__(128) k_nearest_vertex_brute(int N, int C, cons
 
 bool launch_nearest_vertex_brute(int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, double scale,
                                  int *d_prim, double *d_d2, cudaStream_t s) {
-    size_t smem = sizeof(double) * 3 * (size_t)((N + 1) & ~1) + sizeof(float4) * (size_t)N;
+    size_t smem = sizeof(double) * 3 * (size_t)((N + 1) & ~1) + sizeof(float) * 3 * (size_t)((N + 1) & ~1);
     if (smem > 100 * 1024 || C <= 0 || nq <= 0) return false;
     ProfScope _ps(ST_NEAREST_DYNAMIC, s);
     if (smem > 48 * 1024) ICP_CUDA(cudaFuncSetAttribute(k_nearest_vertex_brute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
