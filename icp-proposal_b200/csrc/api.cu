@@ -670,6 +670,8 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
             NearestArgs a;
             a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = n;
             a.Xq = d_X; a.q_ids = p->ids.p; a.Nq = m->N; a.out_cp = w.cp.p; a.perm = p->qperm.p;
+            if (w.seed.n < tot) { w.seed.ensure(tot); ICP_CUDA(cudaMemsetAsync(w.seed.p, 0xFF, sizeof(int) * tot, s)); }
+            a.seed_slot = w.seed.p;
             launch_nearest(a, s);
             oa.cp = w.cp.p; oa.cp_stride = n; oa.cp_map = nullptr;
         }
@@ -1007,6 +1009,8 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
             NearestArgs a;
             a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = e->n_ids;
             a.Xq = d_X; a.q_ids = e->ids.p; a.Nq = m->N; a.out_d2 = w.d2_m2t.p; a.perm = e->qperm.p;
+            if (w.seed_m2t.n < tot) { w.seed_m2t.ensure(tot); ICP_CUDA(cudaMemsetAsync(w.seed_m2t.p, 0xFF, sizeof(int) * tot, s)); }
+            a.seed_slot = w.seed_m2t.p;
             if (collective || w.force_cp_m2t) { w.cp_m2t.ensure(3 * tot); a.out_cp = w.cp_m2t.p; }
             launch_nearest(a, s);
             if (collective && t->has_boundary) {

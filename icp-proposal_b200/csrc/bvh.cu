@@ -293,6 +293,7 @@ struct Hit {
     double x, y, z;
     int prim;
     int feat;
+    int slot;
 };
 
 __device__ __forceinline__ void point_triangle(double px, double py, double pz, double ax, double ay, double az,
@@ -361,7 +362,7 @@ __device__ __forceinline__ void leaf_test(int slot, const int *__restrict__ prim
     double dx = qx - rx, dy = qy - ry, dz = qz - rz;
     double d2 = dx * dx + dy * dy + dz * dz;
     if (d2 < h.d2 || (d2 == h.d2 && p < h.prim)) {
-        h.d2 = d2; h.x = rx; h.y = ry; h.z = rz; h.prim = p; h.feat = feat;
+        h.d2 = d2; h.x = rx; h.y = ry; h.z = rz; h.prim = p; h.feat = feat; h.slot = slot;
     }
 }
 
@@ -382,9 +383,9 @@ __global__ void __launch_bounds__(128) k_nearest(int n, const int2 *__restrict__
                                                  const int *__restrict__ tris, int N, int C, long long nq,
                                                  const double *__restrict__ q, int q_per_chain,
                                                  const double *__restrict__ Xq, const int *__restrict__ q_ids, int Nq,
-                                                 const int *__restrict__ perm, int *__restrict__ out_prim,
-                                                 int *__restrict__ out_feat, double *__restrict__ out_cp,
-                                                 double *__restrict__ out_d2) {
+                                                 const int *__restrict__ perm, int *__restrict__ seed_slot,
+                                                 int *__restrict__ out_prim, int *__restrict__ out_feat,
+                                                 double *__restrict__ out_cp, double *__restrict__ out_d2) {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nq * C) return;
     int c = (int)(g / nq);
@@ -402,12 +403,21 @@ __global__ void __launch_bounds__(128) k_nearest(int n, const int2 *__restrict__
     const double *Xi = DYNAMIC ? X + (size_t)c * N * 3 : nullptr;
     float fx = (float)qx, fy = (float)qy, fz = (float)qz;
     Hit h;
-    h.d2 = INFINITY; h.x = h.y = h.z = 0.0; h.prim = 0x7fffffff; h.feat = -1;
+    h.d2 = INFINITY; h.x = h.y = h.z = 0.0; h.prim = 0x7fffffff; h.feat = -1; h.slot = -1;
     float best = INFINITY;
     int stack_n[kStack];
     float stack_d[kStack];
     int sp = 0, node = 0;
     if (!(qx == qx && qy == qy && qz == qz)) node = 0x7ffffffe;  // NaN query: no traversal, NaN result
+    else if (seed_slot) {
+        // upper bound from the primitive that answered this query last time; ties still resolve to the lowest index
+        // because subtrees are only pruned when their lower bound exceeds the best distance
+        const int s0 = seed_slot[g];
+        if ((unsigned)s0 < (unsigned)n) {
+            leaf_test<PRIM, DYNAMIC>(s0, prim, prim_data, Xi, tris, qx, qy, qz, h);
+            best = __double2float_ru(h.d2);
+        }
+    }
     while (node != 0x7ffffffe) {
         if (node < 0) {
             leaf_test<PRIM, DYNAMIC>(~node, prim, prim_data, Xi, tris, qx, qy, qz, h);
@@ -436,6 +446,7 @@ __global__ void __launch_bounds__(128) k_nearest(int n, const int2 *__restrict__
         }
     }
     if (h.prim == 0x7fffffff) { h.d2 = NAN; h.x = h.y = h.z = NAN; h.prim = -1; }
+    if (seed_slot) seed_slot[g] = h.slot;
     if (out_prim) out_prim[g] = h.prim;
     if (out_feat) out_feat[g] = h.feat;
     if (out_cp) { out_cp[3 * g] = h.x; out_cp[3 * g + 1] = h.y; out_cp[3 * g + 2] = h.z; }
@@ -453,7 +464,7 @@ void launch_nearest(const NearestArgs &a, cudaStream_t s) {
 #define ICP_LAUNCH_NEAREST(P, D)                                                                                  \
     k_nearest<P, D><<<blocks, threads, 0, s>>>(b.n, b.children.p, b.nodes.p, b.prim.p, a.prim_data, a.X, a.tris, \
                                                a.N, a.C, (long long)a.nq, a.q, a.q_per_chain, a.Xq, a.q_ids,     \
-                                               a.Nq, a.perm, a.out_prim, a.out_feat, a.out_cp, a.out_d2)
+                                               a.Nq, a.perm, a.seed_slot, a.out_prim, a.out_feat, a.out_cp, a.out_d2)
     if (b.prim_kind == 0) {
         if (dynamic) ICP_LAUNCH_NEAREST(0, true); else ICP_LAUNCH_NEAREST(0, false);
     } else {

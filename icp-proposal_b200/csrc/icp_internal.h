@@ -141,6 +141,10 @@ struct NearestArgs {
     const int *q_ids = nullptr;     // [nq]
     int Nq = 0;
     const int *perm = nullptr;      // optional processing order (C == 1): thread g handles query perm[g]
+    // optional [C][nq], read and rewritten: leaf slot of the query's previous answer (any value; out of range = none).
+    // The traversal starts from the exact distance to that primitive, which prunes most of the tree when the query
+    // moved little since (successive MH states of a chain). The result does not depend on it.
+    int *seed_slot = nullptr;
     // outputs [C][nq]
     int *out_prim = nullptr;
     int *out_feat = nullptr;
@@ -313,6 +317,7 @@ struct PosteriorWork {
     DevBuf<double> X;        // [C][N][3]
     DevBuf<double> cp, d2;   // [C][n][3], [C][n]
     DevBuf<int> prim;        // [C][n]
+    DevBuf<int> seed;        // [C][n] traversal seeds (NearestArgs::seed_slot)
     DevBuf<uint8_t> flags;   // [C][n]
     DevBuf<int> vid;
     DevBuf<double> F, y;
@@ -350,7 +355,7 @@ struct icp_proposal_s {
 namespace icp {
 struct EvalWork {
     DevBuf<double> X, cp_m2t, d2_m2t, cp_t2m, d2_t2m;
-    DevBuf<int> prim;
+    DevBuf<int> prim, seed_m2t;
     DevBuf<uint8_t> skip_m2t, skip_t2m;
     bool force_cp_m2t = false;  // also keep the model->target closest points (shared with ICP proposals)
 };
