@@ -1031,6 +1031,8 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
             NearestArgs a;
             a.bvh = &m->tri_bvh; a.X = d_X; a.tris = m->tris.p; a.N = m->N; a.C = C; a.nq = e->n_tp; a.q = e->tp.p;
             a.out_d2 = w.d2_t2m.p;
+            if (w.seed_t2m.n < tot) { w.seed_t2m.ensure(tot); ICP_CUDA(cudaMemsetAsync(w.seed_t2m.p, 0xFF, sizeof(int) * tot, s)); }
+            a.seed_slot = w.seed_t2m.p;
             if (collective) { w.cp_t2m.ensure(3 * tot); a.out_cp = w.cp_t2m.p; }
             launch_nearest(a, s);
             if (collective && t->has_boundary) {

@@ -355,7 +355,7 @@ struct icp_proposal_s {
 namespace icp {
 struct EvalWork {
     DevBuf<double> X, cp_m2t, d2_m2t, cp_t2m, d2_t2m;
-    DevBuf<int> prim, seed_m2t;
+    DevBuf<int> prim, seed_m2t, seed_t2m;   // seed_*: traversal seeds (NearestArgs::seed_slot)
     DevBuf<uint8_t> skip_m2t, skip_t2m;
     bool force_cp_m2t = false;  // also keep the model->target closest points (shared with ICP proposals)
 };
