@@ -630,6 +630,23 @@ extern "C" int32_t icp_proposal_destroy(icp_proposal p) {
 
 namespace icp {
 
+// currentMesh.pointSet.findClosestPoint for C chains: the vertex BVH refitted and walked in shared memory (default), the
+// FP32-screened brute force when the tree does not fit, the global-memory refit + traversal as the last resort.
+// ICPCUDA_NEAREST_VERTEX = tree | brute | bvh forces one of them (all three return the same answers).
+void nearest_model_vertex(icp_model m, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, int *d_seed,
+                          int *d_prim, cudaStream_t s) {
+    static const std::string mode = getenv("ICPCUDA_NEAREST_VERTEX") ? getenv("ICPCUDA_NEAREST_VERTEX") : "";
+    if ((mode.empty() || mode == "tree") &&
+        launch_nearest_vertex_tree(m->vert_bvh, m->N, C, d_X, nq, d_q, q_per_chain, d_seed, d_prim, nullptr, s))
+        return;
+    if (mode != "bvh" && launch_nearest_vertex_brute(m->N, C, d_X, nq, d_q, q_per_chain, m->scale, d_prim, nullptr, s)) return;
+    bvh_refit(m->vert_bvh, C, d_X, m->N, nullptr, s);
+    NearestArgs a;
+    a.bvh = &m->vert_bvh; a.X = d_X; a.N = m->N; a.C = C; a.nq = nq; a.q = d_q; a.q_per_chain = q_per_chain;
+    a.out_prim = d_prim; a.seed_slot = d_seed;
+    launch_nearest(a, s);
+}
+
 void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const double *d_X, PosteriorWork &w, double *d_L,
                         double *d_mu, const int *d_out_slot, cudaStream_t s, const SharedCp *shared) {
     if (C <= 0) return;
@@ -652,13 +669,8 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
     if (tsamp) {
         // :118 currentMesh.pointSet.findClosestPoint(targetPoint): vertex BVH refit to the current meshes
         w.prim.ensure(tot);
-        static const bool prefer_bvh = getenv("ICPCUDA_NEAREST_VERTEX") && std::string(getenv("ICPCUDA_NEAREST_VERTEX")) == "bvh";
-        if (prefer_bvh || !launch_nearest_vertex_brute(m->N, C, d_X, n, p->tp.p, 0, m->scale, w.prim.p, nullptr, s)) {
-            bvh_refit(m->vert_bvh, C, d_X, m->N, nullptr, s);
-            NearestArgs a;
-            a.bvh = &m->vert_bvh; a.X = d_X; a.N = m->N; a.C = C; a.nq = n; a.q = p->tp.p; a.out_prim = w.prim.p;
-            launch_nearest(a, s);
-        }
+        if (w.seed.n < tot) { w.seed.ensure(tot); ICP_CUDA(cudaMemsetAsync(w.seed.p, 0xFF, sizeof(int) * tot, s)); }
+        nearest_model_vertex(m, C, d_X, n, p->tp.p, 0, w.seed.p, w.prim.p, s);
         oa.tp = p->tp.p; oa.near_vid = w.prim.p;
     } else {
         // :97 target.operations.closestPointOnSurface(currentMeshPoint)
@@ -898,12 +910,7 @@ extern "C" int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t dire
         oa.m = md; oa.prm = p->prm; oa.C = C; oa.theta = dth.p; oa.X = w.X.p; oa.iso = 1; oa.iso_sigma2 = sigma2;
         if (tsamp) {
             w.prim.ensure(tot);
-            if (!launch_nearest_vertex_brute(m->N, C, w.X.p, n, tmp.tp.p, 0, m->scale, w.prim.p, nullptr, s)) {
-                bvh_refit(m->vert_bvh, C, w.X.p, m->N, nullptr, s);
-                NearestArgs a;
-                a.bvh = &m->vert_bvh; a.X = w.X.p; a.N = m->N; a.C = C; a.nq = n; a.q = tmp.tp.p; a.out_prim = w.prim.p;
-                launch_nearest(a, s);
-            }
+            nearest_model_vertex(m, C, w.X.p, n, tmp.tp.p, 0, nullptr, w.prim.p, s);
             oa.tp = tmp.tp.p; oa.near_vid = w.prim.p;
         } else {
             w.cp.ensure(3 * tot);
@@ -1039,13 +1046,7 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
                 // CollectiveAverage...:58-59: id of the nearest vertex of the MODEL sample, looked up in the
                 // TARGET's boundary table
                 w.prim.ensure(tot); w.skip_t2m.ensure(tot);
-                if (!launch_nearest_vertex_brute(m->N, C, d_X, e->n_tp, w.cp_t2m.p, 1, m->scale, w.prim.p, nullptr, s)) {
-                    bvh_refit(m->vert_bvh, C, d_X, m->N, nullptr, s);
-                    NearestArgs v;
-                    v.bvh = &m->vert_bvh; v.X = d_X; v.N = m->N; v.C = C; v.nq = e->n_tp; v.q = w.cp_t2m.p; v.q_per_chain = 1;
-                    v.out_prim = w.prim.p;
-                    launch_nearest(v, s);
-                }
+                nearest_model_vertex(m, C, d_X, e->n_tp, w.cp_t2m.p, 1, nullptr, w.prim.p, s);
                 launch_lookup_flags((int64_t)tot, w.prim.p, t->boundary.p, t->Nt, w.skip_t2m.p, s);
                 ra.skip_t2m = w.skip_t2m.p;
             }

@@ -581,6 +581,127 @@ __global__ void __launch_bounds__(128) k_nearest_vertex_brute(int N, int C, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// nearest vertex of a per-chain mesh through a vertex BVH that never leaves the SM: one CTA per chain stages the chain's
+// vertices in shared memory, refits the reference-topology LBVH bottom-up into shared memory (level-synchronous, one
+// __syncthreads per level instead of an L2 round trip) and walks it for the chain's queries, seeded with the previous
+// answer of each query. Same boxes, same traversal order and tie rule as bvh_refit + k_nearest<points, dynamic>, so
+// the results are identical; it replaces a 184 MB write + read of per-chain node boxes (C = 2368) by 78 KB of shared
+// memory per CTA.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nearest_vertex_tree(int n, const int *__restrict__ prim, const int2 *__restrict__ children,
+                                                             const int *__restrict__ order, const int *__restrict__ level_off,
+                                                             int n_levels, const double *__restrict__ X, int N, float slack,
+                                                             long long nq, const double *__restrict__ q, int q_per_chain,
+                                                             int *__restrict__ seed_slot, int *__restrict__ out_prim,
+                                                             double *__restrict__ out_d2) {
+    extern __shared__ double smt[];
+    double *sx = smt;                                              // [3 N] vertices of this chain
+    float *sbox = reinterpret_cast<float *>(smt + 3 * (size_t)N);  // [n - 1][6] boxes of the internal nodes (lo, hi)
+    const int c = blockIdx.x;
+    const double *Xc = X + (size_t)c * N * 3;
+    for (int e0 = threadIdx.x; e0 < 3 * N; e0 += 8 * blockDim.x) {
+        double tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; tmp[u] = e < 3 * N ? __ldg(Xc + e) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; if (e < 3 * N) sx[e] = tmp[u]; }
+    }
+    __syncthreads();
+    // box of child `ch` of an internal node: an internal node's box from shared memory, a leaf's from its vertex
+    auto child_box = [&](int ch, float (&b)[6]) {
+        if (ch >= 0) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) b[k] = sbox[6 * ch + k];
+        } else {
+            const double *v = sx + 3 * __ldg(&prim[~ch]);
+            b[0] = __double2float_rd(v[0]) - slack; b[1] = __double2float_rd(v[1]) - slack; b[2] = __double2float_rd(v[2]) - slack;
+            b[3] = __double2float_ru(v[0]) + slack; b[4] = __double2float_ru(v[1]) + slack; b[5] = __double2float_ru(v[2]) + slack;
+        }
+    };
+    for (int lev = 0; lev < n_levels; lev++) {
+        const int k1 = __ldg(&level_off[lev + 1]);
+        for (int k = __ldg(&level_off[lev]) + threadIdx.x; k < k1; k += blockDim.x) {
+            const int node = __ldg(&order[k]);
+            const int2 ch = __ldg(&children[node]);
+            float l[6], r[6];
+            child_box(ch.x, l);
+            child_box(ch.y, r);
+#pragma unroll
+            for (int d = 0; d < 3; d++) { sbox[6 * node + d] = fminf(l[d], r[d]); sbox[6 * node + 3 + d] = fmaxf(l[3 + d], r[3 + d]); }
+        }
+        __syncthreads();
+    }
+    for (long long i = threadIdx.x; i < nq; i += blockDim.x) {
+        const long long g = (long long)c * nq + i;
+        const double *src = q + ((q_per_chain ? (size_t)c * nq : 0) + i) * 3;
+        const double qx = src[0], qy = src[1], qz = src[2];
+        const float fx = (float)qx, fy = (float)qy, fz = (float)qz;
+        double bd2 = INFINITY;
+        int bprim = 0x7fffffff, bslot = -1;
+        float best = INFINITY;
+        auto leaf = [&](int slot) {
+            const int p = __ldg(&prim[slot]);
+            const double dx = qx - sx[3 * p], dy = qy - sx[3 * p + 1], dz = qz - sx[3 * p + 2];
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < bd2 || (d2 == bd2 && p < bprim)) { bd2 = d2; bprim = p; bslot = slot; }
+            best = __double2float_ru(bd2);
+        };
+        int stack_n[kStack];
+        float stack_d[kStack];
+        int sp = 0, node = 0;
+        if (!(qx == qx && qy == qy && qz == qz)) node = 0x7ffffffe;  // NaN query: no traversal, NaN result
+        else if (seed_slot) {
+            const int s0 = seed_slot[g];
+            if ((unsigned)s0 < (unsigned)n) leaf(s0);
+        }
+        while (node != 0x7ffffffe) {
+            if (node < 0) {
+                leaf(~node);
+            } else {
+                const int2 ch = __ldg(&children[node]);
+                float l[6], r[6];
+                child_box(ch.x, l);
+                child_box(ch.y, r);
+                const float dl = box_d2(l[0], l[1], l[2], l[3], l[4], l[5], fx, fy, fz);
+                const float dr = box_d2(r[0], r[1], r[2], r[3], r[4], r[5], fx, fy, fz);
+                const bool hl = dl <= best, hr = dr <= best;
+                if (hl && hr) {
+                    int near = ch.x, far = ch.y;
+                    float dfar = dr;
+                    if (dr < dl) { near = ch.y; far = ch.x; dfar = dl; }
+                    if (sp < kStack) { stack_n[sp] = far; stack_d[sp] = dfar; sp++; }
+                    node = near;
+                    continue;
+                } else if (hl) { node = ch.x; continue; }
+                else if (hr) { node = ch.y; continue; }
+            }
+            node = 0x7ffffffe;
+            while (sp > 0) {
+                --sp;
+                if (stack_d[sp] <= best) { node = stack_n[sp]; break; }
+            }
+        }
+        if (bprim == 0x7fffffff) { bd2 = NAN; bprim = -1; }
+        if (seed_slot) seed_slot[g] = bslot;
+        if (out_prim) out_prim[g] = bprim;
+        if (out_d2) out_d2[g] = bd2;
+    }
+}
+
+// false (nothing launched) when the tree does not fit shared memory or has no level schedule
+bool launch_nearest_vertex_tree(const Bvh &b, int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain,
+                                int *d_seed, int *d_prim, double *d_d2, cudaStream_t s) {
+    size_t smem = sizeof(double) * 3 * (size_t)N + sizeof(float) * 6 * (size_t)(b.n - 1);
+    if (b.prim_kind != 1 || b.n_levels <= 0 || b.n != N || smem > 110 * 1024 || C <= 0 || nq <= 0) return false;
+    ProfScope _ps(ST_NEAREST_DYNAMIC, s);
+    ICP_CUDA(cudaFuncSetAttribute(k_nearest_vertex_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_nearest_vertex_tree<<<C, 256, smem, s>>>(b.n, b.prim.p, b.children.p, b.order.p, b.level_off.p, b.n_levels, d_X, N, b.slack,
+                                               (long long)nq, d_q, q_per_chain, d_seed, d_prim, d_d2);
+    ICP_CUDA(cudaGetLastError());
+    return true;
+}
+
 bool launch_nearest_vertex_brute(int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, double scale,
                                  int *d_prim, double *d_d2, cudaStream_t s) {
     size_t smem = sizeof(double) * 3 * (size_t)((N + 1) & ~1) + sizeof(float) * 3 * (size_t)((N + 1) & ~1);

@@ -161,6 +161,10 @@ struct QuerySort {
 // like launch_nearest for free query points; batches >= 16384 are processed in Morton order (lo / hi: bounding box of
 // the structure). Results are written in the caller's order either way.
 void launch_nearest_sorted(NearestArgs a, QuerySort &qs, const double lo[3], const double hi[3], cudaStream_t s);
+// nearest vertex of C per-chain meshes X[C][N][3] through the model's vertex BVH refitted in shared memory (one CTA per
+// chain); d_seed (nullable) [C][nq] carries each query's previous leaf slot. false: does not fit, nothing launched
+bool launch_nearest_vertex_tree(const Bvh &b, int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain,
+                                int *d_seed, int *d_prim, double *d_d2, cudaStream_t s);
 // brute-force nearest vertex of C small meshes X[C][N][3] (FP32 screening + exact FP64); returns false (nothing
 // launched) when N is too large for the shared-memory tile, in which case the caller uses the vertex BVH
 bool launch_nearest_vertex_brute(int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, double scale,
