@@ -84,6 +84,7 @@ _SIGS = {
     "icp_eval_log_value": [_h, C.c_int32, _dp, _dp, _ip],
     "icp_eval_prior": [_h, C.c_int32, _dp, _dp],
     "icp_registration_metrics": [_h, _h, C.c_int32, _dp, _dp],
+    "icp_posterior_variability": [_h, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _dp],
     "icp_chain_create": [_h, _h, C.POINTER(Component), C.c_int32, _h, C.c_int32, C.POINTER(_h)],
     "icp_chain_destroy": [_h],
     "icp_chain_run": [_h, C.c_int32, C.c_int32, _dp, C.POINTER(ChainIO)],

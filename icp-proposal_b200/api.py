@@ -17,6 +17,7 @@ src/main/scala of the reference.
   SamplingRegistration                                                      api/sampling/SamplingRegistration.scala
   JSONAcceptRejectLogger, jsonLogFormat                                     api/sampling/loggers/JSONAcceptRejectLogger.scala
   IcpBasedSurfaceFitting, RegistrationComparison                           api/other/*.scala
+  LogHelper, PosteriorVariability                                           apps/util/{LogHelper,PosteriorVariability}.scala
 
 Only O(K) bookkeeping happens here (as it does on the JVM in the reference); everything that touches a mesh
 or a K x K matrix runs on the GPU. There is no CPU fallback.
@@ -512,6 +513,65 @@ class JSONAcceptRejectLogger:
     def getBestFittingParsFromJSON(self):
         best = max((l for l in self.loadLog() if l.status), key=lambda l: l.logvalue["product"])
         return self.sampleToModelParameters(best)
+
+
+# ---- posterior variability from a chain log ------------------------------------------------------------------------
+class LogHelper:
+    """apps/util/LogHelper.scala:25-42."""
+
+    @staticmethod
+    def samplesFromLog(log: Sequence[jsonLogFormat], takeEveryN: int = 50, total: int = 100, burnIn: int = 0):
+        def getLogIndex(i):
+            while not log[i].status:
+                i -= 1
+                if i < 0:
+                    raise IndexError("no accepted sample at or before the requested log index")
+            return i
+        filtered = [(log[j], j) for j in (getLogIndex(i) for i in range(burnIn, min(len(log), total), takeEveryN))]
+        return filtered[:min(total, len(filtered))]
+
+    @staticmethod
+    def logSamples2thetas(log: Sequence[jsonLogFormat]) -> np.ndarray:
+        return np.stack([JSONAcceptRejectLogger.sampleToModelParameters(l).allParameters for l in log])
+
+    @staticmethod
+    def logSamples2shapes(model: "StatisticalMeshModel", log: Sequence[jsonLogFormat]) -> np.ndarray:
+        """One batched device reconstruction instead of a transformedMesh call per entry: S x N x 3."""
+        return model.reconstruct(LogHelper.logSamples2thetas(log))
+
+
+class PosteriorVariability:
+    """apps/util/PosteriorVariability.scala:26-74. The reference takes the reconstructed meshes; here the samples stay
+    parameter vectors (a log, or an S x (K+10) array) and reconstruction, normals and the per-vertex reduction run on
+    the device in one call (icp_posterior_variability). `ref` is the parameter vector whose mesh carries the colour map
+    (the reference passes the best sample's mesh); None = the model's reference mesh."""
+
+    @staticmethod
+    def _thetas(samples):
+        if len(samples) and isinstance(samples[0], jsonLogFormat):
+            return LogHelper.logSamples2thetas(samples)
+        if len(samples) and isinstance(samples[0], ModelFittingParameters):
+            return np.stack([t.allParameters for t in samples])
+        return np.asarray(samples, float)
+
+    @staticmethod
+    def _ref(ref):
+        return ref.allParameters if isinstance(ref, ModelFittingParameters) else ref
+
+    @staticmethod
+    def computeDistanceMapFromMeshesTotal(model, samples, ref=None) -> np.ndarray:
+        return core.posterior_variability(model, PosteriorVariability._thetas(samples), True, None)["total_variance"]
+
+    @staticmethod
+    def computeDistanceMapFromMeshesNormal(model, samples, ref=None, sumNormals: bool = True) -> np.ndarray:
+        return core.posterior_variability(model, PosteriorVariability._thetas(samples), sumNormals,
+                                          None if sumNormals else PosteriorVariability._ref(ref))["normal_variance"]
+
+    @staticmethod
+    def statistics(model, samples, ref=None, sumNormals: bool = True):
+        """mean, covariance, total and normal variance in one device pass."""
+        return core.posterior_variability(model, PosteriorVariability._thetas(samples), sumNormals,
+                                          None if sumNormals else PosteriorVariability._ref(ref))
 
 
 # ---- Metropolis-Hastings -----------------------------------------------------------------------------------------

@@ -252,6 +252,21 @@ def registration_metrics(model: Model, target: Target, theta):
     return out
 
 
+def posterior_variability(model: Model, thetas, sum_normals=True, theta_ref=None):
+    """icp_posterior_variability: dict(mean N x 3, cov N x 3 x 3, total_variance N, normal_variance N)."""
+    th, s = model._theta(thetas)
+    n = model.N
+    mean, cov, tot, nrm = np.empty((n, 3)), np.empty((n, 3, 3)), np.empty(n), np.empty(n)
+    ref = None
+    if theta_ref is not None:
+        ref, one = model._theta(theta_ref)
+        if one != 1:
+            raise ValueError("theta_ref must be a single parameter vector")
+    check(model.lib.icp_posterior_variability(model.h, s, dptr(th), 1 if sum_normals else 0, dptr(ref) if ref is not None else None,
+                                              dptr(mean), dptr(cov), dptr(tot), dptr(nrm)), model.ctx.h)
+    return dict(mean=mean, cov=cov, total_variance=tot, normal_variance=nrm)
+
+
 class Chain:
     """Fused Metropolis-Hastings runner (Scalismo MetropolisHastings + MixtureProposal on the device)."""
 

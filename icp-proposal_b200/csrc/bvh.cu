@@ -204,6 +204,17 @@ void bvh_refit_atomic(Bvh &b, int instances, const double *d_X, int N, const int
     ICP_CUDA(cudaGetLastError());
 }
 
+// static structures: the three float4 of child boxes and the child links of a node in one aligned 64-byte record
+__global__ void k_pack_nodes(int n_internal, const int2 *__restrict__ children, const float4 *__restrict__ nodes,
+                             float4 *__restrict__ packed) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    packed[4 * i] = nodes[3 * i];
+    packed[4 * i + 1] = nodes[3 * i + 1];
+    packed[4 * i + 2] = nodes[3 * i + 2];
+    packed[4 * i + 3] = make_float4(__int_as_float(children[i].x), __int_as_float(children[i].y), 0.f, 0.f);
+}
+
 void bvh_build(Bvh &b, int prim_kind, int n_prims, const double *d_verts, const int *d_tris, double scale,
                cudaStream_t s) {
     ICP_REQUIRE(n_prims >= 1, "bvh_build: empty primitive set");
@@ -282,6 +293,9 @@ void bvh_build(Bvh &b, int prim_kind, int n_prims, const double *d_verts, const 
         ICP_CUDA(cudaStreamSynchronize(s));
     }
     bvh_refit_atomic(b, 1, d_verts, nv_needed, d_tris, s);
+    b.packed.alloc((size_t)(n - 1) * 4);
+    k_pack_nodes<<<(n - 1 + threads - 1) / threads, threads, 0, s>>>(n - 1, b.children.p, b.nodes.p, b.packed.p);
+    ICP_CUDA(cudaGetLastError());
     ICP_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -375,9 +389,16 @@ __device__ __forceinline__ float box_d2(float lx, float ly, float lz, float hx, 
 }
 
 constexpr int kStack = 64;
+constexpr int kStackShared = 12;   // stack entries per thread kept in shared memory; deeper entries spill to local memory
+constexpr int kNearestThreads = 128;
+constexpr int kDone = 0x7ffffffe;
 
+// Traversal in two alternating phases per warp ("while-while" with postponed leaves): every lane first descends through
+// internal nodes until it holds a leaf (or has nothing left), then the warp reconverges and all lanes holding a leaf run
+// the exact FP64 primitive test together. Static structures read one 64-byte packed node (child boxes + child links);
+// per-chain (refitted) structures read the shared topology and their own boxes.
 template <int PRIM, bool DYNAMIC>
-__global__ void __launch_bounds__(128) k_nearest(int n, const int2 *__restrict__ children,
+__global__ void __launch_bounds__(kNearestThreads) k_nearest(int n, const int2 *__restrict__ children,
                                                  const float4 *__restrict__ nodes, const int *__restrict__ prim,
                                                  const double *__restrict__ prim_data, const double *__restrict__ X,
                                                  const int *__restrict__ tris, int N, int C, long long nq,
@@ -386,8 +407,11 @@ __global__ void __launch_bounds__(128) k_nearest(int n, const int2 *__restrict__
                                                  const int *__restrict__ perm, int *__restrict__ seed_slot,
                                                  int *__restrict__ out_prim, int *__restrict__ out_feat,
                                                  double *__restrict__ out_cp, double *__restrict__ out_d2) {
+    __shared__ int s_stack_n[kStackShared][kNearestThreads];
+    __shared__ float s_stack_d[kStackShared][kNearestThreads];
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nq * C) return;
+    const bool live = g < nq * C;
+    if (!live) g = nq * C - 1;   // idle lanes stay in the warp-synchronous loop, write nothing
     int c = (int)(g / nq);
     long long i = g % nq;
     if (perm) { i = perm[i]; g = (long long)c * nq + i; }  // spatially sorted processing order, results in caller order
@@ -405,10 +429,11 @@ __global__ void __launch_bounds__(128) k_nearest(int n, const int2 *__restrict__
     Hit h;
     h.d2 = INFINITY; h.x = h.y = h.z = 0.0; h.prim = 0x7fffffff; h.feat = -1; h.slot = -1;
     float best = INFINITY;
-    int stack_n[kStack];
-    float stack_d[kStack];
+    int stack_n[kStack - kStackShared];
+    float stack_d[kStack - kStackShared];
     int sp = 0, node = 0;
-    if (!(qx == qx && qy == qy && qz == qz)) node = 0x7ffffffe;  // NaN query: no traversal, NaN result
+    const int tid = threadIdx.x;
+    if (!live || !(qx == qx && qy == qy && qz == qz)) node = kDone;  // NaN query: no traversal, NaN result
     else if (seed_slot) {
         // upper bound from the primitive that answered this query last time; ties still resolve to the lowest index
         // because subtrees are only pruned when their lower bound exceeds the best distance
@@ -418,13 +443,31 @@ __global__ void __launch_bounds__(128) k_nearest(int n, const int2 *__restrict__
             best = __double2float_ru(h.d2);
         }
     }
-    while (node != 0x7ffffffe) {
-        if (node < 0) {
-            leaf_test<PRIM, DYNAMIC>(~node, prim, prim_data, Xi, tris, qx, qy, qz, h);
-            best = __double2float_ru(h.d2);
-        } else {
-            int2 ch = __ldg(&children[node]);
-            float4 a = __ldg(&nd[3 * node]), b = __ldg(&nd[3 * node + 1]), cc = __ldg(&nd[3 * node + 2]);
+    auto pop = [&]() {
+        int nn = kDone;
+        while (sp > 0) {
+            --sp;
+            float d;
+            int cand;
+            if (sp < kStackShared) { d = s_stack_d[sp][tid]; cand = s_stack_n[sp][tid]; }
+            else { d = stack_d[sp - kStackShared]; cand = stack_n[sp - kStackShared]; }
+            if (d <= best) { nn = cand; break; }
+        }
+        return nn;
+    };
+    while (true) {
+        while ((unsigned)node < (unsigned)kDone) {   // internal node
+            int2 ch;
+            float4 a, b, cc;
+            if (DYNAMIC) {
+                ch = __ldg(&children[node]);
+                a = __ldg(&nd[3 * node]); b = __ldg(&nd[3 * node + 1]); cc = __ldg(&nd[3 * node + 2]);
+            } else {
+                const float4 *pn = nodes + 4 * (size_t)node;
+                a = __ldg(pn); b = __ldg(pn + 1); cc = __ldg(pn + 2);
+                const float4 l = __ldg(pn + 3);
+                ch = make_int2(__float_as_int(l.x), __float_as_int(l.y));
+            }
             float dl = box_d2(a.x, a.y, a.z, a.w, b.x, b.y, fx, fy, fz);
             float dr = box_d2(b.z, b.w, cc.x, cc.y, cc.z, cc.w, fx, fy, fz);
             bool hl = dl <= best, hr = dr <= best;
@@ -432,19 +475,22 @@ __global__ void __launch_bounds__(128) k_nearest(int n, const int2 *__restrict__
                 int near = ch.x, far = ch.y;
                 float dfar = dr;
                 if (dr < dl) { near = ch.y; far = ch.x; dfar = dl; }
-                if (sp < kStack) { stack_n[sp] = far; stack_d[sp] = dfar; sp++; }
+                if (sp < kStackShared) { s_stack_n[sp][tid] = far; s_stack_d[sp][tid] = dfar; sp++; }
+                else if (sp < kStack) { stack_n[sp - kStackShared] = far; stack_d[sp - kStackShared] = dfar; sp++; }
                 node = near;
-                continue;
-            } else if (hl) { node = ch.x; continue; }
-            else if (hr) { node = ch.y; continue; }
+            } else if (hl) node = ch.x;
+            else if (hr) node = ch.y;
+            else node = pop();
         }
-        // pop
-        node = 0x7ffffffe;
-        while (sp > 0) {
-            --sp;
-            if (stack_d[sp] <= best) { node = stack_n[sp]; break; }
+        const bool at_leaf = node != kDone;
+        if (!__any_sync(0xffffffffu, at_leaf)) break;
+        if (at_leaf) {
+            leaf_test<PRIM, DYNAMIC>(~node, prim, prim_data, Xi, tris, qx, qy, qz, h);
+            best = __double2float_ru(h.d2);
+            node = pop();
         }
     }
+    if (!live) return;
     if (h.prim == 0x7fffffff) { h.d2 = NAN; h.x = h.y = h.z = NAN; h.prim = -1; }
     if (seed_slot) seed_slot[g] = h.slot;
     if (out_prim) out_prim[g] = h.prim;
@@ -459,10 +505,10 @@ void launch_nearest(const NearestArgs &a, cudaStream_t s) {
     if (total <= 0) return;
     const Bvh &b = *a.bvh;
     bool dynamic = a.prim_data == nullptr;
-    int threads = 128;
+    int threads = kNearestThreads;
     unsigned blocks = (unsigned)((total + threads - 1) / threads);
 #define ICP_LAUNCH_NEAREST(P, D)                                                                                  \
-    k_nearest<P, D><<<blocks, threads, 0, s>>>(b.n, b.children.p, b.nodes.p, b.prim.p, a.prim_data, a.X, a.tris, \
+    k_nearest<P, D><<<blocks, threads, 0, s>>>(b.n, b.children.p, (D) ? b.nodes.p : b.packed.p, b.prim.p, a.prim_data, a.X, a.tris, \
                                                a.N, a.C, (long long)a.nq, a.q, a.q_per_chain, a.Xq, a.q_ids,     \
                                                a.Nq, a.perm, a.seed_slot, a.out_prim, a.out_feat, a.out_cp, a.out_d2)
     if (b.prim_kind == 0) {

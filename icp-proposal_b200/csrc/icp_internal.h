@@ -110,6 +110,7 @@ struct Bvh {
     DevBuf<int> parent;      // [2n-1]: internal nodes then leaves (n-1+slot)
     DevBuf<int> prim;        // [n]
     DevBuf<float4> nodes;    // [instances][n-1][3] child boxes
+    DevBuf<float4> packed;   // [n-1][4] boxes of the build-time positions + child links in one 64-byte record (static queries)
     DevBuf<float4> nodebox;  // scratch [instances][2n-1][2] full boxes (lo, hi)
     DevBuf<int> counters;    // scratch [instances][n-1] (atomic refit)
     DevBuf<int> order, level_off;  // internal nodes by increasing height + level boundaries (level-synchronous refit)

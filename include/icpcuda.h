@@ -178,6 +178,17 @@ int32_t icp_eval_prior(icp_model m, int32_t C, const double *theta, double *out)
  * (api/other/RegistrationComparison.scala:24-49): per chain {avg, hausdorff, avg_boundary_aware,
  * max_boundary_aware} between transformedMesh(theta) and the target; out C x 4. */
 int32_t icp_registration_metrics(icp_model m, icp_target t, int32_t C, const double *theta, double *out);
+/* PosteriorVariability.computeDistanceMapFromMeshesTotal / ...Normal (apps/util/PosteriorVariability.scala:30-73)
+ * over the shapes LogHelper.logSamples2shapes reconstructs from S logged parameter vectors
+ * (apps/util/LogHelper.scala:39-41): per model vertex the sample mean (mean: N x 3), the sample covariance with
+ * divisor S - 1 (cov: N x 9 row-major), its trace (total_variance: N, the "Total" colour map) and the variance of
+ * the samples along a direction n (normal_variance: N, the "Normal" map). sum_normals != 0: n = mean over the
+ * samples of their unit vertex normals, not re-normalised (:59-60); sum_normals == 0: n = vertex normal of `ref`
+ * = transformedMesh(theta_ref), or of the model's reference mesh when theta_ref is NULL (:62-63). Any output pointer
+ * may be NULL. S == 1 yields NaN variances like the reference (0 * 1/0). */
+int32_t icp_posterior_variability(icp_model m, int32_t S, const double *theta, int32_t sum_normals,
+                                  const double *theta_ref, double *mean, double *cov, double *total_variance,
+                                  double *normal_variance);
 
 /* ---- (7) fused Metropolis-Hastings runner ---------------------------------------------------- */
 /* Scalismo MetropolisHastings.next + MixtureProposal, driven from

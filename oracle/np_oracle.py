@@ -231,3 +231,52 @@ def eval_hausdorff(model, tverts, ttris, rate, theta):
     _, _, b = closest_point_on_triangles(tverts, cur, model.tris)
     hd = np.sqrt(max(a.max(), b.max()))
     return np.log(rate) - rate * hd
+
+
+# ---- posterior variability maps -------------------------------------------
+
+def samples_from_log(status, take_every_n=50, total=100, burn_in=0):
+    """apps/util/LogHelper.scala:27-37: indices burn_in, burn_in + n, ... below min(len, total), each walked back to
+    the last accepted entry (a rejected entry carries no parameters); at most `total` of them."""
+    def get_log_index(i):
+        while not status[i]:
+            i -= 1          # the reference recurses to i - 1 (and fails below index 0, as this does)
+            if i < 0:
+                raise IndexError("no accepted sample at or before the requested index")
+        return i
+    idx = [get_log_index(i) for i in range(burn_in, min(len(status), total), take_every_n)]
+    return idx[:min(total, len(idx))]
+
+
+def posterior_variability(meshes, tris, ref_verts=None, sum_normals=True):
+    """apps/util/PosteriorVariability.scala:30-73, loops kept as the reference writes them (per point id, folds over
+    the samples): returns (mean N x 3, cov N x 3 x 3, total N, normal N)."""
+    meshes = [np.asarray(m, float) for m in meshes]
+    S, N = len(meshes), len(meshes[0])
+    normals = [vertex_normals(m, tris) for m in meshes] if sum_normals else None
+    ref_n = None if sum_normals else vertex_normals(np.asarray(ref_verts, float), tris)
+    mean, cov, total, along = np.zeros((N, 3)), np.zeros((N, 3, 3)), np.zeros(N), np.zeros(N)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv1 = np.float64(1.0) / np.float64(S - 1)
+        for pid in range(N):
+            samples = [m[pid] for m in meshes]
+            mu = np.zeros(3)
+            for s in samples:
+                mu = mu + s
+            mu = mu * (1.0 / S)                                   # :42 / :58
+            c = np.zeros((3, 3))
+            for s in samples:
+                c = c + np.outer(s - mu, s - mu)                  # :43
+            c = c * inv1
+            if sum_normals:
+                n = np.zeros(3)
+                for nm in normals:
+                    n = n + nm[pid] / np.linalg.norm(nm[pid])     # :60-61 (unit normals, mean not re-normalised)
+                n = n * (1.0 / S)
+            else:
+                n = ref_n[pid] / np.linalg.norm(ref_n[pid])       # :64
+            acc = 0.0
+            for s in samples:
+                acc = acc + float(n @ (s - mu)) ** 2              # :66
+            mean[pid], cov[pid], total[pid], along[pid] = mu, c, np.trace(c), acc * inv1
+    return mean, cov, total, along

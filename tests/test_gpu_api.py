@@ -109,3 +109,42 @@ def test_deterministic_icp(setup):
     d = np.sqrt(target.closest_point_surface(mesh)[3])
     d0 = np.sqrt(target.closest_point_surface(m["ref"])[3])
     assert d.mean() < 0.25 * d0.mean()
+
+
+@pytest.mark.parametrize("sum_normals", [True, False])
+def test_posterior_variability_matches_oracle(setup, sum_normals):
+    """icp_posterior_variability against the loop-for-loop restatement of
+    apps/util/PosteriorVariability.scala on the shapes LogHelper.logSamples2shapes would hand it."""
+    from oracle import np_oracle as npo
+    m, model, target, om, ot = setup
+    K = model.rank
+    rng = np.random.default_rng(21)
+    S = 37
+    thetas = np.zeros((S, 10 + K)); thetas[:, 0] = 1.0
+    thetas[:, 10:] = rng.normal(0, 0.4, (S, K))
+    thetas[:, 1:4] = rng.normal(0, 0.5, (S, 3)); thetas[:, 4:7] = rng.normal(0, 0.01, (S, 3)); thetas[:, 7:10] = m["ref"].mean(0)
+    ref = thetas[5]
+    meshes = [om.transformed_mesh(t) for t in thetas]
+    want = npo.posterior_variability(meshes, m["cells"], ref_verts=om.transformed_mesh(ref), sum_normals=sum_normals)
+    got = api.PosteriorVariability.statistics(model, thetas, ref=api.ModelFittingParameters.from_vector(ref), sumNormals=sum_normals)
+    np.testing.assert_allclose(got["mean"], want[0], rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(got["cov"], want[1], rtol=1e-5, atol=1e-10)       # tolerance of BASELINE.json; observed ~1e-12
+    np.testing.assert_allclose(got["total_variance"], want[2], rtol=1e-9)
+    np.testing.assert_allclose(got["normal_variance"], want[3], rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(api.PosteriorVariability.computeDistanceMapFromMeshesTotal(model, thetas), got["total_variance"])
+    np.testing.assert_array_equal(api.PosteriorVariability.computeDistanceMapFromMeshesNormal(
+        model, thetas, api.ModelFittingParameters.from_vector(ref), sumNormals=sum_normals), got["normal_variance"])
+    # through a chain log: accepted entries only, walked back from rejected ones (LogHelper.samplesFromLog)
+    log = [api.jsonLogFormat(i, "p", {"product": 0.0}, i % 3 != 1, t[1:10].tolist() if i % 3 != 1 else [], t[10:].tolist() if i % 3 != 1 else [], "")
+           for i, t in enumerate(thetas)]
+    picked = api.LogHelper.samplesFromLog(log, takeEveryN=2, total=30, burnIn=3)
+    idx = npo.samples_from_log([l.status for l in log], 2, 30, 3)
+    assert [j for _, j in picked] == idx
+    shapes = api.LogHelper.logSamples2shapes(model, [l for l, _ in picked])
+    np.testing.assert_allclose(shapes, np.stack([meshes[j] for j in idx]), rtol=1e-12, atol=1e-10)
+    tot = api.PosteriorVariability.computeDistanceMapFromMeshesTotal(model, [l for l, _ in picked])
+    np.testing.assert_allclose(tot, npo.posterior_variability([meshes[j] for j in idx], m["cells"])[2], rtol=1e-9)
+    # one sample: NaN like the reference; empty input is an error
+    assert np.isnan(api.PosteriorVariability.computeDistanceMapFromMeshesTotal(model, thetas[:1])).all()
+    with pytest.raises(Exception):
+        api.PosteriorVariability.computeDistanceMapFromMeshesTotal(model, thetas[:0])

@@ -158,6 +158,22 @@ def test_json_logger_format_roundtrip(tmp_path):
     assert lg2.numOfAccepted == 1 and lg2.numOfRejected == 1 and lg2.logStatus[1].logvalue == {"product": 3.0, "prior": 4.0, "distance": 5.0}
 
 
+def test_log_helper_samples_from_log_matches_oracle():
+    """LogHelper.samplesFromLog (apps/util/LogHelper.scala:27-37): the host mirror against the oracle's index walk."""
+    from oracle import np_oracle as npo
+    rng = np.random.default_rng(11)
+    status = [True] + [bool(b) for b in rng.random(199) < 0.4]
+    log = [api.jsonLogFormat(i, "p", {"product": 0.0}, st, [0.0] * 9 if st else [], [float(i)] if st else [], "") for i, st in enumerate(status)]
+    for every, total, burn in ((50, 100, 0), (7, 150, 20), (1, 30, 5), (13, 10000, 199)):
+        got = api.LogHelper.samplesFromLog(log, takeEveryN=every, total=total, burnIn=burn)
+        assert [j for _, j in got] == npo.samples_from_log(status, every, total, burn)
+        assert all(l.status and l.index == j for l, j in got)
+    th = api.LogHelper.logSamples2thetas([l for l, _ in api.LogHelper.samplesFromLog(log, 7, 150, 20)])
+    assert th.shape[1] == 11 and (th[:, 0] == 1.0).all()
+    with pytest.raises(IndexError):
+        api.LogHelper.samplesFromLog([api.jsonLogFormat(0, "p", {}, False, [], [], "")], 1, 1, 0)
+
+
 def test_shard_ranges_cover_all_chains():
     for n, w in ((100, 8), (5, 2), (7, 4), (3, 8), (1184 * 8, 8)):
         spans = [sharding.shard_range(n, r, w) for r in range(w)]

@@ -253,3 +253,36 @@ def test_philox_known_answer():
     assert orc.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2).tolist() == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert orc.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]).tolist() == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_posterior_variability_oracle_against_closed_forms(twin31):
+    """The loop-for-loop restatement of PosteriorVariability.scala against vectorised sample statistics, a known
+    answer (rigidly translated copies: all variance along the translation), and LogHelper's index walk."""
+    m = twin31
+    om = npo.Model(m["ref"], m["cells"], m["basis"], m["variance"])
+    rng = np.random.default_rng(3)
+    thetas = np.zeros((9, 10 + om.K)); thetas[:, 0] = 1.0
+    thetas[:, 10:] = rng.normal(0, 0.5, (9, om.K))
+    X = np.stack([om.transformed_mesh(t) for t in thetas])
+    mean, cov, total, along = npo.posterior_variability(list(X), m["cells"], sum_normals=True)
+    np.testing.assert_allclose(mean, X.mean(0), rtol=1e-13)
+    np.testing.assert_allclose(total, X.var(0, ddof=1).sum(1), rtol=1e-12)
+    d = X - X.mean(0)
+    np.testing.assert_allclose(cov, np.einsum("sni,snj->nij", d, d) / 8, rtol=1e-12, atol=1e-14)
+    nbar = np.stack([npo.vertex_normals(x, m["cells"]) for x in X]).mean(0)
+    np.testing.assert_allclose(along, (np.einsum("ni,sni->sn", nbar, d) ** 2).sum(0) / 8, rtol=1e-12)
+    assert (along <= total * (1 + 1e-12)).all()           # |n| <= 1: the normal part never exceeds the trace
+    # known answer: copies translated along e_z by 0, 1, 2 -> cov = diag(0, 0, 1), normal variance = n_z^2
+    shifted = [m["ref"] + np.array([0, 0, k], float) for k in range(3)]
+    mean, cov, total, along = npo.posterior_variability(shifted, m["cells"], ref_verts=m["ref"], sum_normals=False)
+    np.testing.assert_allclose(total, 1.0, rtol=1e-12)
+    np.testing.assert_allclose(along, npo.vertex_normals(m["ref"], m["cells"])[:, 2] ** 2, rtol=1e-12, atol=1e-15)
+    # a single sample: 0 * (1 / 0) = NaN, as on the JVM
+    assert np.isnan(npo.posterior_variability(shifted[:1], m["cells"], sum_normals=True)[2]).all()
+    # LogHelper.samplesFromLog
+    status = [True, False, False, True, False, True, True, False, False, True]
+    assert npo.samples_from_log(status, take_every_n=2, total=7, burn_in=1) == [0, 3, 5]
+    assert npo.samples_from_log(status, take_every_n=3, total=100, burn_in=0) == [0, 3, 6, 9]
+    assert npo.samples_from_log(status, take_every_n=1, total=3, burn_in=0) == [0, 0, 0]
+    with pytest.raises(IndexError):
+        npo.samples_from_log([False, True], 1, 2, 0)
