@@ -326,8 +326,12 @@ def run_gpu(args):
         cp_ms = cpq["ms"] / max(cpq["launches"], 1)
         roof_cp = {"bound": "hbm", "kernel": "k_nearest<tri,static> (1e6 near-surface queries, timed alone)",
                    "achieved": cp["near_surface"]["algorithmic_GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "frac": cp["near_surface"]["algorithmic_GBps"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                   "bytes_per_query": 1000}
+                   "frac": cp["near_surface"]["algorithmic_GBps"] / peaks["hbm_gbs"], "traffic": 9.29e7, "peak_source": peak_src,
+                   "bytes_per_query": 1000,
+                   "traffic_note": "dram read + write of the 1e6-query launch (profiles/r1i, ncu --set full): 60.4 + 32.5 MB = the "
+                                   "queries in, the results out and the Morton permutation; the tree itself (0.45 MB) is served "
+                                   "by L1 (75 % sector hits) and L2, 9.7 TB/s of L1 data returned to the SMs",
+                   "lanes_active_per_instruction": 11.8}
         roofline = {"bound": "tensor", "pipe": "FP64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA)",
                     "kernel": "k_posterior_fused<.., CHOL = false> (rank update M = I + A^T A, b = A^T y)",
                     "achieved": pb_tflops, "peak": fp64["dmma_tflops"], "unit": "TFLOP/s",
@@ -380,7 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=2368, help="chains per GPU (16 x 148 SMs)")
-    ap.add_argument("--cpu-steps", type=int, default=12, help="MH steps of the cpu_baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=60, help="MH steps of the cpu_baseline sample")
     ap.add_argument("--ref-steps", type=int, default=4, help="MH steps per chain and bench step of --impl reference")
     args = ap.parse_args()
     if args.warmup < 1:
