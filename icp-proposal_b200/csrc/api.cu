@@ -195,7 +195,7 @@ extern "C" int32_t icp_model_create(icp_ctx ctx, int32_t N, int32_t T, int32_t K
     try {
         ICP_REQUIRE(ctx != nullptr && out != nullptr, "null handle");
         CtxLock lock(ctx);
-        ICP_REQUIRE(K >= 1 && K <= 160, "rank K must be in [1, 160]");
+        ICP_REQUIRE(K >= 1 && K <= 224, "rank K must be in [1, 224]");
         ICP_REQUIRE(basis != nullptr && variance != nullptr, "basis / variance are null");
         check_mesh(N, T, ref_xyz, tris);
         for (int j = 0; j < K; j++) ICP_REQUIRE(variance[j] >= 0 && std::isfinite(variance[j]), "variance must be finite and >= 0");
@@ -711,7 +711,7 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
     w.Mp.ensure((size_t)C * (Kp / 8) * (Kp / 8 + 1) / 2 * 64);
     if (!launch_posterior_fused(md, C, od, gfp, w.want_M ? w.M.p : nullptr, d_L, d_mu, d_out_slot, w.status.p, w.Mp.p, w.b.p, s)) {
         launch_posterior_build(md, C, od, w.M.p, w.b.p, s, gfp);
-        launch_cholesky_solve(C, m->K, Kp, w.M.p, w.b.p, d_L, d_mu, d_out_slot, w.status.p, s);
+        launch_cholesky_solve(C, m->K, Kp, w.M.p, w.b.p, d_L, d_mu, d_out_slot, w.status.p, s, w.Mp.p);
     }
 }
 
@@ -923,7 +923,8 @@ extern "C" int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t dire
         ObsDev od{n, w.vid.p, w.F.p, w.y.p, w.nobs.p};
         launch_observations(oa, od, s);
         launch_posterior_build(md, C, od, w.M.p, w.b.p, s);
-        launch_cholesky_solve(C, K, Kp, w.M.p, w.b.p, dL.p, dmu.p, nullptr, w.status.p, s);
+        w.Mp.ensure((size_t)C * (Kp / 8) * (Kp / 8 + 1) / 2 * 64);
+        launch_cholesky_solve(C, K, Kp, w.M.p, w.b.p, dL.p, dmu.p, nullptr, w.status.p, s, w.Mp.p);
     }
     k_std_icp_step<<<C, 128, 0, s>>>(C, K, Kp, step_length, m->S.p, dmu.p, da.p, dout.p);
     ICP_CUDA(cudaGetLastError());

@@ -22,7 +22,7 @@ using namespace icp;
 namespace {
 
 constexpr int kMaxComp = 16;
-constexpr int kMaxNBc = 20;   // Kp <= 160 (icp_model_create enforces it)
+constexpr int kMaxNBc = 28;   // Kp <= 224 (icp_model_create enforces it)
 
 struct CompDev {
     int kind, axis, icp_index;  // icp_index: which ICP posterior set (or -1)
@@ -206,10 +206,10 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
 // the warps deal the rows, a lane owns the columns lane + 32 q, so every load is one contiguous row segment, all lanes of
 // all warps stay busy (a column-per-thread loop leaves the triangle's short columns idle) and 2 x 4 rows are in flight
 // per warp. part: 2 * nwarps * Kp doubles of shared memory.
+template <int kQ>   // column slots per lane: Kp <= 32 kQ
 __device__ void chain_quad_LT2(const double *__restrict__ La, const double *__restrict__ Lb, int Kp, const double *da_sm,
                                const double *db_sm, double *part, double *red, double &qa, double &qb) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    constexpr int kQ = (8 * kMaxNBc + 31) / 32;   // column slots per lane
     double va[kQ], vb[kQ];
 #pragma unroll
     for (int q = 0; q < kQ; q++) va[q] = vb[q] = 0.0;
@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st
                 }
                 __syncthreads();
                 double qf, qb;
-                chain_quad_LT2(st.L + sc * Kp * Kp, st.L + sp * Kp * Kp, Kp, sd, sd2, part, red, qf, qb);
+                if (Kp <= 128) chain_quad_LT2<4>(st.L + sc * Kp * Kp, st.L + sp * Kp * Kp, Kp, sd, sd2, part, red, qf, qb);
+                else chain_quad_LT2<(8 * kMaxNBc + 31) / 32>(st.L + sc * Kp * Kp, st.L + sp * Kp * Kp, Kp, sd, sd2, part, red, qf, qb);
                 __syncthreads();
                 fwd = -0.5 * (K * ICP_LOG_2PI + qf);
                 bwd = -0.5 * (K * ICP_LOG_2PI + qb);

@@ -226,8 +226,9 @@ bool launch_posterior_fused(const ModelDev &m, int C, const ObsDev &o, const Gra
                             double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s);
 // in: M (C x Kp x Kp), b (C x Kp). out: L (lower Cholesky factor, C x Kp x Kp), mu = M^-1 b, status (0 ok)
 // out_slot (nullable): chain c writes L / mu at index out_slot[c] instead of c
+// d_Mp: scratch for the block-packed lower triangle (C x NB (NB + 1) / 2 x 64 doubles), needed when Kp > 160
 void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
-                           const int *d_out_slot, int *d_status, cudaStream_t s);
+                           const int *d_out_slot, int *d_status, cudaStream_t s, double *d_Mp = nullptr);
 // alpha' = alpha + step (S (mu + L^-T z) - alpha); L/mu addressed through per-chain slot indices
 void launch_propose(const ModelDev &m, int C, double step, const double *d_theta, const double *d_z,
                     const double *d_L, const double *d_mu, const int *d_slot, double *d_theta_out, cudaStream_t s);

@@ -376,7 +376,7 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 
 constexpr int kMmaRows = 3 * kPbObs;  // 24 staged rows = 6 k4-steps
 constexpr int kProdWarps = 2;         // producer warps (stage A = F Q into shared memory, accumulate b)
-constexpr int kMaxNB = 20;         // largest supported Kp / 8
+constexpr int kMaxNB = 28;         // largest supported Kp / 8 (K <= 224: the packed factorisation must fit shared memory)
 constexpr int kMaxStagedIds = 4096;  // observation ids staged in shared memory by the producers
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
@@ -553,24 +553,31 @@ __global__ void __launch_bounds__((NWC + kProdWarps) * 32) k_posterior_build_mma
                     yy[0] = yy[1] = yy[2] = 0.0;
                 }
                 const double *q = m.Q + (size_t)3 * (v >= 0 ? v : 0) * Kp + cg;
-                double q0[NBMAX], q1[NBMAX], q2[NBMAX];
-#pragma unroll
-                for (int i = 0; i < NBMAX; i++) {
-                    if (i < NB) { q0[i] = __ldg(q + 8 * i); q1[i] = __ldg(q + Kp + 8 * i); q2[i] = __ldg(q + 2 * Kp + 8 * i); }
-                }
-                if (pass == 0) {  // consumers are done with this buffer
-                    if (buf == 0) named_bar_sync<3>(nthreads); else named_bar_sync<4>(nthreads);
-                }
                 double *dst = sA + buf * bufsz + (RPO * lo) * ld + cg;
+                // column blocks in chunks of kCH: the large-rank instantiation must not hold 3 x 28 basis entries at once
+                constexpr int kCH = NBMAX > 14 ? 7 : NBMAX;
 #pragma unroll
-                for (int i = 0; i < NBMAX; i++) {
-                    if (i < NB) {
-                        double a0 = f[0] * q0[i] + f[1] * q1[i] + f[2] * q2[i];
-                        double a1 = f[3] * q0[i] + f[4] * q1[i] + f[5] * q2[i];
-                        double a2 = f[6] * q0[i] + f[7] * q1[i] + f[8] * q2[i];
-                        if (RPO == 3) { dst[8 * i] = a0; dst[ld + 8 * i] = a1; dst[2 * ld + 8 * i] = a2; }
-                        else dst[8 * i] = a0 * row_scale;
-                        bacc[i] = fma(a0, yy[0], fma(a1, yy[1], fma(a2, yy[2], bacc[i])));
+                for (int h0 = 0; h0 < NBMAX; h0 += kCH) {
+                    double q0[kCH], q1[kCH], q2[kCH];
+#pragma unroll
+                    for (int u = 0; u < kCH; u++) {
+                        const int i = h0 + u;
+                        if (i < NBMAX && i < NB) { q0[u] = __ldg(q + 8 * i); q1[u] = __ldg(q + Kp + 8 * i); q2[u] = __ldg(q + 2 * Kp + 8 * i); }
+                    }
+                    if (pass == 0 && h0 == 0) {  // consumers are done with this buffer
+                        if (buf == 0) named_bar_sync<3>(nthreads); else named_bar_sync<4>(nthreads);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kCH; u++) {
+                        const int i = h0 + u;
+                        if (i < NBMAX && i < NB) {
+                            double a0 = f[0] * q0[u] + f[1] * q1[u] + f[2] * q2[u];
+                            double a1 = f[3] * q0[u] + f[4] * q1[u] + f[5] * q2[u];
+                            double a2 = f[6] * q0[u] + f[7] * q1[u] + f[8] * q2[u];
+                            if (RPO == 3) { dst[8 * i] = a0; dst[ld + 8 * i] = a1; dst[2 * ld + 8 * i] = a2; }
+                            else dst[8 * i] = a0 * row_scale;
+                            bacc[i] = fma(a0, yy[0], fma(a1, yy[1], fma(a2, yy[2], bacc[i])));
+                        }
                     }
                 }
             }
@@ -616,7 +623,8 @@ void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d
             if (NB <= 4) launch_pb_mma<4, 4, 4>(m, C, o, d_M, d_b, total, gf, s);
             else if (NB <= 7) launch_pb_mma<8, 7, 4>(m, C, o, d_M, d_b, total, gf, s);
             else if (NB <= 13) launch_pb_mma<24, 13, 4>(m, C, o, d_M, d_b, total, gf, s);
-            else launch_pb_mma<28, 20, 8>(m, C, o, d_M, d_b, total, gf, s);
+            else if (NB <= 20) launch_pb_mma<28, 20, 8>(m, C, o, d_M, d_b, total, gf, s);
+            else launch_pb_mma<36, 28, 12>(m, C, o, d_M, d_b, total, gf, s);
             ICP_CUDA(cudaGetLastError());
             return;
         }
@@ -1631,11 +1639,35 @@ bool launch_posterior_fused(const ModelDev &m, int C, const ObsDev &o, const Gra
     return true;
 }
 
+// full square M -> the block-packed lower triangle k_cholesky_packed reads (row-major 8 x 8 blocks over the block triangle)
+__global__ void __launch_bounds__(128) k_pack_lower(int Kp, const double *__restrict__ M, double *__restrict__ Mp) {
+    const int NB = Kp >> 3, ntri = NB * (NB + 1) / 2, c = blockIdx.x;
+    const double *Mc = M + (size_t)c * Kp * Kp;
+    double *dst = Mp + (size_t)c * ntri * 64;
+    for (int e = threadIdx.x; e < ntri * 64; e += blockDim.x) {
+        int bi, bj;
+        tri_index(e >> 6, bi, bj);
+        dst[e] = Mc[(size_t)(8 * bi + ((e >> 3) & 7)) * Kp + 8 * bj + (e & 7)];
+    }
+}
+
 void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
-                           const int *d_out_slot, int *d_status, cudaStream_t s) {
+                           const int *d_out_slot, int *d_status, cudaStream_t s, double *d_Mp) {
     ProfScope _ps(ST_CHOLESKY, s);
     if (C <= 0) return;
     static const bool no_mma = getenv("ICPCUDA_NO_DMMA") && getenv("ICPCUDA_NO_DMMA")[0] == '1';
+    if (sizeof(double) * ((size_t)(Kp + 8) * (Kp + 4) + 3 * Kp) > 227 * 1024) {
+        // 160 < Kp <= 224: the padded square does not fit shared memory, the block-packed lower triangle does (one CTA / SM)
+        const int NB = Kp / 8, ntri = NB * (NB + 1) / 2;
+        size_t smem_c = sizeof(double) * ((size_t)ntri * 64 + 4 * Kp);
+        ICP_REQUIRE(d_Mp != nullptr && smem_c <= 227 * 1024 - 64, "rank too large for the shared-memory Cholesky (K <= 224)");
+        k_pack_lower<<<C, 128, 0, s>>>(Kp, d_M, d_Mp);
+        ICP_CUDA(cudaGetLastError());
+        ICP_CUDA(cudaFuncSetAttribute(k_cholesky_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        k_cholesky_packed<<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, nullptr, d_L, d_mu, d_out_slot, d_status);
+        ICP_CUDA(cudaGetLastError());
+        return;
+    }
     if (!no_mma) {
         size_t smem2 = sizeof(double) * ((size_t)(Kp + 8) * (Kp + 4) + 3 * Kp);
         ICP_REQUIRE(smem2 <= 227 * 1024, "rank too large for the shared-memory Cholesky (K <= 160)");

@@ -21,7 +21,7 @@ def femur():
     meshes = np.load(os.path.join(GOLDEN, "femur_meshes.npz"))
     out = {"ref": meshes["ref"].astype(np.float64), "cells": meshes["cells"].astype(np.int32),
            "target": meshes["target_aligned"].astype(np.float64), "target_cells": meshes["target_cells"].astype(np.int32)}
-    for k in ("50", "100"):
+    for k in ("50", "100", "200"):
         g = np.load(os.path.join(GOLDEN, f"femur_gpmm_{k}.npz"))
         out[f"gpmm_{k}"] = {"basis": g["basis"].astype(np.float64), "variance": g["variance"].astype(np.float64)}
     with open(os.path.join(GOLDEN, "femur_golden.json")) as f:

@@ -3,7 +3,7 @@
 
 Inputs  : the reference's own data fixtures (data/femur/*.h5, *.stl, *.json), converted to .npz so
           that they can travel: femur reference mesh, landmark-aligned target
-          (apps/femur/LoadTestData.scala:32-50) and the 50-/100-component GPMMs (rank 51 / 101).
+          (apps/femur/LoadTestData.scala:32-50) and the 50-/100-/200-component GPMMs (rank 51 / 101 / 201).
 Outputs : oracle values on those inputs (oracle/icp_oracle.c, cross-checked against
           oracle/np_oracle.py) for fixed parameter vectors: femur_golden.json.
 PARITY UNPINNED: the reference ships no golden vectors for this path; these pin the
@@ -27,6 +27,7 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 def main():
     m100 = fx.load_gpmm_h5(f"{REF}/femur_gp_model_100-components.h5")
     m50 = fx.load_gpmm_h5(f"{REF}/femur_gp_model_50-components.h5")
+    m200 = fx.load_gpmm_h5(f"{REF}/femur_gp_model_200-components.h5")   # rank 201: the model StdIcpVsChainICP...All.scala:88 opens
     tv, tc = fx.read_binary_stl(f"{REF}/femur_target.stl")
     r, t = fx.rigid_landmark_alignment(fx.read_landmarks_json(f"{REF}/femur_target.json"),
                                        fx.read_landmarks_json(f"{REF}/femur_reference.json"))
@@ -34,11 +35,11 @@ def main():
     np.savez_compressed(f"{OUT}/femur_meshes.npz", ref=m100["ref"].astype(np.float32), cells=m100["cells"],
                         target_raw=tv.astype(np.float32), target_cells=tc, target_aligned=tv_aligned,
                         align_R=r, align_t=t)
-    for name, m in (("femur_gpmm_50", m50), ("femur_gpmm_100", m100)):
+    for name, m in (("femur_gpmm_50", m50), ("femur_gpmm_100", m100), ("femur_gpmm_200", m200)):
         np.savez_compressed(f"{OUT}/{name}.npz", basis=m["basis"].astype(np.float32),
                             variance=m["variance"].astype(np.float32))
     golden = {}
-    for name, m in (("gpmm_50", m50), ("gpmm_100", m100)):
+    for name, m in (("gpmm_50", m50), ("gpmm_100", m100), ("gpmm_200", m200)):
         K = len(m["variance"])
         om = orc.Model(m["ref"], m["cells"], m["basis"], m["variance"])
         ot = orc.Mesh(tv_aligned, tc)

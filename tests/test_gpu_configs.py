@@ -110,12 +110,15 @@ def test_config3_random_init_chains_symmetric_full_mesh(ctx, femur):
     chain.close(); ev.close(); gp.close(); model.close(); tgt.close()
 
 
-def test_config4_hausdorff_chains_on_perturbed_targets(ctx, femur):
+@pytest.mark.parametrize("which", ["gpmm_100", "gpmm_200"])
+def test_config4_hausdorff_chains_on_perturbed_targets(ctx, femur, which):
     """Config 4: random inits (alpha0 = 0 for index 0, else N(0, 0.1 I)) x synthetic perturbed targets, Hausdorff
-    evaluator Exponential(100), config-1 mixture (StdIcpVsChainICPrandomInitComparisonAll.scala:100-160)."""
-    base = _femur(femur, "gpmm_100")
-    K = 101
-    for t_index in range(2):
+    evaluator Exponential(100), config-1 mixture (StdIcpVsChainICPrandomInitComparisonAll.scala:100-160). BASELINE.json
+    names GPMM-100; the shipped main opens the 200-component file (rank 201, :88), which takes the large-rank kernels
+    (rank update with 12 consumer warps, block-packed factorisation at one chain per SM)."""
+    base = _femur(femur, which)
+    K = len(base["variance"])
+    for t_index in range(2 if which == "gpmm_100" else 1):
         target = synth.model_instance(base, np.random.default_rng(100 + t_index).normal(0, 1.0, K))
         target = target + np.random.default_rng(7 + t_index).normal(0, 0.5, target.shape)      # 0.5 mm vertex noise
         m = dict(base, target=target, target_cells=base["cells"])

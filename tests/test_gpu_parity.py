@@ -147,13 +147,13 @@ def test_dynamic_model_queries(ctx, twin31):
 
 
 @pytest.mark.parametrize("direction", [_lib.MODEL_SAMPLING, _lib.TARGET_SAMPLING])
-@pytest.mark.parametrize("fixture", ["twin31", "femur100"])
+@pytest.mark.parametrize("fixture", ["twin31", "femur100", "femur200"])
 def test_icp_posterior_propose_transition(ctx, request, femur, direction, fixture):
     if fixture == "twin31":
         m = request.getfixturevalue("twin31")
     else:
         m = dict(ref=femur["ref"], cells=femur["cells"], target=femur["target"], target_cells=femur["target_cells"],
-                 **femur["gpmm_100"])
+                 **femur["gpmm_100" if fixture == "femur100" else "gpmm_200"])
     K = len(m["variance"])
     model, tgt = _dev(ctx, m)
     om, ot = _orc(m)

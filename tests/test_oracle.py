@@ -178,7 +178,7 @@ def test_fp32_reconstruction_error_exceeds_budget(femur):
 
 def test_golden_femur_values(femur):
     """The oracle reproduces the committed golden values on the reference's femur fixtures."""
-    for key, gk in (("gpmm_50", "gpmm_50"), ("gpmm_100", "gpmm_100")):
+    for key, gk in (("gpmm_50", "gpmm_50"), ("gpmm_100", "gpmm_100"), ("gpmm_200", "gpmm_200")):
         g = femur["golden"][gk]
         m = femur[key]
         K = len(m["variance"])
