@@ -68,10 +68,23 @@ int main(int argc, char **argv) {
         auto res = reg.runfitting(*productDev, "distance", proposal, numOfSamples, theta0, argc > 3 ? argv[3] : "");
         const double pbest = product.logValue(res.best);
 
+        // (3) apps/femur/PosteriorVariabilityToMeshColor.scala:45-52: every 10th logged state after a burn-in of 20 -> shapes ->
+        // per-vertex variability maps, reconstructed and reduced on the device
+        std::vector<ModelFittingParameters> picked;
+        for (auto &e : LogHelper::samplesFromLog(res.log, 10, numOfSamples, 20)) picked.push_back(LogHelper::sampleToModelParameters(*e.first));
+        double meanTotal = 0.0, meanNormal = 0.0;
+        if (picked.size() > 1) {
+            auto maps = PosteriorVariability::statistics(model, picked, true);
+            for (double v : maps.total) meanTotal += v / maps.total.size();
+            for (double v : maps.normal) meanNormal += v / maps.normal.size();
+        }
+
         std::printf("{\"K\": %d, \"product_initial\": %.12g, \"host_mh_steps\": 20, \"host_mh_accepted\": %d, \"product_after_host_mh\": %.12g, "
                     "\"fused_steps\": %d, \"fused_accepted\": %lld, \"fused_best_product\": %.12g, \"fused_best_product_recomputed\": %.12g, "
-                    "\"fused_best_generated_by\": \"%s\"}\n",
-                    K, p0, acc, p20, res.steps, (long long)res.accepted, res.bestProduct, pbest, res.best.generatedBy.c_str());
+                    "\"fused_best_generated_by\": \"%s\", \"variability_samples\": %d, \"mean_total_variance\": %.12g, "
+                    "\"mean_normal_variance\": %.12g}\n",
+                    K, p0, acc, p20, res.steps, (long long)res.accepted, res.bestProduct, pbest, res.best.generatedBy.c_str(),
+                    (int)picked.size(), meanTotal, meanNormal);
         return 0;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());

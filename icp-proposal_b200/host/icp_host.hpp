@@ -391,6 +391,62 @@ private:
     std::string path_;
 };
 
+// ---- posterior variability from a chain log -------------------------------------------------------------------------
+// apps/util/LogHelper.scala:25-42
+struct LogHelper {
+    // indices burnIn, burnIn + takeEveryN, ... below min(log size, total), each walked back to the last accepted entry
+    static std::vector<std::pair<const jsonLogFormat *, int>> samplesFromLog(const std::vector<jsonLogFormat> &log, int takeEveryN = 50,
+                                                                             int total = 100, int burnIn = 0) {
+        std::vector<std::pair<const jsonLogFormat *, int>> out;
+        const int end = std::min((int)log.size(), total);
+        for (int i = burnIn; i < end && (int)out.size() < total; i += takeEveryN) {
+            int j = i;
+            while (!log[j].status)
+                if (--j < 0) throw std::out_of_range("no accepted sample at or before the requested log index");
+            out.emplace_back(&log[j], j);
+        }
+        return out;
+    }
+    // JSONAcceptRejectLogger.sampleToModelParameters (:135-141): scale 1, the logged rigid block and coefficients
+    static ModelFittingParameters sampleToModelParameters(const jsonLogFormat &e) {
+        ModelFittingParameters p;
+        p.allParameters.assign(1, 1.0);
+        p.allParameters.insert(p.allParameters.end(), e.rigid.begin(), e.rigid.end());
+        p.allParameters.insert(p.allParameters.end(), e.coeff.begin(), e.coeff.end());
+        p.generatedBy = e.name;
+        return p;
+    }
+};
+
+// apps/util/PosteriorVariability.scala:26-74 on parameter vectors: reconstruction, normals and the per-vertex reduction run
+// on the device in one call (icp_posterior_variability)
+struct PosteriorVariability {
+    struct Maps { std::vector<double> mean, cov, total, normal; };
+    static Maps statistics(const StatisticalMeshModel &model, const std::vector<ModelFittingParameters> &samples, bool sumNormals = true,
+                           const ModelFittingParameters *ref = nullptr) {
+        const int N = model.numberOfPoints(), L = model.rank() + 10;
+        std::vector<double> th;
+        th.reserve(samples.size() * (size_t)L);
+        for (const auto &s : samples) {
+            if ((int)s.allParameters.size() != L) throw std::invalid_argument("sample of the wrong rank");
+            th.insert(th.end(), s.allParameters.begin(), s.allParameters.end());
+        }
+        Maps m;
+        m.mean.resize((size_t)3 * N); m.cov.resize((size_t)9 * N); m.total.resize(N); m.normal.resize(N);
+        check(icp_posterior_variability(model.handle(), (int32_t)samples.size(), th.data(), sumNormals ? 1 : 0,
+                                        (!sumNormals && ref) ? ref->allParameters.data() : nullptr, m.mean.data(), m.cov.data(),
+                                        m.total.data(), m.normal.data()), model.ctx());
+        return m;
+    }
+    static std::vector<double> computeDistanceMapFromMeshesTotal(const StatisticalMeshModel &model, const std::vector<ModelFittingParameters> &samples) {
+        return statistics(model, samples).total;
+    }
+    static std::vector<double> computeDistanceMapFromMeshesNormal(const StatisticalMeshModel &model, const std::vector<ModelFittingParameters> &samples,
+                                                                  const ModelFittingParameters *ref, bool sumNormals) {
+        return statistics(model, samples, sumNormals, ref).normal;
+    }
+};
+
 // ---- Metropolis-Hastings ---------------------------------------------------------------------------------------------
 // Scalismo MetropolisHastings.next over the per-call (drop-in) classes
 class MetropolisHastings {
@@ -423,6 +479,7 @@ public:
         double bestProduct = -INFINITY;
         int64_t accepted = 0;
         int steps = 0;
+        std::vector<jsonLogFormat> log;   // the chain log in the reference's record layout (also written to jsonName)
     };
     // evaluator: the device evaluator behind evaluators("product") - build it with makeProductEvaluator so that it
     // carries prior x distance (ProductEvaluators.scala:44-47); distanceKey: the key of the distance term in the
@@ -457,11 +514,11 @@ public:
                 r.best.allParameters.assign(thl.begin() + (size_t)s * L, thl.begin() + (size_t)(s + 1) * L);
                 r.best.generatedBy = names[comp[s]];
             }
-            if (!jsonName.empty())
-                logger.append(names[comp[s]], {{"product", vals[3 * s]}, {"prior", vals[3 * s + 1]}, {distanceKey, vals[3 * s + 2]}}, ok,
-                              thl.data() + (size_t)s * L, K);
+            logger.append(names[comp[s]], {{"product", vals[3 * s]}, {"prior", vals[3 * s + 1]}, {distanceKey, vals[3 * s + 2]}}, ok,
+                          thl.data() + (size_t)s * L, K);
         }
         if (!jsonName.empty()) logger.writeLog();
+        r.log = std::move(logger.logStatus);
         return r;
     }
 private:

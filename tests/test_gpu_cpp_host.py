@@ -65,4 +65,13 @@ def test_cpp_host_mirror_example(ctx, twin31, tmp_path):
     assert len(acc) == res["fused_accepted"] and all(len(e["coeff"]) == K and len(e["rigid"]) == 9 for e in acc)
     assert all(e["coeff"] == [] and e["rigid"] == [] for e in rej)
     assert {e["name"] for e in entries} <= {"IcpProposal-TargetSampling-0.1Step", "IcpProposal-ModelSampling-0.1Step", "RandomShape-0.1"}
+    # posterior variability of every 10th logged state after a burn-in of 20 (LogHelper.samplesFromLog walks rejected
+    # entries back to the last accepted one): C++ mirror == Python binding on the same chain
+    from oracle import np_oracle as npo
+    idx = npo.samples_from_log([bool(a) for a in ref["accepted"][:, 0]], 10, n, 20)
+    assert res["variability_samples"] == len(idx) and len(idx) == 18
+    pv = core.posterior_variability(model, ref["theta"][idx, 0], True)
+    np.testing.assert_allclose(res["mean_total_variance"], pv["total_variance"].mean(), rtol=1e-9)
+    np.testing.assert_allclose(res["mean_normal_variance"], pv["normal_variance"].mean(), rtol=1e-9)
+    assert 0 < res["mean_normal_variance"] <= res["mean_total_variance"]
     chain.close(); ev.close(); model.close(); tgt.close()
