@@ -628,12 +628,11 @@ __global__ void __launch_bounds__(128) k_nearest_vertex_brute(int N, int C, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
-// nearest vertex of a per-chain mesh through a vertex BVH that never leaves the SM: one CTA per chain stages the chain's
-// vertices in shared memory, refits the reference-topology LBVH bottom-up into shared memory (level-synchronous, one
-// __syncthreads per level instead of an L2 round trip) and walks it for the chain's queries, seeded with the previous
-// answer of each query. Same boxes, same traversal order and tie rule as bvh_refit + k_nearest<points, dynamic>, so
-// the results are identical; it replaces a 184 MB write + read of per-chain node boxes (C = 2368) by 78 KB of shared
-// memory per CTA.
+// nearest vertex of a per-chain mesh through a vertex BVH whose boxes never leave the SM: one CTA per chain refits the
+// reference-topology LBVH bottom-up into shared memory (level-synchronous, one __syncthreads per level instead of an
+// L2 round trip) and walks it for the chain's queries, seeded with the previous answer of each query. Same boxes, same
+// traversal order and tie rule as bvh_refit + k_nearest<points, dynamic>, so the results are identical; it replaces a
+// 184 MB write + read of per-chain node boxes (C = 2368) by 39 KB of shared memory per CTA.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_nearest_vertex_tree(int n, const int *__restrict__ prim, const int2 *__restrict__ children,
                                                              const int *__restrict__ order, const int *__restrict__ level_off,
@@ -641,19 +640,11 @@ __global__ void __launch_bounds__(256) k_nearest_vertex_tree(int n, const int *_
                                                              long long nq, const double *__restrict__ q, int q_per_chain,
                                                              int *__restrict__ seed_slot, int *__restrict__ out_prim,
                                                              double *__restrict__ out_d2) {
-    extern __shared__ double smt[];
-    double *sx = smt;                                              // [3 N] vertices of this chain
-    float *sbox = reinterpret_cast<float *>(smt + 3 * (size_t)N);  // [n - 1][6] boxes of the internal nodes (lo, hi)
+    extern __shared__ float sbox[];                                // [n - 1][6] boxes of the internal nodes (lo, hi)
     const int c = blockIdx.x;
-    const double *Xc = X + (size_t)c * N * 3;
-    for (int e0 = threadIdx.x; e0 < 3 * N; e0 += 8 * blockDim.x) {
-        double tmp[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; tmp[u] = e < 3 * N ? __ldg(Xc + e) : 0.0; }
-#pragma unroll
-        for (int u = 0; u < 8; u++) { int e = e0 + u * blockDim.x; if (e < 3 * N) sx[e] = tmp[u]; }
-    }
-    __syncthreads();
+    const double *sx = X + (size_t)c * N * 3;                      // the chain's vertices stay in global memory (L1 / L2): each
+                                                                   // is read once by the refit and ~5 times by the leaf tests,
+                                                                   // and without them five CTAs share an SM instead of two
     // box of child `ch` of an internal node: an internal node's box from shared memory, a leaf's from its vertex
     auto child_box = [&](int ch, float (&b)[6]) {
         if (ch >= 0) {
@@ -661,8 +652,9 @@ __global__ void __launch_bounds__(256) k_nearest_vertex_tree(int n, const int *_
             for (int k = 0; k < 6; k++) b[k] = sbox[6 * ch + k];
         } else {
             const double *v = sx + 3 * __ldg(&prim[~ch]);
-            b[0] = __double2float_rd(v[0]) - slack; b[1] = __double2float_rd(v[1]) - slack; b[2] = __double2float_rd(v[2]) - slack;
-            b[3] = __double2float_ru(v[0]) + slack; b[4] = __double2float_ru(v[1]) + slack; b[5] = __double2float_ru(v[2]) + slack;
+            const double vx = __ldg(v), vy = __ldg(v + 1), vz = __ldg(v + 2);
+            b[0] = __double2float_rd(vx) - slack; b[1] = __double2float_rd(vy) - slack; b[2] = __double2float_rd(vz) - slack;
+            b[3] = __double2float_ru(vx) + slack; b[4] = __double2float_ru(vy) + slack; b[5] = __double2float_ru(vz) + slack;
         }
     };
     for (int lev = 0; lev < n_levels; lev++) {
@@ -688,7 +680,7 @@ __global__ void __launch_bounds__(256) k_nearest_vertex_tree(int n, const int *_
         float best = INFINITY;
         auto leaf = [&](int slot) {
             const int p = __ldg(&prim[slot]);
-            const double dx = qx - sx[3 * p], dy = qy - sx[3 * p + 1], dz = qz - sx[3 * p + 2];
+            const double dx = qx - __ldg(sx + 3 * p), dy = qy - __ldg(sx + 3 * p + 1), dz = qz - __ldg(sx + 3 * p + 2);
             const double d2 = dx * dx + dy * dy + dz * dz;
             if (d2 < bd2 || (d2 == bd2 && p < bprim)) { bd2 = d2; bprim = p; bslot = slot; }
             best = __double2float_ru(bd2);
@@ -738,7 +730,7 @@ __global__ void __launch_bounds__(256) k_nearest_vertex_tree(int n, const int *_
 // false (nothing launched) when the tree does not fit shared memory or has no level schedule
 bool launch_nearest_vertex_tree(const Bvh &b, int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain,
                                 int *d_seed, int *d_prim, double *d_d2, cudaStream_t s) {
-    size_t smem = sizeof(double) * 3 * (size_t)N + sizeof(float) * 6 * (size_t)(b.n - 1);
+    size_t smem = sizeof(float) * 6 * (size_t)(b.n - 1);
     if (b.prim_kind != 1 || b.n_levels <= 0 || b.n != N || smem > 110 * 1024 || C <= 0 || nq <= 0) return false;
     ProfScope _ps(ST_NEAREST_DYNAMIC, s);
     ICP_CUDA(cudaFuncSetAttribute(k_nearest_vertex_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -19,6 +19,14 @@ __device__ __forceinline__ void pose_matrix(const double *th, double R[9]) {
 }
 
 
+// FP64 tensor-pipe instruction (SASS DMMA): C (8 x 8) += A (8 x 4) B (4 x 8). Lane l holds a = A[l / 4][l % 4],
+// b = B[l % 4][l / 4], c0 / c1 = C[l / 4][2 (l % 4) + 0 / 1].
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 // Scalismo vertexNormals: normalised unweighted mean of the unit cell normals of the adjacent
 // triangles, adjacency in ascending triangle id
 __device__ __forceinline__ void vertex_normal_dev(const ModelDev &m, const double *__restrict__ Xc, int v, double &nx, double &ny,

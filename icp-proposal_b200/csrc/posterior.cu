@@ -368,11 +368,7 @@ __global__ void __launch_bounds__(kPbThreads) k_posterior_build(ModelDev m, ObsD
 // B-operand fragments are the SAME access pattern into the staged rows (element [k][8 b + i] for lane
 // (i = lane / 4, k = lane % 4)), so a fragment loaded for column block b serves as A operand of block row b
 // and as B operand of block column b. Row stride Kp + 4 makes the fragment loads bank-conflict free.
-__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
+// dmma_8x8x4: icp_device.cuh
 
 constexpr int kMmaRows = 3 * kPbObs;  // 24 staged rows = 6 k4-steps
 constexpr int kProdWarps = 2;         // producer warps (stage A = F Q into shared memory, accumulate b)
