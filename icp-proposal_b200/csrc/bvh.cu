@@ -693,27 +693,31 @@ __global__ void __launch_bounds__(256) k_nearest_vertex_tree(int n, const int *_
             const int s0 = seed_slot[g];
             if ((unsigned)s0 < (unsigned)n) leaf(s0);
         }
-        while (node != 0x7ffffffe) {
-            if (node < 0) {
-                leaf(~node);
-            } else {
-                const int2 ch = __ldg(&children[node]);
-                float l[6], r[6];
-                child_box(ch.x, l);
-                child_box(ch.y, r);
-                const float dl = box_d2(l[0], l[1], l[2], l[3], l[4], l[5], fx, fy, fz);
-                const float dr = box_d2(r[0], r[1], r[2], r[3], r[4], r[5], fx, fy, fz);
-                const bool hl = dl <= best, hr = dr <= best;
-                if (hl && hr) {
-                    int near = ch.x, far = ch.y;
-                    float dfar = dr;
-                    if (dr < dl) { near = ch.y; far = ch.x; dfar = dl; }
-                    if (sp < kStack) { stack_n[sp] = far; stack_d[sp] = dfar; sp++; }
-                    node = near;
-                    continue;
-                } else if (hl) { node = ch.x; continue; }
-                else if (hr) { node = ch.y; continue; }
+        while (node != 0x7ffffffe) {   // node is always internal here
+            const int2 ch = __ldg(&children[node]);
+            // a leaf child is a point: its exact distance costs what its box test would, so it is tested on the spot and
+            // never pushed; only internal children get a box test
+            float dl = INFINITY, dr = INFINITY;
+            if (ch.x < 0) leaf(~ch.x);
+            if (ch.y < 0) leaf(~ch.y);
+            if (ch.x >= 0) {
+                const float *b = sbox + 6 * ch.x;
+                dl = box_d2(b[0], b[1], b[2], b[3], b[4], b[5], fx, fy, fz);
             }
+            if (ch.y >= 0) {
+                const float *b = sbox + 6 * ch.y;
+                dr = box_d2(b[0], b[1], b[2], b[3], b[4], b[5], fx, fy, fz);
+            }
+            const bool hl = ch.x >= 0 && dl <= best, hr = ch.y >= 0 && dr <= best;
+            if (hl && hr) {
+                int near = ch.x, far = ch.y;
+                float dfar = dr;
+                if (dr < dl) { near = ch.y; far = ch.x; dfar = dl; }
+                if (sp < kStack) { stack_n[sp] = far; stack_d[sp] = dfar; sp++; }
+                node = near;
+                continue;
+            } else if (hl) { node = ch.x; continue; }
+            else if (hr) { node = ch.y; continue; }
             node = 0x7ffffffe;
             while (sp > 0) {
                 --sp;
