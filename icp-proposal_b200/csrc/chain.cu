@@ -12,6 +12,7 @@
 // ICP component - for the proposed state.
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <unordered_map>
 
 #include "icp_device.cuh"
@@ -378,6 +379,8 @@ struct icp_chain_s {
     DevBuf<int> h_log_comp;
     DevBuf<uint8_t> h_log_acc;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host-buffer entry point: log rows leave for the host while later steps run
+    cudaEvent_t copy_ev = nullptr;
     double last_ms = 0;
     int64_t last_launches = 0;
     int last_per_step = 0;
@@ -494,6 +497,8 @@ extern "C" int32_t icp_chain_destroy(icp_chain c) {
         if (c->exec) cudaGraphExecDestroy(c->exec);
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
+        if (c->copy_ev) cudaEventDestroy(c->copy_ev);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         delete c;
         return ICP_OK;
     } catch (...) {
@@ -571,7 +576,9 @@ void enqueue_step(RunCtx &r) {
     }
 }
 
-void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev, const icp_chain_io *io, bool async) {
+// on_step(k): called on the host right after step k (1-based) of this call has been enqueued on the library stream
+void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev, const icp_chain_io *io, bool async,
+                      const std::function<void(int)> *on_step = nullptr) {
     icp_model m = ch->model;
     icp_ctx ctx = m->ctx;
     cudaStream_t s = ctx->stream;
@@ -623,6 +630,7 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
         enqueue_step(r);
         steps_done = 1;
         ch->sized_C = C;
+        if (on_step) (*on_step)(steps_done);
     }
     cudaGraphExec_t exec = nullptr;
     if (ch->use_graph && !g_prof && n_steps - steps_done >= 1) {
@@ -670,10 +678,10 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
             }
         }
     }
-    if (exec) {
-        for (; steps_done < n_steps; steps_done++) ICP_CUDA(cudaGraphLaunch(exec, s));
-    } else {
-        for (; steps_done < n_steps; steps_done++) enqueue_step(r);
+    for (; steps_done < n_steps; steps_done++) {
+        if (exec) ICP_CUDA(cudaGraphLaunch(exec, s));
+        else enqueue_step(r);
+        if (on_step) (*on_step)(steps_done + 1);
     }
     if (io->theta_final)
         ICP_CUDA(cudaMemcpyAsync(io->theta_final, ch->theta_cur.p, sizeof(double) * (size_t)C * Lt, cudaMemcpyDeviceToDevice, s));
@@ -734,19 +742,62 @@ extern "C" int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const 
         if (io->log_theta) { c->h_log_theta.ensure(rec * Lt); dio.log_theta = c->h_log_theta.p; }
         if (io->theta_final) { d_final.ensure((size_t)C * Lt); dio.theta_final = d_final.p; }
         if (io->n_accepted) { d_nacc.ensure(C); dio.n_accepted = (int64_t *)d_nacc.p; }
-        chain_run_device(c, C, n_steps, d_theta0.p, &dio, false);
+        // The log is [step][chain]: rows of finished steps are contiguous. When the caller's log buffers are pinned, rows
+        // leave on a copy stream in up to 16 slices while later steps run; pageable buffers (cudaMemcpyAsync would block
+        // the enqueueing thread) are copied after the last step.
+        auto pinned = [](const void *h) {
+            if (!h) return true;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
+            return at.type == cudaMemoryTypeHost;
+        };
+        const bool overlap = n_steps >= 2 && (io->log_component || io->log_accepted || io->log_values || io->log_theta) &&
+                             pinned(io->log_component) && pinned(io->log_accepted) && pinned(io->log_values) && pinned(io->log_theta);
+        int copied = 0;
+        auto copy_rows = [&](cudaStream_t cs, int s0, int s1) {
+            const size_t o = (size_t)s0 * C, nrow = (size_t)(s1 - s0) * C;
+            auto dl = [&](void *h, const void *d, size_t elem) {
+                if (h && nrow) ICP_CUDA(cudaMemcpyAsync((char *)h + o * elem, (const char *)d + o * elem, nrow * elem, cudaMemcpyDeviceToHost, cs));
+            };
+            dl(io->log_component, c->h_log_comp.p, sizeof(int));
+            dl(io->log_accepted, c->h_log_acc.p, 1);
+            dl(io->log_values, c->h_log_values.p, sizeof(double) * 3);
+            dl(io->log_theta, c->h_log_theta.p, sizeof(double) * Lt);
+        };
+        if (overlap) {
+            if (!c->copy_stream) {
+                ICP_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+                ICP_CUDA(cudaEventCreateWithFlags(&c->copy_ev, cudaEventDisableTiming));
+            }
+            const int slice = (n_steps + 15) / 16;
+            std::function<void(int)> hook = [&](int done) {
+                if (done - copied >= slice && done < n_steps) {
+                    ICP_CUDA(cudaEventRecord(c->copy_ev, s));
+                    ICP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_ev, 0));
+                    copy_rows(c->copy_stream, copied, done);
+                    copied = done;
+                }
+            };
+            chain_run_device(c, C, n_steps, d_theta0.p, &dio, true, &hook);
+        } else {
+            chain_run_device(c, C, n_steps, d_theta0.p, &dio, true);
+        }
+        copy_rows(s, copied, n_steps);
         auto dl = [&](void *h, const void *d, size_t bytes) {
             if (h && bytes) ICP_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
         };
-        dl(io->log_component, c->h_log_comp.p, sizeof(int) * rec);
-        dl(io->log_accepted, c->h_log_acc.p, rec);
-        dl(io->log_values, c->h_log_values.p, sizeof(double) * 3 * rec);
-        dl(io->log_theta, c->h_log_theta.p, sizeof(double) * rec * Lt);
         dl(io->theta_final, d_final.p, sizeof(double) * (size_t)C * Lt);
         dl(io->n_accepted, d_nacc.p, sizeof(long long) * (size_t)C);
         ICP_CUDA(cudaStreamSynchronize(s));
+        if (overlap) ICP_CUDA(cudaStreamSynchronize(c->copy_stream));
+        {   // the run was enqueued asynchronously: device time of the K steps, as chain_run_device records it when it waits
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            c->last_ms = ms;
+        }
         return ICP_OK;
     } catch (...) {
+        if (c && c->copy_stream) cudaStreamSynchronize(c->copy_stream);   // no copy into the caller's buffers may outlive the call
         return translate_exception(_ctx);
     }
 }

@@ -233,7 +233,9 @@ typedef struct {
     int64_t *n_accepted;      /* [C] */
 } icp_chain_io;
 
-/* theta0 C x (K+10) (host). io buffers are host memory. */
+/* theta0 C x (K+10) (host). io buffers are host memory. When the log buffers are page-locked (cudaHostAlloc /
+ * cudaHostRegister), finished log rows are copied out on a second stream while later steps run; pageable buffers are
+ * copied after the last step. */
 int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const double *theta0, const icp_chain_io *io);
 /* same with theta0 and every non-NULL io pointer in DEVICE memory; the run is enqueued on the
  * context stream and synchronised before returning unless `async` != 0.
