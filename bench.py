@@ -304,7 +304,7 @@ def run_gpu(args):
                          "traffic": 1.76e8 * C / 2368.0, "avg_launch_ms": ch_ms, "flops_per_launch": flops_chol * C,
                          "share_of_step": shares.get("cholesky_solve"),
                          "note": "a chain of Kp dependent pivots per matrix: latency-bound by construction (4 chains per SM hide "
-                                 "it); traffic = dram read + write per launch from profiles/r1h (ncu --set full, C = 2368), scaled by C"}
+                                 "it); traffic = dram read + write per launch from profiles/r1j (ncu --set full, C = 2368), scaled by C"}
         pb = prof["posterior_build"]
         pb_ms = pb["ms"] / max(pb["launches"], 1)
         pb_tflops = flops_post * C / (pb_ms * 1e-3) / 1e12 if pb_ms > 0 else 0.0
@@ -338,7 +338,7 @@ def run_gpu(args):
                     "frac": pb_tflops / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
                     "hw_achieved": pb_hw, "hw_frac": pb_hw / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
                     "traffic": 1.08e8 * C / 2368.0,
-                    "traffic_note": "dram read+write per launch from profiles/r1h (ncu --set full, C = 2368), scaled by C; "
+                    "traffic_note": "dram read+write per launch from profiles/r1j (ncu --set full, C = 2368), scaled by C; "
                                     "algorithmic bytes per launch = C * (8 * 64 * 91 + 8 Kp) written (packed M, b) ~ 112 MB plus the "
                                     "observation frames read (~ 48 MB); the basis rows come from L2",
                     "peak_source": "DMMA m8n8k4 micro-benchmark run live on this GPU (MEASURED_PEAKS.json has no FP64 figure); "
