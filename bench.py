@@ -157,7 +157,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t_all}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -371,13 +371,33 @@ def run_gpu(args):
                 "cpu_baseline_optimised": {"value": opt_rate, "unit": UNIT, "cores": 1, "kind": "port",
                                            "sample": f"1 chain x {args.cpu_steps * 20} steps, oracle with the same closed forms as the device ({opt_dt:.1f} s)"},
                 "device": ctx.version()}
-        print(json.dumps(line))
+        emit(line)
     barrier()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so that whatever a
+    native library prints (NCCL writes its version banner to stdout) lands on stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _claim_stdout()
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
