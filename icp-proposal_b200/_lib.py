@@ -46,6 +46,10 @@ class Component(C.Structure):
     _fields_ = [("kind", C.c_int32), ("axis", C.c_int32), ("weight", C.c_double), ("sd", C.c_double), ("proposal", _h)]
 
 
+class KernelTerm(C.Structure):
+    _fields_ = [("scale", C.c_double), ("sigma", C.c_double), ("A", C.c_double * 9)]
+
+
 class ChainIO(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("chain_id_offset", C.c_uint64), ("u_comp", C.c_void_p), ("z", C.c_void_p),
                 ("u_acc", C.c_void_p), ("log_component", C.c_void_p), ("log_accepted", C.c_void_p),
@@ -85,6 +89,8 @@ _SIGS = {
     "icp_eval_prior": [_h, C.c_int32, _dp, _dp],
     "icp_registration_metrics": [_h, _h, C.c_int32, _dp, _dp],
     "icp_posterior_variability": [_h, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _dp],
+    "icp_gpmm_kernel_matrix": [_h, C.c_int32, _dp, C.c_int32, _dp, C.POINTER(KernelTerm), C.c_int32, _dp],
+    "icp_gpmm_nystrom_extend": [_h, C.c_int32, _dp, C.c_int32, _dp, C.POINTER(KernelTerm), C.c_int32, C.c_int32, _dp, _dp, _dp, _dp],
     "icp_chain_create": [_h, _h, C.POINTER(Component), C.c_int32, _h, C.c_int32, C.POINTER(_h)],
     "icp_chain_destroy": [_h],
     "icp_chain_run": [_h, C.c_int32, C.c_int32, _dp, C.POINTER(ChainIO)],

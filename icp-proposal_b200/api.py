@@ -18,6 +18,8 @@ src/main/scala of the reference.
   JSONAcceptRejectLogger, jsonLogFormat                                     api/sampling/loggers/JSONAcceptRejectLogger.scala
   IcpBasedSurfaceFitting, RegistrationComparison                           api/other/*.scala
   LogHelper, PosteriorVariability                                           apps/util/{LogHelper,PosteriorVariability}.scala
+  GaussianKernel3D, DiagonalKernel3D, MatrixValuedKernel,
+  LowRankGaussianProcess.approximateGPNystrom, femurKernel                  apps/femur/CreateGPModel.scala (Scalismo kernels)
 
 Only O(K) bookkeeping happens here (as it does on the JVM in the reference); everything that touches a mesh
 or a K x K matrix runs on the GPU. There is no CPU fallback.
@@ -572,6 +574,73 @@ class PosteriorVariability:
         """mean, covariance, total and normal variance in one device pass."""
         return core.posterior_variability(model, PosteriorVariability._thetas(samples), sumNormals,
                                           None if sumNormals else PosteriorVariability._ref(ref))
+
+
+# ---- GPMM construction from analytic kernels (apps/femur/CreateGPModel.scala) -----------------------------------------
+class MatrixValuedKernel:
+    """Sum of terms scale * exp(-|x - y|^2 / sigma^2) * A: what `*` and `+` build from Scalismo's GaussianKernel3D /
+    DiagonalKernel3D in CreateGPModel.scala:74-80."""
+
+    def __init__(self, terms):
+        self.terms = list(terms)     # (scale, sigma, A or None)
+
+    def __mul__(self, factor):
+        if isinstance(factor, (int, float)):
+            return MatrixValuedKernel([(s * float(factor), sg, a) for s, sg, a in self.terms])
+        return NotImplemented
+
+    __rmul__ = __mul__
+
+    def __add__(self, other):
+        return MatrixValuedKernel(self.terms + other.terms)
+
+    def with_matrix(self, A):
+        """baseMatrix * kernel(x, y) (CreateGPModel.scala:79)."""
+        A = np.asarray(A, float)
+        return MatrixValuedKernel([(s, sg, A if a is None else A @ np.asarray(a, float)) for s, sg, a in self.terms])
+
+
+def GaussianKernel3D(sigma, scaleFactor=1.0):
+    """Scalismo GaussianKernel3D(sigma): exp(-|x - y|^2 / sigma^2); scalar, lifted to 3 x 3 by DiagonalKernel3D or a matrix."""
+    return MatrixValuedKernel([(float(scaleFactor), float(sigma), None)])
+
+
+def DiagonalKernel3D(kernel: MatrixValuedKernel, outputDim=3):
+    if outputDim != 3:
+        raise ValueError("3-D deformation fields only")
+    return kernel
+
+
+def getAxisOfMainVariance(points):
+    """CreateGPModel.scala:49-55: left singular vectors of the point covariance."""
+    c = np.asarray(points, float) - np.asarray(points, float).mean(0)
+    u, _, _ = np.linalg.svd(c.T @ c / len(c))
+    return u
+
+
+def femurKernel(referencePoints):
+    """The kernel of CreateGPModel.scala:70-83: 10x more variance along the bone's main axis on the 90 mm scale, isotropic
+    40 mm and 10 mm kernels."""
+    d = getAxisOfMainVariance(referencePoints)
+    baseMatrix = d @ np.diag([10.0, 1.0, 1.0]) @ d.T
+    return (GaussianKernel3D(90) * 10.0).with_matrix(baseMatrix) + DiagonalKernel3D(GaussianKernel3D(40), 3) * 5.0 + \
+        DiagonalKernel3D(GaussianKernel3D(10), 3) * 3.0
+
+
+class LowRankGaussianProcess:
+    @staticmethod
+    def approximateGPNystrom(ctx: core.Context, kernel: MatrixValuedKernel, points, nystromPoints, numBasisFunctions: int):
+        """Scalismo LowRankGaussianProcess.approximateGPNystrom as CreateGPModel.scala:86 calls it: kernel matrix of the
+        Nystrom points (device), its leading eigenpairs (host LAPACK, where the reference has this step too), Nystrom
+        extension to every model point (device). Returns (basis 3N x K, variance K) = pcaBasis / pcaVariance of the
+        StatisticalMeshModel; eigenvector signs: largest-magnitude entry positive."""
+        nys = np.asarray(nystromPoints, float).reshape(-1, 3)
+        kmm = core.gpmm_kernel_matrix(ctx, nys, nys, kernel.terms)
+        w, v = np.linalg.eigh(0.5 * (kmm + kmm.T))
+        order = np.argsort(w)[::-1][:numBasisFunctions]
+        w, v = w[order], v[:, order]
+        v = v * np.sign(v[np.abs(v).argmax(0), np.arange(v.shape[1])])
+        return core.gpmm_nystrom_extend(ctx, points, nys, kernel.terms, v, w)
 
 
 # ---- Metropolis-Hastings -----------------------------------------------------------------------------------------

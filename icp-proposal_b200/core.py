@@ -252,6 +252,38 @@ def registration_metrics(model: Model, target: Target, theta):
     return out
 
 
+def _kernel_terms(terms):
+    """terms: iterable of (scale, sigma, A) with A a 3 x 3 matrix or None (identity)."""
+    arr = (_lib.KernelTerm * len(terms))()
+    for t, (scale, sigma, a) in zip(arr, terms):
+        t.scale, t.sigma = float(scale), float(sigma)
+        t.A[:] = list(np.asarray(np.eye(3) if a is None else a, float).reshape(9))
+    return arr
+
+
+def gpmm_kernel_matrix(ctx: "Context", x, y, terms):
+    """icp_gpmm_kernel_matrix: (3 nx) x (3 ny) matrix of the Gaussian-mixture matrix-valued kernel."""
+    x, y = f64(x).reshape(-1, 3), f64(y).reshape(-1, 3)
+    out = np.empty((3 * len(x), 3 * len(y)))
+    arr = _kernel_terms(terms)
+    check(ctx.lib.icp_gpmm_kernel_matrix(ctx.h, len(x), dptr(x), len(y), dptr(y), arr, len(arr), dptr(out)), ctx.h)
+    return out
+
+
+def gpmm_nystrom_extend(ctx: "Context", pts, nys_pts, terms, V, w):
+    """icp_gpmm_nystrom_extend: (basis 3N x rank, variance rank) from the leading eigenpairs (V, w) of the Nystrom kernel matrix."""
+    pts, nys = f64(pts).reshape(-1, 3), f64(nys_pts).reshape(-1, 3)
+    V, w = f64(V), f64(w)
+    rank = len(w)
+    if V.shape != (3 * len(nys), rank):
+        raise ValueError("V must be (3 m) x rank")
+    basis, var = np.empty((3 * len(pts), rank)), np.empty(rank)
+    arr = _kernel_terms(terms)
+    check(ctx.lib.icp_gpmm_nystrom_extend(ctx.h, len(pts), dptr(pts), len(nys), dptr(nys), arr, len(arr), rank, dptr(V), dptr(w),
+                                          dptr(basis), dptr(var)), ctx.h)
+    return basis, var
+
+
 def posterior_variability(model: Model, thetas, sum_normals=True, theta_ref=None):
     """icp_posterior_variability: dict(mean N x 3, cov N x 3 x 3, total_variance N, normal_variance N)."""
     th, s = model._theta(thetas)

@@ -249,6 +249,27 @@ int32_t icp_ctx_synchronize(icp_ctx ctx);
  * library stream) and the number of kernels it launched */
 int32_t icp_chain_last_run_stats(icp_chain c, double *device_ms, int64_t *kernel_launches);
 
+/* ---- (9) GPMM construction from analytic kernels (the step before the hot path) -------------------- */
+/* One term of the matrix-valued kernel of apps/femur/CreateGPModel.scala:68-83:
+ *   k(x, y) = sum_t scale_t * exp(-|x - y|^2 / sigma_t^2) * A_t
+ * (Scalismo GaussianKernel3D(sigma) * scale; DiagonalKernel3D: A = I; the anisotropic base kernel: A = baseMatrix). */
+typedef struct {
+    double scale;
+    double sigma;
+    double A[9]; /* row-major 3 x 3 */
+} icp_kernel_term;
+/* out (3 nx) x (3 ny) row-major: block (i, j) = k(x_i, y_j). n_terms in [1, 8]. */
+int32_t icp_gpmm_kernel_matrix(icp_ctx ctx, int32_t nx, const double *x, int32_t ny, const double *y,
+                               const icp_kernel_term *terms, int32_t n_terms, double *out);
+/* LowRankGaussianProcess.approximateGPNystrom (CreateGPModel.scala:86) after the eigen-decomposition of the m-point
+ * kernel matrix (V: 3m x rank row-major eigenvectors, w: the rank leading eigenvalues, all > 0; the 3m x 3m symmetric
+ * eigenproblem itself stays with the host's LAPACK, as in the reference): basis (3N x rank row-major) =
+ * k(pts, nys_pts) V diag(sqrt(m) / w), variance (rank, may be NULL) = w / m, i.e. the pcaBasis / pcaVariance of the
+ * StatisticalMeshModel over `pts`. rank <= min(224, 3 m). */
+int32_t icp_gpmm_nystrom_extend(icp_ctx ctx, int32_t N, const double *pts, int32_t m, const double *nys_pts,
+                                const icp_kernel_term *terms, int32_t n_terms, int32_t rank, const double *V,
+                                const double *w, double *basis, double *variance);
+
 /* ---- (8) introspection used by bench.py / tests ---------------------------------------------- */
 /* Philox4x32-10 block as the chain runner draws it: out[4] for (seed, chain, step, block) */
 int32_t icp_debug_philox(icp_ctx ctx, uint64_t seed, uint64_t chain, uint32_t step, uint32_t block, uint32_t out[4]);

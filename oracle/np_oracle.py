@@ -280,3 +280,27 @@ def posterior_variability(meshes, tris, ref_verts=None, sum_normals=True):
                 acc = acc + float(n @ (s - mu)) ** 2              # :66
             mean[pid], cov[pid], total[pid], along[pid] = mu, c, np.trace(c), acc * inv1
     return mean, cov, total, along
+
+
+# ---- GPMM construction from analytic kernels -------------------------------
+
+def gauss_mixture_kernel(x, y, terms):
+    """apps/femur/CreateGPModel.scala:70-83 [S-recall: Scalismo GaussianKernel(sigma)(x, y) = exp(-|x - y|^2 / sigma^2)]:
+    k(x, y) = sum_t scale_t g_t(x, y) A_t, evaluated pair by pair. terms: (scale, sigma, A or None). -> (3 nx) x (3 ny)."""
+    x, y = np.asarray(x, float).reshape(-1, 3), np.asarray(y, float).reshape(-1, 3)
+    out = np.zeros((3 * len(x), 3 * len(y)))
+    for i, xi in enumerate(x):
+        for j, yj in enumerate(y):
+            d2 = float((xi - yj) @ (xi - yj))
+            b = np.zeros((3, 3))
+            for scale, sigma, a in terms:
+                b = b + scale * np.exp(-d2 / (sigma * sigma)) * (np.eye(3) if a is None else np.asarray(a, float))
+            out[3 * i:3 * i + 3, 3 * j:3 * j + 3] = b
+    return out
+
+
+def nystrom_extend(kernel_nm, v, w):
+    """[S-recall] LowRankGaussianProcess.approximateGPNystrom: with (w_i, v_i) the eigenpairs of the m-point kernel matrix,
+    lambda_i = w_i / m and phi_i(x) = sqrt(m) / w_i * k(x, X_m) v_i. -> (basis, variance)."""
+    m = kernel_nm.shape[1] // 3
+    return kernel_nm @ v * (np.sqrt(m) / w), w / m

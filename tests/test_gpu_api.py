@@ -148,3 +148,45 @@ def test_posterior_variability_matches_oracle(setup, sum_normals):
     assert np.isnan(api.PosteriorVariability.computeDistanceMapFromMeshesTotal(model, thetas[:1])).all()
     with pytest.raises(Exception):
         api.PosteriorVariability.computeDistanceMapFromMeshesTotal(model, thetas[:0])
+
+
+def test_gpmm_construction_matches_oracle(ctx, twin31):
+    """the femur kernel of apps/femur/CreateGPModel.scala:70-83 and its Nystrom low-rank approximation
+    (kernel matrix and extension on the device) against the pair-by-pair oracle; the resulting model reconstructs."""
+    from oracle import np_oracle as npo
+    ref = twin31["ref"]
+    kernel = api.femurKernel(ref)
+    assert len(kernel.terms) == 3 and kernel.terms[0][0] == 10.0 and kernel.terms[1][:2] == (5.0, 40.0) and kernel.terms[2][:2] == (3.0, 10.0)
+    rng = np.random.default_rng(1024)
+    rank = 31
+    nys = ref[np.sort(rng.choice(len(ref), 2 * rank, replace=False))]           # numOfSamplePoints = 2 i (:84)
+    from icp_proposal_b200 import core
+    kmm = core.gpmm_kernel_matrix(ctx, nys, nys, kernel.terms)
+    np.testing.assert_allclose(kmm, npo.gauss_mixture_kernel(nys, nys, kernel.terms), rtol=1e-12, atol=1e-300)
+    sub = ref[::7]
+    np.testing.assert_allclose(core.gpmm_kernel_matrix(ctx, sub, nys, kernel.terms), npo.gauss_mixture_kernel(sub, nys, kernel.terms),
+                               rtol=1e-12, atol=1e-300)
+    # Nystrom extension on the device against the oracle's, from the same eigenpairs
+    w, v = np.linalg.eigh(npo.gauss_mixture_kernel(nys, nys, kernel.terms))
+    order = np.argsort(w)[::-1][:rank]
+    w, v = w[order], v[:, order]
+    got_b, got_v = core.gpmm_nystrom_extend(ctx, ref, nys, kernel.terms, v, w)
+    want_b, want_v = npo.nystrom_extend(npo.gauss_mixture_kernel(ref[:300], nys, kernel.terms), v, w)
+    np.testing.assert_allclose(got_v, want_v, rtol=1e-14)
+    np.testing.assert_allclose(got_b[:900], want_b, rtol=1e-9, atol=1e-12 * np.abs(want_b).max())
+    # the whole construction (eigenvectors of near-degenerate pairs may rotate with the last bit of the kernel matrix, the
+    # covariance they span may not): Q Q^T on the Nystrom points is the rank-truncated kernel matrix
+    basis, var = api.LowRankGaussianProcess.approximateGPNystrom(ctx, kernel, ref, nys, rank)
+    np.testing.assert_allclose(var, want_v, rtol=1e-9)
+    sel = np.sort(np.random.default_rng(1024).choice(len(ref), 2 * rank, replace=False))
+    rows = (3 * sel[:, None] + np.arange(3)).ravel()
+    q = (basis * np.sqrt(var))[rows]
+    np.testing.assert_allclose(q @ q.T, (v * w) @ v.T, rtol=1e-5, atol=1e-7 * w[0])
+    # the constructed model is a model: it loads and reconstructs its own instance
+    model = api.StatisticalMeshModel(ctx, ref, twin31["cells"], basis, var)
+    alpha = rng.normal(0, 0.5, rank)
+    got = model.reconstruct(model.theta(alpha))[0]
+    np.testing.assert_allclose(got, ref + ((basis * np.sqrt(var)) @ alpha).reshape(-1, 3), rtol=0, atol=1e-9)
+    model.close()
+    with pytest.raises(Exception):
+        core.gpmm_nystrom_extend(ctx, ref, nys, kernel.terms, v, -w)          # non-positive eigenvalues are an error

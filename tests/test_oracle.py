@@ -286,3 +286,25 @@ def test_posterior_variability_oracle_against_closed_forms(twin31):
     assert npo.samples_from_log(status, take_every_n=1, total=3, burn_in=0) == [0, 0, 0]
     with pytest.raises(IndexError):
         npo.samples_from_log([False, True], 1, 2, 0)
+
+
+def test_nystrom_oracle_reproduces_the_kernel_on_the_nystrom_points():
+    """The pair-by-pair kernel restatement against a vectorised evaluation, and the defining property of the Nystrom
+    extension: with all 3m eigenpairs, basis diag(variance) basis^T restricted to the Nystrom points is their kernel matrix."""
+    rng = np.random.default_rng(5)
+    pts = rng.normal(0, 30, (40, 3))
+    a = rng.normal(size=(3, 3)); a = a @ a.T
+    terms = [(10.0, 90.0, a), (5.0, 40.0, None), (3.0, 10.0, None)]
+    nys = pts[:12]
+    k = npo.gauss_mixture_kernel(pts, nys, terms)
+    d2 = ((pts[:, None] - nys[None]) ** 2).sum(-1)
+    want = sum(s * np.exp(-d2 / sg ** 2)[:, None, :, None] * (np.eye(3) if m is None else m)[None, :, None, :] for s, sg, m in terms)
+    np.testing.assert_allclose(k, want.reshape(120, 36), rtol=1e-14, atol=1e-300)
+    kmm = npo.gauss_mixture_kernel(nys, nys, terms)
+    w, v = np.linalg.eigh(kmm)
+    assert w.min() > 0
+    basis, var = npo.nystrom_extend(k, v, w)
+    q = basis * np.sqrt(var)
+    np.testing.assert_allclose((q @ q.T)[:36, :36], kmm, rtol=1e-9, atol=1e-9)
+    # orthonormality of the discretised eigenfunctions on the Nystrom points: (1/m) sum_x phi_i(x) phi_j(x) = delta_ij
+    np.testing.assert_allclose(basis[:36].T @ basis[:36] / 12, np.eye(36), atol=1e-7)
