@@ -630,16 +630,13 @@ def femurKernel(referencePoints):
 class LowRankGaussianProcess:
     @staticmethod
     def approximateGPNystrom(ctx: core.Context, kernel: MatrixValuedKernel, points, nystromPoints, numBasisFunctions: int):
-        """Scalismo LowRankGaussianProcess.approximateGPNystrom as CreateGPModel.scala:86 calls it: kernel matrix of the
-        Nystrom points (device), its leading eigenpairs (host LAPACK, where the reference has this step too), Nystrom
-        extension to every model point (device). Returns (basis 3N x K, variance K) = pcaBasis / pcaVariance of the
-        StatisticalMeshModel; eigenvector signs: largest-magnitude entry positive."""
+        """Scalismo LowRankGaussianProcess.approximateGPNystrom as CreateGPModel.scala:86 calls it, every step on the device:
+        kernel matrix of the Nystrom points, its leading eigenpairs (one-sided Jacobi), Nystrom extension to every model
+        point. Returns (basis 3N x K, variance K) = pcaBasis / pcaVariance of the StatisticalMeshModel; eigenvector signs:
+        largest-magnitude entry positive."""
         nys = np.asarray(nystromPoints, float).reshape(-1, 3)
         kmm = core.gpmm_kernel_matrix(ctx, nys, nys, kernel.terms)
-        w, v = np.linalg.eigh(0.5 * (kmm + kmm.T))
-        order = np.argsort(w)[::-1][:numBasisFunctions]
-        w, v = w[order], v[:, order]
-        v = v * np.sign(v[np.abs(v).argmax(0), np.arange(v.shape[1])])
+        w, v = core.gpmm_eigen_psd(ctx, kmm, numBasisFunctions)
         return core.gpmm_nystrom_extend(ctx, points, nys, kernel.terms, v, w)
 
 

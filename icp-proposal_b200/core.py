@@ -270,6 +270,17 @@ def gpmm_kernel_matrix(ctx: "Context", x, y, terms):
     return out
 
 
+def gpmm_eigen_psd(ctx: "Context", A, n_top):
+    """icp_gpmm_eigen_psd: (w descending, V n x n_top) of a symmetric positive semi-definite matrix, on the device."""
+    A = f64(A)
+    n = len(A)
+    if A.shape != (n, n):
+        raise ValueError("A must be square")
+    w, V = np.empty(n_top), np.empty((n, n_top))
+    check(ctx.lib.icp_gpmm_eigen_psd(ctx.h, n, dptr(A), int(n_top), dptr(w), dptr(V)), ctx.h)
+    return w, V
+
+
 def gpmm_nystrom_extend(ctx: "Context", pts, nys_pts, terms, V, w):
     """icp_gpmm_nystrom_extend: (basis 3N x rank, variance rank) from the leading eigenpairs (V, w) of the Nystrom kernel matrix."""
     pts, nys = f64(pts).reshape(-1, 3), f64(nys_pts).reshape(-1, 3)

@@ -7,9 +7,11 @@
 //                             m-point kernel matrix extended to all N model points,
 //                             phi_i(x) = sqrt(m) / w_i * k(x, X_m) v_i,   lambda_i = w_i / m
 //
-// The 3m x 3m symmetric eigenproblem between the two calls is left to the host (LAPACK), where the reference has it too
-// (Breeze); everything that scales with the number of model points runs here.
+//   icp_gpmm_eigen_psd        the symmetric eigenproblem of the m-point kernel matrix between the two: one-sided Jacobi
+//                             (Hestenes), one launch per round of the round-robin pair schedule
 #include <algorithm>
+#include <cmath>
+#include <vector>
 
 #include "icp_internal.h"
 #include "icp_device.cuh"
@@ -114,6 +116,89 @@ __global__ void __launch_bounds__(128) k_nystrom_extend(KernelTerms kt, int N, c
     }
 }
 
+// ---- symmetric positive semi-definite eigen-decomposition: one-sided Jacobi (Hestenes) ----------------------------------
+// G = A V is kept column by column (A symmetric: its rows are its columns); a rotation of the column pair (i, j) makes
+// g_i and g_j orthogonal. At convergence the columns of V are the eigenvectors and |g_k| the eigenvalues (A is PSD).
+// One launch = one round of the round-robin tournament (circle method): n / 2 disjoint pairs, one CTA each.
+__global__ void __launch_bounds__(128) k_jacobi_round(int n, int npad, int round, double *__restrict__ G, double *__restrict__ V,
+                                                      double tol, double floor2, int *__restrict__ rotated) {
+    const int k = blockIdx.x, np1 = npad - 1;
+    int i, j;
+    if (k == 0) { i = np1; j = round; }
+    else { i = (round + k) % np1; j = (round - k + np1) % np1; }
+    if (i > j) { const int t = i; i = j; j = t; }
+    if (j >= n) return;   // padding player
+    double *gi = G + (size_t)i * n, *gj = G + (size_t)j * n, *vi = V + (size_t)i * n, *vj = V + (size_t)j * n;
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const double x = gi[r], y = gj[r];
+        a = fma(x, x, a); b = fma(y, y, b); c = fma(x, y, c);
+    }
+    __shared__ double red[40];
+    __shared__ double rot[2];
+    a = block_sum(a, red);
+    b = block_sum(b, red);
+    c = block_sum(c, red);
+    if (threadIdx.x == 0) {
+        double cs = 1.0, sn = 0.0;
+        // columns whose norm has sunk below the rounding noise of the large ones are null vectors: never rotated
+        if (a > floor2 && b > floor2 && fabs(c) > tol * sqrt(a * b)) {
+            const double zeta = (b - a) / (2.0 * c);
+            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            cs = 1.0 / sqrt(1.0 + t * t);
+            sn = cs * t;
+            *rotated = 1;
+        }
+        rot[0] = cs; rot[1] = sn;
+    }
+    __syncthreads();
+    const double cs = rot[0], sn = rot[1];
+    if (sn == 0.0) return;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const double x = gi[r], y = gj[r];
+        gi[r] = cs * x - sn * y; gj[r] = sn * x + cs * y;
+        const double p = vi[r], q = vj[r];
+        vi[r] = cs * p - sn * q; vj[r] = sn * p + cs * q;
+    }
+}
+
+__global__ void k_identity(int n, double *__restrict__ V) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < (long long)n * n) V[g] = (g / n == g % n) ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(128) k_column_norms(int n, const double *__restrict__ G, double *__restrict__ w) {
+    __shared__ double red[40];
+    const double *g = G + (size_t)blockIdx.x * n;
+    double a = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) a = fma(g[r], g[r], a);
+    a = block_sum(a, red);
+    if (threadIdx.x == 0) w[blockIdx.x] = sqrt(a);
+}
+
+// d_A: n x n symmetric PSD (destroyed: becomes G). d_V: n x n, column k = eigenvector k. d_w: n eigenvalues (unsorted).
+static int jacobi_eigen_psd(int n, double *d_A, double *d_V, double *d_w, double frob, cudaStream_t s) {
+    const int npad = (n + 1) & ~1;
+    const double eps = 2.220446049250313e-16, tol = std::max(1e-14, 4.0 * n * eps), floor2 = (n * eps * frob) * (n * eps * frob);
+    DevBuf<int> flag;
+    flag.alloc(1);
+    k_identity<<<(unsigned)(((long long)n * n + 255) / 256), 256, 0, s>>>(n, d_V);
+    ICP_CUDA(cudaGetLastError());
+    int sweeps = 0;
+    for (; sweeps < 40; sweeps++) {
+        ICP_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
+        for (int round = 0; round < npad - 1; round++) k_jacobi_round<<<npad / 2, 128, 0, s>>>(n, npad, round, d_A, d_V, tol, floor2, flag.p);
+        ICP_CUDA(cudaGetLastError());
+        int h = 0;
+        ICP_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        ICP_CUDA(cudaStreamSynchronize(s));
+        if (!h) break;
+    }
+    k_column_norms<<<n, 128, 0, s>>>(n, d_A, d_w);
+    ICP_CUDA(cudaGetLastError());
+    return sweeps;
+}
+
 static KernelTerms pack_terms(const icp_kernel_term *terms, int n_terms) {
     ICP_REQUIRE(terms != nullptr && n_terms >= 1 && n_terms <= kMaxKernelTerms, "between 1 and 8 kernel terms");
     KernelTerms kt;
@@ -182,6 +267,43 @@ extern "C" int32_t icp_gpmm_nystrom_extend(icp_ctx ctx, int32_t N, const double 
         ICP_CUDA(cudaStreamSynchronize(s));
         if (variance)
             for (int k = 0; k < rank; k++) variance[k] = w[k] / m;
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+// Leading eigenpairs of a symmetric positive semi-definite matrix (the Nystrom kernel matrix) on the device.
+extern "C" int32_t icp_gpmm_eigen_psd(icp_ctx ctx, int32_t n, const double *A, int32_t n_top, double *w, double *V) {
+    icp_ctx _ctx = ctx;
+    try {
+        ICP_REQUIRE(_ctx != nullptr, "null handle");
+        CtxLock lock(_ctx);
+        ICP_REQUIRE(n >= 1 && A && w && V && n_top >= 1 && n_top <= n, "bad argument");
+        cudaStream_t s = _ctx->stream;
+        DevBuf<double> dA, dV, dw;
+        dA.upload(A, (size_t)n * n, s);
+        dV.alloc((size_t)n * n);
+        dw.alloc(n);
+        double frob = 0.0;
+        for (size_t e = 0; e < (size_t)n * n; e++) frob += A[e] * A[e];
+        jacobi_eigen_psd(n, dA.p, dV.p, dw.p, std::sqrt(frob), s);
+        std::vector<double> hw(n), hV((size_t)n * n);
+        ICP_CUDA(cudaMemcpyAsync(hw.data(), dw.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+        ICP_CUDA(cudaMemcpyAsync(hV.data(), dV.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, s));
+        ICP_CUDA(cudaStreamSynchronize(s));
+        std::vector<int> order(n);
+        for (int k = 0; k < n; k++) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return hw[a] > hw[b]; });
+        for (int k = 0; k < n_top; k++) {
+            const double *col = hV.data() + (size_t)order[k] * n;
+            int big = 0;
+            for (int r = 1; r < n; r++)
+                if (fabs(col[r]) > fabs(col[big])) big = r;
+            const double sgn = col[big] < 0.0 ? -1.0 : 1.0;   // sign convention: the largest-magnitude entry is positive
+            w[k] = hw[order[k]];
+            for (int r = 0; r < n; r++) V[(size_t)r * n_top + k] = sgn * col[r];
+        }
         return ICP_OK;
     } catch (...) {
         return translate_exception(_ctx);

@@ -261,9 +261,12 @@ typedef struct {
 /* out (3 nx) x (3 ny) row-major: block (i, j) = k(x_i, y_j). n_terms in [1, 8]. */
 int32_t icp_gpmm_kernel_matrix(icp_ctx ctx, int32_t nx, const double *x, int32_t ny, const double *y,
                                const icp_kernel_term *terms, int32_t n_terms, double *out);
+/* Leading n_top eigenpairs of a symmetric positive semi-definite n x n matrix A (row-major; the Nystrom kernel matrix)
+ * by one-sided Jacobi on the device: w (n_top, descending), V (n x n_top row-major, unit columns, the largest-magnitude
+ * entry of every eigenvector positive). */
+int32_t icp_gpmm_eigen_psd(icp_ctx ctx, int32_t n, const double *A, int32_t n_top, double *w, double *V);
 /* LowRankGaussianProcess.approximateGPNystrom (CreateGPModel.scala:86) after the eigen-decomposition of the m-point
- * kernel matrix (V: 3m x rank row-major eigenvectors, w: the rank leading eigenvalues, all > 0; the 3m x 3m symmetric
- * eigenproblem itself stays with the host's LAPACK, as in the reference): basis (3N x rank row-major) =
+ * kernel matrix (V: 3m x rank row-major eigenvectors, w: the rank leading eigenvalues, all > 0): basis (3N x rank row-major) =
  * k(pts, nys_pts) V diag(sqrt(m) / w), variance (rank, may be NULL) = w / m, i.e. the pcaBasis / pcaVariance of the
  * StatisticalMeshModel over `pts`. rank <= min(224, 3 m). */
 int32_t icp_gpmm_nystrom_extend(icp_ctx ctx, int32_t N, const double *pts, int32_t m, const double *nys_pts,

@@ -174,14 +174,26 @@ def test_gpmm_construction_matches_oracle(ctx, twin31):
     want_b, want_v = npo.nystrom_extend(npo.gauss_mixture_kernel(ref[:300], nys, kernel.terms), v, w)
     np.testing.assert_allclose(got_v, want_v, rtol=1e-14)
     np.testing.assert_allclose(got_b[:900], want_b, rtol=1e-9, atol=1e-12 * np.abs(want_b).max())
+    # the device eigensolver (one-sided Jacobi) against LAPACK: eigenvalues, and the invariant subspace through its projector
+    we, ve = core.gpmm_eigen_psd(ctx, kmm, rank)
+    np.testing.assert_allclose(we, w, rtol=1e-10)
+    np.testing.assert_allclose(ve.T @ ve, np.eye(rank), atol=1e-11)
+    np.testing.assert_allclose(kmm @ ve, ve * we, atol=1e-9 * w[0])
+    assert (ve[np.abs(ve).argmax(0), np.arange(rank)] > 0).all()
     # the whole construction (eigenvectors of near-degenerate pairs may rotate with the last bit of the kernel matrix, the
     # covariance they span may not): Q Q^T on the Nystrom points is the rank-truncated kernel matrix
     basis, var = api.LowRankGaussianProcess.approximateGPNystrom(ctx, kernel, ref, nys, rank)
     np.testing.assert_allclose(var, want_v, rtol=1e-9)
+    # ... compared at a rank where the spectrum has a gap (the ellipsoid's near-symmetries pair eigenvalues up; a pair cut
+    # in half by the truncation has no unique half)
+    wa, va = np.linalg.eigh(npo.gauss_mixture_kernel(nys, nys, kernel.terms))
+    wa, va = wa[::-1], va[:, ::-1]
+    rg = max(r for r in range(8, rank + 1) if wa[r - 1] - wa[r] > 0.05 * wa[r - 1])
+    bg, vg = api.LowRankGaussianProcess.approximateGPNystrom(ctx, kernel, ref, nys, rg)
     sel = np.sort(np.random.default_rng(1024).choice(len(ref), 2 * rank, replace=False))
     rows = (3 * sel[:, None] + np.arange(3)).ravel()
-    q = (basis * np.sqrt(var))[rows]
-    np.testing.assert_allclose(q @ q.T, (v * w) @ v.T, rtol=1e-5, atol=1e-7 * w[0])
+    q = (bg * np.sqrt(vg))[rows]
+    np.testing.assert_allclose(q @ q.T, (va[:, :rg] * wa[:rg]) @ va[:, :rg].T, rtol=1e-5, atol=1e-8 * wa[0])
     # the constructed model is a model: it loads and reconstructs its own instance
     model = api.StatisticalMeshModel(ctx, ref, twin31["cells"], basis, var)
     alpha = rng.normal(0, 0.5, rank)
