@@ -11,6 +11,8 @@
 //                             (Hestenes), one launch per round of the round-robin pair schedule
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "icp_internal.h"
@@ -179,21 +181,37 @@ __global__ void __launch_bounds__(128) k_column_norms(int n, const double *__res
 // d_A: n x n symmetric PSD (destroyed: becomes G). d_V: n x n, column k = eigenvector k. d_w: n eigenvalues (unsorted).
 static int jacobi_eigen_psd(int n, double *d_A, double *d_V, double *d_w, double frob, cudaStream_t s) {
     const int npad = (n + 1) & ~1;
-    const double eps = 2.220446049250313e-16, tol = std::max(1e-14, 4.0 * n * eps), floor2 = (n * eps * frob) * (n * eps * frob);
+    const double eps = 2.220446049250313e-16, tol = std::max(1e-12, 32.0 * n * eps)   /* the orthogonality a sweep of n rotations per column can hold */, floor2 = (n * eps * frob) * (n * eps * frob);
     DevBuf<int> flag;
     flag.alloc(1);
     k_identity<<<(unsigned)(((long long)n * n + 255) / 256), 256, 0, s>>>(n, d_V);
     ICP_CUDA(cudaGetLastError());
-    int sweeps = 0;
-    for (; sweeps < 40; sweeps++) {
+    // one sweep = npad - 1 dependent launches: captured once in a CUDA graph and replayed per sweep (launch-bound otherwise)
+    auto enqueue_sweep = [&]() {
         ICP_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
         for (int round = 0; round < npad - 1; round++) k_jacobi_round<<<npad / 2, 128, 0, s>>>(n, npad, round, d_A, d_V, tol, floor2, flag.p);
         ICP_CUDA(cudaGetLastError());
+    };
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        bool ok = true;
+        try { enqueue_sweep(); } catch (...) { ok = false; }
+        if (cudaStreamEndCapture(s, &graph) != cudaSuccess || !ok || !graph) { if (graph) cudaGraphDestroy(graph); graph = nullptr; }
+        if (graph && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+    }
+    cudaGetLastError();
+    int sweeps = 0;
+    for (; sweeps < 40; sweeps++) {
+        if (exec) ICP_CUDA(cudaGraphLaunch(exec, s));
+        else enqueue_sweep();
         int h = 0;
         ICP_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         ICP_CUDA(cudaStreamSynchronize(s));
         if (!h) break;
     }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
     k_column_norms<<<n, 128, 0, s>>>(n, d_A, d_w);
     ICP_CUDA(cudaGetLastError());
     return sweeps;
@@ -287,7 +305,8 @@ extern "C" int32_t icp_gpmm_eigen_psd(icp_ctx ctx, int32_t n, const double *A, i
         dw.alloc(n);
         double frob = 0.0;
         for (size_t e = 0; e < (size_t)n * n; e++) frob += A[e] * A[e];
-        jacobi_eigen_psd(n, dA.p, dV.p, dw.p, std::sqrt(frob), s);
+        const int sweeps = jacobi_eigen_psd(n, dA.p, dV.p, dw.p, std::sqrt(frob), s);
+        if (getenv("ICPCUDA_VERBOSE")) fprintf(stderr, "icp_gpmm_eigen_psd: n = %d, %d sweeps\n", n, sweeps + 1);
         std::vector<double> hw(n), hV((size_t)n * n);
         ICP_CUDA(cudaMemcpyAsync(hw.data(), dw.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
         ICP_CUDA(cudaMemcpyAsync(hV.data(), dV.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, s));
