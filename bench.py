@@ -270,6 +270,25 @@ def run_gpu(args):
     h2d = h_th0.nbytes / e_steps
     d2h = (h_comp.nbytes + h_acc.nbytes + h_val.nbytes + h_thl.nbytes + h_fin.nbytes + h_nacc.nbytes) / e_steps
 
+    # ---- closest-point traversal on every GPU: 1000 B / query on the femur mesh, 1e6 device-resident queries
+    # per GPU (the target BVH is replicated, queries shard like chains); whole-job queries/s = the sum over the ranks -----
+    import ctypes as Cc2
+    cp = {}
+    nq = 1_000_000
+    for name, q in (("near_surface", synth.near_surface_queries(tv, tc, nq, seed=11 + 100 * rank)),
+                    ("far_field", synth.far_field_queries(tv, nq, seed=12 + 100 * rank))):
+        qd = torch.from_numpy(q).to(dev)
+        tri = torch.empty(nq, dtype=torch.int32, device=dev); cpd = torch.empty((nq, 3), dtype=torch.float64, device=dev)
+        d2 = torch.empty(nq, dtype=torch.float64, device=dev)
+        ms = Cc2.c_double(0)
+        barrier()
+        _lib.check(chain.lib.icp_debug_time_closest_point(tgt.h, nq, qd.data_ptr(), tri.data_ptr(), cpd.data_ptr(), d2.data_ptr(),
+                                                          10, Cc2.byref(ms)), ctx.h)
+        worst = max_over_ranks(ms.value)     # device time of the slowest rank
+        cp[name] = {"queries_per_s": world * nq / (worst * 1e-3), "queries_per_s_per_gpu": nq / (ms.value * 1e-3), "ms_per_launch": ms.value,
+                    "algorithmic_GBps": nq * 1000.0 / (ms.value * 1e-3) / 1e9, "n_gpus": world}
+        del qd, tri, cpd, d2
+
     line = None
     if rank == 0:
         # ---- per-kernel device times (CUDA events on the launching stream, eager pass over the same workload) --
@@ -309,18 +328,6 @@ def run_gpu(args):
         pb_ms = pb["ms"] / max(pb["launches"], 1)
         pb_tflops = flops_post * C / (pb_ms * 1e-3) / 1e12 if pb_ms > 0 else 0.0
         pb_hw = flops_exec * C / (pb_ms * 1e-3) / 1e12 if pb_ms > 0 else 0.0
-        # closest-point traversal: 1000 B / query on the femur mesh, 1e6 device-resident queries
-        cp = {}
-        nq = 1_000_000
-        for name, q in (("near_surface", synth.near_surface_queries(tv, tc, nq, seed=11)), ("far_field", synth.far_field_queries(tv, nq, seed=12))):
-            qd = torch.from_numpy(q).to(dev)
-            tri = torch.empty(nq, dtype=torch.int32, device=dev); cpd = torch.empty((nq, 3), dtype=torch.float64, device=dev)
-            d2 = torch.empty(nq, dtype=torch.float64, device=dev)
-            ms = Cc.c_double(0)
-            _lib.check(chain.lib.icp_debug_time_closest_point(tgt.h, nq, qd.data_ptr(), tri.data_ptr(), cpd.data_ptr(), d2.data_ptr(),
-                                                              10, Cc.byref(ms)), ctx.h)
-            cp[name] = {"queries_per_s": nq / (ms.value * 1e-3), "ms_per_launch": ms.value,
-                        "algorithmic_GBps": nq * 1000.0 / (ms.value * 1e-3) / 1e9}
         top = max(shares, key=shares.get)
         cpq = prof["closest_point_static"]
         cp_ms = cpq["ms"] / max(cpq["launches"], 1)
