@@ -398,7 +398,7 @@ constexpr int kDone = 0x7ffffffe;
 // the exact FP64 primitive test together. Static structures read one 64-byte packed node (child boxes + child links);
 // per-chain (refitted) structures read the shared topology and their own boxes.
 template <int PRIM, bool DYNAMIC>
-__global__ void __launch_bounds__(kNearestThreads) k_nearest(int n, const int2 *__restrict__ children,
+__global__ void __launch_bounds__(kNearestThreads, 7) k_nearest(int n, const int2 *__restrict__ children,
                                                  const float4 *__restrict__ nodes, const int *__restrict__ prim,
                                                  const double *__restrict__ prim_data, const double *__restrict__ X,
                                                  const int *__restrict__ tris, int N, int C, long long nq,

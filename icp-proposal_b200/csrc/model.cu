@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(128) k_reconstruct(ModelDev m, int C, const do
 // of 34 doubles, which makes those B-operand reads and the epilogue's reads of the staged tile conflict free.
 // Epilogue: the accumulators go through shared memory so that one lane holds x, y, z of a vertex for the similarity
 // transform (same arithmetic as k_reconstruct), 8 consecutive vertices of a chain per 8 lanes (192 contiguous bytes).
-constexpr int kRmV = 128;       // vertices per CTA (four groups of 8 per warp: the coefficient tile is staged once for all of them)
+constexpr int kRmV = 96;        // vertices per CTA (three groups of 8 per warp share one staged coefficient tile); at N = 1622 and
+                                // 2368 chains: 17 x 74 CTAs = 2.8 waves of 3 CTAs / SM (128 vertices: 2.2 waves, the third 17 % full)
 constexpr int kRmC = 32;        // chains per CTA
 constexpr int kRmLd = 34;       // row stride (doubles) of the coefficient tile and of the staged result
 
