@@ -174,6 +174,33 @@ def test_log_helper_samples_from_log_matches_oracle():
         api.LogHelper.samplesFromLog([api.jsonLogFormat(0, "p", {}, False, [], [], "")], 1, 1, 0)
 
 
+def test_kernel_algebra_builds_the_femur_kernel_terms():
+    """The Scalismo-style kernel algebra of the GPMM-construction mirror (apps/femur/CreateGPModel.scala:70-83) reduces to
+    the (scale, sigma, A) terms the device evaluates; checked against the oracle's pair-by-pair kernel written out by hand."""
+    from oracle import np_oracle as npo
+    rng = np.random.default_rng(2)
+    pts = rng.normal(0, 40, (30, 3)) * np.array([1.0, 0.8, 5.0])
+    k = api.femurKernel(pts)
+    d = api.getAxisOfMainVariance(pts)
+    base = d @ np.diag([10.0, 1.0, 1.0]) @ d.T
+    assert [(s, sg) for s, sg, _ in k.terms] == [(10.0, 90.0), (5.0, 40.0), (3.0, 10.0)]
+    np.testing.assert_allclose(k.terms[0][2], base, rtol=1e-14)
+    assert k.terms[1][2] is None and k.terms[2][2] is None
+    np.testing.assert_allclose(base, base.T, atol=1e-12)
+    assert abs(abs(d[2, 0]) - 1.0) < 0.05                      # the long axis carries the 10x variance
+    x, y = pts[:4], pts[4:9]
+    want = np.zeros((12, 15))
+    for i in range(4):
+        for j in range(5):
+            r2 = ((x[i] - y[j]) ** 2).sum()
+            want[3 * i:3 * i + 3, 3 * j:3 * j + 3] = base * 10.0 * np.exp(-r2 / 90.0 ** 2) + np.eye(3) * (5.0 * np.exp(-r2 / 40.0 ** 2) + 3.0 * np.exp(-r2 / 10.0 ** 2))
+    np.testing.assert_allclose(npo.gauss_mixture_kernel(x, y, k.terms), want, rtol=1e-13, atol=1e-300)
+    k2 = (api.GaussianKernel3D(20) * 2.0 + api.DiagonalKernel3D(api.GaussianKernel3D(5), 3)) * 0.5
+    assert [(s, sg) for s, sg, _ in k2.terms] == [(1.0, 20.0), (0.5, 5.0)]
+    with pytest.raises(ValueError):
+        api.DiagonalKernel3D(api.GaussianKernel3D(5), 2)
+
+
 def test_shard_ranges_cover_all_chains():
     for n, w in ((100, 8), (5, 2), (7, 4), (3, 8), (1184 * 8, 8)):
         spans = [sharding.shard_range(n, r, w) for r in range(w)]
