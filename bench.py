@@ -354,6 +354,17 @@ def run_gpu(args):
                     "share_of_step": shares.get("posterior_build"), "top_kernel_by_time": top,
                     "note": "achieved counts the reference's algorithmic flops per posterior (SURVEY 8d); hw_* counts the flops "
                             "actually executed after exploiting symmetry and the constant Gram term"}
+        # ---- BASELINE.json configs[0] shape: ONE chain, fixed seed - latency-bound by construction: steps/s of
+        # the device-resident loop with a single resident chain, next to the 1-core CPU port below -------------------
+        sc_steps = 300
+        th1 = torch.from_numpy(np.ascontiguousarray(th0_host[:1])).to(dev)
+        chain.run_device(1, 20, th1.data_ptr(), seed=seed, chain_id_offset=off)        # warm-up, sizes + captures the C = 1 graph
+        torch.cuda.synchronize()
+        chain.run_device(1, sc_steps, None, seed=seed, chain_id_offset=off)             # resumed: exactly sc_steps steps
+        sc_ms, _ = chain.last_run_stats()
+        single_chain = {"steps_per_s": sc_steps / (sc_ms * 1e-3), "ms_per_step": sc_ms / sc_steps, "steps": sc_steps,
+                        "note": "one chain resident on the GPU (configs[0] shape): every kernel of the step runs a single CTA / "
+                                "a handful of warps, so this is launch + dependent-latency time, not throughput"}
         # ---- CPU baseline: the oracle port of the same chain on this box's host cores (bounded sample) ------
         cores = os.cpu_count() or 1
         cb_rate, cb_dt, _ = oracle_chain_rate(m, tv, tc, ids, eids, tp, 1, args.cpu_steps, 1, closed_form=False)
@@ -372,7 +383,7 @@ def run_gpu(args):
                 "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / steps, "accept_rate": accept_rate,
                 "clocks": clocks.summary(), "roofline": roofline, "roofline_cholesky": roof_chol, "roofline_closest_point": roof_cp, "closest_point": cp,
                 "kernel_shares": shares, "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items() if v["launches"]},
-                "fp64_peak": fp64, "gather_ms": gather_ms,
+                "fp64_peak": fp64, "gather_ms": gather_ms, "single_chain": single_chain,
                 "cpu_baseline": {"value": cb_rate, "unit": UNIT, "cores": 1, "kind": "port",
                                  "sample": f"1 chain x {args.cpu_steps} MH steps of the same workload, oracle in the reference's structure, 1 thread ({cb_dt:.1f} s); host has {cores} cores"},
                 "cpu_baseline_optimised": {"value": opt_rate, "unit": UNIT, "cores": 1, "kind": "port",
