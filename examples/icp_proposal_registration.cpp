@@ -79,11 +79,21 @@ int main(int argc, char **argv) {
             for (double v : maps.normal) meanNormal += v / maps.normal.size();
         }
 
-        std::printf("{\"K\": %d, \"product_initial\": %.12g, \"host_mh_steps\": 20, \"host_mh_accepted\": %d, \"product_after_host_mh\": %.12g, "
+        // (4) apps/femur/CreateGPModel.scala:70-86 in small: isotropic two-scale Gaussian kernel, Nystrom on every 20th reference
+        // point, 8 basis functions - kernel matrix, eigen-decomposition and extension all on the device
+        std::vector<double> nys;
+        for (int i = 0; i < N; i += 20) nys.insert(nys.end(), ref.begin() + 3 * i, ref.begin() + 3 * i + 3);
+        auto gpKernel = MatrixValuedKernel::gaussian(40.0) * 5.0 + MatrixValuedKernel::gaussian(10.0) * 3.0;
+        auto lowRank = LowRankGaussianProcess::approximateGPNystrom(ctx, gpKernel, ref, nys, 8);
+        double varSum = 0.0, basisAbs = 0.0;
+        for (double v : lowRank.variance) varSum += v;
+        for (double v : lowRank.basis) basisAbs += std::fabs(v);
+
+        std::printf("{\"gp_variance_sum\": %.12g, \"gp_basis_abs_sum\": %.12g, \"K\": %d, \"product_initial\": %.12g, \"host_mh_steps\": 20, \"host_mh_accepted\": %d, \"product_after_host_mh\": %.12g, "
                     "\"fused_steps\": %d, \"fused_accepted\": %lld, \"fused_best_product\": %.12g, \"fused_best_product_recomputed\": %.12g, "
                     "\"fused_best_generated_by\": \"%s\", \"variability_samples\": %d, \"mean_total_variance\": %.12g, "
                     "\"mean_normal_variance\": %.12g}\n",
-                    K, p0, acc, p20, res.steps, (long long)res.accepted, res.bestProduct, pbest, res.best.generatedBy.c_str(),
+                    varSum, basisAbs, K, p0, acc, p20, res.steps, (long long)res.accepted, res.bestProduct, pbest, res.best.generatedBy.c_str(),
                     (int)picked.size(), meanTotal, meanNormal);
         return 0;
     } catch (const std::exception &e) {

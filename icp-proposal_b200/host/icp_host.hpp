@@ -447,6 +447,55 @@ struct PosteriorVariability {
     }
 };
 
+// ---- GPMM construction from analytic kernels (apps/femur/CreateGPModel.scala:68-93) -------------------------------
+// sum of terms scale * exp(-|x - y|^2 / sigma^2) * A: what `*` and `+` build from Scalismo's GaussianKernel3D / DiagonalKernel3D
+class MatrixValuedKernel {
+public:
+    std::vector<icp_kernel_term> terms;
+    static MatrixValuedKernel gaussian(double sigma, double scale = 1.0) {          // DiagonalKernel3D(GaussianKernel3D(sigma), 3) * scale
+        MatrixValuedKernel k;
+        icp_kernel_term t{scale, sigma, {1, 0, 0, 0, 1, 0, 0, 0, 1}};
+        k.terms.push_back(t);
+        return k;
+    }
+    MatrixValuedKernel operator*(double f) const { MatrixValuedKernel k = *this; for (auto &t : k.terms) t.scale *= f; return k; }
+    MatrixValuedKernel operator+(const MatrixValuedKernel &o) const {
+        MatrixValuedKernel k = *this;
+        k.terms.insert(k.terms.end(), o.terms.begin(), o.terms.end());
+        return k;
+    }
+    MatrixValuedKernel withMatrix(const double B[9]) const {                         // baseMatrix * kernel(x, y) (:79)
+        MatrixValuedKernel k = *this;
+        for (auto &t : k.terms) {
+            double a[9];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) a[3 * r + c] = B[3 * r] * t.A[c] + B[3 * r + 1] * t.A[3 + c] + B[3 * r + 2] * t.A[6 + c];
+            std::memcpy(t.A, a, sizeof a);
+        }
+        return k;
+    }
+};
+
+struct LowRankGaussianProcess {
+    struct Model { std::vector<double> basis, variance; };   // pcaBasis 3N x K row-major, pcaVariance K
+    // LowRankGaussianProcess.approximateGPNystrom (:86), every step on the device: kernel matrix of the Nystrom points, its
+    // leading eigenpairs (one-sided Jacobi), Nystrom extension to all model points
+    static Model approximateGPNystrom(Context &ctx, const MatrixValuedKernel &kernel, const std::vector<double> &points,
+                                      const std::vector<double> &nystromPoints, int numBasisFunctions) {
+        const int N = (int)points.size() / 3, m = (int)nystromPoints.size() / 3, n = 3 * m, K = numBasisFunctions;
+        std::vector<double> kmm((size_t)n * n), w(K), V((size_t)n * K);
+        check(icp_gpmm_kernel_matrix(ctx.handle(), m, nystromPoints.data(), m, nystromPoints.data(), kernel.terms.data(),
+                                     (int)kernel.terms.size(), kmm.data()), ctx.handle());
+        check(icp_gpmm_eigen_psd(ctx.handle(), n, kmm.data(), K, w.data(), V.data()), ctx.handle());
+        Model out;
+        out.basis.resize((size_t)3 * N * K);
+        out.variance.resize(K);
+        check(icp_gpmm_nystrom_extend(ctx.handle(), N, points.data(), m, nystromPoints.data(), kernel.terms.data(),
+                                      (int)kernel.terms.size(), K, V.data(), w.data(), out.basis.data(), out.variance.data()), ctx.handle());
+        return out;
+    }
+};
+
 // ---- Metropolis-Hastings ---------------------------------------------------------------------------------------------
 // Scalismo MetropolisHastings.next over the per-call (drop-in) classes
 class MetropolisHastings {

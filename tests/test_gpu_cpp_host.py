@@ -74,4 +74,10 @@ def test_cpp_host_mirror_example(ctx, twin31, tmp_path):
     np.testing.assert_allclose(res["mean_total_variance"], pv["total_variance"].mean(), rtol=1e-9)
     np.testing.assert_allclose(res["mean_normal_variance"], pv["normal_variance"].mean(), rtol=1e-9)
     assert 0 < res["mean_normal_variance"] <= res["mean_total_variance"]
+    # GPMM construction through the C++ mirror == through the Python mirror (same device calls)
+    from icp_proposal_b200 import api
+    kern = api.DiagonalKernel3D(api.GaussianKernel3D(40.0), 3) * 5.0 + api.DiagonalKernel3D(api.GaussianKernel3D(10.0), 3) * 3.0
+    basis, var = api.LowRankGaussianProcess.approximateGPNystrom(ctx, kern, m["ref"], m["ref"][::20], 8)
+    np.testing.assert_allclose(res["gp_variance_sum"], var.sum(), rtol=1e-10)
+    np.testing.assert_allclose(res["gp_basis_abs_sum"], np.abs(basis).sum(), rtol=1e-9)
     chain.close(); ev.close(); model.close(); tgt.close()
