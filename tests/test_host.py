@@ -222,6 +222,20 @@ def _gloo_worker(rank, world, port, q):
     want = sharding.combine_statistics(sharding.chain_statistics(theta, logv)[None])
     ok = got["n"] == want["n"] and np.allclose(got["mean"], want["mean"], rtol=1e-13) and \
         np.allclose(got["var"], want["var"], rtol=1e-10) and np.isclose(got["mean_logp"], want["mean_logp"], rtol=1e-13)
+    # posterior variability maps: every rank reduces its own samples, the gathered centred moments merge to the unsharded maps
+    from oracle import np_oracle as npo
+    S, nv = 11, 12
+    verts = rng.normal(0, 50, (nv, 3)) + 200.0
+    tris = np.array([[0, 1, 2], [2, 3, 4], [4, 5, 6], [6, 7, 8], [8, 9, 10], [10, 11, 0], [1, 3, 5], [7, 9, 11]])
+    meshes = [verts + rng.normal(0, 0.3, verts.shape) for _ in range(S)]
+    slo, shi = sharding.shard_range(S, rank, world)
+    m_loc, c_loc, _, _ = npo.posterior_variability(meshes[slo:shi], tris, ref_verts=verts, sum_normals=False)
+    parts = sharding.gather_statistics(sharding.variability_partials(shi - slo, m_loc, c_loc))
+    nrm = npo.vertex_normals(verts, tris)
+    merged = sharding.merge_variability(parts, normals=nrm)
+    m_all, c_all, t_all, a_all = npo.posterior_variability(meshes, tris, ref_verts=verts, sum_normals=False)
+    ok = ok and merged["n"] == S and np.allclose(merged["mean"], m_all, rtol=1e-14) and np.allclose(merged["cov"], c_all, rtol=1e-9, atol=1e-14) \
+        and np.allclose(merged["total_variance"], t_all, rtol=1e-10) and np.allclose(merged["normal_variance"], a_all, rtol=1e-9)
     q.put((rank, bool(ok), lo, hi))
     dist.barrier()
     dist.destroy_process_group()
