@@ -55,7 +55,8 @@ int32_t icp_version(icp_ctx ctx, char *buf, size_t n);
 
 /* ---- (2) model: StatisticalMeshModel (read at apps/femur/LoadTestData.scala:34-35) ---------- */
 /* ref_xyz N x 3, mean_def 3N (NULL = zero mean deformation), basis 3N x K unscaled U,
- * variance K, tris T x 3. Q = U diag(sqrt(variance)) is formed on the device. */
+ * variance K, tris T x 3. Q = U diag(sqrt(variance)) is formed on the device. 1 <= K <= 224 (the reference ships
+ * ranks 51, 101 and 201); larger ranks are ICP_ERR_INVALID_ARGUMENT. */
 int32_t icp_model_create(icp_ctx ctx, int32_t N, int32_t T, int32_t K, const double *ref_xyz,
                          const double *mean_def, const double *basis, const double *variance,
                          const int32_t *tris, icp_model *out);
