@@ -65,6 +65,28 @@ def main():
         xyz = om.transformed_mesh(theta)
         g["mesh_checksum"] = [float(xyz.sum()), float(np.abs(xyz).sum())]
         golden[name] = g
+    # posterior variability maps of five fixed samples of the 50-component model, and the femur kernel of
+    # apps/femur/CreateGPModel.scala:70-83 on the first reference points (oracle/np_oracle.py)
+    from oracle import np_oracle as npo
+    K50 = len(m50["variance"])
+    om50 = orc.Model(m50["ref"], m50["cells"], m50["basis"], m50["variance"])
+    rng = np.random.default_rng(77)
+    thetas = np.zeros((5, K50 + 10)); thetas[:, 0] = 1.0; thetas[:, 7:10] = m50["ref"].mean(0)
+    thetas[:, 10:] = rng.normal(0, 0.4, (5, K50))
+    meshes = [om50.transformed_mesh(t) for t in thetas]
+    mean, cov, total, along = npo.posterior_variability(meshes, m50["cells"], sum_normals=True)
+    golden["variability_gpmm_50"] = {"thetas": thetas.tolist(), "mean_checksum": [float(mean.sum()), float(np.abs(mean).sum())],
+                                     "total_first8": total[:8].tolist(), "normal_first8": along[:8].tolist(),
+                                     "total_sum": float(total.sum()), "normal_sum": float(along.sum())}
+    pts = m50["ref"][:12]
+    c = m50["ref"] - m50["ref"].mean(0)
+    u = np.linalg.svd(c.T @ c / len(c))[0]
+    base = u @ np.diag([10.0, 1.0, 1.0]) @ u.T
+    terms = [(10.0, 90.0, base), (5.0, 40.0, None), (3.0, 10.0, None)]
+    kk = npo.gauss_mixture_kernel(pts, pts, terms)
+    w = np.linalg.eigvalsh(kk)[::-1]
+    golden["femur_kernel"] = {"base_matrix": base.tolist(), "k_checksum": [float(kk.sum()), float(np.abs(kk).sum())],
+                              "k_row0_first9": kk[0, :9].tolist(), "eigenvalues_first6": w[:6].tolist()}
     with open(f"{OUT}/femur_golden.json", "w") as f:
         json.dump(golden, f, indent=1)
     print({k: os.path.getsize(f"{OUT}/{k}") for k in sorted(os.listdir(OUT))})

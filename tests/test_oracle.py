@@ -308,3 +308,27 @@ def test_nystrom_oracle_reproduces_the_kernel_on_the_nystrom_points():
     np.testing.assert_allclose((q @ q.T)[:36, :36], kmm, rtol=1e-9, atol=1e-9)
     # orthonormality of the discretised eigenfunctions on the Nystrom points: (1/m) sum_x phi_i(x) phi_j(x) = delta_ij
     np.testing.assert_allclose(basis[:36].T @ basis[:36] / 12, np.eye(36), atol=1e-7)
+
+
+def test_golden_variability_and_femur_kernel(femur):
+    """The oracle restatements of the SURVEY 8f rows reproduce their committed golden values on the reference's femur
+    fixtures (tests/golden/make_golden.py)."""
+    g = femur["golden"]["variability_gpmm_50"]
+    m = femur["gpmm_50"]
+    om = orc.Model(femur["ref"], femur["cells"], m["basis"], m["variance"])
+    meshes = [om.transformed_mesh(np.array(t)) for t in g["thetas"]]
+    mean, cov, total, along = npo.posterior_variability(meshes, femur["cells"], sum_normals=True)
+    np.testing.assert_allclose([mean.sum(), np.abs(mean).sum()], g["mean_checksum"], rtol=1e-12)
+    np.testing.assert_allclose(total[:8], g["total_first8"], rtol=1e-9)
+    np.testing.assert_allclose(along[:8], g["normal_first8"], rtol=1e-9)
+    np.testing.assert_allclose([total.sum(), along.sum()], [g["total_sum"], g["normal_sum"]], rtol=1e-9)
+    k = femur["golden"]["femur_kernel"]
+    base = np.array(k["base_matrix"])
+    terms = [(10.0, 90.0, base), (5.0, 40.0, None), (3.0, 10.0, None)]
+    kk = npo.gauss_mixture_kernel(femur["ref"][:12], femur["ref"][:12], terms)
+    np.testing.assert_allclose([kk.sum(), np.abs(kk).sum()], k["k_checksum"], rtol=1e-12)
+    np.testing.assert_allclose(kk[0, :9], k["k_row0_first9"], rtol=1e-12)
+    np.testing.assert_allclose(np.linalg.eigvalsh(kk)[::-1][:6], k["eigenvalues_first6"], rtol=1e-9)
+    # the host mirror builds the same base matrix from the reference points (up to the sign-free product d diag d^T)
+    from icp_proposal_b200 import api
+    np.testing.assert_allclose(api.femurKernel(femur["ref"]).terms[0][2], base, rtol=1e-9, atol=1e-12)
