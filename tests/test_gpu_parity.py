@@ -453,3 +453,50 @@ def test_full_size_properties(ctx, twin101):
     want = orc.Mesh(verts, tris).closest_point(q[sub], brute=True)
     np.testing.assert_allclose(np.sqrt(d2[sub]), np.sqrt(want[3]), rtol=1e-10, atol=1e-11)
     tgt.close()
+
+
+@pytest.mark.parametrize("which", ["gpmm_50", "gpmm_100", "gpmm_200"])
+def test_device_reproduces_committed_golden_values(ctx, femur, which):
+    """The CUDA path against the committed golden values (tests/golden/femur_golden.json, written by make_golden.py from the
+    reference-structure oracle on the reference's own femur fixtures): no oracle call in this test."""
+    g = femur["golden"][which]
+    m = dict(ref=femur["ref"], cells=femur["cells"], target=femur["target"], target_cells=femur["target_cells"], **femur[which])
+    K = len(m["variance"])
+    model, tgt = _dev(ctx, m)
+    theta = np.array(g["theta"])
+    ids, eids = np.arange(g["n_icp"]), np.arange(g["n_eval"])
+    tp = femur["target"][:: max(1, len(femur["target"]) // (2 * K))][: 2 * K]
+    xyz = model.reconstruct(theta)[0]
+    np.testing.assert_allclose([xyz.sum(), np.abs(xyz).sum()], g["mesh_checksum"], rtol=1e-11)
+    for direction, name in ((_lib.MODEL_SAMPLING, "model_sampling"), (_lib.TARGET_SAMPLING, "target_sampling")):
+        gp = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, direction, True, ids, tp)
+        mu, M, n = gp.posterior(theta)
+        assert n[0] == g[name]["n_obs"]
+        np.testing.assert_allclose(mu[0], g[name]["mu"], rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose(np.diag(M[0]), g[name]["M_diag"], rtol=1e-9)
+        np.testing.assert_allclose(np.linalg.norm(M[0]), g[name]["M_fro"], rtol=1e-9)
+        to = gp.propose(theta, np.zeros((1, K)))
+        np.testing.assert_allclose(to[0, 10:], g[name]["propose_z0"], rtol=RTOL, atol=1e-8)
+        np.testing.assert_allclose(gp.log_transition(theta, to)[0], g[name]["log_transition_to_z0"], rtol=RTOL)
+        gp.close()
+    for mode, key in ((_lib.MODEL_TO_TARGET, "independent_m2t"), (_lib.SYMMETRIC, "independent_sym")):
+        ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, mode, True, 0.0, 2.0, 0.0, eids, tp)
+        v = ev.log_value(theta)[0]
+        np.testing.assert_allclose(v[2], g[key], rtol=RTOL)
+        np.testing.assert_allclose(v[1], g["prior"], rtol=1e-12)
+        np.testing.assert_allclose(v[0], g["prior"] + g[key], rtol=RTOL)
+        ev.close()
+    ev = core.Evaluator(model, tgt, _lib.EVAL_HAUSDORFF, 0, False, 100.0)
+    np.testing.assert_allclose(ev.log_value(theta)[0, 2], g["hausdorff"], rtol=RTOL)
+    ev.close()
+    ev = core.Evaluator(model, tgt, _lib.EVAL_COLLECTIVE, _lib.SYMMETRIC, True, 0.1, 0.3, 1.0, eids, tp)
+    np.testing.assert_allclose(ev.log_value(theta)[0, 2], g["collective_sym"], rtol=RTOL)
+    ev.close()
+    if which == "gpmm_50":
+        gv = femur["golden"]["variability_gpmm_50"]
+        pv = core.posterior_variability(model, np.array(gv["thetas"]), True)
+        np.testing.assert_allclose([pv["mean"].sum(), np.abs(pv["mean"]).sum()], gv["mean_checksum"], rtol=1e-11)
+        np.testing.assert_allclose(pv["total_variance"][:8], gv["total_first8"], rtol=1e-8)
+        np.testing.assert_allclose(pv["normal_variance"][:8], gv["normal_first8"], rtol=1e-8)
+        np.testing.assert_allclose([pv["total_variance"].sum(), pv["normal_variance"].sum()], [gv["total_sum"], gv["normal_sum"]], rtol=1e-8)
+    model.close(); tgt.close()
