@@ -12,7 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libicpcuda" + ("_" + os.environ["ICPCUDA_LIB_TAG"] if os.environ.get("ICPCUDA_LIB_TAG") else "") + ".so")
 
 OK = 0
-ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_EMPTY_SET, ERR_NOT_POSITIVE_DEFINITE = -1, -2, -3, -4, -5
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_EMPTY_SET, ERR_NOT_POSITIVE_DEFINITE, ERR_NAN = -1, -2, -3, -4, -5, -6
+CHAIN_EMPTY_SET, CHAIN_NOT_POSITIVE_DEFINITE, CHAIN_NAN_TRANSITION, CHAIN_NAN_VALUE = 1, 2, 4, 8
+FACTOR_CHOLESKY, FACTOR_SVD = 0, 1
 MODEL_SAMPLING, TARGET_SAMPLING = 0, 1
 EVAL_ACCEPT_ALL, EVAL_INDEPENDENT, EVAL_HAUSDORFF, EVAL_COLLECTIVE = 0, 1, 2, 3
 MODEL_TO_TARGET, TARGET_TO_MODEL, SYMMETRIC = 0, 1, 2
@@ -34,7 +36,7 @@ class IcpCudaError(RuntimeError):
 
 class ProposalParams(C.Structure):
     _fields_ = [("step_length", C.c_double), ("tangential_noise", C.c_double), ("noise_along_normal", C.c_double),
-                ("direction", C.c_int32), ("boundary_aware", C.c_int32)]
+                ("direction", C.c_int32), ("boundary_aware", C.c_int32), ("factor", C.c_int32), ("reserved", C.c_int32)]
 
 
 class EvaluatorParams(C.Structure):
@@ -54,7 +56,8 @@ class ChainIO(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("chain_id_offset", C.c_uint64), ("u_comp", C.c_void_p), ("z", C.c_void_p),
                 ("u_acc", C.c_void_p), ("log_component", C.c_void_p), ("log_accepted", C.c_void_p),
                 ("log_values", C.c_void_p), ("log_theta", C.c_void_p), ("theta_final", C.c_void_p),
-                ("n_accepted", C.c_void_p)]
+                ("n_accepted", C.c_void_p), ("status", C.c_void_p), ("theta_best", C.c_void_p), ("value_best", C.c_void_p),
+                ("metrics_interval", C.c_int32), ("reserved", C.c_int32), ("log_metrics", C.c_void_p)]
 
 
 _SIGS = {
@@ -88,6 +91,7 @@ _SIGS = {
     "icp_eval_log_value": [_h, C.c_int32, _dp, _dp, _ip],
     "icp_eval_prior": [_h, C.c_int32, _dp, _dp],
     "icp_registration_metrics": [_h, _h, C.c_int32, _dp, _dp],
+    "icp_dice_coefficient": [_h, _h, C.c_int32, _dp, C.c_int32, _dp, C.c_uint64, _dp],
     "icp_posterior_variability": [_h, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _dp],
     "icp_gpmm_kernel_matrix": [_h, C.c_int32, _dp, C.c_int32, _dp, C.POINTER(KernelTerm), C.c_int32, _dp],
     "icp_gpmm_eigen_psd": [_h, C.c_int32, _dp, C.c_int32, _dp, _dp],

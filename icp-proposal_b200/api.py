@@ -493,7 +493,16 @@ class JSONAcceptRejectLogger:
         return sum(l.status for l in f) / len(f) if f else float("nan")
 
     def prettyPrint(self):
-        return json.dumps([dataclasses.asdict(l) for l in self.logStatus], indent=2)
+        # spray-json cannot represent NaN / infinities (it writes null): keep the file loadable by the reference's loader
+        def clean(x):
+            if isinstance(x, float) and not math.isfinite(x):
+                return None
+            if isinstance(x, dict):
+                return {k: clean(v) for k, v in x.items()}
+            if isinstance(x, list):
+                return [clean(v) for v in x]
+            return x
+        return json.dumps([clean(dataclasses.asdict(l)) for l in self.logStatus], indent=2, allow_nan=False)
 
     def writeLog(self):
         try:
@@ -701,14 +710,13 @@ class SamplingRegistration:
         else:
             th0 = np.tile((initialModelParameters or self.initialParametersZero).allParameters, (n_chains, 1))
         out = chain.run(th0, numOfSamples, seed=self.seed)
+        # BestSampleLogger (SamplingRegistration.scala:58,87) tracked on the device: theta0 and the state that is current
+        # after every step compete, so a retained initial state can win (icp_chain_io.theta_best / value_best)
         best = []
         for c in range(n_chains):
-            prod = np.where(out["accepted"][:, c], out["values"][:, c, 0], -np.inf)
-            if np.isfinite(prod).any():
-                s = int(np.argmax(prod))
-                best.append(ModelFittingParameters.from_vector(out["theta"][s, c], names[int(out["component"][s, c])]))
-            else:
-                best.append(ModelFittingParameters.from_vector(th0[c]))
+            same = np.nonzero((out["theta"][:, c] == out["theta_best"][c]).all(axis=1) & out["accepted"][:, c])[0]
+            name = names[int(out["component"][same[0], c])] if len(same) else "Anonymous"
+            best.append(ModelFittingParameters.from_vector(out["theta_best"][c], name))
         self.last_run = out
         if jsonName is not None:
             logger = JSONAcceptRejectLogger(jsonName)

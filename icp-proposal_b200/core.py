@@ -169,11 +169,12 @@ class IcpProposal:
     """Device side of NonRigidIcpProposal (api/sampling/proposals/NonRigidIcpProposal.scala)."""
 
     def __init__(self, model: Model, target: Target, step_length, tangential_noise, noise_along_normal, direction,
-                 boundary_aware, model_point_ids, target_points):
+                 boundary_aware, model_point_ids, target_points, factor=_lib.FACTOR_CHOLESKY):
         self.model, self.target, self.lib, self.ctx = model, target, model.lib, model.ctx
         self.ids = i32(np.asarray(model_point_ids).reshape(-1))
         self.tp = f64(np.asarray(target_points, dtype=np.float64).reshape(-1, 3))
-        self.params = _lib.ProposalParams(step_length, tangential_noise, noise_along_normal, int(direction), int(boundary_aware))
+        self.params = _lib.ProposalParams(step_length, tangential_noise, noise_along_normal, int(direction), int(boundary_aware),
+                                          int(factor), 0)
         self.h = C.c_void_p()
         check(self.lib.icp_proposal_create(model.h, target.h, C.byref(self.params), iptr(self.ids), len(self.ids),
                                            dptr(self.tp), len(self.tp), C.byref(self.h)), self.ctx.h)
@@ -249,6 +250,19 @@ def registration_metrics(model: Model, target: Target, theta):
     th, c = model._theta(theta)
     out = np.empty((c, 4))
     check(model.lib.icp_registration_metrics(model.h, target.h, c, dptr(th), dptr(out)), model.ctx.h)
+    return out
+
+
+def dice_coefficient(model: Model, target: Target, theta, unit_samples=None, n_samples=10000, seed=0):
+    """icp_dice_coefficient: MeshMetrics.diceCoefficient(transformedMesh(theta), target) per parameter vector."""
+    th, c = model._theta(theta)
+    out = np.empty(c)
+    us = None
+    if unit_samples is not None:
+        us = f64(unit_samples).reshape(-1, 3)
+        n_samples = len(us)
+    check(model.lib.icp_dice_coefficient(model.h, target.h, c, dptr(th), int(n_samples), dptr(us) if us is not None else None,
+                                         int(seed), dptr(out)), model.ctx.h)
     return out
 
 
@@ -328,7 +342,10 @@ class Chain:
         check(self.lib.icp_chain_create(model.h, target.h, arr, len(components), evaluator.h, self.max_chains,
                                         C.byref(self.h)), self.ctx.h)
 
-    def run(self, theta0, n_steps, seed=1024, chain_id_offset=0, u_comp=None, z=None, u_acc=None, log_theta=True):
+    def run(self, theta0, n_steps, seed=1024, chain_id_offset=0, u_comp=None, z=None, u_acc=None, log_theta=True,
+            raise_on_status=True, metrics_interval=0):
+        """raise_on_status=False: a per-chain status failure (empty set / not positive definite / NaN, the cases in which the
+        reference throws) does not raise; the result carries `status` (per-chain words) and `status_code` (the return code)."""
         th, c = self.model._theta(theta0)
         K, L = self.model.K, self.model.K + THETA0
         io = _lib.ChainIO()
@@ -346,8 +363,19 @@ class Chain:
             thl = np.empty((n_steps, c, L))
             io.log_theta = thl.ctypes.data
         io.theta_final, io.n_accepted = final.ctypes.data, nacc.ctypes.data
-        check(self.lib.icp_chain_run(self.h, c, int(n_steps), dptr(th), C.byref(io)), self.ctx.h)
-        return dict(component=comp, accepted=acc.astype(bool), values=vals, theta=thl, theta_final=final, n_accepted=nacc)
+        status = np.zeros(c, np.int32)
+        io.status = status.ctypes.data
+        best, vbest = np.empty((c, L)), np.empty(c)
+        io.theta_best, io.value_best = best.ctypes.data, vbest.ctypes.data
+        metrics = None
+        if metrics_interval > 0:
+            metrics = np.empty((n_steps // metrics_interval, c, 4))
+            io.metrics_interval, io.log_metrics = int(metrics_interval), metrics.ctypes.data
+        rc = self.lib.icp_chain_run(self.h, c, int(n_steps), dptr(th), C.byref(io))
+        if rc != _lib.OK and (raise_on_status or rc not in (_lib.ERR_EMPTY_SET, _lib.ERR_NOT_POSITIVE_DEFINITE, _lib.ERR_NAN)):
+            check(rc, self.ctx.h)
+        return dict(component=comp, accepted=acc.astype(bool), values=vals, theta=thl, theta_final=final, n_accepted=nacc,
+                    status=status, status_code=rc, theta_best=best, value_best=vbest, metrics=metrics)
 
     def run_device(self, C_, n_steps, theta0_ptr, seed=1024, chain_id_offset=0, log_component=0, log_accepted=0,
                    log_values=0, log_theta=0, theta_final=0, n_accepted=0, async_=False):

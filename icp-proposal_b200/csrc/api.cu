@@ -225,6 +225,13 @@ extern "C" int32_t icp_model_create(icp_ctx ctx, int32_t N, int32_t T, int32_t K
         DevBuf<double> dU, dvar;
         dU.upload(basis, n3 * K, s);
         dvar.upload(variance, K, s);
+        m->h_var.assign(variance, variance + K);
+        {
+            std::vector<double> sv(Kp, 1.0);
+            for (int j = 0; j < K; j++) sv[j] = std::sqrt(variance[j]);
+            m->sqrt_var.upload(sv.data(), sv.size(), s);
+            sync_stream(ctx);
+        }
         m->Q.alloc(n3 * Kp);
         m->QT.alloc(n3 * Kp);
         launch_scale_basis((int)n3, K, Kp, dU.p, dvar.p, m->Q.p, m->QT.p, s);
@@ -345,6 +352,29 @@ extern "C" int32_t icp_target_create(icp_ctx ctx, int32_t Nt, int32_t Tt, const 
         t->h_boundary = boundary_table(Nt, Tt, tris);
         t->has_boundary = std::any_of(t->h_boundary.begin(), t->h_boundary.end(), [](uint8_t b) { return b != 0; });
         t->boundary.upload(t->h_boundary.data(), t->h_boundary.size(), s);
+        {   // Scalismo vertexNormals: normalised unweighted mean of the adjacent unit cell normals
+            std::vector<double> acc((size_t)3 * Nt, 0.0);
+            std::vector<int> cnt(Nt, 0);
+            for (int k = 0; k < Tt; k++) {
+                const double *a = xyz + 3 * (size_t)tris[3 * k], *b = xyz + 3 * (size_t)tris[3 * k + 1], *c = xyz + 3 * (size_t)tris[3 * k + 2];
+                const double u[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, v[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+                double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+                const double nrm = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+                for (int e = 0; e < 3; e++) {
+                    const int vtx = tris[3 * k + e];
+                    for (int d = 0; d < 3; d++) acc[(size_t)3 * vtx + d] += n[d] / nrm;
+                    cnt[vtx]++;
+                }
+            }
+            for (int vtx = 0; vtx < Nt; vtx++) {
+                double n[3];
+                for (int d = 0; d < 3; d++) n[d] = acc[(size_t)3 * vtx + d] / (double)cnt[vtx];
+                const double nrm = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+                for (int d = 0; d < 3; d++) acc[(size_t)3 * vtx + d] = n[d] / nrm;
+            }
+            t->vnormals.upload(acc.data(), acc.size(), s);
+            sync_stream(ctx);
+        }
         double scale = std::max(max_abs(xyz, (size_t)3 * Nt), 1e-3);
         for (int d = 0; d < 3; d++) { t->lo[d] = 1e300; t->hi[d] = -1e300; }
         for (int v = 0; v < Nt; v++)
@@ -588,6 +618,9 @@ extern "C" int32_t icp_proposal_create(icp_model m, icp_target t, const icp_prop
         ICP_REQUIRE(params->direction == ICP_MODEL_SAMPLING || params->direction == ICP_TARGET_SAMPLING, "bad direction");
         ICP_REQUIRE(params->step_length != 0.0 && std::isfinite(params->step_length), "step_length must be finite and non-zero");
         ICP_REQUIRE(params->tangential_noise > 0 && params->noise_along_normal > 0, "noise std-devs must be > 0");
+        ICP_REQUIRE(params->factor == ICP_FACTOR_CHOLESKY || params->factor == ICP_FACTOR_SVD, "bad covariance factor");
+        if (params->factor == ICP_FACTOR_SVD)
+            for (double v : m->h_var) ICP_REQUIRE(v > 0.0, "ICP_FACTOR_SVD needs strictly positive variances");
         check_ids(m->N, model_point_ids, n_ids);
         ICP_REQUIRE(n_tp >= 0 && (n_tp == 0 || target_points != nullptr), "bad target point list");
         p = new icp_proposal_s();
@@ -648,7 +681,7 @@ void nearest_model_vertex(icp_model m, int C, const double *d_X, int64_t nq, con
 }
 
 void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const double *d_X, PosteriorWork &w, double *d_L,
-                        double *d_mu, const int *d_out_slot, cudaStream_t s, const SharedCp *shared) {
+                        double *d_mu, const int *d_out_slot, cudaStream_t s, const SharedCp *shared, double *d_W) {
     if (C <= 0) return;
     icp_model m = p->model;
     icp_target t = p->target;
@@ -713,6 +746,7 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
         launch_posterior_build(md, C, od, w.M.p, w.b.p, s, gfp);
         launch_cholesky_solve(C, m->K, Kp, w.M.p, w.b.p, d_L, d_mu, d_out_slot, w.status.p, s, w.Mp.p);
     }
+    if (d_W) launch_svd_factor(C, m->K, Kp, d_L, m->sqrt_var.p, d_out_slot, d_W, w.svd_scratch, s);
 }
 
 }  // namespace icp
@@ -763,6 +797,7 @@ static std::vector<int> ensure_posteriors(icp_proposal p, int C, const double *t
         p->slot_key.assign(want, std::string());
         p->cache_L.alloc((size_t)want * Kp * Kp);
         p->cache_mu.alloc((size_t)want * Kp);
+        if (p->prm.factor == ICP_FACTOR_SVD) p->cache_W.alloc((size_t)want * Kp * Kp);
         p->cache_next = 0;
     }
     std::vector<int> slot(C, -1);
@@ -800,7 +835,8 @@ static std::vector<int> ensure_posteriors(icp_proposal p, int C, const double *t
         }
         p->s_theta2.upload(th.data(), th.size(), s);
         p->s_slot.upload(out_slot.data(), nm, s);
-        posterior_pipeline(p, nm, p->s_theta2.p, nullptr, p->work, p->cache_L.p, p->cache_mu.p, p->s_slot.p, s);
+        posterior_pipeline(p, nm, p->s_theta2.p, nullptr, p->work, p->cache_L.p, p->cache_mu.p, p->s_slot.p, s, nullptr,
+                           p->prm.factor == ICP_FACTOR_SVD ? p->cache_W.p : nullptr);
         sync_stream(p->model->ctx);  // host staging vectors go out of scope
     }
     return slot;
@@ -827,7 +863,7 @@ extern "C" int32_t icp_propose(icp_proposal p, int32_t C, const double *theta, c
     dslot.upload(slot.data(), C, s);
     p->s_out.ensure((size_t)C * Lt);
     launch_propose(m->dev(), C, p->prm.step_length, p->s_theta.p, p->s_z.p, p->cache_L.p, p->cache_mu.p, dslot.p,
-                   p->s_out.p, s);
+                   p->s_out.p, s, p->prm.factor == ICP_FACTOR_SVD ? p->cache_W.p : nullptr);
     download(theta_out, p->s_out.p, (size_t)C * Lt, s);
     sync_stream(_ctx);
     ICP_API_END
@@ -886,7 +922,7 @@ extern "C" int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t dire
     icp_proposal_s tmp;
     tmp.model = m; tmp.target = t;
     tmp.prm.step_length = step_length; tmp.prm.tangential_noise = 1; tmp.prm.noise_along_normal = 1;
-    tmp.prm.direction = direction; tmp.prm.boundary_aware = 0;
+    tmp.prm.direction = direction; tmp.prm.boundary_aware = 0; tmp.prm.factor = ICP_FACTOR_CHOLESKY;
     tmp.n_ids = n_ids; tmp.n_tp = n_tp;
     tmp.ids.upload(model_point_ids, n_ids, s);
     tmp.tp.upload(target_points, (size_t)3 * n_tp, s);
@@ -1084,80 +1120,6 @@ extern "C" int32_t icp_eval_prior(icp_model m, int32_t C, const double *theta, d
     m->s_d.ensure(C);
     launch_prior(C, m->K, m->s_theta.p, m->s_d.p, s);
     download(out, m->s_d.p, C, s);
-    sync_stream(_ctx);
-    ICP_API_END
-}
-
-// RegistrationComparison (api/other/RegistrationComparison.scala:24-49): avg / Hausdorff / boundary-aware avg + max
-__global__ void __launch_bounds__(128) k_metrics(int N, int Nt, const double *__restrict__ d2_m2t,
-                                                 const uint8_t *__restrict__ skip, const double *__restrict__ d2_t2m,
-                                                 double *__restrict__ out) {
-    __shared__ double red[4][128];
-    int c = blockIdx.x;
-    double s = 0, mx = 0, sb = 0, cb = 0, mb = -INFINITY, mt = 0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        double d = sqrt(d2_m2t[(size_t)c * N + i]);
-        s += d; mx = fmax(mx, d);
-        if (!(skip && skip[(size_t)c * N + i])) { sb += d; cb += 1; mb = fmax(mb, d); }
-    }
-    for (int i = threadIdx.x; i < Nt; i += blockDim.x) mt = fmax(mt, sqrt(d2_t2m[(size_t)c * Nt + i]));
-    red[0][threadIdx.x] = s; red[1][threadIdx.x] = fmax(mx, mt); red[2][threadIdx.x] = sb; red[3][threadIdx.x] = cb;
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-            red[0][threadIdx.x] += red[0][threadIdx.x + o];
-            red[1][threadIdx.x] = fmax(red[1][threadIdx.x], red[1][threadIdx.x + o]);
-            red[2][threadIdx.x] += red[2][threadIdx.x + o];
-            red[3][threadIdx.x] += red[3][threadIdx.x + o];
-        }
-        __syncthreads();
-    }
-    double avg = red[0][0] / N, hd = red[1][0], avgb = red[2][0] / red[3][0];
-    __syncthreads();
-    red[0][threadIdx.x] = mb;
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-        if (threadIdx.x < o) red[0][threadIdx.x] = fmax(red[0][threadIdx.x], red[0][threadIdx.x + o]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { out[4 * c] = avg; out[4 * c + 1] = hd; out[4 * c + 2] = avgb; out[4 * c + 3] = red[0][0]; }
-}
-
-extern "C" int32_t icp_registration_metrics(icp_model m, icp_target t, int32_t C, const double *theta, double *out) {
-    ICP_API_BEGIN(m ? m->ctx : nullptr)
-    ICP_REQUIRE(t && t->ctx == m->ctx, "bad target");
-    if (C == 0) return ICP_OK;
-    ICP_REQUIRE(out != nullptr, "out is null");
-    cudaStream_t s = _ctx->stream;
-    upload_theta(m, C, theta, m->s_theta, s);
-    const int N = m->N, Nt = t->Nt;
-    DevBuf<double> X, d2a, cpa, d2b, dout;
-    DevBuf<int> prim;
-    DevBuf<uint8_t> skip;
-    X.alloc((size_t)C * N * 3); d2a.alloc((size_t)C * N); cpa.alloc((size_t)C * N * 3); d2b.alloc((size_t)C * Nt); dout.alloc((size_t)4 * C);
-    launch_reconstruct(m->dev(), C, m->s_theta.p, X.p, s);
-    // every model vertex against the target surface
-    NearestArgs a;
-    a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = N; a.q = X.p; a.q_per_chain = 1;
-    a.out_d2 = d2a.p; a.out_cp = cpa.p;
-    launch_nearest(a, s);
-    const uint8_t *skip_p = nullptr;
-    if (t->has_boundary) {
-        prim.alloc((size_t)C * N); skip.alloc((size_t)C * N);
-        NearestArgs v;
-        v.bvh = &t->vert_bvh; v.prim_data = t->vert_data.p; v.C = C; v.nq = N; v.q = cpa.p; v.q_per_chain = 1; v.out_prim = prim.p;
-        launch_nearest(v, s);
-        launch_lookup_flags((int64_t)C * N, prim.p, t->boundary.p, Nt, skip.p, s);
-        skip_p = skip.p;
-    }
-    // every target vertex against the model surfaces (second half of hausdorffDistance)
-    bvh_refit(m->tri_bvh, C, X.p, N, m->tris.p, s);
-    NearestArgs b;
-    b.bvh = &m->tri_bvh; b.X = X.p; b.tris = m->tris.p; b.N = N; b.C = C; b.nq = Nt; b.q = t->verts.p; b.out_d2 = d2b.p;
-    launch_nearest(b, s);
-    k_metrics<<<C, 128, 0, s>>>(N, Nt, d2a.p, skip_p, d2b.p, dout.p);
-    ICP_CUDA(cudaGetLastError());
-    download(out, dout.p, (size_t)4 * C, s);
     sync_stream(_ctx);
     ICP_API_END
 }

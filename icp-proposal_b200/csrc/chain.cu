@@ -27,6 +27,7 @@ constexpr int kMaxNBc = 28;   // Kp <= 224 (icp_model_create enforces it)
 
 struct CompDev {
     int kind, axis, icp_index;  // icp_index: which ICP posterior set (or -1)
+    int factor;                 // ICP components: ICP_FACTOR_CHOLESKY | ICP_FACTOR_SVD
     double cdf, weight, sd, step;
 };
 
@@ -59,7 +60,44 @@ struct StateDev {
     long long *n_acc;                   // [C]
     int *step;                          // [1] device step counter
     double *L, *mu;                     // [n_icp][2 C][Kp Kp], [n_icp][2 C][Kp]
+    double *W;                          // [n_icp][2 C][Kp Kp] the reference's SVD factor (ICP_FACTOR_SVD components; else null)
+    int *status;                        // [C] sticky per-chain status bits (kSt*)
+    double *theta_best, *value_best;    // [C][L], [C]: BestSampleLogger - the state with the largest product value so far
 };
+
+// per-chain status bits of a run (icp_chain_io.status)
+constexpr int kStEmptySet = 1;      // the collective evaluator's filtered distance list was empty (the reference throws)
+constexpr int kStNotPD = 2;         // a posterior's M was not positive definite
+constexpr int kStNanTransition = 4; // a mixture component returned a NaN transition density (Scalismo's mixture throws)
+constexpr int kStNanValue = 8;      // the evaluator returned NaN for the initial state
+
+// where the pipelines of the step leave their per-chain status words
+struct StatusSrc {
+    const int *eval;              // [C] ICP_OK | ICP_ERR_EMPTY_SET
+    const int *post[kMaxComp];    // per ICP component [C], 0 = ok
+    int n_post;
+};
+
+__device__ __forceinline__ int fold_status(const StatusSrc &ss, int c) {
+    int st = 0;
+    if (ss.eval && ss.eval[c] != 0) st |= kStEmptySet;
+    for (int i = 0; i < ss.n_post; i++)
+        if (ss.post[i] && ss.post[i][c] != 0) st |= kStNotPD;
+    return st;
+}
+
+// status of the initial state (theta0): evaluator / posterior status words + a NaN log-value
+__global__ void k_chain_status0(int C, int Lt, StateDev st, StatusSrc ss) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    int v = fold_status(ss, c);
+    const double p = st.values_cur[3 * c];
+    if (p != p) v |= kStNanValue;
+    st.status[c] = v;
+    // Scalismo's chain iterator yields the initial state first, so BestSampleLogger starts from it
+    st.value_best[c] = p;
+    for (int j = 0; j < Lt; j++) st.theta_best[(size_t)c * Lt + j] = st.theta_cur[(size_t)c * Lt + j];
+}
 
 __global__ void k_chain_init(int C, StateDev st) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,6 +107,7 @@ __global__ void k_chain_init(int C, StateDev st) {
     st.slot_cur[c] = c;
     st.slot_prop[c] = C + c;
     st.n_acc[c] = 0;
+    st.status[c] = 0;
 }
 
 // standard normals of chain `chain` at step `step`: Philox block 1 + k/2 -> Box-Muller pair
@@ -145,6 +184,10 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
     if (cd.kind == ICP_PROP_ICP) {
         size_t pslot = (size_t)cd.icp_index * 2 * C + st.slot_cur[c];
         const double *Lc = st.L + pslot * Kp * Kp, *muc = st.mu + pslot * Kp;
+        if (cd.factor == ICP_FACTOR_SVD) {
+            // the reference's factor W = D^-1 Ubar diag(sqrt(lambda')) of the current state's posterior (svdfactor.cu)
+            block_matvec_rows(st.W + pslot * Kp * Kp, Kp, sz, sw);
+        } else {
         // lower triangle of L, packed row-major (row i at i (i + 1) / 2): warps take rows, lanes take columns
         {
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -168,6 +211,7 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
         for (int i = threadIdx.x; i < Kp; i += blockDim.x) { double *d = sL + (i * (i + 1)) / 2 + i; *d = 1.0 / *d; }
         __syncthreads();
         if (threadIdx.x < 32) warp_backsolve_packed(sL, Kp, sz, sw);
+        }
         __syncthreads();
         for (int k = threadIdx.x; k < Kp; k += blockDim.x) sz[k] = muc[k] + sw[k];
         __syncthreads();
@@ -250,7 +294,7 @@ __device__ __forceinline__ double gauss1_logpdf(double x, double sd) {
 }
 
 // log transition densities of every mixture component in both directions, log-sum-exp, acceptance, log append
-__global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st, LogDev lg) {
+__global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st, LogDev lg, StatusSrc stsrc) {
     extern __shared__ double sm[];
     const int K = P.K, Kp = P.Kp, Lt = K + kTheta0, C = P.C;
     double *sd = sm, *sd2 = sm + Kp, *red = sm + 2 * Kp, *part = sm + 2 * Kp + 40;   // part: [2][nwarps][Kp]
@@ -323,6 +367,10 @@ __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st
         double a = vp - vc - t;                                                   // MetropolisHastings.next
         int ok = (!nan) && ((a > 0.0) || (st.u_acc[c] < exp(a)));
         s_acc = ok;
+        // the reference throws where these happen (CollectiveAverage...Evaluator.scala:51,63; Scalismo's mixture on a NaN
+        // transition); here the step is rejected and the chain's sticky status word records it
+        const int stw = fold_status(stsrc, c) | (nan ? kStNanTransition : 0);
+        if (stw) st.status[c] |= stw;
     }
     __syncthreads();
     int ok = s_acc;
@@ -335,6 +383,13 @@ __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st
     size_t rec = (size_t)(step - lg.step_base) * C + c;
     if (lg.theta)
         for (int j = threadIdx.x; j < Lt; j += blockDim.x) lg.theta[rec * Lt + j] = ok ? prp[j] : cur[j];
+    // BestSampleLogger.logState on the state that is current after the step (a rejected step re-offers the retained state,
+    // which cannot beat itself)
+    if (ok && st.values_prop[3 * c] > st.value_best[c]) {
+        for (int j = threadIdx.x; j < Lt; j += blockDim.x) st.theta_best[(size_t)c * Lt + j] = prp[j];
+        __syncthreads();
+        if (threadIdx.x == 0) st.value_best[c] = st.values_prop[3 * c];
+    }
     if (threadIdx.x == 0) {
         if (ok) {
             int sel = 1 - st.cur_sel[c];
@@ -365,8 +420,11 @@ struct icp_chain_s {
     ChainParams P{};
     std::vector<icp_proposal> icp_props;
     // state
-    DevBuf<double> theta_cur, theta_prop, values_cur, values_prop, u_acc, L, mu, X;
-    DevBuf<int> cur_sel, slot_cur, slot_prop, comp_sel, step;
+    DevBuf<double> theta_cur, theta_prop, values_cur, values_prop, u_acc, L, mu, X, W, theta_best, value_best;
+    MetricsWork mwork;       // periodic RegistrationComparison of the best sample (icp_chain_io.metrics_interval)
+    DevBuf<int> cur_sel, slot_cur, slot_prop, comp_sel, step, status;
+    bool any_svd = false;    // some ICP component samples with the reference's SVD factor
+    std::vector<int> h_status;   // per-chain status words of the last synchronous run
     DevBuf<long long> n_acc;
     std::vector<PosteriorWork> pwork;
     std::vector<DevBuf<int>> cp_map;     // per ICP component: index of its model points in the evaluator's list
@@ -375,7 +433,7 @@ struct icp_chain_s {
     EvalWork ework;
     DevBuf<int> estatus;
     // staging for the host-buffer entry point
-    DevBuf<double> h_u_comp, h_z, h_u_acc, h_log_values, h_log_theta;
+    DevBuf<double> h_u_comp, h_z, h_u_acc, h_log_values, h_log_theta, h_log_metrics;
     DevBuf<int> h_log_comp;
     DevBuf<uint8_t> h_log_acc;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -418,7 +476,7 @@ extern "C" int32_t icp_chain_create(icp_model m, icp_target t, const icp_compone
         for (int i = 0; i < n_components; i++) {
             const icp_component &ci = components[i];
             CompDev &cd = P.comp[i];
-            cd.kind = ci.kind; cd.axis = ci.axis; cd.sd = ci.sd; cd.icp_index = -1; cd.step = 1.0;
+            cd.kind = ci.kind; cd.axis = ci.axis; cd.sd = ci.sd; cd.icp_index = -1; cd.step = 1.0; cd.factor = ICP_FACTOR_CHOLESKY;
             cd.weight = ci.weight / wsum;
             acc += cd.weight;
             cd.cdf = i == n_components - 1 ? 1.0 : acc;
@@ -428,6 +486,8 @@ extern "C" int32_t icp_chain_create(icp_model m, icp_target t, const icp_compone
                                 "ICP component needs a proposal built for this model / target");
                     cd.icp_index = P.n_icp++;
                     cd.step = ci.proposal->prm.step_length;
+                    cd.factor = ci.proposal->prm.factor;
+                    if (cd.factor == ICP_FACTOR_SVD) ch->any_svd = true;
                     ch->icp_props.push_back(ci.proposal);
                     break;
                 case ICP_PROP_RANDOM_SHAPE:
@@ -531,7 +591,8 @@ void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, cons
     // Profiling runs stay on one stream so that the per-kernel event times do not overlap.
     // (the model's vertex-BVH boxes are shared scratch: only fork when the nearest-vertex queries use the brute-force tile)
     const bool brute_ok = sizeof(double) * 3 * (size_t)((m->N + 1) & ~1) + sizeof(float4) * (size_t)m->N <= 100 * 1024;
-    const bool fork = !g_prof && ch->use_streams && brute_ok;
+    static const bool forced_bvh = getenv("ICPCUDA_NEAREST_VERTEX") && std::string(getenv("ICPCUDA_NEAREST_VERTEX")) == "bvh";
+    const bool fork = !g_prof && ch->use_streams && brute_ok && !forced_bvh;
     int n_side = 0;
     if (fork) ICP_CUDA(cudaEventRecord(ctx->ev_fork, r.s));
     for (int i = 0; i < ch->P.n_icp; i++) {
@@ -539,7 +600,8 @@ void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, cons
         cudaStream_t ss = ctx->aux[n_side];
         ICP_CUDA(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
         double *Lb = r.st.L + (size_t)i * 2 * C * Kp * Kp, *mub = r.st.mu + (size_t)i * 2 * C * Kp;
-        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, ss, nullptr);
+        double *Wb = ch->icp_props[i]->prm.factor == ICP_FACTOR_SVD ? r.st.W + (size_t)i * 2 * C * Kp * Kp : nullptr;
+        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, ss, nullptr, Wb);
         ICP_CUDA(cudaEventRecord(ctx->ev_join[n_side], ss));
         ch->on_side[i] = 1;
         n_side++;
@@ -549,9 +611,18 @@ void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, cons
         if (ch->on_side[i]) { ch->on_side[i] = 0; continue; }
         double *Lb = r.st.L + (size_t)i * 2 * C * Kp * Kp, *mub = r.st.mu + (size_t)i * 2 * C * Kp;
         SharedCp sh{ch->ework.cp_m2t.p, ch->evaluator->n_ids, ch->cp_map[i].p};
-        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, r.s, ch->cp_shared[i] ? &sh : nullptr);
+        double *Wb = ch->icp_props[i]->prm.factor == ICP_FACTOR_SVD ? r.st.W + (size_t)i * 2 * C * Kp * Kp : nullptr;
+        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, r.s, ch->cp_shared[i] ? &sh : nullptr, Wb);
     }
     for (int k = 0; k < n_side; k++) ICP_CUDA(cudaStreamWaitEvent(r.s, ctx->ev_join[k], 0));   // join
+}
+
+StatusSrc status_sources(icp_chain ch) {
+    StatusSrc ss{};
+    ss.eval = ch->estatus.p;
+    ss.n_post = ch->P.n_icp;
+    for (int i = 0; i < ch->P.n_icp; i++) ss.post[i] = ch->pwork[i].status.p;
+    return ss;
 }
 
 void enqueue_step(RunCtx &r) {
@@ -569,7 +640,7 @@ void enqueue_step(RunCtx &r) {
     enqueue_state_eval(r, r.st.theta_prop, r.st.values_prop, r.st.slot_prop);
     {
         ProfScope ps(ST_ACCEPT, r.s);
-        k_chain_accept<<<C, 128, sizeof(double) * (2 * Kp + 40 + 2 * 4 * Kp), r.s>>>(P, r.st, r.lg);
+        k_chain_accept<<<C, 128, sizeof(double) * (2 * Kp + 40 + 2 * 4 * Kp), r.s>>>(P, r.st, r.lg, status_sources(ch));
         ICP_CUDA(cudaGetLastError());
         k_step_increment<<<1, 1, 0, r.s>>>(r.st.step);
         ICP_CUDA(cudaGetLastError());
@@ -594,7 +665,11 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     ch->theta_cur.ensure((size_t)C * Lt); ch->theta_prop.ensure((size_t)C * Lt);
     ch->values_cur.ensure((size_t)3 * C); ch->values_prop.ensure((size_t)3 * C);
     ch->u_acc.ensure(C); ch->cur_sel.ensure(C); ch->slot_cur.ensure(C); ch->slot_prop.ensure(C);
-    ch->comp_sel.ensure(C); ch->step.ensure(1); ch->n_acc.ensure(C); ch->estatus.ensure(C);
+    ch->comp_sel.ensure(C); ch->step.ensure(1); ch->n_acc.ensure(C); ch->estatus.ensure(C); ch->status.ensure(C);
+    if (ch->any_svd) ch->W.ensure((size_t)std::max(n_icp, 1) * 2 * C * Kp * Kp);
+    ch->theta_best.ensure((size_t)C * Lt); ch->value_best.ensure(C);
+    ICP_REQUIRE(io->metrics_interval >= 0, "metrics_interval must be >= 0");
+    ICP_REQUIRE(io->metrics_interval == 0 || io->log_metrics != nullptr, "metrics_interval > 0 needs log_metrics");
     ch->L.ensure((size_t)std::max(n_icp, 1) * 2 * C * Kp * Kp); ch->mu.ensure((size_t)std::max(n_icp, 1) * 2 * C * Kp);
     ch->X.ensure((size_t)C * m->N * 3);
 
@@ -602,7 +677,7 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     r.ch = ch; r.C = C; r.s = s;
     r.st = StateDev{ch->theta_cur.p, ch->theta_prop.p, ch->values_cur.p, ch->values_prop.p, ch->cur_sel.p,
                     ch->slot_cur.p, ch->slot_prop.p, ch->comp_sel.p, ch->u_acc.p, ch->n_acc.p, ch->step.p, ch->L.p,
-                    ch->mu.p};
+                    ch->mu.p, ch->any_svd ? ch->W.p : nullptr, ch->status.p, ch->theta_best.p, ch->value_best.p};
     const int step_base = resume ? ch->steps_total : 0;
     r.rng = RngDev{io->seed, io->chain_id_offset, io->u_comp, io->z, io->u_acc, step_base};
     r.lg = LogDev{io->log_component, io->log_accepted, io->log_values, io->log_theta, step_base};
@@ -619,8 +694,23 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
         ICP_CUDA(cudaFuncSetAttribute(k_chain_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
     }
     // state of theta0: log-values + posteriors of every ICP component (state 0)
-    if (!resume) enqueue_state_eval(r, ch->theta_cur.p, ch->values_cur.p, ch->slot_cur.p);
+    if (!resume) {
+        enqueue_state_eval(r, ch->theta_cur.p, ch->values_cur.p, ch->slot_cur.p);
+        k_chain_status0<<<(C + 127) / 128, 128, 0, s>>>(C, Lt, r.st, status_sources(ch));
+        ICP_CUDA(cudaGetLastError());
+    }
 
+    // SamplingRegistration.scala:75-82: every acceptInfoPrintInterval iterations (iterator index i % interval == 0, i != 0;
+    // index 0 is the initial state, so index i is the state after step i) the boundary-aware registration measures of the
+    // best sample so far. Enqueued between the steps on the same stream; row r - 1 belongs to step r * interval.
+    int metrics_rows = 0;
+    auto after_step = [&](int done) {
+        if (io->metrics_interval > 0 && done % io->metrics_interval == 0) {
+            registration_metrics_device(m, ch->target, C, ch->theta_best.p, io->log_metrics + (size_t)metrics_rows * C * 4, ch->mwork, s);
+            metrics_rows++;
+        }
+        if (on_step) (*on_step)(done);
+    };
     // The step graph is cached on the chain: its kernel arguments are the state / RNG / log descriptors by value, so it
     // can be replayed by any later call whose descriptors are byte-identical (same C, buffers, seed, offsets).
     int steps_done = 0;
@@ -630,7 +720,7 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
         enqueue_step(r);
         steps_done = 1;
         ch->sized_C = C;
-        if (on_step) (*on_step)(steps_done);
+        after_step(steps_done);
     }
     cudaGraphExec_t exec = nullptr;
     if (ch->use_graph && !g_prof && n_steps - steps_done >= 1) {
@@ -641,6 +731,14 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
         key.append((const char *)&r.st, sizeof r.st);
         key.append((const char *)&r.rng, sizeof r.rng);
         key.append((const char *)&r.lg, sizeof r.lg);
+        {   // buffers the captured kernels address that are not part of the descriptors above: the pipelines' status words
+            // and the MODEL's BVH scratch, which other calls on the same model may reallocate (a replay would dangle)
+            StatusSrc ss = status_sources(ch);
+            key.append((const char *)&ss, sizeof ss);
+            const void *shared[] = {m->tri_bvh.nodes.p, m->tri_bvh.nodebox.p, m->tri_bvh.counters.p,
+                                    m->vert_bvh.nodes.p, m->vert_bvh.nodebox.p, m->vert_bvh.counters.p};
+            key.append((const char *)shared, sizeof shared);
+        }
         if (ch->exec && ch->exec_key == key) {
             exec = ch->exec;
         } else {
@@ -681,21 +779,43 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     for (; steps_done < n_steps; steps_done++) {
         if (exec) ICP_CUDA(cudaGraphLaunch(exec, s));
         else enqueue_step(r);
-        if (on_step) (*on_step)(steps_done + 1);
+        after_step(steps_done + 1);
     }
     if (io->theta_final)
         ICP_CUDA(cudaMemcpyAsync(io->theta_final, ch->theta_cur.p, sizeof(double) * (size_t)C * Lt, cudaMemcpyDeviceToDevice, s));
     if (io->n_accepted)
         ICP_CUDA(cudaMemcpyAsync(io->n_accepted, ch->n_acc.p, sizeof(long long) * (size_t)C, cudaMemcpyDeviceToDevice, s));
+    if (io->status)
+        ICP_CUDA(cudaMemcpyAsync(io->status, ch->status.p, sizeof(int) * (size_t)C, cudaMemcpyDeviceToDevice, s));
+    if (io->theta_best)
+        ICP_CUDA(cudaMemcpyAsync(io->theta_best, ch->theta_best.p, sizeof(double) * (size_t)C * Lt, cudaMemcpyDeviceToDevice, s));
+    if (io->value_best)
+        ICP_CUDA(cudaMemcpyAsync(io->value_best, ch->value_best.p, sizeof(double) * (size_t)C, cudaMemcpyDeviceToDevice, s));
     ICP_CUDA(cudaEventRecord(ch->ev1, s));
     ch->resident_C = C;
     ch->steps_total = step_base + n_steps;
     ch->last_launches = (int64_t)ch->last_per_step * n_steps;
     if (!async) {
+        ch->h_status.resize(C);
+        ICP_CUDA(cudaMemcpyAsync(ch->h_status.data(), ch->status.p, sizeof(int) * (size_t)C, cudaMemcpyDeviceToHost, s));
         ICP_CUDA(cudaStreamSynchronize(s));
         float ms = 0;
         cudaEventElapsedTime(&ms, ch->ev0, ch->ev1);
         ch->last_ms = ms;
+    }
+}
+
+// The reference throws where a chain's status word is set; the batched runner finishes the run (the step is rejected, the
+// other chains are unaffected), writes every output and then reports the first such chain through the return code.
+void throw_on_chain_status(const std::vector<int> &st) {
+    for (size_t c = 0; c < st.size(); c++) {
+        const int v = st[c];
+        if (!v) continue;
+        std::string where = "chain " + std::to_string(c) + " (icp_chain_io.status has the per-chain words; outputs were written)";
+        if (v & kStEmptySet) throw StatusError{ICP_ERR_EMPTY_SET, "empty filtered distance list in the collective evaluator, " + where};
+        if (v & kStNotPD) throw StatusError{ICP_ERR_NOT_POSITIVE_DEFINITE, "posterior matrix not positive definite, " + where};
+        if (v & kStNanTransition) throw StatusError{ICP_ERR_NAN, "NaN transition probability, " + where};
+        throw StatusError{ICP_ERR_NAN, "NaN log-value of the initial state, " + where};
     }
 }
 
@@ -708,6 +828,7 @@ extern "C" int32_t icp_chain_run_device(icp_chain c, int32_t C, int32_t n_steps,
         ICP_REQUIRE(_ctx != nullptr, "null handle");
         CtxLock lock(_ctx);
         chain_run_device(c, C, n_steps, theta0_dev, io_dev, async != 0);
+        if (!async) throw_on_chain_status(c->h_status);
         return ICP_OK;
     } catch (...) {
         return translate_exception(_ctx);
@@ -742,6 +863,14 @@ extern "C" int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const 
         if (io->log_theta) { c->h_log_theta.ensure(rec * Lt); dio.log_theta = c->h_log_theta.p; }
         if (io->theta_final) { d_final.ensure((size_t)C * Lt); dio.theta_final = d_final.p; }
         if (io->n_accepted) { d_nacc.ensure(C); dio.n_accepted = (int64_t *)d_nacc.p; }
+        dio.status = nullptr;   // read from the chain's own status words below
+        dio.theta_best = nullptr; dio.value_best = nullptr;   // likewise (chain-resident)
+        const int n_rows = io->metrics_interval > 0 ? n_steps / io->metrics_interval : 0;
+        if (io->metrics_interval > 0) {
+            ICP_REQUIRE(io->log_metrics != nullptr, "metrics_interval > 0 needs log_metrics");
+            c->h_log_metrics.ensure((size_t)std::max(n_rows, 1) * C * 4);
+            dio.log_metrics = c->h_log_metrics.p;
+        }
         // The log is [step][chain]: rows of finished steps are contiguous. When the caller's log buffers are pinned, rows
         // leave on a copy stream in up to 16 slices while later steps run; pageable buffers (cudaMemcpyAsync would block
         // the enqueueing thread) are copied after the last step.
@@ -788,6 +917,11 @@ extern "C" int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const 
         };
         dl(io->theta_final, d_final.p, sizeof(double) * (size_t)C * Lt);
         dl(io->n_accepted, d_nacc.p, sizeof(long long) * (size_t)C);
+        c->h_status.resize(C);
+        dl(c->h_status.data(), c->status.p, sizeof(int) * (size_t)C);
+        dl(io->theta_best, c->theta_best.p, sizeof(double) * (size_t)C * Lt);
+        dl(io->value_best, c->value_best.p, sizeof(double) * (size_t)C);
+        if (n_rows > 0) dl(io->log_metrics, c->h_log_metrics.p, sizeof(double) * (size_t)n_rows * C * 4);
         ICP_CUDA(cudaStreamSynchronize(s));
         if (overlap) ICP_CUDA(cudaStreamSynchronize(c->copy_stream));
         {   // the run was enqueued asynchronously: device time of the K steps, as chain_run_device records it when it waits
@@ -795,6 +929,8 @@ extern "C" int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const 
             cudaEventElapsedTime(&ms, c->ev0, c->ev1);
             c->last_ms = ms;
         }
+        if (io->status) memcpy(io->status, c->h_status.data(), sizeof(int) * (size_t)C);
+        throw_on_chain_status(c->h_status);
         return ICP_OK;
     } catch (...) {
         if (c && c->copy_stream) cudaStreamSynchronize(c->copy_stream);   // no copy into the caller's buffers may outlive the call

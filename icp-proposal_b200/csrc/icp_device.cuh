@@ -74,6 +74,18 @@ __device__ __forceinline__ double block_sum(double v, double *red /* >= 33 doubl
     return red[32];
 }
 
+// w = A z for a row-major Kp x Kp matrix in global memory, z / w in shared memory: warps deal the rows, lanes the columns
+__device__ __forceinline__ void block_matvec_rows(const double *__restrict__ A, int Kp, const double *z_sm, double *w_sm) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = warp; i < Kp; i += nw) {
+        const double *row = A + (size_t)i * Kp;
+        double acc = 0.0;
+        for (int j = lane; j < Kp; j += 32) acc = fma(__ldg(row + j), z_sm[j], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) w_sm[i] = acc;
+    }
+}
+
 // Philox4x32-10 (Salmon et al. 2011)
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll

@@ -230,8 +230,14 @@ bool launch_posterior_fused(const ModelDev &m, int C, const ObsDev &o, const Gra
 void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
                            const int *d_out_slot, int *d_status, cudaStream_t s, double *d_Mp = nullptr);
 // alpha' = alpha + step (S (mu + L^-T z) - alpha); L/mu addressed through per-chain slot indices
+// d_W (nullable): explicit factor [slot][Kp][Kp] (ICP_FACTOR_SVD); alpha' then uses W z instead of L^-T z
 void launch_propose(const ModelDev &m, int C, double step, const double *d_theta, const double *d_z,
-                    const double *d_L, const double *d_mu, const int *d_slot, double *d_theta_out, cudaStream_t s);
+                    const double *d_L, const double *d_mu, const int *d_slot, double *d_theta_out, cudaStream_t s,
+                    const double *d_W = nullptr);
+// the reference's covariance factor W = D^-1 Ubar diag(sqrt(lambda')) of C posteriors from their Cholesky factors
+// (svdfactor.cu); L / W addressed through d_slot (nullable); scratch is grown when the matrices do not fit shared memory
+void launch_svd_factor(int C, int K, int Kp, const double *d_L, const double *d_sqrt_var, const int *d_slot, double *d_W,
+                       DevBuf<double> &scratch, cudaStream_t s);
 // -1/2 (K ln 2pi + |L^T (alpha_c - mu)|^2), -inf unless only alpha changed
 void launch_log_transition(int C, int K, int Kp, double step, const double *d_from, const double *d_to,
                            const double *d_L, const double *d_mu, const int *d_slot, double *d_out, cudaStream_t s);
@@ -281,6 +287,8 @@ struct icp_model_s {
     icp::DevBuf<double> Q;            // 3N x Kp row-major, scaled basis, zero padded
     icp::DevBuf<double> QT;           // Kp x 3N
     icp::DevBuf<double> S;            // Kp x Kp, Appendix A5 constant (identity on the padding)
+    icp::DevBuf<double> sqrt_var;     // Kp: sqrt(lambda) (1 on the padding)
+    std::vector<double> h_var;        // K
     icp::DevBuf<int> tris;            // T x 3
     icp::DevBuf<int> adj_off, adj;    // vertex -> triangles CSR (ascending triangle id)
     icp::DevBuf<uint8_t> boundary;    // N
@@ -306,6 +314,7 @@ struct icp_target_s {
     icp::DevBuf<double> tri_data;   // [leaf slot][10]: a b c (9 doubles) + pad, Morton order
     icp::DevBuf<double> vert_data;  // [leaf slot][4]: xyz + pad, Morton order
     icp::DevBuf<uint8_t> boundary;  // Nt
+    icp::DevBuf<double> vnormals;   // Nt x 3 vertex normals (Scalismo vertexNormals; inside test of the Dice coefficient)
     bool has_boundary = false;
     std::vector<uint8_t> h_boundary;
     icp::Bvh tri_bvh, vert_bvh;
@@ -332,6 +341,7 @@ struct PosteriorWork {
     DevBuf<double> Mp;       // [C][NB (NB + 1) / 2][64] block-packed lower triangle of M (rank update -> factorisation)
     bool want_M = false;     // the primitive API returns M; the chain runner never needs it in global memory
     DevBuf<int> status;
+    DevBuf<double> svd_scratch;   // ICP_FACTOR_SVD at ranks whose matrices do not fit shared memory
 };
 
 }  // namespace icp
@@ -353,6 +363,7 @@ struct icp_proposal_s {
     std::vector<int> slot_nobs, slot_status;
     int cache_next = 0;
     icp::DevBuf<double> cache_L, cache_mu, cache_M;  // [slots][Kp*Kp], [slots][Kp], [slots][Kp*Kp]
+    icp::DevBuf<double> cache_W;                     // [slots][Kp*Kp] (ICP_FACTOR_SVD only)
     icp::PosteriorWork work;
     icp::DevBuf<double> s_theta, s_theta2, s_z, s_out;
     icp::DevBuf<int> s_slot;
@@ -381,6 +392,18 @@ struct icp_evaluator_s {
 };
 
 namespace icp {
+// workspace of registration_metrics_device
+struct MetricsWork {
+    DevBuf<double> X, d2a, cpa, d2b;
+    DevBuf<int> prim;
+    DevBuf<uint8_t> skip;
+};
+// RegistrationComparison measures of C parameter vectors on the device: d_out [C][4] = {avg, hausdorff,
+// avg_boundary_aware, max_boundary_aware}
+void registration_metrics_device(icp_model m, icp_target t, int C, const double *d_theta, double *d_out, MetricsWork &w,
+                                 cudaStream_t s);
+void nearest_model_vertex(icp_model m, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, int *d_seed,
+                          int *d_prim, cudaStream_t s);
 // correspondence + posterior pipeline: L / mu (at out_slot[c] or c) for C parameter vectors on the device.
 // d_X: transformed meshes [C][N][3] if the caller already has them, else nullptr.
 // shared: closest points another consumer already computed for a superset of this proposal's model points
@@ -390,8 +413,10 @@ struct SharedCp {
     int stride;
     const int *map;     // [n_ids] index into the shared list
 };
+// d_W (nullable, [slot][Kp][Kp]): also the reference's SVD-based covariance factor (ICP_FACTOR_SVD)
 void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const double *d_X, PosteriorWork &w, double *d_L,
-                        double *d_mu, const int *d_out_slot, cudaStream_t s, const SharedCp *shared = nullptr);
+                        double *d_mu, const int *d_out_slot, cudaStream_t s, const SharedCp *shared = nullptr,
+                        double *d_W = nullptr);
 // distance evaluator pipeline: values [C][3] = {product, prior, distance}
 void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_theta, const double *d_X, double *d_values,
                         int *d_status, cudaStream_t s);

@@ -1708,7 +1708,7 @@ __device__ void warp_backsolve_LT(const double *__restrict__ Lc, int Kp, const d
 __global__ void __launch_bounds__(128) k_propose(ModelDev m, double step, const double *__restrict__ theta,
                                                  const double *__restrict__ z, const double *__restrict__ L,
                                                  const double *__restrict__ mu, const int *__restrict__ slot,
-                                                 double *__restrict__ theta_out) {
+                                                 double *__restrict__ theta_out, const double *__restrict__ W) {
     extern __shared__ double sm[];
     const int Kp = m.Kp, K = m.K, Lt = K + kTheta0;
     double *sz = sm, *sw = sm + Kp;
@@ -1717,7 +1717,8 @@ __global__ void __launch_bounds__(128) k_propose(ModelDev m, double step, const 
     const double *Lc = L + (size_t)sl * Kp * Kp, *muc = mu + (size_t)sl * Kp;
     for (int k = threadIdx.x; k < Kp; k += blockDim.x) sz[k] = k < K ? z[(size_t)c * K + k] : 0.0;
     __syncthreads();
-    if (threadIdx.x < 32) warp_backsolve_LT(Lc, Kp, sz, sw);
+    if (W) block_matvec_rows(W + (size_t)sl * Kp * Kp, Kp, sz, sw);          // the reference's SVD factor (ICP_FACTOR_SVD)
+    else if (threadIdx.x < 32) warp_backsolve_LT(Lc, Kp, sz, sw);
     __syncthreads();
     for (int k = threadIdx.x; k < Kp; k += blockDim.x) sz[k] = muc[k] + sw[k];   // v = mu + W z
     __syncthreads();
@@ -1733,10 +1734,11 @@ __global__ void __launch_bounds__(128) k_propose(ModelDev m, double step, const 
 }
 
 void launch_propose(const ModelDev &m, int C, double step, const double *d_theta, const double *d_z,
-                    const double *d_L, const double *d_mu, const int *d_slot, double *d_theta_out, cudaStream_t s) {
+                    const double *d_L, const double *d_mu, const int *d_slot, double *d_theta_out, cudaStream_t s,
+                    const double *d_W) {
     if (C <= 0) return;
     ICP_REQUIRE(m.Kp <= 256, "rank too large for the propose kernel (K <= 256)");
-    k_propose<<<C, 128, sizeof(double) * 2 * m.Kp, s>>>(m, step, d_theta, d_z, d_L, d_mu, d_slot, d_theta_out);
+    k_propose<<<C, 128, sizeof(double) * 2 * m.Kp, s>>>(m, step, d_theta, d_z, d_L, d_mu, d_slot, d_theta_out, d_W);
     ICP_CUDA(cudaGetLastError());
 }
 

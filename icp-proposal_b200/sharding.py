@@ -48,6 +48,8 @@ def variability_partials(count: int, mean: np.ndarray, cov: np.ndarray):
     sub-millimetre variances to cancellation."""
     mean = np.asarray(mean, float).reshape(-1, 3)
     cov = np.asarray(cov, float).reshape(len(mean), 9)
+    if count <= 0:   # an empty shard (fewer samples than ranks) contributes nothing; its device outputs are undefined
+        mean = np.zeros_like(mean)
     m2 = cov * (count - 1) if count > 1 else np.zeros_like(cov)
     return np.concatenate([[float(count)], (mean * count).ravel(), m2.ravel(), mean.ravel()])
 
@@ -63,7 +65,7 @@ def merge_variability(parts: np.ndarray, normals: np.ndarray | None = None):
     mean = parts[:, 1:1 + 3 * nv].sum(0).reshape(nv, 3) / n
     m2 = parts[:, 1 + 3 * nv:1 + 12 * nv].sum(0).reshape(nv, 3, 3)
     mean_r = parts[:, 1 + 12 * nv:].reshape(len(parts), nv, 3)
-    d = mean_r - mean[None]
+    d = np.where((n_r > 0)[:, None, None], mean_r - mean[None], 0.0)
     m2 = m2 + np.einsum("r,rvi,rvj->vij", n_r, d, d)
     with np.errstate(divide="ignore", invalid="ignore"):
         cov = m2 * (np.float64(1.0) / np.float64(n - 1))

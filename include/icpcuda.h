@@ -37,6 +37,7 @@ extern "C" {
 #define ICP_ERR_OUT_OF_MEMORY (-3)
 #define ICP_ERR_EMPTY_SET (-4)   /* CollectiveAverage...Evaluator.scala:51,63 `filteredDists.max` on an empty list */
 #define ICP_ERR_NOT_POSITIVE_DEFINITE (-5)
+#define ICP_ERR_NAN (-6)         /* a NaN transition probability (Scalismo's MixtureProposal throws) or a NaN initial log-value */
 
 typedef struct icp_ctx_s *icp_ctx;
 typedef struct icp_model_s *icp_model;
@@ -104,12 +105,24 @@ int32_t icp_model_boundary_flags(icp_model m, uint8_t *flags /* N */);
 #define ICP_MODEL_SAMPLING 0    /* api/other/IcpProjectionDirection.scala */
 #define ICP_TARGET_SAMPLING 1
 
+/* Covariance factor W (W W^T = M^-1) that maps the caller's standard normals z to a posterior sample (:55):
+ *   ICP_FACTOR_CHOLESKY  W = L^-T, M = L L^T: one back substitution per proposal (default of the fused runner; the
+ *                        same proposal DISTRIBUTION as the reference, different values for the same z)
+ *   ICP_FACTOR_SVD       W = D^-1 Ubar diag(sqrt(lambda')), Ubar diag(lambda') Ubar^T = D M^-1 D, lambda' descending,
+ *                        largest-magnitude entry of every vector positive: the factor Scalismo's posterior GP samples
+ *                        with, i.e. the reference's VALUE for the caller's z. Costs one K x K
+ *                        eigen-decomposition per posterior (batched one-sided Jacobi on the device); needs variance > 0. */
+#define ICP_FACTOR_CHOLESKY 0
+#define ICP_FACTOR_SVD 1
+
 typedef struct {
     double step_length;         /* stepLength */
     double tangential_noise;    /* tangentialNoise: std-dev in the tangent plane */
     double noise_along_normal;  /* noiseAlongNormal: std-dev along the vertex normal */
     int32_t direction;          /* ICP_MODEL_SAMPLING | ICP_TARGET_SAMPLING */
     int32_t boundary_aware;     /* boundaryAware */
+    int32_t factor;             /* ICP_FACTOR_CHOLESKY | ICP_FACTOR_SVD */
+    int32_t reserved;           /* 0 */
 } icp_proposal_params;
 
 /* model_point_ids: decimatedModel.referenceMesh.pointSet.pointIds (:94; they index the FULL mesh,
@@ -126,7 +139,7 @@ int32_t icp_proposal_destroy(icp_proposal p);
  * filter; NULL to skip). */
 int32_t icp_posterior(icp_proposal p, int32_t C, const double *theta, double *mu, double *M, int32_t *n_obs);
 /* propose (:53-68). z: C x K standard normals drawn by the caller's RNG (posterior.sample(), :55).
- * theta_out C x (K+10). alpha' = alpha + step (S (mu + W z) - alpha), W W^T = M^-1 (W = L^-T). */
+ * theta_out C x (K+10). alpha' = alpha + step (S (mu + W z) - alpha), W W^T = M^-1 (W as selected by params.factor). */
 int32_t icp_propose(icp_proposal p, int32_t C, const double *theta, const double *z, double *theta_out);
 /* logTransitionProbability(from, to) (:71-85): out C. -inf unless only alpha changed (:72-74). */
 int32_t icp_log_transition(icp_proposal p, int32_t C, const double *from, const double *to, double *out);
@@ -179,6 +192,14 @@ int32_t icp_eval_prior(icp_model m, int32_t C, const double *theta, double *out)
  * (api/other/RegistrationComparison.scala:24-49): per chain {avg, hausdorff, avg_boundary_aware,
  * max_boundary_aware} between transformedMesh(theta) and the target; out C x 4. */
 int32_t icp_registration_metrics(icp_model m, icp_target t, int32_t C, const double *theta, double *out);
+/* MeshMetrics.diceCoefficient(transformedMesh(theta), target) (apps/femur/StdIcpVsChainICPrandomInitComparisonAll.scala:46):
+ * Monte-Carlo overlap 2 |A and B| / (|A| + |B|) over n_samples points drawn uniformly in the union of the two bounding
+ * boxes; a point is inside a mesh when vertexNormal(v) . (v - p) > 0 for the mesh vertex v nearest to p (Scalismo
+ * toBinaryImage). The reference draws 10 000 points from an unseeded RNG; here the caller supplies them as unit-cube
+ * samples (unit_samples, n_samples x 3 in [0, 1], scaled into each chain's evaluation region) or passes NULL for
+ * device-generated Philox samples keyed by `seed` (the same set for every chain). out: C. */
+int32_t icp_dice_coefficient(icp_model m, icp_target t, int32_t C, const double *theta, int32_t n_samples,
+                             const double *unit_samples, uint64_t seed, double *out);
 /* PosteriorVariability.computeDistanceMapFromMeshesTotal / ...Normal (apps/util/PosteriorVariability.scala:30-73)
  * over the shapes LogHelper.logSamples2shapes reconstructs from S logged parameter vectors
  * (apps/util/LogHelper.scala:39-41): per model vertex the sample mean (mean: N x 3), the sample covariance with
@@ -232,7 +253,25 @@ typedef struct {
     double *log_theta;        /* [n_steps][C][K+10] parameters of the current state after the step */
     double *theta_final;      /* [C][K+10] */
     int64_t *n_accepted;      /* [C] */
+    /* [C] per-chain status words, OR of the ICP_CHAIN_* bits below, sticky over the run (and over resumed runs). Where the
+     * reference would throw, the batched runner rejects that step, lets every chain finish, writes all outputs and then
+     * returns ICP_ERR_EMPTY_SET / ICP_ERR_NOT_POSITIVE_DEFINITE / ICP_ERR_NAN for the first flagged chain. */
+    int32_t *status;
+    /* BestSampleLogger(evaluator) (api/sampling/SamplingRegistration.scala:58,87): the state with the largest product
+     * log-value among theta0 and the states current after every step. */
+    double *theta_best;       /* [C][K+10] */
+    double *value_best;       /* [C] */
+    /* RegistrationComparison.evaluateReconstruction2GroundTruthBoundaryAware of the best sample so far, every
+     * metrics_interval steps (SamplingRegistration.scala:75-82, acceptInfoPrintInterval; 0 = off): row r - 1 is taken after
+     * step r * metrics_interval of this call; layout of icp_registration_metrics. */
+    int32_t metrics_interval;
+    int32_t reserved;
+    double *log_metrics;      /* [n_steps / metrics_interval][C][4] */
 } icp_chain_io;
+#define ICP_CHAIN_EMPTY_SET 1        /* CollectiveAverage...Evaluator.scala:51,63: filtered distance list empty */
+#define ICP_CHAIN_NOT_POSITIVE_DEFINITE 2
+#define ICP_CHAIN_NAN_TRANSITION 4   /* a mixture component's transition density was NaN */
+#define ICP_CHAIN_NAN_VALUE 8        /* the evaluator returned NaN for theta0 */
 
 /* theta0 C x (K+10) (host). io buffers are host memory. When the log buffers are page-locked (cudaHostAlloc /
  * cudaHostRegister), finished log rows are copied out on a second stream while later steps run; pageable buffers are

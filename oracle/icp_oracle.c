@@ -766,6 +766,15 @@ static void posterior_basis(const orc_proposal *p, post_entry *e)
         for (int j = 0; j < i; j++) { double a = 0.5 * (S[(size_t)i * K + j] + S[(size_t)j * K + i]); S[(size_t)i * K + j] = S[(size_t)j * K + i] = a; }
     e->Ubar = (double *)malloc(sizeof(double) * K * K); e->lamp = (double *)malloc(sizeof(double) * K);
     sym_eig(K, S, e->Ubar, e->lamp);
+    /* Sign convention of the singular vectors: Breeze's svd returns whatever LAPACK dgesdd produced, which cannot be
+     * known without running the JVM (parity unpinned). Oracle, numpy oracle and device all use the
+     * same documented rule instead: the entry of largest magnitude of every vector (lowest index on ties) is positive. */
+    for (int j = 0; j < K; j++) {
+        int im = 0; double vm = 0.0;
+        for (int i = 0; i < K; i++) { double a = fabs(e->Ubar[(size_t)i * K + j]); if (a > vm) { vm = a; im = i; } }
+        if (e->Ubar[(size_t)im * K + j] < 0.0)
+            for (int i = 0; i < K; i++) e->Ubar[(size_t)i * K + j] = -e->Ubar[(size_t)i * K + j];
+    }
     e->Up = (double *)malloc(sizeof(double) * n3 * K);
     mm((int)n3, K, K, md->U, e->Ubar, e->Up);   /* phi'_i(x) = sum_j phi_j(x) Ubar[j,i], N K^2 work */
     e->have_basis = 1;
@@ -891,6 +900,67 @@ double orc_log_transition_closed_form(const orc_proposal *pc, const double *from
     double q = 0; for (int j = 0; j < K; j++) q += d[j] * Md[j];
     free(d); free(Md);
     return -0.5 * (K * LOG_2PI + q);
+}
+
+/* ============================================================================================ */
+/* registration quality measures                                                                  */
+/* ============================================================================================ */
+/* api/other/RegistrationComparison.scala:24-49 between transformedMesh(theta) and the target:
+ * out = {MeshMetrics.avgDistance (:25), MeshMetrics.hausdorffDistance (:27, Appendix A14), avgDistanceBoundaryAware
+ * average and maximum (:31-43)}. An empty filtered list gives NaN for both boundary-aware values (the reference
+ * divides 0 by 0 and then throws on .max). */
+void orc_registration_metrics(const orc_model *md, const orc_mesh *target, const double *theta, double out[4])
+{
+    int N = md->N;
+    double *xyz = (double *)malloc(sizeof(double) * 3 * N);
+    orc_transformed_mesh(md, theta, xyz);
+    orc_mesh *cur = orc_mesh_create(N, xyz, md->T, md->tris);
+    double sum = 0, mx = 0, sb = 0, mb = -INFINITY; int nb = 0;
+    for (int i = 0; i < N; i++) {
+        double cp[3], d2; int32_t tid;
+        orc_mesh_closest_point(target, 1, xyz + 3 * i, NULL, NULL, cp, &d2);     /* :35 */
+        orc_mesh_closest_vertex(target, 1, cp, &tid, NULL);                      /* :36 */
+        double d = sqrt(d2);
+        sum += d; if (d > mx) mx = d;
+        if (!target->boundary[tid]) { sb += d; nb++; if (d > mb) mb = d; }       /* :37-38 */
+    }
+    double back = 0;
+    for (int i = 0; i < target->nv; i++) {
+        double d2; orc_mesh_closest_point(cur, 1, target->v + 3 * i, NULL, NULL, NULL, &d2);
+        if (sqrt(d2) > back) back = sqrt(d2);
+    }
+    out[0] = sum / N; out[1] = mx > back ? mx : back;
+    out[2] = nb ? sb / nb : NAN; out[3] = nb ? mb : NAN;
+    orc_mesh_free(cur); free(xyz);
+}
+
+/* Scalismo MeshMetrics.diceCoefficient(a, b) [S-recall] (apps/femur/StdIcpVsChainICPrandomInitComparisonAll.scala:46):
+ * uniform samples in the box spanned by both bounding boxes; inside(mesh, p) = vertexNormal(v) . (v - p) > 0 with v the
+ * mesh vertex nearest to p (toBinaryImage); 2 |A and B| / (|A| + |B|). unit: n x 3 samples in [0, 1] standing in for the
+ * reference's unseeded UniformSampler. */
+double orc_dice_coefficient(const orc_model *md, const orc_mesh *target, const double *theta, int n, const double *unit)
+{
+    int N = md->N;
+    double *xyz = (double *)malloc(sizeof(double) * 3 * N);
+    orc_transformed_mesh(md, theta, xyz);
+    orc_mesh *cur = orc_mesh_create(N, xyz, md->T, md->tris);
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < N; i++) for (int d = 0; d < 3; d++) { if (xyz[3 * i + d] < lo[d]) lo[d] = xyz[3 * i + d]; if (xyz[3 * i + d] > hi[d]) hi[d] = xyz[3 * i + d]; }
+    for (int i = 0; i < target->nv; i++) for (int d = 0; d < 3; d++) { double x = target->v[3 * i + d]; if (x < lo[d]) lo[d] = x; if (x > hi[d]) hi[d] = x; }
+    double na = 0, nb = 0, nab = 0;
+    for (int i = 0; i < n; i++) {
+        double p[3]; for (int d = 0; d < 3; d++) p[d] = lo[d] + unit[3 * i + d] * (hi[d] - lo[d]);
+        int32_t va, vb; double nrm[3], w[3];
+        orc_mesh_closest_vertex(cur, 1, p, &va, NULL);
+        vertex_normal(cur, va, nrm); v_sub(cur->v + 3 * va, p, w);
+        int ina = v_dot(nrm, w) > 0.0;
+        orc_mesh_closest_vertex(target, 1, p, &vb, NULL);
+        vertex_normal(target, vb, nrm); v_sub(target->v + 3 * vb, p, w);
+        int inb = v_dot(nrm, w) > 0.0;
+        na += ina; nb += inb; nab += ina && inb;
+    }
+    orc_mesh_free(cur); free(xyz);
+    return 2.0 * nab / (na + nb);
 }
 
 /* ============================================================================================ */

@@ -119,6 +119,12 @@ double orc_random_walk_log_transition(int K, double sd, const double *from, cons
  * kind 1 = translation axis */
 double orc_pose_log_transition(int K, int kind, int axis, double sd, const double *from, const double *to);
 
+/* ---- registration quality measures ------------------------------------------------------------ */
+/* api/other/RegistrationComparison.scala:24-49: {avg, hausdorff, boundary-aware avg, boundary-aware max} */
+void orc_registration_metrics(const orc_model *model, const orc_mesh *target, const double *theta, double out[4]);
+/* MeshMetrics.diceCoefficient over n unit-cube samples (apps/femur/StdIcpVsChainICPrandomInitComparisonAll.scala:46) */
+double orc_dice_coefficient(const orc_model *model, const orc_mesh *target, const double *theta, int n, const double *unit);
+
 /* ---- Metropolis-Hastings chain (Scalismo MetropolisHastings.next + MixtureProposal) ---------- */
 enum { ORC_PROP_ICP = 0, ORC_PROP_RANDOM_SHAPE = 1, ORC_PROP_ROTATION = 2, ORC_PROP_TRANSLATION = 3 };
 enum { ORC_EVAL_ACCEPT_ALL = 0, ORC_EVAL_INDEPENDENT = 1, ORC_EVAL_HAUSDORFF = 2, ORC_EVAL_COLLECTIVE = 3 };

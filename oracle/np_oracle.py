@@ -180,6 +180,10 @@ def posterior_basis(model, post):
     d = np.sqrt(model.var)
     sigma = d[:, None] * post["Minv"] * d[None, :]
     ubar, lam, _ = np.linalg.svd(sigma)
+    # documented sign rule shared with the C oracle and the device (icp_oracle.c posterior_basis): the entry of largest
+    # magnitude of every singular vector is positive
+    im = np.abs(ubar).argmax(axis=0)
+    ubar = ubar * np.where(ubar[im, np.arange(ubar.shape[1])] < 0, -1.0, 1.0)[None, :]
     return ubar, lam
 
 

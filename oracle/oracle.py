@@ -93,6 +93,9 @@ def lib():
         L.orc_random_walk_log_transition.argtypes = [C.c_int, C.c_double, _dp, _dp]
         L.orc_pose_log_transition.restype = C.c_double
         L.orc_pose_log_transition.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp]
+        L.orc_registration_metrics.argtypes = [_vp, _vp, _dp, _dp]
+        L.orc_dice_coefficient.restype = C.c_double
+        L.orc_dice_coefficient.argtypes = [_vp, _vp, _dp, C.c_int, _dp]
         L.orc_chain_run.restype = C.c_int
         L.orc_chain_run.argtypes = [C.POINTER(_ChainDesc), _dp, C.c_int, _dp, _dp, _dp, _ip, _bp, _dp, _dp]
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -284,6 +287,18 @@ def random_walk_log_transition(K, sd, frm, to):
 def pose_log_transition(K, kind, axis, sd, frm, to):
     f, fp = _d(frm); t, tp = _d(to)
     return lib().orc_pose_log_transition(K, kind, axis, sd, fp, tp)
+
+
+def registration_metrics(model, target, theta):
+    th, thp = _d(theta)
+    out = np.empty(4)
+    lib().orc_registration_metrics(model.h, target.h, thp, out.ctypes.data_as(_dp))
+    return out
+
+
+def dice_coefficient(model, target, theta, unit_samples):
+    th, thp = _d(theta); u, up = _d(np.asarray(unit_samples).reshape(-1, 3))
+    return lib().orc_dice_coefficient(model.h, target.h, thp, len(u), up)
 
 
 def chain_run(model, target, components, use_prior, eval_kind, eval_mode, params, ids, target_points, theta0, n_steps,

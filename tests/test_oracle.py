@@ -86,6 +86,9 @@ def test_posterior_propose_transition_vs_numpy(twin31, direction):
     np.testing.assert_allclose(p.propose(theta, z0), npo.propose(nm, pn, theta, z0, 0.1), rtol=0, atol=1e-11)
     z = rng.normal(size=K)
     to = p.propose(theta, z)
+    # with the shared sign rule of the singular vectors the two independent restatements (tred2/tql2 vs LAPACK gesdd) draw
+    # the same sample for the same z
+    np.testing.assert_allclose(to, npo.propose(nm, pn, theta, z, 0.1), rtol=0, atol=1e-9)
     lt = p.log_transition(theta, to)
     np.testing.assert_allclose(lt, npo.log_transition(nm, pn, theta, to, 0.1), rtol=1e-10)
     # Appendix A6/A7: the sample drawn with z has transition density N(z; 0, I) up to the 1e-5 regulariser
