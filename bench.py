@@ -132,11 +132,21 @@ def oracle_chain_rate(m, tv, tc, ids, eids, tp, n_chains, n_steps, threads, clos
     return n_chains * n_steps / dt, dt, float(np.sum(acc)) / (n_chains * n_steps)
 
 
+def enable_cpu_blas():
+    """The timed CPU arm runs its dense linear algebra on the box's OpenBLAS / LAPACK (as Breeze does through netlib-java
+    when a native BLAS is present); returns a short description for the JSON line."""
+    from oracle import oracle as orc
+    path = orc.use_blas(True)
+    return ("OpenBLAS dgemm/dgemv + LAPACKE dsyevd, 1 BLAS thread per chain (%s)" % os.path.basename(path)) if path else \
+        "built-in C loops (no OpenBLAS found on this box)"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     m, tv, tc, ids, eids, tp = workload()
+    blas = enable_cpu_blas()
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, 32))
     per = max(1, args.ref_steps)
@@ -148,16 +158,59 @@ def run_reference(args):
             rates.append((rate, dt))
     value = float(np.mean([r for r, _ in rates]))
     ms = float(np.mean([d for _, d in rates]) * 1e3)
-    sample = f"{threads} chains x {per} MH steps per bench step on {threads} threads (1 core per chain, reference structure: SVD-rotated basis + full-mesh regressions)"
+    sample = (f"{threads} chains x {per} MH steps per bench step on {threads} threads (1 core per chain, reference structure: "
+              f"SVD-rotated basis + full-mesh regressions; linear algebra: {blas})")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "femur GPMM-100 twin (N=1622,T=3240,K=101), config-1 ICP mixture + Gaussian-point evaluator, independent chains",
                        "chains": threads, "n_icp_points": int(len(ids)), "n_eval_points": int(len(eids))},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "linear_algebra": blas},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t_all}
     emit(line)
+
+
+def profile_constants():
+    """DRAM traffic per launch and lane utilisation are ncu counters: they cannot be measured inside a timed run. They are
+    read from the committed digest of the latest ncu --set full capture (profiles/traffic.json, written by
+    tools/ncu_traffic.py from the .ncu-rep) and labelled as profile constants in the JSON line."""
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        return json.load(f)
+
+
+def per_call_latency(m, model, pt, pm, ev, th0_host, iters=40):
+    """The literal drop-in path: one MH step as a stock Scalismo chain drives it through the per-call entry points
+    (icp_propose, icp_log_transition both ways for both ICP components, icp_eval_log_value), one chain per host thread on
+    SHARED proposal / evaluator handles (RunMHRandomInitComparison.scala:59-86 uses 10 threads). Steps/s whole job."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    K = K_RANK
+
+    def chain(t, n):
+        rng = np.random.default_rng(500 + t)
+        th = th0_host[t % len(th0_host)].copy()[None]
+        for _ in range(n):
+            z = rng.normal(size=(1, K))
+            prop = (pt if rng.random() < 0.5 else pm).propose(th, z)
+            for p in (pt, pm):
+                p.log_transition(th, prop)
+                p.log_transition(prop, th)
+            ev.log_value(prop)
+            th = prop           # always move on: every step needs fresh posteriors, as an accepted step does
+        return n
+
+    out = {}
+    chain(0, 5)                 # warm-up: sizes the handles' scratch
+    for threads in (1, 10):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            done = sum(ex.map(lambda t: chain(t, iters), range(threads)))
+        dt = time.perf_counter() - t0
+        out[f"threads_{threads}"] = {"steps_per_s": done / dt, "ms_per_step_per_thread": dt / iters * 1e3}
+    out["note"] = ("per-call C ABI, C = 1 per call, host buffers in and out on every call; 7 calls per MH step "
+                   "(1 propose, 4 log_transition, 1 eval + the posterior cache); calls on one context serialise")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -226,6 +279,26 @@ def run_gpu(args):
     value = world * C * steps / (t_ms * 1e-3)
     accept_rate = float(log_acc.float().mean().item())
 
+    # ---- sustained arm: >= 2000 resumed steps of the same chains (seconds under load, clocks sampled) -------
+    sustained = None
+    if args.sustain_steps > 0:
+        S = args.sustain_steps
+        s_comp = torch.empty((S, C), dtype=torch.int32, device=dev); s_acc = torch.empty((S, C), dtype=torch.uint8, device=dev)
+        s_val = torch.empty((S, C, 3), dtype=torch.float64, device=dev); s_th = torch.empty((S, C, L), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        with ClockSampler(local) as sclocks:
+            barrier()
+            chain.run_device(C, S, None, seed=seed, chain_id_offset=off, log_component=s_comp.data_ptr(),
+                             log_accepted=s_acc.data_ptr(), log_values=s_val.data_ptr(), log_theta=s_th.data_ptr())
+            barrier()
+        s_ms, _ = chain.last_run_stats()
+        s_ms = max_over_ranks(s_ms)
+        sustained = {"value": world * C * S / (s_ms * 1e-3), "unit": UNIT, "steps": S, "ms_per_step": s_ms / S, "seconds": s_ms * 1e-3,
+                     "accept_rate": float(s_acc.float().mean().item()), "clocks": sclocks.summary(),
+                     "note": "the same chains resumed for S more steps with the full chain log written to HBM (%.1f GB)" %
+                             ((s_comp.nbytes + s_acc.nbytes + s_val.nbytes + s_th.nbytes) / 1e9)}
+        del s_comp, s_acc, s_val, s_th
+
     # ---- chain statistics gathered over NCCL (the only collective; not on the per-sample path) -------------
     gather_ms = None
     if world > 1:
@@ -291,6 +364,8 @@ def run_gpu(args):
 
     line = None
     if rank == 0:
+        l2_gbs = ctx.l2_bandwidth(8 << 20)      # L2 -> SM reads over an L2-resident 8 MB working set, measured live
+        per_call = per_call_latency(m, model, pt, pm, ev, th0_host)
         # ---- per-kernel device times (CUDA events on the launching stream, eager pass over the same workload) --
         prof_steps = max(2, min(steps, 8))
         prof = chain.profile(th0_host, prof_steps, seed=seed)
@@ -298,6 +373,7 @@ def run_gpu(args):
         shares = {k: round(v["ms"] / total_prof, 4) for k, v in prof.items() if v["launches"]}
         fp64 = ctx.fp64_peak()
         peaks, peak_src = measured_peaks()
+        prof_const = profile_constants()
         # posterior = rank-update kernel (k_posterior_fused<.., CHOL = false>: M = I + A^T A, b = A^T y on the FP64 tensor
         # pipe) + k_cholesky_packed; each twice per step (target- and model-sampling proposal). The rank update dominates.
         # Its algorithmic flops per chain-posterior: 2*3n*K^2 (M) + 2*3n*K*3 (Sigma^-1 apply) = 12.4 MFLOP at
@@ -320,7 +396,9 @@ def run_gpu(args):
         if ch["launches"]:
             roof_chol = {"bound": "hbm", "kernel": "k_cholesky_packed", "achieved": ch_bytes / (ch_ms * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ch_bytes / (ch_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                         "traffic": 1.76e8 * C / 2368.0, "avg_launch_ms": ch_ms, "flops_per_launch": flops_chol * C,
+                         "traffic": prof_const["cholesky"]["dram_bytes_per_launch"] * C / prof_const["cholesky"]["chains"],
+                         "traffic_source": prof_const["cholesky"]["source"] + " (profile constant, scaled by C)",
+                         "avg_launch_ms": ch_ms, "flops_per_launch": flops_chol * C,
                          "share_of_step": shares.get("cholesky_solve"),
                          "note": "a chain of Kp dependent pivots per matrix: latency-bound by construction (4 chains per SM hide "
                                  "it); traffic = dram read + write per launch from profiles/r1j (ncu --set full, C = 2368), scaled by C"}
@@ -331,29 +409,37 @@ def run_gpu(args):
         top = max(shares, key=shares.get)
         cpq = prof["closest_point_static"]
         cp_ms = cpq["ms"] / max(cpq["launches"], 1)
-        roof_cp = {"bound": "hbm", "kernel": "k_nearest<tri,static> (1e6 near-surface queries, timed alone)",
-                   "achieved": cp["near_surface"]["algorithmic_GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "frac": cp["near_surface"]["algorithmic_GBps"] / peaks["hbm_gbs"], "traffic": 9.29e7, "peak_source": peak_src,
-                   "bytes_per_query": 1000,
-                   "traffic_note": "dram read + write of the 1e6-query launch (profiles/r1i, ncu --set full): 60.4 + 32.5 MB = the "
-                                   "queries in, the results out and the Morton permutation; the tree itself (0.45 MB) is served "
-                                   "by L1 (75 % sector hits) and L2, 9.7 TB/s of L1 data returned to the SMs",
-                   "lanes_active_per_instruction": 11.8}
+        roof_cp = {"bound": "l2", "kernel": prof_const["closest_point"]["kernel"] + " (1e6 near-surface queries, timed alone)",
+                   "achieved": cp["near_surface"]["algorithmic_GBps"], "peak": l2_gbs, "unit": "GB/s",
+                   "frac": cp["near_surface"]["algorithmic_GBps"] / l2_gbs if l2_gbs else None,
+                   "peak_source": "L2 -> SM read bandwidth over an L2-resident 8 MB working set, measured live (icp_debug_l2_bandwidth); "
+                                  "the tree + triangles (0.5 MB) are cache resident, so L2 - not HBM - is the ceiling (SURVEY 8d)",
+                   "frac_of_hbm_copy": cp["near_surface"]["algorithmic_GBps"] / peaks["hbm_gbs"], "hbm_peak": peaks["hbm_gbs"],
+                   "hbm_peak_source": peak_src, "bytes_per_query": 1000,
+                   "traffic": prof_const["closest_point"]["dram_bytes_per_launch"],
+                   "traffic_source": prof_const["closest_point"]["source"] + " (a PROFILE CONSTANT read from profiles/, not measured in this run)",
+                   "lanes_active_per_instruction": prof_const["closest_point"].get("lanes_active_per_instruction"),
+                   "far_field_frac": cp["far_field"]["algorithmic_GBps"] / l2_gbs if l2_gbs else None}
         roofline = {"bound": "tensor", "pipe": "FP64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA)",
                     "kernel": "k_posterior_fused<.., CHOL = false> (rank update M = I + A^T A, b = A^T y)",
-                    "achieved": pb_tflops, "peak": fp64["dmma_tflops"], "unit": "TFLOP/s",
-                    "frac": pb_tflops / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
-                    "hw_achieved": pb_hw, "hw_frac": pb_hw / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
-                    "traffic": 1.08e8 * C / 2368.0,
-                    "traffic_note": "dram read+write per launch from profiles/r1j (ncu --set full, C = 2368), scaled by C; "
-                                    "algorithmic bytes per launch = C * (8 * 64 * 91 + 8 Kp) written (packed M, b) ~ 112 MB plus the "
+                    # frac = flops the kernel EXECUTES / measured DMMA peak: a hardware fraction (<= 1). The algorithmic figure
+                    # of SURVEY 8d (what the reference's regression computes per posterior) is 2.6x the executed one because
+                    # the kernel only forms the lower-triangle blocks and, on the constant-Gram path, one row per observation;
+                    # it is reported as achieved_algorithmic / frac_algorithmic and may exceed 1.
+                    "achieved": pb_hw, "peak": fp64["dmma_tflops"], "unit": "TFLOP/s",
+                    "frac": pb_hw / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
+                    "achieved_algorithmic": pb_tflops,
+                    "frac_algorithmic": pb_tflops / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
+                    "traffic": prof_const["rank_update"]["dram_bytes_per_launch"] * C / prof_const["rank_update"]["chains"],
+                    "traffic_source": prof_const["rank_update"]["source"] + " (a PROFILE CONSTANT read from profiles/, scaled by C; not measured in this run)",
+                    "traffic_note": "algorithmic bytes per launch = C * (8 * 64 * 91 + 8 Kp) written (packed M, b) ~ 112 MB plus the "
                                     "observation frames read (~ 48 MB); the basis rows come from L2",
                     "peak_source": "DMMA m8n8k4 micro-benchmark run live on this GPU (MEASURED_PEAKS.json has no FP64 figure); "
                                    "DFMA measured %.1f TFLOP/s" % fp64["dfma_tflops"],
                     "flops_per_launch": flops_post * C, "executed_flops_per_launch": flops_exec * C, "avg_launch_ms": pb_ms,
                     "share_of_step": shares.get("posterior_build"), "top_kernel_by_time": top,
-                    "note": "achieved counts the reference's algorithmic flops per posterior (SURVEY 8d); hw_* counts the flops "
-                            "actually executed after exploiting symmetry and the constant Gram term"}
+                    "note": "achieved / frac count the flops actually executed (symmetry + constant Gram term exploited); "
+                            "*_algorithmic count the reference's flops per posterior (SURVEY 8d)"}
         # ---- BASELINE.json configs[0] shape: ONE chain, fixed seed - latency-bound by construction: steps/s of
         # the device-resident loop with a single resident chain, next to the 1-core CPU port below -------------------
         sc_steps = 300
@@ -367,6 +453,7 @@ def run_gpu(args):
                                 "a handful of warps, so this is launch + dependent-latency time, not throughput"}
         # ---- CPU baseline: the oracle port of the same chain on this box's host cores (bounded sample) ------
         cores = os.cpu_count() or 1
+        blas = enable_cpu_blas()
         cb_rate, cb_dt, _ = oracle_chain_rate(m, tv, tc, ids, eids, tp, 1, args.cpu_steps, 1, closed_form=False)
         opt_rate, opt_dt, _ = oracle_chain_rate(m, tv, tc, ids, eids, tp, 1, args.cpu_steps * 20, 1, closed_form=True)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
@@ -383,9 +470,11 @@ def run_gpu(args):
                 "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / steps, "accept_rate": accept_rate,
                 "clocks": clocks.summary(), "roofline": roofline, "roofline_cholesky": roof_chol, "roofline_closest_point": roof_cp, "closest_point": cp,
                 "kernel_shares": shares, "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items() if v["launches"]},
-                "fp64_peak": fp64, "gather_ms": gather_ms, "single_chain": single_chain,
+                "fp64_peak": fp64, "l2_read_gbs": l2_gbs, "gather_ms": gather_ms, "single_chain": single_chain,
+                "sustained": sustained, "per_call_api": per_call,
                 "cpu_baseline": {"value": cb_rate, "unit": UNIT, "cores": 1, "kind": "port",
-                                 "sample": f"1 chain x {args.cpu_steps} MH steps of the same workload, oracle in the reference's structure, 1 thread ({cb_dt:.1f} s); host has {cores} cores"},
+                                 "sample": f"1 chain x {args.cpu_steps} MH steps of the same workload, oracle in the reference's structure, 1 thread ({cb_dt:.1f} s); host has {cores} cores",
+                                 "linear_algebra": blas},
                 "cpu_baseline_optimised": {"value": opt_rate, "unit": UNIT, "cores": 1, "kind": "port",
                                            "sample": f"1 chain x {args.cpu_steps * 20} steps, oracle with the same closed forms as the device ({opt_dt:.1f} s)"},
                 "device": ctx.version()}
@@ -422,8 +511,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=2368, help="chains per GPU (16 x 148 SMs)")
-    ap.add_argument("--cpu-steps", type=int, default=60, help="MH steps of the cpu_baseline sample")
-    ap.add_argument("--ref-steps", type=int, default=4, help="MH steps per chain and bench step of --impl reference")
+    ap.add_argument("--cpu-steps", type=int, default=120, help="MH steps of the cpu_baseline sample")
+    ap.add_argument("--sustain-steps", type=int, default=2000, help="steps of the sustained-load arm (0 = skip)")
+    ap.add_argument("--ref-steps", type=int, default=12, help="MH steps per chain and bench step of --impl reference")
     args = ap.parse_args()
     if args.warmup < 1:
         args.warmup = 1

@@ -107,6 +107,7 @@ _SIGS = {
     "icp_debug_dmma_sweep": [_h, C.c_int32, C.c_int32, C.c_int32, _dp],
     "icp_chain_profile": [_h, C.c_int32, C.c_int32, _dp, C.c_uint64, _dp, _lp],
     "icp_debug_time_closest_point": [_h, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _dp],
+    "icp_debug_l2_bandwidth": [_h, C.c_int64, _dp],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["icp_stage_name"])
 

@@ -25,7 +25,7 @@ def _nvcc():
 
 
 def _newest_dep():
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "icpcuda.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", h) for h in ("icpcuda.h", "icpcuda_debug.h")]
     return max(os.path.getmtime(d) for d in deps)
 
 

@@ -1,6 +1,8 @@
 // debug.cu - profiling support: per-stage CUDA-event timers and FP64 peak micro-benchmarks
 // (the roofline denominators bench.py reports for the FP64 kernels; MEASURED_PEAKS.json only
 // carries HBM bandwidth and bf16 tensor throughput).
+#include <algorithm>
+
 #include "icp_internal.h"
 
 namespace icp {
@@ -60,9 +62,67 @@ __global__ void __launch_bounds__(256) k_dmma_peak(double *out, int iters) {
     if (s == 12345.678) out[0] = s;
 }
 
+// L2 -> SM read bandwidth: every thread streams 16-byte vectors of a working set that stays resident in L2 (a few MB),
+// L1 bypassed (ld.global.cg), four independent loads in flight per thread. The denominator of the closest-point
+// traversal's roofline: its tree and triangles (~0.5 MB) are cache resident, so HBM bandwidth does not bound it.
+__global__ void __launch_bounds__(256) k_l2_read(const float4 *__restrict__ buf, unsigned long long n_vec, int iters,
+                                                 float4 *__restrict__ sink) {
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x,
+                             stride = (unsigned long long)gridDim.x * blockDim.x;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < iters; it++) {
+        for (unsigned long long i = tid; i + 3 * stride < n_vec; i += 4 * stride) {
+            const float4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c = __ldcg(buf + i + 2 * stride),
+                         d = __ldcg(buf + i + 3 * stride);
+            acc.x += a.x + b.x + c.x + d.x; acc.y += a.y + b.y + c.y + d.y;
+            acc.z += a.z + b.z + c.z + d.z; acc.w += a.w + b.w + c.w + d.w;
+        }
+    }
+    if (acc.x == 12345.678f) sink[tid] = acc;
+}
+
 }  // namespace icp
 
 using namespace icp;
+
+extern "C" int32_t icp_debug_l2_bandwidth(icp_ctx ctx, int64_t working_set_bytes, double *gbps) {
+    icp_ctx _ctx = ctx;
+    try {
+        ICP_REQUIRE(ctx && gbps && working_set_bytes >= (1 << 20), "bad argument");
+        CtxLock lock(ctx);
+        cudaStream_t s = ctx->stream;
+        const int threads = 256, blocks = ctx->sm_count * 8;
+        const unsigned long long stride = (unsigned long long)threads * blocks;
+        unsigned long long n_vec = (unsigned long long)working_set_bytes / 16;
+        n_vec = n_vec / (4 * stride) * (4 * stride);          // whole rounds: every thread issues the same number of loads
+        ICP_REQUIRE(n_vec > 0, "working set smaller than one round of the grid");
+        DevBuf<float4> buf, sink;
+        buf.alloc(n_vec); sink.alloc(stride);
+        ICP_CUDA(cudaMemsetAsync(buf.p, 0, sizeof(float4) * n_vec, s));
+        cudaEvent_t e0, e1;
+        ICP_CUDA(cudaEventCreate(&e0));
+        ICP_CUDA(cudaEventCreate(&e1));
+        const int iters = (int)std::max<unsigned long long>(8, (4ull << 30) / (n_vec * 16));   // ~4 GB of reads per launch
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            ICP_CUDA(cudaEventRecord(e0, s));
+            k_l2_read<<<blocks, threads, 0, s>>>(buf.p, n_vec, iters, sink.p);
+            ICP_CUDA(cudaGetLastError());
+            ICP_CUDA(cudaEventRecord(e1, s));
+            ICP_CUDA(cudaStreamSynchronize(s));
+            float ms = 0;
+            ICP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            const double g = (double)n_vec * 16.0 * iters / (ms * 1e-3) / 1e9;
+            if (rep > 0 && g > best) best = g;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *gbps = best;
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
 
 extern "C" int32_t icp_debug_fp64_peak(icp_ctx ctx, double out[2]) {
     icp_ctx _ctx = ctx;

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/icpcuda.h"
+#include "../../include/icpcuda_debug.h"
 
 namespace icp {
 

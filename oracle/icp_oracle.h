@@ -161,6 +161,11 @@ int orc_chain_run(const orc_chain_desc *d, const double *theta0, int n_steps, co
                   const double *z, const double *u_acc, int32_t *comp, uint8_t *accepted, double *logv,
                   double *theta_log);
 
+/* Switches the dense linear algebra (products, symmetric eigen-decomposition) to an OpenBLAS / LAPACKE library opened from
+ * `path` (NULL switches back to the built-in loops). Returns 0 on success. Used by bench.py's timed CPU arm only. */
+int orc_use_blas(const char *path);
+int orc_blas_enabled(void);
+
 /* Philox4x32-10, the counter-based generator the device chain runner uses (bit-exact integer check) */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

@@ -98,9 +98,37 @@ def lib():
         L.orc_dice_coefficient.argtypes = [_vp, _vp, _dp, C.c_int, _dp]
         L.orc_chain_run.restype = C.c_int
         L.orc_chain_run.argtypes = [C.POINTER(_ChainDesc), _dp, C.c_int, _dp, _dp, _dp, _ip, _bp, _dp, _dp]
+        L.orc_use_blas.restype = C.c_int
+        L.orc_use_blas.argtypes = [C.c_char_p]
+        L.orc_blas_enabled.restype = C.c_int
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         _LIB = L
     return _LIB
+
+
+def find_blas():
+    """Path of an OpenBLAS build with CBLAS + LAPACKE entry points (the one scipy bundles), or None."""
+    import glob
+    try:
+        import scipy
+        hits = sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so")))
+    except Exception:
+        hits = []
+    for cand in hits + ["libopenblas.so.0", "libopenblas.so"]:
+        return cand
+    return None
+
+
+def use_blas(enable=True):
+    """Routes the oracle's dense linear algebra through OpenBLAS / LAPACK (timed CPU arm of bench.py). Returns the library
+    path in use, or None when the built-in loops stay active."""
+    if not enable:
+        lib().orc_use_blas(None)
+        return None
+    path = find_blas()
+    if path and lib().orc_use_blas(path.encode()) == 0:
+        return path
+    return None
 
 
 def _d(a):

@@ -17,7 +17,8 @@ from oracle import oracle as orc
 
 
 def _declared_functions():
-    src = open(os.path.join(ROOT, "include", "icpcuda.h")).read()
+    # the drop-in boundary (icpcuda.h) and the introspection / micro-benchmark entry points (icpcuda_debug.h)
+    src = open(os.path.join(ROOT, "include", "icpcuda.h")).read() + open(os.path.join(ROOT, "include", "icpcuda_debug.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(icp_[a-z0-9_]+)\s*\(", src)))
 
