@@ -364,7 +364,7 @@ def run_gpu(args):
 
     line = None
     if rank == 0:
-        l2_gbs = ctx.l2_bandwidth(8 << 20)      # L2 -> SM reads over an L2-resident 8 MB working set, measured live
+        l2_gbs = ctx.l2_bandwidth(32 << 20)     # L2 -> SM reads over an L2-resident 32 MB working set, measured live
         per_call = per_call_latency(m, model, pt, pm, ev, th0_host)
         # ---- per-kernel device times (CUDA events on the launching stream, eager pass over the same workload) --
         prof_steps = max(2, min(steps, 8))
@@ -412,7 +412,7 @@ def run_gpu(args):
         roof_cp = {"bound": "l2", "kernel": prof_const["closest_point"]["kernel"] + " (1e6 near-surface queries, timed alone)",
                    "achieved": cp["near_surface"]["algorithmic_GBps"], "peak": l2_gbs, "unit": "GB/s",
                    "frac": cp["near_surface"]["algorithmic_GBps"] / l2_gbs if l2_gbs else None,
-                   "peak_source": "L2 -> SM read bandwidth over an L2-resident 8 MB working set, measured live (icp_debug_l2_bandwidth); "
+                   "peak_source": "L2 -> SM read bandwidth over an L2-resident 32 MB working set, measured live (icp_debug_l2_bandwidth); "
                                   "the tree + triangles (0.5 MB) are cache resident, so L2 - not HBM - is the ceiling (SURVEY 8d)",
                    "frac_of_hbm_copy": cp["near_surface"]["algorithmic_GBps"] / peaks["hbm_gbs"], "hbm_peak": peaks["hbm_gbs"],
                    "hbm_peak_source": peak_src, "bytes_per_query": 1000,

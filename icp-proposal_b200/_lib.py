@@ -96,6 +96,12 @@ _SIGS = {
     "icp_gpmm_kernel_matrix": [_h, C.c_int32, _dp, C.c_int32, _dp, C.POINTER(KernelTerm), C.c_int32, _dp],
     "icp_gpmm_eigen_psd": [_h, C.c_int32, _dp, C.c_int32, _dp, _dp],
     "icp_gpmm_nystrom_extend": [_h, C.c_int32, _dp, C.c_int32, _dp, C.POINTER(KernelTerm), C.c_int32, C.c_int32, _dp, _dp, _dp, _dp],
+    "icp_comm_unique_id": [_h, _bp],
+    "icp_comm_init": [_h, C.c_int32, C.c_int32, _bp, C.POINTER(_h)],
+    "icp_comm_destroy": [_h],
+    "icp_comm_info": [_h, _ip, _ip, _ip],
+    "icp_chainlog_gather": [_h, C.c_int32, C.c_int32, C.c_int32, C.POINTER(ChainIO), C.POINTER(ChainIO), _dp, _lp],
+    "icp_variability_allreduce": [_h, _h, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _dp, _lp],
     "icp_chain_create": [_h, _h, C.POINTER(Component), C.c_int32, _h, C.c_int32, C.POINTER(_h)],
     "icp_chain_destroy": [_h],
     "icp_chain_run": [_h, C.c_int32, C.c_int32, _dp, C.POINTER(ChainIO)],

@@ -35,7 +35,7 @@ class Context:
         check(self.lib.icp_debug_fp64_peak(self.h, dptr(out)), self.h)
         return {"dfma_tflops": float(out[0]), "dmma_tflops": float(out[1])}
 
-    def l2_bandwidth(self, working_set_bytes=8 << 20):
+    def l2_bandwidth(self, working_set_bytes=32 << 20):
         """GB/s of L2 -> SM reads over an L2-resident working set (icp_debug_l2_bandwidth)."""
         out = C.c_double(0)
         check(self.lib.icp_debug_l2_bandwidth(self.h, int(working_set_bytes), C.byref(out)), self.h)

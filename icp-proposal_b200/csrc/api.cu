@@ -381,6 +381,12 @@ extern "C" int32_t icp_target_create(icp_ctx ctx, int32_t Nt, int32_t Tt, const 
             for (int d = 0; d < 3; d++) { t->lo[d] = std::min(t->lo[d], xyz[3 * v + d]); t->hi[d] = std::max(t->hi[d], xyz[3 * v + d]); }
         bvh_build(t->tri_bvh, 0, Tt, t->verts.p, t->tris.p, scale, s);
         bvh_build(t->vert_bvh, 1, Nt, t->verts.p, nullptr, scale, s);
+        {   // warp-cooperative closest point: L-ary collapse of the triangle LBVH (ICPCUDA_WIDE = 4 | 8). Off by default:
+            // measured on B200 it runs at 0.41 (L = 4) / 0.30 (L = 8) of the per-thread binary walk (profiles/r2_traversal.md)
+            const char *env = getenv("ICPCUDA_WIDE");
+            const int L = env ? atoi(env) : 0;
+            if (L == 4 || L == 8) wide_build(t->tri_bvh, t->tri_wide, L, s);
+        }
         t->tri_data.alloc((size_t)t->tri_bvh.n * 10);
         t->vert_data.alloc((size_t)t->vert_bvh.n * 4);
         k_gather_tri_data<<<(t->tri_bvh.n + 127) / 128, 128, 0, s>>>(t->tri_bvh.n, t->tri_bvh.prim.p, t->verts.p, t->tris.p, t->tri_data.p);
@@ -417,6 +423,8 @@ static NearestArgs target_tri_args(icp_target t) {
     NearestArgs a;
     a.bvh = &t->tri_bvh;
     a.prim_data = t->tri_data.p;
+    a.wide = t->wide();
+    a.sm_count = t->ctx->sm_count;
     return a;
 }
 static NearestArgs target_vert_args(icp_target t) {
@@ -681,7 +689,8 @@ void nearest_model_vertex(icp_model m, int C, const double *d_X, int64_t nq, con
 }
 
 void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const double *d_X, PosteriorWork &w, double *d_L,
-                        double *d_mu, const int *d_out_slot, cudaStream_t s, const SharedCp *shared, double *d_W) {
+                        double *d_mu, const int *d_out_slot, cudaStream_t s, const SharedCp *shared, double *d_W,
+                        const QuadArgs *qa) {
     if (C <= 0) return;
     icp_model m = p->model;
     icp_target t = p->target;
@@ -713,7 +722,7 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
         } else {
             w.cp.ensure(3 * tot);
             NearestArgs a;
-            a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = n;
+            a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.wide = t->wide(); a.sm_count = t->ctx->sm_count; a.C = C; a.nq = n;
             a.Xq = d_X; a.q_ids = p->ids.p; a.Nq = m->N; a.out_cp = w.cp.p; a.perm = p->qperm.p;
             if (w.seed.n < tot) { w.seed.ensure(tot); ICP_CUDA(cudaMemsetAsync(w.seed.p, 0xFF, sizeof(int) * tot, s)); }
             a.seed_slot = w.seed.p;
@@ -742,10 +751,13 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
                                                   (p->prm.tangential_noise * p->prm.tangential_noise)))};
     const GramFast *gfp = (p->gram_fast && all_kept) ? &gf : nullptr;
     w.Mp.ensure((size_t)C * (Kp / 8) * (Kp / 8 + 1) / 2 * 64);
-    if (!launch_posterior_fused(md, C, od, gfp, w.want_M ? w.M.p : nullptr, d_L, d_mu, d_out_slot, w.status.p, w.Mp.p, w.b.p, s)) {
+    bool quad_done = false;
+    if (!launch_posterior_fused(md, C, od, gfp, w.want_M ? w.M.p : nullptr, d_L, d_mu, d_out_slot, w.status.p, w.Mp.p, w.b.p, s, qa,
+                                &quad_done)) {
         launch_posterior_build(md, C, od, w.M.p, w.b.p, s, gfp);
-        launch_cholesky_solve(C, m->K, Kp, w.M.p, w.b.p, d_L, d_mu, d_out_slot, w.status.p, s, w.Mp.p);
+        launch_cholesky_solve(C, m->K, Kp, w.M.p, w.b.p, d_L, d_mu, d_out_slot, w.status.p, s, w.Mp.p, qa, &quad_done);
     }
+    if (qa && !quad_done) launch_quad_form(C, Kp, d_L, d_mu, d_out_slot, *qa, s);
     if (d_W) launch_svd_factor(C, m->K, Kp, d_L, m->sqrt_var.p, d_out_slot, d_W, w.svd_scratch, s);
 }
 
@@ -951,7 +963,7 @@ extern "C" int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t dire
         } else {
             w.cp.ensure(3 * tot);
             NearestArgs a;
-            a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = n;
+            a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.wide = t->wide(); a.sm_count = t->ctx->sm_count; a.C = C; a.nq = n;
             a.Xq = w.X.p; a.q_ids = tmp.ids.p; a.Nq = m->N; a.out_cp = w.cp.p;
             launch_nearest(a, s);
             oa.ids = tmp.ids.p; oa.cp = w.cp.p; oa.cp_stride = n; oa.cp_map = nullptr;
@@ -1051,7 +1063,7 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
             size_t tot = (size_t)C * e->n_ids;
             w.d2_m2t.ensure(tot);
             NearestArgs a;
-            a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = e->n_ids;
+            a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.wide = t->wide(); a.sm_count = t->ctx->sm_count; a.C = C; a.nq = e->n_ids;
             a.Xq = d_X; a.q_ids = e->ids.p; a.Nq = m->N; a.out_d2 = w.d2_m2t.p; a.perm = e->qperm.p;
             if (w.seed_m2t.n < tot) { w.seed_m2t.ensure(tot); ICP_CUDA(cudaMemsetAsync(w.seed_m2t.p, 0xFF, sizeof(int) * tot, s)); }
             a.seed_slot = w.seed_m2t.p;
@@ -1124,143 +1136,3 @@ extern "C" int32_t icp_eval_prior(icp_model m, int32_t C, const double *theta, d
     ICP_API_END
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Posterior variability maps from chain samples (apps/util/PosteriorVariability.scala:30-73 over the shapes of
-// apps/util/LogHelper.scala:39-41): S parameter vectors -> batched reconstruction (+ vertex normals) -> per-vertex
-// mean, sample covariance (divisor S - 1), its trace, and the variance along a direction n (the reference mesh's
-// vertex normal, or the un-normalised mean of the samples' unit vertex normals when sum_normals != 0).
-// Two passes like the reference (mean first, then centred moments). Thread / vertex so that a warp reads 768
-// contiguous bytes of one sample; the samples are split over gridDim.y partitions whose partial sums are combined in
-// partition order (deterministic).
-// ---------------------------------------------------------------------------------------------------
-constexpr int kVarThreads = 128;
-
-__global__ void __launch_bounds__(kVarThreads) k_var_sums(int S, int N, const double *__restrict__ X,
-                                                          const double *__restrict__ Nrm, double *__restrict__ part) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    const int P = gridDim.y, p = blockIdx.y;
-    const int s0 = (int)((long long)S * p / P), s1 = (int)((long long)S * (p + 1) / P);
-    double a[6] = {0, 0, 0, 0, 0, 0};
-    for (int s = s0; s < s1; s++) {
-        const double *x = X + ((size_t)s * N + v) * 3;
-        a[0] += x[0]; a[1] += x[1]; a[2] += x[2];
-        if (Nrm) {
-            const double *n = Nrm + ((size_t)s * N + v) * 3;
-            a[3] += n[0]; a[4] += n[1]; a[5] += n[2];
-        }
-    }
-    double *o = part + ((size_t)p * N + v) * 6;
-#pragma unroll
-    for (int k = 0; k < 6; k++) o[k] = a[k];
-}
-
-// mean[v] = sum / S; dir[v] = mean unit normal (sum_normals) or the given reference normal
-__global__ void k_var_means(int S, int N, int P, const double *__restrict__ part, const double *__restrict__ ref_normals,
-                            double *__restrict__ mean, double *__restrict__ dir) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    double a[6] = {0, 0, 0, 0, 0, 0};
-    for (int p = 0; p < P; p++)
-#pragma unroll
-        for (int k = 0; k < 6; k++) a[k] += part[((size_t)p * N + v) * 6 + k];
-    const double inv = 1.0 / S;
-#pragma unroll
-    for (int k = 0; k < 3; k++) mean[3 * v + k] = a[k] * inv;
-#pragma unroll
-    for (int k = 0; k < 3; k++) dir[3 * v + k] = ref_normals ? ref_normals[3 * v + k] : a[3 + k] * inv;
-}
-
-__global__ void __launch_bounds__(kVarThreads) k_var_moments(int S, int N, const double *__restrict__ X,
-                                                             const double *__restrict__ mean, const double *__restrict__ dir,
-                                                             double *__restrict__ part) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    const int P = gridDim.y, p = blockIdx.y;
-    const int s0 = (int)((long long)S * p / P), s1 = (int)((long long)S * (p + 1) / P);
-    const double mx = mean[3 * v], my = mean[3 * v + 1], mz = mean[3 * v + 2];
-    const double nx = dir[3 * v], ny = dir[3 * v + 1], nz = dir[3 * v + 2];
-    double a[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int s = s0; s < s1; s++) {
-        const double *x = X + ((size_t)s * N + v) * 3;
-        const double dx = x[0] - mx, dy = x[1] - my, dz = x[2] - mz;
-        a[0] += dx * dx; a[1] += dy * dy; a[2] += dz * dz;
-        a[3] += dx * dy; a[4] += dx * dz; a[5] += dy * dz;
-        const double t = nx * dx + ny * dy + nz * dz;
-        a[6] += t * t;
-    }
-    double *o = part + ((size_t)p * N + v) * 7;
-#pragma unroll
-    for (int k = 0; k < 7; k++) o[k] = a[k];
-}
-
-__global__ void k_var_finish(int S, int N, int P, const double *__restrict__ part, double *__restrict__ cov,
-                             double *__restrict__ total, double *__restrict__ along) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    double a[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int p = 0; p < P; p++)
-#pragma unroll
-        for (int k = 0; k < 7; k++) a[k] += part[((size_t)p * N + v) * 7 + k];
-    const double inv = 1.0 / (double)(S - 1);   // S == 1: 0 * inf = NaN, as the reference's 0.0 * (1.0 / 0)
-#pragma unroll
-    for (int k = 0; k < 7; k++) a[k] *= inv;
-    double *c = cov + 9 * (size_t)v;
-    c[0] = a[0]; c[4] = a[1]; c[8] = a[2];
-    c[1] = c[3] = a[3]; c[2] = c[6] = a[4]; c[5] = c[7] = a[5];
-    total[v] = a[0] + a[1] + a[2];
-    along[v] = a[6];
-}
-
-extern "C" int32_t icp_posterior_variability(icp_model m, int32_t S, const double *theta, int32_t sum_normals,
-                                             const double *theta_ref, double *mean, double *cov, double *total_variance,
-                                             double *normal_variance) {
-    ICP_API_BEGIN(m ? m->ctx : nullptr)
-    ICP_REQUIRE(S >= 1 && theta != nullptr, "posterior variability needs at least one sample");
-    cudaStream_t s = _ctx->stream;
-    const int N = m->N;
-    const size_t n3 = (size_t)N * 3;
-    DevBuf<double> X, Nrm, refX, refN, part, d_mean, d_dir, d_cov, d_total, d_along;
-    upload_theta(m, S, theta, m->s_theta, s);
-    X.alloc((size_t)S * n3);
-    launch_reconstruct(m->dev(), S, m->s_theta.p, X.p, s);
-    const double *ref_normals = nullptr;
-    if (sum_normals) {
-        Nrm.alloc((size_t)S * n3);
-        launch_vertex_normals(m->dev(), S, X.p, Nrm.p, s);
-    } else {
-        // normals of `ref`: transformedMesh(theta_ref), or the model's reference mesh when theta_ref is NULL
-        refN.alloc(n3);
-        const double *rx = m->ref.p;
-        if (theta_ref) {
-            DevBuf<double> th;
-            upload_theta(m, 1, theta_ref, th, s);
-            refX.alloc(n3);
-            launch_reconstruct(m->dev(), 1, th.p, refX.p, s);
-            rx = refX.p;
-            ICP_CUDA(cudaStreamSynchronize(s));   // th leaves scope
-        }
-        launch_vertex_normals(m->dev(), 1, rx, refN.p, s);
-        ref_normals = refN.p;
-    }
-    const int vb = (N + kVarThreads - 1) / kVarThreads;
-    int P = (4 * 148 + vb - 1) / vb;   // about four waves of CTAs
-    if (P > S) P = S;
-    if (P < 1) P = 1;
-    part.alloc((size_t)P * N * 7);
-    d_mean.alloc(n3); d_dir.alloc(n3); d_cov.alloc((size_t)N * 9); d_total.alloc(N); d_along.alloc(N);
-    k_var_sums<<<dim3(vb, P), kVarThreads, 0, s>>>(S, N, X.p, sum_normals ? Nrm.p : nullptr, part.p);
-    ICP_CUDA(cudaGetLastError());
-    k_var_means<<<vb, kVarThreads, 0, s>>>(S, N, P, part.p, ref_normals, d_mean.p, d_dir.p);
-    ICP_CUDA(cudaGetLastError());
-    k_var_moments<<<dim3(vb, P), kVarThreads, 0, s>>>(S, N, X.p, d_mean.p, d_dir.p, part.p);
-    ICP_CUDA(cudaGetLastError());
-    k_var_finish<<<vb, kVarThreads, 0, s>>>(S, N, P, part.p, d_cov.p, d_total.p, d_along.p);
-    ICP_CUDA(cudaGetLastError());
-    if (mean) download(mean, d_mean.p, n3, s);
-    if (cov) download(cov, d_cov.p, (size_t)N * 9, s);
-    if (total_variance) download(total_variance, d_total.p, N, s);
-    if (normal_variance) download(normal_variance, d_along.p, N, s);
-    sync_stream(_ctx);
-    ICP_API_END
-}

@@ -63,6 +63,9 @@ struct StateDev {
     double *W;                          // [n_icp][2 C][Kp Kp] the reference's SVD factor (ICP_FACTOR_SVD components; else null)
     int *status;                        // [C] sticky per-chain status bits (kSt*)
     double *theta_best, *value_best;    // [C][L], [C]: BestSampleLogger - the state with the largest product value so far
+    // |L^T d|^2 of every ICP component's forward (posterior of the current state, formed by k_chain_propose while it holds
+    // L_cur) and backward (posterior of the proposal, formed in the factorisation's epilogue) transition: [n_icp][C]
+    double *qf, *qb;
 };
 
 // per-chain status bits of a run (icp_chain_io.status)
@@ -146,11 +149,55 @@ __device__ void warp_backsolve_packed(const double *sL, int Kp, const double *z_
     __syncwarp();
 }
 
-// MixtureProposal.propose (pick the first component whose cumulative weight reaches r) + the component's propose
+// lower triangle of L (row-major Kp x Kp in global memory) -> packed row-major in shared memory (row i at i (i + 1) / 2):
+// warps take rows, lanes take columns
+__device__ __forceinline__ void stage_packed_L(const double *__restrict__ Lc, int Kp, double *sL) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i0 = warp; i0 < Kp; i0 += 4 * nw) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int i = i0 + r * nw;
+            if (i < Kp) {
+                const double *src = Lc + (size_t)i * Kp;
+                double *dst = sL + (i * (i + 1)) / 2;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    int j = lane + 32 * q;
+                    if (j <= i) dst[j] = __ldg(src + j);
+                }
+            }
+        }
+    }
+}
+
+// |L^T d|^2 with the packed lower triangle and d in shared memory: thread j owns column j (for a fixed row the threads read
+// consecutive words); result valid in every thread
+__device__ __forceinline__ double block_quad_packed(const double *sL, int Kp, const double *d_sm, double *red) {
+    double part = 0.0;
+    for (int j = threadIdx.x; j < Kp; j += blockDim.x) {
+        double v0 = 0.0, v1 = 0.0;
+        int i = j;
+        for (; i + 1 < Kp; i += 2) {
+            v0 = fma(sL[(i * (i + 1)) / 2 + j], d_sm[i], v0);
+            v1 = fma(sL[((i + 1) * (i + 2)) / 2 + j], d_sm[i + 1], v1);
+        }
+        if (i < Kp) v0 = fma(sL[(i * (i + 1)) / 2 + j], d_sm[i], v0);
+        const double v = v0 + v1;
+        part = fma(v, v, part);
+    }
+    return block_sum(part, red);
+}
+
+// MixtureProposal.propose (pick the first component whose cumulative weight reaches r) + the component's propose, then the
+// forward transition form |L_cur^T d|^2 of EVERY ICP component (MixtureProposal.logTransitionProbability sums over all of
+// them): the factors of the current state are staged here anyway, so k_chain_accept never reads a factor back.
 __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m, StateDev st, RngDev rng) {
     extern __shared__ double sm[];
     const int K = P.K, Kp = P.Kp, Lt = K + kTheta0, C = P.C;
-    double *sz = sm, *sw = sm + Kp, *sL = sm + 2 * Kp;  // sL: packed lower triangle, Kp (Kp + 1) / 2
+    // sz: z, then v = mu + W z | sw: W z | sdl: alpha' - alpha | sd: transition argument | sdg: diagonal of the staged factor |
+    // part: 2 Kp partial sums of S v | red: block reduction | sL: packed lower triangle
+    double *sz = sm, *sw = sm + Kp, *sdl = sm + 2 * Kp, *sd = sm + 3 * Kp, *sdg = sm + 4 * Kp, *part = sm + 5 * Kp, *red = sm + 7 * Kp,
+           *sL = sm + 7 * Kp + 40;
     __shared__ int s_ci;
     int c = blockIdx.x;
     unsigned int step = (unsigned int)*st.step;
@@ -181,6 +228,7 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
     const CompDev cd = P.comp[s_ci];
     const double *th = st.theta_cur + (size_t)c * Lt;
     double *to = st.theta_prop + (size_t)c * Lt;
+    bool staged = false;   // sL holds the selected component's factor (diagonal inverted, true diagonal in sdg)
     if (cd.kind == ICP_PROP_ICP) {
         size_t pslot = (size_t)cd.icp_index * 2 * C + st.slot_cur[c];
         const double *Lc = st.L + pslot * Kp * Kp, *muc = st.mu + pslot * Kp;
@@ -188,35 +236,17 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
             // the reference's factor W = D^-1 Ubar diag(sqrt(lambda')) of the current state's posterior (svdfactor.cu)
             block_matvec_rows(st.W + pslot * Kp * Kp, Kp, sz, sw);
         } else {
-        // lower triangle of L, packed row-major (row i at i (i + 1) / 2): warps take rows, lanes take columns
-        {
-            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-            for (int i0 = warp; i0 < Kp; i0 += 4 * nw) {
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    int i = i0 + r * nw;
-                    if (i < Kp) {
-                        const double *src = Lc + (size_t)i * Kp;
-                        double *dst = sL + (i * (i + 1)) / 2;
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            int j = lane + 32 * q;
-                            if (j <= i) dst[j] = __ldg(src + j);
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < Kp; i += blockDim.x) { double *d = sL + (i * (i + 1)) / 2 + i; *d = 1.0 / *d; }
-        __syncthreads();
-        if (threadIdx.x < 32) warp_backsolve_packed(sL, Kp, sz, sw);
+            stage_packed_L(Lc, Kp, sL);
+            __syncthreads();
+            for (int i = threadIdx.x; i < Kp; i += blockDim.x) { double *d = sL + (i * (i + 1)) / 2 + i; sdg[i] = *d; *d = 1.0 / *d; }
+            __syncthreads();
+            if (threadIdx.x < 32) warp_backsolve_packed(sL, Kp, sz, sw);
+            staged = true;
         }
         __syncthreads();
         for (int k = threadIdx.x; k < Kp; k += blockDim.x) sz[k] = muc[k] + sw[k];
         __syncthreads();
         // S v with S symmetric (read column-wise, coalesced); two halves of the k range per output
-        double *part = sL;  // the factor is no longer needed
         for (int idx = threadIdx.x; idx < 2 * Kp; idx += blockDim.x) {
             int jj = idx % Kp, half = idx / Kp;
             int k0 = half * (Kp / 2), k1 = half ? Kp : Kp / 2;
@@ -227,10 +257,14 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
         }
         __syncthreads();
         for (int j = threadIdx.x; j < Lt; j += blockDim.x) {
-            if (j < kTheta0) { to[j] = th[j]; continue; }
-            int jj = j - kTheta0;
-            double acc = part[jj] + part[Kp + jj];
-            to[j] = th[j] + (acc - th[j]) * cd.step;  // NonRigidIcpProposal.scala:61-62
+            double v = th[j];
+            if (j >= kTheta0) {
+                int jj = j - kTheta0;
+                double acc = part[jj] + part[Kp + jj];
+                v = th[j] + (acc - th[j]) * cd.step;  // NonRigidIcpProposal.scala:61-62
+                sdl[jj] = v - th[j];
+            }
+            to[j] = v;
         }
     } else {
         for (int j = threadIdx.x; j < Lt; j += blockDim.x) {
@@ -243,50 +277,28 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
                 if (j == 1 + cd.axis) v = th[j] + cd.sd * sz[0];         // PoseProposals.scala:70-78
             }
             to[j] = v;
+            if (j >= kTheta0) sdl[j - kTheta0] = v - th[j];
         }
     }
-}
-
-// |L_a^T d_a|^2 and |L_b^T d_b|^2 (forward and backward density of one ICP component; d in shared memory). Row-cooperative:
-// the warps deal the rows, a lane owns the columns lane + 32 q, so every load is one contiguous row segment, all lanes of
-// all warps stay busy (a column-per-thread loop leaves the triangle's short columns idle) and 2 x 4 rows are in flight
-// per warp. part: 2 * nwarps * Kp doubles of shared memory.
-template <int kQ>   // column slots per lane: Kp <= 32 kQ
-__device__ void chain_quad_LT2(const double *__restrict__ La, const double *__restrict__ Lb, int Kp, const double *da_sm,
-                               const double *db_sm, double *part, double *red, double &qa, double &qb) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    double va[kQ], vb[kQ];
-#pragma unroll
-    for (int q = 0; q < kQ; q++) va[q] = vb[q] = 0.0;
-#pragma unroll 2
-    for (int i = warp; i < Kp; i += nw) {
-        const double dai = da_sm[i], dbi = db_sm[i];
-        const double *ra = La + (size_t)i * Kp, *rb = Lb + (size_t)i * Kp;
-#pragma unroll
-        for (int q = 0; q < kQ; q++) {
-            const int j = lane + 32 * q;
-            if (j <= i) {
-                va[q] = fma(__ldg(ra + j), dai, va[q]);
-                vb[q] = fma(__ldg(rb + j), dbi, vb[q]);
-            }
+    __syncthreads();
+    // forward forms: d = (alpha + (alpha' - alpha) / step_i) - mu_cur,i   (NonRigidIcpProposal.scala:79, :82-83)
+    for (int i = 0; i < P.n_comp; i++) {
+        const CompDev ci = P.comp[i];
+        if (ci.kind != ICP_PROP_ICP) continue;
+        const size_t pslot = (size_t)ci.icp_index * 2 * C + st.slot_cur[c];
+        if (staged && i == s_ci) {
+            for (int k = threadIdx.x; k < Kp; k += blockDim.x) sL[(k * (k + 1)) / 2 + k] = sdg[k];   // the true diagonal again
+        } else {
+            stage_packed_L(st.L + pslot * Kp * Kp, Kp, sL);
         }
+        const double *mui = st.mu + pslot * Kp;
+        for (int k = threadIdx.x; k < Kp; k += blockDim.x)
+            sd[k] = k < K ? (th[kTheta0 + k] + (sdl[k] / ci.step)) - mui[k] : 0.0;
+        __syncthreads();
+        const double qf = block_quad_packed(sL, Kp, sd, red);
+        if (threadIdx.x == 0) st.qf[(size_t)ci.icp_index * C + c] = qf;
+        __syncthreads();
     }
-#pragma unroll
-    for (int q = 0; q < kQ; q++) {
-        const int j = lane + 32 * q;
-        if (j < Kp) { part[(size_t)warp * Kp + j] = va[q]; part[(size_t)(nw + warp) * Kp + j] = vb[q]; }
-    }
-    __syncthreads();
-    double pa = 0.0, pb = 0.0;
-    for (int j = threadIdx.x; j < Kp; j += blockDim.x) {
-        double sa = 0.0, sb = 0.0;
-        for (int w = 0; w < nw; w++) { sa += part[(size_t)w * Kp + j]; sb += part[(size_t)(nw + w) * Kp + j]; }
-        pa = fma(sa, sa, pa);
-        pb = fma(sb, sb, pb);
-    }
-    qa = block_sum(pa, red);
-    __syncthreads();
-    qb = block_sum(pb, red);
 }
 
 __device__ __forceinline__ double gauss1_logpdf(double x, double sd) {
@@ -297,7 +309,7 @@ __device__ __forceinline__ double gauss1_logpdf(double x, double sd) {
 __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st, LogDev lg, StatusSrc stsrc) {
     extern __shared__ double sm[];
     const int K = P.K, Kp = P.Kp, Lt = K + kTheta0, C = P.C;
-    double *sd = sm, *sd2 = sm + Kp, *red = sm + 2 * Kp, *part = sm + 2 * Kp + 40;   // part: [2][nwarps][Kp]
+    double *red = sm;
     __shared__ double s_fwd[kMaxComp], s_bwd[kMaxComp];
     __shared__ int s_flags[3];  // [0] any of theta[0..9] differs, [1] outside rotation group, [2] outside translation group
     int c = blockIdx.x;
@@ -324,16 +336,9 @@ __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st
         if (cd.kind == ICP_PROP_ICP) {
             if (s_flags[0]) { fwd = bwd = -INFINITY; }                          // NonRigidIcpProposal.scala:72-74
             else {
-                size_t sc = (size_t)cd.icp_index * 2 * C + st.slot_cur[c], sp = (size_t)cd.icp_index * 2 * C + st.slot_prop[c];
-                for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
-                    sd[k] = k < K ? (cur[kTheta0 + k] + ((prp[kTheta0 + k] - cur[kTheta0 + k]) / cd.step)) - st.mu[sc * Kp + k] : 0.0;
-                    sd2[k] = k < K ? (prp[kTheta0 + k] + ((cur[kTheta0 + k] - prp[kTheta0 + k]) / cd.step)) - st.mu[sp * Kp + k] : 0.0;
-                }
-                __syncthreads();
-                double qf, qb;
-                if (Kp <= 128) chain_quad_LT2<4>(st.L + sc * Kp * Kp, st.L + sp * Kp * Kp, Kp, sd, sd2, part, red, qf, qb);
-                else chain_quad_LT2<(8 * kMaxNBc + 31) / 32>(st.L + sc * Kp * Kp, st.L + sp * Kp * Kp, Kp, sd, sd2, part, red, qf, qb);
-                __syncthreads();
+                // the two quadratic forms were formed where the factors were on chip: forward by k_chain_propose (L_cur),
+                // backward by the factorisation of the proposal's posterior (L_prop)
+                const double qf = st.qf[(size_t)cd.icp_index * C + c], qb = st.qb[(size_t)cd.icp_index * C + c];
                 fwd = -0.5 * (K * ICP_LOG_2PI + qf);
                 bwd = -0.5 * (K * ICP_LOG_2PI + qb);
             }
@@ -420,7 +425,7 @@ struct icp_chain_s {
     ChainParams P{};
     std::vector<icp_proposal> icp_props;
     // state
-    DevBuf<double> theta_cur, theta_prop, values_cur, values_prop, u_acc, L, mu, X, W, theta_best, value_best;
+    DevBuf<double> theta_cur, theta_prop, values_cur, values_prop, u_acc, L, mu, X, W, theta_best, value_best, qf, qb;
     MetricsWork mwork;       // periodic RegistrationComparison of the best sample (icp_chain_io.metrics_interval)
     DevBuf<int> cur_sel, slot_cur, slot_prop, comp_sel, step, status;
     bool any_svd = false;    // some ICP component samples with the reference's SVD factor
@@ -580,7 +585,9 @@ struct RunCtx {
 
 // evaluator + ICP posteriors of the parameter vectors in `theta` (all chains), written to the
 // posterior state selected by `slots`
-void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, const int *d_slots) {
+// proposal: the state is the step's proposal, so every ICP posterior also leaves the backward transition form
+// |L_prop^T d|^2 (theta_prop -> theta_cur) in st.qb while its factor is on chip
+void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, const int *d_slots, bool proposal) {
     icp_chain ch = r.ch;
     icp_model m = ch->model;
     const int C = r.C, Kp = m->Kp;
@@ -601,7 +608,8 @@ void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, cons
         ICP_CUDA(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
         double *Lb = r.st.L + (size_t)i * 2 * C * Kp * Kp, *mub = r.st.mu + (size_t)i * 2 * C * Kp;
         double *Wb = ch->icp_props[i]->prm.factor == ICP_FACTOR_SVD ? r.st.W + (size_t)i * 2 * C * Kp * Kp : nullptr;
-        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, ss, nullptr, Wb);
+        QuadArgs qa{r.st.theta_prop, r.st.theta_cur, ch->icp_props[i]->prm.step_length, m->K, r.st.qb + (size_t)i * C};
+        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, ss, nullptr, Wb, proposal ? &qa : nullptr);
         ICP_CUDA(cudaEventRecord(ctx->ev_join[n_side], ss));
         ch->on_side[i] = 1;
         n_side++;
@@ -612,7 +620,9 @@ void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, cons
         double *Lb = r.st.L + (size_t)i * 2 * C * Kp * Kp, *mub = r.st.mu + (size_t)i * 2 * C * Kp;
         SharedCp sh{ch->ework.cp_m2t.p, ch->evaluator->n_ids, ch->cp_map[i].p};
         double *Wb = ch->icp_props[i]->prm.factor == ICP_FACTOR_SVD ? r.st.W + (size_t)i * 2 * C * Kp * Kp : nullptr;
-        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, r.s, ch->cp_shared[i] ? &sh : nullptr, Wb);
+        QuadArgs qa{r.st.theta_prop, r.st.theta_cur, ch->icp_props[i]->prm.step_length, m->K, r.st.qb + (size_t)i * C};
+        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, r.s, ch->cp_shared[i] ? &sh : nullptr, Wb,
+                           proposal ? &qa : nullptr);
     }
     for (int k = 0; k < n_side; k++) ICP_CUDA(cudaStreamWaitEvent(r.s, ctx->ev_join[k], 0));   // join
 }
@@ -631,16 +641,16 @@ void enqueue_step(RunCtx &r) {
     const int C = r.C, Kp = m->Kp;
     ChainParams P = ch->P;
     P.C = C;
-    size_t smem_p = sizeof(double) * ((size_t)2 * Kp + (size_t)Kp * (Kp + 1) / 2);
+    size_t smem_p = sizeof(double) * ((size_t)7 * Kp + 40 + (size_t)Kp * (Kp + 1) / 2);
     {
         ProfScope ps(ST_PROPOSE, r.s);
         k_chain_propose<<<C, 256, smem_p, r.s>>>(P, m->dev(), r.st, r.rng);
         ICP_CUDA(cudaGetLastError());
     }
-    enqueue_state_eval(r, r.st.theta_prop, r.st.values_prop, r.st.slot_prop);
+    enqueue_state_eval(r, r.st.theta_prop, r.st.values_prop, r.st.slot_prop, true);
     {
         ProfScope ps(ST_ACCEPT, r.s);
-        k_chain_accept<<<C, 128, sizeof(double) * (2 * Kp + 40 + 2 * 4 * Kp), r.s>>>(P, r.st, r.lg, status_sources(ch));
+        k_chain_accept<<<C, 128, sizeof(double) * 40, r.s>>>(P, r.st, r.lg, status_sources(ch));
         ICP_CUDA(cudaGetLastError());
         k_step_increment<<<1, 1, 0, r.s>>>(r.st.step);
         ICP_CUDA(cudaGetLastError());
@@ -668,6 +678,7 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     ch->comp_sel.ensure(C); ch->step.ensure(1); ch->n_acc.ensure(C); ch->estatus.ensure(C); ch->status.ensure(C);
     if (ch->any_svd) ch->W.ensure((size_t)std::max(n_icp, 1) * 2 * C * Kp * Kp);
     ch->theta_best.ensure((size_t)C * Lt); ch->value_best.ensure(C);
+    ch->qf.ensure((size_t)std::max(n_icp, 1) * C); ch->qb.ensure((size_t)std::max(n_icp, 1) * C);
     ICP_REQUIRE(io->metrics_interval >= 0, "metrics_interval must be >= 0");
     ICP_REQUIRE(io->metrics_interval == 0 || io->log_metrics != nullptr, "metrics_interval > 0 needs log_metrics");
     ch->L.ensure((size_t)std::max(n_icp, 1) * 2 * C * Kp * Kp); ch->mu.ensure((size_t)std::max(n_icp, 1) * 2 * C * Kp);
@@ -677,7 +688,8 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     r.ch = ch; r.C = C; r.s = s;
     r.st = StateDev{ch->theta_cur.p, ch->theta_prop.p, ch->values_cur.p, ch->values_prop.p, ch->cur_sel.p,
                     ch->slot_cur.p, ch->slot_prop.p, ch->comp_sel.p, ch->u_acc.p, ch->n_acc.p, ch->step.p, ch->L.p,
-                    ch->mu.p, ch->any_svd ? ch->W.p : nullptr, ch->status.p, ch->theta_best.p, ch->value_best.p};
+                    ch->mu.p, ch->any_svd ? ch->W.p : nullptr, ch->status.p, ch->theta_best.p, ch->value_best.p,
+                    ch->qf.p, ch->qb.p};
     const int step_base = resume ? ch->steps_total : 0;
     r.rng = RngDev{io->seed, io->chain_id_offset, io->u_comp, io->z, io->u_acc, step_base};
     r.lg = LogDev{io->log_component, io->log_accepted, io->log_values, io->log_theta, step_base};
@@ -689,13 +701,13 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
         ICP_CUDA(cudaGetLastError());
     }
     {
-        size_t smem_p = sizeof(double) * ((size_t)2 * Kp + (size_t)Kp * (Kp + 1) / 2);
+        size_t smem_p = sizeof(double) * ((size_t)7 * Kp + 40 + (size_t)Kp * (Kp + 1) / 2);
         ICP_REQUIRE(smem_p <= 227 * 1024, "rank too large for the propose kernel");
         ICP_CUDA(cudaFuncSetAttribute(k_chain_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
     }
     // state of theta0: log-values + posteriors of every ICP component (state 0)
     if (!resume) {
-        enqueue_state_eval(r, ch->theta_cur.p, ch->values_cur.p, ch->slot_cur.p);
+        enqueue_state_eval(r, ch->theta_cur.p, ch->values_cur.p, ch->slot_cur.p, false);
         k_chain_status0<<<(C + 127) / 128, 128, 0, s>>>(C, Lt, r.st, status_sources(ch));
         ICP_CUDA(cudaGetLastError());
     }

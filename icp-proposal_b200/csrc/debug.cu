@@ -91,9 +91,11 @@ extern "C" int32_t icp_debug_l2_bandwidth(icp_ctx ctx, int64_t working_set_bytes
         ICP_REQUIRE(ctx && gbps && working_set_bytes >= (1 << 20), "bad argument");
         CtxLock lock(ctx);
         cudaStream_t s = ctx->stream;
-        const int threads = 256, blocks = ctx->sm_count * 8;
-        const unsigned long long stride = (unsigned long long)threads * blocks;
+        const int threads = 256;
         unsigned long long n_vec = (unsigned long long)working_set_bytes / 16;
+        int blocks = ctx->sm_count * 8;
+        while (blocks > ctx->sm_count && 4ull * threads * blocks > n_vec) blocks -= ctx->sm_count;
+        const unsigned long long stride = (unsigned long long)threads * blocks;
         n_vec = n_vec / (4 * stride) * (4 * stride);          // whole rounds: every thread issues the same number of loads
         ICP_REQUIRE(n_vec > 0, "working set smaller than one round of the grid");
         DevBuf<float4> buf, sink;
@@ -170,7 +172,7 @@ extern "C" int32_t icp_debug_time_closest_point(icp_target t, int64_t nq, const 
         CtxLock lock(_ctx);
         cudaStream_t s = _ctx->stream;
         NearestArgs a;
-        a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.nq = nq; a.q = q_dev;
+        a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.wide = t->wide(); a.sm_count = t->ctx->sm_count; a.nq = nq; a.q = q_dev;
         a.out_prim = tri_dev; a.out_cp = cp_dev; a.out_d2 = d2_dev;
         launch_nearest_sorted(a, t->qsort, t->lo, t->hi, s);
         cudaEvent_t e0, e1;

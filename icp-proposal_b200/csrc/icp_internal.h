@@ -127,9 +127,20 @@ void bvh_build(Bvh &b, int prim_kind, int n_prims, const double *d_verts, const 
 // refits `instances` sets of boxes from vertex positions X[instance][N][3]
 void bvh_refit(Bvh &b, int instances, const double *d_X, int N, const int *d_tris, cudaStream_t s);
 
+// L-ary collapse of a static triangle LBVH for the warp-cooperative traversal (bvh_wide.cu): n_nodes wide nodes in
+// breadth-first order, each L child records of two float4 {lo.x, lo.y, lo.z, hi.x}, {hi.y, hi.z, reference, -}; a
+// reference >= 0 is a wide node, < 0 encodes a leaf cluster ~((first slot << 3) | (count - 1)) of Morton-contiguous triangles
+struct WideBvh {
+    int L = 0, n_nodes = 0, n_leaves = 0;
+    DevBuf<float4> nodes;
+};
+void wide_build(const Bvh &b, WideBvh &w, int L, cudaStream_t s);
+
 struct NearestArgs {
     // structure
     const Bvh *bvh = nullptr;
+    const WideBvh *wide = nullptr;      // static triangle structures: take the warp-cooperative kernel when set
+    int sm_count = 148;
     const double *prim_data = nullptr;  // static: tri_data [slot][10] / vert_data [slot][4]; nullptr => dynamic
     const double *X = nullptr;          // dynamic: vertex positions [instance][N][3]
     const int *tris = nullptr;          // dynamic triangles
@@ -154,6 +165,8 @@ struct NearestArgs {
     double *out_d2 = nullptr;
 };
 void launch_nearest(const NearestArgs &a, cudaStream_t s);
+// false: the arguments are outside the wide kernel's domain (nothing launched)
+bool launch_nearest_wide(const NearestArgs &a, int sm_count, cudaStream_t s);
 // scratch of the query-ordering pass of large point batches
 struct QuerySort {
     DevBuf<unsigned int> keys, keys2;
@@ -223,13 +236,29 @@ struct GramFast {
 void launch_posterior_build(const ModelDev &m, int C, const ObsDev &o, double *d_M, double *d_b, cudaStream_t s,
                             const GramFast *gf = nullptr);
 void launch_gram_rows(const ModelDev &m, int n_ids, const int *d_ids, double *d_G, cudaStream_t s);
+// Transition density of the chain runner that belongs to the posterior being built, formed while the factor is still in
+// shared memory: out[c] = |L_c^T d|^2, d = (theta_post + (theta_other - theta_post) / step)[alpha] - mu_c
+// (logTransitionProbability(theta_post -> theta_other), NonRigidIcpProposal.scala:76-83)
+struct QuadArgs {
+    const double *theta_post;    // [C][K+10] the state the posterior belongs to
+    const double *theta_other;   // [C][K+10] the other end of the transition
+    double step;
+    int K;
+    double *out;                 // [C]
+};
+// qa (nullable): also the quadratic form above; *quad_done tells whether the launched path formed it (the caller runs
+// launch_quad_form otherwise)
 bool launch_posterior_fused(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, double *d_M_or_null, double *d_L,
-                            double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s);
+                            double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s,
+                            const QuadArgs *qa = nullptr, bool *quad_done = nullptr);
+// the same quadratic form from L / mu in global memory (paths whose factorisation kernel does not form it)
+void launch_quad_form(int C, int Kp, const double *d_L, const double *d_mu, const int *d_slot, const QuadArgs &qa, cudaStream_t s);
 // in: M (C x Kp x Kp), b (C x Kp). out: L (lower Cholesky factor, C x Kp x Kp), mu = M^-1 b, status (0 ok)
 // out_slot (nullable): chain c writes L / mu at index out_slot[c] instead of c
 // d_Mp: scratch for the block-packed lower triangle (C x NB (NB + 1) / 2 x 64 doubles), needed when Kp > 160
 void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
-                           const int *d_out_slot, int *d_status, cudaStream_t s, double *d_Mp = nullptr);
+                           const int *d_out_slot, int *d_status, cudaStream_t s, double *d_Mp = nullptr,
+                           const QuadArgs *qa = nullptr, bool *quad_done = nullptr);
 // alpha' = alpha + step (S (mu + L^-T z) - alpha); L/mu addressed through per-chain slot indices
 // d_W (nullable): explicit factor [slot][Kp][Kp] (ICP_FACTOR_SVD); alpha' then uses W z instead of L^-T z
 void launch_propose(const ModelDev &m, int C, double step, const double *d_theta, const double *d_z,
@@ -319,6 +348,8 @@ struct icp_target_s {
     bool has_boundary = false;
     std::vector<uint8_t> h_boundary;
     icp::Bvh tri_bvh, vert_bvh;
+    icp::WideBvh tri_wide;          // L-ary collapse of tri_bvh (empty when ICPCUDA_WIDE=0)
+    const icp::WideBvh *wide() const { return tri_wide.n_nodes > 0 ? &tri_wide : nullptr; }
     icp::QuerySort qsort;
     double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};   // bounding box of the vertices
     icp::DevBuf<double> s_q, s_d;
@@ -417,7 +448,7 @@ struct SharedCp {
 // d_W (nullable, [slot][Kp][Kp]): also the reference's SVD-based covariance factor (ICP_FACTOR_SVD)
 void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const double *d_X, PosteriorWork &w, double *d_L,
                         double *d_mu, const int *d_out_slot, cudaStream_t s, const SharedCp *shared = nullptr,
-                        double *d_W = nullptr);
+                        double *d_W = nullptr, const QuadArgs *qa = nullptr);
 // distance evaluator pipeline: values [C][3] = {product, prior, distance}
 void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_theta, const double *d_X, double *d_values,
                         int *d_status, cudaStream_t s);

@@ -61,7 +61,7 @@ void registration_metrics_device(icp_model m, icp_target t, int C, const double 
     launch_reconstruct(m->dev(), C, d_theta, w.X.p, s);
     // every model vertex against the target surface
     NearestArgs a;
-    a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.C = C; a.nq = N; a.q = w.X.p; a.q_per_chain = 1;
+    a.bvh = &t->tri_bvh; a.prim_data = t->tri_data.p; a.wide = t->wide(); a.sm_count = t->ctx->sm_count; a.C = C; a.nq = N; a.q = w.X.p; a.q_per_chain = 1;
     a.out_d2 = w.d2a.p; a.out_cp = w.cpa.p;
     launch_nearest(a, s);
     const uint8_t *skip_p = nullptr;

@@ -969,7 +969,8 @@ constexpr int kCh3Threads = 128;
 __global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, const double *__restrict__ Mp,
                                                                     const double *__restrict__ bvec, double *__restrict__ M_out,
                                                                     double *__restrict__ L, double *__restrict__ mu,
-                                                                    const int *__restrict__ out_slot, int *__restrict__ status) {
+                                                                    const int *__restrict__ out_slot, int *__restrict__ status,
+                                                                    QuadArgs qa) {
     extern __shared__ __align__(16) double sp[];
     constexpr int NT = kCh3Threads;
     const int NB = Kp >> 3, ntri = NB * (NB + 1) / 2;
@@ -1156,6 +1157,33 @@ __global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, cons
     }
     for (int j = tid; j < Kp; j += NT) __stcs(mu + (size_t)oc * Kp + j, isbad ? NAN : xo[j]);
     if (tid == 0 && status) status[c] = isbad ? 1 : 0;
+    if (qa.out) {
+        // chain runner: |L^T d|^2 of the transition theta_post -> theta_other while L is still here (k_chain_accept would
+        // otherwise read it back from HBM). d overwrites the right-hand side scratch.
+        const int Lt = qa.K + kTheta0;
+        const double *tp = qa.theta_post + (size_t)c * Lt + kTheta0, *to = qa.theta_other + (size_t)c * Lt + kTheta0;
+        for (int k = tid; k < Kp; k += NT) xs[k] = k < qa.K ? (tp[k] + ((to[k] - tp[k]) / qa.step)) - xo[k] : 0.0;
+        __syncthreads();
+        double part = 0.0;
+        for (int j = tid; j < Kp; j += NT) {
+            double v0 = 0.0, v1 = 0.0;
+            int i = j;
+            for (; i + 1 < Kp; i += 2) { v0 = fma(A[pk_at(i, j)], xs[i], v0); v1 = fma(A[pk_at(i + 1, j)], xs[i + 1], v1); }
+            if (i < Kp) v0 = fma(A[pk_at(i, j)], xs[i], v0);
+            const double v = v0 + v1;
+            part = fma(v, v, part);
+        }
+        // block sum through the (now free) dinv scratch
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        __syncthreads();
+        if (lane == 0) dinv[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < NT / 32; w++) t += dinv[w];
+            qa.out[c] = isbad ? NAN : t;
+        }
+    }
     ICP_FT(if (tid == 0 && c < 8192) g_ft[kFtStride * c + 11] = clock64() - fts;)
 }
 
@@ -1580,7 +1608,8 @@ extern "C" int icp_debug_fused_timing(long long *out, int n) {
 
 template <int NBLK, int NBMAX, int NWC>
 static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M, int total, const GramFast *gf, double *d_L,
-                         double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s) {
+                         double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s,
+                         const QuadArgs *qa, bool *quad_done) {
     const int Kp = m.Kp, ld = Kp + 4;
     size_t stage = (size_t)2 * kMmaRows * ld + 8 * Kp + (std::min(o.n, kMaxStagedIds) + 3) / 4 * 2 + (size_t)kRawStages * kProdWarps * 32 * 3 * ((NBMAX + 1) / 2) * 2;
     size_t fact = (size_t)(Kp + 8) * ld + 3 * Kp;
@@ -1602,7 +1631,8 @@ static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M,
         ProfScope _ps(ST_CHOLESKY, s);
         size_t smem_c = sizeof(double) * ((size_t)total * 64 + 4 * Kp);
         ICP_CUDA(cudaFuncSetAttribute(k_cholesky_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-        k_cholesky_packed<<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, d_M, d_L, d_mu, d_out_slot, d_status);
+        k_cholesky_packed<<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, d_M, d_L, d_mu, d_out_slot, d_status, qa ? *qa : QuadArgs{});
+        if (quad_done) *quad_done = qa != nullptr;
         return;
     }
     ProfScope _ps(ST_POSTERIOR_BUILD, s);
@@ -1621,16 +1651,18 @@ static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M,
 // (d_Mp, C x NB (NB + 1) / 2 x 64 doubles) and b (d_b), k_cholesky_packed factorises at four chains per SM.
 // ICPCUDA_FUSE=1 (or d_Mp == nullptr): the single-launch variant, whose factorisation runs at two chains per SM.
 bool launch_posterior_fused(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, double *d_M_or_null, double *d_L,
-                            double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s) {
+                            double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s,
+                            const QuadArgs *qa, bool *quad_done) {
+    if (quad_done) *quad_done = false;
     static const bool off = (getenv("ICPCUDA_NO_DMMA") && getenv("ICPCUDA_NO_DMMA")[0] == '1') ||
                             (getenv("ICPCUDA_NO_FUSE") && getenv("ICPCUDA_NO_FUSE")[0] == '1');
     static const bool one_launch = getenv("ICPCUDA_FUSE") && getenv("ICPCUDA_FUSE")[0] == '1';
     const int NB = m.Kp / 8, total = NB * (NB + 1) / 2;
     if (off || NB > 13 || C <= 0) return false;   // NB <= 13: the 192-thread variants; the fused matrix must fit 2 CTAs / SM
     if (one_launch) d_Mp = nullptr;
-    if (NB <= 4) launch_fused<4, 4, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, d_Mp, d_b, s);
-    else if (NB <= 7) launch_fused<8, 7, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, d_Mp, d_b, s);
-    else launch_fused<24, 13, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, d_Mp, d_b, s);
+    if (NB <= 4) launch_fused<4, 4, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, d_Mp, d_b, s, qa, quad_done);
+    else if (NB <= 7) launch_fused<8, 7, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, d_Mp, d_b, s, qa, quad_done);
+    else launch_fused<24, 13, 4>(m, C, o, d_M_or_null, total, gf, d_L, d_mu, d_out_slot, d_status, d_Mp, d_b, s, qa, quad_done);
     ICP_CUDA(cudaGetLastError());
     return true;
 }
@@ -1648,8 +1680,9 @@ __global__ void __launch_bounds__(128) k_pack_lower(int Kp, const double *__rest
 }
 
 void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double *d_b, double *d_L, double *d_mu,
-                           const int *d_out_slot, int *d_status, cudaStream_t s, double *d_Mp) {
+                           const int *d_out_slot, int *d_status, cudaStream_t s, double *d_Mp, const QuadArgs *qa, bool *quad_done) {
     ProfScope _ps(ST_CHOLESKY, s);
+    if (quad_done) *quad_done = false;
     if (C <= 0) return;
     static const bool no_mma = getenv("ICPCUDA_NO_DMMA") && getenv("ICPCUDA_NO_DMMA")[0] == '1';
     if (sizeof(double) * ((size_t)(Kp + 8) * (Kp + 4) + 3 * Kp) > 227 * 1024) {
@@ -1660,8 +1693,9 @@ void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double
         k_pack_lower<<<C, 128, 0, s>>>(Kp, d_M, d_Mp);
         ICP_CUDA(cudaGetLastError());
         ICP_CUDA(cudaFuncSetAttribute(k_cholesky_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-        k_cholesky_packed<<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, nullptr, d_L, d_mu, d_out_slot, d_status);
+        k_cholesky_packed<<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, nullptr, d_L, d_mu, d_out_slot, d_status, qa ? *qa : QuadArgs{});
         ICP_CUDA(cudaGetLastError());
+        if (quad_done) *quad_done = qa != nullptr;
         return;
     }
     if (!no_mma) {
@@ -1771,6 +1805,27 @@ __global__ void __launch_bounds__(128) k_log_transition(int K, int Kp, double st
     __syncthreads();
     double q = block_quad_LT(L + (size_t)sl * Kp * Kp, Kp, sd, red);
     if (threadIdx.x == 0) out[c] = differs ? -INFINITY : -0.5 * (K * ICP_LOG_2PI + q);  // :83
+}
+
+// |L^T d|^2 with L / mu read back from global memory: the factorisation paths that do not form it in their epilogue
+__global__ void __launch_bounds__(128) k_quad_form(int Kp, const double *__restrict__ L, const double *__restrict__ mu,
+                                                   const int *__restrict__ slot, QuadArgs qa) {
+    extern __shared__ double sm[];
+    double *sd = sm, *red = sm + Kp;
+    const int c = blockIdx.x, Lt = qa.K + kTheta0;
+    const int sl = slot ? slot[c] : c;
+    const double *tp = qa.theta_post + (size_t)c * Lt + kTheta0, *to = qa.theta_other + (size_t)c * Lt + kTheta0;
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x)
+        sd[k] = k < qa.K ? (tp[k] + ((to[k] - tp[k]) / qa.step)) - mu[(size_t)sl * Kp + k] : 0.0;
+    __syncthreads();
+    const double q = block_quad_LT(L + (size_t)sl * Kp * Kp, Kp, sd, red);
+    if (threadIdx.x == 0) qa.out[c] = q;
+}
+
+void launch_quad_form(int C, int Kp, const double *d_L, const double *d_mu, const int *d_slot, const QuadArgs &qa, cudaStream_t s) {
+    if (C <= 0) return;
+    k_quad_form<<<C, 128, sizeof(double) * (Kp + 40), s>>>(Kp, d_L, d_mu, d_slot, qa);
+    ICP_CUDA(cudaGetLastError());
 }
 
 void launch_log_transition(int C, int K, int Kp, double step, const double *d_from, const double *d_to,

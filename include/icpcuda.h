@@ -45,6 +45,7 @@ typedef struct icp_target_s *icp_target;
 typedef struct icp_proposal_s *icp_proposal;
 typedef struct icp_evaluator_s *icp_evaluator;
 typedef struct icp_chain_s *icp_chain;
+typedef struct icp_comm_s *icp_comm;
 
 /* ---- (1) context --------------------------------------------------------------------------- */
 int32_t icp_ctx_create(int32_t device, icp_ctx *out);
@@ -288,6 +289,35 @@ int32_t icp_ctx_synchronize(icp_ctx ctx);
 /* device time in milliseconds of the last icp_chain_run* on this chain (CUDA events on the
  * library stream) and the number of kernels it launched */
 int32_t icp_chain_last_run_stats(icp_chain c, double *device_ms, int64_t *kernel_launches);
+
+/* ---- (8) multi-GPU: one process per GPU, NCCL over NVLink ---------------------------------------------- */
+/* Chains / random-init restarts / targets are independent (apps/femur/RunMHRandomInitComparison.scala:66-86,
+ * StdIcpVsChainICPrandomInitComparisonAll.scala:107-122): rank r runs its own chains with
+ * icp_chain_io.chain_id_offset = first global chain id, model and target replicated, and there is no collective on the
+ * per-sample path. These entry points are the end-of-run exchange: the gather of the chain logs and the reduction of the
+ * posterior statistics. The library opens libnccl.so.2 (or $ICPCUDA_NCCL_LIB) on first use; hosts that never call them
+ * need no NCCL. Rank 0 obtains the 128-byte id and hands it to the other ranks through the host's own channel (the
+ * Scala driver's RPC / a file / an environment variable); icp_comm_init is collective over all `world` ranks. */
+#define ICP_COMM_UNIQUE_ID_BYTES 128
+int32_t icp_comm_unique_id(icp_ctx ctx, uint8_t id[ICP_COMM_UNIQUE_ID_BYTES]);
+int32_t icp_comm_init(icp_ctx ctx, int32_t rank, int32_t world, const uint8_t id[ICP_COMM_UNIQUE_ID_BYTES], icp_comm *out);
+int32_t icp_comm_destroy(icp_comm c);
+int32_t icp_comm_info(icp_comm c, int32_t *rank, int32_t *world, int32_t *nccl_version);
+/* All-gather of a sharded run's chain logs (the records of JSONAcceptRejectLogger, api/sampling/loggers/
+ * JSONAcceptRejectLogger.scala:93-106, as icp_chain_run_device left them in device memory). Every rank passes its own
+ * [n_steps][C] arrays in local_dev and receives [world][n_steps][C] arrays (rank-major) in gathered_dev; the pointers
+ * used are log_component, log_accepted, log_values, log_theta, theta_final, n_accepted, status, theta_best, value_best -
+ * each either non-NULL on both sides or NULL on both. All ranks must pass the same n_steps, C, K and the same set of
+ * arrays. device_ms: CUDA-event time of the exchange on this rank; bytes_received: payload that arrived here. */
+int32_t icp_chainlog_gather(icp_comm c, int32_t n_steps, int32_t C, int32_t K, const icp_chain_io *local_dev,
+                            const icp_chain_io *gathered_dev, double *device_ms, int64_t *bytes_received);
+/* icp_posterior_variability over the samples of ALL ranks (apps/util/PosteriorVariability.scala:30-73): every rank passes
+ * the S_local (>= 0) logged parameter vectors it holds (host memory); the per-vertex sums are all-reduced (global mean
+ * first, then the moments centred on it), and every rank receives the same maps as one call over the union would give
+ * (up to summation order). S_total: number of samples over all ranks. */
+int32_t icp_variability_allreduce(icp_comm c, icp_model m, int32_t S_local, const double *theta_local, int32_t sum_normals,
+                                  const double *theta_ref, double *mean, double *cov, double *total_variance,
+                                  double *normal_variance, int64_t *S_total);
 
 /* ---- (9) GPMM construction from analytic kernels (the step before the hot path) -------------------- */
 /* One term of the matrix-valued kernel of apps/femur/CreateGPModel.scala:68-83:

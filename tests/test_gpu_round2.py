@@ -55,7 +55,9 @@ def test_propose_svd_factor_matches_reference_structure(ctx, request, femur, dir
     mu, M, _ = gp.posterior(th[:1])
     prop0 = gp.propose(th[:1], np.zeros((1, K)))[0, 10:]
     W = np.stack([gp.propose(th[:1], np.eye(K)[i][None])[0, 10:] - prop0 for i in range(K)], axis=1) / 0.1
-    np.testing.assert_allclose(W @ W.T, np.linalg.inv(M[0]), rtol=1e-5, atol=1e-9)
+    # (W is read off through propose, i.e. as S W with the 1e-5 regulariser's S = I + O(2e-7): absolute slack on that scale)
+    Minv = np.linalg.inv(M[0])
+    np.testing.assert_allclose(W @ W.T, Minv, rtol=1e-5, atol=1e-5 * np.abs(Minv).max())
     gc = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, direction, True, ids, tp)
     assert np.abs(gc.propose(th, z) - prop).max() > 1e-3
     gc.close(); gp.close(); model.close(); tgt.close()
