@@ -208,6 +208,23 @@ def per_call_latency(m, model, pt, pm, ev, th0_host, iters=40):
             done = sum(ex.map(lambda t: chain(t, iters), range(threads)))
         dt = time.perf_counter() - t0
         out[f"threads_{threads}"] = {"steps_per_s": done / dt, "ms_per_step_per_thread": dt / iters * 1e3}
+    # the same MH step with C chains funnelled into ONE batched call per entry point ("better: the Scala side
+    # funnels the C chains into one batched call"): whole-job steps/s = C x calls/s
+    for Cb in (10, 100):
+        rng = np.random.default_rng(900 + Cb)
+        th = th0_host[:Cb].copy()
+        n = max(10, iters // 2)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            z = rng.normal(size=(Cb, K))
+            prop = (pt if rng.random() < 0.5 else pm).propose(th, z)
+            for p in (pt, pm):
+                p.log_transition(th, prop)
+                p.log_transition(prop, th)
+            ev.log_value(prop)
+            th = prop
+        dt = time.perf_counter() - t0
+        out[f"batched_{Cb}_chains_per_call"] = {"steps_per_s": Cb * n / dt, "ms_per_batched_step": dt / n * 1e3}
     out["note"] = ("per-call C ABI, C = 1 per call, host buffers in and out on every call; 7 calls per MH step "
                    "(1 propose, 4 log_transition, 1 eval + the posterior cache); calls on one context serialise")
     return out
@@ -299,20 +316,41 @@ def run_gpu(args):
                              ((s_comp.nbytes + s_acc.nbytes + s_val.nbytes + s_th.nbytes) / 1e9)}
         del s_comp, s_acc, s_val, s_th
 
-    # ---- chain statistics gathered over NCCL (the only collective; not on the per-sample path) -------------
+    # ---- end-of-run exchange through the library's own NCCL entry points (icp_comm_*; the only collectives, not on the
+    # per-sample path): all-gather of the FULL chain logs of the timed steps and all-reduce of the posterior variability
+    # maps over the final states. torch.distributed only ferries the 128-byte communicator id. ---------------------------
     gather_ms = None
+    gather = None
     if world > 1:
-        stats = torch.cat([th_final[:, 10:].mean(0), (th_final[:, 10:] ** 2).mean(0), log_val[-1].mean(0)])
-        out = torch.empty((world,) + stats.shape, dtype=stats.dtype, device=dev)
-        fin = torch.empty((world,) + th_final.shape, dtype=th_final.dtype, device=dev)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.all_gather_into_tensor(out, stats)
-        dist.all_gather_into_tensor(fin, th_final)
-        e1.record()
-        torch.cuda.synchronize()
-        gather_ms = max_over_ranks(e0.elapsed_time(e1))
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.from_numpy(core.Comm.unique_id(ctx)).to(dev)
+        dist.broadcast(uid, 0)
+        comm = core.Comm(ctx, rank, world, uid.cpu().numpy())
+        g_comp = torch.empty((world, steps, C), dtype=torch.int32, device=dev); g_acc = torch.empty((world, steps, C), dtype=torch.uint8, device=dev)
+        g_val = torch.empty((world, steps, C, 3), dtype=torch.float64, device=dev); g_th = torch.empty((world, steps, C, L), dtype=torch.float64, device=dev)
+        g_fin = torch.empty((world, C, L), dtype=torch.float64, device=dev); g_nacc = torch.empty((world, C), dtype=torch.int64, device=dev)
+        lio, gio = _lib.ChainIO(), _lib.ChainIO()
+        lio.log_component, lio.log_accepted, lio.log_values, lio.log_theta = log_comp.data_ptr(), log_acc.data_ptr(), log_val.data_ptr(), log_th.data_ptr()
+        lio.theta_final, lio.n_accepted = th_final.data_ptr(), n_acc.data_ptr()
+        gio.log_component, gio.log_accepted, gio.log_values, gio.log_theta = g_comp.data_ptr(), g_acc.data_ptr(), g_val.data_ptr(), g_th.data_ptr()
+        gio.theta_final, gio.n_accepted = g_fin.data_ptr(), g_nacc.data_ptr()
+        comm.chainlog_gather(steps, C, K, lio, gio)                       # warm-up (NCCL sets up its channels on first use)
+        barrier()
+        ms, nbytes = comm.chainlog_gather(steps, C, K, lio, gio)
+        gather_ms = max_over_ranks(ms)
+        ok = bool(torch.equal(g_th[rank], log_th) and torch.equal(g_acc[rank], log_acc))
+        t0 = time.perf_counter()
+        vmaps = comm.variability_allreduce(model, th_final[: min(C, 256)].cpu().numpy(), sum_normals=True)
+        var_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        gather = {"chainlog_gather_ms": gather_ms, "bytes_received_per_rank": int(nbytes), "GBps_per_rank": nbytes / (gather_ms * 1e-3) / 1e9,
+                  "own_shard_intact": ok, "whole_job_accept_rate": float(g_acc.float().mean().item()),
+                  "variability_allreduce_ms": var_ms, "variability_samples": int(vmaps["n"]),
+                  "mean_total_variance": float(vmaps["total_variance"].mean()), "nccl_version": comm.nccl_version(),
+                  "note": "icp_chainlog_gather (ncclAllGather of every log array of the timed steps, grouped) and "
+                          "icp_variability_allreduce (two ncclAllReduce passes), both through libicpcuda's own communicator"}
+        del g_comp, g_acc, g_val, g_th, g_fin, g_nacc
+        comm.close()
 
     # ---- end-to-end arm: the public host-buffer call (pinned host memory in, chain log out) ---------------
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
@@ -470,7 +508,7 @@ def run_gpu(args):
                 "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / steps, "accept_rate": accept_rate,
                 "clocks": clocks.summary(), "roofline": roofline, "roofline_cholesky": roof_chol, "roofline_closest_point": roof_cp, "closest_point": cp,
                 "kernel_shares": shares, "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items() if v["launches"]},
-                "fp64_peak": fp64, "l2_read_gbs": l2_gbs, "gather_ms": gather_ms, "single_chain": single_chain,
+                "fp64_peak": fp64, "l2_read_gbs": l2_gbs, "gather_ms": gather_ms, "gather": gather, "single_chain": single_chain,
                 "sustained": sustained, "per_call_api": per_call,
                 "cpu_baseline": {"value": cb_rate, "unit": UNIT, "cores": 1, "kind": "port",
                                  "sample": f"1 chain x {args.cpu_steps} MH steps of the same workload, oracle in the reference's structure, 1 thread ({cb_dt:.1f} s); host has {cores} cores",

@@ -86,6 +86,7 @@ _SIGS = {
     "icp_log_transition": [_h, C.c_int32, _dp, _dp, _dp],
     "icp_proposal_clear_cache": [_h],
     "icp_std_icp_iteration": [_h, _h, C.c_int32, _ip, C.c_int32, _dp, C.c_int32, C.c_double, C.c_double, C.c_int32, _dp, _dp],
+    "icp_std_icp_iteration_theta": [_h, _h, C.c_int32, _ip, C.c_int32, _dp, C.c_int32, C.c_double, C.c_double, C.c_int32, _dp, _dp],
     "icp_evaluator_create": [_h, _h, C.POINTER(EvaluatorParams), _ip, C.c_int32, _dp, C.c_int32, C.POINTER(_h)],
     "icp_evaluator_destroy": [_h],
     "icp_eval_log_value": [_h, C.c_int32, _dp, _dp, _ip],

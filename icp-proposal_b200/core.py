@@ -226,6 +226,17 @@ def std_icp_iteration(model: Model, target: Target, direction, model_point_ids, 
     return out
 
 
+def std_icp_iteration_theta(model: Model, target: Target, direction, model_point_ids, target_points, sigma2, step_length, theta):
+    """icp_std_icp_iteration_theta: one deterministic ICP iteration under the rigid transform carried by theta -> alpha_out."""
+    ids = i32(np.asarray(model_point_ids).reshape(-1))
+    tp = f64(np.asarray(target_points, dtype=np.float64).reshape(-1, 3))
+    th, c = model._theta(theta)
+    out = np.empty((c, model.K))
+    check(model.lib.icp_std_icp_iteration_theta(model.h, target.h, int(direction), iptr(ids), len(ids), dptr(tp), len(tp),
+                                                float(sigma2), float(step_length), c, dptr(th), dptr(out)), model.ctx.h)
+    return out
+
+
 class Evaluator:
     """Device side of the DistributionEvaluators (api/sampling/evaluators/*.scala)."""
 
@@ -328,6 +339,54 @@ def posterior_variability(model: Model, thetas, sum_normals=True, theta_ref=None
     check(model.lib.icp_posterior_variability(model.h, s, dptr(th), 1 if sum_normals else 0, dptr(ref) if ref is not None else None,
                                               dptr(mean), dptr(cov), dptr(tot), dptr(nrm)), model.ctx.h)
     return dict(mean=mean, cov=cov, total_variance=tot, normal_variance=nrm)
+
+
+class Comm:
+    """NCCL communicator of the library (icp_comm_*): end-of-run gather of chain logs and reduction of posterior statistics.
+    Rank 0 calls Comm.unique_id(ctx) and ships the 128 bytes to the other ranks through any channel it likes."""
+
+    def __init__(self, ctx: Context, rank, world, unique_id):
+        self.ctx, self.lib = ctx, ctx.lib
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        self.h = C.c_void_p()
+        check(self.lib.icp_comm_init(ctx.h, int(rank), int(world), uid.ctypes.data_as(_lib._bp), C.byref(self.h)), ctx.h)
+        self.rank, self.world = int(rank), int(world)
+
+    @staticmethod
+    def unique_id(ctx: Context):
+        uid = np.zeros(128, np.uint8)
+        check(ctx.lib.icp_comm_unique_id(ctx.h, uid.ctypes.data_as(_lib._bp)), ctx.h)
+        return uid
+
+    def nccl_version(self):
+        v = C.c_int32(0)
+        check(self.lib.icp_comm_info(self.h, None, None, C.byref(v)))
+        return v.value
+
+    def chainlog_gather(self, n_steps, C_, K, local: "_lib.ChainIO", gathered: "_lib.ChainIO"):
+        """local / gathered: ChainIO structures holding raw DEVICE addresses. Returns (device ms, bytes received)."""
+        ms = C.c_double(0); nb = C.c_int64(0)
+        check(self.lib.icp_chainlog_gather(self.h, int(n_steps), int(C_), int(K), C.byref(local), C.byref(gathered), C.byref(ms),
+                                           C.byref(nb)), self.ctx.h)
+        return ms.value, nb.value
+
+    def variability_allreduce(self, model: Model, thetas, sum_normals=True, theta_ref=None):
+        th = f64(thetas).reshape(-1, model.K + THETA0)
+        s = len(th)
+        n = model.N
+        mean, cov, tot, nrm = np.empty((n, 3)), np.empty((n, 3, 3)), np.empty(n), np.empty(n)
+        ref = None if theta_ref is None else f64(theta_ref).reshape(-1)
+        total = C.c_int64(0)
+        check(self.lib.icp_variability_allreduce(self.h, model.h, s, dptr(th) if s else None, 1 if sum_normals else 0,
+                                                 dptr(ref) if ref is not None else None, dptr(mean), dptr(cov), dptr(tot), dptr(nrm),
+                                                 C.byref(total)), self.ctx.h)
+        return dict(n=total.value, mean=mean, cov=cov, total_variance=tot, normal_variance=nrm)
+
+    def close(self):
+        if self.h:
+            self.lib.icp_comm_destroy(self.h)
+            self.h = None
 
 
 class Chain:

@@ -301,6 +301,7 @@ extern "C" int32_t icp_model_destroy(icp_model m) {
     icp_ctx _ctx = m->ctx;
     try {
         CtxLock lock(_ctx);
+        ICP_REQUIRE(m->refs == 0, "model is still referenced by " + std::to_string(m->refs) + " proposal / evaluator / chain handle(s): destroy those first");
         sync_stream(_ctx);
         delete m;
         return ICP_OK;
@@ -408,6 +409,7 @@ extern "C" int32_t icp_target_destroy(icp_target t) {
     icp_ctx _ctx = t->ctx;
     try {
         CtxLock lock(_ctx);
+        ICP_REQUIRE(t->refs == 0, "target is still referenced by " + std::to_string(t->refs) + " proposal / evaluator / chain handle(s): destroy those first");
         sync_stream(_ctx);
         delete t;
         return ICP_OK;
@@ -647,6 +649,7 @@ extern "C" int32_t icp_proposal_create(icp_model m, icp_target t, const icp_prop
             }
         }
         sync_stream(_ctx);
+        m->refs++; t->refs++;
         *out = p;
         return ICP_OK;
     } catch (...) {
@@ -661,7 +664,9 @@ extern "C" int32_t icp_proposal_destroy(icp_proposal p) {
     icp_ctx _ctx = p->model->ctx;
     try {
         CtxLock lock(_ctx);
+        ICP_REQUIRE(p->refs == 0, "proposal is still used by a chain: destroy the chain first");
         sync_stream(_ctx);
+        p->model->refs--; p->target->refs--;
         delete p;
         return ICP_OK;
     } catch (...) {
@@ -913,23 +918,49 @@ __global__ void k_std_icp_step(int C, int K, int Kp, double step, const double *
     }
 }
 
+static int32_t std_icp_iteration_impl(icp_model m, icp_target t, int32_t direction, const int32_t *model_point_ids,
+                                      int32_t n_ids, const double *target_points, int32_t n_tp, double sigma2,
+                                      double step_length, int32_t C, const double *alpha, const double *theta, double *alpha_out);
+
 extern "C" int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t direction, const int32_t *model_point_ids,
                                          int32_t n_ids, const double *target_points, int32_t n_tp, double sigma2,
                                          double step_length, int32_t C, const double *alpha, double *alpha_out) {
+    return std_icp_iteration_impl(m, t, direction, model_point_ids, n_ids, target_points, n_tp, sigma2, step_length, C, alpha,
+                                  nullptr, alpha_out);
+}
+
+extern "C" int32_t icp_std_icp_iteration_theta(icp_model m, icp_target t, int32_t direction, const int32_t *model_point_ids,
+                                               int32_t n_ids, const double *target_points, int32_t n_tp, double sigma2,
+                                               double step_length, int32_t C, const double *theta, double *alpha_out) {
+    if (C > 0 && !theta) return ICP_ERR_INVALID_ARGUMENT;
+    return std_icp_iteration_impl(m, t, direction, model_point_ids, n_ids, target_points, n_tp, sigma2, step_length, C, nullptr,
+                                  theta, alpha_out);
+}
+
+// alpha != null: identity pose (IcpRegistration passes the rigid identity); theta != null: currentTrans from theta
+static int32_t std_icp_iteration_impl(icp_model m, icp_target t, int32_t direction, const int32_t *model_point_ids,
+                                      int32_t n_ids, const double *target_points, int32_t n_tp, double sigma2,
+                                      double step_length, int32_t C, const double *alpha, const double *theta, double *alpha_out) {
     ICP_API_BEGIN(m ? m->ctx : nullptr)
     ICP_REQUIRE(t && t->ctx == m->ctx, "bad target");
     ICP_REQUIRE(direction == ICP_MODEL_SAMPLING || direction == ICP_TARGET_SAMPLING, "bad direction");
     ICP_REQUIRE(sigma2 > 0, "sigma2 must be > 0");
     if (C == 0) return ICP_OK;
-    ICP_REQUIRE(alpha && alpha_out, "null array");
+    ICP_REQUIRE((alpha || theta) && alpha_out, "null array");
     check_ids(m->N, model_point_ids, n_ids);
     cudaStream_t s = _ctx->stream;
     const int K = m->K, Kp = m->Kp, Lt = K + kTheta0;
-    // identity pose (IcpRegistration passes the rigid identity), theta = [1, 0.., alpha]
-    std::vector<double> th((size_t)C * Lt, 0.0);
+    // identity pose: theta = [1, 0.., alpha]; otherwise the caller's rigid transform (model.transform(currentTrans), :61)
+    std::vector<double> th((size_t)C * Lt, 0.0), al((size_t)C * K);
     for (int c = 0; c < C; c++) {
-        th[(size_t)c * Lt] = 1.0;
-        memcpy(&th[(size_t)c * Lt + kTheta0], alpha + (size_t)c * K, sizeof(double) * K);
+        if (theta) {
+            memcpy(&th[(size_t)c * Lt], theta + (size_t)c * Lt, sizeof(double) * Lt);
+            memcpy(&al[(size_t)c * K], theta + (size_t)c * Lt + kTheta0, sizeof(double) * K);
+        } else {
+            th[(size_t)c * Lt] = 1.0;
+            memcpy(&th[(size_t)c * Lt + kTheta0], alpha + (size_t)c * K, sizeof(double) * K);
+            memcpy(&al[(size_t)c * K], alpha + (size_t)c * K, sizeof(double) * K);
+        }
     }
     icp_proposal_s tmp;
     tmp.model = m; tmp.target = t;
@@ -941,7 +972,7 @@ extern "C" int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t dire
     DevBuf<double> dth, dL, dmu, da, dout;
     dth.upload(th.data(), th.size(), s);
     dL.alloc((size_t)C * Kp * Kp); dmu.alloc((size_t)C * Kp);
-    da.upload(alpha, (size_t)C * K, s); dout.alloc((size_t)C * K);
+    da.upload(al.data(), (size_t)C * K, s); dout.alloc((size_t)C * K);
     // run the pipeline with isotropic noise: patch ObsArgs through a local copy of the pipeline
     {
         icp_proposal p = &tmp;
@@ -956,6 +987,7 @@ extern "C" int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t dire
         w.M.ensure((size_t)C * Kp * Kp); w.b.ensure((size_t)C * Kp); w.status.ensure(C);
         ObsArgs oa{};
         oa.m = md; oa.prm = p->prm; oa.C = C; oa.theta = dth.p; oa.X = w.X.p; oa.iso = 1; oa.iso_sigma2 = sigma2;
+        oa.world_frame = 1;   // :81 model.posterior(corr, sigma) on the untransformed model, targets as they are
         if (tsamp) {
             w.prim.ensure(tot);
             nearest_model_vertex(m, C, w.X.p, n, tmp.tp.p, 0, nullptr, w.prim.p, s);
@@ -1017,6 +1049,7 @@ extern "C" int32_t icp_evaluator_create(icp_model m, icp_target t, const icp_eva
             if (params->kind == ICP_EVAL_COLLECTIVE) ICP_REQUIRE(params->p2 > 0, "Exponential rate must be > 0");
         }
         sync_stream(_ctx);
+        m->refs++; t->refs++;
         *out = e;
         return ICP_OK;
     } catch (...) {
@@ -1031,7 +1064,9 @@ extern "C" int32_t icp_evaluator_destroy(icp_evaluator e) {
     icp_ctx _ctx = e->model->ctx;
     try {
         CtxLock lock(_ctx);
+        ICP_REQUIRE(e->refs == 0, "evaluator is still used by a chain: destroy the chain first");
         sync_stream(_ctx);
+        e->model->refs--; e->target->refs--;
         delete e;
         return ICP_OK;
     } catch (...) {

@@ -544,6 +544,8 @@ extern "C" int32_t icp_chain_create(icp_model m, icp_target t, const icp_compone
         ICP_CUDA(cudaEventCreate(&ch->ev1));
         const char *env = getenv("ICPCUDA_NO_GRAPH");
         ch->use_graph = !(env && env[0] == '1');
+        m->refs++; t->refs++; evaluator->refs++;
+        for (icp_proposal pr : ch->icp_props) pr->refs++;
         *out = ch;
         return ICP_OK;
     } catch (...) {
@@ -564,6 +566,8 @@ extern "C" int32_t icp_chain_destroy(icp_chain c) {
         if (c->ev1) cudaEventDestroy(c->ev1);
         if (c->copy_ev) cudaEventDestroy(c->copy_ev);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+        c->model->refs--; c->target->refs--; c->evaluator->refs--;
+        for (icp_proposal pr : c->icp_props) pr->refs--;
         delete c;
         return ICP_OK;
     } catch (...) {

@@ -224,6 +224,8 @@ struct ObsArgs {
     const int *near_vid;   // [C][n]
     int iso;               // 1: isotropic noise sigma2 (deterministic ICP), frame = I / sqrt(sigma2)
     double iso_sigma2;
+    int world_frame;       // 1: the observation is target point - reference point as it is, NOT pulled back through the inverse
+                           // pose (IcpBasedSurfaceFitting.scala:81 regresses the untransformed model on world-frame targets)
 };
 void launch_observations(const ObsArgs &a, const ObsDev &o, cudaStream_t s);
 // M = I + sum_i (F_i Q_i)^T (F_i Q_i) (lower + upper, Kp x Kp, identity on the padding), b = sum (F_i Q_i)^T y_i
@@ -311,6 +313,7 @@ struct icp_ctx_s {
 
 struct icp_model_s {
     icp_ctx ctx = nullptr;
+    int refs = 0;                     // proposals / evaluators / chains built on this handle (destroy refuses while > 0)
     int N = 0, T = 0, K = 0, Kp = 0;  // Kp = K padded to a multiple of 8
     icp::DevBuf<double> ref;          // N x 3
     icp::DevBuf<double> mean;         // 3N: mean deformation
@@ -338,6 +341,7 @@ struct icp_model_s {
 
 struct icp_target_s {
     icp_ctx ctx = nullptr;
+    int refs = 0;
     int Nt = 0, Tt = 0;
     icp::DevBuf<double> verts;      // Nt x 3
     icp::DevBuf<int> tris;          // Tt x 3
@@ -379,6 +383,7 @@ struct PosteriorWork {
 }  // namespace icp
 
 struct icp_proposal_s {
+    int refs = 0;             // chains using this proposal
     icp_model model = nullptr;
     icp_target target = nullptr;
     icp_proposal_params prm{};
@@ -411,6 +416,7 @@ struct EvalWork {
 }  // namespace icp
 
 struct icp_evaluator_s {
+    int refs = 0;
     icp_model model = nullptr;
     icp_target target = nullptr;
     icp_evaluator_params prm{};

@@ -116,7 +116,8 @@ __device__ __forceinline__ void observations_grouped(const ObsArgs &a, const Obs
         for (int p = 0; p < mv; p++) {
             const int i = seg[p];
             double ix, iy, iz;
-            inverse_pose(th, R, a.tp[3 * i], a.tp[3 * i + 1], a.tp[3 * i + 2], ix, iy, iz);  // :129
+            if (a.world_frame) { ix = a.tp[3 * i]; iy = a.tp[3 * i + 1]; iz = a.tp[3 * i + 2]; }
+            else inverse_pose(th, R, a.tp[3 * i], a.tp[3 * i + 1], a.tp[3 * i + 2], ix, iy, iz);  // :129
             s0 += (ix - m.ref[3 * v]) - m.mean[3 * v];
             s1 += (iy - m.ref[3 * v + 1]) - m.mean[3 * v + 1];
             s2 += (iz - m.ref[3 * v + 2]) - m.mean[3 * v + 2];
@@ -214,7 +215,8 @@ __global__ void __launch_bounds__(256) k_observations(ObsArgs a, ObsDev o) {
         double R[9];
         pose_matrix(th, R);
         double ix, iy, iz;
-        inverse_pose(th, R, tx, ty, tz, ix, iy, iz);                    // :108,129 inversePoseTransform(targetPoint)
+        if (a.world_frame) { ix = tx; iy = ty; iz = tz; }
+        else inverse_pose(th, R, tx, ty, tz, ix, iy, iz);               // :108,129 inversePoseTransform(targetPoint)
         double y0 = (ix - m.ref[3 * id]) - m.mean[3 * id], y1 = (iy - m.ref[3 * id + 1]) - m.mean[3 * id + 1],
                y2 = (iz - m.ref[3 * id + 2]) - m.mean[3 * id + 2];
         for (int k = 0; k < 9; k++) F[k] = f[k];

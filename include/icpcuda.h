@@ -152,11 +152,18 @@ int32_t icp_proposal_clear_cache(icp_proposal p);
  * O(K) host arithmetic in the reference; they exist on the device inside icp_chain_run only. */
 
 /* model.posterior(corr, sigma2).mean + model.coefficients + step of the deterministic ICP
- * (api/other/IcpBasedSurfaceFitting.scala:55-92), identity pose: alpha C x K -> alpha_out C x K.
+ * (api/other/IcpBasedSurfaceFitting.scala:55-92), identity pose (what IcpRegistration.scala:40-43 passes): alpha C x K -> alpha_out C x K.
  * direction per call (the reference flips an unseeded coin, :67, so the caller supplies it). */
 int32_t icp_std_icp_iteration(icp_model m, icp_target t, int32_t direction, const int32_t *model_point_ids,
                               int32_t n_ids, const double *target_points, int32_t n_tp, double sigma2,
                               double step_length, int32_t C, const double *alpha, double *alpha_out);
+
+/* the same iteration under a rigid transform (currentTrans, :61 `model.transform(currentTrans).instance(params)`): theta
+ * C x (K+10) carries the transform and the coefficients. As in the reference the correspondences are found on the
+ * transformed instance while the posterior (:81) is that of the untransformed model on the target points as they are. */
+int32_t icp_std_icp_iteration_theta(icp_model m, icp_target t, int32_t direction, const int32_t *model_point_ids,
+                                    int32_t n_ids, const double *target_points, int32_t n_tp, double sigma2,
+                                    double step_length, int32_t C, const double *theta, double *alpha_out);
 
 /* ---- (6) evaluators (api/sampling/evaluators/<Name>.scala, ProductEvaluators.scala) -------------- */
 #define ICP_EVAL_ACCEPT_ALL 0     /* AcceptAllEvaluator.scala:22-28 */

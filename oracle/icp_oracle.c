@@ -1014,8 +1014,22 @@ void orc_std_icp_iteration(const orc_model *md, const orc_mesh *target, int dire
                            const int32_t *ids, int n_tp, const double *target_points, double sigma2,
                            double step_length, const double *alpha, double *alpha_out)
 {
-    int K = md->K, N = md->N; size_t n3 = (size_t)3 * N;
+    int K = md->K;
     double *theta = (double *)calloc(K + 10, sizeof(double)); theta[0] = 1.0; memcpy(theta + 10, alpha, sizeof(double) * K);
+    orc_std_icp_iteration_theta(md, target, direction, n_ids, ids, n_tp, target_points, sigma2, step_length, theta, alpha_out);
+    free(theta);
+}
+
+/* The same iteration with a rigid transform (currentTrans, :61): the correspondences are found on
+ * model.transform(currentTrans).instance(params) = transformedMesh(theta), but the posterior (:81) is that of the
+ * UNTRANSFORMED model with the target points as they are - the reference does not pull them back through the transform. */
+void orc_std_icp_iteration_theta(const orc_model *md, const orc_mesh *target, int direction, int n_ids,
+                                 const int32_t *ids, int n_tp, const double *target_points, double sigma2,
+                                 double step_length, const double *theta_in, double *alpha_out)
+{
+    int K = md->K, N = md->N; size_t n3 = (size_t)3 * N;
+    const double *alpha = theta_in + 10;
+    double *theta = (double *)malloc(sizeof(double) * (K + 10)); memcpy(theta, theta_in, sizeof(double) * (K + 10));
     double *xyz = (double *)malloc(sizeof(double) * n3);
     orc_transformed_mesh(md, theta, xyz);                       /* :61 instance */
     int n = direction == ORC_MODEL_SAMPLING ? n_ids : n_tp;

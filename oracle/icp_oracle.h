@@ -96,6 +96,11 @@ void orc_std_icp_iteration(const orc_model *model, const orc_mesh *target, int d
                            const int32_t *ids, int n_tp, const double *target_points, double sigma2,
                            double step_length, const double *alpha, double *alpha_out);
 
+/* the same iteration under a rigid transform: theta = [s, t, rot, centre, alpha] (:61 model.transform(currentTrans)) */
+void orc_std_icp_iteration_theta(const orc_model *model, const orc_mesh *target, int direction, int n_ids,
+                                 const int32_t *ids, int n_tp, const double *target_points, double sigma2,
+                                 double step_length, const double *theta, double *alpha_out);
+
 /* ---- evaluators ----------------------------------------------------------------------------- */
 enum { ORC_MODEL_TO_TARGET = 0, ORC_TARGET_TO_MODEL = 1, ORC_SYMMETRIC = 2 };
 

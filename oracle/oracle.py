@@ -80,6 +80,7 @@ def lib():
         L.orc_log_transition_closed_form.restype = C.c_double
         L.orc_log_transition_closed_form.argtypes = [_vp, _dp, _dp]
         L.orc_std_icp_iteration.argtypes = [_vp, _vp, C.c_int, C.c_int, _ip, C.c_int, _dp, C.c_double, C.c_double, _dp, _dp]
+        L.orc_std_icp_iteration_theta.argtypes = [_vp, _vp, C.c_int, C.c_int, _ip, C.c_int, _dp, C.c_double, C.c_double, _dp, _dp]
         L.orc_eval_independent.restype = C.c_double
         L.orc_eval_independent.argtypes = [_vp, _vp, C.c_int, C.c_double, C.c_double, C.c_int, _ip, C.c_int, _dp, _dp]
         L.orc_eval_hausdorff.restype = C.c_double
@@ -281,6 +282,15 @@ def std_icp_iteration(model, target, direction, ids, target_points, sigma2, step
     out = np.empty_like(a)
     lib().orc_std_icp_iteration(model.h, target.h, direction, len(ids), ip, len(tp), tpp, sigma2, step_length, ap,
                                 out.ctypes.data_as(_dp))
+    return out
+
+
+def std_icp_iteration_theta(model, target, direction, ids, target_points, sigma2, step_length, theta):
+    ids, ip = _i(np.asarray(ids).reshape(-1)); tp, tpp = _d(np.asarray(target_points).reshape(-1, 3))
+    th, thp = _d(theta)
+    out = np.empty(model.K)
+    lib().orc_std_icp_iteration_theta(model.h, target.h, direction, len(ids), ip, len(tp), tpp, sigma2, step_length, thp,
+                                      out.ctypes.data_as(_dp))
     return out
 
 

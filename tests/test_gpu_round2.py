@@ -270,3 +270,49 @@ def test_step_graph_survives_reallocation_of_model_scratch(ctx, twin31):
     for k in ("component", "accepted", "values", "theta"):
         assert np.array_equal(a1[k], a2[k]), k
     chain.close(); ev.close(); model.close(); tgt.close()
+
+
+def test_handles_are_reference_counted(ctx, twin31):
+    """SURVEY 8b ownership: destroying a model / target / proposal that a live handle still references is an error, not a
+    dangling pointer."""
+    m = twin31
+    model, tgt = _dev(ctx, m)
+    ids = np.arange(62)
+    tp = m["target"][::26][:62]
+    gp = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, 0, True, ids, tp)
+    ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, 0, True, 0.0, 2.0, 0.0, np.arange(124), tp)
+    chain = core.Chain(model, tgt, [dict(kind=0, weight=1.0, proposal=gp)], ev, max_chains=2)
+    lib = ctx.lib
+    assert lib.icp_model_destroy(model.h) == _lib.ERR_INVALID_ARGUMENT and "still referenced" in _lib.last_error(ctx.h)
+    assert lib.icp_target_destroy(tgt.h) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.icp_proposal_destroy(gp.h) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.icp_evaluator_destroy(ev.h) == _lib.ERR_INVALID_ARGUMENT
+    th0 = random_theta(m, np.random.default_rng(0), 2)
+    assert chain.run(th0, 3)["theta"].shape == (3, 2, 41)          # everything is still alive
+    for h, fn in ((chain, lib.icp_chain_destroy), (gp, lib.icp_proposal_destroy), (ev, lib.icp_evaluator_destroy),
+                  (model, lib.icp_model_destroy), (tgt, lib.icp_target_destroy)):
+        assert fn(h.h) == _lib.OK
+        h.h = None
+
+
+def test_std_icp_iteration_with_rigid_transform(ctx, femur):
+    """IcpBasedSurfaceFitting.scala:55-92 with a non-identity currentTrans (:61): correspondences on the transformed instance,
+    posterior of the untransformed model on world-frame targets (:81)."""
+    m = _femur(femur, "gpmm_50")
+    K = 51
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    rng = np.random.default_rng(15)
+    th = random_theta(m, rng, 2, pose=True)
+    ids = rng.integers(0, 1622, 400)
+    tp = synth.near_surface_queries(m["target"], m["target_cells"], 400, sd=0.0)
+    for direction in (0, 1):
+        out = core.std_icp_iteration_theta(model, tgt, direction, ids, tp, 1e-15, 1.0, th)
+        for c in range(2):
+            want = orc.std_icp_iteration_theta(om, ot, direction, ids, tp, 1e-15, 1.0, th[c])
+            np.testing.assert_allclose(out[c], want, rtol=RTOL, atol=1e-7)
+        # identity pose reduces to the original entry point
+        th_id = th.copy(); th_id[:, 1:10] = 0.0
+        np.testing.assert_array_equal(core.std_icp_iteration_theta(model, tgt, direction, ids, tp, 1e-15, 1.0, th_id),
+                                      core.std_icp_iteration(model, tgt, direction, ids, tp, 1e-15, 1.0, th_id[:, 10:]))
+    model.close(); tgt.close()
