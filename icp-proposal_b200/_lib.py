@@ -97,6 +97,11 @@ _SIGS = {
     "icp_gpmm_kernel_matrix": [_h, C.c_int32, _dp, C.c_int32, _dp, C.POINTER(KernelTerm), C.c_int32, _dp],
     "icp_gpmm_eigen_psd": [_h, C.c_int32, _dp, C.c_int32, _dp, _dp],
     "icp_gpmm_nystrom_extend": [_h, C.c_int32, _dp, C.c_int32, _dp, C.POINTER(KernelTerm), C.c_int32, C.c_int32, _dp, _dp, _dp, _dp],
+    "icp_jsonlog_open": [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(C.c_char_p), C.POINTER(_h)],
+    "icp_jsonlog_append": [_h, C.c_int32, C.c_int32, C.c_int32, _ip, _bp, _dp, _dp],
+    "icp_jsonlog_close": [_h],
+    "icp_jsonlog_load": [C.c_char_p, C.c_int32, C.c_int64, _lp, _lp, _bp, _dp, _dp, C.c_char_p, C.c_char_p],
+    "icp_chainlog_sample_indices": [C.c_int64, _bp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _lp, _lp],
     "icp_comm_unique_id": [_h, _bp],
     "icp_comm_init": [_h, C.c_int32, C.c_int32, _bp, C.POINTER(_h)],
     "icp_comm_destroy": [_h],

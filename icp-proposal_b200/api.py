@@ -719,10 +719,11 @@ class SamplingRegistration:
             best.append(ModelFittingParameters.from_vector(out["theta_best"][c], name))
         self.last_run = out
         if jsonName is not None:
-            logger = JSONAcceptRejectLogger(jsonName)
-            logger.append_device_log(names, keys, out["component"][:, 0], out["accepted"][:, 0], out["values"][:, 0], out["theta"][:, 0])
-            logger.writeLog()
-            self.logger = logger
+            # the device log goes to the reference's file format through the library's streaming writer (icp_jsonlog_*)
+            native = core.JsonLog(jsonName, self.model.K, names, keys)
+            native.append(out, chain=0)
+            native.close()
+            self.logger = JSONAcceptRejectLogger(jsonName)
         chain.close(); ev.close()
         return best[0] if n_chains == 1 else best
 

@@ -341,6 +341,56 @@ def posterior_variability(model: Model, thetas, sum_normals=True, theta_ref=None
     return dict(mean=mean, cov=cov, total_variance=tot, normal_variance=nrm)
 
 
+class JsonLog:
+    """Streaming writer of the reference's chain-log file (icp_jsonlog_*; JSONAcceptRejectLogger.scala:93-122)."""
+
+    def __init__(self, path, K, component_names, value_keys=("product", "prior", "distance")):
+        self.lib = _lib.load()
+        names = (C.c_char_p * len(component_names))(*[str(n).encode() for n in component_names])
+        keys = (C.c_char_p * 3)(*[str(k).encode() for k in value_keys])
+        self.h = C.c_void_p()
+        check(self.lib.icp_jsonlog_open(str(path).encode(), int(K), names, len(component_names), keys, C.byref(self.h)))
+
+    def append(self, run, chain=0):
+        """run: the dict Chain.run returned (log arrays [n_steps][C])."""
+        comp = i32(run["component"]); acc = np.ascontiguousarray(run["accepted"], dtype=np.uint8)
+        vals, th = f64(run["values"]), f64(run["theta"])
+        n, c = comp.shape
+        check(self.lib.icp_jsonlog_append(self.h, n, c, int(chain), iptr(comp), acc.ctypes.data_as(_lib._bp), dptr(vals), dptr(th)))
+
+    def close(self):
+        if self.h:
+            self.lib.icp_jsonlog_close(self.h)
+            self.h = None
+
+
+def jsonlog_load(path, K):
+    """icp_jsonlog_load -> dict(index, status, values [n, 3], value_keys, theta [n, K + 10] (NaN rows for rejected records), names)."""
+    lib = _lib.load()
+    n = C.c_int64(0)
+    check(lib.icp_jsonlog_load(str(path).encode(), int(K), 0, C.byref(n), None, None, None, None, None, None))
+    cnt = n.value
+    index = np.zeros(cnt, np.int64); status = np.zeros(cnt, np.uint8); values = np.zeros((cnt, 3)); theta = np.zeros((cnt, K + THETA0))
+    names = C.create_string_buffer(64 * max(cnt, 1)); keys = C.create_string_buffer(64 * 3)
+    check(lib.icp_jsonlog_load(str(path).encode(), int(K), cnt, C.byref(n), index.ctypes.data_as(_lib._lp), status.ctypes.data_as(_lib._bp),
+                               dptr(values), dptr(theta), names, keys))
+    nm = [names.raw[64 * i: 64 * i + 64].split(b"\0")[0].decode() for i in range(cnt)]
+    ks = [keys.raw[64 * i: 64 * i + 64].split(b"\0")[0].decode() for i in range(3)]
+    return dict(index=index, status=status.astype(bool), values=values, value_keys=ks, theta=theta, names=nm)
+
+
+def chainlog_sample_indices(status, take_every_n=50, total=100, burn_in=0):
+    """icp_chainlog_sample_indices: LogHelper.samplesFromLog's indices (closest accepted record at or before each pick)."""
+    lib = _lib.load()
+    st = np.ascontiguousarray(status, dtype=np.uint8)
+    n = C.c_int64(0)
+    check(lib.icp_chainlog_sample_indices(len(st), st.ctypes.data_as(_lib._bp), int(take_every_n), int(total), int(burn_in), 0, C.byref(n), None))
+    out = np.zeros(n.value, np.int64)
+    check(lib.icp_chainlog_sample_indices(len(st), st.ctypes.data_as(_lib._bp), int(take_every_n), int(total), int(burn_in), len(out),
+                                          C.byref(n), out.ctypes.data_as(_lib._lp)))
+    return out
+
+
 class Comm:
     """NCCL communicator of the library (icp_comm_*): end-of-run gather of chain logs and reduction of posterior statistics.
     Rank 0 calls Comm.unique_id(ctx) and ships the 128 bytes to the other ranks through any channel it likes."""

@@ -46,6 +46,7 @@ typedef struct icp_proposal_s *icp_proposal;
 typedef struct icp_evaluator_s *icp_evaluator;
 typedef struct icp_chain_s *icp_chain;
 typedef struct icp_comm_s *icp_comm;
+typedef struct icp_jsonlog_s *icp_jsonlog;
 
 /* ---- (1) context --------------------------------------------------------------------------- */
 int32_t icp_ctx_create(int32_t device, icp_ctx *out);
@@ -296,6 +297,32 @@ int32_t icp_ctx_synchronize(icp_ctx ctx);
 /* device time in milliseconds of the last icp_chain_run* on this chain (CUDA events on the
  * library stream) and the number of kernels it launched */
 int32_t icp_chain_last_run_stats(icp_chain c, double *device_ms, int64_t *kernel_launches);
+
+/* ---- (7b) chain log in the reference's JSON wire format (host functions: no CUDA context needed) ---------------------- */
+/* JSONAcceptRejectLogger (api/sampling/loggers/JSONAcceptRejectLogger.scala:35,93-127) as a streaming writer and a loader.
+ * The reference rewrites the whole file on every writeLog (:112-122), quadratic over a run; icp_jsonlog_append appends the
+ * new records and leaves a valid JSON array after every call. component_names[i] is the generatedBy name of mixture
+ * component i (the log's "name"), value_keys[3] the logvalue keys of icp_chain_io.log_values ("product", "prior" and the
+ * distance evaluator's key, ProductEvaluators.scala:49-53; an empty string omits that entry). */
+int32_t icp_jsonlog_open(const char *path, int32_t K, const char *const *component_names, int32_t n_components,
+                         const char *const *value_keys, icp_jsonlog *out);
+/* appends chain `chain` of a run's HOST log arrays ([n_steps][C] records as icp_chain_run returned them): accepted records
+ * carry rigid[9] and coeff[K], rejected ones the current state's log-values with empty arrays (:101-105); NaN / infinite
+ * values are written as null like spray-json does */
+int32_t icp_jsonlog_append(icp_jsonlog log, int32_t n_steps, int32_t C, int32_t chain, const int32_t *log_component,
+                           const uint8_t *log_accepted, const double *log_values, const double *log_theta);
+int32_t icp_jsonlog_close(icp_jsonlog log);
+/* loadLog (:124-127), also for files the reference wrote. capacity == 0: only *n_records is set. Otherwise arrays of
+ * `capacity` records (any may be NULL): index, status, values [n][3] in the order of value_keys (3 x 64 bytes out:
+ * "product", "prior", the third key found), theta [n][K+10] = sampleToModelParameters (:139-146; scale 1; NaN for rejected
+ * records, whose arrays are empty), names [n][64]. */
+int32_t icp_jsonlog_load(const char *path, int32_t K, int64_t capacity, int64_t *n_records, int64_t *index, uint8_t *status,
+                         double *values, double *theta, char *names, char *value_keys);
+/* LogHelper.samplesFromLog (apps/util/LogHelper.scala:27-37) and the loop of ReplayFittingFromLog.scala:53-66: log indices
+ * burn_in, burn_in + take_every_n, ... below min(n_records, total), each replaced by the closest accepted record at or
+ * before it. indices == NULL: only *n_out. Feed theta[indices] to icp_reconstruct / icp_posterior_variability. */
+int32_t icp_chainlog_sample_indices(int64_t n_records, const uint8_t *status, int32_t take_every_n, int64_t total,
+                                    int64_t burn_in, int64_t capacity, int64_t *n_out, int64_t *indices);
 
 /* ---- (8) multi-GPU: one process per GPU, NCCL over NVLink ---------------------------------------------- */
 /* Chains / random-init restarts / targets are independent (apps/femur/RunMHRandomInitComparison.scala:66-86,

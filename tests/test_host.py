@@ -159,6 +159,56 @@ def test_json_logger_format_roundtrip(tmp_path):
     assert lg2.numOfAccepted == 1 and lg2.numOfRejected == 1 and lg2.logStatus[1].logvalue == {"product": 3.0, "prior": 4.0, "distance": 5.0}
 
 
+def test_native_streaming_json_log_roundtrip(tmp_path):
+    """icp_jsonlog_*: the C-boundary writer appends (valid JSON after every append, O(new records) work), writes the reference's
+    record layout (JSONAcceptRejectLogger.scala:35,93-106) and its loader reads both its own files and spray-json-style ones."""
+    from icp_proposal_b200 import core
+    K, C, n = 4, 2, 7
+    rng = np.random.default_rng(11)
+    run = dict(component=rng.integers(0, 2, (n, C)).astype(np.int32), accepted=rng.random((n, C)) < 0.6,
+               values=rng.normal(size=(n, C, 3)), theta=rng.normal(size=(n, C, K + 10)))
+    run["accepted"][0, 1] = True
+    run["values"][2, 1, 2] = np.nan; run["values"][3, 1, 0] = -np.inf            # spray-json writes null for these
+    path = str(tmp_path / "chain.json")
+    lg = core.JsonLog(path, K, ["IcpProposal-ModelSampling-0.1Step", "RandomShape-0.1"], ("product", "prior", "collective_distance"))
+    assert json.load(open(path)) == []
+    first = {k: v[:3] for k, v in run.items()}
+    lg.append(first, chain=1)
+    size1 = os.path.getsize(path)
+    assert len(json.load(open(path))) == 3                                         # valid JSON between appends
+    lg.append({k: v[3:] for k, v in run.items()}, chain=1)
+    lg.close()
+    raw = json.load(open(path))
+    assert len(raw) == n and os.path.getsize(path) > size1
+    assert list(raw[0].keys()) == ["index", "name", "logvalue", "status", "rigid", "coeff", "datetime"]
+    for s_, r in enumerate(raw):
+        ok = bool(run["accepted"][s_, 1])
+        assert r["index"] == s_ and r["status"] is ok
+        assert r["name"] == ["IcpProposal-ModelSampling-0.1Step", "RandomShape-0.1"][run["component"][s_, 1]]
+        assert r["rigid"] == (run["theta"][s_, 1, 1:10].tolist() if ok else []) and r["coeff"] == (run["theta"][s_, 1, 10:].tolist() if ok else [])
+        for k, key in enumerate(("product", "prior", "collective_distance")):
+            v = run["values"][s_, 1, k]
+            assert r["logvalue"][key] == (v if np.isfinite(v) else None)
+    back = core.jsonlog_load(path, K)
+    assert back["value_keys"] == ["product", "prior", "collective_distance"] and np.array_equal(back["status"], run["accepted"][:, 1])
+    np.testing.assert_array_equal(np.nan_to_num(back["values"], nan=7.0, neginf=7.0), np.where(np.isfinite(run["values"][:, 1]), run["values"][:, 1], 7.0))
+    acc = run["accepted"][:, 1]
+    np.testing.assert_array_equal(back["theta"][acc, 1:], run["theta"][acc, 1, 1:])
+    assert np.all(back["theta"][acc, 0] == 1.0) and np.isnan(back["theta"][~acc]).all()
+    # a file as the Python mirror (spray-json layout) writes it loads the same way
+    pl = api.JSONAcceptRejectLogger(str(tmp_path / "py.json"))
+    pl.append_device_log(["a", "b"], ["product", "prior", "distance"], run["component"][:, 0], run["accepted"][:, 0], run["values"][:, 0], run["theta"][:, 0])
+    pl.writeLog()
+    b2 = core.jsonlog_load(str(tmp_path / "py.json"), K)
+    assert np.array_equal(b2["status"], run["accepted"][:, 0]) and b2["names"][0] == ["a", "b"][run["component"][0, 0]]
+    # LogHelper.samplesFromLog indices (apps/util/LogHelper.scala:27-37)
+    st = np.array([1, 0, 0, 1, 0, 1, 0, 0, 0, 1], bool)
+    assert core.chainlog_sample_indices(st, take_every_n=2, total=100, burn_in=1).tolist() == [0, 3, 5, 5, 9]
+    assert core.chainlog_sample_indices(st, take_every_n=3, total=7, burn_in=0).tolist() == [0, 3, 5]
+    with pytest.raises(_lib.IcpCudaError):
+        core.chainlog_sample_indices(np.array([0, 0, 1], bool), take_every_n=1)    # no accepted record at or before index 0
+
+
 def test_log_helper_samples_from_log_matches_oracle():
     """LogHelper.samplesFromLog (apps/util/LogHelper.scala:27-37): the host mirror against the oracle's index walk."""
     from oracle import np_oracle as npo
