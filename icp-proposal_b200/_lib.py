@@ -15,6 +15,7 @@ OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_EMPTY_SET, ERR_NOT_POSITIVE_DEFINITE, ERR_NAN = -1, -2, -3, -4, -5, -6
 CHAIN_EMPTY_SET, CHAIN_NOT_POSITIVE_DEFINITE, CHAIN_NAN_TRANSITION, CHAIN_NAN_VALUE = 1, 2, 4, 8
 FACTOR_CHOLESKY, FACTOR_SVD = 0, 1
+RANK_UPDATE_FP64, RANK_UPDATE_INT8 = 0, 1
 MODEL_SAMPLING, TARGET_SAMPLING = 0, 1
 EVAL_ACCEPT_ALL, EVAL_INDEPENDENT, EVAL_HAUSDORFF, EVAL_COLLECTIVE = 0, 1, 2, 3
 MODEL_TO_TARGET, TARGET_TO_MODEL, SYMMETRIC = 0, 1, 2
@@ -36,7 +37,7 @@ class IcpCudaError(RuntimeError):
 
 class ProposalParams(C.Structure):
     _fields_ = [("step_length", C.c_double), ("tangential_noise", C.c_double), ("noise_along_normal", C.c_double),
-                ("direction", C.c_int32), ("boundary_aware", C.c_int32), ("factor", C.c_int32), ("reserved", C.c_int32)]
+                ("direction", C.c_int32), ("boundary_aware", C.c_int32), ("factor", C.c_int32), ("rank_update", C.c_int32)]
 
 
 class EvaluatorParams(C.Structure):
@@ -120,6 +121,7 @@ _SIGS = {
     "icp_chain_profile": [_h, C.c_int32, C.c_int32, _dp, C.c_uint64, _dp, _lp],
     "icp_debug_time_closest_point": [_h, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _dp],
     "icp_debug_l2_bandwidth": [_h, C.c_int64, _dp],
+    "icp_debug_i8_gram": [_h, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _dp],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["icp_stage_name"])
 

@@ -175,12 +175,13 @@ class IcpProposal:
     """Device side of NonRigidIcpProposal (api/sampling/proposals/NonRigidIcpProposal.scala)."""
 
     def __init__(self, model: Model, target: Target, step_length, tangential_noise, noise_along_normal, direction,
-                 boundary_aware, model_point_ids, target_points, factor=_lib.FACTOR_CHOLESKY):
+                 boundary_aware, model_point_ids, target_points, factor=_lib.FACTOR_CHOLESKY,
+                 rank_update=_lib.RANK_UPDATE_FP64):
         self.model, self.target, self.lib, self.ctx = model, target, model.lib, model.ctx
         self.ids = i32(np.asarray(model_point_ids).reshape(-1))
         self.tp = f64(np.asarray(target_points, dtype=np.float64).reshape(-1, 3))
         self.params = _lib.ProposalParams(step_length, tangential_noise, noise_along_normal, int(direction), int(boundary_aware),
-                                          int(factor), 0)
+                                          int(factor), int(rank_update))
         self.h = C.c_void_p()
         check(self.lib.icp_proposal_create(model.h, target.h, C.byref(self.params), iptr(self.ids), len(self.ids),
                                            dptr(self.tp), len(self.tp), C.byref(self.h)), self.ctx.h)

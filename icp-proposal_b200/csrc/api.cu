@@ -226,6 +226,13 @@ extern "C" int32_t icp_model_create(icp_ctx ctx, int32_t N, int32_t T, int32_t K
         dU.upload(basis, n3 * K, s);
         dvar.upload(variance, K, s);
         m->h_var.assign(variance, variance + K);
+        m->h_col_norm.assign(m->Kp, 0.0);
+        for (int v = 0; v < N; v++)
+            for (int j = 0; j < K; j++) {
+                double s2 = 0.0;
+                for (int e = 0; e < 3; e++) { const double u = basis[((size_t)3 * v + e) * K + j]; s2 += u * u; }
+                m->h_col_norm[j] = std::max(m->h_col_norm[j], std::sqrt(s2 * variance[j]));
+            }
         {
             std::vector<double> sv(Kp, 1.0);
             for (int j = 0; j < K; j++) sv[j] = std::sqrt(variance[j]);
@@ -629,6 +636,7 @@ extern "C" int32_t icp_proposal_create(icp_model m, icp_target t, const icp_prop
         ICP_REQUIRE(params->step_length != 0.0 && std::isfinite(params->step_length), "step_length must be finite and non-zero");
         ICP_REQUIRE(params->tangential_noise > 0 && params->noise_along_normal > 0, "noise std-devs must be > 0");
         ICP_REQUIRE(params->factor == ICP_FACTOR_CHOLESKY || params->factor == ICP_FACTOR_SVD, "bad covariance factor");
+        ICP_REQUIRE(params->rank_update == ICP_RANK_UPDATE_FP64 || params->rank_update == ICP_RANK_UPDATE_INT8, "bad rank_update mode");
         if (params->factor == ICP_FACTOR_SVD)
             for (double v : m->h_var) ICP_REQUIRE(v > 0.0, "ICP_FACTOR_SVD needs strictly positive variances");
         check_ids(m->N, model_point_ids, n_ids);
@@ -647,6 +655,17 @@ extern "C" int32_t icp_proposal_create(icp_model m, icp_target t, const icp_prop
                 launch_gram_rows(m->dev(), n_ids, p->ids.p, p->Gs.p, _ctx->stream);
                 p->gram_fast = true;
             }
+        }
+        {   // column scales of the INT8 rank update (tc_i8.cu): |A[r][j]| <= |frame row| * max_v |Q_v[:, j]|, doubled so that
+            // the scaled entries stay inside (-1/2, 1/2) with the base-255 margin
+            const double margin = 2.0 * (255.0 / 254.0) * (1.0 + 1e-6);
+            const double fmax = std::max(1.0 / params->noise_along_normal, 1.0 / params->tangential_noise);
+            const double kappa_row = std::sqrt(std::max(0.0, 1.0 - (params->noise_along_normal * params->noise_along_normal) /
+                                                                       (params->tangential_noise * params->tangential_noise))) / params->noise_along_normal;
+            std::vector<double> a(m->Kp), b(m->Kp);
+            for (int j = 0; j < m->Kp; j++) { a[j] = margin * fmax * m->h_col_norm[j]; b[j] = margin * kappa_row * m->h_col_norm[j]; }
+            p->col_scale.upload(a.data(), a.size(), _ctx->stream);
+            p->col_scale_gram.upload(b.data(), b.size(), _ctx->stream);
         }
         sync_stream(_ctx);
         m->refs++; t->refs++;
@@ -757,6 +776,17 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
     const GramFast *gfp = (p->gram_fast && all_kept) ? &gf : nullptr;
     w.Mp.ensure((size_t)C * (Kp / 8) * (Kp / 8 + 1) / 2 * 64);
     bool quad_done = false;
+    // ICPCUDA_RANK_UPDATE=int8: the rank update on the tcgen05 INT8 tensor cores (split-integer emulation of the FP64 product,
+    // 1e-8 on the posterior mean; tc_i8.cu) instead of the FP64 tensor pipe. Not for grouped observations (their rows are
+    // scaled by sqrt(multiplicity), outside the column bound).
+    static const std::string ru_env = getenv("ICPCUDA_RANK_UPDATE") ? getenv("ICPCUDA_RANK_UPDATE") : "";
+    const bool want_i8 = ru_env == "int8" || (ru_env != "fp64" && p->prm.rank_update == ICP_RANK_UPDATE_INT8);
+    const bool grouped = tsamp && 2 * (long long)n >= m->N;
+    if (want_i8 && !grouped && p->col_scale.p &&
+        launch_rank_update_i8(md, C, od, gfp, gfp ? p->col_scale_gram.p : p->col_scale.p, w.Mp.p, w.b.p, s)) {
+        launch_cholesky_packed(C, Kp, w.Mp.p, w.b.p, w.want_M ? w.M.p : nullptr, d_L, d_mu, d_out_slot, w.status.p, qa, s);
+        quad_done = qa != nullptr;
+    } else
     if (!launch_posterior_fused(md, C, od, gfp, w.want_M ? w.M.p : nullptr, d_L, d_mu, d_out_slot, w.status.p, w.Mp.p, w.b.p, s, qa,
                                 &quad_done)) {
         launch_posterior_build(md, C, od, w.M.p, w.b.p, s, gfp);
@@ -965,7 +995,7 @@ static int32_t std_icp_iteration_impl(icp_model m, icp_target t, int32_t directi
     icp_proposal_s tmp;
     tmp.model = m; tmp.target = t;
     tmp.prm.step_length = step_length; tmp.prm.tangential_noise = 1; tmp.prm.noise_along_normal = 1;
-    tmp.prm.direction = direction; tmp.prm.boundary_aware = 0; tmp.prm.factor = ICP_FACTOR_CHOLESKY;
+    tmp.prm.direction = direction; tmp.prm.boundary_aware = 0; tmp.prm.factor = ICP_FACTOR_CHOLESKY; tmp.prm.rank_update = ICP_RANK_UPDATE_FP64;
     tmp.n_ids = n_ids; tmp.n_tp = n_tp;
     tmp.ids.upload(model_point_ids, n_ids, s);
     tmp.tp.upload(target_points, (size_t)3 * n_tp, s);

@@ -1648,6 +1648,16 @@ static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M,
     }
 }
 
+void launch_cholesky_packed(int C, int Kp, const double *d_Mp, const double *d_b, double *d_M_or_null, double *d_L, double *d_mu,
+                            const int *d_out_slot, int *d_status, const QuadArgs *qa, cudaStream_t s) {
+    ProfScope _ps(ST_CHOLESKY, s);
+    const int NB = Kp / 8, total = NB * (NB + 1) / 2;
+    size_t smem_c = sizeof(double) * ((size_t)total * 64 + 4 * Kp);
+    ICP_CUDA(cudaFuncSetAttribute(k_cholesky_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    k_cholesky_packed<<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, d_M_or_null, d_L, d_mu, d_out_slot, d_status, qa ? *qa : QuadArgs{});
+    ICP_CUDA(cudaGetLastError());
+}
+
 // posterior build + Cholesky + solve; returns false when the shape is outside the DMMA kernels' range (the caller then
 // runs launch_posterior_build + launch_cholesky_solve). Default: two launches - the rank update writes M block-packed
 // (d_Mp, C x NB (NB + 1) / 2 x 64 doubles) and b (d_b), k_cholesky_packed factorises at four chains per SM.

@@ -116,6 +116,15 @@ int32_t icp_model_boundary_flags(icp_model m, uint8_t *flags /* N */);
  *                        eigen-decomposition per posterior (batched one-sided Jacobi on the device); needs variance > 0. */
 #define ICP_FACTOR_CHOLESKY 0
 #define ICP_FACTOR_SVD 1
+/* Arithmetic of the posterior's rank update M = I + sum Q_i^T Sigma_i^-1 Q_i (:152), the dominant kernel of an MH step:
+ *   ICP_RANK_UPDATE_FP64  FP64 tensor pipe (mma.sync m8n8k4 f64): M to ~1e-15, posterior mean to ~1e-12 (default)
+ *   ICP_RANK_UPDATE_INT8  5th-generation tensor cores (tcgen05.mma kind::i8, INT32 accumulators in TMEM) through a
+ *                         split-integer (Ozaki) emulation of the FP64 product with four base-255 digits: M to 2e-9,
+ *                         posterior mean to ~1e-8 relative - inside the 1e-5 contract of BASELINE.json, several times
+ *                         faster. Ranks up to 112; other shapes fall back to FP64.
+ * The environment variable ICPCUDA_RANK_UPDATE=int8|fp64 overrides the field for every proposal of the process. */
+#define ICP_RANK_UPDATE_FP64 0
+#define ICP_RANK_UPDATE_INT8 1
 
 typedef struct {
     double step_length;         /* stepLength */
@@ -124,7 +133,7 @@ typedef struct {
     int32_t direction;          /* ICP_MODEL_SAMPLING | ICP_TARGET_SAMPLING */
     int32_t boundary_aware;     /* boundaryAware */
     int32_t factor;             /* ICP_FACTOR_CHOLESKY | ICP_FACTOR_SVD */
-    int32_t reserved;           /* 0 */
+    int32_t rank_update;        /* ICP_RANK_UPDATE_FP64 | ICP_RANK_UPDATE_INT8 */
 } icp_proposal_params;
 
 /* model_point_ids: decimatedModel.referenceMesh.pointSet.pointIds (:94; they index the FULL mesh,

@@ -34,6 +34,12 @@ int32_t icp_debug_time_closest_point(icp_target t, int64_t nq, const double *q_d
  * bypassed, 16-byte loads): the roofline denominator of the cache-resident closest-point traversal */
 int32_t icp_debug_l2_bandwidth(icp_ctx ctx, int64_t working_set_bytes, double *gbps);
 
+/* tcgen05 INT8 self-test / micro-benchmark (csrc/tc_i8.cu): D (128 x 128 row-major int32, columns < 112 valid) = A^T A of an
+ * int8 matrix A (rows x 128 row-major, rows a multiple of 32) through tcgen05.mma kind::i8 with the accumulator in TMEM; then
+ * `ctas` CTAs repeat the product `iters` times and *ms is the device time of that launch (MMA rate of the rank update's
+ * tile shape M = 128, N = 112, K = 32). */
+int32_t icp_debug_i8_gram(icp_ctx ctx, int32_t rows, const int8_t *A, int32_t *D, int32_t iters, int32_t ctas, double *ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -316,3 +316,73 @@ def test_std_icp_iteration_with_rigid_transform(ctx, femur):
         np.testing.assert_array_equal(core.std_icp_iteration_theta(model, tgt, direction, ids, tp, 1e-15, 1.0, th_id),
                                       core.std_icp_iteration(model, tgt, direction, ids, tp, 1e-15, 1.0, th_id[:, 10:]))
     model.close(); tgt.close()
+
+
+@pytest.mark.parametrize("direction", [_lib.MODEL_SAMPLING, _lib.TARGET_SAMPLING])
+@pytest.mark.parametrize("fixture", ["twin31", "femur100", "open_twin"])
+def test_int8_tensor_core_rank_update(ctx, request, femur, direction, fixture):
+    """ICP_RANK_UPDATE_INT8: the posterior's rank update on tcgen05 INT8 tensor cores (split-integer emulation of the FP64
+    product) against the oracle at the contract tolerance (1e-5 relative on posterior means and transition densities), and
+    against the FP64 path of the library."""
+    m = _femur(femur, "gpmm_100") if fixture == "femur100" else request.getfixturevalue(fixture)
+    K = len(m["variance"])
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    rng = np.random.default_rng(23)
+    C = 5
+    th = random_theta(m, rng, C, pose=(fixture != "femur100"))
+    if fixture == "open_twin":
+        ids, tp = np.arange(0, len(m["ref"]), 5), m["target"][::4]         # boundary filtering drops observations
+    else:
+        ids = np.arange(2 * K)
+        tp = m["target"][:: max(1, len(m["target"]) // (2 * K))][: 2 * K] + rng.normal(0, 0.1, (2 * K, 3))
+    gi = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, direction, True, ids, tp, rank_update=_lib.RANK_UPDATE_INT8)
+    gf = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, direction, True, ids, tp)
+    op = orc.IcpProposal(om, ot, 0.1, 10.0, 5.0, direction, True, ids, tp)
+    mu, M, n = gi.posterior(th)
+    mu64, M64, n64 = gf.posterior(th)
+    assert np.array_equal(n, n64)
+    scale = np.abs(M64).max(axis=(1, 2), keepdims=True)
+    assert np.abs(M - M64).max() / scale.max() < 2e-8 and np.abs(M - M64).max() > 0.0      # a different arithmetic, 2e-9 typical
+    z = rng.normal(size=(C, K))
+    prop = gi.propose(th, z)
+    lt = gi.log_transition(th, prop)
+    for c in range(C):
+        po = op.posterior(th[c])
+        assert n[c] == po["n"]
+        np.testing.assert_allclose(M[c], po["M"], rtol=0, atol=2e-8 * np.abs(po["M"]).max())
+        np.testing.assert_allclose(mu[c], po["mu"], rtol=RTOL, atol=RTOL * np.abs(po["mu"]).max())
+        assert np.abs(mu[c] - po["mu"]).max() <= 1e-6 * np.abs(po["mu"]).max()        # measured ~1e-8
+        np.testing.assert_allclose(prop[c], op.propose(th[c], z[c], closed_form=True), rtol=RTOL, atol=1e-7)
+        np.testing.assert_allclose(lt[c], op.log_transition(th[c], prop[c], closed_form=True), rtol=RTOL)
+    gi.close(); gf.close(); model.close(); tgt.close()
+
+
+def test_int8_rank_update_chain_matches_oracle(ctx, femur):
+    """Config 1 (femur GPMM-100) with both ICP proposals on the INT8 tensor-core path: the fused runner against the oracle chain."""
+    m = _femur(femur, "gpmm_100")
+    K = 101
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    ids, eids = np.arange(2 * K), np.arange(4 * K)
+    tp = m["target"][:: len(m["target"]) // (2 * K)][: 2 * K]
+    mk = lambda d: core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, d, True, ids, tp, rank_update=_lib.RANK_UPDATE_INT8)
+    mo = lambda d: orc.IcpProposal(om, ot, 0.1, 10.0, 5.0, d, True, ids, tp)
+    comps = [dict(kind=0, weight=0.45, proposal=mk(1)), dict(kind=0, weight=0.45, proposal=mk(0)), dict(kind=1, weight=0.1, sd=0.1)]
+    comps_o = [dict(kind=0, weight=0.45, icp=mo(1)), dict(kind=0, weight=0.45, icp=mo(0)), dict(kind=1, weight=0.1, sd=0.1)]
+    ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, 0, True, 0.0, 2.0, 0.0, eids, tp)
+    chain = core.Chain(model, tgt, comps, ev, max_chains=4)
+    rng = np.random.default_rng(77)
+    n, C = 40, 3
+    th0 = np.stack([model.theta()] + [model.theta(rng.normal(0, 0.3, K)) for _ in range(C - 1)])
+    u_comp, u_acc, z = rng.random((n, C)), rng.random((n, C)), rng.normal(size=(n, C, K))
+    got = chain.run(th0, n, u_comp=u_comp, z=z, u_acc=u_acc)
+    for c in range(C):
+        want = orc.chain_run(om, ot, comps_o, True, orc.EVAL_INDEPENDENT, 0, (0.0, 2.0), eids, tp, th0[c], n, u_comp[:, c], z[:, c],
+                             u_acc[:, c], closed_form=True)
+        assert np.array_equal(got["component"][:, c], want["comp"])
+        assert np.array_equal(got["accepted"][:, c], want["accepted"])
+        np.testing.assert_allclose(got["values"][:, c], want["logv"], rtol=RTOL)
+        np.testing.assert_allclose(got["theta"][:, c], want["theta"], rtol=0, atol=1e-5)
+    assert np.all(got["status"] == 0)
+    chain.close(); ev.close(); model.close(); tgt.close()
