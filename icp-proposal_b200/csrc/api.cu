@@ -242,6 +242,9 @@ extern "C" int32_t icp_model_create(icp_ctx ctx, int32_t N, int32_t T, int32_t K
         m->Q.alloc(n3 * Kp);
         m->QT.alloc(n3 * Kp);
         launch_scale_basis((int)n3, K, Kp, dU.p, dvar.p, m->Q.p, m->QT.p, s);
+        m->col_norm.upload(m->h_col_norm.data(), m->h_col_norm.size(), s);
+        m->Qhat.alloc(n3 * Kp);
+        launch_unit_basis((int)n3, Kp, m->Q.p, m->col_norm.p, m->Qhat.p, s);
         // S = (G/eps + I)^-1 G/eps, eps = 1e-5 (model.coefficients): G on the device,
         // the one-off K x K solve on the host
         m->S.alloc((size_t)Kp * Kp);
@@ -654,18 +657,9 @@ extern "C" int32_t icp_proposal_create(icp_model m, icp_target t, const icp_prop
                 p->Gs.alloc((size_t)m->Kp * m->Kp);
                 launch_gram_rows(m->dev(), n_ids, p->ids.p, p->Gs.p, _ctx->stream);
                 p->gram_fast = true;
+                p->Qsub.alloc((size_t)n_ids * (3 * m->Kp + 2));
+                launch_pack_obs_rows(n_ids, m->Kp, p->ids.p, m->Qhat.p, p->Qsub.p, _ctx->stream);
             }
-        }
-        {   // column scales of the INT8 rank update (tc_i8.cu): |A[r][j]| <= |frame row| * max_v |Q_v[:, j]|, doubled so that
-            // the scaled entries stay inside (-1/2, 1/2) with the base-255 margin
-            const double margin = 2.0 * (255.0 / 254.0) * (1.0 + 1e-6);
-            const double fmax = std::max(1.0 / params->noise_along_normal, 1.0 / params->tangential_noise);
-            const double kappa_row = std::sqrt(std::max(0.0, 1.0 - (params->noise_along_normal * params->noise_along_normal) /
-                                                                       (params->tangential_noise * params->tangential_noise))) / params->noise_along_normal;
-            std::vector<double> a(m->Kp), b(m->Kp);
-            for (int j = 0; j < m->Kp; j++) { a[j] = margin * fmax * m->h_col_norm[j]; b[j] = margin * kappa_row * m->h_col_norm[j]; }
-            p->col_scale.upload(a.data(), a.size(), _ctx->stream);
-            p->col_scale_gram.upload(b.data(), b.size(), _ctx->stream);
         }
         sync_stream(_ctx);
         m->refs++; t->refs++;
@@ -782,8 +776,20 @@ void posterior_pipeline(icp_proposal p, int C, const double *d_theta, const doub
     static const std::string ru_env = getenv("ICPCUDA_RANK_UPDATE") ? getenv("ICPCUDA_RANK_UPDATE") : "";
     const bool want_i8 = ru_env == "int8" || (ru_env != "fp64" && p->prm.rank_update == ICP_RANK_UPDATE_INT8);
     const bool grouped = tsamp && 2 * (long long)n >= m->N;
-    if (want_i8 && !grouped && p->col_scale.p &&
-        launch_rank_update_i8(md, C, od, gfp, gfp ? p->col_scale_gram.p : p->col_scale.p, w.Mp.p, w.b.p, s)) {
+    I8Scale sc{0.0, 0.0, 0.0};
+    if (want_i8 && !grouped) {
+        // whitened rows |F_d . Qhat_v[:, j]| <= max(1 / sd_n, 1 / sd_t) resp. sqrt(kappa) (constant-Gram rows): scaled to 2^30
+        const double top = 1073741824.0 * (1.0 - 1e-6);
+        if (gfp) {
+            const double kr = gf.row_scale / p->prm.noise_along_normal;
+            if (kr > 0.0) { const double fs = top / kr; sc = I8Scale{gf.row_scale * fs, 16777216.0 / (fs * fs), 1.0}; }
+        } else {
+            const double fs = top / std::max(1.0 / p->prm.noise_along_normal, 1.0 / p->prm.tangential_noise);
+            sc = I8Scale{fs, 16777216.0 / (fs * fs), 1.0 / fs};
+        }
+    }
+    if (want_i8 && !grouped &&
+        launch_rank_update_i8(md, C, od, gfp, I8Model{m->Qhat.p, m->col_norm.p, p->Qsub.p}, sc, w.Mp.p, w.b.p, m->ctx->sm_count, s)) {
         launch_cholesky_packed(C, Kp, w.Mp.p, w.b.p, w.want_M ? w.M.p : nullptr, d_L, d_mu, d_out_slot, w.status.p, qa, s);
         quad_done = qa != nullptr;
     } else

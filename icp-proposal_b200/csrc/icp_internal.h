@@ -253,10 +253,16 @@ struct QuadArgs {
 bool launch_posterior_fused(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, double *d_M_or_null, double *d_L,
                             double *d_mu, const int *d_out_slot, int *d_status, double *d_Mp, double *d_b, cudaStream_t s,
                             const QuadArgs *qa = nullptr, bool *quad_done = nullptr);
-// rank update on the INT8 tensor cores (tc_i8.cu): block-packed M and b like the DMMA rank update; d_col_scale [Kp] is the
-// proposal's column scale s_j. false: shape outside the kernel's domain, nothing launched
-bool launch_rank_update_i8(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, const double *d_col_scale,
-                           double *d_Mp, double *d_b, cudaStream_t s);
+// rank update on the INT8 tensor cores (tc_i8.cu): block-packed M and b like the DMMA rank update.
+// I8Model: the basis with every column divided by its bound (max over the vertices of |Q_v[:, j]|) and the bounds;
+// I8Scale: frame multiplier that brings the whitened rows into |x| <= 2^30 and the factors that undo it.
+// false: shape outside the kernel's domain, nothing launched
+struct I8Model { const double *Qhat, *colnorm, *Qsub; };   // Qsub (nullable): the proposal's rows packed by launch_pack_obs_rows
+struct I8Scale { double fmul, w2, bscale; };
+bool launch_rank_update_i8(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, const I8Model &im, const I8Scale &sc,
+                           double *d_Mp, double *d_b, int n_sm, cudaStream_t s);
+void launch_unit_basis(int rows, int Kp, const double *d_Q, const double *d_colnorm, double *d_Qhat, cudaStream_t s);
+void launch_pack_obs_rows(int n, int Kp, const int *d_ids, const double *d_Qhat, double *d_Qsub /* [n][3 Kp + 2] */, cudaStream_t s);
 // k_cholesky_packed on a block-packed M (the second half of launch_posterior_fused's default path)
 void launch_cholesky_packed(int C, int Kp, const double *d_Mp, const double *d_b, double *d_M_or_null, double *d_L, double *d_mu,
                             const int *d_out_slot, int *d_status, const QuadArgs *qa, cudaStream_t s);
@@ -328,6 +334,7 @@ struct icp_model_s {
     icp::DevBuf<double> QT;           // Kp x 3N
     icp::DevBuf<double> S;            // Kp x Kp, Appendix A5 constant (identity on the padding)
     icp::DevBuf<double> sqrt_var;     // Kp: sqrt(lambda) (1 on the padding)
+    icp::DevBuf<double> Qhat, col_norm;  // INT8 rank update (tc_i8.cu): Q with unit column bounds (3N x Kp), the bounds (Kp)
     std::vector<double> h_col_norm;   // Kp: max over the vertices of |Q_v[:, j]|_2 (column bound of the INT8 rank update)
     std::vector<double> h_var;        // K
     icp::DevBuf<int> tris;            // T x 3
@@ -400,7 +407,7 @@ struct icp_proposal_s {
     icp::DevBuf<double> tp;   // n_tp x 3
     icp::DevBuf<int> qperm;   // processing order of the model points (Morton order of their reference positions)
     icp::DevBuf<double> Gs;   // Kp x Kp: sum of Q_i^T Q_i over the model points (constant-Gram fast path), empty if unused
-    icp::DevBuf<double> col_scale, col_scale_gram;   // Kp: column scales of the INT8 rank update (general rows / constant-Gram rows)
+    icp::DevBuf<double> Qsub; // [n_ids][3 Kp + 2]: the model points' unit-bound basis rows in slot order (INT8 rank update of the constant-Gram path)
     bool gram_fast = false;
     // posterior cache (the reference's Memoize(icpPosterior, 20)): theta bytes -> slot
     int cache_slots = 0;

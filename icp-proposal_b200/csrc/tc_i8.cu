@@ -88,6 +88,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, int (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // byte offset of the 16-byte line (row r, column chunk ch) inside a digit image: blocks of 32 rows (one MMA K step) of
 // 4 KB, inside a block [row group of 8][chunk][row in group][16 bytes]  ->  SBO = 128, LBO = 1024
 constexpr int kI8Cols = 128;          // columns of a digit image (MMA M; the first 112 are the MMA N)
@@ -182,250 +192,533 @@ extern "C" int32_t icp_debug_i8_gram(icp_ctx ctx, int32_t rows, const int8_t *A,
 
 // =======================================================================================================================
 // Rank update of the ICP posterior on the INT8 tensor cores:  Mp = block-packed lower triangle of I + A^T A (+ Gs term),
-// b = A^T y~.  One CTA per chain-posterior, 512 threads, one CTA per SM (the four INT32 accumulators take all 512 TMEM
-// columns). Stage = 32 observations (RPO rows each): thread (observation slot, 16-column chunk, half) gathers its 8 columns
-// of the observation's three basis rows, whitens them in FP64 (the same arithmetic as the DMMA kernel's producers), adds
-// its share of b, cuts every value into four base-255 digits and stores them into the stage's four digit images. One thread
-// then issues the ten digit-pair MMAs per 32-row K step; tcgen05.commit releases the stage through an mbarrier, so the
-// producers fill the other stage while the tensor core works. The epilogue reads the accumulators back with tcgen05.ld,
-// recombines them in FP64 (Horner in 1/255) and writes the blocks k_cholesky_packed consumes.
+// b = A^T y~.   Persistent, warp-specialised CTAs (one per SM: the four INT32 accumulators take all 512 TMEM columns),
+// each walking its share of the chain-posteriors:
+//
+//   warp 14  "gather": per raw stage of 16 observations one TMA bulk copy (cp.async.bulk, mbarrier complete_tx) of the
+//            observation's three unit-scaled basis rows (3 Kp doubles, contiguous in Qhat) into a ring in shared memory, and
+//            the observation's whitening frame + right-hand side with cp.async (completion signalled on the same mbarrier)
+//   warps 0..13  "converters": thread = (observation, 8 columns): the 3 x 3 whitening in FP64 straight into fixed point,
+//            x = rn(f . Qhat * 2^30 / bound) (|x| <= 2^30), the four balanced base-256 digits of x are the bytes of
+//            (x + 0x00808080) ^ 0x00808080, byte-transposed with PRMT into the four digit images of a 32-row MMA K block;
+//            b accumulates in FP64 on the way
+//   warp 15  "mma": one thread issues, per K block, the ten digit-pair products D_k^T D_l, k + l <= 3, into the accumulator
+//            of weight 256^-(k+l) (tcgen05.mma kind::i8, both operands the same MN-major images), tcgen05.commit frees the
+//            digit buffer for the converters
+//   epilogue (all but the gather warp, which is already prefetching the next chain): tcgen05.ld, Horner in FP64 (exact:
+//            |sum| < 2^53), scale by the column bounds, add I (+ the constant Gram term), write the 8 x 8 blocks
+//            k_cholesky_packed consumes.
+// Rows of A may be summed in any order (integer accumulation is exact), so K block d of a step holds frame row d of the
+// step's 32 observations.
 // =======================================================================================================================
 namespace icp {
 
 constexpr int kRuThreads = 512;
-constexpr int kRuObs = 32;                 // observations per stage
-constexpr double kRuBase = 255.0;
+constexpr int kRuGatherWarp = 12, kRuMmaWarp = 15;    // the gather warp skips the epilogue: it sits in TMEM lane quarter 0, which has the fewest blocks
+constexpr int kRuFrameDoubles = 14;                  // F (9), y (3), valid flag, pad: 112-byte stride = conflict-free LDS.128
+constexpr int kRuRawObs = 16;                        // observations per raw stage
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_u32(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// executed by the whole (converged) warp with warp-uniform operands: one elected lane issues the copy
+__device__ __forceinline__ void tma_bulk_g2s_elect(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+        "}\n" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+#ifdef ICP_I8_TIMING
+__device__ long long g_i8_timing[256 * 16];
+#define I8T_DECL long long _tm[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long _t0 = clock64(), _tk = _t0; (void)_tk; (void)_tm;
+#define I8T_MARK() (_tk = clock64())
+#define I8T_ADD(i) do { const long long _n = clock64(); _tm[i] += _n - _tk; _tk = _n; } while (0)
+#define I8T_FLUSH(cond, lo, hi) do { if (cond) for (int _i = lo; _i <= hi; _i++) g_i8_timing[(blockIdx.x & 255) * 16 + _i] = _tm[_i]; } while (0)
+#else
+#define I8T_DECL
+#define I8T_MARK()
+#define I8T_ADD(i)
+#define I8T_FLUSH(cond, lo, hi)
+#endif
+
+struct I8Args {
+    const double *Qhat;      // 3N x Kp: Q with every column divided by its bound colnorm_j (max over the vertices of |Q_v[:, j]|)
+    const double *Qsub;      // nullable: the proposal's observation rows in slot order, [n][3 Kp + 2] (= the shared-memory stride):
+                             // one bulk copy per raw stage instead of one per observation (every slot is then an observation)
+    const double *colnorm;   // Kp (0 on the padding)
+    double fmul;             // frame rows are multiplied by this: |fmul * F_d . Qhat_v[:, j]| <= 2^30
+    double w2;               // (A^T A)[i][j] = colnorm_i colnorm_j w2 * sum_t 256^(3-t) ACC_t[i][j]
+    double bscale;           // b_j = colnorm_j bscale * (accumulated value)
+    int nraw;                // raw stages in the ring
+};
+
+// digit buffer geometry: K block = 4 row groups of 8 rows; a row group holds the 4 images' 7 column chunks side by side
+// (28 chunks + 1 pad chunk of 128 B), so that an MMA's B operand can span two adjacent images (N = 224)
+constexpr int kRuChunksPerImage = 7;                 // 112 columns
+constexpr int kRuGroupBytes = (4 * kRuChunksPerImage + 1) * 128;   // 3712
+constexpr int kRuKBlockBytes = 4 * kRuGroupBytes;                  // 14848
+constexpr int kRuAccStride = 112;                    // TMEM columns between the accumulators of consecutive weights
 
 template <int RPO>
-__global__ void __launch_bounds__(kRuThreads, 1) k_rank_update_i8(ModelDev m, ObsDev o, const double *__restrict__ col_scale,
-                                                                  double row_scale, const double *__restrict__ Gs,
+__global__ void __launch_bounds__(kRuThreads, 1) k_rank_update_i8(ModelDev m, ObsDev o, int C, I8Args a, const double *__restrict__ Gs,
                                                                   double gs_scale, double *__restrict__ Mp,
                                                                   double *__restrict__ bvec) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr int kStageRows = kRuObs * RPO;                    // 96 or 32
-    constexpr int kImageBytes = kStageRows * kI8Cols;           // one digit image of a stage
-    constexpr int kStageBytes = 4 * kImageBytes;
-    __shared__ uint64_t bar[2];
+    constexpr int kBufBytes = RPO * kRuKBlockBytes;             // one digit buffer: RPO K blocks of 32 rows
+    __shared__ uint64_t full_raw[8], empty_raw[8], full_dig[2], empty_dig[2], acc_done;
     __shared__ uint32_t s_tmem;
-    __shared__ int s_poison;
-    const int Kp = m.Kp, c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    double *s_inv = reinterpret_cast<double *>(smem + 2 * kStageBytes);   // [128] 1 / s_j (0 beyond Kp)
-    double *s_scl = s_inv + 128;                                           // [128] s_j
-    double *s_b = s_scl + 128;                                             // [kRuObs][Kp] per-slot partial sums of b
+    __shared__ int s_poison[3];        // by chain % 3: written a chain early by the converters' look-ahead step
+    const int Kp = m.Kp, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NG = Kp >> 3, NPAIR = (NG + 1) >> 1, ncv = 2 * NPAIR;      // column groups of 8, converter warps
+    const int row_bytes = Kp * 8, obs_bytes = 3 * row_bytes, obs_stride = obs_bytes + 16;
+    const int raw_stage = kRuRawObs * obs_stride, NRAW = a.nraw;
+    unsigned char *dig = smem;
+    unsigned char *raw = smem + ((2 * kBufBytes + 127) & ~127);
+    double *frames = reinterpret_cast<double *>(raw + (size_t)NRAW * raw_stage);     // [NRAW][16][14]
+    double *s_b = frames + (size_t)NRAW * kRuRawObs * kRuFrameDoubles;                // [2 chains in flight][2 teams][Kp]
+    double *s_cn = s_b + 4 * Kp;                                                     // [128]
+    double *s_gs = s_cn + 128;                                                       // RPO == 1: gs_scale * Gs, block-packed like Mp
     if (warp == 0) tmem_alloc(&s_tmem, 512);
     if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        s_poison = 0;
+        for (int i = 0; i < NRAW; i++) { mbar_init(&full_raw[i], 32 + kRuRawObs); mbar_init(&empty_raw[i], NPAIR); }
+        for (int i = 0; i < 2; i++) { mbar_init(&full_dig[i], NPAIR); mbar_init(&empty_dig[i], 1); }
+        mbar_init(&acc_done, 1);
+        s_poison[0] = s_poison[1] = s_poison[2] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int j = tid; j < 128; j += kRuThreads) {
-        const double s = j < Kp ? col_scale[j] : 0.0;
-        s_scl[j] = s;
-        s_inv[j] = s > 0.0 ? 1.0 / s : 0.0;
+    for (int j = tid; j < 128; j += kRuThreads) s_cn[j] = j < Kp ? a.colnorm[j] : 0.0;
+    if (RPO == 1) {
+        const int NB = Kp >> 3;
+        for (int e = tid; e < NB * (NB + 1) / 2 * 64; e += kRuThreads) {
+            const int blk = e >> 6, r = (e >> 3) & 7, cc = e & 7;
+            int bi = (int)((sqrtf(8.f * blk + 1.f) - 1.f) * 0.5f);
+            while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+            while (bi * (bi + 1) / 2 > blk) bi--;
+            const int bj = blk - bi * (bi + 1) / 2;
+            s_gs[e] = gs_scale * Gs[(size_t)(8 * bi + r) * Kp + 8 * bj + cc];
+        }
     }
-    // the images start as zeros: rows past the last observation and columns >= Kp are never written
-    for (int e = tid; e < 2 * kStageBytes / 16; e += kRuThreads) reinterpret_cast<uint4 *>(smem)[e] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const int nrows = o.nrows ? min(o.nrows[c], o.n) : o.n;    // observation slots in use
-    const int nstage = (nrows + kRuObs - 1) / kRuObs;
-    const int half = tid & 1, ch = (tid >> 1) & 7, os = tid >> 4;
-    const int j0 = 16 * ch + 8 * half;                          // this thread's 8 columns
-    const bool cols_live = j0 < Kp;
-    const int *vid = o.vid + (size_t)c * o.n;
-    const double *F = o.F + (size_t)c * o.n * 9, *yt = o.y + (size_t)c * o.n * 3;
-    double bacc[8];
+    const int nmax = o.n;
+    I8T_DECL
+
+    if (warp == kRuGatherWarp) {
+        // ---------------- gather warp: raw stage R of the CTA's flattened (chain, stage) sequence ----------------
+        unsigned R = 0;
+        int c = blockIdx.x;
+        int nrows = c < C ? (o.nrows ? min(o.nrows[c], nmax) : nmax) : 0;
+        int nst = 2 * ((nrows + 31) >> 5), rs = 0;
+        while (c < C && nst == 0) { c += gridDim.x; nrows = c < C ? (o.nrows ? min(o.nrows[c], nmax) : nmax) : 0; nst = 2 * ((nrows + 31) >> 5); }
+        int v = -1;                                             // vertex of (c, rs) of lane's observation, loaded one stage ahead
+        if (c < C && lane < kRuRawObs && lane < nrows) v = __ldg(o.vid + (size_t)c * nmax + lane);
+        while (c < C) {
+            // successor (c2, rs2)
+            int c2 = c, rs2 = rs + 1, nrows2 = nrows, nst2 = nst;
+            if (rs2 >= nst) {
+                rs2 = 0;
+                do { c2 += gridDim.x; nrows2 = c2 < C ? (o.nrows ? min(o.nrows[c2], nmax) : nmax) : 0; nst2 = 2 * ((nrows2 + 31) >> 5); } while (c2 < C && nst2 == 0);
+            }
+            int vnext = -1;
+            if (c2 < C && lane < kRuRawObs && rs2 * kRuRawObs + lane < nrows2) vnext = __ldg(o.vid + (size_t)c2 * nmax + rs2 * kRuRawObs + lane);
+            const unsigned slot = R % NRAW;
+            I8T_MARK();
+            if (R >= (unsigned)NRAW) mbar_wait(&empty_raw[slot], ((R / NRAW) - 1) & 1);
+            I8T_ADD(7);
+            const int g0 = rs * kRuRawObs, nob = max(0, min(kRuRawObs, nrows - g0));       // observation slots of this stage
+            double *fr0 = frames + (size_t)slot * kRuRawObs * kRuFrameDoubles;
+            {   // frames and right-hand sides: 9 nob + 3 nob contiguous doubles, dealt over the 32 lanes
+                const double *F = o.F + ((size_t)c * nmax + g0) * 9, *y = o.y + ((size_t)c * nmax + g0) * 3;
 #pragma unroll
-    for (int k = 0; k < 8; k++) bacc[k] = 0.0;
-    double inv[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) inv[k] = cols_live ? s_inv[j0 + k] : 0.0;
-    // frames travel one stage ahead in registers (they come from DRAM)
-    double fn[12];
-    int vn = -1;
-    auto frame = [&](int st) {
-        const int gi = st * kRuObs + os;
-        vn = (st < nstage && gi < nrows) ? __ldg(&vid[gi]) : -1;
-        if (vn >= 0) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) fn[k] = __ldg(F + (size_t)gi * 9 + k);
-#pragma unroll
-            for (int k = 0; k < 3; k++) fn[9 + k] = __ldg(yt + (size_t)gi * 3 + k);
-        }
-    };
-    frame(0);
-    const uint32_t idesc = umma_idesc_i8(128, kI8N);
-    bool poison = false;
-    for (int st = 0; st < nstage; st++) {
-        const int buf = st & 1;
-        unsigned char *stage = smem + buf * kStageBytes;
-        // the MMAs that read this buffer two stages ago must have finished
-        if (st >= 2) mbar_wait(&bar[buf], ((st >> 1) - 1) & 1);
-        const int v = vn;
-        double f[12];
-#pragma unroll
-        for (int k = 0; k < 12; k++) f[k] = fn[k];
-        frame(st + 1);
-        if (cols_live) {
-            unsigned long long dig[RPO][4];
-#pragma unroll
-            for (int d = 0; d < RPO; d++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) dig[d][q] = 0ull;
-            if (v >= 0) {
-                const double2 *q0 = reinterpret_cast<const double2 *>(m.Q + (size_t)3 * v * Kp + j0);
-                const double2 *q1 = reinterpret_cast<const double2 *>(m.Q + ((size_t)3 * v + 1) * Kp + j0);
-                const double2 *q2 = reinterpret_cast<const double2 *>(m.Q + ((size_t)3 * v + 2) * Kp + j0);
-                double qa[8], qb[8], qc[8];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const double2 a = __ldg(q0 + k), b = __ldg(q1 + k), cc = __ldg(q2 + k);
-                    qa[2 * k] = a.x; qa[2 * k + 1] = a.y; qb[2 * k] = b.x; qb[2 * k + 1] = b.y; qc[2 * k] = cc.x; qc[2 * k + 1] = cc.y;
-                }
-                if (RPO == 1) {
-                    // b += Q_i^T (F^T F y): w = F^T (F y)
-                    const double w0 = f[0] * f[9] + f[3] * f[10] + f[6] * f[11], w1 = f[1] * f[9] + f[4] * f[10] + f[7] * f[11],
-                                 w2 = f[2] * f[9] + f[5] * f[10] + f[8] * f[11];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) bacc[k] = fma(w0, qa[k], fma(w1, qb[k], fma(w2, qc[k], bacc[k])));
+                for (int j = 0; j < 5; j++) {
+                    const int e = lane + 32 * j;
+                    if (e < 9 * nob) cp_async8(fr0 + (e / 9) * kRuFrameDoubles + e % 9, F + e);
                 }
 #pragma unroll
-                for (int d = 0; d < RPO; d++) {
-                    const double f0 = RPO == 1 ? f[0] * row_scale : f[3 * d], f1 = RPO == 1 ? f[1] * row_scale : f[3 * d + 1],
-                                 f2 = RPO == 1 ? f[2] * row_scale : f[3 * d + 2];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const double a = f0 * qa[k] + f1 * qb[k] + f2 * qc[k];       // the DMMA producers' arithmetic
-                        if (RPO == 3) bacc[k] = fma(f[9 + d], a, bacc[k]);
-                        double t = a * inv[k];
-                        if (!(fabs(t) < 0.5)) { poison = poison || (t != 0.0); t = 0.0; }   // out of the scaled range or NaN
-                        // four balanced base-255 digits: two in FP64, the remainder (|r| <= 1/2, 2^-16 needed) in FP32
-                        // (a remainder of exactly +-1/2 would round to +-128: clamped to +-127, the next digit absorbs it)
-                        const int i0 = __double2int_rn(t * kRuBase);
-                        double r = fma(t, kRuBase, -(double)i0);
-                        const int i1 = max(-127, min(127, __double2int_rn(r * kRuBase)));
-                        r = fma(r, kRuBase, -(double)i1);
-                        float rf = (float)r;
-                        const int i2 = max(-127, min(127, __float2int_rn(rf * 255.f)));
-                        rf = fmaf(rf, 255.f, -(float)i2);
-                        const int i3 = max(-127, min(127, __float2int_rn(rf * 255.f)));
-                        dig[d][0] |= (unsigned long long)(unsigned char)i0 << (8 * k);
-                        dig[d][1] |= (unsigned long long)(unsigned char)i1 << (8 * k);
-                        dig[d][2] |= (unsigned long long)(unsigned char)i2 << (8 * k);
-                        dig[d][3] |= (unsigned long long)(unsigned char)i3 << (8 * k);
-                    }
+                for (int j = 0; j < 2; j++) {
+                    const int e = lane + 32 * j;
+                    if (e < 3 * nob) cp_async8(fr0 + (e / 3) * kRuFrameDoubles + 9 + e % 3, y + e);
+                }
+                cp_async_mbar_arrive_noinc(&full_raw[slot]);
+            }
+            if (lane < kRuRawObs) fr0[lane * kRuFrameDoubles + 12] = v >= 0 ? 1.0 : 0.0;
+            const uint32_t dst = smem_u32(raw + (size_t)slot * raw_stage), bar = smem_u32(&full_raw[slot]);
+            const bool leader = lane == 0;
+            if (a.Qsub) {
+                // every slot of the stage is an observation: one bulk copy
+                if (leader && nob > 0) {
+                    mbar_arrive_expect_tx(&full_raw[slot], (uint32_t)(nob * obs_stride));
+                    tma_bulk_g2s_u32(dst, reinterpret_cast<const unsigned char *>(a.Qsub) + (size_t)g0 * obs_stride, (uint32_t)(nob * obs_stride), bar);
+                } else if (lane < kRuRawObs) mbar_arrive(&full_raw[slot]);
+            } else {
+                // one bulk copy per observation (3 Kp doubles, contiguous in Qhat). Measured alternatives, all slower than the
+                // compiler's per-lane issue loop (~77 clocks per copy): straight-line issue from warp-uniform operands
+                // (redux + elect.sync, ~130 clocks per copy) and 16-byte cp.async.cg dealt over the lanes (~330 clocks per row triple)
+                if (lane < kRuRawObs) {
+                    if (v >= 0) {
+                        mbar_arrive_expect_tx(&full_raw[slot], (uint32_t)obs_bytes);
+                        tma_bulk_g2s_u32(dst + (uint32_t)(lane * obs_stride), a.Qhat + (size_t)3 * v * Kp, (uint32_t)obs_bytes, bar);
+                    } else mbar_arrive(&full_raw[slot]);
                 }
             }
-#pragma unroll
-            for (int d = 0; d < RPO; d++) {
-                const uint32_t off = i8_line_offset(os * RPO + d, ch) + 8 * half;
-#pragma unroll
-                for (int q = 0; q < 4; q++) *reinterpret_cast<unsigned long long *>(stage + q * kImageBytes + off) = dig[d][q];
-            }
+            __syncwarp();
+            I8T_ADD(8);
+            R++;
+            c = c2; rs = rs2; nrows = nrows2; nst = nst2; v = vnext;
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t sbase = smem_u32(stage);
+        I8T_FLUSH(lane == 0, 7, 8);
+    } else {
+        unsigned S = 0, it = 0, nacc = 0;                        // 32-observation steps / chains / non-empty chains done by this CTA
+        // converter state
+        const int cw = warp < kRuGatherWarp ? warp : warp - 1;       // converter index 0..13 (warps 0..11, 13, 14)
+        const int pair = cw >> 1, h = cw & 1, gh = (lane >> 3) & 1, g = 2 * pair + gh;
+        const int osl = (lane & 7) + 8 * (lane >> 4);                 // observation inside the raw stage (0..15)
+        const bool live = cw < ncv && g < NG;
+        double bacc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) bacc[k] = 0.0;
+        bool ovf = false;
+        int pre_done = 0;                                             // the team's first step of this chain was converted early
+        auto reduce_b = [&]() {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                double s = bacc[k];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s += __shfl_xor_sync(0xffffffffu, s, 16);
+                bacc[k] = s;
+            }
+        };
+        // one 32-observation step (global index Sg) of team h: two raw stages of 16 observations into digit buffer h
+        auto convert_step = [&](unsigned Sg) {
+            const double lim = 1.152921504606846976e18;               // 2^60: |fmul F_d|^2 above it could leave |x| <= 2^30
 #pragma unroll 1
-            for (int ks = 0; ks < RPO; ks++) {
+            for (int pass = 0; pass < 2; pass++) {
+                const unsigned R = 2 * Sg + pass, slot = R % NRAW;
+                I8T_MARK();
+                mbar_wait(&full_raw[slot], (R / NRAW) & 1);
+                I8T_ADD(1);
+                const double *fr = frames + ((size_t)slot * kRuRawObs + osl) * kRuFrameDoubles;
+                const bool valid = live && fr[12] != 0.0;
+                double f[12];
+                double2 q[3][4];
+                if (valid) {
 #pragma unroll
-                for (int t = 0; t < 4; t++)
+                    for (int k = 0; k < 6; k++) { const double2 t2 = reinterpret_cast<const double2 *>(fr)[k]; f[2 * k] = t2.x; f[2 * k + 1] = t2.y; }
+                    const unsigned char *rp = raw + (size_t)slot * raw_stage + (size_t)osl * obs_stride + g * 64;
 #pragma unroll
-                    for (int k = 0; k <= t; k++) {
-                        const uint64_t da = umma_desc_noswizzle(sbase + k * kImageBytes + ks * kI8BlockBytes, 1024, 128);
-                        const uint64_t db = umma_desc_noswizzle(sbase + (t - k) * kImageBytes + ks * kI8BlockBytes, 1024, 128);
-                        umma_i8(tmem + 128 * t, da, db, idesc, (st | ks | k) ? 1u : 0u);
-                    }
-            }
-            umma_commit(&bar[buf]);
-        }
-    }
-    // b: per-slot partial sums, reduced in slot order (deterministic)
-    if (cols_live) {
+                    for (int d = 0; d < 3; d++)
 #pragma unroll
-        for (int k = 0; k < 8; k++) s_b[os * Kp + j0 + k] = bacc[k];
-    }
-    if (poison) atomicOr(&s_poison, 1);
-    // every issued MMA has completed once the last commit of each buffer has arrived
-    if (nstage >= 1) mbar_wait(&bar[(nstage - 1) & 1], ((nstage - 1) >> 1) & 1);
-    if (nstage >= 2) mbar_wait(&bar[(nstage - 2) & 1], ((nstage - 2) >> 1) & 1);
-    tc_fence_after();
-    __syncthreads();
-    const bool bad = s_poison != 0;
-    for (int j = tid; j < Kp; j += kRuThreads) {
-        double s = 0.0;
-        for (int sl = 0; sl < kRuObs; sl++) s += s_b[sl * Kp + j];
-        bvec[(size_t)c * Kp + j] = bad ? NAN : s;
-    }
-    // epilogue: thread = (row i = TMEM lane, column chunks cg, cg + 4)
-    {
-        const int i = 32 * (warp & 3) + lane, cg = warp >> 2, NB = Kp >> 3, ntri = NB * (NB + 1) / 2;
-        double *Mc = Mp + (size_t)c * ntri * 64;
-        const double si = i < Kp ? s_scl[i] : 0.0;
-        const double w2 = 1.0 / (kRuBase * kRuBase), cinv = 1.0 / kRuBase;
-        for (int chn = cg; chn < 7; chn += 4) {
-            const int jc = 16 * chn;
-            if (nstage == 0 || i >= Kp || jc >= Kp || (jc >> 3) > (i >> 3)) {
-                // (all lanes of a warp must still issue the TMEM loads together: the branch is evaluated per lane below)
-            }
-            int a0[16], a1[16], a2[16], a3[16];
-            const uint32_t ta = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + jc;
-            if (nstage > 0) { tmem_ld16(ta, a0); tmem_ld16(ta + 128, a1); tmem_ld16(ta + 256, a2); tmem_ld16(ta + 384, a3); }
-            else {
-#pragma unroll
-                for (int k = 0; k < 16; k++) a0[k] = a1[k] = a2[k] = a3[k] = 0;
-            }
-            if (i >= Kp) continue;
-            const int bi = i >> 3;
-#pragma unroll
-            for (int hb = 0; hb < 2; hb++) {
-                const int bj = (jc >> 3) + hb;
-                if (bj > bi || 8 * bj >= Kp) continue;
-                double *dst = Mc + (size_t)((bi * (bi + 1) >> 1) + bj) * 64 + (i & 7) * 8;
-#pragma unroll
-                for (int k = 0; k < 8; k += 2) {
-                    double v[2];
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const int kk = 8 * hb + k + u, j = jc + kk;
-                        const double acc = ((((double)a3[kk] * cinv + (double)a2[kk]) * cinv + (double)a1[kk]) * cinv + (double)a0[kk]) * w2;
-                        double val = si * s_scl[j] * acc + (i == j ? 1.0 : 0.0);
-                        if (RPO == 1) val = fma(__ldg(Gs + (size_t)i * Kp + j), gs_scale, val);
-                        v[u] = bad ? NAN : val;
-                    }
-                    *reinterpret_cast<double2 *>(dst + k) = make_double2(v[0], v[1]);
+                        for (int k = 0; k < 4; k++) q[d][k] = *reinterpret_cast<const double2 *>(rp + d * row_bytes + 16 * k);
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_raw[slot]);             // NPAIR warps read this stage: one arrival each
+                I8T_ADD(12);
+                if (pass == 0 && Sg >= 2) mbar_wait(&empty_dig[h], ((Sg >> 1) - 1) & 1);
+                I8T_ADD(2);
+                // 16-byte line of (row 16 pass + osl, image 0, chunk pair) inside a K block, + this thread's 8-byte half
+                unsigned char *blk = dig + h * kBufBytes + (2 * pass + (lane >> 4)) * kRuGroupBytes + pair * 128 + (lane & 7) * 16 + gh * 8;
+                if (valid) {
+                    double w0 = 0, w1 = 0, w2v = 0;
+                    if (RPO == 1) {
+                        // b += Q_i^T (F^T F y)
+                        w0 = f[0] * f[9] + f[3] * f[10] + f[6] * f[11];
+                        w1 = f[1] * f[9] + f[4] * f[10] + f[7] * f[11];
+                        w2v = f[2] * f[9] + f[5] * f[10] + f[8] * f[11];
+                    }
+#pragma unroll
+                    for (int d = 0; d < RPO; d++) {
+                        const double f0 = f[3 * d] * a.fmul, f1 = f[3 * d + 1] * a.fmul, f2 = f[3 * d + 2] * a.fmul;
+                        ovf = ovf || !(fma(f2, f2, fma(f1, f1, f0 * f0)) <= lim);        // also catches NaN frames
+                        uint32_t w[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const double qa = (k & 1) ? q[0][k >> 1].y : q[0][k >> 1].x, qb = (k & 1) ? q[1][k >> 1].y : q[1][k >> 1].x,
+                                         qc = (k & 1) ? q[2][k >> 1].y : q[2][k >> 1].x;
+                            const double av = fma(f2, qc, fma(f1, qb, f0 * qa));
+                            if (RPO == 3) bacc[k] = fma(f[9 + d], av, bacc[k]);
+                            else bacc[k] = fma(w0, qa, fma(w1, qb, fma(w2v, qc, bacc[k])));
+                            // x = rn(av) (|av| <= 2^30) is the low word of av + 1.5 * 2^52; the constant also carries the
+                            // + 0x00808080 of the balanced base-256 digits: x + 0x00808080 = sum_k (d_k + 128 [k > 0]) 256^(3-k)
+                            w[k] = (uint32_t)__double2loint(av + (6755399441055744.0 + 8421504.0));
+                        }
+                        // 4 x 4 byte transposes: image q gets byte 3 - q of the eight words; the lower digits leave their
+                        // + 128 offset here (^ 0x80 per byte), the top byte is the signed leading digit as it is
+                        const uint32_t t0 = prmt(w[0], w[1], 0x5140), t1 = prmt(w[0], w[1], 0x7362), t2 = prmt(w[2], w[3], 0x5140),
+                                       t3 = prmt(w[2], w[3], 0x7362), u0 = prmt(w[4], w[5], 0x5140), u1 = prmt(w[4], w[5], 0x7362),
+                                       u2 = prmt(w[6], w[7], 0x5140), u3 = prmt(w[6], w[7], 0x7362);
+                        unsigned char *bd = blk + d * kRuKBlockBytes;
+                        const uint32_t X = 0x80808080u;
+                        *reinterpret_cast<uint2 *>(bd + 3 * kRuChunksPerImage * 128) = make_uint2(prmt(t0, t2, 0x5410) ^ X, prmt(u0, u2, 0x5410) ^ X);
+                        *reinterpret_cast<uint2 *>(bd + 2 * kRuChunksPerImage * 128) = make_uint2(prmt(t0, t2, 0x7632) ^ X, prmt(u0, u2, 0x7632) ^ X);
+                        *reinterpret_cast<uint2 *>(bd + 1 * kRuChunksPerImage * 128) = make_uint2(prmt(t1, t3, 0x5410) ^ X, prmt(u1, u3, 0x5410) ^ X);
+                        *reinterpret_cast<uint2 *>(bd) = make_uint2(prmt(t1, t3, 0x7632), prmt(u1, u3, 0x7632));
+                    }
+                } else if (live) {
+#pragma unroll
+                    for (int d = 0; d < RPO; d++)
+#pragma unroll
+                        for (int qq = 0; qq < 4; qq++)
+                            *reinterpret_cast<uint2 *>(blk + d * kRuKBlockBytes + qq * kRuChunksPerImage * 128) = make_uint2(0u, 0u);
+                }
+                I8T_ADD(3);
             }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_dig[h]);
+            I8T_ADD(13);
+        };
+        for (int c = blockIdx.x; c < C; c += gridDim.x, it++) {
+            const int nrows = o.nrows ? min(o.nrows[c], nmax) : nmax;
+            const int nsteps = (nrows + 31) >> 5;
+            double *sb = s_b + (it & 1) * 2 * Kp;
+            if (warp == kRuMmaWarp) {
+                // ---------------- MMA warp ----------------
+                const uint32_t idw = umma_idesc_i8(128, 2 * kRuAccStride), idn = umma_idesc_i8(128, kRuAccStride);
+                for (int st = 0; st < nsteps; st++) {
+                    const unsigned Sg = S + st, buf = Sg & 1;
+                    I8T_MARK();
+                    mbar_wait(&full_dig[buf], (Sg >> 1) & 1);
+                    I8T_ADD(5);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sbase = smem_u32(dig + buf * kBufBytes);
+#pragma unroll 1
+                        for (int d = 0; d < RPO; d++) {
+                            // image q of K block d: operand descriptors start at its first chunk; LBO = row-group stride
+                            auto img = [&](int q) { return umma_desc_noswizzle(sbase + d * kRuKBlockBytes + q * kRuChunksPerImage * 128, kRuGroupBytes, 128); };
+                            const uint32_t first = (st | d) ? 1u : 0u;
+                            // D_k^T [D_l D_l+1] lands in the accumulators of weight k + l and k + l + 1 (adjacent TMEM columns)
+                            umma_i8(tmem + 0 * kRuAccStride, img(0), img(0), idw, first);     // (0,0) (0,1)
+                            umma_i8(tmem + 2 * kRuAccStride, img(0), img(2), idw, first);     // (0,2) (0,3)
+                            umma_i8(tmem + 1 * kRuAccStride, img(1), img(0), idw, 1u);        // (1,0) (1,1)
+                            umma_i8(tmem + 3 * kRuAccStride, img(1), img(2), idn, 1u);        // (1,2)
+                            umma_i8(tmem + 2 * kRuAccStride, img(2), img(0), idw, 1u);        // (2,0) (2,1)
+                            umma_i8(tmem + 3 * kRuAccStride, img(3), img(0), idn, 1u);        // (3,0)
+                        }
+                        umma_commit(&empty_dig[buf]);
+                        if (st == nsteps - 1) umma_commit(&acc_done);
+                    }
+                    __syncwarp();
+                    I8T_ADD(6);
+                }
+            } else if (cw < ncv) {
+                // ---------------- converter warps: team h = cw & 1 converts the steps of its parity into digit buffer h ----------------
+                // steps of this chain the team still owes, then - while the tensor core finishes the chain - its first step
+                // of the next chain (one call site of the step body: two would double its register footprint)
+                int st = ((h - (int)S) & 1) + 2 * pre_done;
+                const bool had_pre = pre_done != 0;
+                pre_done = 0;
+                bool published = false;
+                for (;;) {
+                    unsigned Sg;
+                    if (st < nsteps) { Sg = S + st; st += 2; }
+                    else if (!published) {
+                        // b: the 16 observation lanes of this warp (same gh), fixed order; the two teams meet in shared memory.
+                        // The early step's share is already there (it must not stay in registers across the epilogue)
+                        reduce_b();
+                        if (live && (lane & 23) == 0) {                       // lanes 0 and 8: one per column group
+#pragma unroll
+                            for (int k = 0; k < 8; k++) sb[h * Kp + 8 * g + k] = bacc[k] + (had_pre ? sb[h * Kp + 8 * g + k] : 0.0);
+                        }
+                        if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(&s_poison[it % 3], 1);
+                        ovf = false;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) bacc[k] = 0.0;
+                        published = true;
+                        const int c2 = c + gridDim.x;
+                        if (c2 >= C) break;
+                        const int nrows2 = o.nrows ? min(o.nrows[c2], nmax) : nmax, nsteps2 = (nrows2 + 31) >> 5;
+                        const unsigned S2 = S + nsteps;
+                        const int first2 = (h - (int)S2) & 1;
+                        if (first2 >= nsteps2) break;
+                        Sg = S2 + first2;
+                        pre_done = 1;
+                    } else break;
+                    convert_step(Sg);
+                    if (published) break;
+                }
+                if (pre_done) {
+                    // the early step's share of the next chain's b goes to that chain's buffer now
+                    reduce_b();
+                    double *sbn = s_b + ((it + 1) & 1) * 2 * Kp;
+                    if (live && (lane & 23) == 0) {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) sbn[h * Kp + 8 * g + k] = bacc[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) bacc[k] = 0.0;
+                    if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(&s_poison[(it + 1) % 3], 1);
+                    ovf = false;
+                }
+                I8T_MARK();
+            }
+            S += nsteps;
+            // ---------------- epilogue: every warp but the gather warp ----------------
+            named_bar_sync(1, kRuThreads - 32);
+            I8T_ADD(4);
+            const bool bad = s_poison[it % 3] != 0;
+            for (int j = tid; j < Kp; j += kRuThreads)
+                bvec[(size_t)c * Kp + j] = bad ? NAN : (sb[j] + sb[Kp + j]) * s_cn[j] * a.bscale;
+            I8T_MARK();
+            if (nsteps > 0) { mbar_wait(&acc_done, nacc & 1); nacc++; }
+            I8T_ADD(9);
+            tc_fence_after();
+            {
+                // warp = TMEM lane quarter qd (rows 32 qd ..); the half blocks (4 columns) of the 8-column blocks bj <= 4 qd + 3 are
+                // dealt over the quarter's warps (16 accumulator registers per task: nothing of the converters' state spills)
+                const int qd = warp & 3, i = 32 * qd + lane, NB = Kp >> 3, ntri = NB * (NB + 1) / 2;
+                const int nw = qd == (kRuGatherWarp & 3) ? 3 : 4, idx = warp >> 2;          // (quarter 0's missing warp is its last: idx stays dense)
+                const int nhalf = 2 * min(4 * qd + 4, NB);
+                double *Mc = Mp + (size_t)c * ntri * 64;
+                const double cij = (i < Kp && nsteps > 0) ? s_cn[i] * a.w2 : 0.0;   // no observation: the accumulators are undefined
+                const int bi = i >> 3;
+                if (32 * qd < Kp)
+                    for (int hb = idx; hb < nhalf; hb += nw) {
+                        // (two half blocks in flight - the next one's TMEM loads issued before this one's arithmetic - needs 16 more
+                        // registers, spills, and measured 2.7x slower: with 220 KB of shared memory the L1 is too small for local memory)
+                        const int bj = hb >> 1, j0 = 4 * hb;
+                        int a0[4], a1[4], a2[4], a3[4];
+                        const uint32_t ta = tmem + ((uint32_t)(32 * qd) << 16) + j0;
+                        tmem_ld4_nowait(ta, a0); tmem_ld4_nowait(ta + kRuAccStride, a1); tmem_ld4_nowait(ta + 2 * kRuAccStride, a2);
+                        tmem_ld4_nowait(ta + 3 * kRuAccStride, a3);
+                        tmem_ld_wait();
+                        if (i < Kp && bj <= bi) {
+                            const int off = ((bi * (bi + 1) >> 1) + bj) * 64 + (i & 7) * 8 + (j0 & 7);
+                            double *dst = Mc + off;
+#pragma unroll
+                            for (int k = 0; k < 4; k += 2) {
+                                double vv[2];
+#pragma unroll
+                                for (int u = 0; u < 2; u++) {
+                                    const int kk = k + u, j = j0 + kk;
+                                    // exact integer Horner in base 256 (|H| < 2^51), then int64 -> double through the 1.5 * 2^52 offset
+                                    const long long H = (((long long)a0[kk] * 256 + a1[kk]) * 256 + a2[kk]) * 256 + a3[kk];
+                                    const double acc = __longlong_as_double(H + 0x4338000000000000ll) - 6755399441055744.0;
+                                    double val = fma(cij * s_cn[j], acc, i == j ? 1.0 : 0.0);
+                                    if (RPO == 1) val += s_gs[off + kk];
+                                    vv[u] = bad ? NAN : val;
+                                }
+                                *reinterpret_cast<double2 *>(dst + k) = make_double2(vv[0], vv[1]);
+                            }
+                        }
+                    }
+            }
+            I8T_ADD(14);
+            tc_fence_before();
+            named_bar_sync(1, kRuThreads - 32);
+            tc_fence_after();
+            if (tid == 0) s_poison[it % 3] = 0;     // next written for chain it + 3, at the earliest after the barriers of chain it + 1
+            I8T_ADD(10);
+#ifdef ICP_I8_TIMING
+            _tm[11] += 1;
+#endif
         }
+        I8T_FLUSH(tid == 0, 1, 4);
+        I8T_FLUSH(tid == 0, 9, 14);
+#ifdef ICP_I8_TIMING
+        if (warp == 3) { _tm[15] = _tm[14]; I8T_FLUSH(lane == 0, 15, 15); }
+#endif
+        I8T_FLUSH(warp == kRuMmaWarp && lane == 0, 5, 6);
     }
+#ifdef ICP_I8_TIMING
+    if (tid == 0) g_i8_timing[(blockIdx.x & 255) * 16] = clock64() - _t0;
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// the observation rows of a model-sampling proposal in slot order, padded to the shared-memory stride of the rank update
+__global__ void k_pack_obs_rows(int n, int Kp, const int *__restrict__ ids, const double *__restrict__ Qhat, double *__restrict__ Qsub) {
+    const int i = blockIdx.x, stride = 3 * Kp + 2;
+    const double *src = Qhat + (size_t)3 * ids[i] * Kp;
+    for (int e = threadIdx.x; e < stride; e += blockDim.x) Qsub[(size_t)i * stride + e] = e < 3 * Kp ? src[e] : 0.0;
+}
+void launch_pack_obs_rows(int n, int Kp, const int *d_ids, const double *d_Qhat, double *d_Qsub, cudaStream_t s) {
+    if (n <= 0) return;
+    k_pack_obs_rows<<<n, 128, 0, s>>>(n, Kp, d_ids, d_Qhat, d_Qsub);
+    ICP_CUDA(cudaGetLastError());
+}
+
+__global__ void k_unit_basis(long long total, int Kp, const double *__restrict__ Q, const double *__restrict__ colnorm, double *__restrict__ Qhat) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const double cn = colnorm[g % Kp];
+    Qhat[g] = cn > 0.0 ? Q[g] / cn : 0.0;
+}
+void launch_unit_basis(int rows, int Kp, const double *d_Q, const double *d_colnorm, double *d_Qhat, cudaStream_t s) {
+    const long long total = (long long)rows * Kp;
+    k_unit_basis<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(total, Kp, d_Q, d_colnorm, d_Qhat);
+    ICP_CUDA(cudaGetLastError());
+}
+
+}  // namespace icp
+#ifdef ICP_I8_TIMING
+extern "C" int32_t icp_debug_i8_timing(long long *out, int32_t n) {
+    return (int32_t)cudaMemcpyFromSymbol(out, icp::g_i8_timing, sizeof(long long) * std::min(n, 256 * 16));
+}
+#endif
+namespace icp {
 // false: outside the kernel's domain (nothing launched) - the caller takes the FP64 tensor-pipe path
-bool launch_rank_update_i8(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, const double *d_col_scale,
-                           double *d_Mp, double *d_b, cudaStream_t s) {
-    if (C <= 0 || m.Kp > kI8N || (m.Kp & 7)) return false;
+bool launch_rank_update_i8(const ModelDev &m, int C, const ObsDev &o, const GramFast *gf, const I8Model &im, const I8Scale &sc,
+                           double *d_Mp, double *d_b, int n_sm, cudaStream_t s) {
+    const int rpo = gf ? 1 : 3;
+    // INT32 accumulators: rows * 4 digit pairs * 128^2 < 2^31
+    if (C <= 0 || m.Kp > kI8N || (m.Kp & 7) || !im.Qhat || (long long)o.n * rpo > 32000 || !(sc.fmul > 0.0) || !std::isfinite(sc.fmul)) return false;
     ProfScope _ps(ST_POSTERIOR_BUILD, s);
-    const size_t tail = sizeof(double) * (256 + (size_t)kRuObs * m.Kp) + 1024;
+    const size_t obs_stride = (size_t)3 * m.Kp * 8 + 16;
+    const size_t per_stage = kRuRawObs * obs_stride + kRuRawObs * kRuFrameDoubles * 8;
+    const size_t fixed = (size_t)2 * rpo * kRuKBlockBytes + 128 + (size_t)(4 * m.Kp + 128) * 8 + 1024 +
+                         (gf ? (size_t)(m.Kp / 8) * (m.Kp / 8 + 1) / 2 * 64 * 8 : 0);
+    const size_t budget = 227 * 1024 - 1024;     // static shared memory (barriers) comes on top
+    int nraw = (int)std::min<size_t>(8, (budget - fixed) / per_stage);
+    if (nraw < 2) return false;
+    I8Args a{im.Qhat, gf ? im.Qsub : nullptr, im.colnorm, sc.fmul, sc.w2, sc.bscale, nraw};
+    // one CTA per SM (all 512 TMEM columns): ask for more than half of the shared memory so that no second CTA is scheduled
+    // only to wait for the allocation
+    const size_t smem = std::max<size_t>(fixed + nraw * per_stage, 120 * 1024);
+    const int grid = std::min(C, std::max(1, n_sm));
     if (gf) {
-        const size_t smem = (size_t)2 * 4 * kRuObs * kI8Cols + tail;
-        // one CTA per SM (all 512 TMEM columns): ask for more than half of the shared memory so that no second CTA is
-        // scheduled only to wait for the allocation
-        const size_t ask = std::max<size_t>(smem, 116 * 1024);
-        ICP_CUDA(cudaFuncSetAttribute(k_rank_update_i8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ask));
-        k_rank_update_i8<1><<<C, kRuThreads, ask, s>>>(m, o, d_col_scale, gf->row_scale, gf->Gs, gf->gs_scale, d_Mp, d_b);
+        ICP_CUDA(cudaFuncSetAttribute(k_rank_update_i8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_rank_update_i8<1><<<grid, kRuThreads, smem, s>>>(m, o, C, a, gf->Gs, gf->gs_scale, d_Mp, d_b);
     } else {
-        const size_t smem = (size_t)2 * 4 * kRuObs * 3 * kI8Cols + tail;
         ICP_CUDA(cudaFuncSetAttribute(k_rank_update_i8<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_rank_update_i8<3><<<C, kRuThreads, smem, s>>>(m, o, d_col_scale, 1.0, nullptr, 0.0, d_Mp, d_b);
+        k_rank_update_i8<3><<<grid, kRuThreads, smem, s>>>(m, o, C, a, nullptr, 0.0, d_Mp, d_b);
     }
     ICP_CUDA(cudaGetLastError());
     return true;
