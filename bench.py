@@ -263,8 +263,11 @@ def run_gpu(args):
     ctx = core.Context(local)
     model = core.Model(ctx, m["ref"], m["cells"], m["basis"], m["variance"])
     tgt = core.Target(ctx, tv, tc)
-    pt = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.TARGET_SAMPLING, True, ids, tp)
-    pm = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.MODEL_SAMPLING, True, ids, tp)
+    # rank update of the ICP posteriors: INT8 tensor cores (tcgen05, split-integer emulation of the FP64 product, 1e-8 on the
+    # posterior mean against the 1e-5 contract) by default; --rank-update fp64 selects the FP64 tensor pipe (DMMA, 1e-12)
+    ru = _lib.RANK_UPDATE_INT8 if args.rank_update == "int8" else _lib.RANK_UPDATE_FP64
+    pt = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.TARGET_SAMPLING, True, ids, tp, rank_update=ru)
+    pm = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.MODEL_SAMPLING, True, ids, tp, rank_update=ru)
     comps = [dict(kind=_lib.PROP_ICP, weight=0.45, proposal=pt), dict(kind=_lib.PROP_ICP, weight=0.45, proposal=pm),
              dict(kind=_lib.PROP_RANDOM_SHAPE, weight=0.1, sd=0.1)]
     ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, _lib.MODEL_TO_TARGET, True, 0.0, 2.0, 0.0, eids, tp)
@@ -315,6 +318,34 @@ def run_gpu(args):
                      "note": "the same chains resumed for S more steps with the full chain log written to HBM (%.1f GB)" %
                              ((s_comp.nbytes + s_acc.nbytes + s_val.nbytes + s_th.nbytes) / 1e9)}
         del s_comp, s_acc, s_val, s_th
+
+    # ---- the same K steps with the other arithmetic of the rank update (comparison only) --------------------------------
+    other = None
+    if rank == 0 and world == 1:
+        oru = _lib.RANK_UPDATE_FP64 if ru == _lib.RANK_UPDATE_INT8 else _lib.RANK_UPDATE_INT8
+        opt_ = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.TARGET_SAMPLING, True, ids, tp, rank_update=oru)
+        opm_ = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.MODEL_SAMPLING, True, ids, tp, rank_update=oru)
+        ocomps = [dict(kind=_lib.PROP_ICP, weight=0.45, proposal=opt_), dict(kind=_lib.PROP_ICP, weight=0.45, proposal=opm_),
+                  dict(kind=_lib.PROP_RANDOM_SHAPE, weight=0.1, sd=0.1)]
+        ochain = core.Chain(model, tgt, ocomps, ev, max_chains=C)
+        o_th = torch.empty((steps, C, L), dtype=torch.float64, device=dev); o_acc = torch.empty((steps, C), dtype=torch.uint8, device=dev)
+        ochain.run_device(C, warm, th0.data_ptr(), seed=seed, chain_id_offset=off)
+        torch.cuda.synchronize()
+        ochain.run_device(C, steps, None, seed=seed, chain_id_offset=off, log_accepted=o_acc.data_ptr(), log_theta=o_th.data_ptr())
+        torch.cuda.synchronize()
+        o_ms, _ = ochain.last_run_stats()
+        same = (o_acc == log_acc)
+        # chains whose accept decisions all agree took the same path: their states differ by the arithmetic alone
+        agree = same.all(dim=0)
+        dth = (o_th - log_th).abs().amax(dim=2)[:, agree]
+        scale = log_th.abs().amax().item()
+        other = {"rank_update": "fp64" if oru == _lib.RANK_UPDATE_FP64 else "int8", "value": C * steps / (o_ms * 1e-3), "unit": UNIT,
+                 "ms_per_step": o_ms / steps, "accept_decisions_equal": float(same.float().mean().item()),
+                 "chains_with_identical_decisions": int(agree.sum().item()),
+                 "max_abs_theta_diff_on_those": float(dth.max().item()) if dth.numel() else None, "theta_scale": scale,
+                 "note": "same seed, same chains, the other arithmetic of the rank update; states compared after every one of the K steps"}
+        del o_th, o_acc
+        ochain.close(); opt_.close(); opm_.close()
 
     # ---- end-of-run exchange through the library's own NCCL entry points (icp_comm_*; the only collectives, not on the
     # per-sample path): all-gather of the FULL chain logs of the timed steps and all-reduce of the posterior variability
@@ -478,6 +509,31 @@ def run_gpu(args):
                     "share_of_step": shares.get("posterior_build"), "top_kernel_by_time": top,
                     "note": "achieved / frac count the flops actually executed (symmetry + constant Gram term exploited); "
                             "*_algorithmic count the reference's flops per posterior (SURVEY 8d)"}
+        if ru == _lib.RANK_UPDATE_INT8:
+            i8_peak = ctx.i8_peak()
+            # executed on the INT8 tensor cores per chain-posterior: ceil(n / 32) steps x (3 | 1) K blocks of 32 rows x ten digit
+            # pair products of 128 x 112 x 32 (issued as four 128 x 224 and two 128 x 112 MMAs)
+            nst = (n_obs + 31) // 32
+            ops_exec = 0.5 * (3 + 1) * nst * 10 * 2.0 * 128 * 112 * 32
+            i8_hw = ops_exec * C / (pb_ms * 1e-3) / 1e12 if pb_ms > 0 else 0.0
+            roofline = {"bound": "tensor", "pipe": "5th-generation tensor cores: tcgen05.mma kind::i8, INT32 accumulators in TMEM (SASS UTCIMMA / LDTM)",
+                        "kernel": "k_rank_update_i8<3|1> (rank update M = I + A^T A, b = A^T y by split-integer emulation of the FP64 product: "
+                                  "four balanced base-256 digits, ten digit-pair products, exact INT32 accumulation)",
+                        "achieved": i8_hw, "peak": i8_peak, "unit": "TFLOP/s",
+                        "frac": i8_hw / i8_peak if i8_peak else None,
+                        "achieved_algorithmic": pb_tflops,
+                        "frac_algorithmic_of_fp64_tensor_peak": pb_tflops / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
+                        "peak_bf16_dense_measured": peaks.get("bf16_tflops") or peaks.get("bf16_dense_tflops"),
+                        "traffic": None,
+                        "peak_source": "INT8 tensor-core rate of the same MMA tile (128 x 112 x 32, operands in shared memory) measured live on this "
+                                       "GPU with 2 CTAs / SM (icp_debug_i8_gram); MEASURED_PEAKS.json holds bf16, not INT8; achieved / peak are "
+                                       "integer tera-operations per second",
+                        "flops_per_launch": flops_post * C, "executed_int8_ops_per_launch": ops_exec * C, "avg_launch_ms": pb_ms,
+                        "share_of_step": shares.get("posterior_build"), "top_kernel_by_time": top,
+                        "note": "achieved / frac count the INT8 operations the tensor cores execute (ten digit pairs of the full 128 x 112 tile); "
+                                "achieved_algorithmic counts the reference's FP64 flops per posterior (SURVEY 8d). The kernel is bound by "
+                                "the FP64 whitening + digit extraction in its converter warps and by shared-memory bandwidth (staging ring + "
+                                "MMA operands), not by the tensor pipe: profiles/r2_i8_rank_update.md"}
         # ---- BASELINE.json configs[0] shape: ONE chain, fixed seed - latency-bound by construction: steps/s of
         # the device-resident loop with a single resident chain, next to the 1-core CPU port below -------------------
         sc_steps = 300
@@ -495,12 +551,13 @@ def run_gpu(args):
         cb_rate, cb_dt, _ = oracle_chain_rate(m, tv, tc, ids, eids, tp, 1, args.cpu_steps, 1, closed_form=False)
         opt_rate, opt_dt, _ = oracle_chain_rate(m, tv, tc, ids, eids, tp, 1, args.cpu_steps * 20, 1, closed_form=True)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
-                "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 (rank update of the posterior: INT8 tensor-core emulation of the FP64 product, 1e-8)" if ru == _lib.RANK_UPDATE_INT8 else "f64",
                 "data": "synthetic",
                 "config": {"workload": "femur GPMM-100 twin (N=1622,T=3240,K=101), config-1 ICP mixture (0.45 target-sampling + 0.45 "
                                        "model-sampling ICP n=202, 0.1 random walk) + prior x Gaussian-point(sd 2, 404 pts) evaluator, "
                                        "independent random-init chains batched per GPU",
-                           "chains_per_gpu": C, "samples_per_step": world * C, "n_icp_points": int(len(ids)), "n_eval_points": int(len(eids)),
+                           "rank_update": args.rank_update, "chains_per_gpu": C, "samples_per_step": world * C, "n_icp_points": int(len(ids)), "n_eval_points": int(len(eids)),
                            "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
                            "l2_policy": "per-step working set (posteriors 4x%.0f MB + meshes) exceeds L2" % (C * 104 * 104 * 8 / 1e6)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e_steps,
@@ -509,7 +566,7 @@ def run_gpu(args):
                 "clocks": clocks.summary(), "roofline": roofline, "roofline_cholesky": roof_chol, "roofline_closest_point": roof_cp, "closest_point": cp,
                 "kernel_shares": shares, "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items() if v["launches"]},
                 "fp64_peak": fp64, "l2_read_gbs": l2_gbs, "gather_ms": gather_ms, "gather": gather, "single_chain": single_chain,
-                "sustained": sustained, "per_call_api": per_call,
+                "sustained": sustained, "other_rank_update": other, "per_call_api": per_call,
                 "cpu_baseline": {"value": cb_rate, "unit": UNIT, "cores": 1, "kind": "port",
                                  "sample": f"1 chain x {args.cpu_steps} MH steps of the same workload, oracle in the reference's structure, 1 thread ({cb_dt:.1f} s); host has {cores} cores",
                                  "linear_algebra": blas},
@@ -551,6 +608,8 @@ def main():
     ap.add_argument("--chains", type=int, default=2368, help="chains per GPU (16 x 148 SMs)")
     ap.add_argument("--cpu-steps", type=int, default=120, help="MH steps of the cpu_baseline sample")
     ap.add_argument("--sustain-steps", type=int, default=2000, help="steps of the sustained-load arm (0 = skip)")
+    ap.add_argument("--rank-update", default="int8", choices=["int8", "fp64"],
+                    help="arithmetic of the posterior's rank update: INT8 tensor cores (tcgen05; default) or the FP64 tensor pipe")
     ap.add_argument("--ref-steps", type=int, default=12, help="MH steps per chain and bench step of --impl reference")
     args = ap.parse_args()
     if args.warmup < 1:

@@ -35,6 +35,14 @@ class Context:
         check(self.lib.icp_debug_fp64_peak(self.h, dptr(out)), self.h)
         return {"dfma_tflops": float(out[0]), "dmma_tflops": float(out[1])}
 
+    def i8_peak(self, ctas=296, iters=400):
+        """INT8 tensor-core TOP/s of the rank update's MMA tile (tcgen05.mma kind::i8, 128 x 112 x 32, operands in shared
+        memory, accumulator in TMEM), `ctas` CTAs each running `iters` passes over a 608-row image (icp_debug_i8_gram)."""
+        a = np.ones((608, 128), np.int8)
+        ms = C.c_double(0)
+        check(self.lib.icp_debug_i8_gram(self.h, 608, a.ctypes.data, None, int(iters), int(ctas), C.byref(ms)), self.h)
+        return 2.0 * 128 * 112 * 608 * iters * ctas / (ms.value * 1e-3) / 1e12
+
     def l2_bandwidth(self, working_set_bytes=32 << 20):
         """GB/s of L2 -> SM reads over an L2-resident working set (icp_debug_l2_bandwidth)."""
         out = C.c_double(0)
