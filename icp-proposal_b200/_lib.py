@@ -53,6 +53,11 @@ class KernelTerm(C.Structure):
     _fields_ = [("scale", C.c_double), ("sigma", C.c_double), ("A", C.c_double * 9)]
 
 
+class FaceKernel(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("level", C.c_int32 * 8), ("scale", C.c_double * 8), ("symmetric_weight", C.c_double),
+                ("plain_weight", C.c_double)]
+
+
 class ChainIO(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("chain_id_offset", C.c_uint64), ("u_comp", C.c_void_p), ("z", C.c_void_p),
                 ("u_acc", C.c_void_p), ("log_component", C.c_void_p), ("log_accepted", C.c_void_p),
@@ -98,6 +103,8 @@ _SIGS = {
     "icp_gpmm_kernel_matrix": [_h, C.c_int32, _dp, C.c_int32, _dp, C.POINTER(KernelTerm), C.c_int32, _dp],
     "icp_gpmm_eigen_psd": [_h, C.c_int32, _dp, C.c_int32, _dp, _dp],
     "icp_gpmm_nystrom_extend": [_h, C.c_int32, _dp, C.c_int32, _dp, C.POINTER(KernelTerm), C.c_int32, C.c_int32, _dp, _dp, _dp, _dp],
+    "icp_gpmm_face_kernel_matrix": [_h, C.c_int32, _dp, _dp, C.c_int32, _dp, _dp, _dp, C.POINTER(FaceKernel), _dp],
+    "icp_gpmm_face_nystrom_extend": [_h, C.c_int32, _dp, _dp, C.c_int32, _dp, _dp, _dp, C.POINTER(FaceKernel), C.c_int32, _dp, _dp, _dp, _dp],
     "icp_jsonlog_open": [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(C.c_char_p), C.POINTER(_h)],
     "icp_jsonlog_append": [_h, C.c_int32, C.c_int32, C.c_int32, _ip, _bp, _dp, _dp],
     "icp_jsonlog_close": [_h],

@@ -636,14 +636,53 @@ def femurKernel(referencePoints):
         DiagonalKernel3D(GaussianKernel3D(10), 3) * 3.0
 
 
+class FaceKernel:
+    """apps/bfm/FaceKernel.scala:58-104: SpatiallyVaryingMultiscaleKernel (order-3 B-spline kernels on the levels -6..-2 with
+    the scales 128, 64, 32, 10, 4, weighted by the face mask's smoothed regions) under the symmetrisation about x = 0,
+    0.7 symmetric + 0.3 plain. `regionWeights(level, points) -> weights` plays FaceMask.computeSmoothedRegions (the mask is
+    BFM data that is not part of the reference checkout); None = no mask."""
+
+    levelsAndScales = ((-6, 128.0), (-5, 64.0), (-4, 32.0), (-3, 10.0), (-2, 4.0))
+
+    def __init__(self, regionWeights=None, levelsAndScales=None, symmetricWeight=0.7, plainWeight=0.3):
+        self.regionWeights = regionWeights
+        if levelsAndScales is not None:
+            self.levelsAndScales = tuple(levelsAndScales)
+        self.symmetricWeight, self.plainWeight = symmetricWeight, plainWeight
+
+    @property
+    def levels(self):
+        return [l for l, _ in self.levelsAndScales]
+
+    @property
+    def scales(self):
+        return [s for _, s in self.levelsAndScales]
+
+    def weights(self, points, mirrored=False):
+        if self.regionWeights is None:
+            return None
+        p = np.asarray(points, float).reshape(-1, 3)
+        if mirrored:
+            p = p * np.array([-1.0, 1.0, 1.0])
+        return np.stack([np.asarray(self.regionWeights(l, p), float) for l in self.levels])
+
+    def matrix(self, ctx, x, y):
+        return core.gpmm_face_kernel_matrix(ctx, x, y, self.levels, self.scales, self.symmetricWeight, self.plainWeight,
+                                            self.weights(x), self.weights(y), self.weights(y, True))
+
+
 class LowRankGaussianProcess:
     @staticmethod
-    def approximateGPNystrom(ctx: core.Context, kernel: MatrixValuedKernel, points, nystromPoints, numBasisFunctions: int):
+    def approximateGPNystrom(ctx: core.Context, kernel, points, nystromPoints, numBasisFunctions: int):
         """Scalismo LowRankGaussianProcess.approximateGPNystrom as CreateGPModel.scala:86 calls it, every step on the device:
         kernel matrix of the Nystrom points, its leading eigenpairs (one-sided Jacobi), Nystrom extension to every model
         point. Returns (basis 3N x K, variance K) = pcaBasis / pcaVariance of the StatisticalMeshModel; eigenvector signs:
         largest-magnitude entry positive."""
         nys = np.asarray(nystromPoints, float).reshape(-1, 3)
+        if isinstance(kernel, FaceKernel):
+            w, v = core.gpmm_eigen_psd(ctx, kernel.matrix(ctx, nys, nys), numBasisFunctions)
+            return core.gpmm_face_nystrom_extend(ctx, points, nys, kernel.levels, kernel.scales, v, w, kernel.symmetricWeight,
+                                                 kernel.plainWeight, kernel.weights(points), kernel.weights(nys), kernel.weights(nys, True))
         kmm = core.gpmm_kernel_matrix(ctx, nys, nys, kernel.terms)
         w, v = core.gpmm_eigen_psd(ctx, kmm, numBasisFunctions)
         return core.gpmm_nystrom_extend(ctx, points, nys, kernel.terms, v, w)

@@ -335,6 +335,50 @@ def gpmm_nystrom_extend(ctx: "Context", pts, nys_pts, terms, V, w):
     return basis, var
 
 
+def _face_kernel(levels, scales, symmetric_weight, plain_weight):
+    fk = _lib.FaceKernel()
+    fk.n_levels = len(levels)
+    for i, (l, sc) in enumerate(zip(levels, scales)):
+        fk.level[i], fk.scale[i] = int(l), float(sc)
+    fk.symmetric_weight, fk.plain_weight = float(symmetric_weight), float(plain_weight)
+    return fk
+
+
+def _opt_weights(w, n_levels, n):
+    if w is None:
+        return None, None
+    w = f64(w)
+    if w.shape != (n_levels, n):
+        raise ValueError("region weights must be n_levels x n_points")
+    return w, dptr(w)
+
+
+def gpmm_face_kernel_matrix(ctx: "Context", x, y, levels, scales, symmetric_weight=0.7, plain_weight=0.3, wx=None, wy=None, wy_mirror=None):
+    """icp_gpmm_face_kernel_matrix: (3 nx) x (3 ny) matrix of the symmetrised multiscale B-spline kernel (apps/bfm/FaceKernel.scala)."""
+    x, y = f64(x).reshape(-1, 3), f64(y).reshape(-1, 3)
+    out = np.empty((3 * len(x), 3 * len(y)))
+    fk = _face_kernel(levels, scales, symmetric_weight, plain_weight)
+    (a, pa), (b, pb), (c, pc) = _opt_weights(wx, len(levels), len(x)), _opt_weights(wy, len(levels), len(y)), _opt_weights(wy_mirror, len(levels), len(y))
+    check(ctx.lib.icp_gpmm_face_kernel_matrix(ctx.h, len(x), dptr(x), pa, len(y), dptr(y), pb, pc, C.byref(fk), dptr(out)), ctx.h)
+    return out
+
+
+def gpmm_face_nystrom_extend(ctx: "Context", pts, nys_pts, levels, scales, V, w, symmetric_weight=0.7, plain_weight=0.3, w_pts=None,
+                             w_nys=None, w_nys_mirror=None):
+    """icp_gpmm_face_nystrom_extend: (basis 3N x rank, variance rank) for the face kernel."""
+    pts, nys = f64(pts).reshape(-1, 3), f64(nys_pts).reshape(-1, 3)
+    V, w = f64(V), f64(w)
+    rank = len(w)
+    if V.shape != (3 * len(nys), rank):
+        raise ValueError("V must be (3 m) x rank")
+    basis, var = np.empty((3 * len(pts), rank)), np.empty(rank)
+    fk = _face_kernel(levels, scales, symmetric_weight, plain_weight)
+    (a, pa), (b, pb), (c, pc) = _opt_weights(w_pts, len(levels), len(pts)), _opt_weights(w_nys, len(levels), len(nys)), _opt_weights(w_nys_mirror, len(levels), len(nys))
+    check(ctx.lib.icp_gpmm_face_nystrom_extend(ctx.h, len(pts), dptr(pts), pa, len(nys), dptr(nys), pb, pc, C.byref(fk), rank, dptr(V), dptr(w),
+                                               dptr(basis), dptr(var)), ctx.h)
+    return basis, var
+
+
 def posterior_variability(model: Model, thetas, sum_normals=True, theta_ref=None):
     """icp_posterior_variability: dict(mean N x 3, cov N x 3 x 3, total_variance N, normal_variance N)."""
     th, s = model._theta(thetas)

@@ -37,14 +37,63 @@ __device__ __forceinline__ void kernel_block(const KernelTerms &kt, double dx, d
     }
 }
 
+struct GaussSpec {
+    KernelTerms kt;
+    __device__ __forceinline__ void block(int, int, double px, double py, double pz, double qx, double qy, double qz, double (&b)[9]) const {
+        kernel_block(kt, px - qx, py - qy, pz - qz, b);
+    }
+};
+
+// ---- the face kernel of apps/bfm/FaceKernel.scala --------------------------------------------------------------------
+// SpatiallyVaryingMultiscaleKernel (:26-55): k(x, y) = sum_l scale_l w_l(x) w_l(y) B3(2^level_l x, 2^level_l y) I_3 with the
+// order-3 B-spline kernel of Scalismo's BSplineKernel[_3D](order = 3, scale = 0) [S-recall]:
+//     B3(a, b) = prod_d sum_k beta3(a_d - k) beta3(b_d - k),   k over the integers with both factors non-zero,
+// and the symmetrisation about the plane x = 0 of FaceKernel (:58-100):
+//     k_face(x, y) = 0.7 (I k(x, y) + Ibar k(x, ybar)) + 0.3 k(x, y),   ybar = (-y_x, y_y, y_z), Ibar = diag(-1, 1, 1).
+// The region weights w_l come from the face mask (FaceMask.computeSmoothedRegions, data that is not part of the reference
+// checkout): the caller passes them per level and point, for y also at the mirrored points.
+constexpr int kMaxFaceLevels = 8;
+struct FaceSpec {
+    int n, nx, ny;
+    double mul[kMaxFaceLevels], scale[kMaxFaceLevels];     // 2^level, LevelWithScale.scale
+    double sym, plain;
+    const double *wx, *wy, *wyb;                           // [n][nx], [n][ny], [n][ny] or null (= 1)
+    static __device__ __forceinline__ double beta3(double t) {
+        t = fabs(t);
+        if (t >= 2.0) return 0.0;
+        if (t >= 1.0) { const double u = 2.0 - t; return u * u * u * (1.0 / 6.0); }
+        return 2.0 / 3.0 - t * t + 0.5 * t * t * t;
+    }
+    static __device__ __forceinline__ double lattice_sum(double a, double b) {
+        const int kl = (int)ceil(fmax(a, b) - 2.0), ku = (int)floor(fmin(a, b) + 2.0);
+        double s = 0.0;
+        for (int k = kl; k <= ku; k++) s += beta3(a - (double)k) * beta3(b - (double)k);
+        return s;
+    }
+    __device__ __forceinline__ void block(int i, int j, double px, double py, double pz, double qx, double qy, double qz, double (&b)[9]) const {
+        double k = 0.0, kb = 0.0;
+        for (int l = 0; l < n; l++) {
+            const double c = mul[l], wi = wx ? wx[(size_t)l * nx + i] : 1.0;
+            const double syz = lattice_sum(c * py, c * qy) * lattice_sum(c * pz, c * qz) * scale[l] * wi;
+            k = fma(syz * (wy ? wy[(size_t)l * ny + j] : 1.0), lattice_sum(c * px, c * qx), k);
+            if (sym != 0.0) kb = fma(syz * (wyb ? wyb[(size_t)l * ny + j] : 1.0), lattice_sum(c * px, -c * qx), kb);
+        }
+#pragma unroll
+        for (int e = 0; e < 9; e++) b[e] = 0.0;
+        b[0] = sym * (k - kb) + plain * k;
+        b[4] = b[8] = sym * (k + kb) + plain * k;
+    }
+};
+
 // thread / (x_i, y_j) pair: writes the 3 x 3 block (j fastest: a warp writes three runs of 768 contiguous bytes)
-__global__ void __launch_bounds__(256) k_kernel_matrix(KernelTerms kt, int nx, const double *__restrict__ x, int ny,
+template <class KS>
+__global__ void __launch_bounds__(256) k_kernel_matrix(KS kt, int nx, const double *__restrict__ x, int ny,
                                                        const double *__restrict__ y, double *__restrict__ out) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)nx * ny) return;
     const int i = (int)(g / ny), j = (int)(g % ny);
     double b[9];
-    kernel_block(kt, x[3 * i] - y[3 * j], x[3 * i + 1] - y[3 * j + 1], x[3 * i + 2] - y[3 * j + 2], b);
+    kt.block(i, j, x[3 * i], x[3 * i + 1], x[3 * i + 2], y[3 * j], y[3 * j + 1], y[3 * j + 2], b);
     const size_t ld = (size_t)3 * ny;
 #pragma unroll
     for (int r = 0; r < 3; r++)
@@ -56,7 +105,8 @@ __global__ void __launch_bounds__(256) k_kernel_matrix(KernelTerms kt, int nx, c
 // columns cg + 16 u. Per chunk of 16 Nystrom points the CTA first evaluates its 8 x 16 kernel blocks (one per thread, the
 // exp() is the expensive part and is done once), stages the 48 matching rows of V, then accumulates.
 constexpr int kNyV = 8, kNyY = 16, kNyCols = 14;   // 16 x 14 = 224 columns at most
-__global__ void __launch_bounds__(128) k_nystrom_extend(KernelTerms kt, int N, const double *__restrict__ pts, int m,
+template <class KS>
+__global__ void __launch_bounds__(128) k_nystrom_extend(KS kt, int N, const double *__restrict__ pts, int m,
                                                         const double *__restrict__ nys, int rank, const double *__restrict__ V,
                                                         const double *__restrict__ w, double *__restrict__ basis) {
     extern __shared__ double sm[];
@@ -75,7 +125,7 @@ __global__ void __launch_bounds__(128) k_nystrom_extend(KernelTerms kt, int N, c
         {   // this thread's block: model point v, Nystrom point y0 + cg
             const int j = y0 + cg;
             double b[9];
-            if (j < m) kernel_block(kt, px - nys[3 * j], py - nys[3 * j + 1], pz - nys[3 * j + 2], b);
+            if (j < m) kt.block(ic, j, px, py, pz, nys[3 * j], nys[3 * j + 1], nys[3 * j + 2], b);
             else {
 #pragma unroll
                 for (int k = 0; k < 9; k++) b[k] = 0.0;
@@ -234,6 +284,52 @@ static KernelTerms pack_terms(const icp_kernel_term *terms, int n_terms) {
 
 using namespace icp;
 
+template <class KS>
+static void run_kernel_matrix(icp_ctx ctx, const KS &ks, int nx, const double *d_x, int ny, const double *d_y, double *out) {
+    cudaStream_t s = ctx->stream;
+    const size_t total = (size_t)9 * nx * ny;
+    DevBuf<double> dout;
+    dout.alloc(total);
+    const long long pairs = (long long)nx * ny;
+    k_kernel_matrix<KS><<<(unsigned)((pairs + 255) / 256), 256, 0, s>>>(ks, nx, d_x, ny, d_y, dout.p);
+    ICP_CUDA(cudaGetLastError());
+    ICP_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * total, cudaMemcpyDeviceToHost, s));
+    ICP_CUDA(cudaStreamSynchronize(s));
+}
+
+template <class KS>
+static void run_nystrom_extend(icp_ctx ctx, const KS &ks, int N, const double *d_pts, int m, const double *d_nys, int rank, const double *V,
+                               const double *w, double *basis, double *variance) {
+    ICP_REQUIRE(rank >= 1 && rank <= 16 * kNyCols && rank <= 3 * m, "rank must be in [1, min(224, 3 m)]");
+    for (int k = 0; k < rank; k++) ICP_REQUIRE(w[k] > 0.0, "eigenvalues of the kernel matrix must be positive");
+    cudaStream_t s = ctx->stream;
+    DevBuf<double> dV, dw, dB;
+    dV.upload(V, (size_t)3 * m * rank, s);
+    dw.upload(w, rank, s);
+    dB.alloc((size_t)3 * N * rank);
+    const size_t smem = sizeof(double) * ((size_t)kNyV * kNyY * 9 + (size_t)3 * kNyY * rank);
+    ICP_CUDA(cudaFuncSetAttribute(k_nystrom_extend<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_nystrom_extend<KS><<<(N + kNyV - 1) / kNyV, 128, smem, s>>>(ks, N, d_pts, m, d_nys, rank, dV.p, dw.p, dB.p);
+    ICP_CUDA(cudaGetLastError());
+    ICP_CUDA(cudaMemcpyAsync(basis, dB.p, sizeof(double) * (size_t)3 * N * rank, cudaMemcpyDeviceToHost, s));
+    ICP_CUDA(cudaStreamSynchronize(s));
+    if (variance)
+        for (int k = 0; k < rank; k++) variance[k] = w[k] / m;
+}
+
+static FaceSpec pack_face(const icp_face_kernel *k, int nx, int ny) {
+    ICP_REQUIRE(k != nullptr && k->n_levels >= 1 && k->n_levels <= kMaxFaceLevels, "between 1 and 8 kernel levels");
+    ICP_REQUIRE(std::isfinite(k->symmetric_weight) && std::isfinite(k->plain_weight), "kernel weights must be finite");
+    FaceSpec f{};
+    f.n = k->n_levels; f.nx = nx; f.ny = ny; f.sym = k->symmetric_weight; f.plain = k->plain_weight;
+    for (int l = 0; l < k->n_levels; l++) {
+        ICP_REQUIRE(k->level[l] >= -60 && k->level[l] <= 60 && std::isfinite(k->scale[l]), "bad kernel level");
+        f.mul[l] = std::ldexp(1.0, k->level[l]);
+        f.scale[l] = k->scale[l];
+    }
+    return f;
+}
+
 extern "C" int32_t icp_gpmm_kernel_matrix(icp_ctx ctx, int32_t nx, const double *x, int32_t ny, const double *y,
                                           const icp_kernel_term *terms, int32_t n_terms, double *out) {
     icp_ctx _ctx = ctx;
@@ -241,18 +337,11 @@ extern "C" int32_t icp_gpmm_kernel_matrix(icp_ctx ctx, int32_t nx, const double 
         ICP_REQUIRE(_ctx != nullptr, "null handle");
         CtxLock lock(_ctx);
         ICP_REQUIRE(nx >= 1 && ny >= 1 && x && y && out, "bad point sets");
-        const KernelTerms kt = pack_terms(terms, n_terms);
-        cudaStream_t s = _ctx->stream;
-        DevBuf<double> dx, dy, dout;
-        dx.upload(x, (size_t)3 * nx, s);
-        dy.upload(y, (size_t)3 * ny, s);
-        const size_t total = (size_t)9 * nx * ny;
-        dout.alloc(total);
-        const long long pairs = (long long)nx * ny;
-        k_kernel_matrix<<<(unsigned)((pairs + 255) / 256), 256, 0, s>>>(kt, nx, dx.p, ny, dy.p, dout.p);
-        ICP_CUDA(cudaGetLastError());
-        ICP_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * total, cudaMemcpyDeviceToHost, s));
-        ICP_CUDA(cudaStreamSynchronize(s));
+        const GaussSpec ks{pack_terms(terms, n_terms)};
+        DevBuf<double> dx, dy;
+        dx.upload(x, (size_t)3 * nx, _ctx->stream);
+        dy.upload(y, (size_t)3 * ny, _ctx->stream);
+        run_kernel_matrix(_ctx, ks, nx, dx.p, ny, dy.p, out);
         return ICP_OK;
     } catch (...) {
         return translate_exception(_ctx);
@@ -267,24 +356,57 @@ extern "C" int32_t icp_gpmm_nystrom_extend(icp_ctx ctx, int32_t N, const double 
         ICP_REQUIRE(_ctx != nullptr, "null handle");
         CtxLock lock(_ctx);
         ICP_REQUIRE(N >= 1 && m >= 1 && pts && nys_pts && V && w && basis, "bad argument");
-        ICP_REQUIRE(rank >= 1 && rank <= 16 * kNyCols && rank <= 3 * m, "rank must be in [1, min(224, 3 m)]");
-        for (int k = 0; k < rank; k++) ICP_REQUIRE(w[k] > 0.0, "eigenvalues of the kernel matrix must be positive");
-        const KernelTerms kt = pack_terms(terms, n_terms);
+        const GaussSpec ks{pack_terms(terms, n_terms)};
+        DevBuf<double> dp, dn;
+        dp.upload(pts, (size_t)3 * N, _ctx->stream);
+        dn.upload(nys_pts, (size_t)3 * m, _ctx->stream);
+        run_nystrom_extend(_ctx, ks, N, dp.p, m, dn.p, rank, V, w, basis, variance);
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+extern "C" int32_t icp_gpmm_face_kernel_matrix(icp_ctx ctx, int32_t nx, const double *x, const double *wx, int32_t ny, const double *y,
+                                               const double *wy, const double *wy_mirror, const icp_face_kernel *kernel, double *out) {
+    icp_ctx _ctx = ctx;
+    try {
+        ICP_REQUIRE(_ctx != nullptr, "null handle");
+        CtxLock lock(_ctx);
+        ICP_REQUIRE(nx >= 1 && ny >= 1 && x && y && out, "bad point sets");
+        FaceSpec ks = pack_face(kernel, nx, ny);
         cudaStream_t s = _ctx->stream;
-        DevBuf<double> dp, dn, dV, dw, dB;
+        DevBuf<double> dx, dy, dwx, dwy, dwb;
+        dx.upload(x, (size_t)3 * nx, s);
+        dy.upload(y, (size_t)3 * ny, s);
+        if (wx) { dwx.upload(wx, (size_t)ks.n * nx, s); ks.wx = dwx.p; }
+        if (wy) { dwy.upload(wy, (size_t)ks.n * ny, s); ks.wy = dwy.p; }
+        if (wy_mirror) { dwb.upload(wy_mirror, (size_t)ks.n * ny, s); ks.wyb = dwb.p; }
+        run_kernel_matrix(_ctx, ks, nx, dx.p, ny, dy.p, out);
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+extern "C" int32_t icp_gpmm_face_nystrom_extend(icp_ctx ctx, int32_t N, const double *pts, const double *w_pts, int32_t m,
+                                                const double *nys_pts, const double *w_nys, const double *w_nys_mirror,
+                                                const icp_face_kernel *kernel, int32_t rank, const double *V, const double *w, double *basis,
+                                                double *variance) {
+    icp_ctx _ctx = ctx;
+    try {
+        ICP_REQUIRE(_ctx != nullptr, "null handle");
+        CtxLock lock(_ctx);
+        ICP_REQUIRE(N >= 1 && m >= 1 && pts && nys_pts && V && w && basis, "bad argument");
+        FaceSpec ks = pack_face(kernel, N, m);
+        cudaStream_t s = _ctx->stream;
+        DevBuf<double> dp, dn, dwx, dwy, dwb;
         dp.upload(pts, (size_t)3 * N, s);
         dn.upload(nys_pts, (size_t)3 * m, s);
-        dV.upload(V, (size_t)3 * m * rank, s);
-        dw.upload(w, rank, s);
-        dB.alloc((size_t)3 * N * rank);
-        const size_t smem = sizeof(double) * ((size_t)kNyV * kNyY * 9 + (size_t)3 * kNyY * rank);
-        ICP_CUDA(cudaFuncSetAttribute(k_nystrom_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_nystrom_extend<<<(N + kNyV - 1) / kNyV, 128, smem, s>>>(kt, N, dp.p, m, dn.p, rank, dV.p, dw.p, dB.p);
-        ICP_CUDA(cudaGetLastError());
-        ICP_CUDA(cudaMemcpyAsync(basis, dB.p, sizeof(double) * (size_t)3 * N * rank, cudaMemcpyDeviceToHost, s));
-        ICP_CUDA(cudaStreamSynchronize(s));
-        if (variance)
-            for (int k = 0; k < rank; k++) variance[k] = w[k] / m;
+        if (w_pts) { dwx.upload(w_pts, (size_t)ks.n * N, s); ks.wx = dwx.p; }
+        if (w_nys) { dwy.upload(w_nys, (size_t)ks.n * m, s); ks.wy = dwy.p; }
+        if (w_nys_mirror) { dwb.upload(w_nys_mirror, (size_t)ks.n * m, s); ks.wyb = dwb.p; }
+        run_nystrom_extend(_ctx, ks, N, dp.p, m, dn.p, rank, V, w, basis, variance);
         return ICP_OK;
     } catch (...) {
         return translate_exception(_ctx);

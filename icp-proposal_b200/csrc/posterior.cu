@@ -1013,10 +1013,21 @@ __global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, cons
         __syncthreads();
     }
     for (int bj = 0; bj < NB; bj++) {
-        if (bj > 0) {
+        // Left-looking update of block column bj and the factorisation of its diagonal block run side by side: warp 0 updates
+        // the diagonal block and the right-hand side and goes straight on to the 8 dependent pivots (every lane redundantly,
+        // so the rsqrt -> scale chain has no hand-offs), the other warps update the blocks below the diagonal meanwhile.
+        // One barrier per phase pair instead of two, and the pivot chain hides behind the DMMA updates.
+        double *D = A + pk_blk(bj, bj);
+        {
             const double *pb = A + pk_blk(bj, 0) + fr * 8;
             const int o0 = fc ^ sw, o1 = o0 ^ 4;
-            for (int bi = bj + warp; bi <= NB; bi += NT / 32) {
+            const int nwork = NT / 32 - 1;
+            // warp 0: bi = bj (diagonal) and bi = NB (right-hand side); warps 1..: bi = bj + warp, bj + warp + nwork, ..
+            for (int it = 0;; it++) {
+                int bi;
+                if (warp == 0) { if (it > 1) break; bi = it == 0 ? bj : NB; }
+                else { bi = bj + warp + it * nwork; if (bi >= NB) break; }
+                if (bj == 0) continue;      // nothing to subtract yet
                 double e0 = 0.0, e1 = 0.0;   // two accumulators halve the dependent DMMA chain
                 if (bi < NB) {
                     double *pc = A + pk_blk(bi, bj) + fr * 8 + ((2 * fc) ^ sw);
@@ -1041,13 +1052,9 @@ __global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, cons
                     if (fr == 0) *reinterpret_cast<double2 *>(yv + 8 * bj + 2 * fc) = make_double2(cc.x + e0, cc.y + e1);
                 }
             }
-            __syncthreads();
         }
-        // diagonal block: warp 0 factors it (every lane redundantly, so the rsqrt -> scale chain has no hand-offs) and
-        // publishes L_jj and the reciprocal pivots through shared memory. With four chains per SM the other warps'
-        // issue slots are worth more to the other chains than a redundant copy of this chain would be.
-        double *D = A + pk_blk(bj, bj);
         if (warp == 0) {
+            __syncwarp();
             double l[8][8], inv[8];
 #pragma unroll
             for (int i = 0; i < 8; i++)

@@ -386,6 +386,33 @@ int32_t icp_gpmm_nystrom_extend(icp_ctx ctx, int32_t N, const double *pts, int32
                                 const icp_kernel_term *terms, int32_t n_terms, int32_t rank, const double *V,
                                 const double *w, double *basis, double *variance);
 
+
+/* ---- (9b) the face kernel (apps/bfm/FaceKernel.scala) --------------------------------------------------------------- */
+/* SpatiallyVaryingMultiscaleKernel (:26-55) under FaceKernel's symmetrisation about the plane x = 0 (:58-100):
+ *   k(x, y)      = sum_l scale_l w_l(x) w_l(y) B3(2^level_l x, 2^level_l y) I_3,
+ *   B3(a, b)     = prod_d sum_k beta3(a_d - k) beta3(b_d - k)        (Scalismo BSplineKernel[_3D](order = 3, scale = 0))
+ *   k_face(x, y) = symmetric_weight (I k(x, y) + diag(-1, 1, 1) k(x, ybar)) + plain_weight k(x, y),  ybar = (-y_x, y_y, y_z)
+ * FaceKernel.scala:60-70 uses levels -6..-2 with scales 128, 64, 32, 10, 4 and the weights 0.7 / 0.3. symmetric_weight = 0
+ * evaluates the plain multiscale kernel. */
+typedef struct {
+    int32_t n_levels;          /* 1..8 */
+    int32_t level[8];          /* LevelWithScale.level */
+    double scale[8];           /* LevelWithScale.scale */
+    double symmetric_weight;   /* 0.7 */
+    double plain_weight;       /* 0.3 */
+} icp_face_kernel;
+/* out (3 nx) x (3 ny) row-major. Region weights of the face mask (FaceMask.computeSmoothedRegions, :33-35) per level and
+ * point: wx [n_levels][nx], wy [n_levels][ny], wy_mirror [n_levels][ny] = the weights at the mirrored points ybar; any of
+ * them NULL = 1 (no mask). */
+int32_t icp_gpmm_face_kernel_matrix(icp_ctx ctx, int32_t nx, const double *x, const double *wx, int32_t ny, const double *y,
+                                    const double *wy, const double *wy_mirror, const icp_face_kernel *kernel, double *out);
+/* icp_gpmm_nystrom_extend for the face kernel (the BFM-sized model of BASELINE config 5): w_pts [n_levels][N],
+ * w_nys / w_nys_mirror [n_levels][m] or NULL */
+int32_t icp_gpmm_face_nystrom_extend(icp_ctx ctx, int32_t N, const double *pts, const double *w_pts, int32_t m,
+                                     const double *nys_pts, const double *w_nys, const double *w_nys_mirror,
+                                     const icp_face_kernel *kernel, int32_t rank, const double *V, const double *w, double *basis,
+                                     double *variance);
+
 #ifdef __cplusplus
 }
 #endif

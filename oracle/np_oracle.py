@@ -303,6 +303,52 @@ def gauss_mixture_kernel(x, y, terms):
     return out
 
 
+def bspline3(t):
+    """Centred cardinal cubic B-spline, Scalismo BSpline.nthOrderBSpline(3) [S-recall]: support (-2, 2)."""
+    t = abs(float(t))
+    if t >= 2.0:
+        return 0.0
+    if t >= 1.0:
+        return (2.0 - t) ** 3 / 6.0
+    return 2.0 / 3.0 - t * t + 0.5 * t ** 3
+
+
+def bspline_kernel3d(a, b):
+    """Scalismo BSplineKernel[_3D](order = 3, scale = 0) [S-recall]: sum over the integer lattice of the products of the
+    tensor-product B-splines centred at the lattice points, evaluated at a and at b; factorises over the dimensions."""
+    out = 1.0
+    for d in range(3):
+        kl, ku = int(np.ceil(max(a[d], b[d]) - 2.0)), int(np.floor(min(a[d], b[d]) + 2.0))
+        out *= sum(bspline3(a[d] - k) * bspline3(b[d] - k) for k in range(kl, ku + 1))
+    return out
+
+
+def face_kernel(x, y, levels, scales, symmetric_weight=0.7, plain_weight=0.3, wx=None, wy=None, wy_mirror=None):
+    """apps/bfm/FaceKernel.scala:26-104, pair by pair: SpatiallyVaryingMultiscaleKernel k(x, y) = sum_l scale_l w_l(x) w_l(y)
+    B3(2^l x, 2^l y) I (:40-52) and FaceKernel = 0.7 symmetrize(k) + 0.3 k (:70), symmetrize(k)(x, y) = I k(x, y) +
+    diag(-1, 1, 1) k(x, ybar) (:83-95). -> (3 nx) x (3 ny)."""
+    x, y = np.asarray(x, float).reshape(-1, 3), np.asarray(y, float).reshape(-1, 3)
+    out = np.zeros((3 * len(x), 3 * len(y)))
+    ibar = np.diag([-1.0, 1.0, 1.0])
+
+    def k(xi, yj, i, j, wyy):
+        s = 0.0
+        for li, (level, scale) in enumerate(zip(levels, scales)):
+            c = 2.0 ** level
+            s += bspline_kernel3d(xi * c, yj * c) * scale * (1.0 if wx is None else wx[li][i]) * (1.0 if wyy is None else wyy[li][j])
+        return s
+
+    for i, xi in enumerate(x):
+        for j, yj in enumerate(y):
+            kk = k(xi, yj, i, j, wy)
+            blk = plain_weight * kk * np.eye(3)
+            if symmetric_weight != 0.0:
+                kb = k(xi, yj * np.array([-1.0, 1.0, 1.0]), i, j, wy_mirror)
+                blk = blk + symmetric_weight * (np.eye(3) * kk + ibar * kb)
+            out[3 * i:3 * i + 3, 3 * j:3 * j + 3] = blk
+    return out
+
+
 def nystrom_extend(kernel_nm, v, w):
     """[S-recall] LowRankGaussianProcess.approximateGPNystrom: with (w_i, v_i) the eigenpairs of the m-point kernel matrix,
     lambda_i = w_i / m and phi_i(x) = sqrt(m) / w_i * k(x, X_m) v_i. -> (basis, variance)."""

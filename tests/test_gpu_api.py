@@ -202,3 +202,41 @@ def test_gpmm_construction_matches_oracle(ctx, twin31):
     model.close()
     with pytest.raises(Exception):
         core.gpmm_nystrom_extend(ctx, ref, nys, kernel.terms, v, -w)          # non-positive eigenvalues are an error
+
+
+@pytest.mark.gpu
+def test_face_kernel_matches_oracle(ctx):
+    """SURVEY 8f rank 4, second kernel family: the symmetrised multiscale B-spline kernel of apps/bfm/FaceKernel.scala on the
+    device (icp_gpmm_face_kernel_matrix / icp_gpmm_face_nystrom_extend) against the pair-by-pair oracle, with and without
+    face-mask region weights, and the Nystrom model it yields."""
+    from oracle import np_oracle as npo
+    from icp_proposal_b200 import core
+    rng = np.random.default_rng(77)
+    levels, scales = api.FaceKernel().levels, api.FaceKernel().scales
+    assert levels == [-6, -5, -4, -3, -2] and scales == [128.0, 64.0, 32.0, 10.0, 4.0]            # FaceKernel.scala:60-65
+    x, y = rng.uniform(-90, 90, (40, 3)), rng.uniform(-90, 90, (23, 3))
+    y[:5] = x[:5] * np.array([-1.0, 1.0, 1.0])                                                        # mirrored partners
+    wx, wy, wyb = rng.uniform(0, 1, (5, 40)), rng.uniform(0, 1, (5, 23)), rng.uniform(0, 1, (5, 23))
+    for sym, plain, a, b, c in ((0.7, 0.3, None, None, None), (0.7, 0.3, wx, wy, wyb), (0.0, 1.0, wx, wy, None)):
+        got = core.gpmm_face_kernel_matrix(ctx, x, y, levels, scales, sym, plain, a, b, c)
+        want = npo.face_kernel(x, y, levels, scales, sym, plain, a, b, c)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-13 * np.abs(want).max())
+    # Nystrom model of a face-sized point cloud through the mirror (region weight = a smooth function of the position)
+    pts = rng.uniform(-80, 80, (300, 3))
+    nys = pts[::6]
+    region = lambda level, p: 0.5 + 0.5 * np.exp(-(p[:, 1] / (40.0 * 2.0 ** (level + 6))) ** 2)      # symmetric in x
+    fk = api.FaceKernel(region)
+    rank = 20
+    kmm = fk.matrix(ctx, nys, nys)
+    np.testing.assert_allclose(kmm, kmm.T, rtol=1e-11, atol=1e-12 * np.abs(kmm).max())
+    w, v = np.linalg.eigh(kmm)
+    order = np.argsort(w)[::-1][:rank]
+    w, v = w[order], v[:, order]
+    got_b, got_v = core.gpmm_face_nystrom_extend(ctx, pts, nys, levels, scales, v, w, 0.7, 0.3, fk.weights(pts), fk.weights(nys), fk.weights(nys, True))
+    kpn = npo.face_kernel(pts[:60], nys, levels, scales, 0.7, 0.3, fk.weights(pts[:60]), fk.weights(nys), fk.weights(nys, True))
+    want_b, want_v = npo.nystrom_extend(kpn, v, w)
+    np.testing.assert_allclose(got_v, want_v, rtol=1e-14)
+    np.testing.assert_allclose(got_b[:180], want_b, rtol=1e-9, atol=1e-12 * np.abs(want_b).max())
+    basis, var = api.LowRankGaussianProcess.approximateGPNystrom(ctx, fk, pts, nys, rank)
+    np.testing.assert_allclose(var, want_v, rtol=1e-9)
+    assert basis.shape == (900, rank) and np.isfinite(basis).all()

@@ -335,3 +335,42 @@ def test_golden_variability_and_femur_kernel(femur):
     # the host mirror builds the same base matrix from the reference points (up to the sign-free product d diag d^T)
     from icp_proposal_b200 import api
     np.testing.assert_allclose(api.femurKernel(femur["ref"]).terms[0][2], base, rtol=1e-9, atol=1e-12)
+
+
+def test_face_kernel_oracle_known_answers():
+    """apps/bfm/FaceKernel.scala restated (np_oracle.face_kernel): analytic known answers of the order-3 B-spline kernel, the
+    symmetrisation about x = 0 and positive semi-definiteness of the resulting kernel matrix."""
+    from oracle import np_oracle as npo
+    rng = np.random.default_rng(5)
+    # the cardinal cubic B-spline: partition of unity, unit integral, known values
+    assert npo.bspline3(0.0) == pytest.approx(2.0 / 3.0) and npo.bspline3(1.0) == pytest.approx(1.0 / 6.0) and npo.bspline3(2.0) == 0.0
+    for t in rng.uniform(-3, 3, 20):
+        assert sum(npo.bspline3(t - k) for k in range(-6, 7)) == pytest.approx(1.0, abs=1e-14)
+    # the lattice-sum kernel is symmetric, shift invariant by integers and vanishes beyond the joint support (|a - b| >= 4)
+    a, b = rng.uniform(-5, 5, 3), rng.uniform(-5, 5, 3)
+    assert npo.bspline_kernel3d(a, b) == pytest.approx(npo.bspline_kernel3d(b, a), rel=1e-14)
+    assert npo.bspline_kernel3d(a + 3.0, b + 3.0) == pytest.approx(npo.bspline_kernel3d(a, b), rel=1e-12)
+    assert npo.bspline_kernel3d(a, a + np.array([4.0, 0.0, 0.0])) == 0.0
+    # 1-D closed form at lattice points: sum_k beta(0 - k) beta(0 - k) = (2/3)^2 + 2 (1/6)^2
+    one_d = (2.0 / 3.0) ** 2 + 2.0 / 36.0
+    assert npo.bspline_kernel3d(np.zeros(3), np.zeros(3)) == pytest.approx(one_d ** 3, rel=1e-14)
+    # symmetrised kernel: mirrored point pairs are perfectly (anti-)correlated per axis: k_face(x, xbar) = diag(-1, 1, 1) k_face(x, x)
+    levels, scales = [-6, -5, -4, -3, -2], [128.0, 64.0, 32.0, 10.0, 4.0]
+    x = rng.uniform(-80, 80, (6, 3))
+    xbar = x * np.array([-1.0, 1.0, 1.0])
+    kxx = npo.face_kernel(x, x, levels, scales, 1.0, 0.0)
+    kxb = npo.face_kernel(x, xbar, levels, scales, 1.0, 0.0)
+    for i in range(len(x)):
+        np.testing.assert_allclose(kxb[3 * i:3 * i + 3, 3 * i:3 * i + 3], np.diag([-1.0, 1.0, 1.0]) @ kxx[3 * i:3 * i + 3, 3 * i:3 * i + 3], rtol=1e-12)
+    # the face kernel (0.7 symmetric + 0.3 plain) with region weights is a symmetric positive semi-definite matrix
+    pts = rng.uniform(-60, 60, (14, 3))
+    w = rng.uniform(0.2, 1.0, (5, 14))
+    wm = rng.uniform(0.2, 1.0, (5, 14))
+    plain = npo.face_kernel(pts, pts, levels, scales, 0.0, 1.0, w, w, None)
+    np.testing.assert_allclose(plain, plain.T, rtol=1e-13)
+    assert np.linalg.eigvalsh(plain).min() > -1e-9 * np.abs(plain).max()
+    # with mirror-consistent weights (w(ybar) = w(y)) the symmetrised kernel is symmetric PSD too
+    full = npo.face_kernel(pts, pts, levels, scales, 0.7, 0.3, w, w, w)
+    np.testing.assert_allclose(full, full.T, rtol=1e-12, atol=1e-12)
+    assert np.linalg.eigvalsh(full).min() > -1e-9 * np.abs(full).max()
+    assert np.abs(npo.face_kernel(pts, pts, levels, scales, 0.7, 0.3, w, w, wm) - full).max() > 0     # the mirrored weights matter
