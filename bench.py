@@ -524,7 +524,10 @@ def run_gpu(args):
                         "achieved_algorithmic": pb_tflops,
                         "frac_algorithmic_of_fp64_tensor_peak": pb_tflops / fp64["dmma_tflops"] if fp64["dmma_tflops"] else None,
                         "peak_bf16_dense_measured": peaks.get("bf16_tflops") or peaks.get("bf16_dense_tflops"),
-                        "traffic": None,
+                        "traffic": prof_const["rank_update_i8"]["dram_bytes_per_launch"] * C / prof_const["rank_update_i8"]["chains"],
+                        "traffic_source": prof_const["rank_update_i8"]["source"] + " (a PROFILE CONSTANT read from profiles/, scaled by C; not measured in this run)",
+                        "traffic_note": "algorithmic bytes per launch = C * (8 * 64 * 91 + 8 Kp) written (packed M, b) ~ 112 MB plus the "
+                                        "observation frames read (~ 48 MB); the basis rows (1.2 GB per launch) come from L2",
                         "peak_source": "INT8 tensor-core rate of the same MMA tile (128 x 112 x 32, operands in shared memory) measured live on this "
                                        "GPU with 2 CTAs / SM (icp_debug_i8_gram); MEASURED_PEAKS.json holds bf16, not INT8; achieved / peak are "
                                        "integer tera-operations per second",
