@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kRuThreads, 1) k_rank_update_i8(ModelDev m, Ob
 
     if (warp == kRuGatherWarp) {
         // ---------------- gather warp: raw stage R of the CTA's flattened (chain, stage) sequence ----------------
-        unsigned R = 0;
+        unsigned R = 0, slot = 0, gphase = 0;                  // stage counter, its ring slot and the parity of R / NRAW
         int c = blockIdx.x;
         int nrows = c < C ? (o.nrows ? min(o.nrows[c], nmax) : nmax) : 0;
         int nst = 2 * ((nrows + 31) >> 5), rs = 0;
@@ -354,9 +354,8 @@ __global__ void __launch_bounds__(kRuThreads, 1) k_rank_update_i8(ModelDev m, Ob
             }
             int vnext = -1;
             if (c2 < C && lane < kRuRawObs && rs2 * kRuRawObs + lane < nrows2) vnext = __ldg(o.vid + (size_t)c2 * nmax + rs2 * kRuRawObs + lane);
-            const unsigned slot = R % NRAW;
             I8T_MARK();
-            if (R >= (unsigned)NRAW) mbar_wait(&empty_raw[slot], ((R / NRAW) - 1) & 1);
+            if (R >= (unsigned)NRAW) mbar_wait(&empty_raw[slot], gphase ^ 1u);      // parity of use (R / NRAW) - 1
             I8T_ADD(7);
             const int g0 = rs * kRuRawObs, nob = max(0, min(kRuRawObs, nrows - g0));       // observation slots of this stage
             double *fr0 = frames + (size_t)slot * kRuRawObs * kRuFrameDoubles;
@@ -397,6 +396,8 @@ __global__ void __launch_bounds__(kRuThreads, 1) k_rank_update_i8(ModelDev m, Ob
             __syncwarp();
             I8T_ADD(8);
             R++;
+            if (++slot == (unsigned)NRAW) { slot = 0; gphase ^= 1u; }                   // (no integer division in the loops: R % NRAW and
+                                                                                        //  R / NRAW cost ~700 clocks per stage under contention)
             c = c2; rs = rs2; nrows = nrows2; nst = nst2; v = vnext;
         }
         I8T_FLUSH(lane == 0, 7, 8);
@@ -412,6 +413,10 @@ __global__ void __launch_bounds__(kRuThreads, 1) k_rank_update_i8(ModelDev m, Ob
         for (int k = 0; k < 8; k++) bacc[k] = 0.0;
         bool ovf = false;
         int pre_done = 0;                                             // the team's first step of this chain was converted early
+        // ring slot and use parity of the team's next raw stage R = 2 Sg + pass: the team converts every other 32-observation
+        // step, in order, so R advances by 1, 3, 1, 3, ... - kept incrementally, no integer division in the loop
+        unsigned rslot = (2u * (unsigned)h) % (unsigned)NRAW, rphase = ((2u * (unsigned)h) / (unsigned)NRAW) & 1u;
+        auto advance = [&](unsigned k) { rslot += k; while (rslot >= (unsigned)NRAW) { rslot -= (unsigned)NRAW; rphase ^= 1u; } };
         auto reduce_b = [&]() {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -428,10 +433,11 @@ __global__ void __launch_bounds__(kRuThreads, 1) k_rank_update_i8(ModelDev m, Ob
             const double lim = 1.152921504606846976e18;               // 2^60: |fmul F_d|^2 above it could leave |x| <= 2^30
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {
-                const unsigned R = 2 * Sg + pass, slot = R % NRAW;
+                const unsigned slot = rslot;
                 I8T_MARK();
-                mbar_wait(&full_raw[slot], (R / NRAW) & 1);
+                mbar_wait(&full_raw[slot], rphase);
                 I8T_ADD(1);
+                advance(pass == 0 ? 1u : 3u);
                 const double *fr = frames + ((size_t)slot * kRuRawObs + osl) * kRuFrameDoubles;
                 const bool valid = live && fr[12] != 0.0;
                 double f[12];
@@ -633,7 +639,7 @@ __global__ void __launch_bounds__(kRuThreads, 1) k_rank_update_i8(ModelDev m, Ob
                                     if (RPO == 1) val += s_gs[off + kk];
                                     vv[u] = bad ? NAN : val;
                                 }
-                                *reinterpret_cast<double2 *>(dst + k) = make_double2(vv[0], vv[1]);
+                                __stcs(reinterpret_cast<double2 *>(dst + k), make_double2(vv[0], vv[1]));
                             }
                         }
                     }

@@ -35,7 +35,7 @@ rc = lib.icp_debug_i8_timing(buf.ctypes.data, buf.size)
 assert rc == 0, rc
 t = buf.reshape(256, 16)[:148]
 names = ["CTA total", "converter: wait full_raw", "converter: wait empty_dig", "converter: convert + store", "converter: b reduce + barrier",
-         "mma: wait full_dig", "mma: issue", "gather: wait empty_raw", "gather: issue", "epilogue: wait acc_done", "epilogue: barrier after the tasks", "chains", "converter: LDS + release raw", "converter: proxy fence + arrive", "epilogue: warp 0 own tasks (fewest)", "epilogue: warp 3 own tasks (most tasks)"]
+         "mma: wait full_dig", "mma: issue", "gather: wait empty_raw", "gather: issue", "epilogue: wait acc_done", "epilogue: barrier after the tasks", "chains", "converter: LDS + release raw", "converter: proxy fence + arrive", "epilogue: warp 0 own tasks (fewest)", "converter warp 0: everything else (loop control, b reduction, b output)"]
 print(f"direction {a.direction}: median over 148 CTAs (p10 .. p90), SM clocks per CTA; per chain in brackets")
 ch = max(1.0, float(np.median(t[:, 11])))
 for i, nm in enumerate(names):
