@@ -1012,6 +1012,7 @@ __global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, cons
         }
         __syncthreads();
     }
+    ICP_FT(long long fph[5] = {0, 0, 0, 0, 0}; long long ftk = clock64();)
     for (int bj = 0; bj < NB; bj++) {
         // Left-looking update of block column bj and the factorisation of its diagonal block run side by side: warp 0 updates
         // the diagonal block and the right-hand side and goes straight on to the 8 dependent pivots (every lane redundantly,
@@ -1022,23 +1023,36 @@ __global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, cons
             const double *pb = A + pk_blk(bj, 0) + fr * 8;
             const int o0 = fc ^ sw, o1 = o0 ^ 4;
             const int nwork = NT / 32 - 1;
-            // warp 0: bi = bj (diagonal) and bi = NB (right-hand side); warps 1..: bi = bj + warp, bj + warp + nwork, ..
+            // warp 0: bi = bj (the diagonal block, then straight on to its factorisation); warps 1..: bi = bj + warp,
+            // bj + warp + nwork, ..; the right-hand side (bi = NB) goes to the last warp, which has the fewest blocks left
             for (int it = 0;; it++) {
                 int bi;
-                if (warp == 0) { if (it > 1) break; bi = it == 0 ? bj : NB; }
-                else { bi = bj + warp + it * nwork; if (bi >= NB) break; }
+                if (warp == 0) { if (it > 0) break; bi = bj; }
+                else {
+                    bi = bj + warp + it * nwork;
+                    if (bi >= NB) { if (warp != NT / 32 - 1 || bi >= NB + nwork) break; bi = NB; }
+                }
                 if (bj == 0) continue;      // nothing to subtract yet
                 double e0 = 0.0, e1 = 0.0;   // two accumulators halve the dependent DMMA chain
                 if (bi < NB) {
                     double *pc = A + pk_blk(bi, bj) + fr * 8 + ((2 * fc) ^ sw);
                     double2 cc = *reinterpret_cast<double2 *>(pc);
                     const double *pa = A + pk_blk(bi, 0) + fr * 8;
-#pragma unroll 4
-                    for (int p = 0; p < bj; p++) {
+                    // four independent accumulators: the dependent DMMA chain is a quarter of the 2 bj products
+                    double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
+                    int p = 0;
+#pragma unroll 2
+                    for (; p + 1 < bj; p += 2) {
+                        dmma_8x8x4(cc.x, cc.y, -pa[p * 64 + o0], pb[p * 64 + o0]);
+                        dmma_8x8x4(e0, e1, -pa[p * 64 + o1], pb[p * 64 + o1]);
+                        dmma_8x8x4(g0, g1, -pa[(p + 1) * 64 + o0], pb[(p + 1) * 64 + o0]);
+                        dmma_8x8x4(h0, h1, -pa[(p + 1) * 64 + o1], pb[(p + 1) * 64 + o1]);
+                    }
+                    if (p < bj) {
                         dmma_8x8x4(cc.x, cc.y, -pa[p * 64 + o0], pb[p * 64 + o0]);
                         dmma_8x8x4(e0, e1, -pa[p * 64 + o1], pb[p * 64 + o1]);
                     }
-                    cc.x += e0; cc.y += e1;
+                    cc.x += (e0 + g0) + h0; cc.y += (e1 + g1) + h1;
                     *reinterpret_cast<double2 *>(pc) = cc;
                 } else {   // right-hand side: row 0 of the operand block is y, rows 1..7 are zero
                     double2 cc = make_double2(0.0, 0.0);
@@ -1053,6 +1067,7 @@ __global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, cons
                 }
             }
         }
+        ICP_FT({ const long long n_ = clock64(); fph[0] += n_ - ftk; ftk = n_; })
         if (warp == 0) {
             __syncwarp();
             double l[8][8], inv[8];
@@ -1091,7 +1106,9 @@ __global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, cons
                     }
             }
         }
+        ICP_FT({ const long long n_ = clock64(); fph[1] += n_ - ftk; ftk = n_; })
         __syncthreads();
+        ICP_FT({ const long long n_ = clock64(); fph[2] += n_ - ftk; ftk = n_; })
         if (8 * bj + 8 + tid <= Kp) {   // panel rows (one per thread); r == Kp is the right-hand side
             double l[8][8], inv[8];
 #pragma unroll
@@ -1117,8 +1134,11 @@ __global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, cons
                 for (int j = 0; j < 8; j++) row[j ^ rs] = x[j];
             }
         }
+        ICP_FT({ const long long n_ = clock64(); fph[3] += n_ - ftk; ftk = n_; })
         __syncthreads();
+        ICP_FT({ const long long n_ = clock64(); fph[4] += n_ - ftk; ftk = n_; })
     }
+    ICP_FT(if (tid == 0 && c < 8192) for (int k_ = 0; k_ < 5; k_++) g_ft[kFtStride * c + 1 + k_] = fph[k_];)
     // back substitution L^T x = y
     ICP_FT(const long long ftb = clock64(); if (tid == 0 && c < 8192) g_ft[kFtStride * c + 9] = ftb - ftf;)
     for (int k = tid; k < Kp; k += NT) xs[k] = yv[k];
