@@ -386,3 +386,31 @@ def test_int8_rank_update_chain_matches_oracle(ctx, femur):
         np.testing.assert_allclose(got["theta"][:, c], want["theta"], rtol=0, atol=1e-5)
     assert np.all(got["status"] == 0)
     chain.close(); ev.close(); model.close(); tgt.close()
+
+
+@pytest.mark.parametrize("rank,n_obs", [(20, 1), (20, 33), (110, 95), (105, 202)])
+def test_int8_rank_update_shapes_and_persistence(ctx, rank, n_obs):
+    """The persistent INT8 kernel at its edges: column groups that do not fill a converter pair (Kp = 24), the widest tile
+    (Kp = 112), one observation, observation counts off the 16 / 32 stage grid, and more chains than SMs (every CTA walks
+    several chains: ring slots, barrier parities and the early first step of the next chain carry over). Checked against the
+    FP64 tensor-pipe path of the same library on every chain."""
+    m = synth.femur_twin(rank=rank, n=600)
+    tv, tc, _ = synth.synthetic_target(m)
+    model, tgt = core.Model(ctx, m["ref"], m["cells"], m["basis"], m["variance"]), core.Target(ctx, tv, tc)
+    rng = np.random.default_rng(rank + n_obs)
+    C = 333
+    th = random_theta(m, rng, C, pose=True)
+    ids = np.sort(rng.choice(len(m["ref"]), n_obs, replace=False))
+    tp = tv[np.sort(rng.choice(len(tv), n_obs, replace=False))] + rng.normal(0, 0.2, (n_obs, 3))
+    for direction in (_lib.MODEL_SAMPLING, _lib.TARGET_SAMPLING):
+        gi = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, direction, True, ids, tp, rank_update=_lib.RANK_UPDATE_INT8)
+        gf = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, direction, True, ids, tp)
+        mu, M, n = gi.posterior(th)
+        mu64, M64, n64 = gf.posterior(th)
+        assert np.array_equal(n, n64)
+        scale = np.abs(M64).max(axis=(1, 2))
+        err = np.abs(M - M64).max(axis=(1, 2)) / scale
+        assert err.max() < 2e-8 and err.max() > 0.0, (direction, err.max())
+        assert (np.abs(mu - mu64).max(axis=1) <= 1e-6 * np.maximum(np.abs(mu64).max(axis=1), 1e-3)).all()
+        gi.close(); gf.close()
+    model.close(); tgt.close()
