@@ -1,6 +1,7 @@
 // api.cu - C ABI entry points of libicpcuda.so (include/icpcuda.h): contexts, handles, primitives,
 // the batched proposal / evaluator calls and the pipelines they share with the chain runner.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -17,9 +18,17 @@ static thread_local std::string g_thread_err;
 
 namespace icp {
 
+uint64_t next_alloc_id() {
+    static std::atomic<uint64_t> counter{0};
+    return ++counter;
+}
+
 void set_error(icp_ctx ctx, const std::string &msg) {
     g_thread_err = msg;
-    if (ctx) ctx->err = msg;
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        ctx->err = msg;
+    }
 }
 
 CtxLock::CtxLock(icp_ctx c) : lk(c->mu) {
@@ -59,6 +68,15 @@ int32_t translate_exception(icp_ctx ctx) {
     try {                           \
         ICP_REQUIRE(_ctx != nullptr, "null handle"); \
         CtxLock _lock(_ctx);
+// per-call entry point on a proposal / evaluator: `cs` is the leased call slot (scratch), `s` the stream the call runs on
+// and synchronises
+#define ICP_API_BEGIN_HANDLE(HandleT, h, self_contained)                   \
+    icp_ctx _ctx = (h) ? (h)->model->ctx : nullptr;                        \
+    try {                                                                  \
+        ICP_REQUIRE(_ctx != nullptr, "null handle");                       \
+        CallLease<HandleT> _lease(_ctx, (h), (self_contained));            \
+        HandleT::Call &cs = *_lease.call;                                  \
+        cudaStream_t s = _lease.stream;
 #define ICP_API_END                         \
         return ICP_OK;                      \
     } catch (...) {                         \
@@ -123,7 +141,11 @@ extern "C" int32_t icp_ctx_destroy(icp_ctx ctx) {
 
 extern "C" int32_t icp_last_error(icp_ctx ctx, char *buf, size_t n) {
     if (!buf || n == 0) return ICP_ERR_INVALID_ARGUMENT;
-    const std::string &s = ctx ? ctx->err : g_thread_err;
+    std::string s = g_thread_err;
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        s = ctx->err;
+    }
     size_t k = std::min(n - 1, s.size());
     memcpy(buf, s.data(), k);
     buf[k] = 0;
@@ -678,6 +700,7 @@ extern "C" int32_t icp_proposal_destroy(icp_proposal p) {
     try {
         CtxLock lock(_ctx);
         ICP_REQUIRE(p->refs == 0, "proposal is still used by a chain: destroy the chain first");
+        drain_calls(p);
         sync_stream(_ctx);
         p->model->refs--; p->target->refs--;
         delete p;
@@ -692,9 +715,31 @@ namespace icp {
 // currentMesh.pointSet.findClosestPoint for C chains: the vertex BVH refitted and walked in shared memory (default), the
 // FP32-screened brute force when the tree does not fit, the global-memory refit + traversal as the last resort.
 // ICPCUDA_NEAREST_VERTEX = tree | brute | bvh forces one of them (all three return the same answers).
+static const std::string &nearest_vertex_mode() {
+    static const std::string mode = getenv("ICPCUDA_NEAREST_VERTEX") ? getenv("ICPCUDA_NEAREST_VERTEX") : "";
+    return mode;
+}
+
+// true when nearest_model_vertex never falls through to the refit of the model's own vertex BVH (scratch shared by every
+// user of the model): the shared-memory tree or the brute-force kernel takes every call
+static bool nearest_model_vertex_self_contained(icp_model m) {
+    const std::string &mode = nearest_vertex_mode();
+    if ((mode.empty() || mode == "tree") && nearest_vertex_tree_fits(m->vert_bvh, m->N)) return true;
+    return mode != "bvh" && nearest_vertex_brute_fits(m->N);
+}
+
+// a per-call pipeline that only reads its model and target and writes the handle's own work buffers
+static bool proposal_self_contained(icp_proposal p) {
+    return p->prm.direction != ICP_TARGET_SAMPLING || nearest_model_vertex_self_contained(p->model);
+}
+static bool evaluator_self_contained(icp_evaluator e) {
+    // target -> model distances refit the model's triangle BVH (and the collective evaluator its vertex BVH)
+    return e->prm.kind == ICP_EVAL_ACCEPT_ALL || (e->prm.kind != ICP_EVAL_HAUSDORFF && e->prm.mode == ICP_MODEL_TO_TARGET);
+}
+
 void nearest_model_vertex(icp_model m, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, int *d_seed,
                           int *d_prim, cudaStream_t s) {
-    static const std::string mode = getenv("ICPCUDA_NEAREST_VERTEX") ? getenv("ICPCUDA_NEAREST_VERTEX") : "";
+    const std::string &mode = nearest_vertex_mode();
     if ((mode.empty() || mode == "tree") &&
         launch_nearest_vertex_tree(m->vert_bvh, m->N, C, d_X, nq, d_q, q_per_chain, d_seed, d_prim, nullptr, s))
         return;
@@ -810,25 +855,24 @@ static void strip_pad_vec(const std::vector<double> &src, int C, int K, int Kp, 
 }
 
 extern "C" int32_t icp_posterior(icp_proposal p, int32_t C, const double *theta, double *mu, double *M, int32_t *n_obs) {
-    ICP_API_BEGIN(p ? p->model->ctx : nullptr)
+    ICP_API_BEGIN_HANDLE(icp_proposal_s, p, p && proposal_self_contained(p))
     if (C == 0) return ICP_OK;
     icp_model m = p->model;
     const int K = m->K, Kp = m->Kp;
-    cudaStream_t s = _ctx->stream;
-    upload_theta(m, C, theta, p->s_theta, s);
-    DevBuf<double> dL, dmu;
-    dL.alloc((size_t)C * Kp * Kp);
-    dmu.alloc((size_t)C * Kp);
-    p->work.want_M = M != nullptr;
-    posterior_pipeline(p, C, p->s_theta.p, nullptr, p->work, dL.p, dmu.p, nullptr, s);
-    p->work.want_M = false;
+    upload_theta(m, C, theta, cs.s_theta, s);
+    DevBuf<double> &dL = cs.s_L, &dmu = cs.s_mu;   // kept on the call slot: cudaFree would synchronise the whole device
+    dL.ensure((size_t)C * Kp * Kp);
+    dmu.ensure((size_t)C * Kp);
+    cs.work.want_M = M != nullptr;
+    posterior_pipeline(p, C, cs.s_theta.p, nullptr, cs.work, dL.p, dmu.p, nullptr, s);
+    cs.work.want_M = false;
     std::vector<double> hmu((size_t)C * Kp), hM;
     std::vector<int> hn(C), hst(C);
     download(hmu.data(), dmu.p, hmu.size(), s);
-    if (M) { hM.resize((size_t)C * Kp * Kp); download(hM.data(), p->work.M.p, hM.size(), s); }
-    download(hn.data(), p->work.nobs.p, C, s);
-    download(hst.data(), p->work.status.p, C, s);
-    sync_stream(_ctx);
+    if (M) { hM.resize((size_t)C * Kp * Kp); download(hM.data(), cs.work.M.p, hM.size(), s); }
+    download(hn.data(), cs.work.nobs.p, C, s);
+    download(hst.data(), cs.work.status.p, C, s);
+    ICP_CUDA(cudaStreamSynchronize(s));
     if (mu) strip_pad_vec(hmu, C, K, Kp, mu);
     if (M)
         for (int c = 0; c < C; c++)
@@ -838,106 +882,244 @@ extern "C" int32_t icp_posterior(icp_proposal p, int32_t C, const double *theta,
     ICP_API_END
 }
 
-// Memoize(icpPosterior, 20) (NonRigidIcpProposal.scala:49): per-handle cache keyed by the bytes of theta.
-// Returns the cache slot of every chain; posteriors that are missing are computed in one batch.
-static std::vector<int> ensure_posteriors(icp_proposal p, int C, const double *theta_host, cudaStream_t s) {
-    icp_model m = p->model;
-    const int Kp = m->Kp, Lt = m->K + kTheta0;
-    int want = 32 + 4 * C;
-    if (p->cache_slots < want) {
-        p->cache_slots = want;
-        p->cache_map.clear();
-        p->slot_key.assign(want, std::string());
-        p->cache_L.alloc((size_t)want * Kp * Kp);
-        p->cache_mu.alloc((size_t)want * Kp);
-        if (p->prm.factor == ICP_FACTOR_SVD) p->cache_W.alloc((size_t)want * Kp * Kp);
-        p->cache_next = 0;
-    }
-    std::vector<int> slot(C, -1);
-    std::vector<char> pinned(p->cache_slots, 0);
-    std::vector<int> miss;
-    std::unordered_map<std::string, int> miss_key_slot;
-    for (int c = 0; c < C; c++) {
-        std::string key((const char *)(theta_host + (size_t)c * Lt), sizeof(double) * Lt);
-        auto it = p->cache_map.find(key);
-        if (it != p->cache_map.end()) { slot[c] = it->second; pinned[it->second] = 1; }
-    }
-    for (int c = 0; c < C; c++) {
-        if (slot[c] >= 0) continue;
-        std::string key((const char *)(theta_host + (size_t)c * Lt), sizeof(double) * Lt);
-        auto it = miss_key_slot.find(key);
-        if (it != miss_key_slot.end()) { slot[c] = it->second; continue; }
-        while (pinned[p->cache_next]) p->cache_next = (p->cache_next + 1) % p->cache_slots;
-        int sl = p->cache_next;
-        p->cache_next = (p->cache_next + 1) % p->cache_slots;
-        pinned[sl] = 1;
-        if (!p->slot_key[sl].empty()) p->cache_map.erase(p->slot_key[sl]);
-        p->slot_key[sl] = key;
-        p->cache_map[key] = sl;
-        miss_key_slot[key] = sl;
-        slot[c] = sl;
-        miss.push_back(c);
-    }
-    if (!miss.empty()) {
-        int nm = (int)miss.size();
-        std::vector<double> th((size_t)nm * Lt);
-        std::vector<int> out_slot(nm);
-        for (int i = 0; i < nm; i++) {
-            memcpy(&th[(size_t)i * Lt], theta_host + (size_t)miss[i] * Lt, sizeof(double) * Lt);
-            out_slot[i] = slot[miss[i]];
-        }
-        p->s_theta2.upload(th.data(), th.size(), s);
-        p->s_slot.upload(out_slot.data(), nm, s);
-        posterior_pipeline(p, nm, p->s_theta2.p, nullptr, p->work, p->cache_L.p, p->cache_mu.p, p->s_slot.p, s, nullptr,
-                           p->prm.factor == ICP_FACTOR_SVD ? p->cache_W.p : nullptr);
-        sync_stream(p->model->ctx);  // host staging vectors go out of scope
-    }
-    return slot;
+// ---- per-call entries as replayed graphs (run_call_graph) ----------------------------------------------------------
+static bool call_graphs_enabled() {
+    static const bool on = !(getenv("ICPCUDA_CALL_GRAPH") && getenv("ICPCUDA_CALL_GRAPH")[0] == '0');
+    return on;
+}
+enum CallKind : uint64_t { CALL_POSTERIOR = 1, CALL_PROPOSE, CALL_LOG_TRANSITION, CALL_EVAL };
+static uint64_t call_key(CallKind kind, int C) { return ((uint64_t)kind << 56) | (uint64_t)(uint32_t)C; }
+// every allocation a captured proposal call bakes in (DevBuf / PinnedBuf ids)
+static std::vector<uint64_t> proposal_call_ptrs(icp_proposal p, icp_proposal_s::Call &cs) {
+    const PosteriorWork &w = cs.work;
+    return {w.X.id, w.cp.id, w.d2.id, w.prim.id, w.seed.id, w.flags.id, w.vid.id, w.F.id, w.y.id, w.nobs.id, w.M.id, w.b.id, w.Mp.id,
+            w.status.id, w.svd_scratch.id, cs.s_theta.id, cs.s_theta2.id, cs.s_z.id, cs.s_out.id, cs.s_slot.id, cs.s_qslot.id,
+            cs.h_in.id, cs.h_out.id, cs.h_aux.id, p->cache_L.id, p->cache_mu.id, p->cache_W.id};
+}
+static std::vector<uint64_t> evaluator_call_ptrs(icp_evaluator_s::Call &cs) {
+    const EvalWork &w = cs.work;
+    return {w.X.id, w.cp_m2t.id, w.d2_m2t.id, w.cp_t2m.id, w.d2_t2m.id, w.prim.id, w.seed_m2t.id, w.seed_t2m.id, w.skip_m2t.id,
+            w.skip_t2m.id, cs.s_theta.id, cs.s_values.id, cs.s_status.id, cs.h_in.id, cs.h_out.id};
+}
+static void h2d(void *d, const void *h, size_t bytes, cudaStream_t s) {
+    if (bytes) ICP_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
+}
+static void d2h(void *h, const void *d, size_t bytes, cudaStream_t s) {
+    if (bytes) ICP_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
 }
 
+// Memoize(icpPosterior, 20) (NonRigidIcpProposal.scala:49): per-handle cache keyed by the bytes of theta, shared by the
+// concurrent calls on the handle (Scalismo's Memoize is shared between the fitting threads the same way).
+// PosteriorLease holds the cache slot of every chain of one call: slots are pinned (never evicted) until it goes out of
+// scope; posteriors that are missing are computed in one batch on the call's stream, and a call that hits a slot another
+// call is still computing waits for it.
+namespace {
+struct PosteriorLease {
+    icp_proposal p;
+    std::shared_lock<std::shared_mutex> rd;   // the slot arrays stay where they are
+    std::vector<int> slot;                    // [C]
+    std::vector<int> pinned;                  // distinct slots this call pinned
+    PosteriorLease(icp_proposal p_, icp_proposal_s::Call &cs, int C, const double *theta_host, cudaStream_t s, bool graph);
+    ~PosteriorLease() { unpin(); }
+    void unpin() {
+        if (pinned.empty()) return;
+        {
+            std::lock_guard<std::mutex> g(p->cache_lock);
+            for (int sl : pinned) p->slot_pin[sl]--;
+        }
+        pinned.clear();
+        p->cache_cv.notify_all();
+    }
+};
+
+PosteriorLease::PosteriorLease(icp_proposal p_, icp_proposal_s::Call &cs, int C, const double *theta_host, cudaStream_t s, bool graph)
+    : p(p_) {
+    icp_model m = p->model;
+    const int Kp = m->Kp, Lt = m->K + kTheta0;
+    // room for sixteen concurrent calls of this size plus the 20 states Memoize keeps
+    const int want = 32 + 4 * C + kMaxCallSlots * C;
+    rd = std::shared_lock<std::shared_mutex>(p->cache_rw);
+    while (p->cache_slots < want) {
+        rd.unlock();
+        {
+            std::unique_lock<std::shared_mutex> wr(p->cache_rw);   // no call in flight holds a slot now
+            if (p->cache_slots < want) {
+                p->cache_map.clear();
+                p->slot_key.assign(want, std::string());
+                p->slot_pin.assign(want, 0);
+                p->slot_ready.assign(want, 0);
+                p->cache_L.alloc((size_t)want * Kp * Kp);
+                p->cache_mu.alloc((size_t)want * Kp);
+                if (p->prm.factor == ICP_FACTOR_SVD) p->cache_W.alloc((size_t)want * Kp * Kp);
+                p->cache_next = 0;
+                p->cache_slots = want;
+            }
+        }
+        rd.lock();
+    }
+    std::vector<std::string> key(C);
+    for (int c = 0; c < C; c++) key[c].assign((const char *)(theta_host + (size_t)c * Lt), sizeof(double) * Lt);
+    slot.assign(C, -1);
+    std::vector<int> miss, wait_for;
+    {
+        std::unique_lock<std::mutex> g(p->cache_lock);
+        for (;;) {
+            // hits and distinct missing keys first, nothing is modified until every miss can have a slot
+            std::unordered_map<std::string, int> distinct_miss;
+            std::vector<char> mine(p->cache_slots, 0);
+            for (int c = 0; c < C; c++) {
+                auto it = p->cache_map.find(key[c]);
+                if (it != p->cache_map.end()) mine[it->second] = 1;
+                else distinct_miss.emplace(key[c], -1);
+            }
+            int free_slots = 0;
+            for (int sl = 0; sl < p->cache_slots; sl++) free_slots += (p->slot_pin[sl] == 0 && !mine[sl]);
+            if (free_slots < (int)distinct_miss.size()) { p->cache_cv.wait(g); continue; }   // holding nothing while waiting
+            for (int c = 0; c < C; c++) {
+                auto it = p->cache_map.find(key[c]);
+                if (it != p->cache_map.end()) {
+                    slot[c] = it->second;
+                    if (!p->slot_ready[slot[c]]) wait_for.push_back(c);   // another call is computing it
+                    continue;
+                }
+                int &sl = distinct_miss[key[c]];
+                if (sl < 0) {
+                    while (p->slot_pin[p->cache_next] != 0 || mine[p->cache_next]) p->cache_next = (p->cache_next + 1) % p->cache_slots;
+                    sl = p->cache_next;
+                    p->cache_next = (p->cache_next + 1) % p->cache_slots;
+                    mine[sl] = 1;
+                    if (!p->slot_key[sl].empty()) p->cache_map.erase(p->slot_key[sl]);
+                    p->slot_key[sl] = key[c];
+                    p->slot_ready[sl] = 0;
+                    miss.push_back(c);
+                }
+                slot[c] = sl;
+            }
+            // publish the new keys only now: the lookups above must not take this call's own misses for hits
+            for (int c : miss) p->cache_map[key[c]] = slot[c];
+            for (int sl = 0; sl < p->cache_slots; sl++)
+                if (mine[sl]) { p->slot_pin[sl]++; pinned.push_back(sl); }
+            break;
+        }
+    }
+    if (!miss.empty()) {
+        const int nm = (int)miss.size();
+        try {
+            cs.h_aux.ensure(sizeof(double) * (size_t)nm * Lt + sizeof(int) * (size_t)nm);
+            double *hth = reinterpret_cast<double *>(cs.h_aux.p);
+            int *hslot = reinterpret_cast<int *>(hth + (size_t)nm * Lt);
+            for (int i = 0; i < nm; i++) {
+                memcpy(hth + (size_t)i * Lt, theta_host + (size_t)miss[i] * Lt, sizeof(double) * Lt);
+                hslot[i] = slot[miss[i]];
+            }
+            cs.s_theta2.ensure((size_t)nm * Lt);
+            cs.s_slot.ensure(nm);
+            run_call_graph(cs, graph, call_key(CALL_POSTERIOR, nm), proposal_call_ptrs(p, cs), s, [&] {
+                h2d(cs.s_theta2.p, hth, sizeof(double) * (size_t)nm * Lt, s);
+                h2d(cs.s_slot.p, hslot, sizeof(int) * (size_t)nm, s);
+                posterior_pipeline(p, nm, cs.s_theta2.p, nullptr, cs.work, p->cache_L.p, p->cache_mu.p, cs.s_slot.p, s, nullptr,
+                                   p->prm.factor == ICP_FACTOR_SVD ? p->cache_W.p : nullptr);
+            });
+            ICP_CUDA(cudaStreamSynchronize(s));  // the slots are complete for every stream
+        } catch (...) {
+            {   // forget the keys, wake the calls waiting for these slots (they fail on the key check below)
+                std::lock_guard<std::mutex> g(p->cache_lock);
+                for (int c : miss) { p->cache_map.erase(key[c]); p->slot_key[slot[c]].clear(); p->slot_ready[slot[c]] = 1; }
+            }
+            p->cache_cv.notify_all();
+            unpin();
+            throw;
+        }
+        {
+            std::lock_guard<std::mutex> g(p->cache_lock);
+            for (int c : miss) p->slot_ready[slot[c]] = 1;
+        }
+        p->cache_cv.notify_all();
+    }
+    if (!wait_for.empty()) {
+        std::unique_lock<std::mutex> g(p->cache_lock);
+        for (int c : wait_for) {
+            p->cache_cv.wait(g, [&] { return p->slot_ready[slot[c]] != 0; });
+            if (p->slot_key[slot[c]] != key[c]) {
+                g.unlock();
+                unpin();
+                throw StatusError{ICP_ERR_CUDA, "the posterior this call waited for failed in a concurrent call"};
+            }
+        }
+    }
+}
+}  // namespace
+
 extern "C" int32_t icp_proposal_clear_cache(icp_proposal p) {
-    ICP_API_BEGIN(p ? p->model->ctx : nullptr)
-    p->cache_map.clear();
-    for (auto &k : p->slot_key) k.clear();
+    icp_ctx _ctx = p ? p->model->ctx : nullptr;
+    try {
+        ICP_REQUIRE(_ctx != nullptr, "null handle");
+        std::unique_lock<std::shared_mutex> wr(p->cache_rw);   // waits for the calls in flight
+        p->cache_map.clear();
+        for (auto &k : p->slot_key) k.clear();
     ICP_API_END
 }
 
 extern "C" int32_t icp_propose(icp_proposal p, int32_t C, const double *theta, const double *z, double *theta_out) {
-    ICP_API_BEGIN(p ? p->model->ctx : nullptr)
+    const bool self_contained = p && proposal_self_contained(p);
+    ICP_API_BEGIN_HANDLE(icp_proposal_s, p, self_contained)
     if (C == 0) return ICP_OK;
+    ICP_REQUIRE(C > 0, "C must be >= 0");
     icp_model m = p->model;
     ICP_REQUIRE(theta && z && theta_out, "null array");
-    cudaStream_t s = _ctx->stream;
+    const bool graph = self_contained && call_graphs_enabled();
     const int Lt = m->K + kTheta0;
-    std::vector<int> slot = ensure_posteriors(p, C, theta, s);
-    upload_theta(m, C, theta, p->s_theta, s);
-    p->s_z.upload(z, (size_t)C * m->K, s);
-    DevBuf<int> dslot;
-    dslot.upload(slot.data(), C, s);
-    p->s_out.ensure((size_t)C * Lt);
-    launch_propose(m->dev(), C, p->prm.step_length, p->s_theta.p, p->s_z.p, p->cache_L.p, p->cache_mu.p, dslot.p,
-                   p->s_out.p, s, p->prm.factor == ICP_FACTOR_SVD ? p->cache_W.p : nullptr);
-    download(theta_out, p->s_out.p, (size_t)C * Lt, s);
-    sync_stream(_ctx);
+    const size_t nth = (size_t)C * Lt, nz = (size_t)C * m->K;
+    PosteriorLease post(p, cs, C, theta, s, graph);
+    cs.h_in.ensure(sizeof(double) * (nth + nz) + sizeof(int) * (size_t)C);
+    cs.h_out.ensure(sizeof(double) * nth);
+    double *hth = reinterpret_cast<double *>(cs.h_in.p), *hz = hth + nth;
+    int *hslot = reinterpret_cast<int *>(hz + nz);
+    memcpy(hth, theta, sizeof(double) * nth);
+    memcpy(hz, z, sizeof(double) * nz);
+    memcpy(hslot, post.slot.data(), sizeof(int) * (size_t)C);
+    cs.s_theta.ensure(nth); cs.s_z.ensure(nz); cs.s_qslot.ensure(C); cs.s_out.ensure(nth);
+    run_call_graph(cs, graph, call_key(CALL_PROPOSE, C), proposal_call_ptrs(p, cs), s, [&] {
+        h2d(cs.s_theta.p, hth, sizeof(double) * nth, s);
+        h2d(cs.s_z.p, hz, sizeof(double) * nz, s);
+        h2d(cs.s_qslot.p, hslot, sizeof(int) * (size_t)C, s);
+        launch_propose(m->dev(), C, p->prm.step_length, cs.s_theta.p, cs.s_z.p, p->cache_L.p, p->cache_mu.p, cs.s_qslot.p,
+                       cs.s_out.p, s, p->prm.factor == ICP_FACTOR_SVD ? p->cache_W.p : nullptr);
+        d2h(cs.h_out.p, cs.s_out.p, sizeof(double) * nth, s);
+    });
+    ICP_CUDA(cudaStreamSynchronize(s));
+    memcpy(theta_out, cs.h_out.p, sizeof(double) * nth);
     ICP_API_END
 }
 
 extern "C" int32_t icp_log_transition(icp_proposal p, int32_t C, const double *from, const double *to, double *out) {
-    ICP_API_BEGIN(p ? p->model->ctx : nullptr)
+    const bool self_contained = p && proposal_self_contained(p);
+    ICP_API_BEGIN_HANDLE(icp_proposal_s, p, self_contained)
     if (C == 0) return ICP_OK;
+    ICP_REQUIRE(C > 0, "C must be >= 0");
     icp_model m = p->model;
     ICP_REQUIRE(from && to && out, "null array");
-    cudaStream_t s = _ctx->stream;
-    std::vector<int> slot = ensure_posteriors(p, C, from, s);
-    upload_theta(m, C, from, p->s_theta, s);
-    upload_theta(m, C, to, p->s_theta2, s);
-    DevBuf<int> dslot;
-    dslot.upload(slot.data(), C, s);
-    p->s_out.ensure((size_t)C);
-    launch_log_transition(C, m->K, m->Kp, p->prm.step_length, p->s_theta.p, p->s_theta2.p, p->cache_L.p, p->cache_mu.p,
-                          dslot.p, p->s_out.p, s);
-    download(out, p->s_out.p, C, s);
-    sync_stream(_ctx);
+    const bool graph = self_contained && call_graphs_enabled();
+    const size_t nth = (size_t)C * (m->K + kTheta0);
+    PosteriorLease post(p, cs, C, from, s, graph);
+    cs.h_in.ensure(sizeof(double) * 2 * nth + sizeof(int) * (size_t)C);
+    cs.h_out.ensure(sizeof(double) * (size_t)C);
+    double *hfrom = reinterpret_cast<double *>(cs.h_in.p), *hto = hfrom + nth;
+    int *hslot = reinterpret_cast<int *>(hto + nth);
+    memcpy(hfrom, from, sizeof(double) * nth);
+    memcpy(hto, to, sizeof(double) * nth);
+    memcpy(hslot, post.slot.data(), sizeof(int) * (size_t)C);
+    cs.s_theta.ensure(nth); cs.s_theta2.ensure(nth); cs.s_qslot.ensure(C); cs.s_out.ensure((size_t)C);
+    run_call_graph(cs, graph, call_key(CALL_LOG_TRANSITION, C), proposal_call_ptrs(p, cs), s, [&] {
+        h2d(cs.s_theta.p, hfrom, sizeof(double) * nth, s);
+        h2d(cs.s_theta2.p, hto, sizeof(double) * nth, s);
+        h2d(cs.s_qslot.p, hslot, sizeof(int) * (size_t)C, s);
+        launch_log_transition(C, m->K, m->Kp, p->prm.step_length, cs.s_theta.p, cs.s_theta2.p, p->cache_L.p, p->cache_mu.p,
+                              cs.s_qslot.p, cs.s_out.p, s);
+        d2h(cs.h_out.p, cs.s_out.p, sizeof(double) * (size_t)C, s);
+    });
+    ICP_CUDA(cudaStreamSynchronize(s));
+    memcpy(out, cs.h_out.p, sizeof(double) * (size_t)C);
     ICP_API_END
 }
 
@@ -1101,6 +1283,7 @@ extern "C" int32_t icp_evaluator_destroy(icp_evaluator e) {
     try {
         CtxLock lock(_ctx);
         ICP_REQUIRE(e->refs == 0, "evaluator is still used by a chain: destroy the chain first");
+        drain_calls(e);
         sync_stream(_ctx);
         e->model->refs--; e->target->refs--;
         delete e;
@@ -1180,17 +1363,30 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
 }  // namespace icp
 
 extern "C" int32_t icp_eval_log_value(icp_evaluator e, int32_t C, const double *theta, double *values, int32_t *status) {
-    ICP_API_BEGIN(e ? e->model->ctx : nullptr)
+    const bool self_contained = e && evaluator_self_contained(e);
+    ICP_API_BEGIN_HANDLE(icp_evaluator_s, e, self_contained)
     if (C == 0) return ICP_OK;
+    ICP_REQUIRE(C > 0 && theta != nullptr, "bad theta array");
     ICP_REQUIRE(values != nullptr, "values is null");
-    cudaStream_t s = _ctx->stream;
-    upload_theta(e->model, C, theta, e->s_theta, s);
-    e->s_values.ensure((size_t)3 * C);
-    e->s_status.ensure(C);
-    evaluator_pipeline(e, e->work, C, e->s_theta.p, nullptr, e->s_values.p, e->s_status.p, s);
-    download(values, e->s_values.p, (size_t)3 * C, s);
-    download(status, e->s_status.p, C, s);
-    sync_stream(_ctx);
+    const bool graph = self_contained && call_graphs_enabled();
+    const size_t nth = (size_t)C * (e->model->K + kTheta0);
+    cs.h_in.ensure(sizeof(double) * nth);
+    cs.h_out.ensure(sizeof(double) * 3 * (size_t)C + sizeof(int) * (size_t)C);
+    double *hval = reinterpret_cast<double *>(cs.h_out.p);
+    int *hst = reinterpret_cast<int *>(hval + 3 * (size_t)C);
+    memcpy(cs.h_in.p, theta, sizeof(double) * nth);
+    cs.s_theta.ensure(nth);
+    cs.s_values.ensure((size_t)3 * C);
+    cs.s_status.ensure(C);
+    run_call_graph(cs, graph, call_key(CALL_EVAL, C), evaluator_call_ptrs(cs), s, [&] {
+        h2d(cs.s_theta.p, cs.h_in.p, sizeof(double) * nth, s);
+        evaluator_pipeline(e, cs.work, C, cs.s_theta.p, nullptr, cs.s_values.p, cs.s_status.p, s);
+        d2h(hval, cs.s_values.p, sizeof(double) * 3 * (size_t)C, s);
+        d2h(hst, cs.s_status.p, sizeof(int) * (size_t)C, s);
+    });
+    ICP_CUDA(cudaStreamSynchronize(s));
+    memcpy(values, hval, sizeof(double) * 3 * (size_t)C);
+    if (status) memcpy(status, hst, sizeof(int) * (size_t)C);
     ICP_API_END
 }
 

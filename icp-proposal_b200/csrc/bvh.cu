@@ -644,11 +644,18 @@ __global__ void __launch_bounds__(256) k_nearest_vertex_tree(int n, const int *_
     }
 }
 
+bool nearest_vertex_tree_fits(const Bvh &b, int N) {
+    return b.prim_kind == 1 && b.n_levels > 0 && b.n == N && sizeof(float) * 6 * (size_t)(b.n - 1) <= 110 * 1024;
+}
+bool nearest_vertex_brute_fits(int N) {
+    return sizeof(double) * 3 * (size_t)((N + 1) & ~1) + sizeof(float) * 3 * (size_t)((N + 1) & ~1) <= 100 * 1024;
+}
+
 // false (nothing launched) when the tree does not fit shared memory or has no level schedule
 bool launch_nearest_vertex_tree(const Bvh &b, int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain,
                                 int *d_seed, int *d_prim, double *d_d2, cudaStream_t s) {
     size_t smem = sizeof(float) * 6 * (size_t)(b.n - 1);
-    if (b.prim_kind != 1 || b.n_levels <= 0 || b.n != N || smem > 110 * 1024 || C <= 0 || nq <= 0) return false;
+    if (!nearest_vertex_tree_fits(b, N) || C <= 0 || nq <= 0) return false;
     ProfScope _ps(ST_NEAREST_DYNAMIC, s);
     ICP_CUDA(cudaFuncSetAttribute(k_nearest_vertex_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_nearest_vertex_tree<<<C, 256, smem, s>>>(b.n, b.prim.p, b.children.p, b.order.p, b.level_off.p, b.n_levels, d_X, N, b.slack,
@@ -660,7 +667,7 @@ bool launch_nearest_vertex_tree(const Bvh &b, int N, int C, const double *d_X, i
 bool launch_nearest_vertex_brute(int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, double scale,
                                  int *d_prim, double *d_d2, cudaStream_t s) {
     size_t smem = sizeof(double) * 3 * (size_t)((N + 1) & ~1) + sizeof(float) * 3 * (size_t)((N + 1) & ~1);
-    if (smem > 100 * 1024 || C <= 0 || nq <= 0) return false;
+    if (!nearest_vertex_brute_fits(N) || C <= 0 || nq <= 0) return false;
     ProfScope _ps(ST_NEAREST_DYNAMIC, s);
     if (smem > 48 * 1024) ICP_CUDA(cudaFuncSetAttribute(k_nearest_vertex_brute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((nq + 128 * kBruteQ - 1) / (128 * kBruteQ)), C);

@@ -4,7 +4,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -44,16 +48,20 @@ struct StatusError {
 };
 
 // RAII device buffer (cudaMalloc on the current device)
+uint64_t next_alloc_id();   // api.cu: process-wide counter, never 0
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    uint64_t id = 0;   // unique per allocation (next_alloc_id): a cached graph compares ids, not addresses, so an allocation
+                       // that comes back at the same address after a free is still seen as new
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), id(o.id) { o.p = nullptr; o.n = 0; o.id = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; id = o.id; o.p = nullptr; o.n = 0; o.id = 0; }
         return *this;
     }
     ~DevBuf() { release(); }
@@ -61,6 +69,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
+        id = 0;
     }
     void alloc(size_t count) {
         release();
@@ -71,6 +80,7 @@ struct DevBuf {
             throw CudaError{e, __FILE__, __LINE__};
         }
         n = count;
+        id = next_alloc_id();
     }
     void ensure(size_t count) {
         if (count > n) alloc(count);
@@ -182,6 +192,9 @@ bool launch_nearest_vertex_tree(const Bvh &b, int N, int C, const double *d_X, i
                                 int *d_seed, int *d_prim, double *d_d2, cudaStream_t s);
 // brute-force nearest vertex of C small meshes X[C][N][3] (FP32 screening + exact FP64); returns false (nothing
 // launched) when N is too large for the shared-memory tile, in which case the caller uses the vertex BVH
+// the domains of the two kernels above (what launch_* checks before launching)
+bool nearest_vertex_tree_fits(const Bvh &b, int N);
+bool nearest_vertex_brute_fits(int N);
 bool launch_nearest_vertex_brute(int N, int C, const double *d_X, int64_t nq, const double *d_q, int q_per_chain, double scale,
                                  int *d_prim, double *d_d2, cudaStream_t s);
 
@@ -319,7 +332,8 @@ struct icp_ctx_s {
     static constexpr int kAux = 3;          // side streams: independent pipelines of one MH step run concurrently
     cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr};
-    std::mutex mu;
+    std::mutex mu;                          // serialises calls on ctx->stream and on the scratch shared through models / targets
+    std::mutex err_mu;                      // guards err (calls on different handles run concurrently)
     std::string err;
     std::string device_name;
 };
@@ -397,6 +411,83 @@ struct PosteriorWork {
 
 }  // namespace icp
 
+namespace icp {
+// One in-flight per-call entry (icp_propose / icp_log_transition / icp_posterior / icp_eval_log_value) on a handle: its own
+// stream and scratch. The reference shares ONE proposal and ONE evaluator object between its ten fitting threads
+// (RunMHRandomInitComparison.scala:59-86); a handle whose pipeline touches no scratch of its model (proposal_self_contained /
+// evaluator_self_contained in api.cu) keeps a small pool of these, so concurrent calls on the same handle overlap on the GPU.
+// page-locked host staging of a call slot: inputs and outputs of a per-call entry travel through it, so the copies are
+// plain asynchronous copies (and graph nodes with fixed addresses)
+struct PinnedBuf {
+    char *p = nullptr;
+    size_t n = 0;
+    uint64_t id = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    void ensure(size_t bytes) {
+        if (bytes <= n) return;
+        bytes = (std::max(bytes, 2 * n) + 4095) & ~(size_t)4095;   // grow geometrically: every growth invalidates the slot's graphs
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0; id = 0;
+        cudaError_t e = cudaHostAlloc((void **)&p, bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) { p = nullptr; throw CudaError{e, __FILE__, __LINE__}; }
+        n = bytes;
+        id = next_alloc_id();
+    }
+};
+struct CallSlotBase {
+    std::mutex mu;                // held for the duration of one call
+    cudaStream_t stream = nullptr;
+    PinnedBuf h_in, h_out, h_aux;
+    // The work of one entry point at one batch size, captured once as a CUDA graph (host -> device copies out of h_in, the
+    // kernels, device -> host copies into h_out) and replayed: one graph launch + one synchronise per call instead of
+    // 10 - 20 runtime calls, which is what bounds C = 1 calls from several host threads (they serialise in the driver).
+    // The first call with a key runs eagerly (it sizes the scratch), the second is captured; a graph is dropped when any
+    // allocation it baked in has been replaced since (ids).
+    struct Graph {
+        cudaGraphExec_t exec = nullptr;
+        std::vector<uint64_t> ids;
+        bool seen = false, eager_only = false;
+    };
+    std::unordered_map<uint64_t, Graph> graphs;
+    ~CallSlotBase() {
+        for (auto &g : graphs)
+            if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+// body() enqueues the work on s. graph = false: just that. Otherwise replay / capture as described above.
+template <class F>
+void run_call_graph(CallSlotBase &cs, bool graph, uint64_t key, const std::vector<uint64_t> &ids, cudaStream_t s, F &&body) {
+    if (!graph) { body(); return; }
+    CallSlotBase::Graph &g = cs.graphs[key];
+    if (g.eager_only) { body(); return; }
+    if (g.exec && g.ids != ids) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.seen = false; }
+    if (g.exec) { ICP_CUDA(cudaGraphLaunch(g.exec, s)); return; }
+    if (!g.seen) { body(); g.seen = true; return; }   // sizes every buffer the body touches
+    cudaGraph_t graph_obj = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); body(); return; }
+    bool ok = true;
+    try { body(); } catch (...) { ok = false; }
+    cudaError_t e = cudaStreamEndCapture(s, &graph_obj);
+    cudaGraphExec_t exec = nullptr;
+    if (ok && e == cudaSuccess && graph_obj && cudaGraphInstantiate(&exec, graph_obj, 0) != cudaSuccess) exec = nullptr;
+    if (graph_obj) cudaGraphDestroy(graph_obj);
+    if (!exec) {            // not capturable in this configuration: stay eager for this key
+        cudaGetLastError();
+        g.eager_only = true;
+        body();
+        return;
+    }
+    g.exec = exec;
+    g.ids = ids;
+    ICP_CUDA(cudaGraphLaunch(exec, s));
+}
+constexpr int kMaxCallSlots = 16;
+}  // namespace icp
+
 struct icp_proposal_s {
     int refs = 0;             // chains using this proposal
     icp_model model = nullptr;
@@ -417,9 +508,23 @@ struct icp_proposal_s {
     int cache_next = 0;
     icp::DevBuf<double> cache_L, cache_mu, cache_M;  // [slots][Kp*Kp], [slots][Kp], [slots][Kp*Kp]
     icp::DevBuf<double> cache_W;                     // [slots][Kp*Kp] (ICP_FACTOR_SVD only)
-    icp::PosteriorWork work;
-    icp::DevBuf<double> s_theta, s_theta2, s_z, s_out;
-    icp::DevBuf<int> s_slot;
+    // the cache is shared by the concurrent calls: cache_rw is held shared for the length of a call and exclusively while the
+    // slot arrays are (re)allocated; cache_lock guards the map and the per-slot state; a slot is pinned while a call uses it and
+    // not ready while the call that missed on it is still computing it (other calls with the same key wait on cache_cv)
+    std::shared_mutex cache_rw;
+    std::mutex cache_lock;
+    std::condition_variable cache_cv;
+    std::vector<int> slot_pin;
+    std::vector<char> slot_ready;
+    icp::PosteriorWork work;  // scratch of icp_std_icp_iteration's temporary proposal
+    struct Call : icp::CallSlotBase {
+        icp::PosteriorWork work;
+        icp::DevBuf<double> s_theta, s_theta2, s_z, s_out, s_L, s_mu;
+        icp::DevBuf<int> s_slot, s_qslot;
+    };
+    std::mutex pool_mu;
+    std::vector<std::unique_ptr<Call>> calls;
+    unsigned next_call = 0;
 };
 
 namespace icp {
@@ -440,9 +545,14 @@ struct icp_evaluator_s {
     icp::DevBuf<int> ids;
     icp::DevBuf<int> qperm;   // processing order of the model points (Morton order of their reference positions)
     icp::DevBuf<double> tp;
-    icp::EvalWork work;
-    icp::DevBuf<double> s_theta, s_values;
-    icp::DevBuf<int> s_status;
+    struct Call : icp::CallSlotBase {
+        icp::EvalWork work;
+        icp::DevBuf<double> s_theta, s_values;
+        icp::DevBuf<int> s_status;
+    };
+    std::mutex pool_mu;
+    std::vector<std::unique_ptr<Call>> calls;
+    unsigned next_call = 0;
 };
 
 namespace icp {
@@ -479,6 +589,47 @@ struct CtxLock {
     std::unique_lock<std::mutex> lk;
     explicit CtxLock(icp_ctx c);
 };
+// RAII of a per-call entry point on a proposal / evaluator handle: selects the device and leases one of the handle's call
+// slots (a free one, a new one while the pool is below kMaxCallSlots, else it waits for one). A handle that is not
+// self-contained takes the context lock first (lock order: context, then slot) and runs on ctx->stream like every other call.
+template <class Handle>
+struct CallLease {
+    std::unique_lock<std::mutex> ctx_lk, lk;
+    typename Handle::Call *call = nullptr;
+    cudaStream_t stream = nullptr;
+    CallLease(icp_ctx c, Handle *h, bool self_contained) {
+        if (!self_contained) ctx_lk = std::unique_lock<std::mutex>(c->mu);
+        cudaError_t e = cudaSetDevice(c->device);
+        if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
+        {
+            std::unique_lock<std::mutex> pool(h->pool_mu);
+            for (auto &cs : h->calls) {
+                std::unique_lock<std::mutex> t(cs->mu, std::try_to_lock);
+                if (t.owns_lock()) { call = cs.get(); lk = std::move(t); break; }
+            }
+            if (!call && (int)h->calls.size() < kMaxCallSlots) {
+                std::unique_ptr<typename Handle::Call> cs(new typename Handle::Call());
+                e = cudaStreamCreateWithFlags(&cs->stream, cudaStreamNonBlocking);
+                if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
+                call = cs.get();
+                lk = std::unique_lock<std::mutex>(cs->mu);
+                h->calls.push_back(std::move(cs));
+            }
+            if (!call) call = h->calls[h->next_call++ % h->calls.size()].get();
+        }
+        if (!lk.owns_lock()) lk = std::unique_lock<std::mutex>(call->mu);   // every slot busy: queue on one
+        stream = ctx_lk.owns_lock() ? c->stream : call->stream;
+    }
+};
+// waits for the calls in flight on a handle (destroy; the context lock is held)
+template <class Handle>
+void drain_calls(Handle *h) {
+    std::unique_lock<std::mutex> pool(h->pool_mu);
+    for (auto &cs : h->calls) {
+        std::lock_guard<std::mutex> in_flight(cs->mu);
+        cudaStreamSynchronize(cs->stream);
+    }
+}
 int32_t translate_exception(icp_ctx ctx);  // call inside catch (...)
 void set_error(icp_ctx ctx, const std::string &msg);
 }  // namespace icp

@@ -246,6 +246,126 @@ def test_shared_handles_from_two_threads(ctx, twin31):
     ev.close(); gp.close(); model.close(); tgt.close()
 
 
+def test_ten_threads_on_shared_handles_and_shared_cache(ctx, twin31):
+    """RunMHRandomInitComparison.scala:59-86 as it is written: ONE proposal mixture and ONE evaluator shared by ten fitting
+    threads. Concurrent calls on a handle run on the handle's call slots (own stream, scratch and replayed graph each) and share
+    its posterior cache: all ten walks start from the same state, so the first calls collide on one cache key (one call computes
+    the posterior, the others wait for it). Every walk must equal the same walk made alone on fresh handles."""
+    m = twin31
+    K = 31
+    model, tgt = _dev(ctx, m)
+    ids = np.arange(62)
+    tp = m["target"][::26][:62]
+    n_threads, steps = 10, 8
+    rng = np.random.default_rng(26)
+    th0 = random_theta(m, rng, 1)
+    z = rng.normal(size=(n_threads, steps, 1, K))
+
+    def handles():
+        return (core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.MODEL_SAMPLING, True, ids, tp),
+                core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.TARGET_SAMPLING, True, ids, tp, rank_update=_lib.RANK_UPDATE_INT8),
+                core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, _lib.MODEL_TO_TARGET, True, 0.0, 2.0, 0.0, np.arange(124), tp))
+
+    def walk(t, hs):
+        pm, pt, ev = hs
+        out, th = [], th0
+        for k in range(steps):
+            new = (pm if (k + t) % 2 == 0 else pt).propose(th, z[t, k])
+            out += [new, pm.log_transition(th, new), pm.log_transition(new, th), pt.log_transition(th, new), pt.log_transition(new, th),
+                    ev.log_value(new)]
+            th = new
+        return out
+
+    shared = handles()
+    results, errors = [None] * n_threads, []
+
+    def worker(t):
+        try:
+            results[t] = walk(t, shared)
+        except Exception as e:   # noqa: BLE001
+            errors.append(f"thread {t}: {e!r}")
+
+    for _round in range(2):     # the second round replays the graphs the first one captured
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+        for x in ts:
+            x.start()
+        for x in ts:
+            x.join()
+        assert not errors, errors
+        for t in range(n_threads):
+            alone = handles()
+            want = walk(t, alone)
+            for h in alone:
+                h.close()
+            for a, b in zip(results[t], want):
+                assert np.array_equal(a, b, equal_nan=True), f"round {_round}, thread {t}: differs from the walk made alone"
+    for h in shared:
+        h.close()
+    model.close(); tgt.close()
+
+
+def test_per_thread_handles_run_concurrently(ctx, twin31):
+    """RunMHRandomInitComparison.scala:59-86: ten fitting threads, each with its OWN proposals and evaluators over the shared
+    model and target. Self-contained handles (model-sampling and target-sampling ICP proposals, model->target evaluators) run
+    on their own streams under their own locks, the symmetric evaluator (it refits the model's BVH) takes the context lock;
+    every thread must get exactly what the same calls return serially."""
+    m = twin31
+    K = 31
+    model, tgt = _dev(ctx, m)
+    ids = np.arange(62)
+    tp = m["target"][::26][:62]
+    n_threads, steps = 10, 6
+    rng = np.random.default_rng(16)
+    th0 = [random_theta(m, rng, 1, pose=(t % 2 == 0)) for t in range(n_threads)]
+    z = rng.normal(size=(n_threads, steps, 1, K))
+
+    def handles():
+        return (core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, 0, True, ids, tp), core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, 1, True, ids, tp),
+                core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, 0, True, 0.0, 2.0, 0.0, np.arange(124), tp),
+                core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, 2, True, 0.0, 2.0, 0.0, np.arange(124), tp))
+
+    def walk(t, hs):
+        pm, pt, em, es = hs
+        out, th = [], th0[t]
+        for k in range(steps):
+            p = (pm if k % 2 == 0 else pt)
+            new = p.propose(th, z[t, k])
+            out += [new, pm.log_transition(th, new), pm.log_transition(new, th), pt.log_transition(th, new), pt.log_transition(new, th),
+                    em.log_value(new), es.log_value(new)]
+            th = new
+        return out
+
+    serial = []
+    for t in range(n_threads):
+        hs = handles()
+        serial.append(walk(t, hs))
+        for h in hs:
+            h.close()
+    all_handles = [handles() for _ in range(n_threads)]
+    results, errors = [None] * n_threads, []
+
+    def worker(t):
+        try:
+            results[t] = walk(t, all_handles[t])
+        except Exception as e:   # noqa: BLE001
+            errors.append(f"thread {t}: {e!r}")
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for x in ts:
+        x.start()
+    for x in ts:
+        x.join()
+    assert not errors, errors
+    for t in range(n_threads):
+        assert len(results[t]) == len(serial[t])
+        for a, b in zip(results[t], serial[t]):
+            assert np.array_equal(a, b, equal_nan=True), f"thread {t}: concurrent result differs from the serial one"
+    for hs in all_handles:
+        for h in hs:
+            h.close()
+    model.close(); tgt.close()
+
+
 def test_step_graph_survives_reallocation_of_model_scratch(ctx, twin31):
     """A cached step graph bakes in the model's shared BVH scratch. Run chain A at C = 8 (symmetric evaluator: the graph
     refits the model triangle BVH), make another call reallocate that scratch with a larger batch, then re-run A with the
