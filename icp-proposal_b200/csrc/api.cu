@@ -899,7 +899,7 @@ static std::vector<uint64_t> proposal_call_ptrs(icp_proposal p, icp_proposal_s::
 static std::vector<uint64_t> evaluator_call_ptrs(icp_evaluator_s::Call &cs) {
     const EvalWork &w = cs.work;
     return {w.X.id, w.cp_m2t.id, w.d2_m2t.id, w.cp_t2m.id, w.d2_t2m.id, w.prim.id, w.seed_m2t.id, w.seed_t2m.id, w.skip_m2t.id,
-            w.skip_t2m.id, cs.s_theta.id, cs.s_values.id, cs.s_status.id, cs.h_in.id, cs.h_out.id};
+            w.skip_t2m.id, w.hd_max.id, cs.s_theta.id, cs.s_values.id, cs.s_status.id, cs.h_in.id, cs.h_out.id};
 }
 static void h2d(void *d, const void *h, size_t bytes, cudaStream_t s) {
     if (bytes) ICP_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
@@ -1313,6 +1313,16 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
         const bool use_m = kind == ICP_EVAL_HAUSDORFF || mode != ICP_TARGET_TO_MODEL;
         const bool use_t = kind == ICP_EVAL_HAUSDORFF || mode != ICP_MODEL_TO_TARGET;
         const bool collective = kind == ICP_EVAL_COLLECTIVE;
+        // Hausdorff: only the largest distance of the two directions is used, so both traversals share one running maximum
+        // per chain and stop every query that cannot raise it (k_nearest, HDMAX). Not when the model -> target closest points
+        // are shared with an ICP proposal (they must be exact then). ICPCUDA_HAUSDORFF_PRUNE=0 switches it off.
+        static const bool hd_prune_on = !(getenv("ICPCUDA_HAUSDORFF_PRUNE") && getenv("ICPCUDA_HAUSDORFF_PRUNE")[0] == '0');
+        unsigned long long *hd_max = nullptr;
+        if (kind == ICP_EVAL_HAUSDORFF && hd_prune_on && !w.force_cp_m2t) {
+            w.hd_max.ensure(C);
+            ICP_CUDA(cudaMemsetAsync(w.hd_max.p, 0, sizeof(unsigned long long) * (size_t)C, s));
+            hd_max = w.hd_max.p;
+        }
         if (use_m && e->n_ids > 0) {
             size_t tot = (size_t)C * e->n_ids;
             w.d2_m2t.ensure(tot);
@@ -1322,6 +1332,7 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
             if (w.seed_m2t.n < tot) { w.seed_m2t.ensure(tot); ICP_CUDA(cudaMemsetAsync(w.seed_m2t.p, 0xFF, sizeof(int) * tot, s)); }
             a.seed_slot = w.seed_m2t.p;
             if (collective || w.force_cp_m2t) { w.cp_m2t.ensure(3 * tot); a.out_cp = w.cp_m2t.p; }
+            a.chain_max = hd_max;
             launch_nearest(a, s);
             if (collective && t->has_boundary) {
                 // CollectiveAverage...:46-47: nearest target vertex of the closest point, dropped when on the boundary
@@ -1344,6 +1355,7 @@ void evaluator_pipeline(icp_evaluator e, EvalWork &w, int C, const double *d_the
             if (w.seed_t2m.n < tot) { w.seed_t2m.ensure(tot); ICP_CUDA(cudaMemsetAsync(w.seed_t2m.p, 0xFF, sizeof(int) * tot, s)); }
             a.seed_slot = w.seed_t2m.p;
             if (collective) { w.cp_t2m.ensure(3 * tot); a.out_cp = w.cp_t2m.p; }
+            a.chain_max = hd_max;
             launch_nearest(a, s);
             if (collective && t->has_boundary) {
                 // CollectiveAverage...:58-59: id of the nearest vertex of the MODEL sample, looked up in the

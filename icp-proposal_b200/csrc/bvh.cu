@@ -10,6 +10,9 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "bvh_device.cuh"
+#include <algorithm>
+#include <string>
+
 #include "icp_internal.h"
 
 namespace icp {
@@ -133,7 +136,7 @@ __global__ void k_refit(int n, int instances, int prim_kind, const int *__restri
 
 // level-synchronous refit: one CTA per instance walks the internal nodes in order of increasing height (schedule
 // computed once at build time); no atomics, no counters, boxes of finished levels are read back through L2.
-__global__ void __launch_bounds__(256) k_refit_levels(int n, int prim_kind, const int *__restrict__ prim,
+__global__ void __launch_bounds__(1024) k_refit_levels(int n, int prim_kind, const int *__restrict__ prim,
                                                       const int2 *__restrict__ children, const int *__restrict__ order,
                                                       const int *__restrict__ level_off, int n_levels,
                                                       const double *__restrict__ X, int N, const int *__restrict__ tris,
@@ -175,13 +178,19 @@ __global__ void __launch_bounds__(256) k_refit_levels(int n, int prim_kind, cons
 }
 
 void bvh_refit(Bvh &b, int instances, const double *d_X, int N, const int *d_tris, cudaStream_t s) {
-    if (b.n_levels > 0 && instances >= 8) {
+    // ICPCUDA_REFIT = levels256 | levels1024 | atomic forces one variant (experiments; all three write the same boxes)
+    static const std::string mode = getenv("ICPCUDA_REFIT") ? getenv("ICPCUDA_REFIT") : "";
+    // 1024 threads per instance from 2048 primitives on: with one CTA per instance the refit is bound by the L2 round trips
+    // of its own threads (measured: femur, 3240 triangles x 2368 chains 0.95 -> 0.72 ms; face-sized, 56 k triangles x 148
+    // chains 2.77 -> 2.41 ms; profiles/r2_session3.md)
+    const int threads = mode == "levels256" ? 256 : mode == "levels1024" ? 1024 : (b.n >= 2048 ? 1024 : 256);
+    if (b.n_levels > 0 && instances >= 8 && mode != "atomic") {
         ProfScope _ps(ST_REFIT, s);
         int n = b.n;
         b.nodes.ensure((size_t)instances * (n - 1) * 3);
         b.nodebox.ensure((size_t)instances * (2 * n - 1) * 2);
         b.instances = instances;
-        k_refit_levels<<<instances, 256, 0, s>>>(n, b.prim_kind, b.prim.p, b.children.p, b.order.p, b.level_off.p, b.n_levels,
+        k_refit_levels<<<instances, threads, 0, s>>>(n, b.prim_kind, b.prim.p, b.children.p, b.order.p, b.level_off.p, b.n_levels,
                                                  d_X, N, d_tris, b.slack, b.nodes.p, b.nodebox.p);
         ICP_CUDA(cudaGetLastError());
         return;
@@ -309,7 +318,15 @@ constexpr int kDone = 0x7ffffffe;
 // internal nodes until it holds a leaf (or has nothing left), then the warp reconverges and all lanes holding a leaf run
 // the exact FP64 primitive test together. Static structures read one 64-byte packed node (child boxes + child links);
 // per-chain (refitted) structures read the shared topology and their own boxes.
-template <int PRIM, bool DYNAMIC>
+//
+// HDMAX (Hausdorff evaluator, HausdorffDistanceEvaluator.scala:31-35: only the LARGEST of a chain's distances is used): the
+// early-break scheme of directed Hausdorff distances. chain_max[c] holds the largest exact squared distance any finished
+// query of chain c has produced (atomicMax on the bits of a non-negative double). A query whose current upper bound is
+// already <= chain_max[c] cannot raise the maximum and stops - after its seed test in most cases; its d2 output is then an
+// upper bound <= the chain's maximum, so the maximum over the outputs stays the exact Hausdorff distance. The warps of a
+// launch rotate over the chains (warp w -> chain w % C, 32-query block (w / C) * blk_stride % n_blk of that chain), so the
+// first wave finishes a few blocks of EVERY chain and the following waves prune against those maxima.
+template <int PRIM, bool DYNAMIC, bool HDMAX>
 __global__ void __launch_bounds__(kNearestThreads, 7) k_nearest(int n, const int2 *__restrict__ children,
                                                  const float4 *__restrict__ nodes, const int *__restrict__ prim,
                                                  const double *__restrict__ prim_data, const double *__restrict__ X,
@@ -318,14 +335,28 @@ __global__ void __launch_bounds__(kNearestThreads, 7) k_nearest(int n, const int
                                                  const double *__restrict__ Xq, const int *__restrict__ q_ids, int Nq,
                                                  const int *__restrict__ perm, int *__restrict__ seed_slot,
                                                  int *__restrict__ out_prim, int *__restrict__ out_feat,
-                                                 double *__restrict__ out_cp, double *__restrict__ out_d2) {
+                                                 double *__restrict__ out_cp, double *__restrict__ out_d2,
+                                                 unsigned long long *__restrict__ chain_max, int n_blk, int blk_stride) {
     __shared__ int s_stack_n[kStackShared][kNearestThreads];
     __shared__ float s_stack_d[kStackShared][kNearestThreads];
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = g < nq * C;
-    if (!live) g = nq * C - 1;   // idle lanes stay in the warp-synchronous loop, write nothing
-    int c = (int)(g / nq);
-    long long i = g % nq;
+    bool live;
+    int c;
+    long long i;
+    if (HDMAX) {
+        const long long w = g >> 5;
+        live = w < (long long)n_blk * C;
+        c = live ? (int)(w % C) : C - 1;
+        const long long b = live ? ((w / C) * blk_stride) % n_blk : 0;
+        i = b * 32 + (threadIdx.x & 31);
+        if (i >= nq) { live = false; i = nq - 1; }
+        g = (long long)c * nq + i;
+    } else {
+        live = g < nq * C;
+        if (!live) g = nq * C - 1;   // idle lanes stay in the warp-synchronous loop, write nothing
+        c = (int)(g / nq);
+        i = g % nq;
+    }
     if (perm) { i = perm[i]; g = (long long)c * nq + i; }  // spatially sorted processing order, results in caller order
     double qx, qy, qz;
     if (q_ids) {
@@ -355,6 +386,10 @@ __global__ void __launch_bounds__(kNearestThreads, 7) k_nearest(int n, const int
             best = __double2float_ru(h.d2);
         }
     }
+    const unsigned long long *cmax = HDMAX ? chain_max + c : nullptr;
+    bool pruned = false;
+    // squared distances are >= 0: their bit patterns order like the values
+    if (HDMAX && node != kDone && __double_as_longlong(h.d2) <= (long long)__ldcg(cmax)) { node = kDone; pruned = true; }
     auto pop = [&]() {
         int nn = kDone;
         while (sp > 0) {
@@ -400,11 +435,13 @@ __global__ void __launch_bounds__(kNearestThreads, 7) k_nearest(int n, const int
             leaf_test<PRIM, DYNAMIC>(~node, prim, prim_data, Xi, tris, qx, qy, qz, h);
             best = __double2float_ru(h.d2);
             node = pop();
+            if (HDMAX && node != kDone && __double_as_longlong(h.d2) <= (long long)__ldcg(cmax)) { node = kDone; pruned = true; }
         }
     }
     if (!live) return;
+    if (HDMAX && !pruned && h.d2 == h.d2 && h.prim != 0x7fffffff) atomicMax(chain_max + c, (unsigned long long)__double_as_longlong(h.d2));
     if (h.prim == 0x7fffffff) { h.d2 = NAN; h.x = h.y = h.z = NAN; h.prim = -1; }
-    if (seed_slot) seed_slot[g] = h.slot;
+    if (seed_slot && (!HDMAX || h.slot >= 0)) seed_slot[g] = h.slot;
     if (out_prim) out_prim[g] = h.prim;
     if (out_feat) out_feat[g] = h.feat;
     if (out_cp) { out_cp[3 * g] = h.x; out_cp[3 * g + 1] = h.y; out_cp[3 * g + 2] = h.z; }
@@ -420,14 +457,28 @@ void launch_nearest(const NearestArgs &a, cudaStream_t s) {
     bool dynamic = a.prim_data == nullptr;
     int threads = kNearestThreads;
     unsigned blocks = (unsigned)((total + threads - 1) / threads);
-#define ICP_LAUNCH_NEAREST(P, D)                                                                                  \
-    k_nearest<P, D><<<blocks, threads, 0, s>>>(b.n, b.children.p, (D) ? b.nodes.p : b.packed.p, b.prim.p, a.prim_data, a.X, a.tris, \
+    int n_blk = 0, blk_stride = 1;
+    if (a.chain_max) {
+        // 32-query blocks of a chain are visited with a stride coprime to their number (near the golden section), so that
+        // successive waves sample the whole surface instead of sweeping it in Morton order
+        n_blk = (int)((a.nq + 31) / 32);
+        auto gcd = [](long long x, long long y) { while (y) { long long t = x % y; x = y; y = t; } return x; };
+        blk_stride = std::max(1, (int)(n_blk * 0.618));
+        while (gcd(blk_stride, n_blk) != 1) blk_stride++;
+        blocks = (unsigned)(((long long)n_blk * a.C * 32 + threads - 1) / threads);
+    }
+#define ICP_LAUNCH_NEAREST(P, D, H)                                                                                  \
+    k_nearest<P, D, H><<<blocks, threads, 0, s>>>(b.n, b.children.p, (D) ? b.nodes.p : b.packed.p, b.prim.p, a.prim_data, a.X, a.tris, \
                                                a.N, a.C, (long long)a.nq, a.q, a.q_per_chain, a.Xq, a.q_ids,     \
-                                               a.Nq, a.perm, a.seed_slot, a.out_prim, a.out_feat, a.out_cp, a.out_d2)
-    if (b.prim_kind == 0) {
-        if (dynamic) ICP_LAUNCH_NEAREST(0, true); else ICP_LAUNCH_NEAREST(0, false);
+                                               a.Nq, a.perm, a.seed_slot, a.out_prim, a.out_feat, a.out_cp, a.out_d2, \
+                                               a.chain_max, n_blk, blk_stride)
+    if (a.chain_max) {
+        ICP_REQUIRE(b.prim_kind == 0 && !a.out_cp && !a.out_prim && !a.out_feat, "launch_nearest: chain_max is for distance-only triangle queries");
+        if (dynamic) ICP_LAUNCH_NEAREST(0, true, true); else ICP_LAUNCH_NEAREST(0, false, true);
+    } else if (b.prim_kind == 0) {
+        if (dynamic) ICP_LAUNCH_NEAREST(0, true, false); else ICP_LAUNCH_NEAREST(0, false, false);
     } else {
-        if (dynamic) ICP_LAUNCH_NEAREST(1, true); else ICP_LAUNCH_NEAREST(1, false);
+        if (dynamic) ICP_LAUNCH_NEAREST(1, true, false); else ICP_LAUNCH_NEAREST(1, false, false);
     }
 #undef ICP_LAUNCH_NEAREST
     ICP_CUDA(cudaGetLastError());

@@ -516,7 +516,10 @@ extern "C" int32_t icp_chain_create(icp_model m, icp_target t, const icp_compone
         {
             const icp_evaluator_params &ep = evaluator->prm;
             bool ev_m2t = ep.kind == ICP_EVAL_HAUSDORFF || ((ep.kind == ICP_EVAL_INDEPENDENT || ep.kind == ICP_EVAL_COLLECTIVE) && ep.mode != ICP_TARGET_TO_MODEL);
-            if (ev_m2t && evaluator->n_ids > 0) {
+            // not for the Hausdorff evaluator: its traversals stop every query that cannot raise the chain's maximum
+            // (k_nearest, HDMAX), which is worth more than the shared queries and leaves most closest points unknown
+            static const bool hd_prune_on = !(getenv("ICPCUDA_HAUSDORFF_PRUNE") && getenv("ICPCUDA_HAUSDORFF_PRUNE")[0] == '0');
+            if (ev_m2t && evaluator->n_ids > 0 && !(ep.kind == ICP_EVAL_HAUSDORFF && hd_prune_on)) {
                 std::vector<int> eids(evaluator->n_ids);
                 ICP_CUDA(cudaMemcpy(eids.data(), evaluator->ids.p, sizeof(int) * eids.size(), cudaMemcpyDeviceToHost));
                 std::unordered_map<int, int> pos;

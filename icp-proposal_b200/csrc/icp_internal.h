@@ -168,6 +168,10 @@ struct NearestArgs {
     // The traversal starts from the exact distance to that primitive, which prunes most of the tree when the query
     // moved little since (successive MH states of a chain). The result does not depend on it.
     int *seed_slot = nullptr;
+    // optional [C], Hausdorff evaluator only (distance-only triangle queries): running maximum of the exact squared
+    // distances of the chain (bits of a non-negative double, zeroed by the caller); queries that cannot raise it stop early
+    // and write an upper bound instead of the exact distance (see k_nearest)
+    unsigned long long *chain_max = nullptr;
     // outputs [C][nq]
     int *out_prim = nullptr;
     int *out_feat = nullptr;
@@ -529,6 +533,7 @@ struct icp_proposal_s {
 
 namespace icp {
 struct EvalWork {
+    DevBuf<unsigned long long> hd_max;   // [C] running maxima of the Hausdorff evaluator's two traversals (NearestArgs::chain_max)
     DevBuf<double> X, cp_m2t, d2_m2t, cp_t2m, d2_t2m;
     DevBuf<int> prim, seed_m2t, seed_t2m;   // seed_*: traversal seeds (NearestArgs::seed_slot)
     DevBuf<uint8_t> skip_m2t, skip_t2m;
