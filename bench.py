@@ -615,7 +615,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chains", type=int, default=2368, help="chains per GPU (16 x 148 SMs)")
+    ap.add_argument("--chains", type=int, default=4736, help="chains per GPU (32 x 148 SMs; 2368 gives 4 % less, profiles/r2_session3.md)")
     ap.add_argument("--cpu-steps", type=int, default=120, help="MH steps of the cpu_baseline sample")
     ap.add_argument("--sustain-steps", type=int, default=2000, help="steps of the sustained-load arm (0 = skip)")
     ap.add_argument("--rank-update", default="int8", choices=["int8", "fp64"],

@@ -246,6 +246,28 @@ def test_shared_handles_from_two_threads(ctx, twin31):
     ev.close(); gp.close(); model.close(); tgt.close()
 
 
+def test_hausdorff_early_break_is_exact(ctx, twin31):
+    """HausdorffDistanceEvaluator.scala:31-35 uses only the largest distance of the two directions. The device stops every
+    closest-point query that cannot raise the chain's running maximum (k_nearest, HDMAX); the value must stay the exact one:
+    compared with the Hausdorff distance of icp_registration_metrics (every query run to the end) on 333 chains with pose,
+    on a cold evaluator (no seeds: nothing can be pruned before the first queries finish) and again on the warm one."""
+    m = twin31
+    model, tgt = _dev(ctx, m)
+    rng = np.random.default_rng(46)
+    th = random_theta(m, rng, 333, alpha_sd=0.6, pose=True)
+    hd = core.registration_metrics(model, tgt, th)[:, 1]
+    want = np.log(100.0) - 100.0 * hd
+    ev = core.Evaluator(model, tgt, _lib.EVAL_HAUSDORFF, 0, False, 100.0)
+    for _ in range(3):
+        v = ev.log_value(th)
+        np.testing.assert_allclose(v[:, 2], want, rtol=1e-12, atol=0)
+    # moved states on the warm evaluator (stale seeds), and a single chain (every warp works on the same maximum)
+    th2 = th + np.concatenate([np.zeros((333, 10)), rng.normal(0, 0.05, (333, 31))], axis=1)
+    np.testing.assert_allclose(ev.log_value(th2)[:, 2], np.log(100.0) - 100.0 * core.registration_metrics(model, tgt, th2)[:, 1], rtol=1e-12)
+    np.testing.assert_allclose(ev.log_value(th2[7:8])[:, 2], np.log(100.0) - 100.0 * core.registration_metrics(model, tgt, th2[7:8])[:, 1], rtol=1e-12)
+    ev.close(); model.close(); tgt.close()
+
+
 def test_ten_threads_on_shared_handles_and_shared_cache(ctx, twin31):
     """RunMHRandomInitComparison.scala:59-86 as it is written: ONE proposal mixture and ONE evaluator shared by ten fitting
     threads. Concurrent calls on a handle run on the handle's call slots (own stream, scratch and replayed graph each) and share
