@@ -39,11 +39,12 @@ if "3" in which or "4" in which:
     if "3" in which:
         C = int(os.environ.get("C3", "592"))
         all_ids = np.arange(N, dtype=np.int32)
-        gp = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.MODEL_SAMPLING, True, all_ids, tv)
-        comps = [dict(kind=_lib.PROP_ICP, weight=0.9, proposal=gp), dict(kind=_lib.PROP_RANDOM_SHAPE, weight=0.1, sd=0.1)]
         ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, _lib.SYMMETRIC, True, 0.0, 2.0, 0.0, all_ids, tv)
         th0 = np.stack([model.theta(np.random.default_rng(s).normal(0, 0.3, K)) for s in range(C)])
-        run("config3_n_icp_N_symmetric", model, tgt, comps, ev, th0, 10)
+        for ru, nm in ((_lib.RANK_UPDATE_FP64, "fp64"), (_lib.RANK_UPDATE_INT8, "int8")):
+            gp = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.MODEL_SAMPLING, True, all_ids, tv, rank_update=ru)
+            comps = [dict(kind=_lib.PROP_ICP, weight=0.9, proposal=gp), dict(kind=_lib.PROP_RANDOM_SHAPE, weight=0.1, sd=0.1)]
+            run("config3_n_icp_N_symmetric_" + nm, model, tgt, comps, ev, th0, 10)
     if "4" in which:
         C = int(os.environ.get("C4", "2368"))
         for ru, nm in ((_lib.RANK_UPDATE_INT8, "int8"),):
