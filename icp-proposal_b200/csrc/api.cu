@@ -884,7 +884,12 @@ extern "C" int32_t icp_posterior(icp_proposal p, int32_t C, const double *theta,
 
 // ---- per-call entries as replayed graphs (run_call_graph) ----------------------------------------------------------
 static bool call_graphs_enabled() {
-    static const bool on = !(getenv("ICPCUDA_CALL_GRAPH") && getenv("ICPCUDA_CALL_GRAPH")[0] == '0');
+    // ICPCUDA_CALL_GRAPH=0: launch the kernels of a per-call entry directly. Also under Nsight Compute (it sets
+    // NV_COMPUTE_PROFILER_PERFWORKS_DIR in the target process): stream capture from several host threads aborts inside the
+    // profiler's injection library (ncu 2025.2.1, measured: profiles/r2_session3.md section 1), and a profile wants the
+    // kernels one by one anyway.
+    static const bool on = !(getenv("ICPCUDA_CALL_GRAPH") && getenv("ICPCUDA_CALL_GRAPH")[0] == '0') &&
+                           !getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
     return on;
 }
 enum CallKind : uint64_t { CALL_POSTERIOR = 1, CALL_PROPOSE, CALL_LOG_TRANSITION, CALL_EVAL };
