@@ -546,15 +546,29 @@ def run_gpu(args):
                                 "MMA operands), not by the tensor pipe: profiles/r2_i8_rank_update.md"}
         # ---- BASELINE.json configs[0] shape: ONE chain, fixed seed - latency-bound by construction: steps/s of
         # the device-resident loop with a single resident chain, next to the 1-core CPU port below -------------------
-        sc_steps = 300
-        th1 = torch.from_numpy(np.ascontiguousarray(th0_host[:1])).to(dev)
-        chain.run_device(1, 20, th1.data_ptr(), seed=seed, chain_id_offset=off)        # warm-up, sizes + captures the C = 1 graph
-        torch.cuda.synchronize()
-        chain.run_device(1, sc_steps, None, seed=seed, chain_id_offset=off)             # resumed: exactly sc_steps steps
-        sc_ms, _ = chain.last_run_stats()
-        single_chain = {"steps_per_s": sc_steps / (sc_ms * 1e-3), "ms_per_step": sc_ms / sc_steps, "steps": sc_steps,
-                        "note": "one chain resident on the GPU (configs[0] shape): every kernel of the step runs a single CTA / "
-                                "a handful of warps, so this is launch + dependent-latency time, not throughput"}
+        # The fused runner's rejection look-ahead (icp_chain_set_lookahead; automatic for <= 8 chains) evaluates the proposals of
+        # the next 8 steps from the same state in one batched round - same chain log, 2.4 x fewer rounds at this acceptance rate.
+        # th0_host[1] is a random-init chain (index 0 starts from the mean); 500 burn-in steps first, acceptance is high at first.
+        sc_steps = 2000
+        th1 = torch.from_numpy(np.ascontiguousarray(th0_host[1:2])).to(dev)
+        single_chain = {}
+        for name, width in (("step_by_step", 0), ("lookahead", -1)):
+            chain.set_lookahead(width)
+            sc_acc = torch.zeros(1, dtype=torch.int64, device=dev)
+            chain.run_device(1, 500, th1.data_ptr(), seed=seed, chain_id_offset=off + 1)   # burn-in; sizes + captures the graph
+            torch.cuda.synchronize()
+            chain.run_device(1, sc_steps, None, seed=seed, chain_id_offset=off + 1, n_accepted=sc_acc.data_ptr())   # resumed
+            sc_ms, _ = chain.last_run_stats()
+            rounds = chain.last_run_rounds()
+            single_chain[name] = {"steps_per_s": sc_steps / (sc_ms * 1e-3), "ms_per_step": sc_ms / sc_steps, "steps": sc_steps,
+                                  "rounds": int(rounds), "accepted_total": int(sc_acc.item())}
+        chain.set_lookahead(-1)
+        single_chain.update(single_chain["lookahead"])
+        single_chain["note"] = ("one chain resident on the GPU (configs[0] shape): every kernel of a step runs a single CTA / a handful "
+                                "of warps, so a step is launch + dependent-latency time. 'lookahead' (the default for <= 8 chains): 8 lanes "
+                                "propose the next 8 steps from the current state in one batched round, the first accepting lane is the "
+                                "chain's next state - the log is bit-identical to 'step_by_step' (tests/test_gpu_round2.py::"
+                                "test_rejection_lookahead_is_bit_identical). n_accepted counts from the start of the chain (burn-in included)")
         # ---- CPU baseline: the oracle port of the same chain on this box's host cores (bounded sample) ------
         cores = os.cpu_count() or 1
         blas = enable_cpu_blas()

@@ -122,6 +122,8 @@ _SIGS = {
     "icp_chain_run_device": [_h, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(ChainIO), C.c_int32],
     "icp_ctx_synchronize": [_h],
     "icp_chain_last_run_stats": [_h, _dp, _lp],
+    "icp_chain_set_lookahead": [_h, C.c_int32],
+    "icp_chain_last_run_rounds": [_h, _lp],
     "icp_debug_philox": [_h, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)],
     "icp_debug_fp64_peak": [_h, _dp],
     "icp_debug_dmma_sweep": [_h, C.c_int32, C.c_int32, C.c_int32, _dp],

@@ -559,6 +559,15 @@ class Chain:
         check(self.lib.icp_chain_last_run_stats(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def set_lookahead(self, width):
+        """icp_chain_set_lookahead: -1 automatic, 0 off, 2..32 lanes per chain."""
+        check(self.lib.icp_chain_set_lookahead(self.h, int(width)), self.ctx.h)
+
+    def last_run_rounds(self):
+        n = C.c_int64(0)
+        check(self.lib.icp_chain_last_run_rounds(self.h, C.byref(n)))
+        return n.value
+
     def profile(self, theta0, n_steps, seed=1024):
         th, c = self.model._theta(theta0)
         ms = np.zeros(_lib.N_STAGES); n = np.zeros(_lib.N_STAGES, np.int64)

@@ -33,6 +33,9 @@ struct CompDev {
 
 struct ChainParams {
     int n_comp, n_icp, K, Kp, C;
+    // Rejection look-ahead (see enqueue_round): W > 1 lanes per chain. C then counts the lanes (C = Cr * W, lane v belongs to
+    // chain v / W) and every per-chain array of StateDev is per lane, except step / n_acc / status / theta_best / value_best.
+    int W, Cr;
     CompDev comp[kMaxComp];
 };
 
@@ -66,6 +69,8 @@ struct StateDev {
     // |L^T d|^2 of every ICP component's forward (posterior of the current state, formed by k_chain_propose while it holds
     // L_cur) and backward (posterior of the proposal, formed in the factorisation's epilogue) transition: [n_icp][C]
     double *qf, *qb;
+    // look-ahead only: the lanes' accept decisions and status words of this round, the first step the run must not take
+    int *lane_ok, *lane_status, *step_end;
 };
 
 // per-chain status bits of a run (icp_chain_io.status)
@@ -200,13 +205,22 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
            *sL = sm + 7 * Kp + 40;
     __shared__ int s_ci;
     int c = blockIdx.x;
+    // look-ahead: lane c proposes step step[chain] + lane index of chain c / W from the chain's current state; the randomness
+    // of a step is a function of (seed, chain, step) only, so this is the proposal the sequential chain makes at that step
+    // if every step before it is rejected. Lanes past the end of the run repeat the last step (ignored by k_la_resolve).
+    const int cr = P.W > 1 ? c / P.W : c, Cr = P.W > 1 ? P.Cr : C;
     unsigned int step = (unsigned int)*st.step;
-    unsigned long long chain = rng.chain_offset + (unsigned long long)c;
+    if (P.W > 1) {
+        int sv = st.step[cr] + (c - cr * P.W);
+        const int last = *st.step_end - 1;
+        step = (unsigned int)(sv > last ? last : sv);
+    }
+    unsigned long long chain = rng.chain_offset + (unsigned long long)cr;
     if (threadIdx.x == 0) {
         double uc, ua;
         if (rng.u_comp) {
-            uc = rng.u_comp[(size_t)(step - rng.step_base) * C + c];
-            ua = rng.u_acc[(size_t)(step - rng.step_base) * C + c];
+            uc = rng.u_comp[(size_t)(step - rng.step_base) * Cr + cr];
+            ua = rng.u_acc[(size_t)(step - rng.step_base) * Cr + cr];
         } else {
             uint4 r = chain_philox(rng.seed, chain, step, 0u);
             uc = u53(r.x, r.y);
@@ -221,7 +235,7 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
     }
     for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
         double zz = 0.0;
-        if (k < K) zz = rng.z ? rng.z[((size_t)(step - rng.step_base) * C + c) * K + k] : chain_normal(rng.seed, chain, step, k);
+        if (k < K) zz = rng.z ? rng.z[((size_t)(step - rng.step_base) * Cr + cr) * K + k] : chain_normal(rng.seed, chain, step, k);
         sz[k] = zz;
     }
     __syncthreads();
@@ -375,9 +389,11 @@ __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st
         // the reference throws where these happen (CollectiveAverage...Evaluator.scala:51,63; Scalismo's mixture on a NaN
         // transition); here the step is rejected and the chain's sticky status word records it
         const int stw = fold_status(stsrc, c) | (nan ? kStNanTransition : 0);
-        if (stw) st.status[c] |= stw;
+        if (P.W > 1) { st.lane_ok[c] = ok; st.lane_status[c] = stw; }   // k_la_resolve decides which lanes happened
+        else if (stw) st.status[c] |= stw;
     }
     __syncthreads();
+    if (P.W > 1) return;
     int ok = s_acc;
     if (ok) {
         for (int j = threadIdx.x; j < Lt; j += blockDim.x) st.theta_cur[(size_t)c * Lt + j] = prp[j];
@@ -414,6 +430,100 @@ __global__ void __launch_bounds__(128) k_chain_accept(ChainParams P, StateDev st
 
 __global__ void k_step_increment(int *step) { *step += 1; }
 
+// ---- rejection look-ahead ("prefetching" Metropolis-Hastings) ---------------------------------------------------------
+// A single chain is a chain of dependent latencies (SamplingRegistration.scala:60-85 is sequential), but a REJECTED step leaves
+// the state where it was, and the randomness of step s is a function of (seed, chain, s) alone. So W lanes evaluate the
+// proposals of steps s, s + 1, .., s + W - 1 from the same current state in one batched round - exactly what the sequential
+// chain computes at those steps as long as everything before is rejected. k_la_resolve then walks the lanes in step order:
+// lanes before the first accepting one are the chain's rejected steps (logged as such), the first accepting lane is its next
+// accepted step, the lanes after it are discarded (their steps are proposed again, from the new state, in the next round).
+// The chain log is bit-identical to the sequential runner's; a round costs the latency of one step and consumes
+// (1 - (1 - a)^W) / a steps at acceptance rate a (2.4 at a = 0.4, W = 8).
+__global__ void k_la_init(int Cr, int W, int Lt, const double *__restrict__ theta0, StateDev st) {
+    const int Cv = Cr * W;
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < Cr) { st.step[v] = 0; st.n_acc[v] = 0; st.status[v] = 0; }
+    if (v >= Cv) return;
+    st.cur_sel[v] = 0;
+    st.slot_cur[v] = v;
+    st.slot_prop[v] = Cv + v;
+    const double *src = theta0 + (size_t)(v / W) * Lt;
+    for (int j = 0; j < Lt; j++) st.theta_cur[(size_t)v * Lt + j] = src[j];
+}
+
+__global__ void k_la_set_end(int *step_end, int value) { *step_end = value; }
+
+// status / best sample of the initial state from lane 0 of every chain (all lanes hold the same state)
+__global__ void k_la_status0(int Cr, int W, int Lt, StateDev st, StatusSrc ss) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cr) return;
+    const int v = c * W;
+    int s = fold_status(ss, v);
+    const double p = st.values_cur[3 * v];
+    if (p != p) s |= kStNanValue;
+    st.status[c] = s;
+    st.value_best[c] = p;
+    for (int j = 0; j < Lt; j++) st.theta_best[(size_t)c * Lt + j] = st.theta_cur[(size_t)v * Lt + j];
+}
+
+__global__ void __launch_bounds__(128) k_la_resolve(ChainParams P, StateDev st, LogDev lg) {
+    const int W = P.W, Cr = P.Cr, Cv = P.C, Lt = P.K + kTheta0;
+    const int c = blockIdx.x, v0 = c * W;
+    const int s0 = st.step[c];
+    int limit = *st.step_end - s0;
+    if (limit > W) limit = W;
+    if (limit <= 0) return;                       // this chain has taken all its steps
+    int jstar = -1;
+    for (int j = 0; j < limit; j++)
+        if (st.lane_ok[v0 + j]) { jstar = j; break; }
+    const int consumed = jstar >= 0 ? jstar + 1 : limit;
+    // records of the consumed steps: the state that is current after each of them (JSONAcceptRejectLogger.scala:93-106)
+    const double *cur = st.theta_cur + (size_t)v0 * Lt;
+    for (int j = 0; j < consumed; j++) {
+        const int v = v0 + j;
+        const bool ok = j == jstar;
+        const size_t rec = (size_t)(s0 + j - lg.step_base) * Cr + c;
+        if (lg.theta) {
+            const double *src = ok ? st.theta_prop + (size_t)v * Lt : cur;
+            for (int k = threadIdx.x; k < Lt; k += blockDim.x) lg.theta[rec * Lt + k] = src[k];
+        }
+        if (threadIdx.x == 0) {
+            if (lg.comp) lg.comp[rec] = st.comp_sel[v];
+            if (lg.accepted) lg.accepted[rec] = (uint8_t)ok;
+            if (lg.values) {
+                const double *val = ok ? st.values_prop + 3 * v : st.values_cur + 3 * v0;
+                lg.values[3 * rec] = val[0]; lg.values[3 * rec + 1] = val[1]; lg.values[3 * rec + 2] = val[2];
+            }
+            if (st.lane_status[v]) st.status[c] |= st.lane_status[v];
+        }
+    }
+    __syncthreads();   // the log rows above read the old current state
+    if (jstar >= 0) {
+        const int w = v0 + jstar;
+        const double *prp = st.theta_prop + (size_t)w * Lt;
+        const double vp0 = st.values_prop[3 * w], vp1 = st.values_prop[3 * w + 1], vp2 = st.values_prop[3 * w + 2];
+        // BestSampleLogger.logState
+        if (vp0 > st.value_best[c])
+            for (int k = threadIdx.x; k < Lt; k += blockDim.x) st.theta_best[(size_t)c * Lt + k] = prp[k];
+        // the accepted proposal becomes the current state of every lane; its posteriors (the winner's proposal slot) become the
+        // shared current posteriors, and the winner proposes into the other slot of its pair from now on
+        for (int j = 0; j < W; j++)
+            for (int k = threadIdx.x; k < Lt; k += blockDim.x) st.theta_cur[(size_t)(v0 + j) * Lt + k] = prp[k];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (vp0 > st.value_best[c]) st.value_best[c] = vp0;
+            const int newcur = st.slot_prop[w];
+            for (int j = 0; j < W; j++) {
+                st.slot_cur[v0 + j] = newcur;
+                st.values_cur[3 * (v0 + j)] = vp0; st.values_cur[3 * (v0 + j) + 1] = vp1; st.values_cur[3 * (v0 + j) + 2] = vp2;
+            }
+            st.slot_prop[w] = newcur == w ? Cv + w : w;
+            st.n_acc[c] += 1;
+        }
+    }
+    if (threadIdx.x == 0) st.step[c] = s0 + consumed;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
@@ -428,6 +538,9 @@ struct icp_chain_s {
     DevBuf<double> theta_cur, theta_prop, values_cur, values_prop, u_acc, L, mu, X, W, theta_best, value_best, qf, qb;
     MetricsWork mwork;       // periodic RegistrationComparison of the best sample (icp_chain_io.metrics_interval)
     DevBuf<int> cur_sel, slot_cur, slot_prop, comp_sel, step, status;
+    DevBuf<int> lane_ok, lane_status, step_end;   // rejection look-ahead (k_la_resolve)
+    int lookahead = -1;      // lanes per chain: -1 automatic (8 while chains x 8 <= 64), 0 / 1 off, else the width
+    int resident_W = 1;      // width the resident state was laid out with
     bool any_svd = false;    // some ICP component samples with the reference's SVD factor
     std::vector<int> h_status;   // per-chain status words of the last synchronous run
     DevBuf<long long> n_acc;
@@ -447,6 +560,7 @@ struct icp_chain_s {
     double last_ms = 0;
     int64_t last_launches = 0;
     int last_per_step = 0;
+    int64_t last_rounds = 0;   // batched rounds of the last run (= steps without the look-ahead)
     bool use_graph = true;
     int resident_C = 0;      // chains whose state is resident from the last run (resume)
     int sized_C = 0;         // every workspace is allocated for this many chains (graph capture cannot allocate)
@@ -582,7 +696,8 @@ namespace {
 
 struct RunCtx {
     icp_chain ch;
-    int C;
+    int C;            // chains the kernels see (lanes in look-ahead mode: Cr * W)
+    int W = 1, Cr = 0;
     StateDev st;
     RngDev rng;
     LogDev lg;
@@ -647,7 +762,7 @@ void enqueue_step(RunCtx &r) {
     icp_model m = ch->model;
     const int C = r.C, Kp = m->Kp;
     ChainParams P = ch->P;
-    P.C = C;
+    P.C = C; P.W = r.W; P.Cr = r.Cr;
     size_t smem_p = sizeof(double) * ((size_t)7 * Kp + 40 + (size_t)Kp * (Kp + 1) / 2);
     {
         ProfScope ps(ST_PROPOSE, r.s);
@@ -659,14 +774,31 @@ void enqueue_step(RunCtx &r) {
         ProfScope ps(ST_ACCEPT, r.s);
         k_chain_accept<<<C, 128, sizeof(double) * 40, r.s>>>(P, r.st, r.lg, status_sources(ch));
         ICP_CUDA(cudaGetLastError());
-        k_step_increment<<<1, 1, 0, r.s>>>(r.st.step);
+        if (r.W > 1) k_la_resolve<<<r.Cr, 128, 0, r.s>>>(P, r.st, r.lg);   // one round of the look-ahead: 1 .. W steps per chain
+        else k_step_increment<<<1, 1, 0, r.s>>>(r.st.step);
         ICP_CUDA(cudaGetLastError());
     }
 }
 
+// Width of the rejection look-ahead a run of C chains will use (1 = the plain step-by-step runner). Off while profiling, with
+// periodic metrics (they are defined per step), for asynchronous runs (the look-ahead reads the step counters back between
+// batches of rounds) and for resumed runs of a state that was laid out without it.
+int lookahead_width(icp_chain ch, int C, const icp_chain_io *io, bool resume, bool may_block) {
+    if (resume) return ch->resident_W;
+    static const int env = getenv("ICPCUDA_LOOKAHEAD") ? atoi(getenv("ICPCUDA_LOOKAHEAD")) : -1;
+    int w = ch->lookahead >= 0 ? ch->lookahead : env;
+    if (g_prof || !may_block || io->metrics_interval > 0) return 1;
+    if (w < 0) w = (long long)C * 8 <= 64 ? 8 : 1;
+    if (w > 32) w = 32;
+    return w < 2 ? 1 : w;
+}
+
 // on_step(k): called on the host right after step k (1-based) of this call has been enqueued on the library stream
+// may_block: the call may synchronise with the device before it returns (the look-ahead needs that); async callers that
+// synchronise themselves afterwards (icp_chain_run) pass true
 void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev, const icp_chain_io *io, bool async,
-                      const std::function<void(int)> *on_step = nullptr) {
+                      const std::function<void(int)> *on_step = nullptr, bool may_block = false) {
+    may_block = may_block || !async;
     icp_model m = ch->model;
     icp_ctx ctx = m->ctx;
     cudaStream_t s = ctx->stream;
@@ -679,10 +811,20 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     bool host_rng = io->u_comp || io->z || io->u_acc;
     if (host_rng) ICP_REQUIRE(io->u_comp && io->z && io->u_acc, "u_comp, z and u_acc must be given together");
     const int n_icp = ch->P.n_icp;
+    // rejection look-ahead: W lanes per chain; from here on C counts lanes, Cr chains
+    const int W = on_step ? 1 : lookahead_width(ch, C, io, resume, may_block), Cr = C;
+    if (resume) ICP_REQUIRE(W == ch->resident_W, "this chain's resident state uses the rejection look-ahead: resume it without "
+                            "a per-step hook, or restart it from theta0");
+    if (W > 1) {
+        ICP_REQUIRE(io->metrics_interval == 0 && may_block, "this chain's resident state uses the rejection look-ahead: "
+                    "resume it without metrics_interval and synchronously, or restart it from theta0");
+        C = Cr * W;
+        ch->lane_ok.ensure(C); ch->lane_status.ensure(C); ch->step_end.ensure(1);
+    }
     ch->theta_cur.ensure((size_t)C * Lt); ch->theta_prop.ensure((size_t)C * Lt);
     ch->values_cur.ensure((size_t)3 * C); ch->values_prop.ensure((size_t)3 * C);
     ch->u_acc.ensure(C); ch->cur_sel.ensure(C); ch->slot_cur.ensure(C); ch->slot_prop.ensure(C);
-    ch->comp_sel.ensure(C); ch->step.ensure(1); ch->n_acc.ensure(C); ch->estatus.ensure(C); ch->status.ensure(C);
+    ch->comp_sel.ensure(C); ch->step.ensure(Cr); ch->n_acc.ensure(C); ch->estatus.ensure(C); ch->status.ensure(C);
     if (ch->any_svd) ch->W.ensure((size_t)std::max(n_icp, 1) * 2 * C * Kp * Kp);
     ch->theta_best.ensure((size_t)C * Lt); ch->value_best.ensure(C);
     ch->qf.ensure((size_t)std::max(n_icp, 1) * C); ch->qb.ensure((size_t)std::max(n_icp, 1) * C);
@@ -692,19 +834,26 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     ch->X.ensure((size_t)C * m->N * 3);
 
     RunCtx r;
-    r.ch = ch; r.C = C; r.s = s;
+    r.ch = ch; r.C = C; r.s = s; r.W = W; r.Cr = Cr;
     r.st = StateDev{ch->theta_cur.p, ch->theta_prop.p, ch->values_cur.p, ch->values_prop.p, ch->cur_sel.p,
                     ch->slot_cur.p, ch->slot_prop.p, ch->comp_sel.p, ch->u_acc.p, ch->n_acc.p, ch->step.p, ch->L.p,
                     ch->mu.p, ch->any_svd ? ch->W.p : nullptr, ch->status.p, ch->theta_best.p, ch->value_best.p,
-                    ch->qf.p, ch->qb.p};
+                    ch->qf.p, ch->qb.p, ch->lane_ok.p, ch->lane_status.p, ch->step_end.p};
     const int step_base = resume ? ch->steps_total : 0;
     r.rng = RngDev{io->seed, io->chain_id_offset, io->u_comp, io->z, io->u_acc, step_base};
     r.lg = LogDev{io->log_component, io->log_accepted, io->log_values, io->log_theta, step_base};
 
     ICP_CUDA(cudaEventRecord(ch->ev0, s));
-    if (!resume) {
+    if (!resume && W > 1) {
+        k_la_init<<<(C + 127) / 128, 128, 0, s>>>(Cr, W, Lt, theta0_dev, r.st);
+        ICP_CUDA(cudaGetLastError());
+    } else if (!resume) {
         ICP_CUDA(cudaMemcpyAsync(ch->theta_cur.p, theta0_dev, sizeof(double) * (size_t)C * Lt, cudaMemcpyDeviceToDevice, s));
         k_chain_init<<<(C + 127) / 128, 128, 0, s>>>(C, r.st);
+        ICP_CUDA(cudaGetLastError());
+    }
+    if (W > 1) {
+        k_la_set_end<<<1, 1, 0, s>>>(ch->step_end.p, step_base + n_steps);
         ICP_CUDA(cudaGetLastError());
     }
     {
@@ -715,7 +864,8 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     // state of theta0: log-values + posteriors of every ICP component (state 0)
     if (!resume) {
         enqueue_state_eval(r, ch->theta_cur.p, ch->values_cur.p, ch->slot_cur.p, false);
-        k_chain_status0<<<(C + 127) / 128, 128, 0, s>>>(C, Lt, r.st, status_sources(ch));
+        if (W > 1) k_la_status0<<<(Cr + 127) / 128, 128, 0, s>>>(Cr, W, Lt, r.st, status_sources(ch));
+        else k_chain_status0<<<(C + 127) / 128, 128, 0, s>>>(C, Lt, r.st, status_sources(ch));
         ICP_CUDA(cudaGetLastError());
     }
 
@@ -744,7 +894,7 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     cudaGraphExec_t exec = nullptr;
     if (ch->use_graph && !g_prof && n_steps - steps_done >= 1) {
         ChainParams Pk = ch->P;
-        Pk.C = C;
+        Pk.C = C; Pk.W = W; Pk.Cr = Cr;
         std::string key;
         key.append((const char *)&Pk, sizeof Pk);
         key.append((const char *)&r.st, sizeof r.st);
@@ -795,28 +945,57 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
             }
         }
     }
-    for (; steps_done < n_steps; steps_done++) {
-        if (exec) ICP_CUDA(cudaGraphLaunch(exec, s));
-        else enqueue_step(r);
-        after_step(steps_done + 1);
+    int64_t rounds_total = steps_done;
+    if (W > 1) {
+        // Rounds instead of steps: a round consumes 1 .. W steps of every unfinished chain, so remaining / W rounds can never
+        // overshoot; the step counters are read back after each batch of rounds (a few dozen synchronisations per run).
+        std::vector<int> h_step(Cr);
+        int remaining = n_steps;
+        if (steps_done > 0) remaining = -1;   // the eager first round already ran: read the counters first
+        while (true) {
+            if (remaining >= 0) {
+                const int rounds = std::max(1, remaining / W);
+                for (int k = 0; k < rounds; k++) {
+                    if (exec) ICP_CUDA(cudaGraphLaunch(exec, s));
+                    else enqueue_step(r);
+                }
+                rounds_total += rounds;
+            }
+            ICP_CUDA(cudaMemcpyAsync(h_step.data(), ch->step.p, sizeof(int) * (size_t)Cr, cudaMemcpyDeviceToHost, s));
+            ICP_CUDA(cudaStreamSynchronize(s));
+            int lo = h_step[0];
+            for (int c = 1; c < Cr; c++) lo = std::min(lo, h_step[c]);
+            remaining = step_base + n_steps - lo;
+            if (remaining <= 0) break;
+        }
+    } else {
+        for (; steps_done < n_steps; steps_done++) {
+            if (exec) ICP_CUDA(cudaGraphLaunch(exec, s));
+            else enqueue_step(r);
+            after_step(steps_done + 1);
+        }
+        rounds_total = n_steps;
     }
-    if (io->theta_final)
-        ICP_CUDA(cudaMemcpyAsync(io->theta_final, ch->theta_cur.p, sizeof(double) * (size_t)C * Lt, cudaMemcpyDeviceToDevice, s));
+    if (io->theta_final)   // look-ahead: lane 0 of every chain (all lanes hold the chain's state)
+        ICP_CUDA(cudaMemcpy2DAsync(io->theta_final, sizeof(double) * Lt, ch->theta_cur.p, sizeof(double) * Lt * W, sizeof(double) * Lt, Cr,
+                                   cudaMemcpyDeviceToDevice, s));
     if (io->n_accepted)
-        ICP_CUDA(cudaMemcpyAsync(io->n_accepted, ch->n_acc.p, sizeof(long long) * (size_t)C, cudaMemcpyDeviceToDevice, s));
+        ICP_CUDA(cudaMemcpyAsync(io->n_accepted, ch->n_acc.p, sizeof(long long) * (size_t)Cr, cudaMemcpyDeviceToDevice, s));
     if (io->status)
-        ICP_CUDA(cudaMemcpyAsync(io->status, ch->status.p, sizeof(int) * (size_t)C, cudaMemcpyDeviceToDevice, s));
+        ICP_CUDA(cudaMemcpyAsync(io->status, ch->status.p, sizeof(int) * (size_t)Cr, cudaMemcpyDeviceToDevice, s));
     if (io->theta_best)
-        ICP_CUDA(cudaMemcpyAsync(io->theta_best, ch->theta_best.p, sizeof(double) * (size_t)C * Lt, cudaMemcpyDeviceToDevice, s));
+        ICP_CUDA(cudaMemcpyAsync(io->theta_best, ch->theta_best.p, sizeof(double) * (size_t)Cr * Lt, cudaMemcpyDeviceToDevice, s));
     if (io->value_best)
-        ICP_CUDA(cudaMemcpyAsync(io->value_best, ch->value_best.p, sizeof(double) * (size_t)C, cudaMemcpyDeviceToDevice, s));
+        ICP_CUDA(cudaMemcpyAsync(io->value_best, ch->value_best.p, sizeof(double) * (size_t)Cr, cudaMemcpyDeviceToDevice, s));
     ICP_CUDA(cudaEventRecord(ch->ev1, s));
-    ch->resident_C = C;
+    ch->resident_C = Cr;
+    ch->resident_W = W;
     ch->steps_total = step_base + n_steps;
-    ch->last_launches = (int64_t)ch->last_per_step * n_steps;
+    ch->last_launches = (int64_t)ch->last_per_step * rounds_total;
+    ch->last_rounds = rounds_total;
     if (!async) {
-        ch->h_status.resize(C);
-        ICP_CUDA(cudaMemcpyAsync(ch->h_status.data(), ch->status.p, sizeof(int) * (size_t)C, cudaMemcpyDeviceToHost, s));
+        ch->h_status.resize(Cr);
+        ICP_CUDA(cudaMemcpyAsync(ch->h_status.data(), ch->status.p, sizeof(int) * (size_t)Cr, cudaMemcpyDeviceToHost, s));
         ICP_CUDA(cudaStreamSynchronize(s));
         float ms = 0;
         cudaEventElapsedTime(&ms, ch->ev0, ch->ev1);
@@ -899,8 +1078,10 @@ extern "C" int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const 
             if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
             return at.type == cudaMemoryTypeHost;
         };
+        // (not with the rejection look-ahead: its rounds finish a varying number of steps, the rows are copied at the end)
         const bool overlap = n_steps >= 2 && (io->log_component || io->log_accepted || io->log_values || io->log_theta) &&
-                             pinned(io->log_component) && pinned(io->log_accepted) && pinned(io->log_values) && pinned(io->log_theta);
+                             pinned(io->log_component) && pinned(io->log_accepted) && pinned(io->log_values) && pinned(io->log_theta) &&
+                             lookahead_width(c, C, &dio, false, true) == 1;
         int copied = 0;
         auto copy_rows = [&](cudaStream_t cs, int s0, int s1) {
             const size_t o = (size_t)s0 * C, nrow = (size_t)(s1 - s0) * C;
@@ -928,7 +1109,7 @@ extern "C" int32_t icp_chain_run(icp_chain c, int32_t C, int32_t n_steps, const 
             };
             chain_run_device(c, C, n_steps, d_theta0.p, &dio, true, &hook);
         } else {
-            chain_run_device(c, C, n_steps, d_theta0.p, &dio, true);
+            chain_run_device(c, C, n_steps, d_theta0.p, &dio, true, nullptr, true);
         }
         copy_rows(s, copied, n_steps);
         auto dl = [&](void *h, const void *d, size_t bytes) {
@@ -961,6 +1142,24 @@ extern "C" int32_t icp_chain_last_run_stats(icp_chain c, double *device_ms, int6
     if (!c) return ICP_ERR_INVALID_ARGUMENT;
     if (device_ms) *device_ms = c->last_ms;
     if (kernel_launches) *kernel_launches = c->last_launches;
+    return ICP_OK;
+}
+
+extern "C" int32_t icp_chain_set_lookahead(icp_chain c, int32_t width) {
+    if (!c || width < -1 || width > 32) return ICP_ERR_INVALID_ARGUMENT;
+    icp_ctx _ctx = c->model->ctx;
+    try {
+        CtxLock lock(_ctx);
+        c->lookahead = width;
+        return ICP_OK;
+    } catch (...) {
+        return translate_exception(_ctx);
+    }
+}
+
+extern "C" int32_t icp_chain_last_run_rounds(icp_chain c, int64_t *rounds) {
+    if (!c || !rounds) return ICP_ERR_INVALID_ARGUMENT;
+    *rounds = c->last_rounds;
     return ICP_OK;
 }
 

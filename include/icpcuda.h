@@ -306,6 +306,18 @@ int32_t icp_ctx_synchronize(icp_ctx ctx);
 /* device time in milliseconds of the last icp_chain_run* on this chain (CUDA events on the
  * library stream) and the number of kernels it launched */
 int32_t icp_chain_last_run_stats(icp_chain c, double *device_ms, int64_t *kernel_launches);
+/* Rejection look-ahead of the fused runner ("prefetching" Metropolis-Hastings). The loop of
+ * api/sampling/SamplingRegistration.scala:60-85 is sequential, and with few chains every step is a chain of dependent kernel
+ * latencies. A rejected step leaves the state where it was and the randomness of step s depends on (seed, chain, s) only, so
+ * `width` lanes per chain evaluate the proposals of steps s .. s + width - 1 from the same current state in ONE batched
+ * round; the lanes before the first accepting one are the chain's rejected steps, that lane is its next accepted step, the
+ * rest is discarded. The chain log is bit-identical to the step-by-step runner's (also with caller-supplied u_comp / z /
+ * u_acc); a round costs the latency of one step and takes (1 - (1 - a)^width) / a steps at acceptance rate a.
+ * width: -1 automatic (8 lanes while C * 8 <= 64, else off; the default, ICPCUDA_LOOKAHEAD overrides it), 0 or 1 off,
+ * 2 .. 32 that many lanes. Not used by runs with metrics_interval > 0, asynchronous icp_chain_run_device calls or
+ * icp_chain_profile. rounds (nullable): batched rounds of the last run (= its steps when the look-ahead was off). */
+int32_t icp_chain_set_lookahead(icp_chain c, int32_t width);
+int32_t icp_chain_last_run_rounds(icp_chain c, int64_t *rounds);
 
 /* ---- (7b) chain log in the reference's JSON wire format (host functions: no CUDA context needed) ---------------------- */
 /* JSONAcceptRejectLogger (api/sampling/loggers/JSONAcceptRejectLogger.scala:35,93-127) as a streaming writer and a loader.

@@ -246,6 +246,65 @@ def test_shared_handles_from_two_threads(ctx, twin31):
     ev.close(); gp.close(); model.close(); tgt.close()
 
 
+@pytest.mark.parametrize("n_chains,width", [(1, 8), (3, 4), (5, 32), (2, 2)])
+def test_rejection_lookahead_is_bit_identical(ctx, twin31, n_chains, width):
+    """icp_chain_set_lookahead: `width` lanes per chain evaluate the proposals of the next `width` steps from the same current
+    state in one batched round (SamplingRegistration.scala:60-85 is sequential; a rejected step leaves the state where it was and
+    the randomness of a step depends on (seed, chain, step) only). The chain log - components, accept decisions, log-values,
+    states - the accepted counts, the best sample and the final state must be bit-identical to the step-by-step runner's, with
+    the Philox streams and with caller-supplied random numbers, on a mixture with ICP, random-walk and pose components."""
+    m = twin31
+    K = 31
+    model, tgt = _dev(ctx, m)
+    ids = np.arange(62)
+    tp = m["target"][::26][:62]
+    pt = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.TARGET_SAMPLING, True, ids, tp)
+    pm = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.MODEL_SAMPLING, True, ids, tp, rank_update=_lib.RANK_UPDATE_INT8)
+    comps = [dict(kind=_lib.PROP_ICP, weight=0.3, proposal=pt), dict(kind=_lib.PROP_ICP, weight=0.3, proposal=pm),
+             dict(kind=_lib.PROP_RANDOM_SHAPE, weight=0.3, sd=0.15), dict(kind=2, weight=0.05, sd=0.01, axis=1), dict(kind=3, weight=0.05, sd=0.2, axis=0)]
+    ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, _lib.MODEL_TO_TARGET, True, 0.0, 1.0, 0.0, np.arange(124), tp)
+    rng = np.random.default_rng(60 + n_chains)
+    th0 = random_theta(m, rng, n_chains, alpha_sd=0.4)
+    n = 45
+    keys = ("component", "accepted", "values", "theta", "theta_final", "n_accepted", "theta_best", "value_best", "status")
+    for host_rng in (False, True):
+        kw = dict(seed=77)
+        if host_rng:
+            kw = dict(u_comp=rng.random((n, n_chains)), z=rng.normal(size=(n, n_chains, K)), u_acc=rng.random((n, n_chains)))
+        plain = core.Chain(model, tgt, comps, ev, max_chains=n_chains)
+        plain.set_lookahead(0)
+        want = plain.run(th0, n, **kw)
+        assert plain.last_run_rounds() == n
+        ahead = core.Chain(model, tgt, comps, ev, max_chains=n_chains)
+        ahead.set_lookahead(width)
+        got = ahead.run(th0, n, **kw)
+        for k in keys:
+            assert np.array_equal(got[k], want[k], equal_nan=True), f"{k} differs (host_rng={host_rng})"
+        rate = want["n_accepted"].mean() / n
+        assert 0.05 < rate < 0.98                      # both branches of the resolution are exercised
+        assert ahead.last_run_rounds() < n             # rounds took more than one step
+        plain.close(); ahead.close()
+    # resumed device-resident run: the look-ahead state carries over, the step counter and the Philox stream continue
+    import torch
+    dev = torch.device("cuda", ctx.device if hasattr(ctx, "device") else 0)
+    L = K + 10
+    outs = []
+    for width_ in (0, width):
+        ch = core.Chain(model, tgt, comps, ev, max_chains=n_chains)
+        ch.set_lookahead(width_)
+        t0 = torch.from_numpy(th0).to(dev)
+        logs = []
+        for part, first in ((20, True), (25, False)):
+            acc = torch.zeros((part, n_chains), dtype=torch.uint8, device=dev); tl = torch.zeros((part, n_chains, L), dtype=torch.float64, device=dev)
+            ch.run_device(n_chains, part, t0.data_ptr() if first else None, seed=77, log_accepted=acc.data_ptr(), log_theta=tl.data_ptr())
+            logs += [acc.cpu().numpy(), tl.cpu().numpy()]
+        outs.append(logs)
+        ch.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    ev.close(); pt.close(); pm.close(); model.close(); tgt.close()
+
+
 def test_hausdorff_early_break_is_exact(ctx, twin31):
     """HausdorffDistanceEvaluator.scala:31-35 uses only the largest distance of the two directions. The device stops every
     closest-point query that cannot raise the chain's running maximum (k_nearest, HDMAX); the value must stay the exact one:
