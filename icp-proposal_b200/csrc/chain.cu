@@ -952,7 +952,7 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
         std::vector<int> h_step(Cr);
         int remaining = n_steps;
         if (steps_done > 0) remaining = -1;   // the eager first round already ran: read the counters first
-        while (true) {
+        while (n_steps > 0) {
             if (remaining >= 0) {
                 const int rounds = std::max(1, remaining / W);
                 for (int k = 0; k < rounds; k++) {
