@@ -539,7 +539,7 @@ struct icp_chain_s {
     MetricsWork mwork;       // periodic RegistrationComparison of the best sample (icp_chain_io.metrics_interval)
     DevBuf<int> cur_sel, slot_cur, slot_prop, comp_sel, step, status;
     DevBuf<int> lane_ok, lane_status, step_end;   // rejection look-ahead (k_la_resolve)
-    int lookahead = -1;      // lanes per chain: -1 automatic (8 while chains x 8 <= 64), 0 / 1 off, else the width
+    int lookahead = -1;      // lanes per chain: -1 automatic (lookahead_width), 0 / 1 off, else the width
     int resident_W = 1;      // width the resident state was laid out with
     bool any_svd = false;    // some ICP component samples with the reference's SVD factor
     std::vector<int> h_status;   // per-chain status words of the last synchronous run
@@ -788,7 +788,9 @@ int lookahead_width(icp_chain ch, int C, const icp_chain_io *io, bool resume, bo
     static const int env = getenv("ICPCUDA_LOOKAHEAD") ? atoi(getenv("ICPCUDA_LOOKAHEAD")) : -1;
     int w = ch->lookahead >= 0 ? ch->lookahead : env;
     if (g_prof || !may_block || io->metrics_interval > 0) return 1;
-    if (w < 0) w = (long long)C * 8 <= 64 ? 8 : 1;
+    // automatic: as many lanes as still ride on latency rather than throughput (measured, tools/chains_sweep.py:
+    // profiles/r2_session3.md section 9) - 8 up to 8 chains, 4 up to 32, 2 up to 148, none beyond
+    if (w < 0) w = C <= 8 ? 8 : C <= 32 ? 4 : C <= 148 ? 2 : 1;
     if (w > 32) w = 32;
     return w < 2 ? 1 : w;
 }
