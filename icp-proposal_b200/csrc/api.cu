@@ -941,8 +941,9 @@ PosteriorLease::PosteriorLease(icp_proposal p_, icp_proposal_s::Call &cs, int C,
     : p(p_) {
     icp_model m = p->model;
     const int Kp = m->Kp, Lt = m->K + kTheta0;
-    // room for sixteen concurrent calls of this size plus the 20 states Memoize keeps
-    const int want = 32 + 4 * C + kMaxCallSlots * C;
+    // the 20 states Memoize keeps and room for a handful of concurrent calls of this size (a call that finds every slot pinned
+    // by others waits for one of them to finish, holding nothing)
+    const int want = 32 + 6 * C;
     rd = std::shared_lock<std::shared_mutex>(p->cache_rw);
     while (p->cache_slots < want) {
         rd.unlock();

@@ -15,6 +15,40 @@ from icp_proposal_b200 import _lib, core
 pytestmark = pytest.mark.gpu
 
 
+def write_model_bin(path, m, K, ids, eids, tp):
+    """The binary the C++ examples read: sizes, then the double arrays, then the int32 arrays."""
+    with open(path, "wb") as f:
+        np.array([len(m["ref"]), len(m["cells"]), K, len(m["target"]), len(m["target_cells"]), len(ids), len(tp), len(eids)], np.int32).tofile(f)
+        for a in (m["ref"], m["basis"], m["variance"], m["target"], tp):
+            np.ascontiguousarray(a, np.float64).tofile(f)
+        for a in (m["cells"], m["target_cells"], ids, eids):
+            np.ascontiguousarray(a, np.int32).tofile(f)
+
+
+def test_cpp_threads_on_shared_handles(ctx, twin31, tmp_path):
+    """examples/per_call_threads.cpp: ten std::threads (no GIL - what JVM threads would see) drive their own Metropolis-Hastings
+    walks through the per-call C ABI on ONE shared pair of proposals and ONE shared evaluator
+    (RunMHRandomInitComparison.scala:59-86); every walk must end exactly where it ends when it runs alone."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    m = twin31
+    K = 31
+    ids = np.arange(2 * K, dtype=np.int32)
+    eids = np.arange(4 * K, dtype=np.int32)
+    tp = np.ascontiguousarray(m["target"][::26][:2 * K])
+    path = tmp_path / "model.bin"
+    write_model_bin(path, m, K, ids, eids, tp)
+    exe = tmp_path / "per_call_threads"
+    libdir = os.path.join(ROOT, "icp-proposal_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "per_call_threads.cpp"), "-o", str(exe), "-L", libdir, "-licpcuda", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe), str(path), "10", "25"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["threads"] == 10 and res["failed_threads"] == 0 and res["walks_that_differ_from_the_serial_run"] == 0
+    assert 0 < res["accepted_total"] < 250
+
+
 def test_cpp_host_mirror_example(ctx, twin31, tmp_path):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
@@ -24,12 +58,7 @@ def test_cpp_host_mirror_example(ctx, twin31, tmp_path):
     eids = np.arange(4 * K, dtype=np.int32)
     tp = np.ascontiguousarray(m["target"][::26][:2 * K])
     path = tmp_path / "model.bin"
-    with open(path, "wb") as f:
-        np.array([len(m["ref"]), len(m["cells"]), K, len(m["target"]), len(m["target_cells"]), len(ids), len(tp), len(eids)], np.int32).tofile(f)
-        for a in (m["ref"], m["basis"], m["variance"], m["target"], tp):
-            np.ascontiguousarray(a, np.float64).tofile(f)
-        for a in (m["cells"], m["target_cells"], ids, eids):
-            np.ascontiguousarray(a, np.int32).tofile(f)
+    write_model_bin(path, m, K, ids, eids, tp)
     exe = tmp_path / "icp_proposal_registration"
     libdir = os.path.join(ROOT, "icp-proposal_b200")
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(libdir, "host"),
