@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <unordered_map>
 
 #include "icp_device.cuh"
@@ -33,9 +34,11 @@ struct CompDev {
 
 struct ChainParams {
     int n_comp, n_icp, K, Kp, C;
-    // Rejection look-ahead (see enqueue_round): W > 1 lanes per chain. C then counts the lanes (C = Cr * W, lane v belongs to
-    // chain v / W) and every per-chain array of StateDev is per lane, except step / n_acc / status / theta_best / value_best.
-    int W, Cr;
+    // Rejection look-ahead (see k_la_resolve): W > 1 lanes per chain. C then counts the lanes (C = Cr * W; lane-major: lane v is
+    // lane v / Cr of chain v % Cr, so the first Cr * Wa entries are the lanes 0 .. Wa - 1 of every chain) and every per-chain
+    // array of StateDev is per lane, except step / n_acc / status / theta_best / value_best. Wa <= W lanes are active in this
+    // round (the kernels are launched over Cr * Wa lanes; C stays the stride of the per-lane arrays).
+    int W, Cr, Wa;
     CompDev comp[kMaxComp];
 };
 
@@ -208,10 +211,10 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
     // look-ahead: lane c proposes step step[chain] + lane index of chain c / W from the chain's current state; the randomness
     // of a step is a function of (seed, chain, step) only, so this is the proposal the sequential chain makes at that step
     // if every step before it is rejected. Lanes past the end of the run repeat the last step (ignored by k_la_resolve).
-    const int cr = P.W > 1 ? c / P.W : c, Cr = P.W > 1 ? P.Cr : C;
+    const int cr = P.W > 1 ? c % P.Cr : c, Cr = P.W > 1 ? P.Cr : C;
     unsigned int step = (unsigned int)*st.step;
     if (P.W > 1) {
-        int sv = st.step[cr] + (c - cr * P.W);
+        int sv = st.step[cr] + c / P.Cr;
         const int last = *st.step_end - 1;
         step = (unsigned int)(sv > last ? last : sv);
     }
@@ -447,7 +450,7 @@ __global__ void k_la_init(int Cr, int W, int Lt, const double *__restrict__ thet
     st.cur_sel[v] = 0;
     st.slot_cur[v] = v;
     st.slot_prop[v] = Cv + v;
-    const double *src = theta0 + (size_t)(v / W) * Lt;
+    const double *src = theta0 + (size_t)(v % Cr) * Lt;
     for (int j = 0; j < Lt; j++) st.theta_cur[(size_t)v * Lt + j] = src[j];
 }
 
@@ -457,7 +460,7 @@ __global__ void k_la_set_end(int *step_end, int value) { *step_end = value; }
 __global__ void k_la_status0(int Cr, int W, int Lt, StateDev st, StatusSrc ss) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= Cr) return;
-    const int v = c * W;
+    const int v = c;   // lane 0
     int s = fold_status(ss, v);
     const double p = st.values_cur[3 * v];
     if (p != p) s |= kStNanValue;
@@ -468,19 +471,19 @@ __global__ void k_la_status0(int Cr, int W, int Lt, StateDev st, StatusSrc ss) {
 
 __global__ void __launch_bounds__(128) k_la_resolve(ChainParams P, StateDev st, LogDev lg) {
     const int W = P.W, Cr = P.Cr, Cv = P.C, Lt = P.K + kTheta0;
-    const int c = blockIdx.x, v0 = c * W;
+    const int c = blockIdx.x, v0 = c;             // lane j of chain c is entry c + j * Cr
     const int s0 = st.step[c];
     int limit = *st.step_end - s0;
-    if (limit > W) limit = W;
+    if (limit > P.Wa) limit = P.Wa;               // lanes that ran in this round
     if (limit <= 0) return;                       // this chain has taken all its steps
     int jstar = -1;
     for (int j = 0; j < limit; j++)
-        if (st.lane_ok[v0 + j]) { jstar = j; break; }
+        if (st.lane_ok[v0 + j * Cr]) { jstar = j; break; }
     const int consumed = jstar >= 0 ? jstar + 1 : limit;
     // records of the consumed steps: the state that is current after each of them (JSONAcceptRejectLogger.scala:93-106)
     const double *cur = st.theta_cur + (size_t)v0 * Lt;
     for (int j = 0; j < consumed; j++) {
-        const int v = v0 + j;
+        const int v = v0 + j * Cr;
         const bool ok = j == jstar;
         const size_t rec = (size_t)(s0 + j - lg.step_base) * Cr + c;
         if (lg.theta) {
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(128) k_la_resolve(ChainParams P, StateDev st, 
     }
     __syncthreads();   // the log rows above read the old current state
     if (jstar >= 0) {
-        const int w = v0 + jstar;
+        const int w = v0 + jstar * Cr;
         const double *prp = st.theta_prop + (size_t)w * Lt;
         const double vp0 = st.values_prop[3 * w], vp1 = st.values_prop[3 * w + 1], vp2 = st.values_prop[3 * w + 2];
         // BestSampleLogger.logState
@@ -508,14 +511,15 @@ __global__ void __launch_bounds__(128) k_la_resolve(ChainParams P, StateDev st, 
         // the accepted proposal becomes the current state of every lane; its posteriors (the winner's proposal slot) become the
         // shared current posteriors, and the winner proposes into the other slot of its pair from now on
         for (int j = 0; j < W; j++)
-            for (int k = threadIdx.x; k < Lt; k += blockDim.x) st.theta_cur[(size_t)(v0 + j) * Lt + k] = prp[k];
+            for (int k = threadIdx.x; k < Lt; k += blockDim.x) st.theta_cur[(size_t)(v0 + j * Cr) * Lt + k] = prp[k];
         __syncthreads();
         if (threadIdx.x == 0) {
             if (vp0 > st.value_best[c]) st.value_best[c] = vp0;
             const int newcur = st.slot_prop[w];
             for (int j = 0; j < W; j++) {
-                st.slot_cur[v0 + j] = newcur;
-                st.values_cur[3 * (v0 + j)] = vp0; st.values_cur[3 * (v0 + j) + 1] = vp1; st.values_cur[3 * (v0 + j) + 2] = vp2;
+                const int v = v0 + j * Cr;
+                st.slot_cur[v] = newcur;
+                st.values_cur[3 * v] = vp0; st.values_cur[3 * v + 1] = vp1; st.values_cur[3 * v + 2] = vp2;
             }
             st.slot_prop[w] = newcur == w ? Cv + w : w;
             st.n_acc[c] += 1;
@@ -539,7 +543,8 @@ struct icp_chain_s {
     MetricsWork mwork;       // periodic RegistrationComparison of the best sample (icp_chain_io.metrics_interval)
     DevBuf<int> cur_sel, slot_cur, slot_prop, comp_sel, step, status;
     DevBuf<int> lane_ok, lane_status, step_end;   // rejection look-ahead (k_la_resolve)
-    int lookahead = -1;      // lanes per chain: -1 automatic (lookahead_width), 0 / 1 off, else the width
+    int lookahead = -1;      // lanes per chain: -1 automatic (lookahead_width) with the active width adapted while the run
+                             // goes (chain_run_device), 0 / 1 off, else exactly that width
     int resident_W = 1;      // width the resident state was laid out with
     bool any_svd = false;    // some ICP component samples with the reference's SVD factor
     std::vector<int> h_status;   // per-chain status words of the last synchronous run
@@ -566,6 +571,12 @@ struct icp_chain_s {
     int sized_C = 0;         // every workspace is allocated for this many chains (graph capture cannot allocate)
     cudaGraphExec_t exec = nullptr;   // cached step graph + the bytes of the kernel arguments it was captured with
     std::string exec_key;
+    std::map<int, cudaGraphExec_t> exec_wa;   // look-ahead: the round graphs of the other active widths under the same key
+    // what the adaptive look-ahead has learnt on this chain object (kept across runs of the same shape): ms per round of
+    // every active width tried, the smoothed acceptance rate
+    std::map<int, double> la_t_round;
+    double la_a_hat = -1.0;
+    int la_Cr = 0, la_W = 0;
     DevBuf<double> d_theta0, d_final;   // persistent staging of the host-buffer entry point
     DevBuf<long long> d_nacc;
     int steps_total = 0;     // value of the device step counter
@@ -679,6 +690,7 @@ extern "C" int32_t icp_chain_destroy(icp_chain c) {
         CtxLock lock(_ctx);
         ICP_CUDA(cudaStreamSynchronize(_ctx->stream));
         if (c->exec) cudaGraphExecDestroy(c->exec);
+        for (auto &kv : c->exec_wa) if (kv.second) cudaGraphExecDestroy(kv.second);
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
         if (c->copy_ev) cudaEventDestroy(c->copy_ev);
@@ -696,8 +708,9 @@ namespace {
 
 struct RunCtx {
     icp_chain ch;
-    int C;            // chains the kernels see (lanes in look-ahead mode: Cr * W)
-    int W = 1, Cr = 0;
+    int C;            // stride of the per-chain arrays (lanes in look-ahead mode: Cr * W)
+    int Cn = 0;       // entries the kernels of this step / round process (C, or Cr * Wa with Wa active lanes)
+    int W = 1, Cr = 0, Wa = 1;
     StateDev st;
     RngDev rng;
     LogDev lg;
@@ -712,9 +725,9 @@ struct RunCtx {
 void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, const int *d_slots, bool proposal) {
     icp_chain ch = r.ch;
     icp_model m = ch->model;
-    const int C = r.C, Kp = m->Kp;
+    const int C = r.C, Cn = r.Cn, Kp = m->Kp;   // C: stride of the posterior / form arrays, Cn: entries to evaluate
     icp_ctx ctx = m->ctx;
-    launch_reconstruct(m->dev(), C, d_theta, ch->X.p, r.s);
+    launch_reconstruct(m->dev(), Cn, d_theta, ch->X.p, r.s);
     // fork: ICP pipelines that do not consume the evaluator's closest points run on side streams, concurrently with
     // the evaluator and with each other (their Cholesky phases are latency bound and overlap the DMMA of the rest).
     // Profiling runs stay on one stream so that the per-kernel event times do not overlap.
@@ -731,19 +744,19 @@ void enqueue_state_eval(RunCtx &r, const double *d_theta, double *d_values, cons
         double *Lb = r.st.L + (size_t)i * 2 * C * Kp * Kp, *mub = r.st.mu + (size_t)i * 2 * C * Kp;
         double *Wb = ch->icp_props[i]->prm.factor == ICP_FACTOR_SVD ? r.st.W + (size_t)i * 2 * C * Kp * Kp : nullptr;
         QuadArgs qa{r.st.theta_prop, r.st.theta_cur, ch->icp_props[i]->prm.step_length, m->K, r.st.qb + (size_t)i * C};
-        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, ss, nullptr, Wb, proposal ? &qa : nullptr);
+        posterior_pipeline(ch->icp_props[i], Cn, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, ss, nullptr, Wb, proposal ? &qa : nullptr);
         ICP_CUDA(cudaEventRecord(ctx->ev_join[n_side], ss));
         ch->on_side[i] = 1;
         n_side++;
     }
-    evaluator_pipeline(ch->evaluator, ch->ework, C, d_theta, ch->X.p, d_values, ch->estatus.p, r.s);
+    evaluator_pipeline(ch->evaluator, ch->ework, Cn, d_theta, ch->X.p, d_values, ch->estatus.p, r.s);
     for (int i = 0; i < ch->P.n_icp; i++) {
         if (ch->on_side[i]) { ch->on_side[i] = 0; continue; }
         double *Lb = r.st.L + (size_t)i * 2 * C * Kp * Kp, *mub = r.st.mu + (size_t)i * 2 * C * Kp;
         SharedCp sh{ch->ework.cp_m2t.p, ch->evaluator->n_ids, ch->cp_map[i].p};
         double *Wb = ch->icp_props[i]->prm.factor == ICP_FACTOR_SVD ? r.st.W + (size_t)i * 2 * C * Kp * Kp : nullptr;
         QuadArgs qa{r.st.theta_prop, r.st.theta_cur, ch->icp_props[i]->prm.step_length, m->K, r.st.qb + (size_t)i * C};
-        posterior_pipeline(ch->icp_props[i], C, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, r.s, ch->cp_shared[i] ? &sh : nullptr, Wb,
+        posterior_pipeline(ch->icp_props[i], Cn, d_theta, ch->X.p, ch->pwork[i], Lb, mub, d_slots, r.s, ch->cp_shared[i] ? &sh : nullptr, Wb,
                            proposal ? &qa : nullptr);
     }
     for (int k = 0; k < n_side; k++) ICP_CUDA(cudaStreamWaitEvent(r.s, ctx->ev_join[k], 0));   // join
@@ -760,19 +773,19 @@ StatusSrc status_sources(icp_chain ch) {
 void enqueue_step(RunCtx &r) {
     icp_chain ch = r.ch;
     icp_model m = ch->model;
-    const int C = r.C, Kp = m->Kp;
+    const int C = r.C, Cn = r.Cn, Kp = m->Kp;
     ChainParams P = ch->P;
-    P.C = C; P.W = r.W; P.Cr = r.Cr;
+    P.C = C; P.W = r.W; P.Cr = r.Cr; P.Wa = r.Wa;
     size_t smem_p = sizeof(double) * ((size_t)7 * Kp + 40 + (size_t)Kp * (Kp + 1) / 2);
     {
         ProfScope ps(ST_PROPOSE, r.s);
-        k_chain_propose<<<C, 256, smem_p, r.s>>>(P, m->dev(), r.st, r.rng);
+        k_chain_propose<<<Cn, 256, smem_p, r.s>>>(P, m->dev(), r.st, r.rng);
         ICP_CUDA(cudaGetLastError());
     }
     enqueue_state_eval(r, r.st.theta_prop, r.st.values_prop, r.st.slot_prop, true);
     {
         ProfScope ps(ST_ACCEPT, r.s);
-        k_chain_accept<<<C, 128, sizeof(double) * 40, r.s>>>(P, r.st, r.lg, status_sources(ch));
+        k_chain_accept<<<Cn, 128, sizeof(double) * 40, r.s>>>(P, r.st, r.lg, status_sources(ch));
         ICP_CUDA(cudaGetLastError());
         if (r.W > 1) k_la_resolve<<<r.Cr, 128, 0, r.s>>>(P, r.st, r.lg);   // one round of the look-ahead: 1 .. W steps per chain
         else k_step_increment<<<1, 1, 0, r.s>>>(r.st.step);
@@ -836,7 +849,7 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     ch->X.ensure((size_t)C * m->N * 3);
 
     RunCtx r;
-    r.ch = ch; r.C = C; r.s = s; r.W = W; r.Cr = Cr;
+    r.ch = ch; r.C = C; r.Cn = C; r.s = s; r.W = W; r.Cr = Cr; r.Wa = W;
     r.st = StateDev{ch->theta_cur.p, ch->theta_prop.p, ch->values_cur.p, ch->values_prop.p, ch->cur_sel.p,
                     ch->slot_cur.p, ch->slot_prop.p, ch->comp_sel.p, ch->u_acc.p, ch->n_acc.p, ch->step.p, ch->L.p,
                     ch->mu.p, ch->any_svd ? ch->W.p : nullptr, ch->status.p, ch->theta_best.p, ch->value_best.p,
@@ -894,9 +907,41 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
         after_step(steps_done);
     }
     cudaGraphExec_t exec = nullptr;
-    if (ch->use_graph && !g_prof && n_steps - steps_done >= 1) {
+    // captures the step / round r describes (r.Cn entries, r.Wa active lanes) as a graph; nullptr when that fails
+    auto capture = [&](int *per_step_out) -> cudaGraphExec_t {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t ex = nullptr;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        bool ok = true;
+        try {
+            enqueue_step(r);
+        } catch (...) {
+            ok = false;
+        }
+        cudaError_t e = cudaStreamEndCapture(s, &graph);
+        if (!ok || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return nullptr;
+        }
+        size_t nn = 0;
+        int per_step = 0;
+        cudaGraphGetNodes(graph, nullptr, &nn);
+        std::vector<cudaGraphNode_t> nodes(nn);
+        cudaGraphGetNodes(graph, nodes.data(), &nn);
+        for (size_t i = 0; i < nn; i++) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) per_step++;
+        }
+        if (cudaGraphInstantiate(&ex, graph, 0) != cudaSuccess) { ex = nullptr; cudaGetLastError(); }
+        cudaGraphDestroy(graph);
+        if (ex && per_step_out) *per_step_out = per_step;
+        return ex;
+    };
+    const bool graphs = ch->use_graph && !g_prof && n_steps - steps_done >= 1;
+    if (graphs) {
         ChainParams Pk = ch->P;
-        Pk.C = C; Pk.W = W; Pk.Cr = Cr;
+        Pk.C = C; Pk.W = W; Pk.Cr = Cr; Pk.Wa = W;
         std::string key;
         key.append((const char *)&Pk, sizeof Pk);
         key.append((const char *)&r.st, sizeof r.st);
@@ -910,66 +955,119 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
                                     m->vert_bvh.nodes.p, m->vert_bvh.nodebox.p, m->vert_bvh.counters.p};
             key.append((const char *)shared, sizeof shared);
         }
-        if (ch->exec && ch->exec_key == key) {
-            exec = ch->exec;
-        } else {
+        if (!(ch->exec && ch->exec_key == key)) {
             if (ch->exec) { cudaGraphExecDestroy(ch->exec); ch->exec = nullptr; }
-            cudaGraph_t graph = nullptr;
-            cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
-            if (e == cudaSuccess) {
-                bool ok = true;
-                try {
-                    enqueue_step(r);
-                } catch (...) {
-                    ok = false;
-                }
-                e = cudaStreamEndCapture(s, &graph);
-                if (!ok || e != cudaSuccess || !graph) {
-                    if (graph) cudaGraphDestroy(graph);
-                    graph = nullptr;
-                    cudaGetLastError();
-                } else {
-                    size_t nn = 0;
-                    int per_step = 0;
-                    cudaGraphGetNodes(graph, nullptr, &nn);
-                    std::vector<cudaGraphNode_t> nodes(nn);
-                    cudaGraphGetNodes(graph, nodes.data(), &nn);
-                    for (size_t i = 0; i < nn; i++) {
-                        cudaGraphNodeType ty;
-                        if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) per_step++;
-                    }
-                    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { exec = nullptr; cudaGetLastError(); }
-                    cudaGraphDestroy(graph);
-                    if (exec) { ch->exec = exec; ch->exec_key = key; ch->last_per_step = per_step; }
-                }
-            } else {
-                cudaGetLastError();
-            }
+            for (auto &kv : ch->exec_wa)
+                if (kv.second) cudaGraphExecDestroy(kv.second);
+            ch->exec_wa.clear();
+            ch->exec_key = key;
+            int per_step = 0;
+            ch->exec = capture(&per_step);      // full width (r.Wa == W)
+            if (ch->exec) ch->last_per_step = per_step;
         }
+        exec = ch->exec;
     }
-    int64_t rounds_total = steps_done;
+    int64_t rounds_total = steps_done, launches_total = (int64_t)ch->last_per_step * steps_done;
     if (W > 1) {
-        // Rounds instead of steps: a round consumes 1 .. W steps of every unfinished chain, so remaining / W rounds can never
-        // overshoot; the step counters are read back after each batch of rounds (a few dozen synchronisations per run).
+        // Rounds instead of steps. A round of Wa active lanes consumes 1 .. Wa steps of every unfinished chain, so remaining / Wa
+        // rounds can never overshoot; the step and acceptance counters are read back after each batch of rounds.
+        // With the automatic width (ch->lookahead < 0) the ACTIVE width adapts while the run goes: the lanes are laid out lane
+        // major, so a round over the first Cr * Wa entries runs the lanes 0 .. Wa - 1 of every chain. A batch is timed with
+        // events; the next batch takes the width with the largest expected steps per millisecond,
+        // (1 - (1 - a)^w) / (a t_w), from the measured acceptance rate a and the measured (or, for a width not tried yet, the
+        // neighbour's) round time t_w. Wide rounds win when steps are rejected and lanes are cheap (few chains, small point
+        // sets); a chain that accepts everything, or lanes that already fill the GPU, settle at one lane.
+        const bool adaptive = ch->lookahead < 0 && graphs;
+        std::vector<int> widths;
+        for (int w = 1; w < W; w *= 2) widths.push_back(w);
+        widths.push_back(W);
+        if (ch->la_Cr != Cr || ch->la_W != W) { ch->la_t_round.clear(); ch->la_a_hat = -1.0; ch->la_Cr = Cr; ch->la_W = W; }
+        std::map<int, double> &t_round = ch->la_t_round;       // measured ms per round at a width
         std::vector<int> h_step(Cr);
-        int remaining = n_steps;
-        if (steps_done > 0) remaining = -1;   // the eager first round already ran: read the counters first
-        while (n_steps > 0) {
-            if (remaining >= 0) {
-                const int rounds = std::max(1, remaining / W);
+        std::vector<long long> h_acc(Cr);
+        cudaEvent_t eb0 = nullptr, eb1 = nullptr;
+        ICP_CUDA(cudaEventCreate(&eb0));
+        ICP_CUDA(cudaEventCreate(&eb1));
+        auto read_counters = [&](long long &steps_sum, long long &acc_sum, int &lo) {
+            ICP_CUDA(cudaMemcpyAsync(h_step.data(), ch->step.p, sizeof(int) * (size_t)Cr, cudaMemcpyDeviceToHost, s));
+            ICP_CUDA(cudaMemcpyAsync(h_acc.data(), ch->n_acc.p, sizeof(long long) * (size_t)Cr, cudaMemcpyDeviceToHost, s));
+            ICP_CUDA(cudaStreamSynchronize(s));
+            steps_sum = 0; acc_sum = 0; lo = h_step[0];
+            for (int c = 0; c < Cr; c++) { steps_sum += h_step[c]; acc_sum += h_acc[c]; lo = std::min(lo, h_step[c]); }
+        };
+        long long steps0 = 0, acc0 = 0;
+        int lo = 0;
+        try {
+            read_counters(steps0, acc0, lo);
+            int remaining = step_base + n_steps - lo;
+            double a_hat = ch->la_a_hat >= 0.0 ? ch->la_a_hat : 0.5;   // acceptance rate, smoothed over the batches
+            int wa = adaptive ? 1 : W, batches = ch->la_a_hat >= 0.0 ? 1 : 0;
+            // every width not timed yet is timed once (8 rounds each), narrowest first: a short run costs what the plain
+            // step-by-step run costs
+            std::vector<int> probe;
+            for (int w : widths)
+                if (!t_round.count(w)) probe.push_back(w);
+            while (remaining > 0) {
+                bool probing = false;
+                if (adaptive && !probe.empty() && (t_round.empty() || remaining >= 64)) {   // no experiments at the end of a run
+                    wa = probe.front();
+                    probe.erase(probe.begin());
+                    probing = true;
+                } else if (adaptive) {
+                    // expected steps per millisecond of every width; ties go to the narrower round
+                    double best_rate = -1.0;
+                    int best_w = wa;
+                    const double a = std::min(std::max(a_hat, 1e-3), 1.0);
+                    for (int w : widths) {
+                        auto it = t_round.find(w);
+                        if (it == t_round.end() || it->second <= 0.0) continue;
+                        const double rate = (1.0 - std::pow(1.0 - a, w)) / a / it->second;
+                        if (rate > best_rate * 1.02) { best_rate = rate; best_w = w; }
+                    }
+                    wa = best_w;
+                }
+                // a batch: at most 128 rounds (the acceptance rate drifts), never past the end of the run
+                int rounds = std::max(1, std::min(remaining / wa, adaptive ? (probing ? 8 : 128) : (1 << 30)));
+                r.Wa = wa; r.Cn = Cr * wa;
+                cudaGraphExec_t ex = nullptr;
+                if (graphs) {
+                    if (wa == W) ex = exec;
+                    else {
+                        auto it = ch->exec_wa.find(wa);
+                        if (it == ch->exec_wa.end()) it = ch->exec_wa.emplace(wa, capture(nullptr)).first;
+                        ex = it->second;
+                    }
+                }
+                ICP_CUDA(cudaEventRecord(eb0, s));
                 for (int k = 0; k < rounds; k++) {
-                    if (exec) ICP_CUDA(cudaGraphLaunch(exec, s));
+                    if (ex) ICP_CUDA(cudaGraphLaunch(ex, s));
                     else enqueue_step(r);
                 }
+                ICP_CUDA(cudaEventRecord(eb1, s));
                 rounds_total += rounds;
+                launches_total += (int64_t)ch->last_per_step * rounds;
+                long long steps1 = 0, acc1 = 0;
+                read_counters(steps1, acc1, lo);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, eb0, eb1);
+                const double t = ms / rounds;
+                auto it = t_round.find(wa);
+                if (it == t_round.end()) t_round[wa] = t; else it->second = 0.5 * it->second + 0.5 * t;
+                if (steps1 > steps0) {
+                    const double a = (double)(acc1 - acc0) / (double)(steps1 - steps0);
+                    a_hat = batches == 0 ? a : 0.5 * a_hat + 0.5 * a;
+                }
+                steps0 = steps1; acc0 = acc1;
+                remaining = step_base + n_steps - lo;
+                batches++;
             }
-            ICP_CUDA(cudaMemcpyAsync(h_step.data(), ch->step.p, sizeof(int) * (size_t)Cr, cudaMemcpyDeviceToHost, s));
-            ICP_CUDA(cudaStreamSynchronize(s));
-            int lo = h_step[0];
-            for (int c = 1; c < Cr; c++) lo = std::min(lo, h_step[c]);
-            remaining = step_base + n_steps - lo;
-            if (remaining <= 0) break;
+            if (batches > 0) ch->la_a_hat = a_hat;
+        } catch (...) {
+            cudaEventDestroy(eb0); cudaEventDestroy(eb1);
+            throw;
         }
+        cudaEventDestroy(eb0); cudaEventDestroy(eb1);
+        r.Wa = W; r.Cn = C;
     } else {
         for (; steps_done < n_steps; steps_done++) {
             if (exec) ICP_CUDA(cudaGraphLaunch(exec, s));
@@ -977,10 +1075,10 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
             after_step(steps_done + 1);
         }
         rounds_total = n_steps;
+        launches_total = (int64_t)ch->last_per_step * n_steps;
     }
-    if (io->theta_final)   // look-ahead: lane 0 of every chain (all lanes hold the chain's state)
-        ICP_CUDA(cudaMemcpy2DAsync(io->theta_final, sizeof(double) * Lt, ch->theta_cur.p, sizeof(double) * Lt * W, sizeof(double) * Lt, Cr,
-                                   cudaMemcpyDeviceToDevice, s));
+    if (io->theta_final)   // look-ahead: lane 0 of every chain = the first Cr entries (all lanes hold the chain's state)
+        ICP_CUDA(cudaMemcpyAsync(io->theta_final, ch->theta_cur.p, sizeof(double) * (size_t)Cr * Lt, cudaMemcpyDeviceToDevice, s));
     if (io->n_accepted)
         ICP_CUDA(cudaMemcpyAsync(io->n_accepted, ch->n_acc.p, sizeof(long long) * (size_t)Cr, cudaMemcpyDeviceToDevice, s));
     if (io->status)
@@ -993,7 +1091,7 @@ void chain_run_device(icp_chain ch, int C, int n_steps, const double *theta0_dev
     ch->resident_C = Cr;
     ch->resident_W = W;
     ch->steps_total = step_base + n_steps;
-    ch->last_launches = (int64_t)ch->last_per_step * rounds_total;
+    ch->last_launches = launches_total;
     ch->last_rounds = rounds_total;
     if (!async) {
         ch->h_status.resize(Cr);

@@ -313,8 +313,10 @@ int32_t icp_chain_last_run_stats(icp_chain c, double *device_ms, int64_t *kernel
  * round; the lanes before the first accepting one are the chain's rejected steps, that lane is its next accepted step, the
  * rest is discarded. The chain log is bit-identical to the step-by-step runner's (also with caller-supplied u_comp / z /
  * u_acc); a round costs the latency of one step and takes (1 - (1 - a)^width) / a steps at acceptance rate a.
- * width: -1 automatic (8 lanes up to 8 chains, 4 up to 32, 2 up to 148, off beyond; the default, ICPCUDA_LOOKAHEAD overrides it), 0 or 1 off,
- * 2 .. 32 that many lanes. Not used by runs with metrics_interval > 0, asynchronous icp_chain_run_device calls or
+ * width: -1 automatic (the default; ICPCUDA_LOOKAHEAD overrides it): up to 8 lanes for up to 8 chains, 4 up to 32, 2 up to 148, none
+ * beyond, and the number of lanes that are ACTIVE in a round adapts while the run goes - every active width is timed once, then
+ * each batch of rounds takes the width with the most expected steps per millisecond at the measured acceptance rate, so a chain
+ * that accepts everything, or lanes that already fill the GPU, run at one lane; 0 or 1 off; 2 .. 32 exactly that many lanes. Not used by runs with metrics_interval > 0, asynchronous icp_chain_run_device calls or
  * icp_chain_profile. rounds (nullable): batched rounds of the last run (= its steps when the look-ahead was off). */
 int32_t icp_chain_set_lookahead(icp_chain c, int32_t width);
 int32_t icp_chain_last_run_rounds(icp_chain c, int64_t *rounds);

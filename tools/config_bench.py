@@ -21,11 +21,14 @@ def run(name, model, tgt, comps, ev, th0, steps):
     C = len(th0)
     chain = core.Chain(model, tgt, comps, ev, max_chains=C)
     chain.run(th0, 3, seed=5, log_theta=False)
+    if C <= 148:      # latency-bound batches: a longer run (the adaptive look-ahead times its widths during the first ~100 steps)
+        steps = int(os.environ.get("SMALL_STEPS", "400"))
+        chain.run(th0, 150, seed=6, log_theta=False)
     r = chain.run(th0, steps, seed=6, log_theta=False)
     ms, launches = chain.last_run_stats()
     prof = chain.profile(th0, 4, seed=7)
     out[name] = {"chains": C, "steps": steps, "ms_per_step": ms / steps, "samples_per_s": C * steps / (ms * 1e-3),
-                 "accept_rate": float(r["n_accepted"].mean() / steps), "launches": launches,
+                 "accept_rate": float(r["n_accepted"].mean() / steps), "launches": launches, "rounds": chain.last_run_rounds(),
                  "stage_ms_per_step": {k: round(v["ms"] / 4, 4) for k, v in prof.items() if v["launches"]}}
     print(name, json.dumps(out[name]), flush=True)
     chain.close()
