@@ -101,6 +101,10 @@ constexpr int kRmV = 96;        // vertices per CTA (three groups of 8 per warp 
 constexpr int kRmC = 32;        // chains per CTA
 constexpr int kRmLd = 34;       // row stride (doubles) of the coefficient tile and of the staged result
 
+// RMV: vertices per CTA. kRmV for full batches; 32 (one group of 8 per warp) when the grid would not fill the GPU - a few chains
+// are a chain of dependent kernel latencies, and three groups in sequence are three times the latency of one. The arithmetic of
+// a vertex does not depend on RMV.
+template <int RMV>
 __global__ void __launch_bounds__(128) k_reconstruct_mma(ModelDev m, int C, const double *__restrict__ theta,
                                                          double *__restrict__ X) {
     extern __shared__ __align__(16) double sm[];
@@ -145,8 +149,8 @@ __global__ void __launch_bounds__(128) k_reconstruct_mma(ModelDev m, int C, cons
     const int last_row = 3 * m.N - 1;
     const double *sb = sa + (2 * q) * kRmLd + g;
     double *sx = sp + kRmC * 16 + (size_t)warp * 24 * kRmLd;   // [24 rows][kRmLd], private to the warp
-    for (int grp = 0; grp < kRmV / 32; grp++) {
-        const int v0 = blockIdx.x * kRmV + grp * 32 + warp * 8;
+    for (int grp = 0; grp < RMV / 32; grp++) {
+        const int v0 = blockIdx.x * RMV + grp * 32 + warp * 8;
         if (v0 >= m.N) break;                        // warp-uniform
         const double2 *qa0, *qa1, *qa2;
         qa0 = reinterpret_cast<const double2 *>(m.Q + (size_t)min(3 * v0 + g, last_row) * Kp) + q;        // rows past the mesh are
@@ -217,8 +221,14 @@ void launch_reconstruct(const ModelDev &m, int C, const double *d_theta, double 
     if (!no_mma) {   // every batch size takes the same kernel: a chain's mesh must not depend on how chains are batched or sharded
         dim3 grid((m.N + kRmV - 1) / kRmV, (C + kRmC - 1) / kRmC);
         const size_t smem = sizeof(double) * ((size_t)m.Kp * kRmLd + kRmC * 16 + (size_t)4 * 24 * kRmLd);
-        ICP_CUDA(cudaFuncSetAttribute(k_reconstruct_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_reconstruct_mma<<<grid, 128, smem, s>>>(m, C, d_theta, d_X);
+        if ((long long)grid.x * grid.y < 148) {   // latency-bound batch: three times the CTAs, a third of the work each
+            grid.x = (m.N + 31) / 32;
+            ICP_CUDA(cudaFuncSetAttribute(k_reconstruct_mma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_reconstruct_mma<32><<<grid, 128, smem, s>>>(m, C, d_theta, d_X);
+        } else {
+            ICP_CUDA(cudaFuncSetAttribute(k_reconstruct_mma<kRmV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_reconstruct_mma<kRmV><<<grid, 128, smem, s>>>(m, C, d_theta, d_X);
+        }
         ICP_CUDA(cudaGetLastError());
         return;
     }
