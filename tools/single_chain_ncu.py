@@ -21,3 +21,8 @@ C = int(os.environ.get("CHAINS", "1"))
 chain = core.Chain(model, tgt, comps, ev, max_chains=C)
 th0 = bench.init_thetas(m, C)
 chain.profile(th0, 6, seed=1)     # eager pass, kernel by kernel
+if os.environ.get("LOOKAHEAD"):      # a few look-ahead rounds as well (graph launches: ncu still lists every kernel)
+    import torch
+    chain.set_lookahead(int(os.environ["LOOKAHEAD"]))
+    t0 = torch.from_numpy(th0).to(torch.device("cuda", 0))
+    chain.run_device(C, 30, t0.data_ptr(), seed=1)
