@@ -685,6 +685,7 @@ extern "C" int32_t icp_proposal_create(icp_model m, icp_target t, const icp_prop
         }
         sync_stream(_ctx);
         m->refs++; t->refs++;
+        { std::lock_guard<std::mutex> g(m->props_mu); m->proposals.push_back(p); }
         *out = p;
         return ICP_OK;
     } catch (...) {
@@ -700,7 +701,16 @@ extern "C" int32_t icp_proposal_destroy(icp_proposal p) {
     try {
         CtxLock lock(_ctx);
         ICP_REQUIRE(p->refs == 0, "proposal is still used by a chain: destroy the chain first");
+        {
+            std::lock_guard<std::mutex> g(p->model->props_mu);
+            auto &v = p->model->proposals;
+            v.erase(std::remove(v.begin(), v.end(), p), v.end());
+        }
         drain_calls(p);
+        {
+            std::lock_guard<std::mutex> g(p->bg_mu);
+            if (p->bg_busy) { cudaEventSynchronize(p->bg_ev); p->bg_busy = false; }
+        }
         sync_stream(_ctx);
         p->model->refs--; p->target->refs--;
         delete p;
@@ -919,6 +929,129 @@ static void d2h(void *h, const void *d, size_t bytes, cudaStream_t s) {
 // scope; posteriors that are missing are computed in one batch on the call's stream, and a call that hits a slot another
 // call is still computing waits for it.
 namespace {
+// waits for the background posterior of q (bg_mu held) and publishes its cache slots
+void bg_finalize_locked(icp_proposal q) {
+    if (!q->bg_busy) return;
+    const cudaError_t e = cudaEventSynchronize(q->bg_ev);
+    {
+        std::lock_guard<std::mutex> g(q->cache_lock);
+        for (size_t i = 0; i < q->bg_slots.size(); i++) {
+            const int sl = q->bg_slots[i];
+            if (e != cudaSuccess) { q->cache_map.erase(q->bg_keys[i]); q->slot_key[sl].clear(); }   // waiters fail on the key check
+            q->slot_ready[sl] = 1;
+            q->slot_bg[sl] = 0;
+            q->slot_pin[sl]--;
+        }
+    }
+    if (e != cudaSuccess) cudaGetLastError();
+    q->bg_slots.clear();
+    q->bg_keys.clear();
+    q->bg_busy = false;
+    q->cache_cv.notify_all();
+}
+
+bool prefetch_enabled() {
+    static const bool on = !(getenv("ICPCUDA_PREFETCH") && getenv("ICPCUDA_PREFETCH")[0] == '0');
+    return on;
+}
+}  // namespace
+
+
+// starts the posteriors of C states on q in the background (see icp_proposal_s::bg_call); never blocks, never throws: a
+// prefetch that cannot start right away (another one in flight, cache being resized, no free slot) simply does not happen
+static void prefetch_posterior(icp_proposal q, int C, const double *theta_host) noexcept {
+    try {
+        if (!prefetch_enabled() || C > 64 || !proposal_self_contained(q)) return;
+        std::unique_lock<std::mutex> bg(q->bg_mu, std::try_to_lock);
+        if (!bg.owns_lock()) return;
+        if (q->bg_busy) {
+            if (cudaEventQuery(q->bg_ev) != cudaSuccess) { cudaGetLastError(); return; }
+            bg_finalize_locked(q);
+        }
+        std::shared_lock<std::shared_mutex> rd(q->cache_rw, std::try_to_lock);
+        if (!rd.owns_lock() || q->cache_slots < 32 + 6 * C) return;
+        icp_model m = q->model;
+        const int Lt = m->K + kTheta0;
+        std::vector<std::string> key(C);
+        for (int c = 0; c < C; c++) key[c].assign((const char *)(theta_host + (size_t)c * Lt), sizeof(double) * Lt);
+        std::vector<int> miss, slots;
+        {
+            std::lock_guard<std::mutex> g(q->cache_lock);
+            if (q->slot_bg.size() != (size_t)q->cache_slots) q->slot_bg.assign(q->cache_slots, 0);
+            std::unordered_map<std::string, int> distinct;
+            for (int c = 0; c < C; c++)
+                if (!q->cache_map.count(key[c])) distinct.emplace(key[c], c);
+            if (distinct.empty()) return;
+            int free_slots = 0;
+            for (int sl = 0; sl < q->cache_slots; sl++) free_slots += q->slot_pin[sl] == 0;
+            if (free_slots < (int)distinct.size() + 8) return;     // leave room for the calls that are about to come
+            for (auto &kv : distinct) {
+                while (q->slot_pin[q->cache_next] != 0) q->cache_next = (q->cache_next + 1) % q->cache_slots;
+                const int sl = q->cache_next;
+                q->cache_next = (q->cache_next + 1) % q->cache_slots;
+                if (!q->slot_key[sl].empty()) q->cache_map.erase(q->slot_key[sl]);
+                q->slot_key[sl] = kv.first;
+                q->cache_map[kv.first] = sl;
+                q->slot_ready[sl] = 0;
+                q->slot_bg[sl] = 1;
+                q->slot_pin[sl]++;
+                miss.push_back(kv.second);
+                slots.push_back(sl);
+            }
+        }
+        // from here on the slots are published as "in flight": on any failure they must be withdrawn
+        q->bg_slots = slots;
+        q->bg_keys.clear();
+        for (int c : miss) q->bg_keys.push_back(key[c]);
+        q->bg_busy = true;
+        bool started = false;
+        try {
+            if (!q->bg_call) {
+                q->bg_call.reset(new icp_proposal_s::Call());
+                ICP_CUDA(cudaStreamCreateWithFlags(&q->bg_call->stream, cudaStreamNonBlocking));
+            }
+            if (!q->bg_ev) ICP_CUDA(cudaEventCreateWithFlags(&q->bg_ev, cudaEventDisableTiming));
+            icp_proposal_s::Call &cs = *q->bg_call;
+            cudaStream_t s = cs.stream;
+            const int nm = (int)miss.size();
+            cs.h_aux.ensure(sizeof(double) * (size_t)nm * Lt + sizeof(int) * (size_t)nm);
+            double *hth = reinterpret_cast<double *>(cs.h_aux.p);
+            int *hslot = reinterpret_cast<int *>(hth + (size_t)nm * Lt);
+            for (int i = 0; i < nm; i++) {
+                memcpy(hth + (size_t)i * Lt, theta_host + (size_t)miss[i] * Lt, sizeof(double) * Lt);
+                hslot[i] = slots[i];
+            }
+            cs.s_theta2.ensure((size_t)nm * Lt);
+            cs.s_slot.ensure(nm);
+            run_call_graph(cs, call_graphs_enabled(), ((uint64_t)1 << 56) | (uint64_t)(uint32_t)nm, proposal_call_ptrs(q, cs), s, [&] {
+                ICP_CUDA(cudaMemcpyAsync(cs.s_theta2.p, hth, sizeof(double) * (size_t)nm * Lt, cudaMemcpyHostToDevice, s));
+                ICP_CUDA(cudaMemcpyAsync(cs.s_slot.p, hslot, sizeof(int) * (size_t)nm, cudaMemcpyHostToDevice, s));
+                posterior_pipeline(q, nm, cs.s_theta2.p, nullptr, cs.work, q->cache_L.p, q->cache_mu.p, cs.s_slot.p, s, nullptr,
+                                   q->prm.factor == ICP_FACTOR_SVD ? q->cache_W.p : nullptr);
+            });
+            ICP_CUDA(cudaEventRecord(q->bg_ev, s));
+            started = true;
+        } catch (...) {
+            cudaGetLastError();
+        }
+        if (!started) {      // withdraw: forget the keys, wake anyone who already waits for them
+            if (q->bg_call && q->bg_call->stream) cudaStreamSynchronize(q->bg_call->stream);
+            {
+                std::lock_guard<std::mutex> g(q->cache_lock);
+                for (size_t i = 0; i < q->bg_slots.size(); i++) {
+                    const int sl = q->bg_slots[i];
+                    q->cache_map.erase(q->bg_keys[i]); q->slot_key[sl].clear();
+                    q->slot_ready[sl] = 1; q->slot_bg[sl] = 0; q->slot_pin[sl]--;
+                }
+            }
+            q->bg_slots.clear(); q->bg_keys.clear(); q->bg_busy = false;
+            q->cache_cv.notify_all();
+        }
+    } catch (...) {
+    }
+}
+
+namespace {
 struct PosteriorLease {
     icp_proposal p;
     std::shared_lock<std::shared_mutex> rd;   // the slot arrays stay where they are
@@ -949,7 +1082,9 @@ PosteriorLease::PosteriorLease(icp_proposal p_, icp_proposal_s::Call &cs, int C,
         rd.unlock();
         {
             std::unique_lock<std::shared_mutex> wr(p->cache_rw);   // no call in flight holds a slot now
+            { std::lock_guard<std::mutex> bg(p->bg_mu); bg_finalize_locked(p); }   // nor the background computation
             if (p->cache_slots < want) {
+                p->slot_bg.assign(want, 0);
                 p->cache_map.clear();
                 p->slot_key.assign(want, std::string());
                 p->slot_pin.assign(want, 0);
@@ -1043,6 +1178,12 @@ PosteriorLease::PosteriorLease(icp_proposal p_, icp_proposal_s::Call &cs, int C,
         p->cache_cv.notify_all();
     }
     if (!wait_for.empty()) {
+        bool on_bg = false;
+        {
+            std::lock_guard<std::mutex> g(p->cache_lock);
+            for (int c : wait_for) on_bg = on_bg || (!p->slot_ready[slot[c]] && (size_t)slot[c] < p->slot_bg.size() && p->slot_bg[slot[c]]);
+        }
+        if (on_bg) { std::lock_guard<std::mutex> bg(p->bg_mu); bg_finalize_locked(p); }   // the speculative posterior: wait for its event
         std::unique_lock<std::mutex> g(p->cache_lock);
         for (int c : wait_for) {
             p->cache_cv.wait(g, [&] { return p->slot_ready[slot[c]] != 0; });
@@ -1061,6 +1202,7 @@ extern "C" int32_t icp_proposal_clear_cache(icp_proposal p) {
     try {
         ICP_REQUIRE(_ctx != nullptr, "null handle");
         std::unique_lock<std::shared_mutex> wr(p->cache_rw);   // waits for the calls in flight
+        { std::lock_guard<std::mutex> bg(p->bg_mu); bg_finalize_locked(p); }
         p->cache_map.clear();
         for (auto &k : p->slot_key) k.clear();
     ICP_API_END
@@ -1095,6 +1237,17 @@ extern "C" int32_t icp_propose(icp_proposal p, int32_t C, const double *theta, c
     });
     ICP_CUDA(cudaStreamSynchronize(s));
     memcpy(theta_out, cs.h_out.p, sizeof(double) * nth);
+    post.unpin();
+    post.rd.unlock();
+    {   // the host will ask every ICP component for the transition back from theta': start those posteriors now
+        std::vector<icp_proposal> siblings;
+        {
+            std::lock_guard<std::mutex> g(m->props_mu);
+            for (icp_proposal q : m->proposals)
+                if (q->target == p->target) siblings.push_back(q);
+        }
+        for (icp_proposal q : siblings) prefetch_posterior(q, C, theta_out);
+    }
     ICP_API_END
 }
 

@@ -343,6 +343,8 @@ struct icp_ctx_s {
 };
 
 struct icp_model_s {
+    std::mutex props_mu;
+    std::vector<icp_proposal> proposals;   // live proposals built on this model (siblings for the speculative posterior)
     icp_ctx ctx = nullptr;
     int refs = 0;                     // proposals / evaluators / chains built on this handle (destroy refuses while > 0)
     int N = 0, T = 0, K = 0, Kp = 0;  // Kp = K padded to a multiple of 8
@@ -529,6 +531,19 @@ struct icp_proposal_s {
     std::mutex pool_mu;
     std::vector<std::unique_ptr<Call>> calls;
     unsigned next_call = 0;
+    // Speculative posterior of the state a proposal just produced (api.cu: prefetch_posterior): a Metropolis-Hastings host asks
+    // every ICP component for logTransitionProbability(theta', theta) right after propose(theta) returned theta', which needs
+    // the posterior AT theta'. icp_propose therefore starts that posterior on every self-contained proposal of the same model
+    // and target in the background (own call slot, no synchronisation) - a pure cache fill: the later call finds the entry "in
+    // flight" and waits for the rest of it instead of starting it. One computation in flight per proposal.
+    std::mutex bg_mu;                 // guards the fields below; lock order: cache_rw -> bg_mu -> cache_lock
+    std::unique_ptr<Call> bg_call;
+    cudaEvent_t bg_ev = nullptr;
+    bool bg_busy = false;
+    std::vector<int> bg_slots;        // cache slots the computation in flight fills (pinned, not ready)
+    std::vector<std::string> bg_keys;
+    std::vector<char> slot_bg;        // [cache_slots] 1: being filled by the background computation
+    ~icp_proposal_s() { if (bg_ev) cudaEventDestroy(bg_ev); }
 };
 
 namespace icp {
