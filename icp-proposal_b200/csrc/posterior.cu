@@ -968,13 +968,16 @@ __device__ __forceinline__ int pk_at(int i, int j) {   // element (i, j) of a st
 }
 
 constexpr int kCh3Threads = 128;
-__global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, const double *__restrict__ Mp,
+// NT threads per matrix: 128 (four matrices per SM) for full batches; 256 when every matrix of the launch is resident anyway
+// (a few chains are latency-bound: the load, store and column-update phases get twice the threads; the arithmetic of every
+// element - and for Kp <= 128 the association of the final quadratic form - does not depend on NT)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 128 ? 4 : 2) k_cholesky_packed(int Kp, const double *__restrict__ Mp,
                                                                     const double *__restrict__ bvec, double *__restrict__ M_out,
                                                                     double *__restrict__ L, double *__restrict__ mu,
                                                                     const int *__restrict__ out_slot, int *__restrict__ status,
                                                                     QuadArgs qa) {
     extern __shared__ __align__(16) double sp[];
-    constexpr int NT = kCh3Threads;
     const int NB = Kp >> 3, ntri = NB * (NB + 1) / 2;
     double *A = sp;                  // [ntri][64]
     double *yv = A + ntri * 64;      // [Kp] b, then y = L^-1 b
@@ -1214,6 +1217,20 @@ __global__ void __launch_bounds__(kCh3Threads, 4) k_cholesky_packed(int Kp, cons
         }
     }
     ICP_FT(if (tid == 0 && c < 8192) g_ft[kFtStride * c + 11] = clock64() - fts;)
+}
+
+static void run_cholesky_packed(int C, int Kp, size_t smem_c, const double *d_Mp, const double *d_b, double *d_M, double *d_L, double *d_mu,
+                                const int *d_out_slot, int *d_status, const QuadArgs *qa, cudaStream_t s) {
+    const QuadArgs q = qa ? *qa : QuadArgs{};
+    // the two ICP posteriors of a step factorise concurrently: up to 148 chains all their matrices are resident at two per SM
+    // (measured: 148 chains 605 k -> 646 k samples/s, one chain's round 0.179 -> 0.175 ms; at 296 chains 128 threads win)
+    if (C <= 148 && Kp <= 128) {
+        ICP_CUDA(cudaFuncSetAttribute(k_cholesky_packed<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        k_cholesky_packed<256><<<C, 256, smem_c, s>>>(Kp, d_Mp, d_b, d_M, d_L, d_mu, d_out_slot, d_status, q);
+    } else {
+        ICP_CUDA(cudaFuncSetAttribute(k_cholesky_packed<kCh3Threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        k_cholesky_packed<kCh3Threads><<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, d_M, d_L, d_mu, d_out_slot, d_status, q);
+    }
 }
 
 // accumulator block (bi, bj) -> shared-memory matrix of the factorisation (+ I, + Gs / sd_t^2 on the fast path)
@@ -1659,8 +1676,7 @@ static void launch_fused(const ModelDev &m, int C, const ObsDev &o, double *d_M,
         }
         ProfScope _ps(ST_CHOLESKY, s);
         size_t smem_c = sizeof(double) * ((size_t)total * 64 + 4 * Kp);
-        ICP_CUDA(cudaFuncSetAttribute(k_cholesky_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-        k_cholesky_packed<<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, d_M, d_L, d_mu, d_out_slot, d_status, qa ? *qa : QuadArgs{});
+        run_cholesky_packed(C, Kp, smem_c, d_Mp, d_b, d_M, d_L, d_mu, d_out_slot, d_status, qa, s);
         if (quad_done) *quad_done = qa != nullptr;
         return;
     }
@@ -1680,8 +1696,7 @@ void launch_cholesky_packed(int C, int Kp, const double *d_Mp, const double *d_b
     ProfScope _ps(ST_CHOLESKY, s);
     const int NB = Kp / 8, total = NB * (NB + 1) / 2;
     size_t smem_c = sizeof(double) * ((size_t)total * 64 + 4 * Kp);
-    ICP_CUDA(cudaFuncSetAttribute(k_cholesky_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    k_cholesky_packed<<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, d_M_or_null, d_L, d_mu, d_out_slot, d_status, qa ? *qa : QuadArgs{});
+    run_cholesky_packed(C, Kp, smem_c, d_Mp, d_b, d_M_or_null, d_L, d_mu, d_out_slot, d_status, qa, s);
     ICP_CUDA(cudaGetLastError());
 }
 
@@ -1731,8 +1746,7 @@ void launch_cholesky_solve(int C, int K, int Kp, const double *d_M, const double
         ICP_REQUIRE(d_Mp != nullptr && smem_c <= 227 * 1024 - 64, "rank too large for the shared-memory Cholesky (K <= 224)");
         k_pack_lower<<<C, 128, 0, s>>>(Kp, d_M, d_Mp);
         ICP_CUDA(cudaGetLastError());
-        ICP_CUDA(cudaFuncSetAttribute(k_cholesky_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-        k_cholesky_packed<<<C, kCh3Threads, smem_c, s>>>(Kp, d_Mp, d_b, nullptr, d_L, d_mu, d_out_slot, d_status, qa ? *qa : QuadArgs{});
+        run_cholesky_packed(C, Kp, smem_c, d_Mp, d_b, nullptr, d_L, d_mu, d_out_slot, d_status, qa, s);
         ICP_CUDA(cudaGetLastError());
         if (quad_done) *quad_done = qa != nullptr;
         return;
