@@ -19,7 +19,12 @@
  *  - "C" is the number of chains (parameter vectors) in a batched call.
  *  - There is no CPU fallback: every compute entry point runs CUDA kernels on the context's device
  *    and fails with ICP_ERR_CUDA when that is impossible.
- *  - Handles are safe to use from several host threads; calls on one handle serialise.
+ *  - Handles are safe to use from several host threads. The per-call entries of a proposal or evaluator (icp_propose,
+ *    icp_log_transition, icp_posterior, icp_eval_log_value) run concurrently, also on ONE shared handle - the reference shares its
+ *    proposal mixture and evaluator between ten fitting threads (apps/femur/RunMHRandomInitComparison.scala:59-86): every call
+ *    leases a call slot of the handle (own stream and scratch, at most 16 in flight), the posterior cache of a proposal is shared.
+ *    Handles whose pipeline refits scratch of the model (evaluators that measure target -> model distances) and every other entry
+ *    point serialise on the context.
  */
 #ifndef ICPCUDA_H
 #define ICPCUDA_H
