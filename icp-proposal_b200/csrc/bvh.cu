@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kNearestThreads, 7) k_nearest(int n, const int
                                                  const int *__restrict__ perm, int *__restrict__ seed_slot,
                                                  int *__restrict__ out_prim, int *__restrict__ out_feat,
                                                  double *__restrict__ out_cp, double *__restrict__ out_d2,
-                                                 unsigned long long *__restrict__ chain_max, int n_blk, int blk_stride) {
+                                                 unsigned long long *__restrict__ chain_max, int n_blk, int blk_stride, int lpw) {
     __shared__ int s_stack_n[kStackShared][kNearestThreads];
     __shared__ float s_stack_d[kStackShared][kNearestThreads];
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -352,7 +352,10 @@ __global__ void __launch_bounds__(kNearestThreads, 7) k_nearest(int n, const int
         if (i >= nq) { live = false; i = nq - 1; }
         g = (long long)c * nq + i;
     } else {
-        live = g < nq * C;
+        // lpw < 32 (small batches): only the first lpw lanes of a warp take a query. A warp runs as many rounds as its slowest
+        // lane needs; with few queries in all there are SMs to spare, and eight queries per warp finish sooner than thirty-two
+        if (lpw < 32) g = (g >> 5) * lpw + (threadIdx.x & 31);
+        live = (lpw >= 32 || (int)(threadIdx.x & 31) < lpw) && g < nq * C;
         if (!live) g = nq * C - 1;   // idle lanes stay in the warp-synchronous loop, write nothing
         c = (int)(g / nq);
         i = g % nq;
@@ -467,11 +470,15 @@ void launch_nearest(const NearestArgs &a, cudaStream_t s) {
         while (gcd(blk_stride, n_blk) != 1) blk_stride++;
         blocks = (unsigned)(((long long)n_blk * a.C * 32 + threads - 1) / threads);
     }
+    // a small batch is a chain of dependent latencies: eight queries per warp (see k_nearest) while the grid still fits one wave
+    static const int lpw_small = getenv("ICPCUDA_LPW") ? atoi(getenv("ICPCUDA_LPW")) : 8;   // (experiments: 4 / 8 / 16)
+    const int lpw = (!a.chain_max && total <= 16384 && lpw_small >= 1 && lpw_small < 32) ? lpw_small : 32;
+    if (lpw < 32) blocks = (unsigned)((((total + lpw - 1) / lpw) * 32 + threads - 1) / threads);
 #define ICP_LAUNCH_NEAREST(P, D, H)                                                                                  \
     k_nearest<P, D, H><<<blocks, threads, 0, s>>>(b.n, b.children.p, (D) ? b.nodes.p : b.packed.p, b.prim.p, a.prim_data, a.X, a.tris, \
                                                a.N, a.C, (long long)a.nq, a.q, a.q_per_chain, a.Xq, a.q_ids,     \
                                                a.Nq, a.perm, a.seed_slot, a.out_prim, a.out_feat, a.out_cp, a.out_d2, \
-                                               a.chain_max, n_blk, blk_stride)
+                                               a.chain_max, n_blk, blk_stride, lpw)
     if (a.chain_max) {
         ICP_REQUIRE(b.prim_kind == 0 && !a.out_cp && !a.out_prim && !a.out_feat, "launch_nearest: chain_max is for distance-only triangle queries");
         if (dynamic) ICP_LAUNCH_NEAREST(0, true, true); else ICP_LAUNCH_NEAREST(0, false, true);
@@ -598,12 +605,14 @@ __global__ void __launch_bounds__(128) k_nearest_vertex_brute(int N, int C, cons
 // traversal order and tie rule as bvh_refit + k_nearest<points, dynamic>, so the results are identical; it replaces a
 // 184 MB write + read of per-chain node boxes (C = 2368) by 39 KB of shared memory per CTA.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_nearest_vertex_tree(int n, const int *__restrict__ prim, const int2 *__restrict__ children,
-                                                             const int *__restrict__ order, const int *__restrict__ level_off,
-                                                             int n_levels, const double *__restrict__ X, int N, float slack,
-                                                             long long nq, const double *__restrict__ q, int q_per_chain,
-                                                             int *__restrict__ seed_slot, int *__restrict__ out_prim,
-                                                             double *__restrict__ out_d2) {
+// lpw: queries per warp (32; 8 with 1024 threads per chain for small batches, where the SM has nothing else to do: the refit
+// gets four times the threads and a warp waits for the slowest of eight walks instead of thirty-two)
+__global__ void __launch_bounds__(1024) k_nearest_vertex_tree(int n, const int *__restrict__ prim, const int2 *__restrict__ children,
+                                                              const int *__restrict__ order, const int *__restrict__ level_off,
+                                                              int n_levels, const double *__restrict__ X, int N, float slack,
+                                                              long long nq, const double *__restrict__ q, int q_per_chain,
+                                                              int *__restrict__ seed_slot, int *__restrict__ out_prim,
+                                                              double *__restrict__ out_d2, int lpw) {
     extern __shared__ float sbox[];                                // [n - 1][6] boxes of the internal nodes (lo, hi)
     const int c = blockIdx.x;
     const double *sx = X + (size_t)c * N * 3;                      // the chain's vertices stay in global memory (L1 / L2): each
@@ -634,7 +643,8 @@ __global__ void __launch_bounds__(256) k_nearest_vertex_tree(int n, const int *_
         }
         __syncthreads();
     }
-    for (long long i = threadIdx.x; i < nq; i += blockDim.x) {
+    const int q_lane = threadIdx.x & 31, q_warps = blockDim.x >> 5;
+    for (long long i = (long long)(threadIdx.x >> 5) * lpw + q_lane; q_lane < lpw && i < nq; i += (long long)q_warps * lpw) {
         const long long g = (long long)c * nq + i;
         const double *src = q + ((q_per_chain ? (size_t)c * nq : 0) + i) * 3;
         const double qx = src[0], qy = src[1], qz = src[2];
@@ -709,8 +719,10 @@ bool launch_nearest_vertex_tree(const Bvh &b, int N, int C, const double *d_X, i
     if (!nearest_vertex_tree_fits(b, N) || C <= 0 || nq <= 0) return false;
     ProfScope _ps(ST_NEAREST_DYNAMIC, s);
     ICP_CUDA(cudaFuncSetAttribute(k_nearest_vertex_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_nearest_vertex_tree<<<C, 256, smem, s>>>(b.n, b.prim.p, b.children.p, b.order.p, b.level_off.p, b.n_levels, d_X, N, b.slack,
-                                               (long long)nq, d_q, q_per_chain, d_seed, d_prim, d_d2);
+    static const int lpw_small = getenv("ICPCUDA_LPW") ? atoi(getenv("ICPCUDA_LPW")) : 8;   // (experiments: 4 / 8 / 16)
+    const bool small = C <= 64 && lpw_small >= 1 && lpw_small < 32;   // the SMs are mostly idle: 1024 threads per chain, eight queries per warp
+    k_nearest_vertex_tree<<<C, small ? 1024 : 256, smem, s>>>(b.n, b.prim.p, b.children.p, b.order.p, b.level_off.p, b.n_levels, d_X, N,
+                                                              b.slack, (long long)nq, d_q, q_per_chain, d_seed, d_prim, d_d2, small ? lpw_small : 32);
     ICP_CUDA(cudaGetLastError());
     return true;
 }
