@@ -299,11 +299,18 @@ __global__ void __launch_bounds__(256) k_chain_propose(ChainParams P, ModelDev m
     }
     __syncthreads();
     // forward forms: d = (alpha + (alpha' - alpha) / step_i) - mu_cur,i   (NonRigidIcpProposal.scala:79, :82-83)
-    for (int i = 0; i < P.n_comp; i++) {
+    // The selected component goes first when its factor is still staged: the other components stage theirs over it. (Taking
+    // the components in index order formed the selected component's form from an overwritten factor whenever an ICP
+    // component with a smaller index came before it - invisible next to a random-walk component, whose density dominates
+    // the mixture's at these step sizes, and wrong in an ICP-only mixture: tools/check_forward_forms.py.)
+    for (int pass = 0; pass < P.n_comp + 1; pass++) {
+        const int i = pass == 0 ? s_ci : pass - 1;
+        if (pass == 0 && !staged) continue;
+        if (pass > 0 && staged && i == s_ci) continue;
         const CompDev ci = P.comp[i];
         if (ci.kind != ICP_PROP_ICP) continue;
         const size_t pslot = (size_t)ci.icp_index * 2 * C + st.slot_cur[c];
-        if (staged && i == s_ci) {
+        if (pass == 0) {
             for (int k = threadIdx.x; k < Kp; k += blockDim.x) sL[(k * (k + 1)) / 2 + k] = sdg[k];   // the true diagonal again
         } else {
             stage_packed_L(st.L + pslot * Kp * Kp, Kp, sL);

@@ -373,6 +373,57 @@ def test_chain_matches_oracle_chain(ctx, twin31, evaluator):
     chain.close(); ev.close(); model.close(); tgt.close()
 
 
+def test_chain_icp_only_mixture_matches_oracle_chain(ctx, twin31):
+    """A mixture of the two ICP proposals alone (MixedProposalDistributions.mixedProposalICP without the random walk): here the ICP
+    components' own transition densities decide the acceptance - next to a random-walk component its density dominates the
+    mixture's log-sum-exp at these step sizes and hides them. Regression test for the forward form of the selected component,
+    which was formed from an overwritten factor whenever an ICP component with a smaller index came first."""
+    m = twin31
+    K = 31
+    model, tgt = _dev(ctx, m)
+    om, ot = _orc(m)
+    rng = np.random.default_rng(77)
+    ids, eids = np.arange(62), np.arange(124)
+    tp = m["target"][::26][:62]
+    comps_d = _mixture(model, tgt, om, ot, K, ids, tp, True)[:2]
+    comps_o = _mixture(model, tgt, om, ot, K, ids, tp, False)[:2]
+    ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, 0, True, 0.0, 2.0, 0.0, eids, tp)
+    C, n = 2, 120
+    th0 = random_theta(m, rng, C, alpha_sd=0.5)
+    u_comp, u_acc, z = rng.random((n, C)), rng.random((n, C)), rng.normal(size=(n, C, K))
+    chain = core.Chain(model, tgt, comps_d, ev, max_chains=C)
+    got = chain.run(th0, n, u_comp=u_comp, z=z, u_acc=u_acc)
+    for c in range(C):
+        want = orc.chain_run(om, ot, comps_o, True, orc.EVAL_INDEPENDENT, 0, (0.0, 2.0), eids, tp, th0[c], n, u_comp[:, c], z[:, c],
+                             u_acc[:, c], closed_form=True)
+        assert np.array_equal(got["component"][:, c], want["comp"])
+        assert len(set(want["comp"])) == 2
+        assert np.array_equal(got["accepted"][:, c], want["accepted"])
+        np.testing.assert_allclose(got["theta"][:, c], want["theta"], rtol=0, atol=1e-7)
+        assert want["n_accepted"] >= 1
+    # the same decisions from the per-call entry points (an independent code path for the transition densities): before the fix
+    # 64 of 160 steps proposed by the second component were decided differently in this set-up (tools/check_forward_forms.py)
+    p0, p1 = comps_d[0]["proposal"], comps_d[1]["proposal"]
+    cur = th0[:1].copy()
+    vcur = ev.log_value(cur)[0, 0]
+    lse = lambda a, b: max(a, b) + np.log(0.5 * np.exp(a - max(a, b)) + 0.5 * np.exp(b - max(a, b)))
+    n_second = 0
+    for s in range(n):
+        ci = int(got["component"][s, 0])
+        prop = (p0 if ci == 0 else p1).propose(cur, z[s, :1])
+        vprop = ev.log_value(prop)[0, 0]
+        lf = lse(p0.log_transition(cur, prop)[0], p1.log_transition(cur, prop)[0])
+        lb = lse(p0.log_transition(prop, cur)[0], p1.log_transition(prop, cur)[0])
+        a = vprop - vcur - (lf - lb)
+        if abs(np.log(u_acc[s, 0]) - a) > 1e-6:        # (not within rounding of the threshold)
+            assert bool(got["accepted"][s, 0]) == bool(a > 0 or u_acc[s, 0] < np.exp(a)), f"step {s}, component {ci}"
+        n_second += ci == 1
+        if got["accepted"][s, 0]:
+            cur, vcur = got["theta"][s:s + 1, 0].copy(), got["values"][s, 0, 0]
+    assert n_second > 20
+    chain.close(); ev.close(); model.close(); tgt.close()
+
+
 def test_chain_with_pose_proposals(ctx, open_twin):
     """BFM-style mixture: ICP + random walk + axis rotation/translation proposals, collective evaluator."""
     m = open_twin
