@@ -10,15 +10,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from icp_proposal_b200 import _lib, core, synth  # noqa: E402
 
-m = synth.femur_twin(rank=31)
+K = int(os.environ.get("RANK", "31"))
+m = synth.femur_twin(rank=K)
 tv, tc, _ = synth.synthetic_target(m)
-K = 31
 ctx = core.Context(0)
 model = core.Model(ctx, m["ref"], m["cells"], m["basis"], m["variance"])
 tgt = core.Target(ctx, tv, tc)
-ids, eids, tp = np.arange(62), np.arange(124), tv[::26][:62]
-p0 = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.TARGET_SAMPLING, True, ids, tp)
-p1 = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.MODEL_SAMPLING, True, ids, tp)
+ids, eids, tp = np.arange(2 * K), np.arange(4 * K), tv[:: max(1, len(tv) // (2 * K))][:2 * K]
+ru = _lib.RANK_UPDATE_INT8 if os.environ.get("RU") == "int8" else _lib.RANK_UPDATE_FP64
+fac = _lib.FACTOR_SVD if os.environ.get("FACTOR") == "svd" else _lib.FACTOR_CHOLESKY
+p0 = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.TARGET_SAMPLING, True, ids, tp, factor=fac, rank_update=ru)
+p1 = core.IcpProposal(model, tgt, 0.1, 10.0, 5.0, _lib.MODEL_SAMPLING, True, ids, tp, factor=fac, rank_update=ru)
 # ICP_ONLY=1: no random-walk component (its density dominates the mixture's at these step sizes and hides the ICP terms)
 icp_only = os.environ.get("ICP_ONLY", "1") == "1"
 w = np.array([0.5, 0.5, 0.0]) if icp_only else np.array([0.45, 0.45, 0.1]); sd = 0.1
@@ -27,7 +29,7 @@ if not icp_only:
     comps.append(dict(kind=_lib.PROP_RANDOM_SHAPE, weight=w[2], sd=sd))
 ev = core.Evaluator(model, tgt, _lib.EVAL_INDEPENDENT, _lib.MODEL_TO_TARGET, True, 0.0, 2.0, 0.0, eids, tp)
 chain = core.Chain(model, tgt, comps, ev, max_chains=1)
-chain.set_lookahead(0)
+chain.set_lookahead(int(os.environ.get("LOOKAHEAD", "0")))
 rng = np.random.default_rng(3)
 n = int(os.environ.get("STEPS", "300"))
 th0 = model.theta(rng.normal(0, 0.5, K))[None]
